@@ -1,0 +1,148 @@
+/* kosmosx_b200.h — C ABI of libkosmosx_sm100.so
+ *
+ * The drop-in boundary of the B200-native Kosmos-X forward path.  The reference
+ * (/root/reference/kosmosx/model.py) is a Python nn.Module; it has no FFI of its own, so
+ * the entry points below are the operators its forward dispatches to through PyTorch
+ * (F.linear, softmax/bmm attention, layer_norm, embedding/cat splice ...), re-cut at the
+ * fusion boundaries of the sm_100a kernels.  Each declaration cites the reference call
+ * site (file:line under /root/reference, or [HF] = transformers/models/clip/modeling_clip.py,
+ * or SURVEY.md Appendix A for the un-vendored torchscale / flamingo_pytorch semantics).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - all kernels are enqueued on `stream`; nothing synchronises, nothing allocates;
+ *   - return value: KX_OK (0) or a negative KX_ERR_* code; kx_last_error() gives the text;
+ *   - bf16 = __nv_bfloat16 storage (uint16_t), row-major, `ld*` = row pitch in ELEMENTS.
+ */
+#ifndef KOSMOSX_B200_H
+#define KOSMOSX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
+
+enum {
+    KX_OK = 0,
+    KX_ERR_ARG = -1,       /* bad argument (shape, alignment, null pointer) */
+    KX_ERR_NO_DEVICE = -2, /* no CUDA device / driver: there is NO CPU fallback */
+    KX_ERR_TMAP = -3,      /* cuTensorMapEncodeTiled rejected a tensor */
+    KX_ERR_LAUNCH = -4     /* kernel launch failed */
+};
+
+enum { KX_ACT_NONE = 0, KX_ACT_GELU = 1 /* erf */, KX_ACT_QUICK_GELU = 2 /* x*sigmoid(1.702x) */ };
+enum { KX_EPI_GENERIC = 0, KX_EPI_QKV_XPOS = 1 };
+
+/* ---- library ---------------------------------------------------------------------- */
+const char* kx_last_error(void);      /* thread-local text of the last failure */
+int kx_abi_version(void);             /* bumped on any signature change */
+int kx_device_check(void);            /* KX_OK iff device 0.. current is sm_100 (B200) */
+unsigned long long kx_launch_count(void);   /* kernels launched by this library so far */
+
+/* ---- Linear layers ----------------------------------------------------------------- *
+ * out = epilogue(A[M,K] . W[N,K]^T): tcgen05/TMEM GEMM with fused epilogue.
+ * Replaces: HF CLIP q/k/v/out_proj, fc1/fc2 ([HF]:295-298,344-351) and the conv patch
+ * embedding ([HF]:148-154,209, as GEMM over im2col rows); flamingo to_q/to_kv/to_out/FF
+ * (SURVEY A.2); image_proj (model.py:205-206,232); torchscale q/k/v/out_proj, fc1, fc2
+ *  and output_projection (model.py:166).
+ *   epilogue order: +bias -> [xPos rotation of q,k column pairs] -> activation
+ *                   -> +add_tab[(m % grp_rows) + add_off] -> +res[out_row] -> store(out_row)
+ *   out_row = grp_rows ? (m / grp_rows) * grp_stride + grp_off + m % grp_rows : m
+ */
+typedef struct kx_gemm_args {
+    int M, N, K;
+    const float* bias;            /* [N] fp32 or NULL */
+    const float* res;             /* fp32 [rows, ld_res] residual (may alias out) or NULL */
+    long long ld_res;
+    void* out;                    /* bf16 or fp32 [rows, ld_out] */
+    long long ld_out;
+    int out_f32;                  /* 1: fp32 output, 0: bf16 output */
+    int act;                      /* KX_ACT_* */
+    int epi;                      /* KX_EPI_* */
+    int grp_rows, grp_stride, grp_off;    /* output row scatter (0 = identity) */
+    const float* add_tab;         /* fp32 [*, ld_add] periodic additive table or NULL */
+    int add_off;
+    long long ld_add;
+    const float *xq_cos, *xq_sin, *xk_cos, *xk_sin;  /* KX_EPI_QKV_XPOS: [seq_len,32] fp32 (kx_xpos_tables) */
+    int seq_len;                  /* position of row m is m % seq_len */
+    int d_model;                  /* N == 3*d_model: q | k | v column blocks */
+    int cta_group;                /* 0 = auto, 1 = single CTA tiles, 2 = cta_group::2 pairs */
+    int block_n;                  /* 0 = auto, 128 or 256 */
+    int max_ctas;                 /* 0 = all SMs */
+} kx_gemm_args;
+
+int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const kx_gemm_args* args,
+                 kx_stream_t stream);
+
+/* ---- attention -------------------------------------------------------------------- *
+ * Flash attention forward, head_dim 64, tcgen05 (S = Q.K^T and P.V on tensor cores, online
+ * softmax in fp32).  q/k/v are column blocks of token-major matrices: row (b*T + t),
+ * column (head*64 + d) relative to the given base pointer.
+ * Replaces: torchscale MultiheadAttention core — bmm, nan_to_num, +triu(-inf) mask,
+ * softmax(fp32), bmm, head merge (decoder, causal=1) — and HF CLIPAttention's
+ * eager/sdpa core ([HF]:318-331; ViT, causal=0).  `scale` multiplies q.k^T (64^-0.5).
+ */
+int kx_attn_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
+                int batch, int heads, int seq_len, int causal, float scale, kx_stream_t stream);
+
+/* Perceiver cross-attention core (flamingo_pytorch PerceiverAttention; reached from
+ * model.py:231): per (batch, head) softmax(q.k^T * scale - rowmax) . v with n_q latent queries and
+ * n_kv = media + latent keys, head_dim 64.  q: [batch*n_q, ld_q], kv: [batch*n_kv, ld_kv] with
+ * k at column head*64 and v at column v_col_off + head*64.  out: bf16 [batch*n_q, ld_out].
+ */
+int kx_perceiver_xattn_fwd(const void* q, long long ld_q, const void* kv, long long ld_kv, int v_col_off, void* out,
+                           long long ld_out, int batch, int heads, int n_q, int n_kv, float scale,
+                           kx_stream_t stream);
+
+/* ---- LayerNorm -------------------------------------------------------------------- *
+ * y = (x + pre_add) normalised over the last dim, * gamma + beta, written as bf16 (GEMM
+ * operand) at out_row (same scatter rule as kx_gemm_args).  x is fp32 (residual stream)
+ * or bf16.  eps 1e-5 everywhere in the reference.  Replaces nn.LayerNorm at: [HF]:359,361,
+ * 677 (ViT), flamingo norm_media/norm_latents/FF norm/final norm (A.2), torchscale
+ * self_attn_layer_norm, inner_attn_ln, final_layer_norm, ffn_layernorm, decoder.layer_norm
+ * (A.4).  pre_add ([N] fp32 or NULL) fuses `x + media_pos_emb[:1]` of the perceiver (A.2).
+ */
+int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, const float* gamma,
+                     const float* beta, float eps, void* out_bf16, long long ld_out, int rows, int n, int grp_rows,
+                     int grp_stride, int grp_off, kx_stream_t stream);
+
+/* ---- embedding / splice ----------------------------------------------------------- *
+ * x0[b, t, :] for every NON-image row of the spliced sequence (image rows are written by the
+ * image_proj GEMM epilogue): token embedding gather + learned position (index t + 2).
+ * Row t of the spliced sequence holds text token t (t < img_start), image feature
+ * t - img_start (img_start <= t < img_start + n_img), or text token t - n_img.
+ * Replaces Decoder.forward_embedding x2 + torch.cat of model.py:238-244.
+ * For KosmosLanguage (model.py:310-320) pass n_img = 0.
+ * Token ids outside [0, vocab) set *err_flag (device int, may be NULL) instead of faulting.
+ */
+int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
+                        const float* pos_table, int pos_rows, int dim, int img_start, int n_img, float* x0,
+                        int* err_flag, kx_stream_t stream);
+
+/* CLIP patch embedding front end ([HF]:202-218): im2col of (B,3,H,W) pixels (fp32) into bf16
+ * rows [B*gh*gw, k_pad] (k = c*p*p + dy*p + dx, zero padded to k_pad), and the CLS rows
+ * x[b, 0, :] = class_embedding + pos[0] written into the fp32 token buffer x [B, 1+gh*gw, dim].
+ */
+int kx_im2col_patches(const float* pixels, int batch, int image, int patch, void* patches_bf16, int k_pad,
+                      const float* class_embedding, const float* pos_table, float* x, int dim, kx_stream_t stream);
+
+/* xPos tables (torchscale XPOS): for t in [0,T), j in [0,32):
+ *   S = scale[j] ** ((t + min_pos) / scale_base), theta = t * inv_freq[j]
+ *   q_cos = cos*S, q_sin = sin*S, k_cos = cos/S, k_sin = sin/S     (each [T,32] fp32)
+ */
+int kx_xpos_tables(const float* scale, const float* inv_freq, int T, int min_pos, float scale_base, float* q_cos,
+                   float* q_sin, float* k_cos, float* k_sin, kx_stream_t stream);
+
+/* fp32 -> bf16 conversion of a parameter tensor (weight staging), and broadcast of the
+ * perceiver latents over the batch (A.2: latents.expand). */
+int kx_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, kx_stream_t stream);
+int kx_broadcast_rows(const float* src, float* dst, long long row_elems, int copies, kx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOSMOSX_B200_H */

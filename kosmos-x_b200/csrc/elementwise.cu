@@ -1,0 +1,300 @@
+// HBM-bound glue kernels of the Kosmos-X path: LayerNorm (-> bf16 GEMM operand), token
+// embedding + splice + positions, CLIP patch im2col, xPos tables, parameter staging.
+// All are coalesced, 16-byte vectorised, one pass over their input.
+#include "kx_internal.h"
+#include "ptx.cuh"
+
+namespace kx {
+
+// ----------------------------------------------------------------------------- LayerNorm
+// Row statistics exactly as torch.nn.LayerNorm: mean, then biased variance of (x - mean), eps
+// inside the sqrt; fp32 throughout; the row lives in registers between the passes.
+template <bool IN_BF16, int TPR, int MAX_VEC>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __restrict__ pre_add,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 __nv_bfloat16* __restrict__ out, long long ld_out, int rows, int n, int grp_rows, int grp_stride,
+                 int grp_off) {
+    constexpr int ROWS_PER_BLOCK = 256 / TPR;
+    __shared__ float red[2][8];
+    const int tr = threadIdx.x % TPR;
+    const int row = blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / TPR;
+    const bool active = row < rows;          // inactive threads still take part in the reductions
+    const int nvec = n >> 3;
+
+    float v[MAX_VEC][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+        const int vi = tr + i * TPR;
+        if (active && vi < nvec) {
+            if constexpr (IN_BF16) {
+                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + row * ld_x + vi * 8);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 f = __bfloat1622float2(h[u]);
+                    v[i][2 * u] = f.x; v[i][2 * u + 1] = f.y;
+                }
+            } else {
+                const float* px = reinterpret_cast<const float*>(x) + row * ld_x + vi * 8;
+                const float4 a = *reinterpret_cast<const float4*>(px);
+                const float4 b = *reinterpret_cast<const float4*>(px + 4);
+                v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+                v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+            }
+            if (pre_add != nullptr) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(pre_add + vi * 8));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(pre_add + vi * 8 + 4));
+                v[i][0] += a.x; v[i][1] += a.y; v[i][2] += a.z; v[i][3] += a.w;
+                v[i][4] += b.x; v[i][5] += b.y; v[i][6] += b.z; v[i][7] += b.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sum += v[i][u];
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[i][u] = 0.f;
+        }
+    }
+    auto row_reduce = [&](float val, int which) -> float {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if constexpr (TPR > 32) {
+            if ((threadIdx.x & 31) == 0) red[which][threadIdx.x >> 5] = val;
+            __syncthreads();
+            val = 0.f;
+#pragma unroll
+            for (int w = 0; w < TPR / 32; ++w) val += red[which][w];
+        }
+        return val;
+    };
+    const float mean = row_reduce(sum, 0) / static_cast<float>(n);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+        const int vi = tr + i * TPR;
+        if (active && vi < nvec) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const float d = v[i][u] - mean; sq += d * d; }
+        }
+    }
+    const float var = row_reduce(sq, 1) / static_cast<float>(n);
+    const float rstd = 1.0f / sqrtf(var + eps);
+    if (!active) return;
+
+    long long orow = row;
+    if (grp_rows > 0) {
+        const int g = row / grp_rows;
+        orow = static_cast<long long>(g) * grp_stride + grp_off + (row - g * grp_rows);
+    }
+#pragma unroll
+    for (int i = 0; i < MAX_VEC; ++i) {
+        const int vi = tr + i * TPR;
+        if (vi < nvec) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) y[u] = (v[i][u] - mean) * rstd * g[u] + bb[u];
+            uint4 q;
+            q.x = pack_bf16(y[0], y[1]); q.y = pack_bf16(y[2], y[3]);
+            q.z = pack_bf16(y[4], y[5]); q.w = pack_bf16(y[6], y[7]);
+            *reinterpret_cast<uint4*>(out + orow * ld_out + vi * 8) = q;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- embedding + splice + positions
+__global__ void __launch_bounds__(256)
+embed_splice_pos_kernel(const long long* __restrict__ tokens, int t_text, const float* __restrict__ embed, int vocab,
+                        const float* __restrict__ pos, int dim, int img_start, int n_img, float* __restrict__ x0,
+                        int* __restrict__ err_flag) {
+    const int T = t_text + n_img;
+    const int b = blockIdx.x / T;
+    const int t = blockIdx.x - b * T;
+    if (t >= img_start && t < img_start + n_img) return;      // written by the image_proj GEMM epilogue
+    const int ti = (t < img_start) ? t : t - n_img;
+    long long tok = tokens[static_cast<long long>(b) * t_text + ti];
+    if (tok < 0 || tok >= vocab) {
+        if (err_flag != nullptr && threadIdx.x == 0) atomicExch(err_flag, 1);
+        tok = 0;
+    }
+    const float4* e = reinterpret_cast<const float4*>(embed + tok * dim);
+    const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<long long>(t + 2) * dim);
+    float4* o = reinterpret_cast<float4*>(x0 + static_cast<long long>(blockIdx.x) * dim);
+    for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
+        const float4 a = __ldg(e + i), c = __ldg(pp + i);
+        o[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+    }
+}
+
+// ----------------------------------------------------------------------------- CLIP patch im2col + CLS rows
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ pixels, int batch, int image, int patch, __nv_bfloat16* __restrict__ patches,
+              int k_pad, const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x, int dim) {
+    const int g = image / patch;
+    const int n_patch_rows = batch * g * g;
+    if (blockIdx.x < n_patch_rows) {
+        const int b = blockIdx.x / (g * g);
+        const int pi = blockIdx.x - b * g * g;
+        const int py = pi / g, px = pi - py * g;
+        const int pp = patch * patch;
+        __nv_bfloat16* o = patches + static_cast<long long>(blockIdx.x) * k_pad;
+        for (int k = threadIdx.x; k < k_pad; k += blockDim.x) {
+            float val = 0.f;
+            if (k < 3 * pp) {
+                const int c = k / pp, r = k - c * pp;
+                const int dy = r / patch, dx = r - dy * patch;
+                val = pixels[((static_cast<long long>(b) * 3 + c) * image + (py * patch + dy)) * image + px * patch + dx];
+            }
+            o[k] = __float2bfloat16_rn(val);
+        }
+    } else {
+        const int b = blockIdx.x - n_patch_rows;
+        float* o = x + static_cast<long long>(b) * (g * g + 1) * dim;
+        for (int i = threadIdx.x; i < dim; i += blockDim.x) o[i] = cls[i] + pos[i];
+    }
+}
+
+// ----------------------------------------------------------------------------- xPos tables
+__global__ void xpos_tables_kernel(const float* __restrict__ scale, const float* __restrict__ inv_freq, int T,
+                                   int min_pos, float scale_base, float* q_cos, float* q_sin, float* k_cos,
+                                   float* k_sin) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * 32) return;
+    const int t = idx >> 5, j = idx & 31;
+    // the reference computes the exponent, the power and the angle in fp32; keep
+    // those roundings, evaluate pow / sin / cos in double so the table is the correctly
+    // rounded value of the reference's own fp32 arguments.
+    const float expo = static_cast<float>(t + min_pos) / scale_base;
+    const float S = static_cast<float>(pow(static_cast<double>(scale[j]), static_cast<double>(expo)));
+    const float theta = static_cast<float>(t) * inv_freq[j];
+    const float sn = static_cast<float>(sin(static_cast<double>(theta)));
+    const float cs = static_cast<float>(cos(static_cast<double>(theta)));
+    const float Sinv = 1.0f / S;
+    q_cos[idx] = cs * S;
+    q_sin[idx] = sn * S;
+    k_cos[idx] = cs * Sinv;
+    k_sin[idx] = sn * Sinv;
+}
+
+// ----------------------------------------------------------------------------- staging helpers
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long nv = n >> 3;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+        uint4 q;
+        q.x = pack_bf16(a.x, a.y); q.y = pack_bf16(a.z, a.w);
+        q.z = pack_bf16(b.x, b.y); q.w = pack_bf16(b.z, b.w);
+        reinterpret_cast<uint4*>(dst)[i] = q;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+        const long long i = (nv << 3) + threadIdx.x;
+        dst[i] = __float2bfloat16_rn(src[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long row_elems, int copies) {
+    const long long total = row_elems * copies;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride)
+        dst[i] = __ldg(src + i % row_elems);
+}
+
+}  // namespace kx
+
+using namespace kx;
+
+extern "C" int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, const float* gamma,
+                                const float* beta, float eps, void* out, long long ld_out, int rows, int n,
+                                int grp_rows, int grp_stride, int grp_off, cudaStream_t stream) {
+    if (!x || !gamma || !beta || !out) { set_error("kx_layernorm_fwd: null pointer"); return KX_ERR_ARG; }
+    if (rows <= 0 || n <= 0 || (n % 8) || n > 32768) { set_error("kx_layernorm_fwd: n=%d must be a multiple of 8 and <= 32768", n); return KX_ERR_ARG; }
+    const int in_align = x_is_bf16 ? 8 : 4;
+    if ((ld_x % in_align) || (ld_out % 8) || ((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)gamma & 15) ||
+        ((uintptr_t)beta & 15) || (pre_add && ((uintptr_t)pre_add & 15))) {
+        set_error("kx_layernorm_fwd: pointers and row pitches must be 16-byte aligned");
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#define KX_LN(BF, TPR, MV)                                                                                             \
+    layernorm_kernel<BF, TPR, MV><<<(rows + (256 / TPR) - 1) / (256 / TPR), 256, 0, stream>>>(                          \
+        x, ld_x, pre_add, gamma, beta, eps, o, ld_out, rows, n, grp_rows, grp_stride, grp_off)
+    if (n <= 1024) { if (x_is_bf16) KX_LN(true, 32, 4); else KX_LN(false, 32, 4); }
+    else if (n <= 2048) { if (x_is_bf16) KX_LN(true, 32, 8); else KX_LN(false, 32, 8); }
+    else if (n <= 8192) { if (x_is_bf16) KX_LN(true, 256, 4); else KX_LN(false, 256, 4); }
+    else { if (x_is_bf16) KX_LN(true, 256, 16); else KX_LN(false, 256, 16); }
+#undef KX_LN
+    return check_launch("kx_layernorm_fwd");
+}
+
+extern "C" int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
+                                   const float* pos_table, int pos_rows, int dim, int img_start, int n_img, float* x0,
+                                   int* err_flag, cudaStream_t stream) {
+    if (!tokens || !embed_table || !pos_table || !x0) { set_error("kx_embed_splice_pos: null pointer"); return KX_ERR_ARG; }
+    const int T = t_text + n_img;
+    if (batch <= 0 || t_text <= 0 || n_img < 0 || (dim % 4) || img_start < 0 || img_start > t_text) {
+        set_error("kx_embed_splice_pos: bad shape (batch=%d t_text=%d n_img=%d dim=%d img_start=%d)", batch, t_text, n_img, dim, img_start);
+        return KX_ERR_ARG;
+    }
+    if (T + 2 > pos_rows) {
+        set_error("kx_embed_splice_pos: sequence length %d needs %d position rows, table has %d", T, T + 2, pos_rows);
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    embed_splice_pos_kernel<<<batch * T, 256, 0, stream>>>(tokens, t_text, embed_table, vocab, pos_table, dim, img_start, n_img, x0, err_flag);
+    return check_launch("kx_embed_splice_pos");
+}
+
+extern "C" int kx_im2col_patches(const float* pixels, int batch, int image, int patch, void* patches_bf16, int k_pad,
+                                 const float* class_embedding, const float* pos_table, float* x, int dim,
+                                 cudaStream_t stream) {
+    if (!pixels || !patches_bf16 || !class_embedding || !pos_table || !x) { set_error("kx_im2col_patches: null pointer"); return KX_ERR_ARG; }
+    if (batch <= 0 || patch <= 0 || image % patch || k_pad < 3 * patch * patch || (k_pad % 8)) {
+        set_error("kx_im2col_patches: bad shape (image=%d patch=%d k_pad=%d)", image, patch, k_pad);
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    const int g = image / patch;
+    im2col_kernel<<<batch * g * g + batch, 256, 0, stream>>>(pixels, batch, image, patch,
+                                                             reinterpret_cast<__nv_bfloat16*>(patches_bf16), k_pad,
+                                                             class_embedding, pos_table, x, dim);
+    return check_launch("kx_im2col_patches");
+}
+
+extern "C" int kx_xpos_tables(const float* scale, const float* inv_freq, int T, int min_pos, float scale_base,
+                              float* q_cos, float* q_sin, float* k_cos, float* k_sin, cudaStream_t stream) {
+    if (!scale || !inv_freq || !q_cos || !q_sin || !k_cos || !k_sin || T <= 0) { set_error("kx_xpos_tables: bad argument"); return KX_ERR_ARG; }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    xpos_tables_kernel<<<(T * 32 + 255) / 256, 256, 0, stream>>>(scale, inv_freq, T, min_pos, scale_base, q_cos, q_sin, k_cos, k_sin);
+    return check_launch("kx_xpos_tables");
+}
+
+extern "C" int kx_cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+    if (!src || !dst || n <= 0 || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) { set_error("kx_cast_f32_to_bf16: bad argument"); return KX_ERR_ARG; }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const long long nv = (n >> 3) + 1;
+    const int blocks = static_cast<int>(std::min<long long>((nv + 255) / 256, static_cast<long long>(sms) * 8));
+    cast_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    return check_launch("kx_cast_f32_to_bf16");
+}
+
+extern "C" int kx_broadcast_rows(const float* src, float* dst, long long row_elems, int copies, cudaStream_t stream) {
+    if (!src || !dst || row_elems <= 0 || copies <= 0) { set_error("kx_broadcast_rows: bad argument"); return KX_ERR_ARG; }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const long long total = row_elems * copies;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sms) * 8));
+    broadcast_rows_kernel<<<blocks, 256, 0, stream>>>(src, dst, row_elems, copies);
+    return check_launch("kx_broadcast_rows");
+}

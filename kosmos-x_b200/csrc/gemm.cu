@@ -1,0 +1,452 @@
+// kx_gemm_bf16: C[M,N] = epilogue(A[M,K] . W[N,K]^T)   — the Linear layers of the Kosmos-X path.
+//
+// Replaces every F.linear / addmm the reference reaches through torchscale / HF CLIP /
+// flamingo_pytorch (SURVEY.md §2.4 k1,k3,k5,k6,k7,k11,k15,k16,k17,k18).
+//
+// sm_100a design: persistent, warp-specialised.  One CTA (CG=1) or one CTA pair (CG=2,
+// cta_group::2) per SM / SM pair owns a (128*CG) x BN output tile per iteration:
+//   warp 0   TMA producer   : cp.async.bulk.tensor (SWIZZLE_128B) -> smem ring (mbarrier full/empty)
+//   warp 1   MMA issuer     : tcgen05.mma kind::f16 (bf16 x bf16 -> fp32) into TMEM, 2 accumulator
+//                             stages of BN columns; tcgen05.commit releases smem slots / signals epilogue
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue      : tcgen05.ld 32x32b -> registers -> fused bias / xPos rotation / GELU /
+//                             residual / positional add / row scatter -> global (bf16 or fp32)
+// The epilogue of tile i overlaps the MMAs of tile i+1 (double-buffered TMEM accumulator).
+#include "kx_internal.h"
+#include "ptx.cuh"
+
+namespace kx {
+
+constexpr int BLOCK_M = 128;   // rows per CTA (UMMA M = 128 * CG)
+constexpr int BLOCK_K = 64;    // 64 bf16 = one 128-byte swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+template <int CG, int BN>
+struct GemmCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_ROWS = BN / CG;
+    static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;                                    // power of two for BN in {64,128,256}
+};
+
+struct GemmEpi {
+    int M, N, K;
+    const float* bias;         // [N] fp32 or null
+    const float* res;          // fp32 residual, indexed like out (row remap applied), or null
+    long long ld_res;
+    void* out;                 // bf16 or fp32
+    long long ld_out;
+    int act;                   // KX_ACT_*
+    int grp_rows, grp_stride, grp_off;   // out_row = (m / grp_rows) * grp_stride + grp_off + m % grp_rows
+    const float* add_tab;      // fp32 [*, ld_add]; row (m % grp_rows) + add_off is added (positional tables)
+    int add_off;
+    long long ld_add;
+    const float *xq_cos, *xq_sin, *xk_cos, *xk_sin;   // xPos tables [seq_len, 32] fp32
+    int seq_len, d_model;
+    int vec_ok;                // 16-byte vector access to out/res/add_tab rows is legal
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+    constexpr int G = 8;       // m-blocks per raster group: neighbours in time share B tiles in L2
+    const int per_group = G * num_n;
+    const int g = t / per_group;
+    const int first_m = g * G;
+    const int gsz = min(G, num_m - first_m);
+    const int r = t - g * per_group;
+    m_blk = first_m + r % gsz;
+    n_blk = r / gsz;
+}
+
+template <bool OUT_F32, int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t (&v)[32], int m, int n0) {
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    const bool full = (n0 + 32 <= ep.N);
+
+    if (ep.bias != nullptr) {
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
+                f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < ep.N) f[i] += __ldg(ep.bias + n0 + i);
+        }
+    }
+
+    if constexpr (EPI == KX_EPI_QKV_XPOS) {
+        // columns [0,d) = q (upscale tables), [d,2d) = k (downscale tables), [2d,3d) = v (untouched).
+        // Pair j of a 64-wide head = columns (2j, 2j+1): out0 = x0*c - x1*s ; out1 = x1*c + x0*s.
+        const int which = n0 / ep.d_model;
+        if (which < 2) {
+            const int t = m % ep.seq_len;
+            const int j0 = (n0 & 63) >> 1;
+            const float* ct = (which == 0 ? ep.xq_cos : ep.xk_cos) + t * 32 + j0;
+            const float* st = (which == 0 ? ep.xq_sin : ep.xk_sin) + t * 32 + j0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + i));
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(st + i));
+                const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+                const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float x0 = f[2 * (i + u)], x1 = f[2 * (i + u) + 1];
+                    f[2 * (i + u)] = x0 * c[u] - x1 * s[u];
+                    f[2 * (i + u) + 1] = x1 * c[u] + x0 * s[u];
+                }
+            }
+        }
+    }
+
+    if (ep.act == KX_ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+    } else if (ep.act == KX_ACT_QUICK_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+    }
+
+    long long orow = m;
+    int prow = 0;
+    if (ep.grp_rows > 0) {
+        const int g = m / ep.grp_rows;
+        prow = m - g * ep.grp_rows;
+        orow = static_cast<long long>(g) * ep.grp_stride + ep.grp_off + prow;
+    }
+    const bool vec = full && ep.vec_ok;
+
+    if (ep.add_tab != nullptr) {
+        const float* a = ep.add_tab + static_cast<long long>(prow + ep.add_off) * ep.ld_add + n0;
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(a + i));
+                f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < ep.N) f[i] += __ldg(a + i);
+        }
+    }
+    if (ep.res != nullptr) {
+        const float* r = ep.res + orow * ep.ld_res + n0;
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(r + i);
+                f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < ep.N) f[i] += r[i];
+        }
+    }
+
+    if constexpr (OUT_F32) {
+        float* o = reinterpret_cast<float*>(ep.out) + orow * ep.ld_out + n0;
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        } else if (full && ((ep.ld_out & 1) == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 7) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) *reinterpret_cast<float2*>(o + i) = make_float2(f[i], f[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < ep.N) o[i] = f[i];
+        }
+    } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + orow * ep.ld_out + n0;
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                uint4 q;
+                q.x = pack_bf16(f[i], f[i + 1]);
+                q.y = pack_bf16(f[i + 2], f[i + 3]);
+                q.z = pack_bf16(f[i + 4], f[i + 5]);
+                q.w = pack_bf16(f[i + 6], f[i + 7]);
+                *reinterpret_cast<uint4*>(o + i) = q;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < ep.N) o[i] = __float2bfloat16_rn(f[i]);
+        }
+    }
+}
+
+template <int CG, int BN, bool OUT_F32, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmEpi ep) {
+    using Cfg = GemmCfg<CG, BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment (identical offset in both CTAs of a pair)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = (rank == 0);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], CG);       // one arrival per CTA producer, on the leader's barrier
+            mbar_init(&empty[s], 1);       // one tcgen05.commit (multicast to both CTAs when CG=2)
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], CG * 128);   // every epilogue thread of every CTA, on the leader's barrier
+        }
+        fence_mbar_init();
+    }
+    if constexpr (CG == 2) cluster_sync_all();
+    if (warp == 2) {
+        tmem_alloc<CG>(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish<CG>();
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_m = (ep.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
+    const int num_n = (ep.N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (ep.K + BLOCK_K - 1) / BLOCK_K;
+    const int cluster_id = blockIdx.x / CG;
+    const int num_clusters = gridDim.x / CG;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            int m_blk, n_blk;
+            tile_coords(t, num_m, num_n, m_blk, n_blk);
+            const int m0 = m_blk * (BLOCK_M * CG) + rank * BLOCK_M;
+            const int n0 = n_blk * BN + rank * Cfg::B_ROWS;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[s], ph ^ 1);
+                if constexpr (CG == 1) {
+                    mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                    tma_load_2d(&tmA, &full[s], smem_a + s * Cfg::A_BYTES, kb * BLOCK_K, m0);
+                    tma_load_2d(&tmB, &full[s], smem_b + s * Cfg::B_BYTES, kb * BLOCK_K, n0);
+                } else {
+                    if (leader) mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES * 2);
+                    else mbar_arrive_cluster(&full[s], 0);
+                    tma_load_2d_cg2(&tmA, &full[s], smem_a + s * Cfg::A_BYTES, kb * BLOCK_K, m0);
+                    tma_load_2d_cg2(&tmB, &full[s], smem_b + s * Cfg::B_BYTES, kb * BLOCK_K, n0);
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ================= MMA issuer (leader CTA only) =================
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BN);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(&tempty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + a * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES));
+                const uint64_t bdesc = make_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                    umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                if constexpr (CG == 1) umma_commit(&empty[s]); else umma_commit_cg2(&empty[s], 0b11);
+                if (kb == num_kb - 1) {
+                    if constexpr (CG == 1) umma_commit(&tfull[a]); else umma_commit_cg2(&tfull[a], 0b11);
+                }
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+        if constexpr (CG == 2) {
+            // the peer's last remote arrivals must land before this CTA's barriers go away
+            if (it > 0) {
+                const int last = it - 1;
+                mbar_wait(&tempty[last & 1], (last >> 1) & 1);
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ================= epilogue =================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            int m_blk, n_blk;
+            tile_coords(t, num_m, num_n, m_blk, n_blk);
+            const int a = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int m = m_blk * (BLOCK_M * CG) + rank * BLOCK_M + q * 32 + lane;
+            const int nb = n_blk * BN;
+            mbar_wait(&tfull[a], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                if (nb + c * 32 >= ep.N) break;       // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (m < ep.M) epilogue_chunk<OUT_F32, EPI>(ep, v, m, nb + c * 32);
+            }
+            tc_fence_before();
+            if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------- host side
+static bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer,
+                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    auto fn = driver_api().encode_tiled;
+    if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return false; }
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r, ptr,
+                  (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
+                  box_outer);
+        return false;
+    }
+    return true;
+}
+bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                       uint32_t box_inner, uint32_t box_outer) {
+    return make_tmap_2d(tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer);
+}
+
+template <int CG, int BN, bool OUT_F32, int EPI>
+static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmEpi& ep, int max_ctas,
+                       cudaStream_t stream) {
+    using Cfg = GemmCfg<CG, BN>;
+    CUtensorMap tmA, tmB;
+    if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP;
+    if (!make_tmap_2d(&tmB, W, ep.K, ep.N, ldw * 2, BLOCK_K, Cfg::B_ROWS)) return KX_ERR_TMAP;
+    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI>;
+    static bool attr_set = false;   // per template instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
+        attr_set = true;
+    }
+    const int num_m = (ep.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
+    const int num_n = (ep.N + BN - 1) / BN;
+    int clusters = std::min(num_m * num_n, std::max(1, max_ctas / CG));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CG);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ep);
+    if (e != cudaSuccess) { set_error("gemm launch failed: %s", cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
+    count_launch();
+    return KX_OK;
+}
+
+}  // namespace kx
+
+using namespace kx;
+
+extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const kx_gemm_args* g,
+                            cudaStream_t stream) {
+    if (!A || !W || !g || !g->out) { set_error("kx_gemm_bf16: null pointer"); return KX_ERR_ARG; }
+    if (g->M <= 0 || g->N <= 0 || g->K <= 0) { set_error("kx_gemm_bf16: bad shape M=%d N=%d K=%d", g->M, g->N, g->K); return KX_ERR_ARG; }
+    if ((lda % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) {
+        set_error("kx_gemm_bf16: A/W need 16-byte aligned base and row pitch (lda=%lld ldw=%lld)", lda, ldw);
+        return KX_ERR_ARG;
+    }
+    GemmEpi ep = {};
+    ep.M = g->M; ep.N = g->N; ep.K = g->K;
+    ep.bias = g->bias; ep.res = g->res; ep.ld_res = g->ld_res;
+    ep.out = g->out; ep.ld_out = g->ld_out; ep.act = g->act;
+    ep.grp_rows = g->grp_rows; ep.grp_stride = g->grp_stride; ep.grp_off = g->grp_off;
+    ep.add_tab = g->add_tab; ep.add_off = g->add_off; ep.ld_add = g->ld_add;
+    ep.xq_cos = g->xq_cos; ep.xq_sin = g->xq_sin; ep.xk_cos = g->xk_cos; ep.xk_sin = g->xk_sin;
+    ep.seq_len = g->seq_len; ep.d_model = g->d_model;
+    const int esz = g->out_f32 ? 4 : 2;
+    bool vec = ((g->ld_out * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->out) & 15) == 0);
+    if (g->res) vec = vec && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
+    if (g->add_tab) vec = vec && ((g->ld_add * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->add_tab) & 15) == 0);
+    if (g->bias && (reinterpret_cast<uintptr_t>(g->bias) & 15)) { set_error("kx_gemm_bf16: bias must be 16-byte aligned"); return KX_ERR_ARG; }
+    ep.vec_ok = vec ? 1 : 0;
+    if (g->epi == KX_EPI_QKV_XPOS) {
+        if (!g->xq_cos || !g->xq_sin || !g->xk_cos || !g->xk_sin || g->seq_len <= 0 || g->d_model <= 0 ||
+            (g->d_model % 64) || g->N != 3 * g->d_model || g->out_f32) {
+            set_error("kx_gemm_bf16: QKV_XPOS needs tables, seq_len, d_model%%64==0, N==3*d_model, bf16 out");
+            return KX_ERR_ARG;
+        }
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    int cg = g->cta_group;
+    if (cg == 0) cg = (g->M > 128) ? 2 : 1;
+    int bn = g->block_n;
+    if (bn == 0) bn = (g->N >= 256 && (long long)((g->M + 127) / 128) * ((g->N + 255) / 256) >= sms / 2) ? 256 : 128;
+    const int max_ctas = g->max_ctas > 0 ? std::min(g->max_ctas, sms) : sms;
+
+#define KX_GEMM_CASE(CG_, BN_)                                                                               \
+    if (cg == CG_ && bn == BN_) {                                                                            \
+        if (g->epi == KX_EPI_QKV_XPOS) return launch_gemm<CG_, BN_, false, KX_EPI_QKV_XPOS>(A, lda, W, ldw, ep, max_ctas, stream); \
+        if (g->out_f32) return launch_gemm<CG_, BN_, true, KX_EPI_GENERIC>(A, lda, W, ldw, ep, max_ctas, stream);                  \
+        return launch_gemm<CG_, BN_, false, KX_EPI_GENERIC>(A, lda, W, ldw, ep, max_ctas, stream);                                  \
+    }
+    KX_GEMM_CASE(1, 128)
+    KX_GEMM_CASE(1, 256)
+    KX_GEMM_CASE(2, 128)
+    KX_GEMM_CASE(2, 256)
+#undef KX_GEMM_CASE
+    set_error("kx_gemm_bf16: unsupported config cta_group=%d block_n=%d", cg, bn);
+    return KX_ERR_ARG;
+}

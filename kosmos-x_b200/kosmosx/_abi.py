@@ -1,0 +1,80 @@
+"""ctypes binding of libkosmosx_sm100.so (the C ABI declared in include/kosmosx_b200.h).
+
+There is no fallback: if the shared library is missing, importing this module raises, and
+every entry point returns an error (surfaced as RuntimeError) when no B200 is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libkosmosx_sm100.so")
+
+KX_OK = 0
+KX_ACT_NONE, KX_ACT_GELU, KX_ACT_QUICK_GELU = 0, 1, 2
+KX_EPI_GENERIC, KX_EPI_QKV_XPOS = 0, 1
+
+_f32p = C.c_void_p
+_vp = C.c_void_p
+_ll = C.c_longlong
+_i = C.c_int
+_f = C.c_float
+
+
+class GemmArgs(C.Structure):
+    """struct kx_gemm_args (include/kosmosx_b200.h)."""
+
+    _fields_ = [
+        ("M", _i), ("N", _i), ("K", _i),
+        ("bias", _f32p), ("res", _f32p), ("ld_res", _ll),
+        ("out", _vp), ("ld_out", _ll), ("out_f32", _i), ("act", _i), ("epi", _i),
+        ("grp_rows", _i), ("grp_stride", _i), ("grp_off", _i),
+        ("add_tab", _f32p), ("add_off", _i), ("ld_add", _ll),
+        ("xq_cos", _f32p), ("xq_sin", _f32p), ("xk_cos", _f32p), ("xk_sin", _f32p),
+        ("seq_len", _i), ("d_model", _i),
+        ("cta_group", _i), ("block_n", _i), ("max_ctas", _i),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/kosmosx_b200.h
+SIGNATURES = {
+    "kx_last_error": (C.c_char_p, []),
+    "kx_abi_version": (_i, []),
+    "kx_device_check": (_i, []),
+    "kx_launch_count": (C.c_ulonglong, []),
+    "kx_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, C.POINTER(GemmArgs), _vp]),
+    "kx_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
+    "kx_perceiver_xattn_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
+    "kx_layernorm_fwd": (_i, [_vp, _i, _ll, _f32p, _f32p, _f32p, _f, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
+    "kx_embed_splice_pos": (_i, [_vp, _i, _i, _f32p, _i, _f32p, _i, _i, _i, _i, _f32p, _vp, _vp]),
+    "kx_im2col_patches": (_i, [_f32p, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
+    "kx_xpos_tables": (_i, [_f32p, _f32p, _i, _i, _f, _f32p, _f32p, _f32p, _f32p, _vp]),
+    "kx_cast_f32_to_bf16": (_i, [_f32p, _vp, _ll, _vp]),
+    "kx_broadcast_rows": (_i, [_f32p, _f32p, _ll, _i, _vp]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with kosmos-x_b200/build.sh (or __graft_entry__.build()). "
+            "kosmosx has no CPU or PyTorch fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    return (lib.kx_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(status: int, what: str) -> None:
+    if status != KX_OK:
+        raise RuntimeError(f"{what} failed (status {status}): {last_error()}")

@@ -1,0 +1,137 @@
+"""Thin Python wrappers over the C ABI: tensors in, raw pointers out.  No arithmetic here."""
+from __future__ import annotations
+
+import torch
+
+from . import _abi
+from ._abi import GemmArgs, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: kosmosx has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name} must be contiguous in its last dimension")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=None, act=_abi.KX_ACT_NONE,
+         grp=None, add_tab=None, add_off=0, xpos=None, seq_len=0, cta_group=0, block_n=0, max_ctas=0, M=None):
+    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; out bf16 or fp32 (2-D views, row pitch = stride(0))."""
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    g = GemmArgs()
+    g.M = a.shape[0] if M is None else M
+    g.K = a.shape[1]
+    g.N = w.shape[0]
+    if w.shape[1] != g.K:
+        raise ValueError(f"gemm: K mismatch {a.shape} vs {w.shape}")
+    g.bias = _ptr(bias)
+    g.res = _ptr(res)
+    g.ld_res = res.stride(0) if res is not None else 0
+    g.out = out.data_ptr()
+    g.ld_out = out.stride(0)
+    g.out_f32 = 1 if out.dtype == torch.float32 else 0
+    if out.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("gemm: out must be fp32 or bf16")
+    g.act = act
+    if grp is not None:
+        g.grp_rows, g.grp_stride, g.grp_off = grp
+    g.add_tab = _ptr(add_tab)
+    g.add_off = add_off
+    g.ld_add = add_tab.stride(0) if add_tab is not None else 0
+    if xpos is not None:
+        g.epi = _abi.KX_EPI_QKV_XPOS
+        g.xq_cos, g.xq_sin, g.xk_cos, g.xk_sin = (t.data_ptr() for t in xpos)
+        g.seq_len = seq_len
+        g.d_model = g.N // 3
+    g.cta_group, g.block_n, g.max_ctas = cta_group, block_n, max_ctas
+    check(lib.kx_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), g, _stream()), "kx_gemm_bf16")
+    return out
+
+
+def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale):
+    """q, k, v: bf16 2-D views [batch*seq_len, heads*64] sharing one row pitch; out bf16 [batch*seq_len, >=heads*64]."""
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _req(t, torch.bfloat16, n)
+    if not (q.stride(0) == k.stride(0) == v.stride(0)):
+        raise ValueError("attention: q, k, v must share a row pitch")
+    check(lib.kx_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                          batch, heads, seq_len, 1 if causal else 0, float(scale), _stream()), "kx_attn_fwd")
+    return out
+
+
+def perceiver_attention(q, kv, out, *, batch, heads, n_q, n_kv, v_col_off, scale):
+    for n, t in (("q", q), ("kv", kv), ("out", out)):
+        _req(t, torch.bfloat16, n)
+    check(lib.kx_perceiver_xattn_fwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), v_col_off, out.data_ptr(),
+                                     out.stride(0), batch, heads, n_q, n_kv, float(scale), _stream()),
+          "kx_perceiver_xattn_fwd")
+    return out
+
+
+def layernorm(x, gamma, beta, out, *, eps=1e-5, pre_add=None, grp=None, rows=None):
+    """out(bf16) = LayerNorm(x (+ pre_add)) over the last dim; x fp32 or bf16, 2-D."""
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("layernorm: x must be fp32 or bf16")
+    _req(x, x.dtype, "x")
+    _req(out, torch.bfloat16, "out")
+    g = grp or (0, 0, 0)
+    r = x.shape[0] if rows is None else rows
+    check(lib.kx_layernorm_fwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _ptr(pre_add),
+                               gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), r,
+                               x.shape[1], g[0], g[1], g[2], _stream()), "kx_layernorm_fwd")
+    return out
+
+
+def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_start, n_img, err_flag=None):
+    _req(tokens, torch.int64, "tokens")
+    B, t_text = tokens.shape
+    if not tokens.is_contiguous():
+        tokens = tokens.contiguous()
+    check(lib.kx_embed_splice_pos(tokens.data_ptr(), B, t_text, embed_table.data_ptr(), embed_table.shape[0],
+                                  pos_table.data_ptr(), pos_table.shape[0], embed_table.shape[1], img_start, n_img,
+                                  x0.data_ptr(), _ptr(err_flag), _stream()), "kx_embed_splice_pos")
+    return x0
+
+
+def im2col_patches(pixels, patches, class_embedding, pos_table, x, *, image, patch):
+    _req(pixels, torch.float32, "pixels")
+    check(lib.kx_im2col_patches(pixels.data_ptr(), pixels.shape[0], image, patch, patches.data_ptr(), patches.shape[1],
+                                class_embedding.data_ptr(), pos_table.data_ptr(), x.data_ptr(), x.shape[-1], _stream()),
+          "kx_im2col_patches")
+    return patches
+
+
+def xpos_tables(scale, inv_freq, T, min_pos, scale_base, device):
+    tabs = torch.empty(4, T, 32, dtype=torch.float32, device=device)
+    check(lib.kx_xpos_tables(scale.data_ptr(), inv_freq.data_ptr(), T, min_pos, float(scale_base), tabs[0].data_ptr(),
+                             tabs[1].data_ptr(), tabs[2].data_ptr(), tabs[3].data_ptr(), _stream()), "kx_xpos_tables")
+    return tabs
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor | None = None) -> torch.Tensor:
+    _req(src, torch.float32, "src")
+    src = src.contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(lib.kx_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "kx_cast_f32_to_bf16")
+    return dst
+
+
+def broadcast_rows(src, dst, copies):
+    check(lib.kx_broadcast_rows(src.data_ptr(), dst.data_ptr(), src.numel(), copies, _stream()), "kx_broadcast_rows")
+    return dst
+
+
+def launch_count() -> int:
+    return int(lib.kx_launch_count())

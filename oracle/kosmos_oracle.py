@@ -1,0 +1,573 @@
+"""CPU oracle for the Kosmos-X multimodal forward path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain eager PyTorch (fp32), the algorithm that
+``kosmosx.model.Kosmos.forward(text_tokens, images)`` executes in the reference
+(/root/reference/kosmosx/model.py:208-253).  It exists so that the CUDA path in
+``kosmos-x_b200/`` can be checked against the reference semantics; it is never
+imported by the product package.  Only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.
+
+PARITY UNPINNED: the reference's hot-path arithmetic lives in
+three third-party packages that are NOT vendored in /root/reference and are NOT
+installed here (torchscale [unpinned, + the private ``passed_x`` patch of
+README.md:179-193], flamingo_pytorch [unpinned], bitsandbytes 0.38.1), and the
+reference's own tests hold no valid golden vectors for this path.
+What *is* pinned:
+  * the CLIP ViT-L/14 tower restated here is checked weight-for-weight against
+    the installed ``transformers`` implementation (tests/test_oracle.py), which
+    is the real dependency the reference calls at model.py:154-156,230;
+  * the sub-LN decoder block (xPos off) is checked against the installed
+    ``transformers`` Kosmos-2 text block, an independent port of the same
+    torchscale layer (same parameter names);
+  * xPos is checked for its defining relative-position (Toeplitz) property.
+Everything else follows the published algorithms of those packages as recorded
+in SURVEY.md Appendix A; each class cites the reference call site it serves.
+
+``emulate_bf16=True`` re-runs the same algorithm with every tensor-core operand
+rounded to bf16 at exactly the points where the CUDA path rounds (fp32
+accumulate, fp32 residual stream, fp32 LayerNorm/softmax/GELU).  It is used by
+the tests to separate "kernel bug" from "bf16 rounding".
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- config
+@dataclass
+class OracleConfig:
+    """Sizes of the reference model (defaults = /root/reference/kosmosx/model.py:149-206)."""
+
+    # decoder (model.py:161-183)
+    vocab: int = 32002
+    dim: int = 2048
+    layers: int = 24
+    ffn: int = 8192
+    heads: int = 32
+    max_positions: int = 2048          # PositionalEmbedding(2048, 2048, 1): rows; T <= rows-2
+    multiway: bool = True
+    xpos_scale_base: int = 512
+    eps: float = 1e-5
+    # CLIP ViT-L/14 (model.py:154-156)
+    vit_dim: int = 1024
+    vit_layers: int = 24
+    vit_heads: int = 16
+    vit_mlp: int = 4096
+    patch: int = 14
+    image: int = 224
+    vit_act: str = "gelu"              # laion ViT-L/14 checkpoint; HF config default is quick_gelu
+    # PerceiverResampler (model.py:196-203)
+    p_depth: int = 2
+    p_heads: int = 8
+    p_dim_head: int = 64
+    p_latents: int = 64
+    p_media_embeds: int = 257
+    p_ff_mult: int = 4
+
+    @property
+    def vit_tokens(self) -> int:
+        return (self.image // self.patch) ** 2 + 1
+
+    @staticmethod
+    def tiny(**kw) -> "OracleConfig":
+        """A small configuration with the same structure (head_dim stays 64)."""
+        base = dict(vocab=1002, dim=128, layers=2, ffn=256, heads=2, max_positions=256,
+                    vit_dim=128, vit_layers=2, vit_heads=2, vit_mlp=256, patch=14, image=56,
+                    p_depth=2, p_heads=2, p_dim_head=64, p_latents=64, p_media_embeds=17)
+        base.update(kw)
+        return OracleConfig(**base)
+
+
+class _Emu:
+    """bf16 operand rounding switch shared by every oracle module of one model."""
+
+    def __init__(self, on: bool = False):
+        self.on = on
+
+    def r(self, x: torch.Tensor) -> torch.Tensor:
+        return x.to(torch.bfloat16).to(torch.float32) if self.on else x
+
+
+def _linear(emu: _Emu, x, lin: nn.Linear):
+    return F.linear(emu.r(x), emu.r(lin.weight), lin.bias)
+
+
+# --------------------------------------------------------------------------- CLIP ViT
+class _ClipAttention(nn.Module):
+    """[HF] transformers/models/clip/modeling_clip.py:282-336 (eager attention)."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        d = cfg.vit_dim
+        self.h = cfg.vit_heads
+        self.emu = emu
+        self.k_proj = nn.Linear(d, d)
+        self.v_proj = nn.Linear(d, d)
+        self.q_proj = nn.Linear(d, d)
+        self.out_proj = nn.Linear(d, d)
+
+    def forward(self, x):
+        B, T, D = x.shape
+        hd = D // self.h
+        e = self.emu
+        q = e.r(_linear(e, x, self.q_proj) * hd ** -0.5).view(B, T, self.h, hd).transpose(1, 2)
+        k = e.r(_linear(e, x, self.k_proj)).view(B, T, self.h, hd).transpose(1, 2)
+        v = e.r(_linear(e, x, self.v_proj)).view(B, T, self.h, hd).transpose(1, 2)
+        s = q @ k.transpose(-1, -2)
+        m = s.amax(-1, keepdim=True)
+        p = torch.exp(s - m)
+        o = (e.r(p) @ v) / p.sum(-1, keepdim=True)
+        o = e.r(o).transpose(1, 2).reshape(B, T, D)
+        return _linear(e, o, self.out_proj)
+
+
+class _ClipMLP(nn.Module):
+    """[HF] modeling_clip.py:339-351."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        self.emu = emu
+        self.act = cfg.vit_act
+        self.fc1 = nn.Linear(cfg.vit_dim, cfg.vit_mlp)
+        self.fc2 = nn.Linear(cfg.vit_mlp, cfg.vit_dim)
+
+    def forward(self, x):
+        h = _linear(self.emu, x, self.fc1)
+        h = F.gelu(h) if self.act == "gelu" else h * torch.sigmoid(1.702 * h)
+        return _linear(self.emu, h, self.fc2)
+
+
+class _ClipLayer(nn.Module):
+    """[HF] modeling_clip.py:363-385 (pre-LN block)."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        self.self_attn = _ClipAttention(cfg, emu)
+        self.layer_norm1 = nn.LayerNorm(cfg.vit_dim, eps=cfg.eps)
+        self.mlp = _ClipMLP(cfg, emu)
+        self.layer_norm2 = nn.LayerNorm(cfg.vit_dim, eps=cfg.eps)
+
+    def forward(self, x):
+        x = x + self.self_attn(self.layer_norm1(x))
+        return x + self.mlp(self.layer_norm2(x))
+
+
+class _ClipEmbeddings(nn.Module):
+    """[HF] modeling_clip.py:138-159, 202-218."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        self.cfg, self.emu = cfg, emu
+        self.class_embedding = nn.Parameter(torch.randn(cfg.vit_dim))
+        self.patch_embedding = nn.Conv2d(3, cfg.vit_dim, cfg.patch, cfg.patch, bias=False)
+        self.position_embedding = nn.Embedding(cfg.vit_tokens, cfg.vit_dim)
+
+    def forward(self, pixels):
+        B, _, H, W = pixels.shape
+        if H != self.cfg.image or W != self.cfg.image:
+            raise ValueError(f"Input image size ({H}*{W}) doesn't match model "
+                             f"({self.cfg.image}*{self.cfg.image}).")
+        e = self.emu
+        w = self.patch_embedding.weight
+        x = F.conv2d(e.r(pixels.to(w.dtype)), e.r(w), stride=self.cfg.patch)
+        x = x.flatten(2).transpose(1, 2)
+        x = torch.cat([self.class_embedding.expand(B, 1, -1), x], dim=1)
+        return x + self.position_embedding.weight[None]
+
+
+class _ClipEncoder(nn.Module):
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        self.layers = nn.ModuleList(_ClipLayer(cfg, emu) for _ in range(cfg.vit_layers))
+
+
+class ClipVisionTower(nn.Module):
+    """CLIPVisionTransformer, [HF] modeling_clip.py:647-697.  ``forward`` returns the
+    un-normalised ``last_hidden_state`` that model.py:230 consumes (post_layernorm is
+    applied to the pooled CLS token only and is unused on this path)."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        self.embeddings = _ClipEmbeddings(cfg, emu)
+        self.pre_layrnorm = nn.LayerNorm(cfg.vit_dim, eps=cfg.eps)   # (sic) HF attribute name
+        self.encoder = _ClipEncoder(cfg, emu)
+        self.post_layernorm = nn.LayerNorm(cfg.vit_dim, eps=cfg.eps)
+
+    def forward(self, pixel_values):
+        x = self.pre_layrnorm(self.embeddings(pixel_values))
+        for layer in self.encoder.layers:
+            x = layer(x)
+        return x
+
+
+# --------------------------------------------------------------------------- perceiver
+class _PerceiverAttention(nn.Module):
+    """flamingo_pytorch PerceiverAttention; call site model.py:196-203,231."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        d, inner = cfg.vit_dim, cfg.p_heads * cfg.p_dim_head
+        self.h, self.dh, self.emu = cfg.p_heads, cfg.p_dim_head, emu
+        self.norm_media = nn.LayerNorm(d)
+        self.norm_latents = nn.LayerNorm(d)
+        self.to_q = nn.Linear(d, inner, bias=False)
+        self.to_kv = nn.Linear(d, inner * 2, bias=False)
+        self.to_out = nn.Linear(inner, d, bias=False)
+
+    def forward(self, x, latents):
+        # x: (B, m, n, D)   latents: (B, m, L, D)
+        e = self.emu
+        x = self.norm_media(x)
+        latents = self.norm_latents(latents)
+        B, m, L, _ = latents.shape
+        q = _linear(e, latents, self.to_q)
+        kv = _linear(e, torch.cat([x, latents], dim=-2), self.to_kv)
+        k, v = kv.chunk(2, dim=-1)
+
+        def split(t):                                      # b m n (h d) -> b h m n d
+            return t.view(B, m, t.shape[2], self.h, self.dh).permute(0, 3, 1, 2, 4)
+
+        q, k, v = e.r(split(q)), e.r(split(k)), e.r(split(v))
+        q = q * self.dh ** -0.5
+        sim = q @ k.transpose(-1, -2)
+        sim = sim - sim.amax(dim=-1, keepdim=True)
+        attn = sim.softmax(dim=-1)
+        out = e.r(attn @ v)                                # b h m L d
+        out = out.permute(0, 2, 3, 1, 4).reshape(B, m, L, self.h * self.dh)
+        return _linear(e, out, self.to_out)
+
+
+class _EmuLinear(nn.Linear):
+    """nn.Linear whose operands go through the bf16 emulation switch (keeps the
+    ``Sequential`` index names ``1``/``3`` of the flamingo FeedForward)."""
+
+    emu: _Emu = None
+
+    def forward(self, x):
+        return _linear(self.emu, x, self)
+
+
+def _perceiver_ff(cfg: OracleConfig, emu: _Emu):
+    d, inner = cfg.vit_dim, cfg.vit_dim * cfg.p_ff_mult
+    l1, l3 = _EmuLinear(d, inner, bias=False), _EmuLinear(inner, d, bias=False)
+    l1.emu = l3.emu = emu
+    return nn.Sequential(nn.LayerNorm(d), l1, nn.GELU(), l3)
+
+
+class PerceiverResampler(nn.Module):
+    """flamingo_pytorch.PerceiverResampler(dim=1024, depth=2, dim_head=64, heads=8,
+    num_latents=64, num_media_embeds=257) — SURVEY.md A.2; model.py:196-203."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        d = cfg.vit_dim
+        self.latents = nn.Parameter(torch.randn(cfg.p_latents, d))
+        self.media_pos_emb = nn.Parameter(torch.randn(cfg.p_media_embeds, 1, d))
+        self.layers = nn.ModuleList(
+            nn.ModuleList([_PerceiverAttention(cfg, emu), _perceiver_ff(cfg, emu)])
+            for _ in range(cfg.p_depth))
+        self.norm = nn.LayerNorm(d)
+
+    def forward(self, x):
+        if x.ndim == 3:
+            x = x[:, None]                                  # (B, 1, n, D)
+        m = x.shape[1]
+        x = x + self.media_pos_emb[:m]                      # indexed by MEDIA index (A.2)
+        latents = self.latents.expand(x.shape[0], m, -1, -1)
+        for attn, ff in self.layers:
+            latents = attn(x, latents) + latents
+            latents = ff(latents) + latents
+        return self.norm(latents)
+
+
+# --------------------------------------------------------------------------- xPos
+def _rotate_every_two(x):
+    x1, x2 = x[..., ::2], x[..., 1::2]
+    return torch.stack((-x2, x1), dim=-1).flatten(-2)
+
+
+def _dup_interleave(m):
+    return m.repeat_interleave(2, dim=-1)
+
+
+class XPOS(nn.Module):
+    """torchscale.component.xpos_relative_position.XPOS; enabled by
+    ``xpos_rel_pos=True`` at model.py:180."""
+
+    def __init__(self, head_dim: int, scale_base: int = 512):
+        super().__init__()
+        self.head_dim, self.scale_base = head_dim, scale_base
+        self.register_buffer("scale", (torch.arange(0, head_dim, 2) + 0.4 * head_dim) / (1.4 * head_dim))
+
+    def tables(self, length: int, offset: int = 0):
+        """(scale[T,hd/2], sin[T,hd/2], cos[T,hd/2]) before the up/down choice."""
+        min_pos = -(length + offset) // 2
+        max_pos = length + offset + min_pos
+        scale = self.scale ** (torch.arange(min_pos, max_pos, 1).to(self.scale) / self.scale_base)[:, None]
+        dim = scale.shape[1]
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, dim) / dim))
+        sinusoid = torch.einsum("i , j -> i j", torch.arange(0, scale.shape[0], dtype=torch.float), inv_freq).to(scale)
+        return scale, torch.sin(sinusoid), torch.cos(sinusoid)
+
+    def forward(self, x, offset=0, downscale=False):
+        length = x.shape[1]
+        scale, sin, cos = self.tables(length, offset)
+        if scale.shape[0] > length:
+            scale, sin, cos = scale[-length:], sin[-length:], cos[-length:]
+        if downscale:
+            scale = 1 / scale
+        sin, cos = _dup_interleave(sin * scale), _dup_interleave(cos * scale)
+        return x * cos + _rotate_every_two(x) * sin
+
+
+# --------------------------------------------------------------------------- decoder
+class MultiwayNetwork(nn.Module):
+    """torchscale.component.multiway_network.MultiwayNetwork.  Nothing in
+    the reference sets ``split_position`` so only ``.A`` ever runs (model.py:181)."""
+
+    def __init__(self, module: nn.Module, make_b):
+        super().__init__()
+        self.A = module
+        self.B = make_b()
+        self.split_position = -1
+
+    def forward(self, x, **kw):
+        if self.split_position == -1:
+            return self.A(x, **kw)
+        if self.split_position == 0:
+            return self.B(x, **kw)
+        x1, x2 = torch.split(x, [self.split_position, x.size(1) - self.split_position], dim=1)
+        return torch.cat([self.A(x1, **kw), self.B(x2, **kw)], dim=1)
+
+
+def _wrap(cfg: OracleConfig, make):
+    return MultiwayNetwork(make(), make) if cfg.multiway else make()
+
+
+def _inner(mod):
+    """The live branch of a (possibly) multiway-wrapped module."""
+    return mod.A if isinstance(mod, MultiwayNetwork) else mod
+
+
+class FeedForwardNetwork(nn.Module):
+    """torchscale FeedForwardNetwork with sub-LN."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        self.emu = emu
+        self.fc1 = nn.Linear(cfg.dim, cfg.ffn)
+        self.fc2 = nn.Linear(cfg.ffn, cfg.dim)
+        self.ffn_layernorm = nn.LayerNorm(cfg.ffn, eps=cfg.eps)
+
+    def forward(self, x):
+        x = _linear(self.emu, x, self.fc1)
+        x = F.gelu(x.float()).type_as(x)
+        x = self.ffn_layernorm(self.emu.r(x))
+        return _linear(self.emu, x, self.fc2)
+
+
+class MultiheadAttention(nn.Module):
+    """torchscale MultiheadAttention, self-attention with sub-LN and xPos."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        d = cfg.dim
+        self.h, self.hd, self.emu = cfg.heads, cfg.dim // cfg.heads, emu
+        self.scaling = self.hd ** -0.5
+        self.k_proj = _wrap(cfg, lambda: nn.Linear(d, d))
+        self.v_proj = _wrap(cfg, lambda: nn.Linear(d, d))
+        self.q_proj = _wrap(cfg, lambda: nn.Linear(d, d))
+        self.out_proj = _wrap(cfg, lambda: nn.Linear(d, d))
+        self.inner_attn_ln = _wrap(cfg, lambda: nn.LayerNorm(d, eps=cfg.eps))
+        self.xpos = XPOS(self.hd, cfg.xpos_scale_base)
+
+    def forward(self, x, attn_mask):
+        B, T, D = x.shape
+        e = self.emu
+        q = _linear(e, x, _inner(self.q_proj))
+        k = _linear(e, x, _inner(self.k_proj))
+        v = _linear(e, x, _inner(self.v_proj))
+        q = q * self.scaling
+
+        def heads(t):
+            return t.view(B, T, self.h, self.hd).transpose(1, 2).reshape(B * self.h, T, self.hd)
+
+        q, k, v = heads(q), heads(k), e.r(heads(v))
+        k = e.r(self.xpos(k, offset=0, downscale=True))
+        q = e.r(self.xpos(q, offset=0, downscale=False))
+        w = torch.bmm(q, k.transpose(1, 2))
+        w = torch.nan_to_num(w)
+        w = w + attn_mask[None]
+        m = w.amax(-1, keepdim=True)
+        p = torch.exp(w - m)                                 # == softmax(w, dtype=fp32) numerator
+        a = torch.bmm(e.r(p), v) / p.sum(-1, keepdim=True)
+        a = e.r(a).view(B, self.h, T, self.hd).transpose(1, 2).reshape(B, T, D)
+        a = _inner(self.inner_attn_ln)(a)
+        return _linear(e, a, _inner(self.out_proj))
+
+
+class DecoderLayer(nn.Module):
+    """torchscale DecoderLayer, pre-LN (forced by subln), alpha = 1."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu):
+        super().__init__()
+        self.self_attn = MultiheadAttention(cfg, emu)
+        self.self_attn_layer_norm = _wrap(cfg, lambda: nn.LayerNorm(cfg.dim, eps=cfg.eps))
+        self.ffn = _wrap(cfg, lambda: FeedForwardNetwork(cfg, emu))
+        self.final_layer_norm = _wrap(cfg, lambda: nn.LayerNorm(cfg.dim, eps=cfg.eps))
+
+    def forward(self, x, mask):
+        r = x
+        x = self.self_attn(_inner(self.self_attn_layer_norm)(x), mask)
+        x = r + x
+        r = x
+        x = _inner(self.ffn)(_inner(self.final_layer_norm)(x))
+        return r + x
+
+
+class PositionalEmbedding(nn.Embedding):
+    """torchscale.component.embedding.PositionalEmbedding: positions start
+    at 2 ("consistent with fairseq"); only ``x.size(1)`` of the argument is used."""
+
+    def forward(self, x, positions=None):
+        if positions is None:
+            positions = torch.arange(2, x.size(1) + 2, device=x.device).long().unsqueeze(0)
+        return F.embedding(positions, self.weight, self.padding_idx)
+
+
+class Decoder(nn.Module):
+    """torchscale.architecture.decoder.Decoder + the ``passed_x`` patch
+    (/root/reference/README.md:179-193); call sites model.py:186-191,238,242,250."""
+
+    def __init__(self, cfg: OracleConfig, emu: _Emu, embed_tokens, embed_positions, output_projection):
+        super().__init__()
+        self.cfg, self.emu = cfg, emu
+        self.embed_scale = 1.0                               # no_scale_embedding=True
+        self.embed_tokens = embed_tokens
+        self.embed_positions = embed_positions
+        self.output_projection = output_projection
+        self.layers = nn.ModuleList(DecoderLayer(cfg, emu) for _ in range(cfg.layers))
+        self.layer_norm = nn.LayerNorm(cfg.dim, eps=cfg.eps)
+        # sub-LN init (decoder-only): scale sqrt(log(2*layers)) on fc1/fc2/out_proj/v_proj
+        init_scale = math.sqrt(math.log(cfg.layers * 2))
+        for name, p in self.named_parameters():
+            if "fc1" in name or "fc2" in name or "out_proj" in name or "v_proj" in name:
+                p.data.mul_(init_scale)
+
+    def forward_embedding(self, tokens, token_embedding=None, incremental_state=None):
+        positions = self.embed_positions(tokens)
+        if token_embedding is None:
+            token_embedding = self.embed_tokens(tokens)
+        x = embed = self.embed_scale * token_embedding
+        x = x + positions
+        return x, embed                                      # dropout p=0.1 is identity in eval
+
+    def forward(self, prev_output_tokens, **kwargs):
+        if kwargs.get("passed_x", None) is None:
+            x, _ = self.forward_embedding(prev_output_tokens)
+        else:
+            x = kwargs["passed_x"]
+        T = x.size(1)
+        inner_states = [x]
+        for layer in self.layers:
+            mask = torch.triu(torch.zeros([T, T]).float().fill_(float("-inf")).type_as(x), 1)
+            x = layer(x, mask)
+            inner_states.append(x)
+        x = self.layer_norm(x)
+        x = F.linear(self.emu.r(x), self.emu.r(self.output_projection.weight))
+        return x, {"inner_states": inner_states, "l_aux": [None] * len(self.layers), "attn": None}
+
+
+# --------------------------------------------------------------------------- top level
+def _embed_init(emb: nn.Embedding):
+    """bitsandbytes.nn.modules.Embedding.reset_parameters: xavier-uniform, padding row zero."""
+    nn.init.xavier_uniform_(emb.weight)
+    with torch.no_grad():
+        emb.weight[emb.padding_idx].fill_(0)
+
+
+class KosmosOracle(nn.Module):
+    """``kosmosx.model.Kosmos`` (/root/reference/kosmosx/model.py:132-253), random-init CLIP."""
+
+    def __init__(self, cfg: OracleConfig | None = None, emulate_bf16: bool = False):
+        super().__init__()
+        cfg = cfg or OracleConfig()
+        self.cfg = cfg
+        self.emu = _Emu(emulate_bf16)
+        self.clip_model = ClipVisionTower(cfg, self.emu)                       # model.py:154-156
+        self.embed = nn.Embedding(cfg.vocab, cfg.dim, padding_idx=1)           # model.py:161-163
+        _embed_init(self.embed)
+        self.embed_positions = PositionalEmbedding(cfg.max_positions, cfg.dim, 1)   # model.py:164
+        self.output_projection = nn.Linear(cfg.dim, cfg.vocab, bias=False)     # model.py:166-167
+        nn.init.normal_(self.output_projection.weight, mean=0, std=cfg.dim ** -0.5)
+        self.decoder = Decoder(cfg, self.emu, self.embed, self.embed_positions, self.output_projection)
+        self.perceive = PerceiverResampler(cfg, self.emu)                      # model.py:196-203
+        self.image_proj = nn.Linear(cfg.vit_dim, cfg.dim, bias=False)          # model.py:205-206
+        nn.init.normal_(self.image_proj.weight, mean=0, std=cfg.dim ** -0.5)
+
+    def set_emulation(self, on: bool):
+        self.emu.on = on
+
+    def forward(self, text_tokens, images, **kwargs):
+        if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):
+            raise TypeError("text_tokens and images must be instances of torch.Tensor")
+        images = self.clip_model(pixel_values=images)                          # model.py:230
+        images = self.perceive(images).squeeze(1)                              # model.py:231
+        images = F.linear(self.emu.r(images), self.emu.r(self.image_proj.weight))  # model.py:232
+        model_input = self.decoder.forward_embedding(text_tokens)[1]           # model.py:238
+        model_input = torch.cat([model_input[:, 0:2], images, model_input[:, 2:]], dim=1)
+        model_input = self.decoder.forward_embedding(model_input, token_embedding=model_input)[0]
+        return self.decoder(model_input, passed_x=model_input)[0]              # model.py:250
+
+    @torch.no_grad()
+    def stages(self, text_tokens, images):
+        """Intermediate tensors, for per-stage parity tests."""
+        out = {}
+        out["vit"] = self.clip_model(pixel_values=images)
+        out["perceive"] = self.perceive(out["vit"]).squeeze(1)
+        out["image_proj"] = F.linear(self.emu.r(out["perceive"]), self.emu.r(self.image_proj.weight))
+        emb = self.decoder.forward_embedding(text_tokens)[1]
+        x = torch.cat([emb[:, 0:2], out["image_proj"], emb[:, 2:]], dim=1)
+        out["x0"] = self.decoder.forward_embedding(x, token_embedding=x)[0]
+        logits, extra = self.decoder(out["x0"], passed_x=out["x0"])
+        out["inner_states"] = extra["inner_states"]
+        out["logits"] = logits
+        return out
+
+
+class KosmosLanguageOracle(nn.Module):
+    """``kosmosx.model.KosmosLanguage`` (/root/reference/kosmosx/model.py:256-320)."""
+
+    def __init__(self, cfg: OracleConfig | None = None, emulate_bf16: bool = False):
+        super().__init__()
+        cfg = cfg or OracleConfig(vocab=64007, max_positions=2048)
+        self.cfg = cfg
+        self.emu = _Emu(emulate_bf16)
+        self.embed = nn.Embedding(cfg.vocab, cfg.dim, padding_idx=1)
+        _embed_init(self.embed)
+        self.embed_positions = PositionalEmbedding(cfg.max_positions, cfg.dim, 1)
+        self.output_projection = nn.Linear(cfg.dim, cfg.vocab, bias=False)
+        self.decoder = Decoder(cfg, self.emu, self.embed, self.embed_positions, self.output_projection)
+
+    def forward(self, x, **kwargs):
+        model_input = self.decoder.forward_embedding(x, **kwargs)[0]
+        return self.decoder(model_input, passed_x=model_input)[0]
+
+
+# --------------------------------------------------------------------------- helpers
+def make_inputs(cfg: OracleConfig, batch: int, t_text: int, seed: int = 1):
+    """Synthetic inputs as README.md:34-37 / example.py:5-8 of the reference."""
+    g = torch.Generator().manual_seed(seed)
+    text = torch.randint(0, cfg.vocab, (batch, t_text), dtype=torch.long, generator=g)
+    images = torch.randn(batch, 3, cfg.image, cfg.image, generator=g)
+    return text, images
+
+
+def build(cfg: OracleConfig | None = None, seed: int = 0, emulate_bf16: bool = False) -> KosmosOracle:
+    torch.manual_seed(seed)
+    return KosmosOracle(cfg, emulate_bf16).eval()

@@ -1,0 +1,322 @@
+"""GPU bring-up checks for the individual kernels (run under gpurun; one case per process so a
+trap in one kernel cannot poison the others).  Usage: python tools/kernel_check.py <case>|list"""
+import math
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kosmos-x_b200"))
+from kosmosx import _abi, ops  # noqa: E402
+
+dev = "cuda"
+
+
+def blockmap(err, br=8, bc=8):
+    M, N = err.shape
+    rs, cs = max(1, M // br), max(1, N // bc)
+    out = []
+    for i in range(0, M, rs):
+        out.append(" ".join(f"{err[i:i+rs, j:j+cs].max().item():8.2e}" for j in range(0, N, cs)))
+    return "\n".join(out[:br + 1])
+
+
+def report(name, got, ref, tol):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    bad = ~torch.isfinite(got)
+    mx = err[~bad].max().item() if (~bad).any() else float("nan")
+    ok = (not bad.any()) and mx <= tol
+    print(f"[{'OK' if ok else 'FAIL'}] {name}: max_abs_err={mx:.4e} tol={tol:.1e} nonfinite={int(bad.sum())} ref_absmax={ref.abs().max().item():.3f}")
+    if not ok and err.ndim == 2:
+        print(blockmap(torch.where(bad, torch.full_like(err, float('inf')), err)))
+    return ok
+
+
+def gemm_case(cg, bn, M=512, N=512, K=256, **kw):
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
+    ops.gemm(a, w, out, cta_group=cg, block_n=bn, **kw)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T
+    return report(f"gemm cg={cg} bn={bn} M={M} N={N} K={K}", out, ref, 2e-3 * math.sqrt(K))
+
+
+def case_gemm_basic():
+    ok = True
+    for cg, bn in ((1, 128), (1, 256), (2, 128), (2, 256)):
+        ok &= gemm_case(cg, bn, 256, 256, 64)
+        ok &= gemm_case(cg, bn, 512, 512, 256)
+    return ok
+
+
+def case_gemm_shapes():
+    ok = True
+    for cg, bn in ((1, 256), (2, 256), (1, 128), (2, 128)):
+        ok &= gemm_case(cg, bn, 2056, 1024, 1024)        # ViT rows (ragged M)
+        ok &= gemm_case(cg, bn, 300, 1002, 128)          # ragged M and N
+        ok &= gemm_case(cg, bn, 4096, 2048, 2048)
+        ok &= gemm_case(cg, bn, 1024, 770, 640)          # N tail, K not multiple of 64*? (640 = 10 blocks)
+        ok &= gemm_case(cg, bn, 640, 512, 72)            # K tail (72 = 64 + 8)
+    return ok
+
+
+def case_gemm_epilogue():
+    torch.manual_seed(1)
+    ok = True
+    M, N, K = 1000, 768, 512
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev)
+    ref0 = a.float() @ w.float().T + bias
+    for cg in (1, 2):
+        # bias + gelu -> bf16
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        ops.gemm(a, w, out, bias=bias, act=_abi.KX_ACT_GELU, cta_group=cg)
+        ok &= report(f"epi bias+gelu bf16 cg={cg}", out, torch.nn.functional.gelu(ref0), 2e-2)
+        # bias + quick gelu
+        out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        ops.gemm(a, w, out, bias=bias, act=_abi.KX_ACT_QUICK_GELU, cta_group=cg)
+        ok &= report(f"epi bias+quickgelu bf16 cg={cg}", out, ref0 * torch.sigmoid(1.702 * ref0), 2e-2)
+        # bias + residual in place (fp32)
+        x = torch.randn(M, N, device=dev)
+        x0 = x.clone()
+        ops.gemm(a, w, x, bias=bias, res=x, cta_group=cg)
+        ok &= report(f"epi bias+res fp32 in-place cg={cg}", x, ref0 + x0, 1e-2)
+        # scatter rows + positional add: groups of 250 rows -> stride 300, offset 7; table row = r + 3
+        G, stride, off = 250, 300, 7
+        tab = torch.randn(G + 3, N, device=dev)
+        outs = torch.zeros(4 * stride + off, N, device=dev)
+        ops.gemm(a, w, outs, grp=(G, stride, off), add_tab=tab, add_off=3, cta_group=cg)
+        ref = torch.zeros_like(outs)
+        base = a.float() @ w.float().T
+        for g in range(4):
+            ref[g * stride + off: g * stride + off + G] = base[g * G:(g + 1) * G] + tab[3:3 + G]
+        ok &= report(f"epi scatter+pos fp32 cg={cg}", outs, ref, 1e-2)
+        # odd ld fp32 (LM-head style N=1002, ld=1002)
+        w2 = (torch.randn(1002, K, device=dev) / math.sqrt(K)).bfloat16()
+        o2 = torch.zeros(M, 1002, device=dev)
+        ops.gemm(a, w2, o2, cta_group=cg)
+        ok &= report(f"epi fp32 N=1002 cg={cg}", o2, a.float() @ w2.float().T, 1e-2)
+    return ok
+
+
+def xpos_ref(T, device):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import kosmos_oracle as ko
+    xp = ko.XPOS(64)
+    scale, sin, cos = xp.tables(T)
+    return xp, scale.to(device), sin.to(device), cos.to(device)
+
+
+def case_xpos():
+    ok = True
+    for T in (5, 114, 2048):
+        xp, S, sin, cos = xpos_ref(T, dev)
+        inv_freq = (1.0 / (10000 ** (torch.arange(0, 32) / 32))).to(dev)
+        tabs = ops.xpos_tables(xp.scale.to(dev), inv_freq, T, -(T // 2) if T % 2 == 0 else -((T + 1) // 2), 512.0, dev)
+        # python floor: -(T)//2
+        mp = (-T) // 2
+        tabs = ops.xpos_tables(xp.scale.to(dev), inv_freq, T, mp, 512.0, dev)
+        ok &= report(f"xpos q_cos T={T}", tabs[0], cos * S, 2e-6 * max(1.0, (cos * S).abs().max().item()))
+        ok &= report(f"xpos q_sin T={T}", tabs[1], sin * S, 2e-6 * max(1.0, (sin * S).abs().max().item()))
+        ok &= report(f"xpos k_cos T={T}", tabs[2], cos / S, 2e-6 * max(1.0, (cos / S).abs().max().item()))
+        ok &= report(f"xpos k_sin T={T}", tabs[3], sin / S, 2e-6 * max(1.0, (sin / S).abs().max().item()))
+    return ok
+
+
+def case_gemm_qkv():
+    torch.manual_seed(2)
+    ok = True
+    B, T, d = 2, 114, 256
+    M = B * T
+    a = torch.randn(M, d, device=dev).bfloat16()
+    w = (torch.randn(3 * d, d, device=dev) / math.sqrt(d)).bfloat16()
+    bias = torch.randn(3 * d, device=dev)
+    xp, S, sin, cos = xpos_ref(T, dev)
+    inv_freq = (1.0 / (10000 ** (torch.arange(0, 32) / 32))).to(dev)
+    tabs = ops.xpos_tables(xp.scale.to(dev), inv_freq, T, (-T) // 2, 512.0, dev)
+    for cg in (1, 2):
+        out = torch.zeros(M, 3 * d, device=dev, dtype=torch.bfloat16)
+        ops.gemm(a, w, out, bias=bias, xpos=tuple(tabs), seq_len=T, cta_group=cg)
+        ref = a.float() @ w.float().T + bias
+        q, k, v = ref[:, :d], ref[:, d:2 * d], ref[:, 2 * d:]
+        H = d // 64
+        xpd = xp.to(dev)
+
+        def rot(t, down):
+            t = t.view(B, T, H, 64).transpose(1, 2).reshape(B * H, T, 64)
+            t = xpd(t, offset=0, downscale=down)
+            return t.view(B, H, T, 64).transpose(1, 2).reshape(M, d)
+
+        ref2 = torch.cat([rot(q, False), rot(k, True), v], dim=1)
+        ok &= report(f"qkv xpos epilogue cg={cg}", out, ref2, 3e-2)
+    return ok
+
+
+def attn_ref(q, k, v, B, H, T, causal, scale):
+    qh = q.float().view(B, T, H, 64).transpose(1, 2)
+    kh = k.float().view(B, T, H, 64).transpose(1, 2)
+    vh = v.float().view(B, T, H, 64).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) * scale
+    if causal:
+        s = s + torch.triu(torch.full((T, T), float("-inf"), device=q.device), 1)
+    p = s.softmax(-1)
+    return (p @ vh).transpose(1, 2).reshape(B * T, H * 64)
+
+
+def case_attn():
+    torch.manual_seed(3)
+    ok = True
+    for (B, H, T, causal) in ((1, 1, 128, False), (1, 1, 128, True), (2, 2, 114, True), (2, 3, 257, False),
+                              (1, 2, 512, True), (2, 4, 2048, True), (1, 2, 300, True)):
+        qkv = torch.randn(B * T, 3 * H * 64, device=dev).bfloat16()
+        q, k, v = qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:]
+        out = torch.full((B * T, H * 64), float("nan"), device=dev, dtype=torch.bfloat16)
+        ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=causal, scale=0.125)
+        torch.cuda.synchronize()
+        ref = attn_ref(q, k, v, B, H, T, causal, 0.125)
+        ok &= report(f"attn B={B} H={H} T={T} causal={causal}", out, ref, 2e-2)
+    return ok
+
+
+def case_layernorm():
+    torch.manual_seed(4)
+    ok = True
+    for (rows, n, dt) in ((100, 128, torch.float32), (2056, 1024, torch.float32), (1000, 2048, torch.float32),
+                          (777, 2048, torch.bfloat16), (513, 8192, torch.bfloat16), (64, 256, torch.bfloat16),
+                          (10, 16384, torch.float32)):
+        x = (torch.randn(rows, n, device=dev) * 2 + 0.5).to(dt)
+        g = torch.randn(n, device=dev)
+        b = torch.randn(n, device=dev)
+        out = torch.zeros(rows, n, device=dev, dtype=torch.bfloat16)
+        ops.layernorm(x, g, b, out)
+        ref = torch.nn.functional.layer_norm(x.float(), (n,), g, b, 1e-5)
+        ok &= report(f"layernorm rows={rows} n={n} {dt}", out, ref, 4e-2)
+    # pre_add + scatter
+    rows, n = 514, 1024
+    x = torch.randn(rows, n, device=dev)
+    pa = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev); b = torch.randn(n, device=dev)
+    out = torch.zeros(2 * 321, n, device=dev, dtype=torch.bfloat16)
+    ops.layernorm(x, g, b, out, pre_add=pa, grp=(257, 321, 0))
+    ref = torch.zeros(2 * 321, n, device=dev)
+    r = torch.nn.functional.layer_norm(x + pa, (n,), g, b, 1e-5)
+    ref[0:257] = r[0:257]; ref[321:321 + 257] = r[257:]
+    ok &= report("layernorm pre_add+scatter", out, ref, 4e-2)
+    return ok
+
+
+def case_embed():
+    torch.manual_seed(5)
+    ok = True
+    B, t_text, V, D, n_img = 3, 50, 1002, 256, 64
+    T = t_text + n_img
+    tok = torch.randint(0, V, (B, t_text), device=dev)
+    emb = torch.randn(V, D, device=dev); pos = torch.randn(T + 2, D, device=dev)
+    x0 = torch.zeros(B, T, D, device=dev)
+    ops.embed_splice_pos(tok, emb, pos, x0, img_start=2, n_img=n_img)
+    e = emb[tok]
+    ref = torch.cat([e[:, :2], torch.zeros(B, n_img, D, device=dev), e[:, 2:]], 1) + pos[2:T + 2]
+    ref[:, 2:2 + n_img] = 0
+    ok &= report("embed_splice_pos", x0.view(B * T, D), ref.view(B * T, D), 1e-6)
+    # im2col
+    Bi, image, patch, dim = 2, 56, 14, 128
+    px = torch.randn(Bi, 3, image, image, device=dev)
+    g = image // patch
+    kp = 640
+    patches = torch.full((Bi * g * g, kp), 7.0, device=dev, dtype=torch.bfloat16)
+    cls = torch.randn(dim, device=dev); p2 = torch.randn(g * g + 1, dim, device=dev)
+    x = torch.zeros(Bi, g * g + 1, dim, device=dev)
+    ops.im2col_patches(px, patches, cls, p2, x, image=image, patch=patch)
+    ref = torch.nn.functional.unfold(px, patch, stride=patch).transpose(1, 2).reshape(Bi * g * g, 3 * patch * patch)
+    ok &= report("im2col", patches[:, :588], ref.bfloat16(), 0.0)
+    ok &= report("im2col pad", patches[:, 588:], torch.zeros(Bi * g * g, kp - 588, device=dev), 0.0)
+    ok &= report("cls rows", x[:, 0], (cls + p2[0]).expand(Bi, dim), 1e-6)
+    # cast / broadcast
+    s = torch.randn(1000003, device=dev)
+    ok &= report("cast bf16", ops.cast_bf16(s).view(1, -1), s.bfloat16().view(1, -1), 0.0)
+    lat = torch.randn(64, 128, device=dev); dst = torch.zeros(3, 64, 128, device=dev)
+    ops.broadcast_rows(lat, dst, 3)
+    ok &= report("broadcast", dst.view(3, -1), lat.expand(3, 64, 128).reshape(3, -1), 0.0)
+    return ok
+
+
+def case_perceiver_attn():
+    torch.manual_seed(6)
+    B, H, nq, nkv = 2, 8, 64, 321
+    q = torch.randn(B * nq, H * 64, device=dev).bfloat16()
+    kv = torch.randn(B * nkv, 2 * H * 64, device=dev).bfloat16()
+    out = torch.zeros(B * nq, H * 64, device=dev, dtype=torch.bfloat16)
+    ops.perceiver_attention(q, kv, out, batch=B, heads=H, n_q=nq, n_kv=nkv, v_col_off=H * 64, scale=0.125)
+    qh = q.float().view(B, nq, H, 64).transpose(1, 2)
+    kh = kv[:, :H * 64].float().view(B, nkv, H, 64).transpose(1, 2)
+    vh = kv[:, H * 64:].float().view(B, nkv, H, 64).transpose(1, 2)
+    ref = ((qh @ kh.transpose(-1, -2)) * 0.125).softmax(-1) @ vh
+    return report("perceiver xattn", out, ref.transpose(1, 2).reshape(B * nq, H * 64), 2e-2)
+
+
+def bench_gemm(M, N, K, cg, bn, iters=20):
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, out, cta_group=cg, block_n=bn)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.gemm(a, w, out, cta_group=cg, block_n=bn)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * M * N * K / ms / 1e9
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, w.T, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / iters
+    print(f"gemm M={M} N={N} K={K} cg={cg} bn={bn}: {ms*1e3:.1f} us  {tf:.0f} TFLOP/s   (cuBLAS {2.0*M*N*K/ms2/1e9:.0f})")
+
+
+def case_bench():
+    for cg, bn in ((1, 256), (2, 256), (2, 128)):
+        bench_gemm(16384, 6144, 2048, cg, bn)
+        bench_gemm(16384, 2048, 2048, cg, bn)
+        bench_gemm(16384, 8192, 2048, cg, bn)
+        bench_gemm(16384, 2048, 8192, cg, bn)
+    B, H, T = 8, 32, 2048
+    qkv = torch.randn(B * T, 3 * H * 64, device=dev).bfloat16()
+    q, k, v = qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:]
+    out = torch.empty(B * T, H * 64, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fl = 2.0 * B * H * T * T * 64 * 2 / 2
+    print(f"attn causal B={B} H={H} T={T}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s (causal-halved)")
+    return True
+
+
+CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
+
+if __name__ == "__main__":
+    name = sys.argv[1] if len(sys.argv) > 1 else "list"
+    if name == "list":
+        print(" ".join(CASES))
+        sys.exit(0)
+    t0 = time.time()
+    _abi.check(_abi.lib.kx_device_check(), "kx_device_check")
+    ok = CASES[name]()
+    torch.cuda.synchronize()
+    print(f"== case {name}: {'PASS' if ok else 'FAIL'} in {time.time()-t0:.1f}s, launches={ops.launch_count()}")
+    sys.exit(0 if ok else 1)
