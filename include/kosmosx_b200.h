@@ -104,11 +104,13 @@ int kx_perceiver_xattn_fwd(const void* q, long long ld_q, const void* kv, long l
  * or bf16.  eps 1e-5 everywhere in the reference.  Replaces nn.LayerNorm at: [HF]:359,361,
  * 677 (ViT), flamingo norm_media/norm_latents/FF norm/final norm (A.2), torchscale
  * self_attn_layer_norm, inner_attn_ln, final_layer_norm, ffn_layernorm, decoder.layer_norm
- * (A.4).  pre_add ([N] fp32 or NULL) fuses `x + media_pos_emb[:1]` of the perceiver (A.2).
+ * (A.4).  pre_add ([pre_add_rows, N] fp32 or NULL) fuses `x + media_pos_emb[:m]` of the perceiver
+ * (A.2): row (r / pre_add_group) % pre_add_rows is added to input row r (pre_add_group 0 = row 0 always).
+ * out is bf16 (GEMM operand) or fp32 (ViT pre_layrnorm, whose output is the residual stream).
  */
-int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, const float* gamma,
-                     const float* beta, float eps, void* out_bf16, long long ld_out, int rows, int n, int grp_rows,
-                     int grp_stride, int grp_off, kx_stream_t stream);
+int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, int pre_add_group,
+                     int pre_add_rows, const float* gamma, const float* beta, float eps, void* out, int out_is_f32,
+                     long long ld_out, int rows, int n, int grp_rows, int grp_stride, int grp_off, kx_stream_t stream);
 
 /* ---- embedding / splice ----------------------------------------------------------- *
  * x0[b, t, :] for every NON-image row of the spliced sequence (image rows are written by the
@@ -118,10 +120,16 @@ int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* 
  * Replaces Decoder.forward_embedding x2 + torch.cat of model.py:238-244.
  * For KosmosLanguage (model.py:310-320) pass n_img = 0.
  * Token ids outside [0, vocab) set *err_flag (device int, may be NULL) instead of faulting.
+ * pos_table NULL = gather only (the `[1]` result of forward_embedding, model.py:238).
  */
 int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
                         const float* pos_table, int pos_rows, int dim, int img_start, int n_img, float* x0,
                         int* err_flag, kx_stream_t stream);
+
+/* x[b,t,:] = in[b,t,:] + pos_table[t+2,:]: Decoder.forward_embedding(x, token_embedding=x)[0] of
+ * model.py:242-244 as a stand-alone call (the fused path is kx_embed_splice_pos + the image_proj epilogue). */
+int kx_add_positions(const float* in, float* out, int batch, int T, int dim, const float* pos_table, int pos_rows,
+                     kx_stream_t stream);
 
 /* CLIP patch embedding front end ([HF]:202-218): im2col of (B,3,H,W) pixels (fp32) into bf16
  * rows [B*gh*gw, k_pad] (k = c*p*p + dy*p + dx, zero padded to k_pad), and the CLS rows

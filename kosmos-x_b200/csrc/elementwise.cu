@@ -9,11 +9,11 @@ namespace kx {
 // ----------------------------------------------------------------------------- LayerNorm
 // Row statistics exactly as torch.nn.LayerNorm: mean, then biased variance of (x - mean), eps
 // inside the sqrt; fp32 throughout; the row lives in registers between the passes.
-template <bool IN_BF16, int TPR, int MAX_VEC>
+template <bool IN_BF16, bool OUT_F32, int TPR, int MAX_VEC>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __restrict__ pre_add,
-                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                 __nv_bfloat16* __restrict__ out, long long ld_out, int rows, int n, int grp_rows, int grp_stride,
+layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __restrict__ pre_add_tab, int pre_add_group,
+                 int pre_add_rows, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 void* __restrict__ out, long long ld_out, int rows, int n, int grp_rows, int grp_stride,
                  int grp_off) {
     constexpr int ROWS_PER_BLOCK = 256 / TPR;
     __shared__ float red[2][8];
@@ -21,6 +21,10 @@ layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __rest
     const int row = blockIdx.x * ROWS_PER_BLOCK + threadIdx.x / TPR;
     const bool active = row < rows;          // inactive threads still take part in the reductions
     const int nvec = n >> 3;
+    // pre_add row = (row / pre_add_group) % pre_add_rows  (perceiver media_pos_emb[:m])
+    const float* pre_add = nullptr;
+    if (pre_add_tab != nullptr && active)
+        pre_add = pre_add_tab + static_cast<long long>(pre_add_group > 0 ? (row / pre_add_group) % pre_add_rows : 0) * n;
 
     float v[MAX_VEC][8];
     float sum = 0.f;
@@ -100,11 +104,30 @@ layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __rest
             float y[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) y[u] = (v[i][u] - mean) * rstd * g[u] + bb[u];
-            uint4 q;
-            q.x = pack_bf16(y[0], y[1]); q.y = pack_bf16(y[2], y[3]);
-            q.z = pack_bf16(y[4], y[5]); q.w = pack_bf16(y[6], y[7]);
-            *reinterpret_cast<uint4*>(out + orow * ld_out + vi * 8) = q;
+            if constexpr (OUT_F32) {
+                float* o = reinterpret_cast<float*>(out) + orow * ld_out + vi * 8;
+                *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            } else {
+                uint4 q;
+                q.x = pack_bf16(y[0], y[1]); q.y = pack_bf16(y[2], y[3]);
+                q.z = pack_bf16(y[4], y[5]); q.w = pack_bf16(y[6], y[7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + orow * ld_out + vi * 8) = q;
+            }
         }
+    }
+}
+
+// x[b, t, :] = in[b, t, :] + pos[t + 2, :]   (Decoder.forward_embedding with token_embedding given)
+__global__ void __launch_bounds__(256)
+add_positions_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int dim, const float* __restrict__ pos) {
+    const int t = blockIdx.x % T;
+    const float4* a = reinterpret_cast<const float4*>(in + static_cast<long long>(blockIdx.x) * dim);
+    const float4* p = reinterpret_cast<const float4*>(pos + static_cast<long long>(t + 2) * dim);
+    float4* o = reinterpret_cast<float4*>(out + static_cast<long long>(blockIdx.x) * dim);
+    for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
+        const float4 x = a[i], c = __ldg(p + i);
+        o[i] = make_float4(x.x + c.x, x.y + c.y, x.z + c.z, x.w + c.w);
     }
 }
 
@@ -124,8 +147,12 @@ embed_splice_pos_kernel(const long long* __restrict__ tokens, int t_text, const 
         tok = 0;
     }
     const float4* e = reinterpret_cast<const float4*>(embed + tok * dim);
-    const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<long long>(t + 2) * dim);
     float4* o = reinterpret_cast<float4*>(x0 + static_cast<long long>(blockIdx.x) * dim);
+    if (pos == nullptr) {                                   // gather only (forward_embedding(...)[1])
+        for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) o[i] = __ldg(e + i);
+        return;
+    }
+    const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<long long>(t + 2) * dim);
     for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
         const float4 a = __ldg(e + i), c = __ldg(pp + i);
         o[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
@@ -213,46 +240,65 @@ broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, lo
 
 using namespace kx;
 
-extern "C" int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, const float* gamma,
-                                const float* beta, float eps, void* out, long long ld_out, int rows, int n,
-                                int grp_rows, int grp_stride, int grp_off, cudaStream_t stream) {
+extern "C" int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, int pre_add_group,
+                                int pre_add_rows, const float* gamma, const float* beta, float eps, void* out,
+                                int out_is_f32, long long ld_out, int rows, int n, int grp_rows, int grp_stride,
+                                int grp_off, cudaStream_t stream) {
     if (!x || !gamma || !beta || !out) { set_error("kx_layernorm_fwd: null pointer"); return KX_ERR_ARG; }
     if (rows <= 0 || n <= 0 || (n % 8) || n > 32768) { set_error("kx_layernorm_fwd: n=%d must be a multiple of 8 and <= 32768", n); return KX_ERR_ARG; }
     const int in_align = x_is_bf16 ? 8 : 4;
-    if ((ld_x % in_align) || (ld_out % 8) || ((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)gamma & 15) ||
+    if (pre_add && pre_add_group > 0 && pre_add_rows <= 0) { set_error("kx_layernorm_fwd: pre_add_rows must be > 0"); return KX_ERR_ARG; }
+    if ((ld_x % in_align) || (ld_out % (out_is_f32 ? 4 : 8)) || ((uintptr_t)x & 15) || ((uintptr_t)out & 15) || ((uintptr_t)gamma & 15) ||
         ((uintptr_t)beta & 15) || (pre_add && ((uintptr_t)pre_add & 15))) {
         set_error("kx_layernorm_fwd: pointers and row pitches must be 16-byte aligned");
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-#define KX_LN(BF, TPR, MV)                                                                                             \
-    layernorm_kernel<BF, TPR, MV><<<(rows + (256 / TPR) - 1) / (256 / TPR), 256, 0, stream>>>(                          \
-        x, ld_x, pre_add, gamma, beta, eps, o, ld_out, rows, n, grp_rows, grp_stride, grp_off)
-    if (n <= 1024) { if (x_is_bf16) KX_LN(true, 32, 4); else KX_LN(false, 32, 4); }
-    else if (n <= 2048) { if (x_is_bf16) KX_LN(true, 32, 8); else KX_LN(false, 32, 8); }
-    else if (n <= 8192) { if (x_is_bf16) KX_LN(true, 256, 4); else KX_LN(false, 256, 4); }
-    else { if (x_is_bf16) KX_LN(true, 256, 16); else KX_LN(false, 256, 16); }
+#define KX_LN2(BF, OF, TPR, MV)                                                                                        \
+    layernorm_kernel<BF, OF, TPR, MV><<<(rows + (256 / TPR) - 1) / (256 / TPR), 256, 0, stream>>>(                      \
+        x, ld_x, pre_add, pre_add_group, pre_add_rows, gamma, beta, eps, out, ld_out, rows, n, grp_rows, grp_stride, grp_off)
+#define KX_LN(TPR, MV)                                                                                                 \
+    do {                                                                                                               \
+        if (x_is_bf16) { if (out_is_f32) KX_LN2(true, true, TPR, MV); else KX_LN2(true, false, TPR, MV); }              \
+        else { if (out_is_f32) KX_LN2(false, true, TPR, MV); else KX_LN2(false, false, TPR, MV); }                      \
+    } while (0)
+    if (n <= 1024) KX_LN(32, 4);
+    else if (n <= 2048) KX_LN(32, 8);
+    else if (n <= 8192) KX_LN(256, 4);
+    else KX_LN(256, 16);
 #undef KX_LN
+#undef KX_LN2
     return check_launch("kx_layernorm_fwd");
 }
 
 extern "C" int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
                                    const float* pos_table, int pos_rows, int dim, int img_start, int n_img, float* x0,
                                    int* err_flag, cudaStream_t stream) {
-    if (!tokens || !embed_table || !pos_table || !x0) { set_error("kx_embed_splice_pos: null pointer"); return KX_ERR_ARG; }
+    if (!tokens || !embed_table || !x0) { set_error("kx_embed_splice_pos: null pointer"); return KX_ERR_ARG; }
     const int T = t_text + n_img;
     if (batch <= 0 || t_text <= 0 || n_img < 0 || (dim % 4) || img_start < 0 || img_start > t_text) {
         set_error("kx_embed_splice_pos: bad shape (batch=%d t_text=%d n_img=%d dim=%d img_start=%d)", batch, t_text, n_img, dim, img_start);
         return KX_ERR_ARG;
     }
-    if (T + 2 > pos_rows) {
+    if (pos_table && T + 2 > pos_rows) {
         set_error("kx_embed_splice_pos: sequence length %d needs %d position rows, table has %d", T, T + 2, pos_rows);
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
     embed_splice_pos_kernel<<<batch * T, 256, 0, stream>>>(tokens, t_text, embed_table, vocab, pos_table, dim, img_start, n_img, x0, err_flag);
     return check_launch("kx_embed_splice_pos");
+}
+
+extern "C" int kx_add_positions(const float* in, float* out, int batch, int T, int dim, const float* pos_table,
+                                int pos_rows, cudaStream_t stream) {
+    if (!in || !out || !pos_table || batch <= 0 || T <= 0 || (dim % 4)) { set_error("kx_add_positions: bad argument"); return KX_ERR_ARG; }
+    if (T + 2 > pos_rows) {
+        set_error("kx_add_positions: sequence length %d needs %d position rows, table has %d", T, T + 2, pos_rows);
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    add_positions_kernel<<<batch * T, 256, 0, stream>>>(in, out, T, dim, pos_table);
+    return check_launch("kx_add_positions");
 }
 
 extern "C" int kx_im2col_patches(const float* pixels, int batch, int image, int patch, void* patches_bf16, int k_pad,

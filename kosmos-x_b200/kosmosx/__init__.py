@@ -1,0 +1,5 @@
+"""kosmosx — B200-native drop-in for the forward path of kyegomez/Kosmos-X
+(same exports as /root/reference/kosmosx/__init__.py:1-4)."""
+from kosmosx.model import Decoder, Kosmos, KosmosConfig, KosmosLanguage, KosmosTokenizer
+
+__all__ = ["KosmosTokenizer", "Kosmos", "KosmosLanguage", "Decoder", "KosmosConfig"]

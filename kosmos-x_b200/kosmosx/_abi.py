@@ -46,7 +46,8 @@ SIGNATURES = {
     "kx_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, C.POINTER(GemmArgs), _vp]),
     "kx_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "kx_perceiver_xattn_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
-    "kx_layernorm_fwd": (_i, [_vp, _i, _ll, _f32p, _f32p, _f32p, _f, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
+    "kx_layernorm_fwd": (_i, [_vp, _i, _ll, _f32p, _i, _i, _f32p, _f32p, _f, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
+    "kx_add_positions": (_i, [_f32p, _f32p, _i, _i, _i, _f32p, _i, _vp]),
     "kx_embed_splice_pos": (_i, [_vp, _i, _i, _f32p, _i, _f32p, _i, _i, _i, _i, _f32p, _vp, _vp]),
     "kx_im2col_patches": (_i, [_f32p, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
     "kx_xpos_tables": (_i, [_f32p, _f32p, _i, _i, _f, _f32p, _f32p, _f32p, _f32p, _vp]),

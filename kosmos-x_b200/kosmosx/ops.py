@@ -79,17 +79,19 @@ def perceiver_attention(q, kv, out, *, batch, heads, n_q, n_kv, v_col_off, scale
     return out
 
 
-def layernorm(x, gamma, beta, out, *, eps=1e-5, pre_add=None, grp=None, rows=None):
-    """out(bf16) = LayerNorm(x (+ pre_add)) over the last dim; x fp32 or bf16, 2-D."""
-    if x.dtype not in (torch.float32, torch.bfloat16):
-        raise TypeError("layernorm: x must be fp32 or bf16")
+def layernorm(x, gamma, beta, out, *, eps=1e-5, pre_add=None, pre_add_group=0, grp=None, rows=None):
+    """out (bf16 or fp32) = LayerNorm(x (+ pre_add)) over the last dim; x fp32 or bf16, 2-D."""
+    if x.dtype not in (torch.float32, torch.bfloat16) or out.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("layernorm: x / out must be fp32 or bf16")
     _req(x, x.dtype, "x")
-    _req(out, torch.bfloat16, "out")
+    _req(out, out.dtype, "out")
     g = grp or (0, 0, 0)
     r = x.shape[0] if rows is None else rows
+    pa_rows = 0 if pre_add is None else (pre_add.numel() // x.shape[1])
     check(lib.kx_layernorm_fwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _ptr(pre_add),
-                               gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), r,
-                               x.shape[1], g[0], g[1], g[2], _stream()), "kx_layernorm_fwd")
+                               pre_add_group, pa_rows, gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(),
+                               1 if out.dtype == torch.float32 else 0, out.stride(0), r, x.shape[1], g[0], g[1], g[2],
+                               _stream()), "kx_layernorm_fwd")
     return out
 
 
@@ -99,9 +101,17 @@ def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_start, n_img, er
     if not tokens.is_contiguous():
         tokens = tokens.contiguous()
     check(lib.kx_embed_splice_pos(tokens.data_ptr(), B, t_text, embed_table.data_ptr(), embed_table.shape[0],
-                                  pos_table.data_ptr(), pos_table.shape[0], embed_table.shape[1], img_start, n_img,
+                                  _ptr(pos_table), 0 if pos_table is None else pos_table.shape[0],
+                                  embed_table.shape[1], img_start, n_img,
                                   x0.data_ptr(), _ptr(err_flag), _stream()), "kx_embed_splice_pos")
     return x0
+
+
+def add_positions(x_in, x_out, pos_table):
+    B, T, D = x_in.shape
+    check(lib.kx_add_positions(x_in.data_ptr(), x_out.data_ptr(), B, T, D, pos_table.data_ptr(), pos_table.shape[0],
+                               _stream()), "kx_add_positions")
+    return x_out
 
 
 def im2col_patches(pixels, patches, class_embedding, pos_table, x, *, image, patch):

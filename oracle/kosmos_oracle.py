@@ -385,6 +385,7 @@ class MultiheadAttention(nn.Module):
         self.out_proj = _wrap(cfg, lambda: nn.Linear(d, d))
         self.inner_attn_ln = _wrap(cfg, lambda: nn.LayerNorm(d, eps=cfg.eps))
         self.xpos = XPOS(self.hd, cfg.xpos_scale_base)
+        self.use_xpos = True            # tests switch it off to cross-check against HF Kosmos-2's block
 
     def forward(self, x, attn_mask):
         B, T, D = x.shape
@@ -398,8 +399,10 @@ class MultiheadAttention(nn.Module):
             return t.view(B, T, self.h, self.hd).transpose(1, 2).reshape(B * self.h, T, self.hd)
 
         q, k, v = heads(q), heads(k), e.r(heads(v))
-        k = e.r(self.xpos(k, offset=0, downscale=True))
-        q = e.r(self.xpos(q, offset=0, downscale=False))
+        if self.use_xpos:
+            k = self.xpos(k, offset=0, downscale=True)
+            q = self.xpos(q, offset=0, downscale=False)
+        k, q = e.r(k), e.r(q)
         w = torch.bmm(q, k.transpose(1, 2))
         w = torch.nan_to_num(w)
         w = w + attn_mask[None]

@@ -1,0 +1,40 @@
+"""Generates tests/golden/tiny_golden.pt from the oracle (seeded tiny configuration).
+
+The reference holds no golden vectors for this path ("parity unpinned"), so the
+fixtures are minted here from the restatement oracle after it has been pinned against the
+installed HF CLIP tower and HF Kosmos-2 text block (tests/test_oracle.py).  They guard the oracle
+against drift and give the GPU parity tests a fixed target that does not depend on the oracle
+code being importable.   Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import kosmos_oracle as ko  # noqa: E402
+
+
+def main():
+    torch.set_num_threads(4)
+    cfg = ko.OracleConfig.tiny()
+    model = ko.build(cfg, seed=0)
+    cases = {}
+    for name, (B, t_text) in {"b2_t10": (2, 10), "b1_t50": (1, 50), "b3_t130": (3, 130)}.items():
+        text, images = ko.make_inputs(cfg, B, t_text, seed=1)
+        st = model.stages(text, images)
+        model.set_emulation(True)
+        emu = model(text, images)
+        model.set_emulation(False)
+        step = 1 if B * t_text <= 20 else 8              # keep the fixture small: every 8th vocab column
+        cases[name] = dict(B=B, t_text=t_text, col_step=step, vit=st["vit"][:, ::4].half(),
+                           perceive=st["perceive"].half(), x0=st["x0"][:, ::2].half(),
+                           logits=st["logits"][..., ::step].clone(), logits_emu_bf16=emu[..., ::step].clone())
+    torch.save(dict(cfg=cfg.__dict__, seed_weights=0, seed_inputs=1, cases=cases),
+               os.path.join(HERE, "tiny_golden.pt"))
+    print("wrote", os.path.join(HERE, "tiny_golden.pt"), {k: tuple(v["logits"].shape) for k, v in cases.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol declared
+in include/kosmosx_b200.h, entry points fail loudly without a GPU (no CPU fallback), and the
+Python surface mirrors the reference's names / state_dict layout."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "kosmosx_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kosmosx import _abi
+    names = _declared_symbols()
+    assert len(names) >= 12
+    raw = ctypes.CDLL(_abi.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in kosmosx_b200.h but not exported"
+    assert set(names) == set(_abi.SIGNATURES), "ctypes SIGNATURES and header disagree"
+    assert _abi.lib.kx_abi_version() == 1
+
+
+def test_gemm_args_struct_matches_header():
+    from kosmosx import _abi
+    src = open(HEADER).read()
+    body = re.search(r"typedef struct kx_gemm_args \{(.*?)\} kx_gemm_args;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            fields.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+    assert fields == [f[0] for f in _abi.GemmArgs._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_entry_points_fail_loudly_without_gpu():
+    from kosmosx import _abi
+    assert _abi.lib.kx_device_check() == -2
+    assert "no CPU fallback" in _abi.last_error()
+    g = _abi.GemmArgs()
+    g.M = g.N = g.K = 64
+    buf = (ctypes.c_char * 65536)()
+    addr = (ctypes.addressof(buf) + 255) & ~255
+    g.out = addr
+    g.ld_out = 64
+    st = _abi.lib.kx_gemm_bf16(addr, 64, addr, 64, g, None)
+    assert st == -2, _abi.last_error()
+
+
+def test_argument_validation_happens_before_any_launch():
+    from kosmosx import _abi
+    g = _abi.GemmArgs()
+    assert _abi.lib.kx_gemm_bf16(None, 0, None, 0, g, None) == -1
+    assert "null" in _abi.last_error()
+    buf = (ctypes.c_char * 4096)()
+    addr = (ctypes.addressof(buf) + 255) & ~255
+    g.M, g.N, g.K, g.out, g.ld_out = 8, 8, 8, addr, 8
+    assert _abi.lib.kx_gemm_bf16(addr, 7, addr, 8, g, None) == -1          # row pitch not 16-byte aligned
+    assert _abi.lib.kx_layernorm_fwd(addr, 0, 12, None, 0, 0, addr, addr, 1e-5, addr, 0, 16, 4, 12, 0, 0, 0, None) == -1
+    assert "multiple of 8" in _abi.last_error()
+    assert _abi.lib.kx_attn_fwd(addr, addr, addr, 8, addr, 8, 0, 1, 1, 1, 0.125, None) == -1
+
+
+def test_public_surface_matches_reference():
+    import kosmosx
+    import kosmosx.model as m
+    assert set(kosmosx.__all__) >= {"KosmosTokenizer", "Kosmos", "KosmosLanguage"}     # reference __init__.py:4
+    assert hasattr(m, "Decoder")                                                       # train.py:44 imports it
+    import inspect
+    sig = inspect.signature(m.Kosmos.forward)
+    assert list(sig.parameters)[:3] == ["self", "text_tokens", "images"]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY
+               for n, p in inspect.signature(m.Kosmos.__init__).parameters.items() if n != "self")
+    ks = inspect.signature(m.KosmosLanguage.__init__).parameters
+    assert [n for n in ks][1:14] == ["vocab_size", "dim", "depth", "ffn_dim", "dropout", "multiway", "decoder_heads",
+                                     "activation_fn", "subln", "alibi_pos_bias", "alibi_num_heads", "xpos_rel_pos",
+                                     "max_rel_pos"]
+    assert ks["vocab_size"].default == 64007 and ks["depth"].default == 24
+
+
+def test_state_dict_layout_matches_oracle_and_appendix_b(tiny_cfgs):
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos
+    oc, kc = tiny_cfgs
+    torch.manual_seed(0)
+    mine, ref = Kosmos(config=kc), ko.KosmosOracle(oc)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert set(a) == set(b)
+    assert all(a[k].shape == b[k].shape for k in a)
+    for k in ("clip_model.embeddings.class_embedding", "clip_model.pre_layrnorm.weight",
+              "clip_model.encoder.layers.0.self_attn.q_proj.weight", "clip_model.post_layernorm.bias",
+              "embed.weight", "decoder.embed_tokens.weight", "embed_positions.weight", "decoder.embed_positions.weight",
+              "output_projection.weight", "decoder.output_projection.weight",
+              "decoder.layers.1.self_attn.q_proj.A.weight", "decoder.layers.1.self_attn.q_proj.B.bias",
+              "decoder.layers.0.self_attn.inner_attn_ln.A.weight", "decoder.layers.0.self_attn.xpos.scale",
+              "decoder.layers.0.self_attn_layer_norm.B.weight", "decoder.layers.0.ffn.A.fc1.weight",
+              "decoder.layers.0.ffn.B.ffn_layernorm.bias", "decoder.layers.0.final_layer_norm.A.bias",
+              "decoder.layer_norm.weight", "perceive.latents", "perceive.media_pos_emb",
+              "perceive.layers.0.0.norm_media.weight", "perceive.layers.1.0.to_kv.weight",
+              "perceive.layers.0.1.0.weight", "perceive.layers.0.1.1.weight", "perceive.layers.0.1.3.weight",
+              "perceive.norm.bias", "image_proj.weight"):
+        assert k in a, k
+    assert a["embed.weight"].data_ptr() == a["decoder.embed_tokens.weight"].data_ptr()
+    mine.load_state_dict(b)                        # drop-in checkpoint load
+    assert torch.equal(mine.state_dict()["decoder.layers.0.ffn.A.fc1.weight"], b["decoder.layers.0.ffn.A.fc1.weight"])
+
+
+def test_reference_error_behaviour(tiny_cfgs):
+    from kosmosx import Kosmos, KosmosLanguage, KosmosTokenizer
+    _, kc = tiny_cfgs
+    model = Kosmos(config=kc)
+    with pytest.raises(TypeError, match="must be instances of torch.Tensor"):       # model.py:222-227
+        model([1, 2, 3], torch.zeros(1, 3, kc.image, kc.image))
+    with pytest.raises(TypeError):
+        model(torch.zeros(1, 5, dtype=torch.long), "img")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            model(torch.zeros(1, 5, dtype=torch.long), torch.zeros(1, 3, kc.image, kc.image))
+    with pytest.raises(NotImplementedError):
+        KosmosTokenizer()
+    with pytest.raises(NotImplementedError):
+        KosmosLanguage(vocab_size=100, dim=128, depth=1, ffn_dim=128, decoder_heads=2, activation_fn="swish")
+
+
+def test_config_validation():
+    from kosmosx import KosmosConfig
+    with pytest.raises(ValueError):
+        KosmosConfig(dim=2048, heads=16).validate()       # head_dim 128
+    KosmosConfig().validate()
+
+
+def test_full_size_parameter_counts():
+    """SURVEY.md Appendix B counts, on the meta device (no memory)."""
+    from kosmosx import Kosmos
+    m = Kosmos(device="meta")
+    n = lambda mod: sum(p.numel() for p in mod.parameters())
+    assert n(m.clip_model) == 303_179_776
+    assert n(m.perceive) == 21_314_560 + 0
+    assert n(m.image_proj) == 2_097_152
+    assert n(m.embed) == 65_540_096 and n(m.output_projection) == 65_540_096
+    per_layer = sum(p.numel() for name, p in m.decoder.layers[0].named_parameters() if ".B." not in name)
+    assert per_layer == 50_378_752

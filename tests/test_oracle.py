@@ -1,0 +1,218 @@
+"""CPU tests of the oracle: pins against the installed third-party implementations the reference
+calls (HF CLIP tower) or that port the same torchscale layer (HF Kosmos-2 text block), the
+reference's structural facts, and the committed golden vectors."""
+import math
+import os
+
+import pytest
+import torch
+
+import kosmos_oracle as ko
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "tiny_golden.pt")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    torch.set_num_threads(4)
+    cfg = ko.OracleConfig.tiny()
+    return cfg, ko.build(cfg, seed=0)
+
+
+def test_vit_matches_hf_clip(tiny):
+    """The reference's vision tower IS HF CLIPVisionTransformer (model.py:154-156,230)."""
+    transformers = pytest.importorskip("transformers")
+    cfg, model = tiny
+    hc = transformers.CLIPVisionConfig(hidden_size=cfg.vit_dim, intermediate_size=cfg.vit_mlp,
+                                       num_hidden_layers=cfg.vit_layers, num_attention_heads=cfg.vit_heads,
+                                       patch_size=cfg.patch, image_size=cfg.image, hidden_act="gelu",
+                                       attn_implementation="eager")
+    hf = transformers.CLIPVisionModel(hc).vision_model.eval()
+    tower = ko.ClipVisionTower(cfg, ko._Emu(False)).eval()
+    tower.load_state_dict(hf.state_dict(), strict=True)          # identical parameter names
+    _, images = ko.make_inputs(cfg, 2, 5)
+    with torch.no_grad():
+        a = hf(pixel_values=images)["last_hidden_state"]
+        b = tower(images)
+    assert a.shape == (2, cfg.vit_tokens, cfg.vit_dim)
+    assert (a - b).abs().max() < 1e-5
+
+
+def test_vit_quick_gelu_matches_hf():
+    transformers = pytest.importorskip("transformers")
+    cfg = ko.OracleConfig.tiny(vit_act="quick_gelu")
+    hc = transformers.CLIPVisionConfig(hidden_size=cfg.vit_dim, intermediate_size=cfg.vit_mlp,
+                                       num_hidden_layers=cfg.vit_layers, num_attention_heads=cfg.vit_heads,
+                                       patch_size=cfg.patch, image_size=cfg.image, hidden_act="quick_gelu",
+                                       attn_implementation="eager")
+    hf = transformers.CLIPVisionModel(hc).vision_model.eval()
+    tower = ko.ClipVisionTower(cfg, ko._Emu(False)).eval()
+    tower.load_state_dict(hf.state_dict(), strict=True)
+    _, images = ko.make_inputs(cfg, 1, 5)
+    with torch.no_grad():
+        assert (hf(pixel_values=images)["last_hidden_state"] - tower(images)).abs().max() < 1e-5
+
+
+def test_vit_rejects_wrong_image_size(tiny):
+    cfg, model = tiny
+    with pytest.raises(ValueError):
+        model.clip_model(torch.zeros(1, 3, cfg.image + 14, cfg.image))
+
+
+def test_subln_layer_matches_hf_kosmos2_block(tiny):
+    """torchscale's sub-LN DecoderLayer (A.4) vs HF's Kosmos-2 port of it (same parameter names),
+    xPos switched off because Kosmos-2 uses sinusoidal absolute positions instead."""
+    pytest.importorskip("transformers")
+    from transformers.models.kosmos2.configuration_kosmos2 import Kosmos2TextConfig
+    from transformers.models.kosmos2.modeling_kosmos2 import Kosmos2TextBlock
+    cfg, _ = tiny
+    torch.manual_seed(3)
+    layer = ko.DecoderLayer(cfg, ko._Emu(False)).eval()
+    layer.self_attn.use_xpos = False
+    hc = Kosmos2TextConfig(embed_dim=cfg.dim, attention_heads=cfg.heads, ffn_dim=cfg.ffn, layers=1, dropout=0.0,
+                           attention_dropout=0.0, activation_function="gelu")
+    hc._attn_implementation = "eager"
+    blk = Kosmos2TextBlock(hc, layer_idx=0).eval()
+    sd = {k.replace(".A.", "."): v for k, v in layer.state_dict().items() if ".B." not in k and "xpos" not in k}
+    blk.load_state_dict(sd, strict=True)
+    T = 11
+    x = torch.randn(2, T, cfg.dim)
+    mask = torch.triu(torch.full((T, T), float("-inf")), 1)
+    with torch.no_grad():
+        a = layer(x, mask)
+        b = blk(x, attention_mask=mask[None, None].expand(2, 1, T, T))
+        b = b[0] if isinstance(b, tuple) else b
+    assert (a - b).abs().max() < 1e-5
+
+
+def test_xpos_is_relative():
+    """q_t . k_u after xPos depends on t-u only."""
+    xp = ko.XPOS(64)
+    torch.manual_seed(0)
+    q = torch.randn(1, 1, 64).expand(1, 33, 64)
+    k = torch.randn(1, 1, 64).expand(1, 33, 64)
+    s = xp(q, downscale=False)[0] @ xp(k, downscale=True)[0].T
+    for d in (0, 1, 5, 17):
+        diag = torch.diagonal(s, -d)
+        assert (diag - diag[0]).abs().max() < 1e-4 * max(1.0, diag.abs().max().item())
+
+
+def test_xpos_min_pos_uses_floor_division():
+    xp = ko.XPOS(64)
+    for T, mp in ((114, -57), (5, -3), (2048, -1024)):
+        scale, _, _ = xp.tables(T)
+        want = xp.scale ** (torch.tensor(float(mp)) / 512)
+        assert torch.allclose(scale[0], want, rtol=1e-6)
+        assert scale.shape == (T, 32)
+
+
+def test_readme_example_shape_and_image_rows(tiny):
+    """README.md:29-53 / example.py: (B, T_text) tokens + one image -> (B, T_text+64, vocab); image
+    features occupy rows 2..65 (model.py:239-241)."""
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 1, 50)
+    with torch.no_grad():
+        st = model.stages(text, images)
+        st2 = model.stages(text, images * 0.5)
+    assert st["logits"].shape == (1, 114, cfg.vocab)
+    changed = (st["x0"] - st2["x0"]).abs().amax(-1)[0] > 0
+    assert changed[2:66].all() and not changed[:2].any() and not changed[66:].any()
+
+
+def test_causality(tiny):
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 1, 20)
+    text2 = text.clone()
+    text2[0, 12:] = (text2[0, 12:] + 7) % cfg.vocab            # spliced rows >= 12+64 change
+    with torch.no_grad():
+        a, b = model(text, images), model(text2, images)
+    assert (a[0, :76] - b[0, :76]).abs().max() < 1e-5
+    assert (a[0, 76:] - b[0, 76:]).abs().max() > 1e-3
+
+
+def test_batch_independence(tiny):
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 3, 12)
+    with torch.no_grad():
+        full = model(text, images)
+        one = model(text[1:2], images[1:2])
+    assert (full[1:2] - one).abs().max() < 1e-4
+
+
+def test_multiway_b_branch_is_inert(tiny):
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 1, 8)
+    with torch.no_grad():
+        a = model(text, images)
+        saved = {n: p.clone() for n, p in model.named_parameters() if ".B." in n}
+        assert len(saved) > 0
+        for n, p in model.named_parameters():
+            if ".B." in n:
+                p.add_(1.0)
+        b = model(text, images)
+        for n, p in model.named_parameters():
+            if ".B." in n:
+                p.copy_(saved[n])
+    assert torch.equal(a, b)
+
+
+def test_passed_x_skips_embedding(tiny):
+    """README.md:179-193: with passed_x the decoder does not embed prev_output_tokens."""
+    cfg, model = tiny
+    x = torch.randn(1, 7, cfg.dim)
+    with torch.no_grad():
+        a = model.decoder(torch.zeros(1, 7, dtype=torch.long), passed_x=x)[0]
+        b = model.decoder(torch.ones(1, 7, dtype=torch.long) * 5, passed_x=x)[0]
+        c = model.decoder(torch.ones(1, 7, dtype=torch.long) * 5)[0]
+    assert torch.equal(a, b) and not torch.allclose(a, c)
+
+
+def test_position_table_limit(tiny):
+    cfg, model = tiny
+    T = cfg.max_positions - 1                                  # needs rows up to T+1 > table
+    with pytest.raises((IndexError, RuntimeError)):
+        model.decoder.forward_embedding(torch.zeros(1, T, dtype=torch.long))
+
+
+def test_sub_ln_init_scale():
+    cfg = ko.OracleConfig.tiny()
+    torch.manual_seed(0)
+    m = ko.KosmosOracle(cfg)
+    s = math.sqrt(math.log(2 * cfg.layers))
+    fc1 = m.decoder.layers[0].ffn.A.fc1.weight
+    q = m.decoder.layers[0].self_attn.q_proj.A.weight
+    bound = 1 / math.sqrt(cfg.dim)
+    assert fc1.abs().max() > bound * 1.01 and fc1.abs().max() <= bound * s * 1.0001
+    assert q.abs().max() <= bound * 1.0001
+
+
+def test_language_model_oracle():
+    cfg = ko.OracleConfig.tiny(vocab=777)
+    torch.manual_seed(0)
+    m = ko.KosmosLanguageOracle(cfg).eval()
+    with torch.no_grad():
+        y = m(torch.randint(0, 777, (2, 9)))
+    assert y.shape == (2, 9, 777)
+
+
+def test_emulation_changes_little_but_something(tiny):
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 1, 10)
+    with torch.no_grad():
+        a = model(text, images)
+        model.set_emulation(True)
+        b = model(text, images)
+        model.set_emulation(False)
+    d = (a - b).abs().max().item()
+    assert 0 < d < 0.1 * a.abs().max().item()
+
+
+def test_oracle_matches_golden(tiny):
+    cfg, model = tiny
+    g = torch.load(GOLDEN)
+    assert g["cfg"] == cfg.__dict__
+    for name, c in g["cases"].items():
+        text, images = ko.make_inputs(cfg, c["B"], c["t_text"], seed=g["seed_inputs"])
+        with torch.no_grad():
+            y = model(text, images)
+        assert (y[..., ::c["col_step"]] - c["logits"]).abs().max() < 2e-4, name
