@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — multimodal tokens/s of the Kosmos-X forward path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one ``Kosmos.forward(text_tokens, images)`` over one batch of synthetic input at
+BASELINE.json configs[2]: B=8 sequences per GPU, spliced sequence length 2048 (1984 text tokens +
+64 image latents), one 224x224 image per sequence, random-init weights of the reference
+architecture (ViT-L/14 + PerceiverResampler + 24-layer d=2048 sub-LN/xPos decoder + 32002-wide head).
+The position table is built with 2050 rows because the reference's 2048-row table caps T at 2046
+(SURVEY.md fact 6); everything else is the reference configuration.
+
+Rank 0 prints ONE JSON line.  Keys beyond the base contract:
+  roofline      dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time of its launches,
+                measured in an instrumented step right after the timed region, vs MEASURED_PEAKS.json
+  decoder_block BASELINE.json configs[1]: one fused decoder layer (B=8, T=2048) TFLOP/s and fraction of peak
+  breakdown     per-kernel-class share of one step (ms)
+  cpu_baseline  the oracle (CPU restatement of the reference path) timed on this box's host cores, N=1 only
+  e2e           same metric through Kosmos.forward with pinned HOST buffers: per step H2D of tokens+images
+                and D2H of the full logits, all inside the timed region
+``--impl reference`` times the oracle on the host cores (the reference's own dependencies are not
+installable offline: SURVEY.md §8(c)); it is the only other place bench.py executes oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "kosmos-x_b200"))
+
+METRIC = "multimodal tokens/sec (seq=2048, 224^2 img), Kosmos.forward"
+UNIT = "tokens/s"
+SEQ = 2048
+N_LATENTS = 64
+T_TEXT = SEQ - N_LATENTS
+BATCH_PER_GPU = 8
+VOCAB = 32002
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(burst=float(p["bf16_tflops"]), sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def forward_flops_per_seq(T=SEQ, images=1):
+    """2mnk per GEMM, decoder attention causal-halved."""
+    d, f, L = 2048, 8192, 24
+    dec_layer = 24 * T * d * d + 2 * T * T * d
+    dec = L * dec_layer + 2 * T * d * VOCAB
+    vit = 162.02e9 * images
+    per = 4.115e9 * images
+    return dec + vit + per, dec_layer
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU reference (oracle)
+def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0):
+    """The reference path restated on the CPU (oracle/kosmos_oracle.py), fp32, all host threads.
+    One step = ONE sequence of the benchmark workload (T=2048, one image): 1/8 of a GPU step."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kosmos_oracle as ko
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ko.OracleConfig(max_positions=SEQ + 2, multiway=False)    # .B branches never execute
+    model = ko.build(cfg, seed=0)
+    small = ko.make_inputs(cfg, 1, 50, seed=1)
+    text, images = ko.make_inputs(cfg, 1, T_TEXT, seed=1)
+    times = []
+    t_begin = time.perf_counter()
+    with torch.no_grad():
+        model(*small)                                              # page in weights / thread pool
+        warmup = min(warmup, 1)                                    # one full-size warm-up pass is enough on a CPU
+        for i in range(warmup + steps):
+            if i >= warmup + 1 and time.perf_counter() - t_begin > budget_s:
+                break                                              # bounded sample: stop once the budget is spent
+            t0 = time.perf_counter()
+            out = model(text, images)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert out.shape == (1, SEQ, VOCAB)
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=SEQ / (ms / 1e3), ms_per_step=ms, steps_done=len(times), cores=cores,
+                sample=f"1 sequence (T={SEQ}: {T_TEXT} text tokens + 1 image) per step, fp32 eager PyTorch oracle, "
+                       f"{cores} threads, {len(times)} timed step(s)")
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = cpu_reference(args.steps, max(args.warmup, 0))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps_done"], "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2] sample: Kosmos.forward on 1 sequence, seq=2048 (1984 text + 64 image latents), "
+                               "1 image 224x224, CPU", "global_batch": 1, "seq_len": SEQ, "parallelism": "cpu"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference deps (torchscale+passed_x patch, flamingo_pytorch, bitsandbytes) are not installable "
+                "offline; this is the oracle restatement of the reference path (kind=port)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    from kosmosx import Kosmos, KosmosConfig, ops
+    from kosmosx import dist as kdist
+    rank, local, world = kdist.init_from_env("nccl")
+    if world != args.gpus:
+        if rank == 0:
+            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun for N>1", file=sys.stderr)
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = _peaks()
+    B = BATCH_PER_GPU
+
+    torch.manual_seed(0)                                   # same replicated random-init weights on every rank
+    model = Kosmos(config=KosmosConfig(max_positions=SEQ + 2), device=dev, cuda_graph=args.graph)
+    g = torch.Generator().manual_seed(1 + rank)            # each rank owns its shard of the global batch
+    h_text = torch.randint(0, VOCAB, (B, T_TEXT), dtype=torch.long, generator=g).pin_memory()
+    h_img = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    d_text, d_img = h_text.to(dev), h_img.to(dev)
+
+    def step_resident():
+        return model(d_text, d_img)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_resident()
+    torch.cuda.synchronize()
+    assert out.shape == (B, SEQ, VOCAB)
+    model.check_tokens()
+    del out
+
+    # ---- timed region 1: inputs resident in HBM ("value")
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kdist.barrier(); torch.cuda.synchronize()
+    if sampler: sampler.start()
+    n0 = ops.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize(); kdist.barrier()
+    launches = ops.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    ms_total = kdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_step = ms_total / args.steps
+    tokens_per_step = B * SEQ * world
+    value = tokens_per_step / (ms_step / 1e3)
+
+    # ---- timed region 2: end to end through the public API with host buffers ("e2e")
+    # H2D of this step's tokens+images from pinned memory, forward, D2H of the full fp32 logits into pinned
+    # memory.  The D2H runs on a copy stream from one of two logits buffers so it overlaps the next forward.
+    copy_stream = torch.cuda.Stream(dev)
+    h_out = [torch.empty(B, SEQ, VOCAB, dtype=torch.float32).pin_memory() for _ in range(2)]
+    d_keep = [None, None]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def step_e2e(i):
+        s = i & 1
+        t = h_text.to(dev, non_blocking=True)
+        im = h_img.to(dev, non_blocking=True)
+        torch.cuda.current_stream().wait_event(done[s])        # the logits slot written now was copied out (step i-2)
+        logits = model(t, im)
+        d_keep[s] = logits                                     # keep alive until its copy is done
+        logits.record_stream(copy_stream)
+        ready = torch.cuda.Event(); ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            h_out[s].copy_(logits, non_blocking=True)
+            done[s].record(copy_stream)
+
+    for i in range(2):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    kdist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    copy_stream.synchronize()
+    torch.cuda.current_stream().wait_stream(copy_stream)
+    e1.record()
+    torch.cuda.synchronize(); kdist.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = kdist.max_over_ranks(max(e0.elapsed_time(e1), wall_ms), dev) / args.steps
+    e2e_value = tokens_per_step / (e2e_ms / 1e3)
+    h2d = h_text.numel() * 8 + h_img.numel() * 4
+    d2h = B * SEQ * VOCAB * 4
+    checksum = float(h_out[(args.steps - 1) & 1][0, -1, :8].sum())
+    d_keep[:] = [None, None]
+
+    # ---- instrumented step: per-kernel CUDA-event times (roofline leg), graph off
+    was_graph, model.cuda_graph = model.cuda_graph, False
+    model(d_text, d_img); torch.cuda.synchronize()
+    ops.profile_begin()
+    for _ in range(2):
+        model(d_text, d_img)
+    recs = ops.profile_end()
+    model.cuda_graph = was_graph
+    agg = {}
+    for kind, fl, by, ms in recs:
+        a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += fl; a[2] += by; a[3] += ms
+    tot_ms = sum(a[3] for a in agg.values())
+    gemm = agg["gemm"]
+    gemm_tflops = gemm[1] / (gemm[3] * 1e-3) / 1e12
+    breakdown = {k: {"launches_per_step": a[0] // 2, "ms_per_step": a[3] / 2, "share": a[3] / tot_ms,
+                     **({"tflops": a[1] / (a[3] * 1e-3) / 1e12} if a[1] else {"gbs": a[2] / (a[3] * 1e-3) / 1e9})}
+                 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][3])}
+
+    # ---- configs[1]: one decoder layer alone (B=8, T=2048)
+    dec = model.decoder
+    x = torch.randn(B * SEQ, 2048, device=dev)
+    one = dec._pack()["layers"][:1]
+    dec_block_ms = _time_decoder_block(torch, dec, one, x, B)
+    flops_seq, dec_layer_flops = forward_flops_per_seq()
+    blk_tflops = dec_layer_flops * B / (dec_block_ms * 1e-3) / 1e12
+
+    step_tflops = flops_seq * B / (ms_step * 1e-3) / 1e12        # per GPU
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "configs[2]: full Kosmos forward (ViT-L/14 + perceiver + 24-layer decoder + LM head), "
+                               "B=8 per GPU, seq=2048 (1984 text + 64 image latents), 1 image 224x224 per sequence, "
+                               "random-init weights, max_positions=2050",
+                   "global_batch": B * world, "seq_len": SEQ, "parallelism": f"dp{world}",
+                   "l2": "no flush needed: each step streams 3.3 GB of weights and >10 GB of activations (L2 = 126 MB)",
+                   "cuda_graph": bool(args.graph)},
+        "step_tflops_per_gpu": step_tflops,
+        "step_frac_of_bf16_peak": {"burst": step_tflops / peaks["burst"], "sustained": step_tflops / peaks["sustained"]},
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (all Linear layers, %d launches/step)" % (gemm[0] // 2),
+                     "achieved": gemm_tflops, "peak": peaks["sustained"], "peak_burst": peaks["burst"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / peaks["sustained"], "frac_of_burst": gemm_tflops / peaks["burst"],
+                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                     "traffic": None, "share_of_step": gemm[3] / tot_ms},
+        "decoder_block": {"config": "configs[1]: one decoder layer, B=8, T=2048, d=2048, 32 heads, bf16",
+                          "ms": dec_block_ms, "tflops": blk_tflops, "frac_of_burst": blk_tflops / peaks["burst"],
+                          "frac_of_sustained": blk_tflops / peaks["sustained"]},
+        "breakdown": breakdown,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "result": "full fp32 logits copied to pinned host memory "
+                "(double-buffered on a copy stream)", "checksum": checksum},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and rank == 0 and not args.no_cpu:
+        del x
+        r = cpu_reference(1, 0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"], "ms_per_sample": r["ms_per_step"]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    kdist.barrier()
+
+
+def _time_decoder_block(torch, dec, one_layer, x, B, iters=10):
+    """configs[1]: the per-layer launch sequence of Decoder.run_layers on one layer."""
+    packed = dec._packed
+    saved = packed["layers"]
+    packed["layers"] = one_layer
+    try:
+        run = lambda: dec.run_layers(x, B, SEQ, head=False)
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    finally:
+        packed["layers"] = saved
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graph", type=int, default=1, help="replay the forward as one CUDA graph (default on)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.steps < 1:
+        ap.error("--steps must be >= 1")
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")))
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -338,9 +338,9 @@ class Decoder(nn.Module):
         if tokens.dtype != torch.int64:
             raise TypeError("token ids must be int64")
 
-    def run_layers(self, x: torch.Tensor, B: int, T: int, logits: torch.Tensor | None = None):
+    def run_layers(self, x: torch.Tensor, B: int, T: int, logits: torch.Tensor | None = None, head: bool = True):
         """24 x (sub-LN attention + sub-LN FFN) in place on the fp32 residual stream x [B*T, D],
-        then final LayerNorm + LM head -> fp32 logits [B*T, vocab]."""
+        then (``head``) final LayerNorm + LM head -> fp32 logits [B*T, vocab]."""
         cfg, p, ws = self.cfg, self._pack(), self._ws
         M, D, F, H = B * T, cfg.dim, cfg.ffn, cfg.heads
         dev = x.device
@@ -362,6 +362,8 @@ class Decoder(nn.Module):
             ops.gemm(h, L["w_fc1"], mid, bias=L["b_fc1"], act=_abi.KX_ACT_GELU)
             ops.layernorm(mid, *L["ln_ffn"], midn, eps=cfg.eps)
             ops.gemm(midn, L["w_fc2"], x, bias=L["b_fc2"], res=x)
+        if not head:
+            return x
         ops.layernorm(x, *p["ln_out"], h, eps=cfg.eps)
         if logits is None:
             logits = torch.empty(M, p["w_out"].shape[0], dtype=torch.float32, device=dev)
@@ -615,25 +617,32 @@ class Kosmos(_KosmosBase):
 
     # ---- CUDA graph replay ----------------------------------------------------------------
     def _forward_graphed(self, text_tokens, images):
+        """One captured graph per input shape and per output slot.  Two output slots alternate, so the
+        logits returned by a call stay valid until the second-next call with the same shapes (lets a
+        caller overlap a device->host copy of the result with the next forward)."""
         key = (tuple(text_tokens.shape), tuple(images.shape))
         g = self._graphs.get(key)
         if g is None:
             st_tok, st_img = text_tokens.clone(), images.clone()
             B, t_text = text_tokens.shape
             M = B * (t_text + self.cfg.p_latents)
-            st_out = torch.empty(M, self.cfg.vocab, dtype=torch.float32, device=text_tokens.device)
-            self._forward_impl(st_tok, st_img, st_out)            # warm-up: stages weights, allocates workspaces
+            outs = [torch.empty(M, self.cfg.vocab, dtype=torch.float32, device=text_tokens.device) for _ in range(2)]
+            self._forward_impl(st_tok, st_img, outs[0])           # warm-up: stages weights, allocates workspaces
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._forward_impl(st_tok, st_img, st_out)
-            g = (graph, st_tok, st_img, st_out)
+            graphs = []
+            for o in outs:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._forward_impl(st_tok, st_img, o)
+                graphs.append(graph)
+            g = [graphs, st_tok, st_img, outs, 0]
             self._graphs[key] = g
-        graph, st_tok, st_img, st_out = g
+        graphs, st_tok, st_img, outs, slot = g
+        g[4] = slot ^ 1
         st_tok.copy_(text_tokens)
         st_img.copy_(images)
-        graph.replay()
-        return st_out
+        graphs[slot].replay()
+        return outs[slot]
 
 
 class KosmosLanguage(_KosmosBase):

@@ -11,6 +11,45 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- optional per-launch timing (bench.py's roofline leg) -------------------------------------
+# When a list is installed with profile_begin(), every wrapper brackets its launch with CUDA
+# events on the launching stream and appends (kind, flops, bytes, start, end).  Off by default.
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> list of (kind, flops, bytes, milliseconds); synchronises."""
+    global _prof
+    recs, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    return [(k, fl, by, e0.elapsed_time(e1)) for k, fl, by, e0, e1 in recs]
+
+
+class _Timed:
+    __slots__ = ("kind", "flops", "bytes", "e0")
+
+    def __init__(self, kind, flops=0.0, nbytes=0.0):
+        self.kind, self.flops, self.bytes = kind, flops, nbytes
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.kind, self.flops, self.bytes, self.e0, e1))
+        return False
+
+
 def _ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -55,7 +94,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
         g.seq_len = seq_len
         g.d_model = g.N // 3
     g.cta_group, g.block_n, g.max_ctas = cta_group, block_n, max_ctas
-    check(lib.kx_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), g, _stream()), "kx_gemm_bf16")
+    with _Timed("gemm", 2.0 * g.M * g.N * g.K,
+                2.0 * (g.M + g.N) * g.K + g.M * g.N * (out.element_size() + (4 if res is not None else 0))):
+        check(lib.kx_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), g, _stream()), "kx_gemm_bf16")
     return out
 
 
@@ -65,17 +106,20 @@ def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale):
         _req(t, torch.bfloat16, n)
     if not (q.stride(0) == k.stride(0) == v.stride(0)):
         raise ValueError("attention: q, k, v must share a row pitch")
-    check(lib.kx_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
-                          batch, heads, seq_len, 1 if causal else 0, float(scale), _stream()), "kx_attn_fwd")
+    fl = 4.0 * batch * heads * seq_len * seq_len * 64 * (0.5 if causal else 1.0)
+    with _Timed("attn_causal" if causal else "attn_full", fl, 8.0 * batch * heads * seq_len * 64):
+        check(lib.kx_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                              batch, heads, seq_len, 1 if causal else 0, float(scale), _stream()), "kx_attn_fwd")
     return out
 
 
 def perceiver_attention(q, kv, out, *, batch, heads, n_q, n_kv, v_col_off, scale):
     for n, t in (("q", q), ("kv", kv), ("out", out)):
         _req(t, torch.bfloat16, n)
-    check(lib.kx_perceiver_xattn_fwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), v_col_off, out.data_ptr(),
-                                     out.stride(0), batch, heads, n_q, n_kv, float(scale), _stream()),
-          "kx_perceiver_xattn_fwd")
+    with _Timed("perceiver_xattn", 4.0 * batch * heads * n_q * n_kv * 64):
+        check(lib.kx_perceiver_xattn_fwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), v_col_off,
+                                         out.data_ptr(), out.stride(0), batch, heads, n_q, n_kv, float(scale),
+                                         _stream()), "kx_perceiver_xattn_fwd")
     return out
 
 
@@ -88,10 +132,11 @@ def layernorm(x, gamma, beta, out, *, eps=1e-5, pre_add=None, pre_add_group=0, g
     g = grp or (0, 0, 0)
     r = x.shape[0] if rows is None else rows
     pa_rows = 0 if pre_add is None else (pre_add.numel() // x.shape[1])
-    check(lib.kx_layernorm_fwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _ptr(pre_add),
-                               pre_add_group, pa_rows, gamma.data_ptr(), beta.data_ptr(), float(eps), out.data_ptr(),
-                               1 if out.dtype == torch.float32 else 0, out.stride(0), r, x.shape[1], g[0], g[1], g[2],
-                               _stream()), "kx_layernorm_fwd")
+    with _Timed("layernorm", 0.0, float(r) * x.shape[1] * (x.element_size() + out.element_size())):
+        check(lib.kx_layernorm_fwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _ptr(pre_add),
+                                   pre_add_group, pa_rows, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                   out.data_ptr(), 1 if out.dtype == torch.float32 else 0, out.stride(0), r,
+                                   x.shape[1], g[0], g[1], g[2], _stream()), "kx_layernorm_fwd")
     return out
 
 
@@ -100,10 +145,11 @@ def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_start, n_img, er
     B, t_text = tokens.shape
     if not tokens.is_contiguous():
         tokens = tokens.contiguous()
-    check(lib.kx_embed_splice_pos(tokens.data_ptr(), B, t_text, embed_table.data_ptr(), embed_table.shape[0],
-                                  _ptr(pos_table), 0 if pos_table is None else pos_table.shape[0],
-                                  embed_table.shape[1], img_start, n_img,
-                                  x0.data_ptr(), _ptr(err_flag), _stream()), "kx_embed_splice_pos")
+    with _Timed("embed_splice_pos", 0.0, 12.0 * B * t_text * embed_table.shape[1]):
+        check(lib.kx_embed_splice_pos(tokens.data_ptr(), B, t_text, embed_table.data_ptr(), embed_table.shape[0],
+                                      _ptr(pos_table), 0 if pos_table is None else pos_table.shape[0],
+                                      embed_table.shape[1], img_start, n_img,
+                                      x0.data_ptr(), _ptr(err_flag), _stream()), "kx_embed_splice_pos")
     return x0
 
 
@@ -116,9 +162,10 @@ def add_positions(x_in, x_out, pos_table):
 
 def im2col_patches(pixels, patches, class_embedding, pos_table, x, *, image, patch):
     _req(pixels, torch.float32, "pixels")
-    check(lib.kx_im2col_patches(pixels.data_ptr(), pixels.shape[0], image, patch, patches.data_ptr(), patches.shape[1],
-                                class_embedding.data_ptr(), pos_table.data_ptr(), x.data_ptr(), x.shape[-1], _stream()),
-          "kx_im2col_patches")
+    with _Timed("im2col", 0.0, 6.0 * pixels.numel()):
+        check(lib.kx_im2col_patches(pixels.data_ptr(), pixels.shape[0], image, patch, patches.data_ptr(),
+                                    patches.shape[1], class_embedding.data_ptr(), pos_table.data_ptr(), x.data_ptr(),
+                                    x.shape[-1], _stream()), "kx_im2col_patches")
     return patches
 
 

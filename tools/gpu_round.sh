@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# One gpurun call: GPU parity tests, bench, ncu launch list + full captures.  Logs under gpurun_out/<tag>/.
+# Usage: tools/gpu_round.sh <tag> [tests] [bench] [launches] [ncu_gemm] [ncu_attn] [smoke]
+cd "$(dirname "$0")/.."
+tag="${1:-r1}"; shift || true
+what="${*:-smoke tests bench launches ncu_gemm ncu_attn}"
+out="gpurun_out/$tag"; mkdir -p "$out"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > "$out/gpu.txt" 2>&1
+nproc >> "$out/gpu.txt"; free -g | head -2 >> "$out/gpu.txt"
+for w in $what; do
+  case $w in
+    smoke)    timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; echo "smoke exit $?" | tee -a "$out/summary.txt"; tail -2 "$out/smoke.log";;
+    tests)    timeout 1500 python -m pytest tests -m gpu -x -q -s > "$out/pytest_gpu.log" 2>&1; echo "pytest exit $?" | tee -a "$out/summary.txt"; grep -E "max=|passed|failed|Error|error|FAIL|agreement" "$out/pytest_gpu.log" | tail -40;;
+    bench)    timeout 900 python bench.py --steps 10 --warmup 3 > "$out/bench.json" 2> "$out/bench.err"; echo "bench exit $?" | tee -a "$out/summary.txt"; cat "$out/bench.json"; tail -5 "$out/bench.err";;
+    benchng)  timeout 900 python bench.py --steps 10 --warmup 3 --graph 0 --no-cpu > "$out/bench_nograph.json" 2> "$out/bench_nograph.err"; echo "bench(nograph) exit $?" | tee -a "$out/summary.txt"; cat "$out/bench_nograph.json"; tail -5 "$out/bench_nograph.err";;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 650 -c 420 --csv --log-file "$out/launches.csv" python tools/profile_step.py --steps 3 > "$out/launches.log" 2>&1; echo "launches exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/launches.log";;
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 4 -o "$out/prof_gemm" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_gemm.log" 2>&1; echo "ncu_gemm exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_gemm.log";;
+    ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
+    kcheck)   bash tools/run_kernel_checks.sh bench;;
+  esac
+done
