@@ -14,6 +14,7 @@
 // blocks above the diagonal are skipped.
 #include "kx_internal.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace kx {
 
@@ -279,6 +280,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace kx
 
+namespace kx {
+int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
+                   int heads, int seq_len, int causal, float scale, cudaStream_t stream);   // attention_pp.cu
+// KX_ATTN_IMPL=0 selects the first-generation kernel of this file (kept for A/B measurements).
+static int attn_impl() {
+    static int impl = -1;
+    if (impl < 0) {
+        const char* e = getenv("KX_ATTN_IMPL");
+        impl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return impl;
+}
+}  // namespace kx
+
 using namespace kx;
 
 extern "C" int kx_attn_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
@@ -290,6 +305,7 @@ extern "C" int kx_attn_fwd(const void* q, const void* k, const void* v, long lon
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    if (attn_impl() == 1) return launch_attn_pp(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stream);
     const unsigned long long rows = (unsigned long long)batch * seq_len;
     CUtensorMap tq, tk, tv;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * AT_D, rows, ld_qkv * 2, AT_D, AT_BM)) return KX_ERR_TMAP;

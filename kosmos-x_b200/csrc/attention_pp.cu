@@ -1,0 +1,324 @@
+// attn_pp_kernel: flash-attention forward, head_dim 64, "ping-pong" variant (the default path of
+// kx_attn_fwd; attention.cu keeps the first-generation kernel, selectable with KX_ATTN_IMPL=0).
+//
+// Same contract as attention.cu (torchscale MultiheadAttention core, SURVEY.md A.4 / HF CLIPAttention
+// [HF] modeling_clip.py:318-331), reorganised around what limited the first kernel (ncu, profiles/):
+// issue slots and TMEM re-reads in the softmax, not the tensor pipe.
+//
+// One CTA = TWO 128-row query tiles (A, B) of one (batch, head) sharing every K/V block; 1 CTA/SM.
+//   warps 0-3  softmax of tile A   } thread == query row.  S row read ONCE from TMEM into registers
+//   warps 4-7  softmax of tile B   } (128 fp32), max with 3-input FMNMX, exp2 on packed FFMA2 operands,
+//                                    P (bf16 pairs) written back over S in TMEM with tcgen05.st
+//   warp 8     TMA producer: Q tiles once, K/V 128-row blocks through 3-slot rings
+//   warp 9     MMA issuer: S_w = Q_w.K^T (SS) and O_w += P_w.V (A operand = P in TMEM, TS form);
+//              while one tile's softmax runs, the tensor core works on the other tile
+// O accumulates in TMEM across blocks.  The running maximum is only "committed" (O and l rescaled)
+// when a new block raises it by more than 2^8 (lazy rescale): exp2 arguments stay <= 8, so P fits
+// bf16 and the final O/l is unchanged mathematically.
+#include "kx_internal.h"
+#include "ptx.cuh"
+
+namespace kx {
+
+constexpr int PP_THREADS = 384;                     // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
+constexpr int PP_TILE_BYTES = 128 * 64 * 2;          // one [128 x 64] bf16 tile
+constexpr int PP_KV_STAGES = 3;
+constexpr int PP_SMEM_Q = 0;                                              // 2 tiles
+constexpr int PP_SMEM_K = PP_SMEM_Q + 2 * PP_TILE_BYTES;
+constexpr int PP_SMEM_V = PP_SMEM_K + PP_KV_STAGES * PP_TILE_BYTES;
+constexpr int PP_SMEM_BAR = PP_SMEM_V + PP_KV_STAGES * PP_TILE_BYTES;
+constexpr int PP_SMEM_BYTES = PP_SMEM_BAR + 256;
+constexpr int PP_TMEM_COLS = 512;                    // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+constexpr float PP_RESCALE_THRESHOLD = 8.0f;         // log2 units
+
+struct AttnPPParams {
+    __nv_bfloat16* out;
+    long long ld_out;
+    int seq_len, heads, num_pairs;
+    float scale_log2;                                // scale * log2(e)
+};
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PP_SMEM_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;                      // [3]
+    uint64_t* k_empty = bars + 4;                     // [3]
+    uint64_t* v_full = bars + 7;                      // [3]
+    uint64_t* v_empty = bars + 10;                    // [3]
+    uint64_t* s_full = bars + 13;                     // [2] per tile
+    uint64_t* p_full = bars + 15;                     // [2]
+    uint64_t* o_full = bars + 17;                     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int pair = p.num_pairs - 1 - blockIdx.y;    // heaviest (longest KV range) pairs are scheduled first
+    const int head = blockIdx.x % p.heads;
+    const int b = blockIdx.x / p.heads;
+    const int T = p.seq_len;
+    const int nkv = (T + 127) >> 7;
+    const int nblk0 = CAUSAL ? min(2 * pair + 1, nkv) : nkv;
+    const int nblk1 = CAUSAL ? min(2 * pair + 2, nkv) : nkv;
+    const int row_base = b * T;
+    const int q0 = pair * 256;
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023) { printf("kx attn_pp: dynamic smem base not 1024-aligned\n"); __trap(); }
+        mbar_init(q_full, 1);
+        for (int i = 0; i < PP_KV_STAGES; ++i) {
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+        }
+        for (int w = 0; w < 2; ++w) {
+            mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 128); mbar_init(&o_full[w], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 8) {
+        if (lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); }
+        tmem_alloc<1>(tmem_slot, PP_TMEM_COLS);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");       // hand registers to the softmax warpgroups
+        if (warp == 8 && lane == 0) {
+            // ================= TMA producer =================
+            mbar_arrive_expect_tx(q_full, 2 * PP_TILE_BYTES);
+            tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q, head * 64, row_base + q0, kEvictFirst);
+            tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q + PP_TILE_BYTES, head * 64, row_base + q0 + 128, kEvictFirst);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nblk1; ++j) {
+                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[s], PP_TILE_BYTES);
+                tma_load_2d(&tmK, &k_full[s], smem + PP_SMEM_K + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[s], PP_TILE_BYTES);
+                tma_load_2d(&tmV, &v_full[s], smem + PP_SMEM_V + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
+                if (++s == PP_KV_STAGES) { s = 0; ph ^= 1; }
+            }
+        } else if (warp == 9 && lane == 0) {
+            // ================= MMA issuer =================
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM)    x V (MN-major)
+            auto issue_s = [&](int w, int slot) {
+                const uint64_t qdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_Q + w * PP_TILE_BYTES));
+                const uint64_t kdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_K + slot * PP_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16<1>(tmem_base + w * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+            };
+            auto issue_pv = [&](int w, int slot, bool first) {
+                const uint64_t vdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_V + slot * PP_TILE_BYTES), PP_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)      // 16 keys per step: 8 TMEM columns of P, 16 V rows = 2 KB
+                    umma_bf16_ts(tmem_base + 256 + w * 64, tmem_base + w * 128 + k * 8, vdesc + k * (2048 >> 4), idesc_o,
+                                 (!first || k != 0) ? 1u : 0u);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            umma_commit(&s_full[0]);
+            issue_s(1, 0);
+            umma_commit(&s_full[1]);
+            umma_commit(&k_empty[0]);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nblk1; ++j) {
+                int sn = s + 1;
+                uint32_t phn = ph;
+                if (sn == PP_KV_STAGES) { sn = 0; phn ^= 1; }
+                mbar_wait(&v_full[s], ph);
+                if (j < nblk0) {
+                    mbar_wait(&p_full[0], j & 1);
+                    tc_fence_after();
+                    issue_pv(0, s, j == 0);
+                    umma_commit(&o_full[0]);
+                    if (j + 1 < nblk0) {
+                        mbar_wait(&k_full[sn], phn);
+                        tc_fence_after();
+                        issue_s(0, sn);
+                        umma_commit(&s_full[0]);
+                    }
+                }
+                mbar_wait(&p_full[1], j & 1);
+                tc_fence_after();
+                issue_pv(1, s, j == 0);
+                umma_commit(&o_full[1]);
+                umma_commit(&v_empty[s]);
+                if (j + 1 < nblk1) {
+                    mbar_wait(&k_full[sn], phn);
+                    tc_fence_after();
+                    issue_s(1, sn);
+                    umma_commit(&s_full[1]);
+                    umma_commit(&k_empty[sn]);
+                }
+                s = sn;
+                ph = phn;
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        // ================= softmax / output: warps 0-3 tile A, warps 4-7 tile B; thread == query row ==========
+        const int w = warp >> 2;
+        const int r = (warp & 3) * 32 + lane;
+        const int qrow = q0 + w * 128 + r;
+        const int nblk = w ? nblk1 : nblk0;
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t tmem_s = tmem_base + lane_addr + w * 128;
+        const uint32_t tmem_o = tmem_base + lane_addr + 256 + w * 64;
+        const float sl2 = p.scale_log2;
+        const uint64_t sl2x2 = pack_f32x2(sl2, sl2);
+        float m_ref = -INFINITY;      // reference maximum the exponentials are taken against (raw score units)
+        float l_run = 0.f;
+
+        for (int j = 0; j < nblk; ++j) {
+            const int kv0 = j * 128;
+            mbar_wait(&s_full[w], j & 1);
+            tc_fence_after();
+            uint32_t sv[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[c * 32]));
+            tmem_ld_wait();
+
+            // ---- mask: only the diagonal block (causal) and the ragged tail block
+            const bool need_mask = (kv0 + 128 > T) || (CAUSAL && (kv0 + 127 > q0 + w * 128));
+            if (need_mask) {
+                int limit = T - kv0;
+                if (CAUSAL) limit = min(limit, qrow - kv0 + 1);
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= limit) sv[i] = 0xff800000u;          // -inf
+            }
+            // ---- row max (4 independent chains of 3-input max)
+            float mx0 = __uint_as_float(sv[0]), mx1 = __uint_as_float(sv[1]), mx2 = __uint_as_float(sv[2]),
+                  mx3 = __uint_as_float(sv[3]);
+#pragma unroll
+            for (int i = 4; i < 128; i += 8) {
+                mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+                mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+                if (i + 4 < 128) {
+                    mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+                    mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+                }
+            }
+            const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            const float m_new = fmaxf(m_ref, m_blk);
+
+            if (j == 0) {
+                m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+            } else {
+                const bool grow = (m_new - m_ref) * sl2 > PP_RESCALE_THRESHOLD;     // false when m_new == m_ref
+                if (__any_sync(0xffffffffu, grow)) {
+                    // commit the new maximum: O (in TMEM, complete up to block j-1) and l are rescaled
+                    const float alpha = (m_new == m_ref) ? 1.f : ex2_approx((m_ref - m_new) * sl2);
+                    mbar_wait(&o_full[w], (j - 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        uint32_t ov[32];
+                        tmem_ld32(tmem_o + hlf * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                        tmem_st32(tmem_o + hlf * 32, ov);
+                    }
+                    l_run *= alpha;
+                    m_ref = m_new;
+                }
+            }
+
+            // ---- p = exp2(s*scale - m_ref*scale): packed FFMA2, MUFU ex2, packed row sum, bf16x2 pack
+            const float nm = -m_ref * sl2;
+            const uint64_t nm2 = pack_f32x2(nm, nm);
+            uint64_t acc0 = 0ull, acc1 = 0ull;         // (0.f, 0.f)
+            uint32_t pv[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const uint64_t x = ffma2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2x2, nm2);
+                float x0, x1;
+                unpack_f32x2(x, x0, x1);
+                const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+                const uint64_t e = pack_f32x2(e0, e1);
+                if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+                pv[i] = pack_bf16(e0, e1);
+            }
+            float a0, a1;
+            unpack_f32x2(fadd2(acc0, acc1), a0, a1);
+            l_run += a0 + a1;
+            // P over S: columns [0,64) of this tile's S region, element pair (2c, 2c+1) in column c
+            tmem_st32(tmem_s, reinterpret_cast<uint32_t(&)[32]>(pv[0]));
+            tmem_st32(tmem_s + 32, reinterpret_cast<uint32_t(&)[32]>(pv[32]));
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[w]);
+        }
+
+        // ---- epilogue: O / l -> bf16, head-merged token-major output
+        mbar_wait(&o_full[w], (nblk - 1) & 1);
+        tc_fence_after();
+        uint32_t ov[64];
+        tmem_ld32(tmem_o, reinterpret_cast<uint32_t(&)[32]>(ov[0]));
+        tmem_ld32(tmem_o + 32, reinterpret_cast<uint32_t(&)[32]>(ov[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        if (qrow < T) {
+            const float inv_l = 1.0f / l_run;
+            __nv_bfloat16* o = p.out + static_cast<long long>(row_base + qrow) * p.ld_out + head * 64;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                uint4 q;
+                q.x = pack_bf16(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
+                q.y = pack_bf16(__uint_as_float(ov[8 * g + 2]) * inv_l, __uint_as_float(ov[8 * g + 3]) * inv_l);
+                q.z = pack_bf16(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
+                q.w = pack_bf16(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
+                *reinterpret_cast<uint4*>(o + 8 * g) = q;
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<1>(tmem_base, PP_TMEM_COLS);
+}
+
+int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
+                   int heads, int seq_len, int causal, float scale, cudaStream_t stream) {
+    const unsigned long long rows = (unsigned long long)batch * seq_len;
+    CUtensorMap tq, tk, tv;
+    if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
+    if (!make_tmap_bf16_2d(&tk, k, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
+    if (!make_tmap_bf16_2d(&tv, v, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
+    AttnPPParams p;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.ld_out = ld_out;
+    p.seq_len = seq_len;
+    p.heads = heads;
+    p.num_pairs = (seq_len + 255) / 256;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        cudaError_t e2 = cudaFuncSetAttribute(attn_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("kx_attn_fwd: cudaFuncSetAttribute failed"); return KX_ERR_LAUNCH; }
+        attr_set = true;
+    }
+    if (p.num_pairs > 65535) { set_error("kx_attn_fwd: sequence too long"); return KX_ERR_ARG; }
+    dim3 grid(heads * batch, p.num_pairs);
+    if (causal) attn_pp_kernel<true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    else attn_pp_kernel<false><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    return check_launch("kx_attn_fwd");
+}
+
+}  // namespace kx

@@ -9,7 +9,9 @@ namespace kx {
 // ----------------------------------------------------------------------------- LayerNorm
 // Row statistics exactly as torch.nn.LayerNorm: mean, then biased variance of (x - mean), eps
 // inside the sqrt; fp32 throughout; the row lives in registers between the passes.
-template <bool IN_BF16, bool OUT_F32, int TPR, int MAX_VEC>
+// EXACT: n == TPR * MAX_VEC * 8, so every load is unconditional and all of a thread's 16-byte loads are
+// issued back to back before the first use (memory-level parallelism is what bounds this kernel).
+template <bool IN_BF16, bool OUT_F32, int TPR, int MAX_VEC, bool EXACT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __restrict__ pre_add_tab, int pre_add_group,
                  int pre_add_rows, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -28,6 +30,52 @@ layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __rest
 
     float v[MAX_VEC][8];
     float sum = 0.f;
+    if constexpr (EXACT) {
+        const long long lrow = active ? row : (rows - 1);      // inactive threads re-read the last row, never store
+        if constexpr (IN_BF16) {
+            uint4 raw[MAX_VEC];
+            const uint4* px = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + lrow * ld_x);
+#pragma unroll
+            for (int i = 0; i < MAX_VEC; ++i) raw[i] = px[tr + i * TPR];
+#pragma unroll
+            for (int i = 0; i < MAX_VEC; ++i) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 f = __bfloat1622float2(h[u]);
+                    v[i][2 * u] = f.x; v[i][2 * u + 1] = f.y;
+                }
+            }
+        } else {
+            const float4* px = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + lrow * ld_x);
+            float4 raw[MAX_VEC][2];
+#pragma unroll
+            for (int i = 0; i < MAX_VEC; ++i) {
+                raw[i][0] = px[(tr + i * TPR) * 2];
+                raw[i][1] = px[(tr + i * TPR) * 2 + 1];
+            }
+#pragma unroll
+            for (int i = 0; i < MAX_VEC; ++i) {
+                v[i][0] = raw[i][0].x; v[i][1] = raw[i][0].y; v[i][2] = raw[i][0].z; v[i][3] = raw[i][0].w;
+                v[i][4] = raw[i][1].x; v[i][5] = raw[i][1].y; v[i][6] = raw[i][1].z; v[i][7] = raw[i][1].w;
+            }
+        }
+        if (pre_add_tab != nullptr) {
+            const float* pa = pre_add_tab + static_cast<long long>(pre_add_group > 0 ? (lrow / pre_add_group) % pre_add_rows : 0) * n;
+#pragma unroll
+            for (int i = 0; i < MAX_VEC; ++i) {
+                const int vi = tr + i * TPR;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(pa + vi * 8));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(pa + vi * 8 + 4));
+                v[i][0] += a.x; v[i][1] += a.y; v[i][2] += a.z; v[i][3] += a.w;
+                v[i][4] += b.x; v[i][5] += b.y; v[i][6] += b.z; v[i][7] += b.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAX_VEC; ++i)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sum += v[i][u];
+    } else
 #pragma unroll
     for (int i = 0; i < MAX_VEC; ++i) {
         const int vi = tr + i * TPR;
@@ -77,7 +125,7 @@ layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __rest
 #pragma unroll
     for (int i = 0; i < MAX_VEC; ++i) {
         const int vi = tr + i * TPR;
-        if (active && vi < nvec) {
+        if (EXACT || (active && vi < nvec)) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) { const float d = v[i][u] - mean; sq += d * d; }
         }
@@ -94,7 +142,7 @@ layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __rest
 #pragma unroll
     for (int i = 0; i < MAX_VEC; ++i) {
         const int vi = tr + i * TPR;
-        if (vi < nvec) {
+        if (EXACT || vi < nvec) {
             const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
             const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
@@ -254,9 +302,11 @@ extern "C" int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, co
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-#define KX_LN2(BF, OF, TPR, MV)                                                                                        \
-    layernorm_kernel<BF, OF, TPR, MV><<<(rows + (256 / TPR) - 1) / (256 / TPR), 256, 0, stream>>>(                      \
+#define KX_LN3(BF, OF, TPR, MV, EX)                                                                                    \
+    layernorm_kernel<BF, OF, TPR, MV, EX><<<(rows + (256 / TPR) - 1) / (256 / TPR), 256, 0, stream>>>(                  \
         x, ld_x, pre_add, pre_add_group, pre_add_rows, gamma, beta, eps, out, ld_out, rows, n, grp_rows, grp_stride, grp_off)
+#define KX_LN2(BF, OF, TPR, MV)                                                                                        \
+    do { if (n == (TPR) * (MV) * 8) KX_LN3(BF, OF, TPR, MV, true); else KX_LN3(BF, OF, TPR, MV, false); } while (0)
 #define KX_LN(TPR, MV)                                                                                                 \
     do {                                                                                                               \
         if (x_is_bf16) { if (out_is_f32) KX_LN2(true, true, TPR, MV); else KX_LN2(true, false, TPR, MV); }              \
@@ -268,6 +318,7 @@ extern "C" int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, co
     else KX_LN(256, 16);
 #undef KX_LN
 #undef KX_LN2
+#undef KX_LN3
     return check_launch("kx_layernorm_fwd");
 }
 

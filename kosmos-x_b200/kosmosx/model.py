@@ -632,16 +632,19 @@ class Kosmos(_KosmosBase):
             graphs = []
             for o in outs:
                 graph = torch.cuda.CUDAGraph()
+                n0 = ops.launch_count()
                 with torch.cuda.graph(graph):
                     self._forward_impl(st_tok, st_img, o)
+                nodes = ops.launch_count() - n0
                 graphs.append(graph)
-            g = [graphs, st_tok, st_img, outs, 0]
+            g = [graphs, st_tok, st_img, outs, 0, nodes]
             self._graphs[key] = g
-        graphs, st_tok, st_img, outs, slot = g
+        graphs, st_tok, st_img, outs, slot, nodes = g
         g[4] = slot ^ 1
         st_tok.copy_(text_tokens)
         st_img.copy_(images)
         graphs[slot].replay()
+        ops.count_graph_replay(nodes)
         return outs[slot]
 
 

@@ -190,5 +190,16 @@ def broadcast_rows(src, dst, copies):
     return dst
 
 
+_graph_launches = 0
+
+
+def count_graph_replay(n: int) -> None:
+    """A captured CUDA graph holding `n` of this library's kernels was replayed."""
+    global _graph_launches
+    _graph_launches += n
+
+
 def launch_count() -> int:
-    return int(lib.kx_launch_count())
+    """Kernels of libkosmosx_sm100.so launched so far: direct launches (counted inside the library)
+    plus kernels replayed from captured graphs."""
+    return int(lib.kx_launch_count()) + _graph_launches

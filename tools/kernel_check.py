@@ -171,15 +171,23 @@ def attn_ref(q, k, v, B, H, T, causal, scale):
 def case_attn():
     torch.manual_seed(3)
     ok = True
-    for (B, H, T, causal) in ((1, 1, 128, False), (1, 1, 128, True), (2, 2, 114, True), (2, 3, 257, False),
-                              (1, 2, 512, True), (2, 4, 2048, True), (1, 2, 300, True)):
-        qkv = torch.randn(B * T, 3 * H * 64, device=dev).bfloat16()
+    for (B, H, T, causal, qs) in ((1, 1, 128, False, 1), (1, 1, 128, True, 1), (2, 2, 114, True, 1), (2, 3, 257, False, 1),
+                                  (1, 2, 512, True, 1), (2, 4, 2048, True, 1), (1, 2, 300, True, 1),
+                                  (1, 2, 640, True, 1), (2, 2, 256, False, 1), (3, 2, 1000, True, 1), (1, 1, 1, True, 1),
+                                  # large scores: the running maximum keeps growing -> exercises the O/l rescale path
+                                  (2, 2, 1024, True, 8), (1, 2, 777, False, 8), (1, 3, 2048, True, 4)):
+        qkv = torch.randn(B * T, 3 * H * 64, device=dev)
+        qkv[:, :H * 64] *= qs
+        # make later keys systematically larger so the maximum rises block after block
+        if qs > 1:
+            qkv[:, H * 64:2 * H * 64] *= torch.linspace(0.2, 1.5, B * T, device=dev)[:, None]
+        qkv = qkv.bfloat16()
         q, k, v = qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:]
         out = torch.full((B * T, H * 64), float("nan"), device=dev, dtype=torch.bfloat16)
         ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=causal, scale=0.125)
         torch.cuda.synchronize()
         ref = attn_ref(q, k, v, B, H, T, causal, 0.125)
-        ok &= report(f"attn B={B} H={H} T={T} causal={causal}", out, ref, 2e-2)
+        ok &= report(f"attn B={B} H={H} T={T} causal={causal} qscale={qs}", out, ref, 2e-2)
     return ok
 
 
@@ -289,21 +297,31 @@ def case_bench():
         bench_gemm(16384, 2048, 2048, cg, bn)
         bench_gemm(16384, 8192, 2048, cg, bn)
         bench_gemm(16384, 2048, 8192, cg, bn)
-    B, H, T = 8, 32, 2048
+    return case_bench_attn()
+
+
+def case_bench_attn():
+    for B, H, T, causal in ((8, 32, 2048, True), (8, 16, 257, False), (1, 32, 114, True)):
+        bench_attn(B, H, T, causal)
+    return True
+
+
+def bench_attn(B, H, T, causal):
     qkv = torch.randn(B * T, 3 * H * 64, device=dev).bfloat16()
     q, k, v = qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:]
     out = torch.empty(B * T, H * 64, device=dev, dtype=torch.bfloat16)
     for _ in range(3):
-        ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125)
+        ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=causal, scale=0.125)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125)
+        ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=causal, scale=0.125)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    fl = 2.0 * B * H * T * T * 64 * 2 / 2
-    print(f"attn causal B={B} H={H} T={T}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s (causal-halved)")
+    fl = 2.0 * B * H * T * T * 64 * 2 / (2 if causal else 1)
+    print(f"attn causal={causal} B={B} H={H} T={T}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s "
+          f"({'causal-halved' if causal else 'full'}) impl={os.environ.get('KX_ATTN_IMPL', '1')}")
     return True
 
 
