@@ -73,6 +73,7 @@ typedef struct kx_gemm_args {
     int cta_group;                /* 0 = auto, 1 = single CTA tiles, 2 = cta_group::2 pairs */
     int block_n;                  /* 0 = auto, 128 or 256 */
     int max_ctas;                 /* 0 = all SMs */
+    int epi_mode;                 /* 0 = auto (staged TMA-store epilogue when alignment allows), 1 = direct stores */
 } kx_gemm_args;
 
 int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const kx_gemm_args* args,

@@ -23,16 +23,25 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 
-template <int CG, int BN>
+// TMA_EPI: the epilogue stages each warp's 32-row x 128-byte sub-tile in swizzled shared memory and
+// writes it with cp.async.bulk.tensor (coalesced, asynchronous); the fp32 residual sub-tile is
+// prefetched the same way.  Costs 16 KB of staging per epilogue warp, taken from the operand ring.
+constexpr int EPI_STAGE_BYTES = 32 * 128;                    // 32 rows x 128 B
+constexpr int EPI_WARP_BYTES = 4 * EPI_STAGE_BYTES;          // out[2] + res[2]
+
+template <int CG, int BN, bool TMA_EPI>
 struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_ROWS = BN / CG;
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr int EPI_BYTES = TMA_EPI ? 4 * EPI_WARP_BYTES : 0;
+    static constexpr int RING_BUDGET = TMA_EPI ? (160 * 1024) : (192 * 1024);
+    static constexpr int STAGES = RING_BUDGET / STAGE_BYTES;
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
     static constexpr int TMEM_COLS = 2 * BN;                                    // power of two for BN in {64,128,256}
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct GemmEpi {
@@ -63,13 +72,9 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_
     n_blk = r / gsz;
 }
 
-template <bool OUT_F32, int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t (&v)[32], int m, int n0) {
-    float f[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-    const bool full = (n0 + 32 <= ep.N);
-
+// bias -> [xPos rotation] -> activation on one 32-column chunk of row m (shared by both store paths)
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32], int m, int n0, bool full) {
     if (ep.bias != nullptr) {
         if (full) {
 #pragma unroll
@@ -111,11 +116,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t
 
     if (ep.act == KX_ACT_GELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        for (int i = 0; i < 32; i += 2) gelu_erf_x2(f[i], f[i + 1]);
     } else if (ep.act == KX_ACT_QUICK_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
     }
+}
+
+template <bool OUT_F32, int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t (&v)[32], int m, int n0) {
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    const bool full = (n0 + 32 <= ep.N);
+    epilogue_math<EPI>(ep, f, m, n0, full);
 
     long long orow = m;
     int prow = 0;
@@ -189,23 +203,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t
     }
 }
 
-template <int CG, int BN, bool OUT_F32, int EPI>
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const GemmEpi ep) {
-    using Cfg = GemmCfg<CG, BN>;
+    using Cfg = GemmCfg<CG, BN, TMA_EPI>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment (identical offset in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;          // 1024-aligned (stage sizes are multiples of 1 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* resbar = bars + 2 * STAGES + 4;                      // [4 warps][2 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -215,6 +232,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if constexpr (TMA_EPI) {
+            prefetch_tmap(&tmOut);
+            if (ep.res != nullptr) prefetch_tmap(&tmRes);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -225,6 +246,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], CG * 128);   // every epilogue thread of every CTA, on the leader's barrier
         }
+        for (int i = 0; i < 8; ++i) mbar_init(&resbar[i], 1);
         fence_mbar_init();
     }
     if constexpr (CG == 2) cluster_sync_all();
@@ -306,26 +328,131 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= epilogue =================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         int it = 0;
-        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-            int m_blk, n_blk;
-            tile_coords(t, num_m, num_n, m_blk, n_blk);
-            const int a = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
-            const int m = m_blk * (BLOCK_M * CG) + rank * BLOCK_M + q * 32 + lane;
-            const int nb = n_blk * BN;
-            mbar_wait(&tfull[a], aph);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+        if constexpr (!TMA_EPI) {
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                int m_blk, n_blk;
+                tile_coords(t, num_m, num_n, m_blk, n_blk);
+                const int a = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                const int m = m_blk * (BLOCK_M * CG) + rank * BLOCK_M + q * 32 + lane;
+                const int nb = n_blk * BN;
+                mbar_wait(&tfull[a], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                if (nb + c * 32 >= ep.N) break;       // warp-uniform
-                uint32_t v[32];
-                tmem_ld32(taddr + c * 32, v);
-                tmem_ld_wait();
-                if (m < ep.M) epilogue_chunk<OUT_F32, EPI>(ep, v, m, nb + c * 32);
+                for (int c = 0; c < BN / 32; ++c) {
+                    if (nb + c * 32 >= ep.N) break;       // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    if (m < ep.M) epilogue_chunk<OUT_F32, EPI>(ep, v, m, nb + c * 32);
+                }
+                tc_fence_before();
+                if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
             }
-            tc_fence_before();
-            if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
+        } else {
+            // Staged epilogue: registers -> swizzled smem (this warp's private 32 x 128 B buffers) -> TMA store.
+            // fp32 out: one store per 32-column chunk; bf16 out: one store per two chunks (64 columns = 128 B).
+            uint8_t* st_out = smem_epi + q * EPI_WARP_BYTES;
+            uint8_t* st_res = st_out + 2 * EPI_STAGE_BYTES;
+            uint64_t* rbar = resbar + q * 2;
+            const bool has_res = (ep.res != nullptr);
+            const int sw = lane & 7;
+            uint8_t* my_out = st_out + lane * 128;
+            const uint8_t* my_res = st_res + lane * 128;
+            uint32_t nstore = 0, nres_issued = 0, nres_used = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                int m_blk, n_blk;
+                tile_coords(t, num_m, num_n, m_blk, n_blk);
+                const int a = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                const int m_row0 = m_blk * (BLOCK_M * CG) + rank * BLOCK_M + q * 32;
+                const int m = m_row0 + lane;
+                const int nb = n_blk * BN;
+                const int nchunks = min(BN / 32, (ep.N - nb + 31) >> 5);
+                const bool rows_ok = m_row0 < ep.M;          // warp-uniform; rows >= M inside the box are clipped by TMA
+                auto issue_res = [&](int c) {
+                    if (lane == 0) {
+                        const uint32_t rb = nres_issued & 1;
+                        mbar_arrive_expect_tx(&rbar[rb], EPI_STAGE_BYTES);
+                        tma_load_2d(&tmRes, &rbar[rb], st_res + rb * EPI_STAGE_BYTES, nb + c * 32, m_row0);
+                    }
+                    ++nres_issued;
+                };
+                if (has_res && rows_ok) issue_res(0);          // in flight while the MMAs of this tile finish
+                mbar_wait(&tfull[a], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+#pragma unroll 1
+                for (int c = 0; c < nchunks; ++c) {
+                    const int n0 = nb + c * 32;
+                    if (has_res && rows_ok && c + 1 < nchunks) issue_res(c + 1);
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    if (!rows_ok) continue;
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    epilogue_math<EPI>(ep, f, m, n0, n0 + 32 <= ep.N);
+                    if (has_res) {
+                        const uint32_t rb = nres_used & 1;
+                        mbar_wait(&rbar[rb], (nres_used >> 1) & 1);
+                        ++nres_used;
+                        const uint8_t* r = my_res + rb * EPI_STAGE_BYTES;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const float4 x = *reinterpret_cast<const float4*>(r + ((g ^ sw) << 4));
+                            f[4 * g] += x.x; f[4 * g + 1] += x.y; f[4 * g + 2] += x.z; f[4 * g + 3] += x.w;
+                        }
+                    }
+                    if constexpr (OUT_F32) {
+                        const uint32_t sb = nstore & 1;
+                        if (lane == 0) tma_store_wait_read<1>();       // the store that last read this buffer is done with it
+                        __syncwarp();
+                        uint8_t* o = my_out + sb * EPI_STAGE_BYTES;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            *reinterpret_cast<float4*>(o + ((g ^ sw) << 4)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmOut, st_out + sb * EPI_STAGE_BYTES, n0, m_row0);
+                            tma_store_commit();
+                        }
+                        ++nstore;
+                    } else {
+                        const uint32_t sb = nstore & 1;
+                        const int half = c & 1;
+                        if (half == 0) {
+                            if (lane == 0) tma_store_wait_read<1>();
+                            __syncwarp();
+                        }
+                        uint8_t* o = my_out + sb * EPI_STAGE_BYTES;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 pk;
+                            pk.x = pack_bf16(f[8 * g + 0], f[8 * g + 1]);
+                            pk.y = pack_bf16(f[8 * g + 2], f[8 * g + 3]);
+                            pk.z = pack_bf16(f[8 * g + 4], f[8 * g + 5]);
+                            pk.w = pack_bf16(f[8 * g + 6], f[8 * g + 7]);
+                            *reinterpret_cast<uint4*>(o + (((half * 4 + g) ^ sw) << 4)) = pk;
+                        }
+                        if (half == 1 || c == nchunks - 1) {
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmOut, st_out + sb * EPI_STAGE_BYTES, nb + (c & ~1) * 32, m_row0);
+                                tma_store_commit();
+                            }
+                            ++nstore;
+                        }
+                    }
+                }
+                tc_fence_before();
+                if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
+            }
+            if (lane == 0) tma_store_wait<0>();
         }
     }
 
@@ -337,14 +464,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ----------------------------------------------------------------------------- host side
 static bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer,
-                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
+                         CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {row_stride_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     auto fn = driver_api().encode_tiled;
     if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return false; }
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = fn(tm, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -360,14 +488,28 @@ bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_
     return make_tmap_2d(tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer);
 }
 
-template <int CG, int BN, bool OUT_F32, int EPI>
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmEpi& ep, int max_ctas,
                        cudaStream_t stream) {
-    using Cfg = GemmCfg<CG, BN>;
-    CUtensorMap tmA, tmB;
+    using Cfg = GemmCfg<CG, BN, TMA_EPI>;
+    CUtensorMap tmA, tmB, tmOut, tmRes;
     if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP;
     if (!make_tmap_2d(&tmB, W, ep.K, ep.N, ldw * 2, BLOCK_K, Cfg::B_ROWS)) return KX_ERR_TMAP;
-    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI>;
+    if constexpr (TMA_EPI) {
+        if (!make_tmap_2d(&tmOut, ep.out, ep.N, ep.M, ep.ld_out * (OUT_F32 ? 4 : 2), OUT_F32 ? 32 : 64, 32,
+                          OUT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16))
+            return KX_ERR_TMAP;
+        if (ep.res != nullptr) {
+            if (!make_tmap_2d(&tmRes, ep.res, ep.N, ep.M, ep.ld_res * 4, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
+                return KX_ERR_TMAP;
+        } else {
+            tmRes = tmOut;
+        }
+    } else {
+        tmOut = tmA;
+        tmRes = tmA;
+    }
+    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI>;
     static bool attr_set = false;   // per template instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -389,7 +531,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ep);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, ep);
     if (e != cudaSuccess) { set_error("gemm launch failed: %s", cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
     count_launch();
     return KX_OK;
@@ -436,17 +578,28 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     if (bn == 0) bn = (g->N >= 256 && (long long)((g->M + 127) / 128) * ((g->N + 255) / 256) >= sms / 2) ? 256 : 128;
     const int max_ctas = g->max_ctas > 0 ? std::min(g->max_ctas, sms) : sms;
 
+    // staged TMA epilogue whenever the output (and residual) rows are 16-byte aligned and unscattered;
+    // otherwise (LM head with ld = 32002, image_proj / patch-embed row scatter) direct predicated stores
+    bool tma_epi = (g->grp_rows == 0) && (g->add_tab == nullptr) && ((g->ld_out * esz) % 16 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(g->out) & 15) == 0);
+    if (g->res) tma_epi = tma_epi && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
+    if (g->epi_mode == 1) tma_epi = false;
+#define KX_GEMM_CASE2(CG_, BN_, T_)                                                                          \
+    {                                                                                                        \
+        if (g->epi == KX_EPI_QKV_XPOS) return launch_gemm<CG_, BN_, false, KX_EPI_QKV_XPOS, T_>(A, lda, W, ldw, ep, max_ctas, stream); \
+        if (g->out_f32) return launch_gemm<CG_, BN_, true, KX_EPI_GENERIC, T_>(A, lda, W, ldw, ep, max_ctas, stream);                  \
+        return launch_gemm<CG_, BN_, false, KX_EPI_GENERIC, T_>(A, lda, W, ldw, ep, max_ctas, stream);                                  \
+    }
 #define KX_GEMM_CASE(CG_, BN_)                                                                               \
     if (cg == CG_ && bn == BN_) {                                                                            \
-        if (g->epi == KX_EPI_QKV_XPOS) return launch_gemm<CG_, BN_, false, KX_EPI_QKV_XPOS>(A, lda, W, ldw, ep, max_ctas, stream); \
-        if (g->out_f32) return launch_gemm<CG_, BN_, true, KX_EPI_GENERIC>(A, lda, W, ldw, ep, max_ctas, stream);                  \
-        return launch_gemm<CG_, BN_, false, KX_EPI_GENERIC>(A, lda, W, ldw, ep, max_ctas, stream);                                  \
+        if (tma_epi) KX_GEMM_CASE2(CG_, BN_, true) else KX_GEMM_CASE2(CG_, BN_, false)                       \
     }
     KX_GEMM_CASE(1, 128)
     KX_GEMM_CASE(1, 256)
     KX_GEMM_CASE(2, 128)
     KX_GEMM_CASE(2, 256)
 #undef KX_GEMM_CASE
+#undef KX_GEMM_CASE2
     set_error("kx_gemm_bf16: unsupported config cta_group=%d block_n=%d", cg, bn);
     return KX_ERR_ARG;
 }

@@ -328,6 +328,32 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// erf-GELU on two values at once.  erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the
+// bf16 rounding of the result) with the Horner chain on packed FFMA2; written as
+//   gelu(x) = 0.5*(x + |x|*erf(|x|/sqrt2)) = 0.5*x + h - h*(poly(t)*exp(-z^2)),  h = 0.5|x|, z = |x|/sqrt2, t = 1/(1+p*z)
+// which needs no sign handling and has no cancellation in the negative tail.
+__device__ __forceinline__ void gelu_erf_x2(float& a, float& b) {
+    const float za = fabsf(a) * 0.70710678118654752440f, zb = fabsf(b) * 0.70710678118654752440f;
+    float ta, tb;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ta) : "f"(fmaf(za, 0.3275911f, 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tb) : "f"(fmaf(zb, 0.3275911f, 1.0f)));
+    const uint64_t t = pack_f32x2(ta, tb);
+    const uint64_t z = pack_f32x2(za, zb);
+    uint64_t y = ffma2(t, pack_f32x2(1.061405429f, 1.061405429f), pack_f32x2(-1.453152027f, -1.453152027f));
+    y = ffma2(y, t, pack_f32x2(1.421413741f, 1.421413741f));
+    y = ffma2(y, t, pack_f32x2(-0.284496736f, -0.284496736f));
+    y = ffma2(y, t, pack_f32x2(0.254829592f, 0.254829592f));
+    y = fmul2(y, t);
+    const uint64_t zz = fmul2(fmul2(z, z), pack_f32x2(-1.4426950408889634f, -1.4426950408889634f));
+    float ea, eb;
+    unpack_f32x2(zz, ea, eb);
+    const uint64_t ye = fmul2(y, pack_f32x2(ex2_approx(ea), ex2_approx(eb)));
+    const uint64_t h = fmul2(z, pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f));     // 0.5|x|
+    const uint64_t nh = fmul2(z, pack_f32x2(-0.70710678118654752440f, -0.70710678118654752440f));
+    uint64_t g = ffma2(nh, ye, h);                                                                  // h - h*ye
+    g = ffma2(pack_f32x2(a, b), pack_f32x2(0.5f, 0.5f), g);
+    unpack_f32x2(g, a, b);
+}
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 }  // namespace kx

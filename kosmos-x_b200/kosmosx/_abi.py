@@ -33,7 +33,7 @@ class GemmArgs(C.Structure):
         ("add_tab", _f32p), ("add_off", _i), ("ld_add", _ll),
         ("xq_cos", _f32p), ("xq_sin", _f32p), ("xk_cos", _f32p), ("xk_sin", _f32p),
         ("seq_len", _i), ("d_model", _i),
-        ("cta_group", _i), ("block_n", _i), ("max_ctas", _i),
+        ("cta_group", _i), ("block_n", _i), ("max_ctas", _i), ("epi_mode", _i),
     ]
 
 

@@ -64,7 +64,8 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=None, act=_abi.KX_ACT_NONE,
-         grp=None, add_tab=None, add_off=0, xpos=None, seq_len=0, cta_group=0, block_n=0, max_ctas=0, M=None):
+         grp=None, add_tab=None, add_off=0, xpos=None, seq_len=0, cta_group=0, block_n=0, max_ctas=0, M=None,
+         epi_mode=0):
     """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; out bf16 or fp32 (2-D views, row pitch = stride(0))."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
@@ -93,7 +94,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
         g.xq_cos, g.xq_sin, g.xk_cos, g.xk_sin = (t.data_ptr() for t in xpos)
         g.seq_len = seq_len
         g.d_model = g.N // 3
-    g.cta_group, g.block_n, g.max_ctas = cta_group, block_n, max_ctas
+    g.cta_group, g.block_n, g.max_ctas, g.epi_mode = cta_group, block_n, max_ctas, epi_mode
     with _Timed("gemm", 2.0 * g.M * g.N * g.K,
                 2.0 * (g.M + g.N) * g.K + g.M * g.N * (out.element_size() + (4 if res is not None else 0))):
         check(lib.kx_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), g, _stream()), "kx_gemm_bf16")

@@ -13,7 +13,7 @@ for w in $what; do
     tests)    timeout 1500 python -m pytest tests -m gpu -x -q -s > "$out/pytest_gpu.log" 2>&1; echo "pytest exit $?" | tee -a "$out/summary.txt"; grep -E "max=|passed|failed|Error|error|FAIL|agreement" "$out/pytest_gpu.log" | tail -40;;
     bench)    timeout 900 python bench.py --steps 10 --warmup 3 > "$out/bench.json" 2> "$out/bench.err"; echo "bench exit $?" | tee -a "$out/summary.txt"; cat "$out/bench.json"; tail -5 "$out/bench.err";;
     benchng)  timeout 900 python bench.py --steps 10 --warmup 3 --graph 0 --no-cpu > "$out/bench_nograph.json" 2> "$out/bench_nograph.err"; echo "bench(nograph) exit $?" | tee -a "$out/summary.txt"; cat "$out/bench_nograph.json"; tail -5 "$out/bench_nograph.err";;
-    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kx:: -s 620 -c 420 --csv --log-file "$out/launches.csv" python tools/profile_step.py --steps 3 > "$out/launches.log" 2>&1; echo "launches exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/launches.log";;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:^(attn_|broadcast_rows|embed_splice|gemm_bf16|im2col|layernorm|perceiver_x)" -s 413 -c 413 --csv --log-file "$out/launches.csv" python tools/profile_step.py --steps 3 > "$out/launches.log" 2>&1; echo "launches exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/launches.log";;
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 4 -o "$out/prof_gemm" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_gemm.log" 2>&1; echo "ncu_gemm exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_gemm.log";;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
     kcheck)   bash tools/run_kernel_checks.sh bench;;

@@ -101,6 +101,31 @@ def case_gemm_epilogue():
         o2 = torch.zeros(M, 1002, device=dev)
         ops.gemm(a, w2, o2, cta_group=cg)
         ok &= report(f"epi fp32 N=1002 cg={cg}", o2, a.float() @ w2.float().T, 1e-2)
+    # staged (TMA-store) epilogue vs direct stores: ragged M and N, bf16 and fp32, residual in place, both tile widths
+    for cg, bn in ((1, 128), (2, 128), (1, 256), (2, 256)):
+        for (M2, N2, K2) in ((300, 1000, 192), (2056, 1024, 256), (515, 40, 64)):
+            a2 = torch.randn(M2, K2, device=dev).bfloat16()
+            w3 = (torch.randn(N2, K2, device=dev) / math.sqrt(K2)).bfloat16()
+            b3 = torch.randn(N2, device=dev)
+            base = a2.float() @ w3.float().T + b3
+            for mode in (0, 1):
+                ob = torch.full((M2 + 3, N2), 7.0, device=dev, dtype=torch.bfloat16)     # 3 guard rows must stay untouched
+                ops.gemm(a2, w3, ob, bias=b3, act=_abi.KX_ACT_GELU, cta_group=cg, block_n=bn, epi_mode=mode, M=M2)
+                good = report(f"epi mode={mode} bf16 gelu cg={cg} bn={bn} {M2}x{N2}x{K2}", ob[:M2],
+                              torch.nn.functional.gelu(base), 2e-2)
+                ok &= good and bool((ob[M2:] == 7.0).all())
+                xr = torch.randn(M2 + 3, N2, device=dev)
+                x0 = xr.clone()
+                ops.gemm(a2, w3, xr, bias=b3, res=xr, cta_group=cg, block_n=bn, epi_mode=mode, M=M2)
+                good = report(f"epi mode={mode} fp32 res cg={cg} bn={bn} {M2}x{N2}x{K2}", xr[:M2], base + x0[:M2], 1e-2)
+                ok &= good and bool(torch.equal(xr[M2:], x0[M2:]))
+    # fast erf-GELU against torch's exact erf GELU in fp32 (identity weights isolate the activation)
+    K3 = 256
+    eye = torch.eye(K3, device=dev).bfloat16()
+    xs = torch.linspace(-9, 9, 4096 * K3, device=dev).view(4096, K3).bfloat16()
+    og = torch.empty(4096, K3, device=dev)
+    ops.gemm(xs, eye, og, act=_abi.KX_ACT_GELU)
+    ok &= report("erf-GELU approximation (fp32 out)", og, torch.nn.functional.gelu(xs.float()), 4e-6)
     return ok
 
 
