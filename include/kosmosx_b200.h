@@ -74,6 +74,20 @@ typedef struct kx_gemm_args {
     int block_n;                  /* 0 = auto, 128 or 256 */
     int max_ctas;                 /* 0 = all SMs */
     int epi_mode;                 /* 0 = auto (staged TMA-store epilogue when alignment allows), 1 = direct stores */
+    /* LayerNorm folded into this GEMM (consumer side).  A holds the RAW (un-normalised) rows,
+     * W must already be W*diag(gamma), bias must be W.beta + b, and
+     *     out = rstd[m] * (A.W^T - mean[m] * ln_c[n]) + bias[n] ...
+     * mean/rstd of row m are computed from ln_tiles partial (sum, sumsq) pairs over ln_cols columns. */
+    const float* ln_part;         /* fp32 pairs [ln_tiles][M][2], or NULL = no fold */
+    const float* ln_c;            /* fp32 [N]: sum_k W[n,k] of the (bf16) folded weight */
+    int ln_tiles, ln_cols;
+    float ln_eps;
+    /* producer side: per-row partial (sum, sumsq) of the values this GEMM stores, one pair per 256-column
+     * tile ([ceil(N/256)][M][2] fp32; forces block_n = 256), and a bf16 copy of an fp32 output; the
+     * statistics are those of the bf16 copy when one is written.  Both need the staged epilogue. */
+    float* stats_out;
+    void* out2;
+    long long ld_out2;
 } kx_gemm_args;
 
 int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const kx_gemm_args* args,
@@ -86,9 +100,11 @@ int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, con
  * Replaces: torchscale MultiheadAttention core — bmm, nan_to_num, +triu(-inf) mask,
  * softmax(fp32), bmm, head merge (decoder, causal=1) — and HF CLIPAttention's
  * eager/sdpa core ([HF]:318-331; ViT, causal=0).  `scale` multiplies q.k^T (64^-0.5).
+ * stats_out (fp32 pairs [heads][batch*seq_len][2], or NULL): per-head partial (sum, sumsq) of each stored
+ * output row, consumed by the out_proj GEMM that folds torchscale's inner_attn_ln (kx_gemm_args.ln_part).
  */
 int kx_attn_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
-                int batch, int heads, int seq_len, int causal, float scale, kx_stream_t stream);
+                int batch, int heads, int seq_len, int causal, float scale, float* stats_out, kx_stream_t stream);
 
 /* Perceiver cross-attention core (flamingo_pytorch PerceiverAttention; reached from
  * model.py:231): per (batch, head) softmax(q.k^T * scale - rowmax) . v with n_q latent queries and
@@ -138,6 +154,12 @@ int kx_add_positions(const float* in, float* out, int batch, int T, int dim, con
  */
 int kx_im2col_patches(const float* pixels, int batch, int image, int patch, void* patches_bf16, int k_pad,
                       const float* class_embedding, const float* pos_table, float* x, int dim, kx_stream_t stream);
+
+/* Row statistics + bf16 copy of an fp32 matrix: xb = bf16(x), stats[m] = (sum, sumsq) of xb's row m
+ * ([1][rows][2] fp32).  Seeds the folded-LayerNorm chain (kx_gemm_args.ln_part) for the first decoder layer,
+ * whose input comes from kx_embed_splice_pos / the image_proj epilogue rather than from a GEMM with stats_out. */
+int kx_rowstats_cast(const float* x, long long ld_x, void* xb_bf16, long long ld_xb, float* stats, int rows, int n,
+                     kx_stream_t stream);
 
 /* xPos tables (torchscale XPOS): for t in [0,T), j in [0,32):
  *   S = scale[j] ** ((t + min_pos) / scale_base), theta = t * inv_freq[j]

@@ -282,7 +282,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 namespace kx {
 int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
-                   int heads, int seq_len, int causal, float scale, cudaStream_t stream);   // attention_pp.cu
+                   int heads, int seq_len, int causal, float scale, float* stats_out, cudaStream_t stream);   // attention_pp.cu
 // KX_ATTN_IMPL=0 selects the first-generation kernel of this file (kept for A/B measurements).
 static int attn_impl() {
     static int impl = -1;
@@ -297,7 +297,8 @@ static int attn_impl() {
 using namespace kx;
 
 extern "C" int kx_attn_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
-                           int batch, int heads, int seq_len, int causal, float scale, cudaStream_t stream) {
+                           int batch, int heads, int seq_len, int causal, float scale, float* stats_out,
+                           cudaStream_t stream) {
     if (!q || !k || !v || !out) { set_error("kx_attn_fwd: null pointer"); return KX_ERR_ARG; }
     if (batch <= 0 || heads <= 0 || seq_len <= 0) { set_error("kx_attn_fwd: bad shape"); return KX_ERR_ARG; }
     if ((ld_qkv % 8) || (ld_out % 8) || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) || ((uintptr_t)out & 15)) {
@@ -305,7 +306,9 @@ extern "C" int kx_attn_fwd(const void* q, const void* k, const void* v, long lon
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    if (attn_impl() == 1) return launch_attn_pp(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stream);
+    if (stats_out && (reinterpret_cast<uintptr_t>(stats_out) & 7)) { set_error("kx_attn_fwd: stats_out must be 8-byte aligned"); return KX_ERR_ARG; }
+    if (attn_impl() == 1) return launch_attn_pp(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stats_out, stream);
+    if (stats_out) { set_error("kx_attn_fwd: stats_out is only produced by the default kernel (unset KX_ATTN_IMPL)"); return KX_ERR_ARG; }
     const unsigned long long rows = (unsigned long long)batch * seq_len;
     CUtensorMap tq, tk, tv;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * AT_D, rows, ld_qkv * 2, AT_D, AT_BM)) return KX_ERR_TMAP;

@@ -36,6 +36,8 @@ struct AttnPPParams {
     long long ld_out;
     int seq_len, heads, num_pairs;
     float scale_log2;                                // scale * log2(e)
+    float2* stats_out;                               // [heads][batch*seq_len] partial (sum, sumsq) of the stored row, or null
+    long long total_rows;
 };
 
 template <bool CAUSAL>
@@ -276,6 +278,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const float inv_l = 1.0f / l_run;
             __nv_bfloat16* o = p.out + static_cast<long long>(row_base + qrow) * p.ld_out + head * 64;
 #pragma unroll
+            float s1 = 0.f, s2 = 0.f;
             for (int g = 0; g < 8; ++g) {
                 uint4 q;
                 q.x = pack_bf16(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
@@ -283,7 +286,17 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 q.z = pack_bf16(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
                 q.w = pack_bf16(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
                 *reinterpret_cast<uint4*>(o + 8 * g) = q;
+                if (p.stats_out != nullptr) {          // inner_attn_ln statistics: this head's 64 columns, as stored
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float2 r2 = __bfloat1622float2(h2[u]);
+                        s1 += r2.x + r2.y;
+                        s2 = fmaf(r2.x, r2.x, fmaf(r2.y, r2.y, s2));
+                    }
+                }
             }
+            if (p.stats_out != nullptr) p.stats_out[static_cast<long long>(head) * p.total_rows + row_base + qrow] = make_float2(s1, s2);
         }
     }
 
@@ -294,7 +307,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
-                   int heads, int seq_len, int causal, float scale, cudaStream_t stream) {
+                   int heads, int seq_len, int causal, float scale, float* stats_out, cudaStream_t stream) {
     const unsigned long long rows = (unsigned long long)batch * seq_len;
     CUtensorMap tq, tk, tv;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
@@ -307,6 +320,8 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.heads = heads;
     p.num_pairs = (seq_len + 255) / 256;
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.stats_out = reinterpret_cast<float2*>(stats_out);
+    p.total_rows = static_cast<long long>(rows);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);

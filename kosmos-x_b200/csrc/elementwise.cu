@@ -166,6 +166,38 @@ layernorm_kernel(const void* __restrict__ x, long long ld_x, const float* __rest
     }
 }
 
+// xb = bf16(x) and per-row (sum, sumsq) of xb: one warp per row, 16-byte accesses.
+__global__ void __launch_bounds__(256)
+rowstats_cast_kernel(const float* __restrict__ x, long long ld_x, __nv_bfloat16* __restrict__ xb, long long ld_xb,
+                     float2* __restrict__ stats, int rows, int n) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* px = x + row * ld_x;
+    __nv_bfloat16* po = xb + row * ld_xb;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane * 8; i < n; i += 256) {
+        const float4 a = *reinterpret_cast<const float4*>(px + i);
+        const float4 b = *reinterpret_cast<const float4*>(px + i + 4);
+        uint4 q;
+        q.x = pack_bf16(a.x, a.y); q.y = pack_bf16(a.z, a.w); q.z = pack_bf16(b.x, b.y); q.w = pack_bf16(b.z, b.w);
+        *reinterpret_cast<uint4*>(po + i) = q;
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 r = __bfloat1622float2(h[u]);
+            s1 += r.x + r.y;
+            s2 = fmaf(r.x, r.x, fmaf(r.y, r.y, s2));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) stats[row] = make_float2(s1, s2);
+}
+
 // x[b, t, :] = in[b, t, :] + pos[t + 2, :]   (Decoder.forward_embedding with token_embedding given)
 __global__ void __launch_bounds__(256)
 add_positions_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int dim, const float* __restrict__ pos) {
@@ -320,6 +352,20 @@ extern "C" int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, co
 #undef KX_LN2
 #undef KX_LN3
     return check_launch("kx_layernorm_fwd");
+}
+
+extern "C" int kx_rowstats_cast(const float* x, long long ld_x, void* xb, long long ld_xb, float* stats, int rows, int n,
+                                cudaStream_t stream) {
+    if (!x || !xb || !stats) { set_error("kx_rowstats_cast: null pointer"); return KX_ERR_ARG; }
+    if (rows <= 0 || n <= 0 || (n % 8) || (ld_x % 4) || (ld_xb % 8) || ((uintptr_t)x & 15) || ((uintptr_t)xb & 15) ||
+        ((uintptr_t)stats & 7)) {
+        set_error("kx_rowstats_cast: n must be a multiple of 8 and rows 16-byte aligned");
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    rowstats_cast_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ld_x, reinterpret_cast<__nv_bfloat16*>(xb), ld_xb,
+                                                            reinterpret_cast<float2*>(stats), rows, n);
+    return check_launch("kx_rowstats_cast");
 }
 
 extern "C" int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,

@@ -27,7 +27,7 @@ constexpr int EPI_WARP0 = 4;
 // writes it with cp.async.bulk.tensor (coalesced, asynchronous); the fp32 residual sub-tile is
 // prefetched the same way.  Costs 16 KB of staging per epilogue warp, taken from the operand ring.
 constexpr int EPI_STAGE_BYTES = 32 * 128;                    // 32 rows x 128 B
-constexpr int EPI_WARP_BYTES = 4 * EPI_STAGE_BYTES;          // out[2] + res[2]
+constexpr int EPI_WARP_BYTES = 4 * EPI_STAGE_BYTES;          // main[3] x 4 KB + copy[2] x 2 KB
 
 template <int CG, int BN, bool TMA_EPI>
 struct GemmCfg {
@@ -59,6 +59,18 @@ struct GemmEpi {
     const float *xq_cos, *xq_sin, *xk_cos, *xk_sin;   // xPos tables [seq_len, 32] fp32
     int seq_len, d_model;
     int vec_ok;                // 16-byte vector access to out/res/add_tab rows is legal
+    // LayerNorm folded into this GEMM: A holds the RAW rows, W already carries gamma,
+    //   y = rstd[m] * (acc - mean[m] * ln_c[n]) + bias[n],   bias = W.beta + b
+    // mean/rstd come from ln_tiles partial (sum, sumsq) pairs per row written by the producer's epilogue.
+    const float2* ln_part;     // [ln_tiles][M] or null
+    const float* ln_c;         // [N]: sum_k W'[n,k]
+    int ln_tiles;
+    float ln_inv_n, ln_eps;
+    // producer side: per-row partial (sum, sumsq) of the values this GEMM stores (after bf16 rounding),
+    // one pair per (n-tile, row); and an optional bf16 copy of an fp32 output (staged epilogue only)
+    float2* stats_out;         // [ceil(N/BN)][M] or null
+    void* out2;                // bf16 [M, ld_out2] or null
+    long long ld_out2;
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -73,8 +85,35 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_
 }
 
 // bias -> [xPos rotation] -> activation on one 32-column chunk of row m (shared by both store paths)
+// Row statistics of the A operand for a folded LayerNorm: fixed-order sum of the producer's partials.
+__device__ __forceinline__ float2 ln_row_stats(const GemmEpi& ep, int m) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < ep.ln_tiles; ++i) {
+        const float2 p = __ldg(ep.ln_part + static_cast<long long>(i) * ep.M + m);
+        s1 += p.x; s2 += p.y;
+    }
+    const float mean = s1 * ep.ln_inv_n;
+    const float var = fmaxf(s2 * ep.ln_inv_n - mean * mean, 0.f);
+    return make_float2(mean, rsqrtf(var + ep.ln_eps));
+}
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32], int m, int n0, bool full) {
+__device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32], int m, int n0, bool full, float2 ln) {
+    if (ep.ln_part != nullptr) {
+        const float nmr = -ln.x * ln.y;                 // y = rstd*acc + (-mean*rstd)*c
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>(ep.ln_c + n0 + i));
+                f[i] = fmaf(nmr, c.x, f[i] * ln.y); f[i + 1] = fmaf(nmr, c.y, f[i + 1] * ln.y);
+                f[i + 2] = fmaf(nmr, c.z, f[i + 2] * ln.y); f[i + 3] = fmaf(nmr, c.w, f[i + 3] * ln.y);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (n0 + i < ep.N) f[i] = fmaf(nmr, __ldg(ep.ln_c + n0 + i), f[i] * ln.y);
+        }
+    }
     if (ep.bias != nullptr) {
         if (full) {
 #pragma unroll
@@ -124,12 +163,12 @@ __device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32],
 }
 
 template <bool OUT_F32, int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t (&v)[32], int m, int n0) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t (&v)[32], int m, int n0, float2 ln) {
     float f[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
     const bool full = (n0 + 32 <= ep.N);
-    epilogue_math<EPI>(ep, f, m, n0, full);
+    epilogue_math<EPI>(ep, f, m, n0, full, ln);
 
     long long orow = m;
     int prow = 0;
@@ -207,7 +246,7 @@ template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-                 const GemmEpi ep) {
+                 const __grid_constant__ CUtensorMap tmOut2, const GemmEpi ep) {
     using Cfg = GemmCfg<CG, BN, TMA_EPI>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -221,8 +260,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
-    uint64_t* resbar = bars + 2 * STAGES + 4;                      // [4 warps][2 buffers]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
+    uint64_t* resbar = bars + 2 * STAGES + 4;                      // [4 warps][3 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 16);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -235,6 +274,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (TMA_EPI) {
             prefetch_tmap(&tmOut);
             if (ep.res != nullptr) prefetch_tmap(&tmRes);
+            if (ep.out2 != nullptr) prefetch_tmap(&tmOut2);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -246,7 +286,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], CG * 128);   // every epilogue thread of every CTA, on the leader's barrier
         }
-        for (int i = 0; i < 8; ++i) mbar_init(&resbar[i], 1);
+        for (int i = 0; i < 12; ++i) mbar_init(&resbar[i], 1);
         fence_mbar_init();
     }
     if constexpr (CG == 2) cluster_sync_all();
@@ -339,28 +379,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+                const float2 ln = (ep.ln_part != nullptr && m < ep.M) ? ln_row_stats(ep, m) : make_float2(0.f, 1.f);
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     if (nb + c * 32 >= ep.N) break;       // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
-                    if (m < ep.M) epilogue_chunk<OUT_F32, EPI>(ep, v, m, nb + c * 32);
+                    if (m < ep.M) epilogue_chunk<OUT_F32, EPI>(ep, v, m, nb + c * 32, ln);
                 }
                 tc_fence_before();
                 if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
             }
         } else {
-            // Staged epilogue: registers -> swizzled smem (this warp's private 32 x 128 B buffers) -> TMA store.
-            // fp32 out: one store per 32-column chunk; bf16 out: one store per two chunks (64 columns = 128 B).
-            uint8_t* st_out = smem_epi + q * EPI_WARP_BYTES;
-            uint8_t* st_res = st_out + 2 * EPI_STAGE_BYTES;
-            uint64_t* rbar = resbar + q * 2;
+            // Staged epilogue.  Per warp, private smem: main[3] x 4 KB (32 rows x 128 B, SWIZZLE_128B), rotating
+            // per store unit, and copy[2] x 2 KB (32 rows x 64 B, SWIZZLE_64B) for the bf16 copy of an fp32 output.
+            //   fp32 out: unit = one 32-column chunk.  With a residual, the unit's buffer first receives the
+            //             residual sub-tile by TMA (prefetched one unit ahead) and is updated IN PLACE.
+            //   bf16 out: unit = two chunks (64 columns = 128-byte rows).
+            // One cp.async.bulk group per store; at every unit start lane 0 waits until only the previous
+            // unit's groups may still be reading smem, which frees every buffer touched in this unit.
+            uint8_t* st_main = smem_epi + q * EPI_WARP_BYTES;
+            uint8_t* st_copy = st_main + 3 * EPI_STAGE_BYTES;
+            uint64_t* rbar = resbar + q * 3;
             const bool has_res = (ep.res != nullptr);
+            const bool has_copy = OUT_F32 && (ep.out2 != nullptr);
+            const bool has_stats = (ep.stats_out != nullptr);
             const int sw = lane & 7;
-            uint8_t* my_out = st_out + lane * 128;
-            const uint8_t* my_res = st_res + lane * 128;
-            uint32_t nstore = 0, nres_issued = 0, nres_used = 0;
+            const int sw64 = (lane >> 1) & 3;
+            uint32_t unit = 0;              // store units issued by this warp
+            uint32_t nres = 0;              // residual loads issued by this warp (== unit + prefetch depth)
+            auto wait_units = [&]() {
+                if (lane == 0) { if (has_copy) tma_store_wait_read<2>(); else tma_store_wait_read<1>(); }
+            };
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 int m_blk, n_blk;
                 tile_coords(t, num_m, num_n, m_blk, n_blk);
@@ -370,23 +421,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int m = m_row0 + lane;
                 const int nb = n_blk * BN;
                 const int nchunks = min(BN / 32, (ep.N - nb + 31) >> 5);
-                const bool rows_ok = m_row0 < ep.M;          // warp-uniform; rows >= M inside the box are clipped by TMA
+                const bool rows_ok = m_row0 < ep.M;          // warp-uniform; rows >= M inside a box are clipped by TMA
+                const float2 ln = (ep.ln_part != nullptr && m < ep.M) ? ln_row_stats(ep, m) : make_float2(0.f, 1.f);
+                float s1 = 0.f, s2 = 0.f;
                 auto issue_res = [&](int c) {
                     if (lane == 0) {
-                        const uint32_t rb = nres_issued & 1;
+                        const uint32_t rb = nres % 3;
                         mbar_arrive_expect_tx(&rbar[rb], EPI_STAGE_BYTES);
-                        tma_load_2d(&tmRes, &rbar[rb], st_res + rb * EPI_STAGE_BYTES, nb + c * 32, m_row0);
+                        tma_load_2d(&tmRes, &rbar[rb], st_main + rb * EPI_STAGE_BYTES, nb + c * 32, m_row0);
                     }
-                    ++nres_issued;
+                    ++nres;
                 };
-                if (has_res && rows_ok) issue_res(0);          // in flight while the MMAs of this tile finish
+                if (has_res && rows_ok) {                    // in flight while the MMAs of this tile finish
+                    wait_units();
+                    issue_res(0);
+                }
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
 #pragma unroll 1
                 for (int c = 0; c < nchunks; ++c) {
                     const int n0 = nb + c * 32;
-                    if (has_res && rows_ok && c + 1 < nchunks) issue_res(c + 1);
+                    if (rows_ok && (OUT_F32 || !(c & 1))) {
+                        wait_units();
+                        __syncwarp();
+                        if (has_res && c + 1 < nchunks) issue_res(c + 1);
+                    }
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
@@ -394,41 +454,59 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    epilogue_math<EPI>(ep, f, m, n0, n0 + 32 <= ep.N);
-                    if (has_res) {
-                        const uint32_t rb = nres_used & 1;
-                        mbar_wait(&rbar[rb], (nres_used >> 1) & 1);
-                        ++nres_used;
-                        const uint8_t* r = my_res + rb * EPI_STAGE_BYTES;
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float4 x = *reinterpret_cast<const float4*>(r + ((g ^ sw) << 4));
-                            f[4 * g] += x.x; f[4 * g + 1] += x.y; f[4 * g + 2] += x.z; f[4 * g + 3] += x.w;
-                        }
-                    }
+                    epilogue_math<EPI>(ep, f, m, n0, n0 + 32 <= ep.N, ln);
+                    const uint32_t ub = unit % 3;
+                    uint8_t* mb = st_main + ub * EPI_STAGE_BYTES + lane * 128;
                     if constexpr (OUT_F32) {
-                        const uint32_t sb = nstore & 1;
-                        if (lane == 0) tma_store_wait_read<1>();       // the store that last read this buffer is done with it
-                        __syncwarp();
-                        uint8_t* o = my_out + sb * EPI_STAGE_BYTES;
+                        if (has_res) {
+                            mbar_wait(&rbar[ub], (unit / 3) & 1);
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                const float4 x = *reinterpret_cast<const float4*>(mb + ((g ^ sw) << 4));
+                                f[4 * g] += x.x; f[4 * g + 1] += x.y; f[4 * g + 2] += x.z; f[4 * g + 3] += x.w;
+                            }
+                        }
 #pragma unroll
                         for (int g = 0; g < 8; ++g)
-                            *reinterpret_cast<float4*>(o + ((g ^ sw) << 4)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                            *reinterpret_cast<float4*>(mb + ((g ^ sw) << 4)) = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                        if (has_copy) {
+                            uint8_t* cb = st_copy + (unit & 1) * (EPI_STAGE_BYTES / 2) + lane * 64;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 pk;
+                                pk.x = pack_bf16(f[8 * g + 0], f[8 * g + 1]);
+                                pk.y = pack_bf16(f[8 * g + 2], f[8 * g + 3]);
+                                pk.z = pack_bf16(f[8 * g + 4], f[8 * g + 5]);
+                                pk.w = pack_bf16(f[8 * g + 6], f[8 * g + 7]);
+                                *reinterpret_cast<uint4*>(cb + ((g ^ sw64) << 4)) = pk;
+                                if (has_stats) {          // statistics of what the consumer GEMM will read: the bf16 copy
+                                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const float2 r = __bfloat1622float2(h[u]);
+                                        if (n0 + 8 * g + 2 * u < ep.N) { s1 += r.x; s2 = fmaf(r.x, r.x, s2); }
+                                        if (n0 + 8 * g + 2 * u + 1 < ep.N) { s1 += r.y; s2 = fmaf(r.y, r.y, s2); }
+                                    }
+                                }
+                            }
+                        } else if (has_stats) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (n0 + i < ep.N) { s1 += f[i]; s2 = fmaf(f[i], f[i], s2); }
+                        }
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmOut, st_out + sb * EPI_STAGE_BYTES, n0, m_row0);
+                            tma_store_2d(&tmOut, st_main + ub * EPI_STAGE_BYTES, n0, m_row0);
                             tma_store_commit();
+                            if (has_copy) {
+                                tma_store_2d(&tmOut2, st_copy + (unit & 1) * (EPI_STAGE_BYTES / 2), n0, m_row0);
+                                tma_store_commit();
+                            }
                         }
-                        ++nstore;
+                        ++unit;
                     } else {
-                        const uint32_t sb = nstore & 1;
                         const int half = c & 1;
-                        if (half == 0) {
-                            if (lane == 0) tma_store_wait_read<1>();
-                            __syncwarp();
-                        }
-                        uint8_t* o = my_out + sb * EPI_STAGE_BYTES;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             uint4 pk;
@@ -436,19 +514,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             pk.y = pack_bf16(f[8 * g + 2], f[8 * g + 3]);
                             pk.z = pack_bf16(f[8 * g + 4], f[8 * g + 5]);
                             pk.w = pack_bf16(f[8 * g + 6], f[8 * g + 7]);
-                            *reinterpret_cast<uint4*>(o + (((half * 4 + g) ^ sw) << 4)) = pk;
+                            *reinterpret_cast<uint4*>(mb + (((half * 4 + g) ^ sw) << 4)) = pk;
+                            if (has_stats) {
+                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float2 r = __bfloat1622float2(h[u]);
+                                    if (n0 + 8 * g + 2 * u < ep.N) { s1 += r.x; s2 = fmaf(r.x, r.x, s2); }
+                                    if (n0 + 8 * g + 2 * u + 1 < ep.N) { s1 += r.y; s2 = fmaf(r.y, r.y, s2); }
+                                }
+                            }
                         }
                         if (half == 1 || c == nchunks - 1) {
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_2d(&tmOut, st_out + sb * EPI_STAGE_BYTES, nb + (c & ~1) * 32, m_row0);
+                                tma_store_2d(&tmOut, st_main + ub * EPI_STAGE_BYTES, nb + (c & ~1) * 32, m_row0);
                                 tma_store_commit();
                             }
-                            ++nstore;
+                            ++unit;
                         }
                     }
                 }
+                if (has_stats && m < ep.M) ep.stats_out[static_cast<long long>(n_blk) * ep.M + m] = make_float2(s1, s2);
                 tc_fence_before();
                 if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
             }
@@ -465,7 +553,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ----------------------------------------------------------------------------- host side
 static bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer,
                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
-                         CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+                         CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {row_stride_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
@@ -473,7 +562,7 @@ static bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint6
     auto fn = driver_api().encode_tiled;
     if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver)"); return false; }
     CUresult r = fn(tm, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r, ptr,
@@ -492,7 +581,7 @@ template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmEpi& ep, int max_ctas,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<CG, BN, TMA_EPI>;
-    CUtensorMap tmA, tmB, tmOut, tmRes;
+    CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
     if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP;
     if (!make_tmap_2d(&tmB, W, ep.K, ep.N, ldw * 2, BLOCK_K, Cfg::B_ROWS)) return KX_ERR_TMAP;
     if constexpr (TMA_EPI) {
@@ -505,9 +594,17 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
         } else {
             tmRes = tmOut;
         }
+        if (OUT_F32 && ep.out2 != nullptr) {
+            if (!make_tmap_2d(&tmOut2, ep.out2, ep.N, ep.M, ep.ld_out2 * 2, 32, 32, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+                return KX_ERR_TMAP;
+        } else {
+            tmOut2 = tmOut;
+        }
     } else {
         tmOut = tmA;
         tmRes = tmA;
+        tmOut2 = tmA;
     }
     auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI>;
     static bool attr_set = false;   // per template instantiation
@@ -531,7 +628,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, ep);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, tmOut2, ep);
     if (e != cudaSuccess) { set_error("gemm launch failed: %s", cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
     count_launch();
     return KX_OK;
@@ -563,6 +660,26 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     if (g->add_tab) vec = vec && ((g->ld_add * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->add_tab) & 15) == 0);
     if (g->bias && (reinterpret_cast<uintptr_t>(g->bias) & 15)) { set_error("kx_gemm_bf16: bias must be 16-byte aligned"); return KX_ERR_ARG; }
     ep.vec_ok = vec ? 1 : 0;
+    if (g->ln_part) {
+        if (!g->ln_c || g->ln_tiles <= 0 || g->ln_cols <= 0 || (reinterpret_cast<uintptr_t>(g->ln_c) & 15) ||
+            (reinterpret_cast<uintptr_t>(g->ln_part) & 7)) {
+            set_error("kx_gemm_bf16: LayerNorm fold needs ln_c (16-byte aligned), ln_tiles > 0, ln_cols > 0");
+            return KX_ERR_ARG;
+        }
+        ep.ln_part = reinterpret_cast<const float2*>(g->ln_part);
+        ep.ln_c = g->ln_c;
+        ep.ln_tiles = g->ln_tiles;
+        ep.ln_inv_n = 1.0f / static_cast<float>(g->ln_cols);
+        ep.ln_eps = g->ln_eps;
+    }
+    ep.stats_out = reinterpret_cast<float2*>(g->stats_out);
+    ep.out2 = g->out2;
+    ep.ld_out2 = g->ld_out2;
+    if (g->stats_out && (reinterpret_cast<uintptr_t>(g->stats_out) & 7)) { set_error("kx_gemm_bf16: stats_out must be 8-byte aligned"); return KX_ERR_ARG; }
+    if (g->out2 && (!g->out_f32 || (g->ld_out2 % 8) || (reinterpret_cast<uintptr_t>(g->out2) & 15))) {
+        set_error("kx_gemm_bf16: out2 (bf16 copy) needs an fp32 primary output and 16-byte aligned rows");
+        return KX_ERR_ARG;
+    }
     if (g->epi == KX_EPI_QKV_XPOS) {
         if (!g->xq_cos || !g->xq_sin || !g->xk_cos || !g->xk_sin || g->seq_len <= 0 || g->d_model <= 0 ||
             (g->d_model % 64) || g->N != 3 * g->d_model || g->out_f32) {
@@ -574,7 +691,7 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     if (sms <= 0) return KX_ERR_NO_DEVICE;
     int cg = g->cta_group;
     if (cg == 0) cg = (g->M > 128) ? 2 : 1;
-    int bn = g->block_n;
+    int bn = g->stats_out ? 256 : g->block_n;
     if (bn == 0) bn = (g->N >= 256 && (long long)((g->M + 127) / 128) * ((g->N + 255) / 256) >= sms / 2) ? 256 : 128;
     const int max_ctas = g->max_ctas > 0 ? std::min(g->max_ctas, sms) : sms;
 
@@ -584,6 +701,10 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
                    ((reinterpret_cast<uintptr_t>(g->out) & 15) == 0);
     if (g->res) tma_epi = tma_epi && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
     if (g->epi_mode == 1) tma_epi = false;
+    if ((g->stats_out || g->out2) && !tma_epi) {
+        set_error("kx_gemm_bf16: stats_out / out2 need the staged epilogue (unscattered, 16-byte aligned rows, epi_mode 0)");
+        return KX_ERR_ARG;
+    }
 #define KX_GEMM_CASE2(CG_, BN_, T_)                                                                          \
     {                                                                                                        \
         if (g->epi == KX_EPI_QKV_XPOS) return launch_gemm<CG_, BN_, false, KX_EPI_QKV_XPOS, T_>(A, lda, W, ldw, ep, max_ctas, stream); \

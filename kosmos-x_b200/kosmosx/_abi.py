@@ -34,6 +34,8 @@ class GemmArgs(C.Structure):
         ("xq_cos", _f32p), ("xq_sin", _f32p), ("xk_cos", _f32p), ("xk_sin", _f32p),
         ("seq_len", _i), ("d_model", _i),
         ("cta_group", _i), ("block_n", _i), ("max_ctas", _i), ("epi_mode", _i),
+        ("ln_part", _f32p), ("ln_c", _f32p), ("ln_tiles", _i), ("ln_cols", _i), ("ln_eps", _f),
+        ("stats_out", _f32p), ("out2", _vp), ("ld_out2", _ll),
     ]
 
 
@@ -44,7 +46,8 @@ SIGNATURES = {
     "kx_device_check": (_i, []),
     "kx_launch_count": (C.c_ulonglong, []),
     "kx_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, C.POINTER(GemmArgs), _vp]),
-    "kx_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
+    "kx_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _vp]),
+    "kx_rowstats_cast": (_i, [_f32p, _ll, _vp, _ll, _f32p, _i, _i, _vp]),
     "kx_perceiver_xattn_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "kx_layernorm_fwd": (_i, [_vp, _i, _ll, _f32p, _i, _i, _f32p, _f32p, _f, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
     "kx_add_positions": (_i, [_f32p, _f32p, _i, _i, _i, _f32p, _i, _vp]),

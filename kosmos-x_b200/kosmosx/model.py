@@ -214,6 +214,19 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
     return ops.cast_bf16(_f32(t))
 
 
+def _fold_ln(weight: torch.Tensor, bias, ln: nn.LayerNorm):
+    """Fold a LayerNorm into the Linear that consumes it, once, at weight-staging time:
+        Linear(LN(x)) = rstd * (x . W'^T - mean * c) + d,   W' = W * gamma,  c = W'.1,  d = W.beta + b
+    Returns (W' as bf16, c fp32 [N] summed from the bf16-rounded W' that the tensor cores will see, d fp32 [N])."""
+    w = weight.detach().to(torch.float32)
+    wb = ops.cast_bf16((w * ln.weight.detach().to(torch.float32)[None, :]).contiguous())
+    c = wb.to(torch.float64).sum(dim=1).to(torch.float32).contiguous()
+    d = w.to(torch.float64) @ ln.bias.detach().to(torch.float64)
+    if bias is not None:
+        d = d + bias.detach().to(torch.float64)
+    return wb, c, d.to(torch.float32).contiguous()
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"{what} is on {t.device}: kosmosx (B200 build) has no CPU path — move the module and "
@@ -282,20 +295,16 @@ class Decoder(nn.Module):
             q, k, v, o = (_live(m) for m in (sa.q_proj, sa.k_proj, sa.v_proj, sa.out_proj))
             ffn = _live(L.ffn)
             ln_a, ln_i, ln_f = _live(L.self_attn_layer_norm), _live(sa.inner_attn_ln), _live(L.final_layer_norm)
+            # every LayerNorm of the layer is folded into the Linear that consumes it
             layers.append(dict(
-                w_qkv=_bf16(torch.cat([q.weight, k.weight, v.weight], 0)),
-                b_qkv=_f32(torch.cat([q.bias, k.bias, v.bias], 0)),
-                w_o=_bf16(o.weight), b_o=_f32(o.bias),
-                w_fc1=_bf16(ffn.fc1.weight), b_fc1=_f32(ffn.fc1.bias),
-                w_fc2=_bf16(ffn.fc2.weight), b_fc2=_f32(ffn.fc2.bias),
-                ln_a=(_f32(ln_a.weight), _f32(ln_a.bias)), ln_i=(_f32(ln_i.weight), _f32(ln_i.bias)),
-                ln_f=(_f32(ln_f.weight), _f32(ln_f.bias)),
-                ln_ffn=(_f32(ffn.ffn_layernorm.weight), _f32(ffn.ffn_layernorm.bias)),
+                qkv=_fold_ln(torch.cat([q.weight, k.weight, v.weight], 0), torch.cat([q.bias, k.bias, v.bias], 0), ln_a),
+                o=_fold_ln(o.weight, o.bias, ln_i),
+                fc1=_fold_ln(ffn.fc1.weight, ffn.fc1.bias, ln_f),
+                fc2=_fold_ln(ffn.fc2.weight, ffn.fc2.bias, ffn.ffn_layernorm),
             ))
         self._packed = dict(
             layers=layers,
-            ln_out=(_f32(self.layer_norm.weight), _f32(self.layer_norm.bias)),
-            w_out=_bf16(self.output_projection.weight),
+            out=_fold_ln(self.output_projection.weight, self.output_projection.bias, self.layer_norm),
             embed=_f32(self.embed_tokens.weight), pos=_f32(self.embed_positions.weight),
             xpos_scale=_f32(self.layers[0].self_attn.xpos.scale) if len(self.layers) else None,
         )
@@ -339,35 +348,46 @@ class Decoder(nn.Module):
             raise TypeError("token ids must be int64")
 
     def run_layers(self, x: torch.Tensor, B: int, T: int, logits: torch.Tensor | None = None, head: bool = True):
-        """24 x (sub-LN attention + sub-LN FFN) in place on the fp32 residual stream x [B*T, D],
-        then (``head``) final LayerNorm + LM head -> fp32 logits [B*T, vocab]."""
+        """24 x (sub-LN attention + sub-LN FFN) in place on the fp32 residual stream x [B*T, D], then (``head``)
+        final LayerNorm + LM head -> fp32 logits [B*T, vocab].  5 launches per layer: every LayerNorm is folded
+        into its consumer GEMM (row statistics travel as partial sums from the producer's epilogue)."""
         cfg, p, ws = self.cfg, self._pack(), self._ws
         M, D, F, H = B * T, cfg.dim, cfg.ffn, cfg.heads
         dev = x.device
-        h = ws.get("h", (M, D), torch.bfloat16, dev)
-        qkv = ws.get("qkv", (M, 3 * D), torch.bfloat16, dev)
-        att = ws.get("att", (M, D), torch.bfloat16, dev)
-        mid = ws.get("mid", (M, F), torch.bfloat16, dev)
-        midn = ws.get("midn", (M, F), torch.bfloat16, dev)
+        bf, f32 = torch.bfloat16, torch.float32
+        xb = ws.get("xb", (M, D), bf, dev)                       # bf16 copy of the residual stream (GEMM operand)
+        qkv = ws.get("qkv", (M, 3 * D), bf, dev)
+        att = ws.get("att", (M, D), bf, dev)
+        mid = ws.get("mid", (M, F), bf, dev)
+        # per-row partial (sum, sumsq) emitted by each producer, summed by the consumer's folded LayerNorm
+        st_in = ws.get("st_in", (1, M, 2), f32, dev)
+        st_a = ws.get("st_a", ((D + 255) // 256, M, 2), f32, dev)
+        st_b = ws.get("st_b", ((D + 255) // 256, M, 2), f32, dev)
+        st_att = ws.get("st_att", (H, M, 2), f32, dev)
+        st_mid = ws.get("st_mid", ((F + 255) // 256, M, 2), f32, dev)
         tabs = self._xpos(T, dev)
         scale = (D // H) ** -0.5
+        eps = cfg.eps
+        ops.rowstats_cast(x, xb, st_in)
+        cur = st_in
         for L in p["layers"]:
-            ops.layernorm(x, *L["ln_a"], h, eps=cfg.eps)
-            ops.gemm(h, L["w_qkv"], qkv, bias=L["b_qkv"], xpos=(tabs[0], tabs[1], tabs[2], tabs[3]), seq_len=T)
+            w, c, d = L["qkv"]                                   # self_attn_layer_norm -> q|k|v (+bias, xPos)
+            ops.gemm(xb, w, qkv, bias=d, ln=(cur, c, D, eps), xpos=(tabs[0], tabs[1], tabs[2], tabs[3]), seq_len=T)
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, batch=B, heads=H, seq_len=T, causal=True,
-                          scale=scale)
-            ops.layernorm(att, *L["ln_i"], h, eps=cfg.eps)
-            ops.gemm(h, L["w_o"], x, bias=L["b_o"], res=x)
-            ops.layernorm(x, *L["ln_f"], h, eps=cfg.eps)
-            ops.gemm(h, L["w_fc1"], mid, bias=L["b_fc1"], act=_abi.KX_ACT_GELU)
-            ops.layernorm(mid, *L["ln_ffn"], midn, eps=cfg.eps)
-            ops.gemm(midn, L["w_fc2"], x, bias=L["b_fc2"], res=x)
+                          scale=scale, stats_out=st_att)
+            w, c, d = L["o"]                                     # inner_attn_ln -> out_proj (+bias, +residual)
+            ops.gemm(att, w, x, bias=d, res=x, ln=(st_att, c, D, eps), stats_out=st_a, out2=xb)
+            w, c, d = L["fc1"]                                   # final_layer_norm -> fc1 (+bias, GELU)
+            ops.gemm(xb, w, mid, bias=d, act=_abi.KX_ACT_GELU, ln=(st_a, c, D, eps), stats_out=st_mid)
+            w, c, d = L["fc2"]                                   # ffn_layernorm -> fc2 (+bias, +residual)
+            ops.gemm(mid, w, x, bias=d, res=x, ln=(st_mid, c, F, eps), stats_out=st_b, out2=xb)
+            cur = st_b
         if not head:
             return x
-        ops.layernorm(x, *p["ln_out"], h, eps=cfg.eps)
+        w, c, d = p["out"]                                       # decoder.layer_norm -> output_projection
         if logits is None:
-            logits = torch.empty(M, p["w_out"].shape[0], dtype=torch.float32, device=dev)
-        ops.gemm(h, p["w_out"], logits)
+            logits = torch.empty(M, w.shape[0], dtype=torch.float32, device=dev)
+        ops.gemm(xb, w, logits, bias=d, ln=(cur, c, D, eps))
         return logits
 
     def forward(self, prev_output_tokens, **kwargs):

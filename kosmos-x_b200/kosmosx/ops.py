@@ -65,8 +65,12 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=None, act=_abi.KX_ACT_NONE,
          grp=None, add_tab=None, add_off=0, xpos=None, seq_len=0, cta_group=0, block_n=0, max_ctas=0, M=None,
-         epi_mode=0):
-    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; out bf16 or fp32 (2-D views, row pitch = stride(0))."""
+         epi_mode=0, ln=None, stats_out=None, out2=None):
+    """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; out bf16 or fp32 (2-D views, row pitch = stride(0)).
+
+    ln = (partials fp32 [tiles, M, 2], c fp32 [N], cols, eps): LayerNorm of the rows of `a` folded into the
+    epilogue (w must carry gamma, bias must be W.beta + b).  stats_out fp32 [ceil(N/256), M, 2] and out2
+    (bf16 copy of an fp32 out) make this GEMM the producer of the next fold."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
     g = GemmArgs()
@@ -95,14 +99,35 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
         g.seq_len = seq_len
         g.d_model = g.N // 3
     g.cta_group, g.block_n, g.max_ctas, g.epi_mode = cta_group, block_n, max_ctas, epi_mode
+    if ln is not None:
+        part, c, cols, eps = ln
+        _req(part, torch.float32, "ln partials")
+        if part.ndim != 3 or part.shape[1] != g.M or part.shape[2] != 2 or not part.is_contiguous():
+            raise ValueError(f"gemm: ln partials must be contiguous [tiles, M={g.M}, 2], got {tuple(part.shape)}")
+        if c.numel() != g.N:
+            raise ValueError("gemm: ln c must have N entries")
+        g.ln_part, g.ln_c, g.ln_tiles, g.ln_cols, g.ln_eps = part.data_ptr(), c.data_ptr(), part.shape[0], cols, eps
+    if stats_out is not None:
+        _req(stats_out, torch.float32, "stats_out")
+        if tuple(stats_out.shape) != ((g.N + 255) // 256, g.M, 2) or not stats_out.is_contiguous():
+            raise ValueError(f"gemm: stats_out must be contiguous [{(g.N + 255) // 256}, {g.M}, 2]")
+        g.stats_out = stats_out.data_ptr()
+    if out2 is not None:
+        _req(out2, torch.bfloat16, "out2")
+        g.out2, g.ld_out2 = out2.data_ptr(), out2.stride(0)
     with _Timed("gemm", 2.0 * g.M * g.N * g.K,
                 2.0 * (g.M + g.N) * g.K + g.M * g.N * (out.element_size() + (4 if res is not None else 0))):
         check(lib.kx_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), g, _stream()), "kx_gemm_bf16")
     return out
 
 
-def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale):
-    """q, k, v: bf16 2-D views [batch*seq_len, heads*64] sharing one row pitch; out bf16 [batch*seq_len, >=heads*64]."""
+def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=None):
+    """q, k, v: bf16 2-D views [batch*seq_len, heads*64] sharing one row pitch; out bf16 [batch*seq_len, >=heads*64].
+    stats_out fp32 [heads, batch*seq_len, 2]: per-head partial (sum, sumsq) of every output row."""
+    if stats_out is not None:
+        _req(stats_out, torch.float32, "stats_out")
+        if tuple(stats_out.shape) != (heads, batch * seq_len, 2) or not stats_out.is_contiguous():
+            raise ValueError("attention: stats_out must be contiguous [heads, batch*seq_len, 2]")
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
         _req(t, torch.bfloat16, n)
     if not (q.stride(0) == k.stride(0) == v.stride(0)):
@@ -110,7 +135,8 @@ def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale):
     fl = 4.0 * batch * heads * seq_len * seq_len * 64 * (0.5 if causal else 1.0)
     with _Timed("attn_causal" if causal else "attn_full", fl, 8.0 * batch * heads * seq_len * 64):
         check(lib.kx_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
-                              batch, heads, seq_len, 1 if causal else 0, float(scale), _stream()), "kx_attn_fwd")
+                              batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out), _stream()),
+              "kx_attn_fwd")
     return out
 
 
@@ -139,6 +165,20 @@ def layernorm(x, gamma, beta, out, *, eps=1e-5, pre_add=None, pre_add_group=0, g
                                    out.data_ptr(), 1 if out.dtype == torch.float32 else 0, out.stride(0), r,
                                    x.shape[1], g[0], g[1], g[2], _stream()), "kx_layernorm_fwd")
     return out
+
+
+def rowstats_cast(x, xb, stats):
+    """xb = bf16(x); stats[0, m] = (sum, sumsq) of xb's row m.  x fp32 [rows, n], stats fp32 [1, rows, 2]."""
+    _req(x, torch.float32, "x")
+    _req(xb, torch.bfloat16, "xb")
+    _req(stats, torch.float32, "stats")
+    rows, n = x.shape
+    if stats.numel() != rows * 2 or not stats.is_contiguous():
+        raise ValueError("rowstats_cast: stats must be contiguous [1, rows, 2]")
+    with _Timed("rowstats_cast", 0.0, 6.0 * rows * n):
+        check(lib.kx_rowstats_cast(x.data_ptr(), x.stride(0), xb.data_ptr(), xb.stride(0), stats.data_ptr(), rows, n,
+                                   _stream()), "kx_rowstats_cast")
+    return xb
 
 
 def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_start, n_img, err_flag=None):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in kosmosx_b200.h but not exported"
     assert set(names) == set(_abi.SIGNATURES), "ctypes SIGNATURES and header disagree"
-    assert _abi.lib.kx_abi_version() == 2
+    assert _abi.lib.kx_abi_version() == 3
 
 
 def test_gemm_args_struct_matches_header():
@@ -70,7 +70,8 @@ def test_argument_validation_happens_before_any_launch():
     assert _abi.lib.kx_gemm_bf16(addr, 7, addr, 8, g, None) == -1          # row pitch not 16-byte aligned
     assert _abi.lib.kx_layernorm_fwd(addr, 0, 12, None, 0, 0, addr, addr, 1e-5, addr, 0, 16, 4, 12, 0, 0, 0, None) == -1
     assert "multiple of 8" in _abi.last_error()
-    assert _abi.lib.kx_attn_fwd(addr, addr, addr, 8, addr, 8, 0, 1, 1, 1, 0.125, None) == -1
+    assert _abi.lib.kx_attn_fwd(addr, addr, addr, 8, addr, 8, 0, 1, 1, 1, 0.125, None, None) == -1
+    assert _abi.lib.kx_rowstats_cast(addr, 12, addr, 16, addr, 4, 12, None) == -1      # n not a multiple of 8
 
 
 def test_public_surface_matches_reference():

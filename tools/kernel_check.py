@@ -243,6 +243,73 @@ def case_layernorm():
     return ok
 
 
+def case_ln_fold():
+    """LayerNorm folded into the consumer GEMM: producers emit a bf16 copy + per-row partial
+    (sum, sumsq); the consumer applies rstd*(acc - mean*c) + d.  Checked against torch layer_norm + matmul."""
+    import torch.nn.functional as F
+    torch.manual_seed(7)
+    ok = True
+    for (M, K, N, N2) in ((1000, 512, 768, 320), (70, 128, 128, 256), (515, 2048, 300, 1002), (16384, 2048, 2048, 512)):
+        x = torch.randn(M, K, device=dev) * 2 + 0.3
+        gamma, beta = torch.rand(K, device=dev) + 0.5, torch.randn(K, device=dev) * 0.1
+        W = torch.randn(N, K, device=dev) / math.sqrt(K)
+        b = torch.randn(N, device=dev) * 0.1
+        xb = torch.empty(M, K, device=dev, dtype=torch.bfloat16)
+        st = torch.zeros(1, M, 2, device=dev)
+        ops.rowstats_cast(x, xb, st)
+        ok &= bool(torch.equal(xb, x.bfloat16()))
+        xf = xb.float()
+        ok &= report(f"rowstats sum M={M} K={K}", st[0, :, 0], xf.sum(1), 1e-3 * math.sqrt(K))
+        ok &= report(f"rowstats sumsq M={M} K={K}", st[0, :, 1], (xf * xf).sum(1), 2e-5 * K * 5)
+        wf = (W * gamma).bfloat16()
+        c = wf.double().sum(1).float()
+        d = (W.double() @ beta.double() + b.double()).float()
+        # consumer 1: fp32 out + residual in place + bf16 copy + stats for the next fold
+        res0 = torch.randn(M, N, device=dev)
+        y = res0.clone()
+        yb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        st2 = torch.zeros((N + 255) // 256, M, 2, device=dev)
+        ops.gemm(xb, wf, y, bias=d, res=y, ln=(st, c, K, 1e-5), stats_out=st2, out2=yb)
+        mu, var = xf.mean(1, keepdim=True), xf.var(1, unbiased=False, keepdim=True)
+        ref = ((xf - mu) * torch.rsqrt(var + 1e-5)) @ wf.float().T + d + res0
+        ok &= report(f"fold gemm (same rounded W') M={M} K={K} N={N}", y, ref, 3e-3)
+        ref32 = F.layer_norm(xf, (K,), gamma, beta, 1e-5) @ W.T + b + res0
+        ok &= report(f"fold gemm vs layer_norm+linear fp32", y, ref32, 4e-2)
+        good = bool(torch.equal(yb, y.bfloat16()))
+        print(f"[{'OK' if good else 'FAIL'}] bf16 copy equals bf16(out)")
+        ok &= good
+        ybf = yb.float()
+        ok &= report("producer stats sum", st2[:, :, 0].sum(0), ybf.sum(1), 1e-3 * math.sqrt(N) + 1e-3)
+        ok &= report("producer stats sumsq", st2[:, :, 1].sum(0), (ybf * ybf).sum(1), 1e-4 * N)
+        # consumer 2: chained fold over multi-tile partials, bf16 out + GELU + stats
+        g2, b2 = torch.rand(N, device=dev) + 0.5, torch.randn(N, device=dev) * 0.1
+        W2 = torch.randn(N2, N, device=dev) / math.sqrt(N)
+        wf2 = (W2 * g2).bfloat16()
+        c2 = wf2.double().sum(1).float()
+        d2 = (W2.double() @ b2.double()).float()
+        z = torch.zeros(M, N2, device=dev, dtype=torch.bfloat16) if (N2 * 2) % 16 == 0 else torch.zeros(M, N2, device=dev)
+        st3 = torch.zeros((N2 + 255) // 256, M, 2, device=dev) if z.dtype == torch.bfloat16 else None
+        ops.gemm(yb, wf2, z, bias=d2, act=_abi.KX_ACT_GELU, ln=(st2, c2, N, 1e-5), stats_out=st3)
+        mu2, var2 = ybf.mean(1, keepdim=True), ybf.var(1, unbiased=False, keepdim=True)
+        ref2 = F.gelu(((ybf - mu2) * torch.rsqrt(var2 + 1e-5)) @ wf2.float().T + d2)
+        ok &= report(f"chained fold + gelu N2={N2} ({z.dtype})", z, ref2, 2e-2 if z.dtype == torch.bfloat16 else 3e-3)
+        if st3 is not None:
+            zf = z.float()
+            ok &= report("bf16 producer stats sum", st3[:, :, 0].sum(0), zf.sum(1), 1e-3 * math.sqrt(N2) + 1e-3)
+            ok &= report("bf16 producer stats sumsq", st3[:, :, 1].sum(0), (zf * zf).sum(1), 1e-4 * N2)
+    # attention: per-head partial statistics of the stored rows
+    B, H, T = 2, 4, 300
+    qkv = torch.randn(B * T, 3 * H * 64, device=dev).bfloat16()
+    out = torch.empty(B * T, H * 64, device=dev, dtype=torch.bfloat16)
+    sta = torch.zeros(H, B * T, 2, device=dev)
+    ops.attention(qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:], out, batch=B, heads=H, seq_len=T,
+                  causal=True, scale=0.125, stats_out=sta)
+    of = out.float().view(B * T, H, 64)
+    ok &= report("attention stats sum", sta[:, :, 0].T, of.sum(-1), 1e-4)
+    ok &= report("attention stats sumsq", sta[:, :, 1].T, (of * of).sum(-1), 1e-4)
+    return ok
+
+
 def case_embed():
     torch.manual_seed(5)
     ok = True
