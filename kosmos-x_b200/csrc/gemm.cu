@@ -38,8 +38,9 @@ struct GemmCfg {
     static constexpr int EPI_BYTES = TMA_EPI ? 4 * EPI_WARP_BYTES : 0;
     static constexpr int RING_BUDGET = TMA_EPI ? (160 * 1024) : (192 * 1024);
     static constexpr int STAGES = RING_BUDGET / STAGE_BYTES;
-    static constexpr int BAR_BYTES = 1024;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static constexpr int VEC_BYTES = TMA_EPI ? 2 * BN * 4 : 0;   // this tile's bias[] and ln_c[] columns, staged once per tile
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + VEC_BYTES + BAR_BYTES;   // base must be 1 KB aligned
     static constexpr int TMEM_COLS = 2 * BN;                                    // power of two for BN in {64,128,256}
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -85,6 +86,22 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_
 }
 
 // bias -> [xPos rotation] -> activation on one 32-column chunk of row m (shared by both store paths)
+// (sum, sumsq) of eight stored bf16 values; `full` skips the column-bound checks of the N tail.
+__device__ __forceinline__ void stats_add8(const uint4& pk, bool full, int n, int N, float& s1, float& s2) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float2 r = __bfloat1622float2(h[u]);
+        if (full) {
+            s1 += r.x + r.y;
+            s2 = fmaf(r.x, r.x, fmaf(r.y, r.y, s2));
+        } else {
+            if (n + 2 * u < N) { s1 += r.x; s2 = fmaf(r.x, r.x, s2); }
+            if (n + 2 * u + 1 < N) { s1 += r.y; s2 = fmaf(r.y, r.y, s2); }
+        }
+    }
+}
+
 // Row statistics of the A operand for a folded LayerNorm: fixed-order sum of the producer's partials.
 __device__ __forceinline__ float2 ln_row_stats(const GemmEpi& ep, int m) {
     float s1 = 0.f, s2 = 0.f;
@@ -97,8 +114,28 @@ __device__ __forceinline__ float2 ln_row_stats(const GemmEpi& ep, int m) {
     return make_float2(mean, rsqrtf(var + ep.ln_eps));
 }
 
+// sb / sc: this chunk's 32 bias / ln_c values staged in shared memory (zero padded past N), or null = read global.
 template <int EPI>
-__device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32], int m, int n0, bool full, float2 ln) {
+__device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32], int m, int n0, bool full, float2 ln,
+                                              const float* sb = nullptr, const float* sc = nullptr) {
+    if (sb != nullptr) {
+        if (ep.ln_part != nullptr) {
+            const float nmr = -ln.x * ln.y;             // y = rstd*acc + (-mean*rstd)*c
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 c = *reinterpret_cast<const float4*>(sc + i);
+                f[i] = fmaf(nmr, c.x, f[i] * ln.y); f[i + 1] = fmaf(nmr, c.y, f[i + 1] * ln.y);
+                f[i + 2] = fmaf(nmr, c.z, f[i + 2] * ln.y); f[i + 3] = fmaf(nmr, c.w, f[i + 3] * ln.y);
+            }
+        }
+        if (ep.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(sb + i);
+                f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+            }
+        }
+    } else {
     if (ep.ln_part != nullptr) {
         const float nmr = -ln.x * ln.y;                 // y = rstd*acc + (-mean*rstd)*c
         if (full) {
@@ -126,6 +163,7 @@ __device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32],
             for (int i = 0; i < 32; ++i)
                 if (n0 + i < ep.N) f[i] += __ldg(ep.bias + n0 + i);
         }
+    }
     }
 
     if constexpr (EPI == KX_EPI_QKV_XPOS) {
@@ -249,13 +287,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmOut2, const GemmEpi ep) {
     using Cfg = GemmCfg<CG, BN, TMA_EPI>;
     constexpr int STAGES = Cfg::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B atoms need 1024-byte alignment (identical offset in both CTAs of a pair)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // SWIZZLE_128B atoms need 1024-byte alignment (identical offset in both CTAs of a pair); the kernel has no
+    // static shared memory, so the dynamic window starts at the aligned base of the CTA's allocation.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023)) { printf("kx gemm: dynamic smem base not 1024-aligned\n"); __trap(); }
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
     uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;          // 1024-aligned (stage sizes are multiples of 1 KB)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_BYTES);
+    float* s_vec = reinterpret_cast<float*>(smem_epi + Cfg::EPI_BYTES);    // [2][BN]: bias, ln_c of the current tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_BYTES + Cfg::VEC_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
@@ -424,6 +464,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const bool rows_ok = m_row0 < ep.M;          // warp-uniform; rows >= M inside a box are clipped by TMA
                 const float2 ln = (ep.ln_part != nullptr && m < ep.M) ? ln_row_stats(ep, m) : make_float2(0.f, 1.f);
                 float s1 = 0.f, s2 = 0.f;
+                {   // stage this tile's bias / ln_c columns once (the 4 epilogue warps walk the same tile sequence)
+                    constexpr int CPL = BN / 128;                       // columns per lane
+                    const int col = (q * 32 + lane) * CPL;
+                    float bv[CPL], cv[CPL];
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) {
+                        const bool in = nb + col + u < ep.N;
+                        bv[u] = (in && ep.bias != nullptr) ? __ldg(ep.bias + nb + col + u) : 0.f;
+                        cv[u] = (in && ep.ln_part != nullptr) ? __ldg(ep.ln_c + nb + col + u) : 0.f;
+                    }
+                    named_bar_sync(1, 128);                             // previous tile's readers are done
+#pragma unroll
+                    for (int u = 0; u < CPL; ++u) { s_vec[col + u] = bv[u]; s_vec[BN + col + u] = cv[u]; }
+                    named_bar_sync(1, 128);
+                }
                 auto issue_res = [&](int c) {
                     if (lane == 0) {
                         const uint32_t rb = nres % 3;
@@ -439,6 +494,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
 #pragma unroll 1
                 for (int c = 0; c < nchunks; ++c) {
                     const int n0 = nb + c * 32;
@@ -447,14 +504,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         __syncwarp();
                         if (has_res && c + 1 < nchunks) issue_res(c + 1);
                     }
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    if (!rows_ok) continue;
                     float f[32];
+                    tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    epilogue_math<EPI>(ep, f, m, n0, n0 + 32 <= ep.N, ln);
+                    if (c + 1 < nchunks) tmem_ld32(taddr + (c + 1) * 32, v);      // in flight during this chunk's math
+                    if (!rows_ok) continue;
+                    const bool full = n0 + 32 <= ep.N;
+                    epilogue_math<EPI>(ep, f, m, n0, full, ln, s_vec + c * 32, s_vec + BN + c * 32);
                     const uint32_t ub = unit % 3;
                     uint8_t* mb = st_main + ub * EPI_STAGE_BYTES + lane * 128;
                     if constexpr (OUT_F32) {
@@ -479,15 +536,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 pk.z = pack_bf16(f[8 * g + 4], f[8 * g + 5]);
                                 pk.w = pack_bf16(f[8 * g + 6], f[8 * g + 7]);
                                 *reinterpret_cast<uint4*>(cb + ((g ^ sw64) << 4)) = pk;
-                                if (has_stats) {          // statistics of what the consumer GEMM will read: the bf16 copy
-                                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        const float2 r = __bfloat1622float2(h[u]);
-                                        if (n0 + 8 * g + 2 * u < ep.N) { s1 += r.x; s2 = fmaf(r.x, r.x, s2); }
-                                        if (n0 + 8 * g + 2 * u + 1 < ep.N) { s1 += r.y; s2 = fmaf(r.y, r.y, s2); }
-                                    }
-                                }
+                                if (has_stats)            // statistics of what the consumer GEMM will read: the bf16 copy
+                                    stats_add8(pk, full, n0 + 8 * g, ep.N, s1, s2);
                             }
                         } else if (has_stats) {
 #pragma unroll
@@ -515,15 +565,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             pk.z = pack_bf16(f[8 * g + 4], f[8 * g + 5]);
                             pk.w = pack_bf16(f[8 * g + 6], f[8 * g + 7]);
                             *reinterpret_cast<uint4*>(mb + (((half * 4 + g) ^ sw) << 4)) = pk;
-                            if (has_stats) {
-                                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const float2 r = __bfloat1622float2(h[u]);
-                                    if (n0 + 8 * g + 2 * u < ep.N) { s1 += r.x; s2 = fmaf(r.x, r.x, s2); }
-                                    if (n0 + 8 * g + 2 * u + 1 < ep.N) { s1 += r.y; s2 = fmaf(r.y, r.y, s2); }
-                                }
-                            }
+                            if (has_stats) stats_add8(pk, full, n0 + 8 * g, ep.N, s1, s2);
                         }
                         if (half == 1 || c == nchunks - 1) {
                             fence_proxy_async_smem();

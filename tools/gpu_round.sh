@@ -15,7 +15,7 @@ for w in $what; do
     benchng)  timeout 900 python bench.py --steps 10 --warmup 3 --graph 0 --no-cpu > "$out/bench_nograph.json" 2> "$out/bench_nograph.err"; echo "bench(nograph) exit $?" | tee -a "$out/summary.txt"; cat "$out/bench_nograph.json"; tail -5 "$out/bench_nograph.err";;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:^(attn_|broadcast_rows|embed_splice|gemm_bf16|im2col|layernorm|perceiver_x)" -s 413 -c 413 --csv --log-file "$out/launches.csv" python tools/profile_step.py --steps 3 > "$out/launches.log" 2>&1; echo "launches exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/launches.log";;
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 4 -o "$out/prof_gemm" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_gemm.log" 2>&1; echo "ncu_gemm exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_gemm.log";;
-    ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
+    ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_pp -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
     kcheck)   bash tools/run_kernel_checks.sh bench;;
     attn_ab)  for impl in 1 0; do KX_ATTN_IMPL=$impl timeout 300 python tools/kernel_check.py attn > "$out/attn_impl$impl.log" 2>&1; echo "attn impl=$impl exit $?" | tee -a "$out/summary.txt"; grep -E "^\[(OK|FAIL)\]|^==|rror|timeout" "$out/attn_impl$impl.log" | tail -12;
                 KX_ATTN_IMPL=$impl timeout 300 python tools/kernel_check.py bench_attn > "$out/bench_attn_impl$impl.log" 2>&1; echo "bench_attn impl=$impl exit $?" | tee -a "$out/summary.txt"; grep -E "attn " "$out/bench_attn_impl$impl.log"; done;;
