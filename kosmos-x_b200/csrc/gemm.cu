@@ -39,7 +39,8 @@ struct GemmCfg {
     static constexpr int RING_BUDGET = TMA_EPI ? (160 * 1024) : (192 * 1024);
     static constexpr int STAGES = RING_BUDGET / STAGE_BYTES;
     static constexpr int VEC_BYTES = TMA_EPI ? 2 * BN * 4 : 0;   // this tile's bias[] and ln_c[] columns, staged once per tile
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 512;                       // (2*STAGES + 16) mbarriers + the TMEM slot; STAGES <= 8
+    static_assert((2 * STAGES + 16) * 8 + 8 <= BAR_BYTES, "barrier block");
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + VEC_BYTES + BAR_BYTES;   // base must be 1 KB aligned
     static constexpr int TMEM_COLS = 2 * BN;                                    // power of two for BN in {64,128,256}
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
