@@ -10,8 +10,11 @@
 //   warps 4-7  softmax of tile B   } (128 fp32), max with 3-input FMNMX, exp2 on packed FFMA2 operands,
 //                                    P (bf16 pairs) written back over S in TMEM with tcgen05.st
 //   warp 8     TMA producer: Q tiles once, K/V 128-row blocks through 3-slot rings
-//   warp 9     MMA issuer: S_w = Q_w.K^T (SS) and O_w += P_w.V (A operand = P in TMEM, TS form);
-//              while one tile's softmax runs, the tensor core works on the other tile
+//   warp 9     MMA issuer: S_w = Q_w.K^T (SS) and O_w += P_w.V (A operand = P in TMEM, TS form)
+// TMEM holds, per tile, S (128 fp32 columns), P (64 columns of bf16 pairs) and O (64 columns): 2 x 256 = 512.
+// Because P does not alias S, S_w(j+1) is issued as soon as the softmax has pulled S_w(j) into registers
+// (s_free), i.e. the next score tile is computed while the current one is being exponentiated; the
+// tensor-core latency is off the softmax critical path and the kernel is bound by the MUFU (exp2) rate.
 // O accumulates in TMEM across blocks.  The running maximum is only "committed" (O and l rescaled)
 // when a new block raises it by more than 2^8 (lazy rescale): exp2 arguments stay <= 8, so P fits
 // bf16 and the final O/l is unchanged mathematically.
@@ -28,7 +31,9 @@ constexpr int PP_SMEM_K = PP_SMEM_Q + 2 * PP_TILE_BYTES;
 constexpr int PP_SMEM_V = PP_SMEM_K + PP_KV_STAGES * PP_TILE_BYTES;
 constexpr int PP_SMEM_BAR = PP_SMEM_V + PP_KV_STAGES * PP_TILE_BYTES;
 constexpr int PP_SMEM_BYTES = PP_SMEM_BAR + 256;
-constexpr int PP_TMEM_COLS = 512;                    // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+constexpr int PP_TMEM_COLS = 512;                    // S_A [0,128) S_B [128,256) P_A [256,320) P_B [320,384) O_A [384,448) O_B [448,512)
+constexpr int PP_TMEM_P = 256;
+constexpr int PP_TMEM_O = 384;
 constexpr float PP_RESCALE_THRESHOLD = 8.0f;         // log2 units
 
 struct AttnPPParams {
@@ -54,7 +59,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint64_t* s_full = bars + 13;                     // [2] per tile
     uint64_t* p_full = bars + 15;                     // [2]
     uint64_t* o_full = bars + 17;                     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* s_free = bars + 19;                     // [2] softmax has read S_w out of TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,7 +82,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int w = 0; w < 2; ++w) {
-            mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 128); mbar_init(&o_full[w], 1);
+            mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 128); mbar_init(&o_full[w], 1); mbar_init(&s_free[w], 128);
         }
         fence_mbar_init();
     }
@@ -123,8 +129,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint64_t vdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_V + slot * PP_TILE_BYTES), PP_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)      // 16 keys per step: 8 TMEM columns of P, 16 V rows = 2 KB
-                    umma_bf16_ts(tmem_base + 256 + w * 64, tmem_base + w * 128 + k * 8, vdesc + k * (2048 >> 4), idesc_o,
-                                 (!first || k != 0) ? 1u : 0u);
+                    umma_bf16_ts(tmem_base + PP_TMEM_O + w * 64, tmem_base + PP_TMEM_P + w * 64 + k * 8,
+                                 vdesc + k * (2048 >> 4), idesc_o, (!first || k != 0) ? 1u : 0u);
             };
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
@@ -140,31 +146,36 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 int sn = s + 1;
                 uint32_t phn = ph;
                 if (sn == PP_KV_STAGES) { sn = 0; phn ^= 1; }
-                mbar_wait(&v_full[s], ph);
+                // ---- tile A: next scores first (needs only S_A(j) to have been read), then P.V of this block
+                if (j + 1 < nblk0) {
+                    mbar_wait(&s_free[0], j & 1);
+                    mbar_wait(&k_full[sn], phn);
+                    tc_fence_after();
+                    issue_s(0, sn);
+                    umma_commit(&s_full[0]);
+                }
                 if (j < nblk0) {
                     mbar_wait(&p_full[0], j & 1);
+                    mbar_wait(&v_full[s], ph);
                     tc_fence_after();
                     issue_pv(0, s, j == 0);
                     umma_commit(&o_full[0]);
-                    if (j + 1 < nblk0) {
-                        mbar_wait(&k_full[sn], phn);
-                        tc_fence_after();
-                        issue_s(0, sn);
-                        umma_commit(&s_full[0]);
-                    }
                 }
-                mbar_wait(&p_full[1], j & 1);
-                tc_fence_after();
-                issue_pv(1, s, j == 0);
-                umma_commit(&o_full[1]);
-                umma_commit(&v_empty[s]);
+                // ---- tile B
                 if (j + 1 < nblk1) {
+                    mbar_wait(&s_free[1], j & 1);
                     mbar_wait(&k_full[sn], phn);
                     tc_fence_after();
                     issue_s(1, sn);
                     umma_commit(&s_full[1]);
                     umma_commit(&k_empty[sn]);
                 }
+                mbar_wait(&p_full[1], j & 1);
+                mbar_wait(&v_full[s], ph);
+                tc_fence_after();
+                issue_pv(1, s, j == 0);
+                umma_commit(&o_full[1]);
+                umma_commit(&v_empty[s]);
                 s = sn;
                 ph = phn;
             }
@@ -178,7 +189,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int nblk = w ? nblk1 : nblk0;
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t tmem_s = tmem_base + lane_addr + w * 128;
-        const uint32_t tmem_o = tmem_base + lane_addr + 256 + w * 64;
+        const uint32_t tmem_p = tmem_base + lane_addr + PP_TMEM_P + w * 64;
+        const uint32_t tmem_o = tmem_base + lane_addr + PP_TMEM_O + w * 64;
         const float sl2 = p.scale_log2;
         const uint64_t sl2x2 = pack_f32x2(sl2, sl2);
         float m_ref = -INFINITY;      // reference maximum the exponentials are taken against (raw score units)
@@ -192,6 +204,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[c * 32]));
             tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&s_free[w]);                      // S_w may be overwritten by the next Q.K^T now
 
             // ---- mask: only the diagonal block (causal) and the ragged tail block
             const bool need_mask = (kv0 + 128 > T) || (CAUSAL && (kv0 + 127 > q0 + w * 128));
@@ -258,9 +272,13 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             float a0, a1;
             unpack_f32x2(fadd2(acc0, acc1), a0, a1);
             l_run += a0 + a1;
-            // P over S: columns [0,64) of this tile's S region, element pair (2c, 2c+1) in column c
-            tmem_st32(tmem_s, reinterpret_cast<uint32_t(&)[32]>(pv[0]));
-            tmem_st32(tmem_s + 32, reinterpret_cast<uint32_t(&)[32]>(pv[32]));
+            // P region: element pair (2c, 2c+1) in column c.  P.V of the previous block must have consumed it.
+            if (j > 0) {
+                mbar_wait(&o_full[w], (j - 1) & 1);
+                tc_fence_after();
+            }
+            tmem_st32(tmem_p, reinterpret_cast<uint32_t(&)[32]>(pv[0]));
+            tmem_st32(tmem_p + 32, reinterpret_cast<uint32_t(&)[32]>(pv[32]));
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_full[w]);
