@@ -20,6 +20,7 @@
 // bf16 and the final O/l is unchanged mathematically.
 #include "kx_internal.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace kx {
 
@@ -45,7 +46,9 @@ struct AttnPPParams {
     long long total_rows;
 };
 
-template <bool CAUSAL>
+// POLY: 26 of every 64 element pairs take exp2 through exp2_poly_x2 (FMA pipes) instead of MUFU.EX2 —
+// the split that balances the two pipes for this loop (FA4's trick; the kernel is otherwise MUFU-bound).
+template <bool CAUSAL, bool POLY>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
@@ -146,7 +149,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 int sn = s + 1;
                 uint32_t phn = ph;
                 if (sn == PP_KV_STAGES) { sn = 0; phn ^= 1; }
-                // ---- tile A: next scores first (needs only S_A(j) to have been read), then P.V of this block
+                // ---- next score tiles first: each needs only its S_w(j) to have been pulled into registers,
+                //      so both are in flight long before either softmax finishes
                 if (j + 1 < nblk0) {
                     mbar_wait(&s_free[0], j & 1);
                     mbar_wait(&k_full[sn], phn);
@@ -154,14 +158,6 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     issue_s(0, sn);
                     umma_commit(&s_full[0]);
                 }
-                if (j < nblk0) {
-                    mbar_wait(&p_full[0], j & 1);
-                    mbar_wait(&v_full[s], ph);
-                    tc_fence_after();
-                    issue_pv(0, s, j == 0);
-                    umma_commit(&o_full[0]);
-                }
-                // ---- tile B
                 if (j + 1 < nblk1) {
                     mbar_wait(&s_free[1], j & 1);
                     mbar_wait(&k_full[sn], phn);
@@ -170,8 +166,15 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     umma_commit(&s_full[1]);
                     umma_commit(&k_empty[sn]);
                 }
-                mbar_wait(&p_full[1], j & 1);
+                // ---- then P.V of this block for both tiles
                 mbar_wait(&v_full[s], ph);
+                if (j < nblk0) {
+                    mbar_wait(&p_full[0], j & 1);
+                    tc_fence_after();
+                    issue_pv(0, s, j == 0);
+                    umma_commit(&o_full[0]);
+                }
+                mbar_wait(&p_full[1], j & 1);
                 tc_fence_after();
                 issue_pv(1, s, j == 0);
                 umma_commit(&o_full[1]);
@@ -262,9 +265,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
                 const uint64_t x = ffma2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2x2, nm2);
-                float x0, x1;
+                float x0, x1, e0, e1;
                 unpack_f32x2(x, x0, x1);
-                const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+                if (POLY && ((i % 5) == 1 || (i % 5) == 3)) {
+                    exp2_poly_x2(x0, x1, e0, e1);
+                } else {
+                    e0 = ex2_approx(x0);
+                    e1 = ex2_approx(x1);
+                }
                 const uint64_t e = pack_f32x2(e0, e1);
                 if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
                 pv[i] = pack_bf16(e0, e1);
@@ -341,16 +349,29 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.stats_out = reinterpret_cast<float2*>(stats_out);
     p.total_rows = static_cast<long long>(rows);
     static bool attr_set = false;
+    static bool poly = true;            // KX_ATTN_POLY=0 keeps every exp2 on the MUFU (A/B measurements)
     if (!attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        cudaError_t e2 = cudaFuncSetAttribute(attn_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("kx_attn_fwd: cudaFuncSetAttribute failed"); return KX_ERR_LAUNCH; }
+        const char* e = getenv("KX_ATTN_POLY");
+        poly = !(e && e[0] == '0');
+        cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        cudaError_t e2 = cudaFuncSetAttribute(attn_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        cudaError_t e3 = cudaFuncSetAttribute(attn_pp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        cudaError_t e4 = cudaFuncSetAttribute(attn_pp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+            set_error("kx_attn_fwd: cudaFuncSetAttribute failed");
+            return KX_ERR_LAUNCH;
+        }
         attr_set = true;
     }
     if (p.num_pairs > 65535) { set_error("kx_attn_fwd: sequence too long"); return KX_ERR_ARG; }
     dim3 grid(heads * batch, p.num_pairs);
-    if (causal) attn_pp_kernel<true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
-    else attn_pp_kernel<false><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    if (causal) {
+        if (poly) attn_pp_kernel<true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        else attn_pp_kernel<true, false><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    } else {
+        if (poly) attn_pp_kernel<false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        else attn_pp_kernel<false, false><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    }
     return check_launch("kx_attn_fwd");
 }
 
