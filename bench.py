@@ -56,6 +56,16 @@ def _peaks():
         return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def _ncu_traffic(launch_type: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of this type, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json: {launch type: bytes}); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(launch_type)
+    except Exception:
+        return None
+
+
 def forward_flops_per_seq(T=SEQ, images=1):
     """2mnk per GEMM, decoder attention causal-halved."""
     d, f, L = 2048, 8192, 24
@@ -266,16 +276,24 @@ def run_gpu(args):
         model(d_text, d_img)
     recs = ops.profile_end()
     model.cuda_graph = was_graph
-    agg = {}
+    agg, shapes = {}, {}
     for kind, fl, by, ms in recs:
+        if kind.startswith("gemm "):
+            sh = shapes.setdefault(kind[5:], [0, 0.0, 0.0, 0.0])
+            sh[0] += 1; sh[1] += fl; sh[2] += by; sh[3] += ms
+            kind = "gemm"
         a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
         a[0] += 1; a[1] += fl; a[2] += by; a[3] += ms
     tot_ms = sum(a[3] for a in agg.values())
     gemm = agg["gemm"]
     gemm_tflops = gemm[1] / (gemm[3] * 1e-3) / 1e12
+    top_name, top = max(shapes.items(), key=lambda kv: kv[1][3])          # the launch type with the largest time share
+    top_tflops = top[1] / (top[3] * 1e-3) / 1e12
     breakdown = {k: {"launches_per_step": a[0] // 2, "ms_per_step": a[3] / 2, "share": a[3] / tot_ms,
                      **({"tflops": a[1] / (a[3] * 1e-3) / 1e12} if a[1] else {"gbs": a[2] / (a[3] * 1e-3) / 1e9})}
                  for k, a in sorted(agg.items(), key=lambda kv: -kv[1][3])}
+    gemm_shapes = {k: {"launches_per_step": a[0] // 2, "us_per_launch": 1e3 * a[3] / a[0], "tflops": a[1] / (a[3] * 1e-3) / 1e12}
+                   for k, a in sorted(shapes.items(), key=lambda kv: -kv[1][3])[:8]}
 
     # ---- configs[1]: one decoder layer alone (B=8, T=2048)
     dec = model.decoder
@@ -298,11 +316,17 @@ def run_gpu(args):
                    "cuda_graph": bool(args.graph)},
         "step_tflops_per_gpu": step_tflops,
         "step_frac_of_bf16_peak": {"burst": step_tflops / peaks["burst"], "sustained": step_tflops / peaks["sustained"]},
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (all Linear layers, %d launches/step)" % (gemm[0] // 2),
-                     "achieved": gemm_tflops, "peak": peaks["sustained"], "peak_burst": peaks["burst"], "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peaks["sustained"], "frac_of_burst": gemm_tflops / peaks["burst"],
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel, launch type '%s' (%d launches/step; largest time share)"
+                               % (top_name, top[0] // 2),
+                     "achieved": top_tflops, "peak": peaks["sustained"], "peak_burst": peaks["burst"], "unit": "TFLOP/s",
+                     "frac": top_tflops / peaks["sustained"], "frac_of_burst": top_tflops / peaks["burst"],
+                     "flops_per_launch": top[1] / top[0], "us_per_launch": 1e3 * top[3] / top[0],
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                     "traffic": None, "share_of_step": gemm[3] / tot_ms},
+                     "traffic": _ncu_traffic(top_name), "share_of_step": top[3] / tot_ms,
+                     "all_gemm_launches": {"launches_per_step": gemm[0] // 2, "achieved": gemm_tflops,
+                                           "frac": gemm_tflops / peaks["sustained"],
+                                           "frac_of_burst": gemm_tflops / peaks["burst"], "share_of_step": gemm[3] / tot_ms}},
+        "gemm_launch_types": gemm_shapes,
         "decoder_block": {"config": "configs[1]: one decoder layer, B=8, T=2048, d=2048, 32 heads, bf16",
                           "ms": dec_block_ms, "tflops": blk_tflops, "frac_of_burst": blk_tflops / peaks["burst"],
                           "frac_of_sustained": blk_tflops / peaks["sustained"]},

@@ -115,7 +115,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     if out2 is not None:
         _req(out2, torch.bfloat16, "out2")
         g.out2, g.ld_out2 = out2.data_ptr(), out2.stride(0)
-    with _Timed("gemm", 2.0 * g.M * g.N * g.K,
+    with _Timed(f"gemm {g.M}x{g.N}x{g.K}" + ("+ln" if ln is not None else "") + ("+xpos" if xpos is not None else "")
+                + ("+gelu" if act == _abi.KX_ACT_GELU else "") + ("+res" if res is not None else ""),
+                2.0 * g.M * g.N * g.K,
                 2.0 * (g.M + g.N) * g.K + g.M * g.N * (out.element_size() + (4 if res is not None else 0))):
         check(lib.kx_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), g, _stream()), "kx_gemm_bf16")
     return out
