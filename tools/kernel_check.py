@@ -393,7 +393,8 @@ def case_bench():
 
 
 def case_bench_attn():
-    for B, H, T, causal in ((8, 32, 2048, True), (8, 16, 257, False), (1, 32, 114, True)):
+    for B, H, T, causal in ((8, 32, 2048, True), (8, 32, 1024, True), (8, 32, 4096, True), (8, 32, 256, True),
+                            (8, 16, 257, False), (1, 32, 114, True)):
         bench_attn(B, H, T, causal)
     return True
 
