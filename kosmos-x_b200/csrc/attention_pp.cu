@@ -44,11 +44,22 @@ struct AttnPPParams {
     float scale_log2;                                // scale * log2(e)
     float2* stats_out;                               // [heads][batch*seq_len] partial (sum, sumsq) of the stored row, or null
     long long total_rows;
+    long long* trace;                                // TRACE builds only: clock64 stamps of CTA (0,0), [3 roles][64 iters][8 points]
 };
+
+static long long* g_attn_trace = nullptr;            // kx_attn_set_trace
 
 // POLY: 26 of every 64 element pairs take exp2 through exp2_poly_x2 (FMA pipes) instead of MUFU.EX2 —
 // the split that balances the two pipes for this loop (FA4's trick; the kernel is otherwise MUFU-bound).
-template <bool CAUSAL, bool POLY>
+#define KX_TRACE(role, iter, point)                                                                    \
+    do {                                                                                               \
+        if constexpr (TRACE) {                                                                         \
+            if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (iter) < 64)               \
+                p.trace[((role) * 64 + (iter)) * 8 + (point)] = clock64();                             \
+        }                                                                                              \
+    } while (0)
+
+template <bool CAUSAL, bool POLY, bool TRACE = false>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
@@ -151,15 +162,19 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (sn == PP_KV_STAGES) { sn = 0; phn ^= 1; }
                 // ---- next score tiles first: each needs only its S_w(j) to have been pulled into registers,
                 //      so both are in flight long before either softmax finishes
+                KX_TRACE(2, j, 0);
                 if (j + 1 < nblk0) {
                     mbar_wait(&s_free[0], j & 1);
+                    KX_TRACE(2, j, 1);
                     mbar_wait(&k_full[sn], phn);
                     tc_fence_after();
                     issue_s(0, sn);
                     umma_commit(&s_full[0]);
                 }
+                KX_TRACE(2, j, 2);
                 if (j + 1 < nblk1) {
                     mbar_wait(&s_free[1], j & 1);
+                    KX_TRACE(2, j, 3);
                     mbar_wait(&k_full[sn], phn);
                     tc_fence_after();
                     issue_s(1, sn);
@@ -168,17 +183,21 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 // ---- then P.V of this block for both tiles
                 mbar_wait(&v_full[s], ph);
+                KX_TRACE(2, j, 4);
                 if (j < nblk0) {
                     mbar_wait(&p_full[0], j & 1);
+                    KX_TRACE(2, j, 5);
                     tc_fence_after();
                     issue_pv(0, s, j == 0);
                     umma_commit(&o_full[0]);
                 }
                 mbar_wait(&p_full[1], j & 1);
+                KX_TRACE(2, j, 6);
                 tc_fence_after();
                 issue_pv(1, s, j == 0);
                 umma_commit(&o_full[1]);
                 umma_commit(&v_empty[s]);
+                KX_TRACE(2, j, 7);
                 s = sn;
                 ph = phn;
             }
@@ -201,14 +220,17 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
         for (int j = 0; j < nblk; ++j) {
             const int kv0 = j * 128;
+            if (threadIdx.x == w * 128) KX_TRACE(w, j, 0);
             mbar_wait(&s_full[w], j & 1);
             tc_fence_after();
+            if (threadIdx.x == w * 128) KX_TRACE(w, j, 1);
             uint32_t sv[128];
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[c * 32]));
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&s_free[w]);                      // S_w may be overwritten by the next Q.K^T now
+            if (threadIdx.x == w * 128) KX_TRACE(w, j, 2);
 
             // ---- mask: only the diagonal block (causal) and the ragged tail block
             const bool need_mask = (kv0 + 128 > T) || (CAUSAL && (kv0 + 127 > q0 + w * 128));
@@ -257,29 +279,46 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
             }
 
+            if (threadIdx.x == w * 128) KX_TRACE(w, j, 3);
             // ---- p = exp2(s*scale - m_ref*scale): packed FFMA2, MUFU ex2, packed row sum, bf16x2 pack
             const float nm = -m_ref * sl2;
             const uint64_t nm2 = pack_f32x2(nm, nm);
             uint64_t acc0 = 0ull, acc1 = 0ull;         // (0.f, 0.f)
             uint32_t pv[64];
+            // Software pipeline over 4 groups of 16 pairs: the exponentials of group g are issued while the
+            // results of group g-1 (16 pairs = 32 MUFU issue slots earlier) are summed and packed, so no
+            // consumer waits on MUFU latency.  The exponentials overwrite the scores in place (sv).
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const uint64_t x = ffma2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2x2, nm2);
-                float x0, x1, e0, e1;
-                unpack_f32x2(x, x0, x1);
-                if (POLY && ((i % 5) == 1 || (i % 5) == 3)) {
-                    exp2_poly_x2(x0, x1, e0, e1);
-                } else {
-                    e0 = ex2_approx(x0);
-                    e1 = ex2_approx(x1);
+            for (int g = 0; g <= 4; ++g) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (g < 4) {
+                        const int i = g * 16 + k;
+                        const uint64_t x = ffma2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2x2, nm2);
+                        float x0, x1, e0, e1;
+                        unpack_f32x2(x, x0, x1);
+                        if (POLY && ((i % 5) == 1 || (i % 5) == 3)) {
+                            exp2_poly_x2(x0, x1, e0, e1);
+                        } else {
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
+                        sv[2 * i] = __float_as_uint(e0);
+                        sv[2 * i + 1] = __float_as_uint(e1);
+                    }
+                    if (g > 0) {
+                        const int i = (g - 1) * 16 + k;
+                        const float e0 = __uint_as_float(sv[2 * i]), e1 = __uint_as_float(sv[2 * i + 1]);
+                        const uint64_t e = pack_f32x2(e0, e1);
+                        if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+                        pv[i] = pack_bf16(e0, e1);
+                    }
                 }
-                const uint64_t e = pack_f32x2(e0, e1);
-                if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
-                pv[i] = pack_bf16(e0, e1);
             }
             float a0, a1;
             unpack_f32x2(fadd2(acc0, acc1), a0, a1);
             l_run += a0 + a1;
+            if (threadIdx.x == w * 128) KX_TRACE(w, j, 4);
             // P region: element pair (2c, 2c+1) in column c.  P.V of the previous block must have consumed it.
             if (j > 0) {
                 mbar_wait(&o_full[w], (j - 1) & 1);
@@ -287,9 +326,11 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             tmem_st32(tmem_p, reinterpret_cast<uint32_t(&)[32]>(pv[0]));
             tmem_st32(tmem_p + 32, reinterpret_cast<uint32_t(&)[32]>(pv[32]));
+            if (threadIdx.x == w * 128) KX_TRACE(w, j, 5);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_full[w]);
+            if (threadIdx.x == w * 128) KX_TRACE(w, j, 6);
         }
 
         // ---- epilogue: O / l -> bf16, head-merged token-major output
@@ -348,6 +389,7 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.scale_log2 = scale * 1.4426950408889634f;
     p.stats_out = reinterpret_cast<float2*>(stats_out);
     p.total_rows = static_cast<long long>(rows);
+    p.trace = g_attn_trace;
     static bool attr_set = false;
     static bool poly = true;            // KX_ATTN_POLY=0 keeps every exp2 on the MUFU (A/B measurements)
     if (!attr_set) {
@@ -365,6 +407,17 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     }
     if (p.num_pairs > 65535) { set_error("kx_attn_fwd: sequence too long"); return KX_ERR_ARG; }
     dim3 grid(heads * batch, p.num_pairs);
+    if (p.trace != nullptr && causal) {          // profiling aid (kx_attn_set_trace): same kernel with clock64 stamps
+        static bool tattr = false;
+        if (!tattr) {
+            cudaFuncSetAttribute(attn_pp_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+            cudaFuncSetAttribute(attn_pp_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+            tattr = true;
+        }
+        if (poly) attn_pp_kernel<true, true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        else attn_pp_kernel<true, false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        return check_launch("kx_attn_fwd");
+    }
     if (causal) {
         if (poly) attn_pp_kernel<true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
         else attn_pp_kernel<true, false><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
@@ -376,3 +429,11 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
 }
 
 }  // namespace kx
+
+// Profiling aid: when a device buffer of 3*64*8 int64 is installed, causal kx_attn_fwd launches run a
+// traced build and CTA (0,0) (the heaviest tile pair of batch 0, head 0) records clock64 stamps:
+// [role: 0 = softmax A, 1 = softmax B, 2 = MMA thread][KV block][point].  Pass NULL to switch it off.
+extern "C" int kx_attn_set_trace(long long* device_buffer) {
+    kx::g_attn_trace = device_buffer;
+    return KX_OK;
+}

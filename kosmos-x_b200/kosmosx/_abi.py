@@ -47,6 +47,7 @@ SIGNATURES = {
     "kx_launch_count": (C.c_ulonglong, []),
     "kx_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, C.POINTER(GemmArgs), _vp]),
     "kx_attn_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _vp]),
+    "kx_attn_set_trace": (_i, [_vp]),
     "kx_rowstats_cast": (_i, [_f32p, _ll, _vp, _ll, _f32p, _i, _i, _vp]),
     "kx_perceiver_xattn_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "kx_layernorm_fwd": (_i, [_vp, _i, _ll, _f32p, _i, _i, _f32p, _f32p, _f, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
