@@ -106,8 +106,8 @@ int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, con
 int kx_attn_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
                 int batch, int heads, int seq_len, int causal, float scale, float* stats_out, kx_stream_t stream);
 
-/* Profiling aid for kx_attn_fwd (causal): with a device buffer of 3*64*8 int64 installed, CTA (0,0) of every
- * launch records clock64 stamps [role: softmax A, softmax B, MMA thread][KV block][point]; NULL = off. */
+/* Profiling aid for kx_attn_fwd (causal): with a device buffer of 4*64*8 int64 installed, CTA (0,0) of every
+ * launch records clock64 stamps [role: softmax A, softmax B, MMA thread A, MMA thread B][KV block][point]; NULL = off. */
 int kx_attn_set_trace(long long* device_buffer);
 
 /* Perceiver cross-attention core (flamingo_pytorch PerceiverAttention; reached from

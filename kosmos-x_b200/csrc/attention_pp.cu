@@ -10,7 +10,7 @@
 //   warps 4-7  softmax of tile B   } (128 fp32), max with 3-input FMNMX, exp2 on packed FFMA2 operands,
 //                                    P (bf16 pairs) written back over S in TMEM with tcgen05.st
 //   warp 8     TMA producer: Q tiles once, K/V 128-row blocks through 3-slot rings
-//   warp 9     MMA issuer: S_w = Q_w.K^T (SS) and O_w += P_w.V (A operand = P in TMEM, TS form)
+//   warps 9,10 MMA issuers, one elected thread per tile: S_w = Q_w.K^T (SS) and O_w += P_w.V (A = P in TMEM, TS form)
 // TMEM holds, per tile, S (128 fp32 columns), P (64 columns of bf16 pairs) and O (64 columns): 2 x 256 = 512.
 // Because P does not alias S, S_w(j+1) is issued as soon as the softmax has pulled S_w(j) into registers
 // (s_free), i.e. the next score tile is computed while the current one is being exponentiated; the
@@ -44,7 +44,7 @@ struct AttnPPParams {
     float scale_log2;                                // scale * log2(e)
     float2* stats_out;                               // [heads][batch*seq_len] partial (sum, sumsq) of the stored row, or null
     long long total_rows;
-    long long* trace;                                // TRACE builds only: clock64 stamps of CTA (0,0), [3 roles][64 iters][8 points]
+    long long* trace;                                // TRACE builds only: clock64 stamps of CTA (0,0), [4 roles][64 iters][8 points]
 };
 
 static long long* g_attn_trace = nullptr;            // kx_attn_set_trace
@@ -92,8 +92,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (smem_u32(smem) & 1023) { printf("kx attn_pp: dynamic smem base not 1024-aligned\n"); __trap(); }
         mbar_init(q_full, 1);
         for (int i = 0; i < PP_KV_STAGES; ++i) {
-            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2);     // released by both tiles' MMA threads
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
         }
         for (int w = 0; w < 2; ++w) {
             mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 128); mbar_init(&o_full[w], 1); mbar_init(&s_free[w], 128);
@@ -112,94 +112,94 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");       // hand registers to the softmax warpgroups
-        if (warp == 8 && lane == 0) {
-            // ================= TMA producer =================
-            mbar_arrive_expect_tx(q_full, 2 * PP_TILE_BYTES);
-            tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q, head * 64, row_base + q0, kEvictFirst);
-            tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q + PP_TILE_BYTES, head * 64, row_base + q0 + 128, kEvictFirst);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int j = 0; j < nblk1; ++j) {
-                mbar_wait(&k_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&k_full[s], PP_TILE_BYTES);
-                tma_load_2d(&tmK, &k_full[s], smem + PP_SMEM_K + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
-                mbar_wait(&v_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&v_full[s], PP_TILE_BYTES);
-                tma_load_2d(&tmV, &v_full[s], smem + PP_SMEM_V + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
-                if (++s == PP_KV_STAGES) { s = 0; ph ^= 1; }
+        if (warp == 8) {
+            if (elect_one()) {
+                // ================= TMA producer =================
+                mbar_arrive_expect_tx(q_full, 2 * PP_TILE_BYTES);
+                tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q, head * 64, row_base + q0, kEvictFirst);
+                tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q + PP_TILE_BYTES, head * 64, row_base + q0 + 128, kEvictFirst);
+                int s = 0;
+                uint32_t ph = 0;
+                for (int j = 0; j < nblk1; ++j) {
+                    mbar_wait(&k_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&k_full[s], PP_TILE_BYTES);
+                    tma_load_2d(&tmK, &k_full[s], smem + PP_SMEM_K + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
+                    mbar_wait(&v_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&v_full[s], PP_TILE_BYTES);
+                    tma_load_2d(&tmV, &v_full[s], smem + PP_SMEM_V + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
+                    if (++s == PP_KV_STAGES) { s = 0; ph ^= 1; }
+                }
             }
-        } else if (warp == 9 && lane == 0) {
-            // ================= MMA issuer =================
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-            constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM)    x V (MN-major)
-            auto issue_s = [&](int w, int slot) {
+        } else if (warp <= 10) {
+            // ================= MMA issuers: warp 9 drives tile A, warp 10 tile B =================
+            // One elected thread per tile (elect.sync lets ptxas emit UTCHMMA without a divergence loop).  A
+            // single thread issuing all four MMA groups of an iteration was the measured bottleneck (~100
+            // cycles of issue overhead per tcgen05.mma against 32-64 cycles of execution at these tile sizes).
+            const int w = warp - 9;
+            const int nblk = w ? nblk1 : nblk0;
+            if (elect_one()) {
+                constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+                constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM)    x V (MN-major)
+                const uint32_t t_s = tmem_base + w * 128;
+                const uint32_t t_p = tmem_base + PP_TMEM_P + w * 64;
+                const uint32_t t_o = tmem_base + PP_TMEM_O + w * 64;
                 const uint64_t qdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_Q + w * PP_TILE_BYTES));
-                const uint64_t kdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_K + slot * PP_TILE_BYTES));
+                auto issue_s = [&](int slot) {
+                    const uint64_t kdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_K + slot * PP_TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16<1>(tmem_base + w * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-            };
-            auto issue_pv = [&](int w, int slot, bool first) {
-                const uint64_t vdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_V + slot * PP_TILE_BYTES), PP_TILE_BYTES);
+                    for (int k = 0; k < 4; ++k) umma_bf16<1>(t_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                };
+                auto issue_pv = [&](int slot, bool first) {
+                    const uint64_t vdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_V + slot * PP_TILE_BYTES), PP_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)      // 16 keys per step: 8 TMEM columns of P, 16 V rows = 2 KB
-                    umma_bf16_ts(tmem_base + PP_TMEM_O + w * 64, tmem_base + PP_TMEM_P + w * 64 + k * 8,
-                                 vdesc + k * (2048 >> 4), idesc_o, (!first || k != 0) ? 1u : 0u);
-            };
-            mbar_wait(q_full, 0);
-            mbar_wait(&k_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            umma_commit(&s_full[0]);
-            issue_s(1, 0);
-            umma_commit(&s_full[1]);
-            umma_commit(&k_empty[0]);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int j = 0; j < nblk1; ++j) {
-                int sn = s + 1;
-                uint32_t phn = ph;
-                if (sn == PP_KV_STAGES) { sn = 0; phn ^= 1; }
-                // ---- next score tiles first: each needs only its S_w(j) to have been pulled into registers,
-                //      so both are in flight long before either softmax finishes
-                KX_TRACE(2, j, 0);
-                if (j + 1 < nblk0) {
-                    mbar_wait(&s_free[0], j & 1);
-                    KX_TRACE(2, j, 1);
-                    mbar_wait(&k_full[sn], phn);
-                    tc_fence_after();
-                    issue_s(0, sn);
-                    umma_commit(&s_full[0]);
-                }
-                KX_TRACE(2, j, 2);
-                if (j + 1 < nblk1) {
-                    mbar_wait(&s_free[1], j & 1);
-                    KX_TRACE(2, j, 3);
-                    mbar_wait(&k_full[sn], phn);
-                    tc_fence_after();
-                    issue_s(1, sn);
-                    umma_commit(&s_full[1]);
-                    umma_commit(&k_empty[sn]);
-                }
-                // ---- then P.V of this block for both tiles
-                mbar_wait(&v_full[s], ph);
-                KX_TRACE(2, j, 4);
-                if (j < nblk0) {
-                    mbar_wait(&p_full[0], j & 1);
-                    KX_TRACE(2, j, 5);
-                    tc_fence_after();
-                    issue_pv(0, s, j == 0);
-                    umma_commit(&o_full[0]);
-                }
-                mbar_wait(&p_full[1], j & 1);
-                KX_TRACE(2, j, 6);
+                    for (int k = 0; k < 8; ++k)      // 16 keys per step: 8 TMEM columns of P, 16 V rows = 2 KB
+                        umma_bf16_ts(t_o, t_p + k * 8, vdesc + k * (2048 >> 4), idesc_o, (!first || k != 0) ? 1u : 0u);
+                };
+                mbar_wait(q_full, 0);
+                mbar_wait(&k_full[0], 0);
                 tc_fence_after();
-                issue_pv(1, s, j == 0);
-                umma_commit(&o_full[1]);
-                umma_commit(&v_empty[s]);
-                KX_TRACE(2, j, 7);
-                s = sn;
-                ph = phn;
+                issue_s(0);
+                umma_commit(&s_full[w]);
+                umma_commit(&k_empty[0]);                  // K/V slots are released by BOTH tiles' commits (count 2)
+                int s = 0;
+                uint32_t ph = 0;
+                for (int j = 0; j < nblk1; ++j) {
+                    int sn = s + 1;
+                    uint32_t phn = ph;
+                    if (sn == PP_KV_STAGES) { sn = 0; phn ^= 1; }
+                    if (j < nblk) {
+                        KX_TRACE(2 + w, j, 0);
+                        if (j + 1 < nblk) {                 // next scores: need only S_w(j) to have been read
+                            mbar_wait(&s_free[w], j & 1);
+                            KX_TRACE(2 + w, j, 1);
+                            mbar_wait(&k_full[sn], phn);
+                            tc_fence_after();
+                            issue_s(sn);
+                            umma_commit(&s_full[w]);
+                            umma_commit(&k_empty[sn]);
+                            KX_TRACE(2 + w, j, 2);
+                        }
+                        mbar_wait(&v_full[s], ph);
+                        mbar_wait(&p_full[w], j & 1);
+                        KX_TRACE(2 + w, j, 3);
+                        tc_fence_after();
+                        issue_pv(s, j == 0);
+                        umma_commit(&o_full[w]);
+                        umma_commit(&v_empty[s]);
+                        KX_TRACE(2 + w, j, 4);
+                    } else {
+                        // tile A has one block fewer than tile B (causal): release the slots it does not use,
+                        // once they have been filled (their previous phase is then complete)
+                        mbar_wait(&v_full[s], ph);
+                        mbar_arrive(&v_empty[s]);
+                    }
+                    if (j + 1 < nblk1 && j + 1 >= nblk) {
+                        mbar_wait(&k_full[sn], phn);
+                        mbar_arrive(&k_empty[sn]);
+                    }
+                    s = sn;
+                    ph = phn;
+                }
             }
         }
     } else {
@@ -430,9 +430,9 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
 
 }  // namespace kx
 
-// Profiling aid: when a device buffer of 3*64*8 int64 is installed, causal kx_attn_fwd launches run a
+// Profiling aid: when a device buffer of 4*64*8 int64 is installed, causal kx_attn_fwd launches run a
 // traced build and CTA (0,0) (the heaviest tile pair of batch 0, head 0) records clock64 stamps:
-// [role: 0 = softmax A, 1 = softmax B, 2 = MMA thread][KV block][point].  Pass NULL to switch it off.
+// [role: 0 = softmax A, 1 = softmax B, 2 = MMA thread A, 3 = MMA thread B][KV block][point].  Pass NULL to switch it off.
 extern "C" int kx_attn_set_trace(long long* device_buffer) {
     kx::g_attn_trace = device_buffer;
     return KX_OK;

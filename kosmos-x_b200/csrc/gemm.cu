@@ -347,7 +347,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int cluster_id = blockIdx.x / CG;
     const int num_clusters = gridDim.x / CG;
 
-    if (warp == 0 && lane == 0) {
+    // Single-thread roles are entered through elect.sync: ptxas then knows exactly one lane is active and emits
+    // the uniform-datapath instructions (UTMALDG / UTCHMMA) straight-line, without a per-instruction
+    // divergence loop (measurably cheaper issue than `lane == 0`).
+    if (warp == 0) {
+        if (elect_one()) {
         // ================= TMA producer =================
         int s = 0;
         uint32_t ph = 0;
@@ -371,7 +375,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0 && leader) {
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
         // ================= MMA issuer (leader CTA only) =================
         constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BN);
         int s = 0;
@@ -404,6 +410,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int last = it - 1;
                 mbar_wait(&tempty[last & 1], (last >> 1) & 1);
             }
+        }
         }
     } else if (warp >= EPI_WARP0) {
         // ================= epilogue =================

@@ -13,7 +13,7 @@ B, H = 8, 32
 qkv = torch.randn(B * T, 3 * H * 64, device="cuda").bfloat16()
 q, k, v = qkv[:, :H * 64], qkv[:, H * 64:2 * H * 64], qkv[:, 2 * H * 64:]
 out = torch.empty(B * T, H * 64, device="cuda", dtype=torch.bfloat16)
-buf = torch.zeros(3, 64, 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4, 64, 8, dtype=torch.int64, device="cuda")
 for _ in range(2):
     ops.attention(q, k, v, out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125)
 _abi.check(_abi.lib.kx_attn_set_trace(buf.data_ptr()), "kx_attn_set_trace")
@@ -24,8 +24,8 @@ t = buf.cpu()
 t0 = int(t[t > 0].min())
 n = T // 128
 print("softmax points: 0 iter start, 1 S ready, 2 S in regs (s_free), 3 max done, 4 exp done, 5 P stored, 6 p_full arrived")
-print("MMA points: 0 iter start, 1 s_free_A seen, 2 S_A issued, 3 s_free_B seen, 4 S_B issued + v_full, 5 p_full_A seen, 6 p_full_B seen, 7 PVs issued")
-for role, name in ((0, "softmax A"), (1, "softmax B"), (2, "MMA")):
+print("MMA points: 0 iter start, 1 s_free seen, 2 next S issued, 3 v_full + p_full seen, 4 PV issued")
+for role, name in ((0, "softmax A"), (1, "softmax B"), (2, "MMA A"), (3, "MMA B")):
     print(f"--- {name}")
     for j in range(n):
         row = t[role, j]
