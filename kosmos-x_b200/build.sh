@@ -19,5 +19,10 @@ for src in runtime gemm attention attention_pp elementwise perceiver_attn; do
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
 "$NVCC" -shared -o "$out/libkosmosx_sm100.so" "${objs[@]}" -cudart static
+if [[ "${KX_BUILD_TRACE:-0}" == "1" ]]; then      # profiling variant: GEMM epilogue clock64 stamps (tools/gemm_trace.py)
+  "$NVCC" "${FLAGS[@]}" -DKX_GEMM_TRACE -c "$here/csrc/gemm.cu" -o "$here/build/gemm_trace.o" > "$here/build/gemm_trace.log" 2>&1 || { cat "$here/build/gemm_trace.log"; exit 1; }
+  tobjs=("${objs[@]/$here\/build\/gemm.o/$here/build/gemm_trace.o}")
+  "$NVCC" -shared -o "$out/libkosmosx_sm100_trace.so" "${tobjs[@]}" -cudart static
+fi
 if [[ "${1:-}" == "-v" ]]; then grep -h -E "registers|spill|error|warning" "$here"/build/*.log || true; fi
 echo "built $out/libkosmosx_sm100.so"

@@ -17,17 +17,31 @@
 
 namespace kx {
 
+// Build with -DKX_GEMM_TRACE to record clock64 stamps of epilogue warp 4 of CTA 0 (staged epilogue):
+// trace[(tile*8 + chunk)*8 + point]; kx_gemm_set_trace installs the device buffer.  Off in the shipped library.
+#ifdef KX_GEMM_TRACE
+__device__ long long* g_gemm_trace = nullptr;
+#define KX_GT(tile, chunk, point)                                                                       \
+    do {                                                                                                \
+        if (g_gemm_trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && (tile) < 16)        \
+            g_gemm_trace[(((tile)*8 + (chunk)) * 8) + (point)] = clock64();                             \
+    } while (0)
+#else
+#define KX_GT(tile, chunk, point) do {} while (0)
+#endif
+
 constexpr int BLOCK_M = 128;   // rows per CTA (UMMA M = 128 * CG)
 constexpr int BLOCK_K = 64;    // 64 bf16 = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: epilogue
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;       // two per SM sub-partition: warp e handles TMEM lanes 32*(e&3).. and column half e>>2
 
 // TMA_EPI: the epilogue stages each warp's 32-row x 128-byte sub-tile in swizzled shared memory and
 // writes it with cp.async.bulk.tensor (coalesced, asynchronous); the fp32 residual sub-tile is
 // prefetched the same way.  Costs 16 KB of staging per epilogue warp, taken from the operand ring.
 constexpr int EPI_STAGE_BYTES = 32 * 128;                    // 32 rows x 128 B
-constexpr int EPI_WARP_BYTES = 4 * EPI_STAGE_BYTES;          // main[3] x 4 KB + copy[2] x 2 KB
+constexpr int EPI_WARP_BYTES = 3 * EPI_STAGE_BYTES;          // main[2] x 4 KB + copy[2] x 2 KB
 
 template <int CG, int BN, bool TMA_EPI>
 struct GemmCfg {
@@ -35,12 +49,13 @@ struct GemmCfg {
     static constexpr int B_ROWS = BN / CG;
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = TMA_EPI ? 4 * EPI_WARP_BYTES : 0;
-    static constexpr int RING_BUDGET = TMA_EPI ? (160 * 1024) : (192 * 1024);
+    static constexpr int EPI_BYTES = TMA_EPI ? EPI_WARPS * EPI_WARP_BYTES : 0;
+    static constexpr int RING_BUDGET = TMA_EPI ? (128 * 1024) : (192 * 1024);
     static constexpr int STAGES = RING_BUDGET / STAGE_BYTES;
     static constexpr int VEC_BYTES = TMA_EPI ? 2 * BN * 4 : 0;   // this tile's bias[] and ln_c[] columns, staged once per tile
-    static constexpr int BAR_BYTES = 512;                       // (2*STAGES + 16) mbarriers + the TMEM slot; STAGES <= 8
-    static_assert((2 * STAGES + 16) * 8 + 8 <= BAR_BYTES, "barrier block");
+    static constexpr int BAR_BYTES = 512;                       // (2*STAGES + 4 + 16) mbarriers + the TMEM slot; STAGES <= 8
+    static_assert((2 * STAGES + 20) * 8 + 8 <= BAR_BYTES, "barrier block");
+    static_assert(STAGES >= 2, "ring too shallow");
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + VEC_BYTES + BAR_BYTES;   // base must be 1 KB aligned
     static constexpr int TMEM_COLS = 2 * BN;                                    // power of two for BN in {64,128,256}
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -69,8 +84,8 @@ struct GemmEpi {
     int ln_tiles;
     float ln_inv_n, ln_eps;
     // producer side: per-row partial (sum, sumsq) of the values this GEMM stores (after bf16 rounding),
-    // one pair per (n-tile, row); and an optional bf16 copy of an fp32 output (staged epilogue only)
-    float2* stats_out;         // [ceil(N/BN)][M] or null
+    // one pair per (128-column block, row); and an optional bf16 copy of an fp32 output (staged epilogue only)
+    float2* stats_out;         // [ceil(N/128)][M] or null
     void* out2;                // bf16 [M, ld_out2] or null
     long long ld_out2;
 };
@@ -87,20 +102,28 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_
 }
 
 // bias -> [xPos rotation] -> activation on one 32-column chunk of row m (shared by both store paths)
-// (sum, sumsq) of eight stored bf16 values; `full` skips the column-bound checks of the N tail.
-__device__ __forceinline__ void stats_add8(const uint4& pk, bool full, int n, int N, float& s1, float& s2) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+// (sum, sumsq) of eight stored bf16 values, accumulated as packed f32x2 pairs on two independent chains
+// (acc[0..1] sums, acc[2..3] sums of squares; folded by stats_fold).  `full` = no N tail in this chunk.
+__device__ __forceinline__ void stats_add8(const uint4& pk, bool full, int n, int N, uint64_t (&acc)[4]) {
+    const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const float2 r = __bfloat1622float2(h[u]);
-        if (full) {
-            s1 += r.x + r.y;
-            s2 = fmaf(r.x, r.x, fmaf(r.y, r.y, s2));
-        } else {
-            if (n + 2 * u < N) { s1 += r.x; s2 = fmaf(r.x, r.x, s2); }
-            if (n + 2 * u + 1 < N) { s1 += r.y; s2 = fmaf(r.y, r.y, s2); }
+        float lo = __uint_as_float(w[u] << 16), hi = __uint_as_float(w[u] & 0xffff0000u);
+        if (!full) {
+            if (n + 2 * u >= N) lo = 0.f;
+            if (n + 2 * u + 1 >= N) hi = 0.f;
         }
+        const uint64_t v = pack_f32x2(lo, hi);
+        acc[u & 1] = fadd2(acc[u & 1], v);
+        acc[2 + (u & 1)] = ffma2(v, v, acc[2 + (u & 1)]);
     }
+}
+__device__ __forceinline__ void stats_fold(const uint64_t (&acc)[4], float& s1, float& s2) {
+    float a0, a1, b0, b1;
+    unpack_f32x2(fadd2(acc[0], acc[1]), a0, a1);
+    unpack_f32x2(fadd2(acc[2], acc[3]), b0, b1);
+    s1 = a0 + a1;
+    s2 = b0 + b1;
 }
 
 // Row statistics of the A operand for a folded LayerNorm: fixed-order sum of the producer's partials.
@@ -301,8 +324,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
-    uint64_t* resbar = bars + 2 * STAGES + 4;                      // [4 warps][3 buffers]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 16);
+    uint64_t* resbar = bars + 2 * STAGES + 4;                      // [8 warps][2 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -325,9 +348,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], CG * 128);   // every epilogue thread of every CTA, on the leader's barrier
+            mbar_init(&tempty[a], CG * EPI_WARPS * 32);   // every epilogue thread of every CTA, on the leader's barrier
         }
-        for (int i = 0; i < 12; ++i) mbar_init(&resbar[i], 1);
+        for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&resbar[i], 1);
         fence_mbar_init();
     }
     if constexpr (CG == 2) cluster_sync_all();
@@ -350,6 +373,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Single-thread roles are entered through elect.sync: ptxas then knows exactly one lane is active and emits
     // the uniform-datapath instructions (UTMALDG / UTCHMMA) straight-line, without a per-instruction
     // divergence loop (measurably cheaper issue than `lane == 0`).
+    if (warp < EPI_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // registers go to the epilogue warpgroups
     if (warp == 0) {
         if (elect_one()) {
         // ================= TMA producer =================
@@ -414,7 +438,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp >= EPI_WARP0) {
         // ================= epilogue =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        const int ew = warp - EPI_WARP0;              // 0..7
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int chalf = ew >> 2;                    // which half of the tile's columns
+        constexpr int CPW = BN / 64;                  // 32-column chunks per warp
+        const int c_begin = chalf * CPW;
         int it = 0;
         if constexpr (!TMA_EPI) {
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
@@ -429,7 +458,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
                 const float2 ln = (ep.ln_part != nullptr && m < ep.M) ? ln_row_stats(ep, m) : make_float2(0.f, 1.f);
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = c_begin; c < c_begin + CPW; ++c) {
                     if (nb + c * 32 >= ep.N) break;       // warp-uniform
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
@@ -440,16 +469,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
             }
         } else {
-            // Staged epilogue.  Per warp, private smem: main[3] x 4 KB (32 rows x 128 B, SWIZZLE_128B), rotating
-            // per store unit, and copy[2] x 2 KB (32 rows x 64 B, SWIZZLE_64B) for the bf16 copy of an fp32 output.
+            // Staged epilogue.  Eight warps; warp (q, half) owns rows 32q..32q+31 and the column half of every tile.
+            // Per warp, private smem: main[2] x 4 KB (32 rows x 128 B, SWIZZLE_128B) alternating per store unit,
+            // and copy[2] x 2 KB (32 rows x 64 B, SWIZZLE_64B) for the bf16 copy of an fp32 output.
             //   fp32 out: unit = one 32-column chunk.  With a residual, the unit's buffer first receives the
             //             residual sub-tile by TMA (prefetched one unit ahead) and is updated IN PLACE.
             //   bf16 out: unit = two chunks (64 columns = 128-byte rows).
-            // One cp.async.bulk group per store; at every unit start lane 0 waits until only the previous
-            // unit's groups may still be reading smem, which frees every buffer touched in this unit.
-            uint8_t* st_main = smem_epi + q * EPI_WARP_BYTES;
-            uint8_t* st_copy = st_main + 3 * EPI_STAGE_BYTES;
-            uint64_t* rbar = resbar + q * 3;
+            // One cp.async.bulk group per store; at every unit start lane 0 waits for the stores that last read
+            // the buffers this unit (and, with a residual, the prefetch for the next unit) is about to overwrite.
+            uint8_t* st_main = smem_epi + ew * EPI_WARP_BYTES;
+            uint8_t* st_copy = st_main + 2 * EPI_STAGE_BYTES;
+            uint64_t* rbar = resbar + ew * 2;
             const bool has_res = (ep.res != nullptr);
             const bool has_copy = OUT_F32 && (ep.out2 != nullptr);
             const bool has_stats = (ep.stats_out != nullptr);
@@ -458,7 +488,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t unit = 0;              // store units issued by this warp
             uint32_t nres = 0;              // residual loads issued by this warp (== unit + prefetch depth)
             auto wait_units = [&]() {
-                if (lane == 0) { if (has_copy) tma_store_wait_read<2>(); else tma_store_wait_read<1>(); }
+                if (lane == 0) {
+                    if (has_res) tma_store_wait_read<0>();           // the next unit's residual lands in the buffer of unit-1
+                    else if (has_copy) tma_store_wait_read<2>();     // only unit-1's two stores may be pending
+                    else tma_store_wait_read<1>();
+                }
             };
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 int m_blk, n_blk;
@@ -468,63 +502,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int m_row0 = m_blk * (BLOCK_M * CG) + rank * BLOCK_M + q * 32;
                 const int m = m_row0 + lane;
                 const int nb = n_blk * BN;
-                const int nchunks = min(BN / 32, (ep.N - nb + 31) >> 5);
+                const int nchunks = min(c_begin + CPW, (ep.N - nb + 31) >> 5);   // this warp walks chunks [c_begin, nchunks)
                 const bool rows_ok = m_row0 < ep.M;          // warp-uniform; rows >= M inside a box are clipped by TMA
                 const float2 ln = (ep.ln_part != nullptr && m < ep.M) ? ln_row_stats(ep, m) : make_float2(0.f, 1.f);
                 float s1 = 0.f, s2 = 0.f;
-                {   // stage this tile's bias / ln_c columns once (the 4 epilogue warps walk the same tile sequence)
-                    constexpr int CPL = BN / 128;                       // columns per lane
-                    const int col = (q * 32 + lane) * CPL;
-                    float bv[CPL], cv[CPL];
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) {
-                        const bool in = nb + col + u < ep.N;
-                        bv[u] = (in && ep.bias != nullptr) ? __ldg(ep.bias + nb + col + u) : 0.f;
-                        cv[u] = (in && ep.ln_part != nullptr) ? __ldg(ep.ln_c + nb + col + u) : 0.f;
-                    }
-                    named_bar_sync(1, 128);                             // previous tile's readers are done
-#pragma unroll
-                    for (int u = 0; u < CPL; ++u) { s_vec[col + u] = bv[u]; s_vec[BN + col + u] = cv[u]; }
-                    named_bar_sync(1, 128);
+                uint64_t sacc[4] = {0ull, 0ull, 0ull, 0ull};
+                KX_GT(it, 0, 0);
+                {   // stage this tile's bias / ln_c columns once (the 8 epilogue warps walk the same tile sequence)
+                    const int col = ew * 32 + lane;                     // 256 threads, BN <= 256 columns
+                    const bool in = col < BN && nb + col < ep.N;
+                    const float bv = (in && ep.bias != nullptr) ? __ldg(ep.bias + nb + col) : 0.f;
+                    const float cv = (in && ep.ln_part != nullptr) ? __ldg(ep.ln_c + nb + col) : 0.f;
+                    named_bar_sync(1, EPI_WARPS * 32);                  // previous tile's readers are done
+                    if (col < BN) { s_vec[col] = bv; s_vec[BN + col] = cv; }
+                    named_bar_sync(1, EPI_WARPS * 32);
                 }
                 auto issue_res = [&](int c) {
                     if (lane == 0) {
-                        const uint32_t rb = nres % 3;
+                        const uint32_t rb = nres & 1;
                         mbar_arrive_expect_tx(&rbar[rb], EPI_STAGE_BYTES);
                         tma_load_2d(&tmRes, &rbar[rb], st_main + rb * EPI_STAGE_BYTES, nb + c * 32, m_row0);
                     }
                     ++nres;
                 };
-                if (has_res && rows_ok) {                    // in flight while the MMAs of this tile finish
+                if (has_res && rows_ok && c_begin < nchunks) {   // in flight while the MMAs of this tile finish
                     wait_units();
-                    issue_res(0);
+                    issue_res(c_begin);
                 }
+                KX_GT(it, 0, 1);
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
+                KX_GT(it, 0, 2);
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
                 uint32_t v[32];
-                tmem_ld32(taddr, v);
+                if (c_begin < nchunks) tmem_ld32(taddr + c_begin * 32, v);
 #pragma unroll 1
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = c_begin; c < nchunks; ++c) {
                     const int n0 = nb + c * 32;
+                    KX_GT(it, c, 3);
                     if (rows_ok && (OUT_F32 || !(c & 1))) {
                         wait_units();
                         __syncwarp();
                         if (has_res && c + 1 < nchunks) issue_res(c + 1);
                     }
+                    KX_GT(it, c, 4);
                     float f[32];
                     tmem_ld_wait();
+                    KX_GT(it, c, 5);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                     if (c + 1 < nchunks) tmem_ld32(taddr + (c + 1) * 32, v);      // in flight during this chunk's math
                     if (!rows_ok) continue;
                     const bool full = n0 + 32 <= ep.N;
                     epilogue_math<EPI>(ep, f, m, n0, full, ln, s_vec + c * 32, s_vec + BN + c * 32);
-                    const uint32_t ub = unit % 3;
+                    KX_GT(it, c, 6);
+                    const uint32_t ub = unit & 1;
                     uint8_t* mb = st_main + ub * EPI_STAGE_BYTES + lane * 128;
                     if constexpr (OUT_F32) {
                         if (has_res) {
-                            mbar_wait(&rbar[ub], (unit / 3) & 1);
+                            mbar_wait(&rbar[ub], (unit >> 1) & 1);
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
                                 const float4 x = *reinterpret_cast<const float4*>(mb + ((g ^ sw) << 4));
@@ -545,7 +581,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 pk.w = pack_bf16(f[8 * g + 6], f[8 * g + 7]);
                                 *reinterpret_cast<uint4*>(cb + ((g ^ sw64) << 4)) = pk;
                                 if (has_stats)            // statistics of what the consumer GEMM will read: the bf16 copy
-                                    stats_add8(pk, full, n0 + 8 * g, ep.N, s1, s2);
+                                    stats_add8(pk, full, n0 + 8 * g, ep.N, sacc);
                             }
                         } else if (has_stats) {
 #pragma unroll
@@ -573,7 +609,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             pk.z = pack_bf16(f[8 * g + 4], f[8 * g + 5]);
                             pk.w = pack_bf16(f[8 * g + 6], f[8 * g + 7]);
                             *reinterpret_cast<uint4*>(mb + (((half * 4 + g) ^ sw) << 4)) = pk;
-                            if (has_stats) stats_add8(pk, full, n0 + 8 * g, ep.N, s1, s2);
+                            if (has_stats) stats_add8(pk, full, n0 + 8 * g, ep.N, sacc);
                         }
                         if (half == 1 || c == nchunks - 1) {
                             fence_proxy_async_smem();
@@ -586,7 +622,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
-                if (has_stats && m < ep.M) ep.stats_out[static_cast<long long>(n_blk) * ep.M + m] = make_float2(s1, s2);
+                KX_GT(it, 7, 7);
+                if (has_stats && m < ep.M && nb + c_begin * 32 < ep.N) {      // one partial per 128 columns
+                    float t1, t2;
+                    stats_fold(sacc, t1, t2);
+                    ep.stats_out[static_cast<long long>(n_blk * 2 + chalf) * ep.M + m] = make_float2(s1 + t1, s2 + t2);
+                }
                 tc_fence_before();
                 if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
             }
@@ -687,6 +728,13 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
 }  // namespace kx
 
 using namespace kx;
+
+#ifdef KX_GEMM_TRACE
+extern "C" int kx_gemm_set_trace(long long* device_buffer) {
+    cudaError_t e = cudaMemcpyToSymbol(g_gemm_trace, &device_buffer, sizeof(device_buffer));
+    return e == cudaSuccess ? KX_OK : KX_ERR_LAUNCH;
+}
+#endif
 
 extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const kx_gemm_args* g,
                             cudaStream_t stream) {

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libkosmosx_sm100.so")
+# KX_LIB selects another build of the same library (the -DKX_GEMM_TRACE profiling variant); default = the shipped one
+LIB_PATH = os.environ.get("KX_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libkosmosx_sm100.so")
 
 KX_OK = 0
 KX_ACT_NONE, KX_ACT_GELU, KX_ACT_QUICK_GELU = 0, 1, 2

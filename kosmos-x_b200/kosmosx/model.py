@@ -361,10 +361,10 @@ class Decoder(nn.Module):
         mid = ws.get("mid", (M, F), bf, dev)
         # per-row partial (sum, sumsq) emitted by each producer, summed by the consumer's folded LayerNorm
         st_in = ws.get("st_in", (1, M, 2), f32, dev)
-        st_a = ws.get("st_a", ((D + 255) // 256, M, 2), f32, dev)
-        st_b = ws.get("st_b", ((D + 255) // 256, M, 2), f32, dev)
+        st_a = ws.get("st_a", ((D + 127) // 128, M, 2), f32, dev)
+        st_b = ws.get("st_b", ((D + 127) // 128, M, 2), f32, dev)
         st_att = ws.get("st_att", (H, M, 2), f32, dev)
-        st_mid = ws.get("st_mid", ((F + 255) // 256, M, 2), f32, dev)
+        st_mid = ws.get("st_mid", ((F + 127) // 128, M, 2), f32, dev)
         tabs = self._xpos(T, dev)
         scale = (D // H) ** -0.5
         eps = cfg.eps

@@ -69,7 +69,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; out bf16 or fp32 (2-D views, row pitch = stride(0)).
 
     ln = (partials fp32 [tiles, M, 2], c fp32 [N], cols, eps): LayerNorm of the rows of `a` folded into the
-    epilogue (w must carry gamma, bias must be W.beta + b).  stats_out fp32 [ceil(N/256), M, 2] and out2
+    epilogue (w must carry gamma, bias must be W.beta + b).  stats_out fp32 [ceil(N/128), M, 2] and out2
     (bf16 copy of an fp32 out) make this GEMM the producer of the next fold."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
@@ -109,8 +109,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
         g.ln_part, g.ln_c, g.ln_tiles, g.ln_cols, g.ln_eps = part.data_ptr(), c.data_ptr(), part.shape[0], cols, eps
     if stats_out is not None:
         _req(stats_out, torch.float32, "stats_out")
-        if tuple(stats_out.shape) != ((g.N + 255) // 256, g.M, 2) or not stats_out.is_contiguous():
-            raise ValueError(f"gemm: stats_out must be contiguous [{(g.N + 255) // 256}, {g.M}, 2]")
+        if tuple(stats_out.shape) != ((g.N + 127) // 128, g.M, 2) or not stats_out.is_contiguous():
+            raise ValueError(f"gemm: stats_out must be contiguous [{(g.N + 127) // 128}, {g.M}, 2]")
         g.stats_out = stats_out.data_ptr()
     if out2 is not None:
         _req(out2, torch.bfloat16, "out2")

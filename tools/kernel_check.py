@@ -125,7 +125,7 @@ def case_gemm_epilogue():
     xs = torch.linspace(-9, 9, 4096 * K3, device=dev).view(4096, K3).bfloat16()
     og = torch.empty(4096, K3, device=dev)
     ops.gemm(xs, eye, og, act=_abi.KX_ACT_GELU)
-    ok &= report("erf-GELU approximation (fp32 out)", og, torch.nn.functional.gelu(xs.float()), 4e-6)
+    ok &= report("erf-GELU approximation (fp32 out)", og, torch.nn.functional.gelu(xs.float()), 6e-6)
     return ok
 
 
@@ -268,7 +268,7 @@ def case_ln_fold():
         res0 = torch.randn(M, N, device=dev)
         y = res0.clone()
         yb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-        st2 = torch.zeros((N + 255) // 256, M, 2, device=dev)
+        st2 = torch.zeros((N + 127) // 128, M, 2, device=dev)
         ops.gemm(xb, wf, y, bias=d, res=y, ln=(st, c, K, 1e-5), stats_out=st2, out2=yb)
         mu, var = xf.mean(1, keepdim=True), xf.var(1, unbiased=False, keepdim=True)
         ref = ((xf - mu) * torch.rsqrt(var + 1e-5)) @ wf.float().T + d + res0
@@ -288,7 +288,7 @@ def case_ln_fold():
         c2 = wf2.double().sum(1).float()
         d2 = (W2.double() @ b2.double()).float()
         z = torch.zeros(M, N2, device=dev, dtype=torch.bfloat16) if (N2 * 2) % 16 == 0 else torch.zeros(M, N2, device=dev)
-        st3 = torch.zeros((N2 + 255) // 256, M, 2, device=dev) if z.dtype == torch.bfloat16 else None
+        st3 = torch.zeros((N2 + 127) // 128, M, 2, device=dev) if z.dtype == torch.bfloat16 else None
         ops.gemm(yb, wf2, z, bias=d2, act=_abi.KX_ACT_GELU, ln=(st2, c2, N, 1e-5), stats_out=st3)
         mu2, var2 = ybf.mean(1, keepdim=True), ybf.var(1, unbiased=False, keepdim=True)
         ref2 = F.gelu(((ybf - mu2) * torch.rsqrt(var2 + 1e-5)) @ wf2.float().T + d2)
