@@ -41,7 +41,7 @@ constexpr int EPI_WARPS = 8;       // two per SM sub-partition: warp e handles T
 // writes it with cp.async.bulk.tensor (coalesced, asynchronous); the fp32 residual sub-tile is
 // prefetched the same way.  Costs 16 KB of staging per epilogue warp, taken from the operand ring.
 constexpr int EPI_STAGE_BYTES = 32 * 128;                    // 32 rows x 128 B
-constexpr int EPI_WARP_BYTES = 3 * EPI_STAGE_BYTES;          // main[2] x 4 KB + copy[2] x 2 KB
+constexpr int EPI_WARP_BYTES = 2 * EPI_STAGE_BYTES;          // main 4 KB + copy[2] x 2 KB
 
 template <int CG, int BN, bool TMA_EPI>
 struct GemmCfg {
@@ -50,7 +50,7 @@ struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_BYTES = TMA_EPI ? EPI_WARPS * EPI_WARP_BYTES : 0;
-    static constexpr int RING_BUDGET = TMA_EPI ? (128 * 1024) : (192 * 1024);
+    static constexpr int RING_BUDGET = TMA_EPI ? (160 * 1024) : (192 * 1024);
     static constexpr int STAGES = RING_BUDGET / STAGE_BYTES;
     static constexpr int VEC_BYTES = TMA_EPI ? 2 * BN * 4 : 0;   // this tile's bias[] and ln_c[] columns, staged once per tile
     static constexpr int BAR_BYTES = 512;                       // (2*STAGES + 4 + 16) mbarriers + the TMEM slot; STAGES <= 8
@@ -76,6 +76,7 @@ struct GemmEpi {
     const float *xq_cos, *xq_sin, *xk_cos, *xk_sin;   // xPos tables [seq_len, 32] fp32
     int seq_len, d_model;
     int vec_ok;                // 16-byte vector access to out/res/add_tab rows is legal
+    int tma_store;             // staged epilogue: 1 = TMA store, 0 = coalesced float2 stores from the staging buffer
     // LayerNorm folded into this GEMM: A holds the RAW rows, W already carries gamma,
     //   y = rstd[m] * (acc - mean[m] * ln_c[n]) + bias[n],   bias = W.beta + b
     // mean/rstd come from ln_tiles partial (sum, sumsq) pairs per row written by the producer's epilogue.
@@ -324,7 +325,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
-    uint64_t* resbar = bars + 2 * STAGES + 4;                      // [8 warps][2 buffers]
+    uint64_t* resbar = bars + 2 * STAGES + 4;                      // [8 warps]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 20);
 
     const int warp = threadIdx.x >> 5;
@@ -469,30 +470,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if constexpr (CG == 1) mbar_arrive(&tempty[a]); else mbar_arrive_cluster(&tempty[a], 0);
             }
         } else {
-            // Staged epilogue.  Eight warps; warp (q, half) owns rows 32q..32q+31 and the column half of every tile.
-            // Per warp, private smem: main[2] x 4 KB (32 rows x 128 B, SWIZZLE_128B) alternating per store unit,
-            // and copy[2] x 2 KB (32 rows x 64 B, SWIZZLE_64B) for the bf16 copy of an fp32 output.
-            //   fp32 out: unit = one 32-column chunk.  With a residual, the unit's buffer first receives the
-            //             residual sub-tile by TMA (prefetched one unit ahead) and is updated IN PLACE.
+            // Staged epilogue.  Eight warps; warp (q, chalf) owns rows 32q..32q+31 and one column half of every tile.
+            // Per warp, private smem: main 4 KB (32 rows x 128 B, SWIZZLE_128B) and copy[2] x 2 KB (32 rows x 64 B,
+            // SWIZZLE_64B) for the bf16 copy of an fp32 output.
+            //   fp32 out: unit = one 32-column chunk.  With a residual, `main` first receives the residual sub-tile
+            //             by TMA (issued at unit start, landing during the TMEM load and the math) and is updated IN PLACE.
             //   bf16 out: unit = two chunks (64 columns = 128-byte rows).
-            // One cp.async.bulk group per store; at every unit start lane 0 waits for the stores that last read
-            // the buffers this unit (and, with a residual, the prefetch for the next unit) is about to overwrite.
+            // One cp.async.bulk group per store.  `main` is single-buffered: before it is overwritten (by the residual
+            // load at unit start, or by the first write of the unit, which comes after the math) lane 0 waits until the
+            // previous unit's store has finished reading it; the second warp on the SM sub-partition covers that latency.
             uint8_t* st_main = smem_epi + ew * EPI_WARP_BYTES;
-            uint8_t* st_copy = st_main + 2 * EPI_STAGE_BYTES;
-            uint64_t* rbar = resbar + ew * 2;
+            uint8_t* st_copy = st_main + EPI_STAGE_BYTES;
+            uint64_t* rbar = resbar + ew;
             const bool has_res = (ep.res != nullptr);
             const bool has_copy = OUT_F32 && (ep.out2 != nullptr);
             const bool has_stats = (ep.stats_out != nullptr);
+            const bool tma_out = ep.tma_store != 0;
             const int sw = lane & 7;
             const int sw64 = (lane >> 1) & 3;
             uint32_t unit = 0;              // store units issued by this warp
-            uint32_t nres = 0;              // residual loads issued by this warp (== unit + prefetch depth)
-            auto wait_units = [&]() {
-                if (lane == 0) {
-                    if (has_res) tma_store_wait_read<0>();           // the next unit's residual lands in the buffer of unit-1
-                    else if (has_copy) tma_store_wait_read<2>();     // only unit-1's two stores may be pending
-                    else tma_store_wait_read<1>();
-                }
+            auto wait_main_free = [&]() {   // group order per unit: main store, then copy store
+                if (lane == 0) { if (has_copy) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+                __syncwarp();
             };
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 int m_blk, n_blk;
@@ -517,18 +516,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (col < BN) { s_vec[col] = bv; s_vec[BN + col] = cv; }
                     named_bar_sync(1, EPI_WARPS * 32);
                 }
-                auto issue_res = [&](int c) {
+                auto issue_res = [&](int c) {               // residual sub-tile of chunk c -> main (freed by wait_main_free)
                     if (lane == 0) {
-                        const uint32_t rb = nres & 1;
-                        mbar_arrive_expect_tx(&rbar[rb], EPI_STAGE_BYTES);
-                        tma_load_2d(&tmRes, &rbar[rb], st_main + rb * EPI_STAGE_BYTES, nb + c * 32, m_row0);
+                        mbar_arrive_expect_tx(rbar, EPI_STAGE_BYTES);
+                        tma_load_2d(&tmRes, rbar, st_main, nb + c * 32, m_row0);
                     }
-                    ++nres;
                 };
-                if (has_res && rows_ok && c_begin < nchunks) {   // in flight while the MMAs of this tile finish
-                    wait_units();
-                    issue_res(c_begin);
-                }
                 KX_GT(it, 0, 1);
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
@@ -540,10 +533,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int c = c_begin; c < nchunks; ++c) {
                     const int n0 = nb + c * 32;
                     KX_GT(it, c, 3);
-                    if (rows_ok && (OUT_F32 || !(c & 1))) {
-                        wait_units();
-                        __syncwarp();
-                        if (has_res && c + 1 < nchunks) issue_res(c + 1);
+                    const bool unit_start = OUT_F32 || !(c & 1);
+                    if (rows_ok && has_res) {                // residual: the buffer must be free before the load is issued
+                        wait_main_free();
+                        issue_res(c);
                     }
                     KX_GT(it, c, 4);
                     float f[32];
@@ -556,11 +549,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const bool full = n0 + 32 <= ep.N;
                     epilogue_math<EPI>(ep, f, m, n0, full, ln, s_vec + c * 32, s_vec + BN + c * 32);
                     KX_GT(it, c, 6);
-                    const uint32_t ub = unit & 1;
-                    uint8_t* mb = st_main + ub * EPI_STAGE_BYTES + lane * 128;
+                    uint8_t* mb = st_main + lane * 128;
+                    if (unit_start && !has_res) wait_main_free();      // after the math: the previous store has had time to drain
                     if constexpr (OUT_F32) {
                         if (has_res) {
-                            mbar_wait(&rbar[ub], (unit >> 1) & 1);
+                            mbar_wait(rbar, unit & 1);
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
                                 const float4 x = *reinterpret_cast<const float4*>(mb + ((g ^ sw) << 4));
@@ -588,15 +581,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = 0; i < 32; ++i)
                                 if (n0 + i < ep.N) { s1 += f[i]; s2 = fmaf(f[i], f[i], s2); }
                         }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tmOut, st_main + ub * EPI_STAGE_BYTES, n0, m_row0);
-                            tma_store_commit();
-                            if (has_copy) {
-                                tma_store_2d(&tmOut2, st_copy + (unit & 1) * (EPI_STAGE_BYTES / 2), n0, m_row0);
+                        if (tma_out) {
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmOut, st_main, n0, m_row0);
                                 tma_store_commit();
+                                if (has_copy) {
+                                    tma_store_2d(&tmOut2, st_copy + (unit & 1) * (EPI_STAGE_BYTES / 2), n0, m_row0);
+                                    tma_store_commit();
+                                }
                             }
+                        } else {
+                            // rows only 8-byte aligned (LM head, ld = 32002): two rows x 128 B per warp instruction
+                            __syncwarp();
+                            const int rsub = lane >> 4, cp = (lane & 15) * 2;
+                            float* og = reinterpret_cast<float*>(ep.out);
+#pragma unroll 4
+                            for (int rr = 0; rr < 32; rr += 2) {
+                                const int r = rr + rsub;
+                                const float2 val = *reinterpret_cast<const float2*>(st_main + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + (cp & 3) * 4);
+                                const long long row = m_row0 + r;
+                                if (row < ep.M) {
+                                    float* dst = og + row * ep.ld_out + n0 + cp;
+                                    if (n0 + cp + 1 < ep.N) *reinterpret_cast<float2*>(dst) = val;
+                                    else if (n0 + cp < ep.N) *dst = val.x;
+                                }
+                            }
+                            __syncwarp();
                         }
                         ++unit;
                     } else {
@@ -615,7 +627,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_2d(&tmOut, st_main + ub * EPI_STAGE_BYTES, nb + (c & ~1) * 32, m_row0);
+                                tma_store_2d(&tmOut, st_main, nb + (c & ~1) * 32, m_row0);
                                 tma_store_commit();
                             }
                             ++unit;
@@ -676,8 +688,10 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
     if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP;
     if (!make_tmap_2d(&tmB, W, ep.K, ep.N, ldw * 2, BLOCK_K, Cfg::B_ROWS)) return KX_ERR_TMAP;
     if constexpr (TMA_EPI) {
-        if (!make_tmap_2d(&tmOut, ep.out, ep.N, ep.M, ep.ld_out * (OUT_F32 ? 4 : 2), OUT_F32 ? 32 : 64, 32,
-                          OUT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16))
+        if (!ep.tma_store) {
+            tmOut = tmA;                       // unused: the staged epilogue writes with coalesced float2 stores
+        } else if (!make_tmap_2d(&tmOut, ep.out, ep.N, ep.M, ep.ld_out * (OUT_F32 ? 4 : 2), OUT_F32 ? 32 : 64, 32,
+                                 OUT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16))
             return KX_ERR_TMAP;
         if (ep.res != nullptr) {
             if (!make_tmap_2d(&tmRes, ep.res, ep.N, ep.M, ep.ld_res * 4, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
@@ -799,7 +813,13 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
                    ((reinterpret_cast<uintptr_t>(g->out) & 15) == 0);
     if (g->res) tma_epi = tma_epi && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
     if (g->epi_mode == 1) tma_epi = false;
-    if ((g->stats_out || g->out2) && !tma_epi) {
+    ep.tma_store = tma_epi ? 1 : 0;
+    // fp32 rows that are only 8-byte aligned (LM head: ld = 32002) still take the staged kernel, which then writes
+    // two 128-byte row segments per warp instruction instead of 32 scattered 8-byte pieces
+    if (!tma_epi && g->epi_mode != 1 && g->out_f32 && !g->res && !g->out2 && !g->stats_out && g->grp_rows == 0 &&
+        g->add_tab == nullptr && (g->ld_out % 2 == 0) && ((reinterpret_cast<uintptr_t>(g->out) & 7) == 0))
+        tma_epi = true;
+    if ((g->stats_out || g->out2) && !ep.tma_store) {
         set_error("kx_gemm_bf16: stats_out / out2 need the staged epilogue (unscattered, 16-byte aligned rows, epi_mode 0)");
         return KX_ERR_ARG;
     }
