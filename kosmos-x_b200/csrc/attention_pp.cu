@@ -27,8 +27,8 @@ namespace kx {
 constexpr int PP_THREADS = 384;                     // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
 constexpr int PP_TILE_BYTES = 128 * 64 * 2;          // one [128 x 64] bf16 tile
 constexpr int PP_KV_STAGES = 3;
-constexpr int PP_SMEM_Q = 0;                                              // 2 tiles
-constexpr int PP_SMEM_K = PP_SMEM_Q + 2 * PP_TILE_BYTES;
+constexpr int PP_SMEM_Q = 0;                                              // 2 buffers x 2 tiles
+constexpr int PP_SMEM_K = PP_SMEM_Q + 4 * PP_TILE_BYTES;
 constexpr int PP_SMEM_V = PP_SMEM_K + PP_KV_STAGES * PP_TILE_BYTES;
 constexpr int PP_SMEM_BAR = PP_SMEM_V + PP_KV_STAGES * PP_TILE_BYTES;
 constexpr int PP_SMEM_BYTES = PP_SMEM_BAR + 256;
@@ -40,7 +40,7 @@ constexpr float PP_RESCALE_THRESHOLD = 8.0f;         // log2 units
 struct AttnPPParams {
     __nv_bfloat16* out;
     long long ld_out;
-    int seq_len, heads, num_pairs;
+    int seq_len, heads, batch, num_pairs;
     float scale_log2;                                // scale * log2(e)
     float2* stats_out;                               // [heads][batch*seq_len] partial (sum, sumsq) of the stored row, or null
     long long total_rows;
@@ -54,49 +54,70 @@ static long long* g_attn_trace = nullptr;            // kx_attn_set_trace
 #define KX_TRACE(role, iter, point)                                                                    \
     do {                                                                                               \
         if constexpr (TRACE) {                                                                         \
-            if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (iter) < 64)               \
+            if (p.trace != nullptr && blockIdx.x == 0 && n == 0 && (iter) < 64)                        \
                 p.trace[((role) * 64 + (iter)) * 8 + (point)] = clock64();                             \
         }                                                                                              \
     } while (0)
 
+// Work item = one pair of 128-row query tiles of one (batch, head).  Items are ordered heaviest first (longest
+// causal KV range) and CTA c takes items c, c + grid, c + 2*grid, ...: every CTA gets one item from each weight
+// class, so the static schedule is balanced.
+struct PPItem {
+    int pair, head, b, nblk0, nblk1, q0, row_base;
+};
+template <bool CAUSAL>
+__device__ __forceinline__ PPItem pp_item(const AttnPPParams& p, int item) {
+    PPItem it;
+    const int bh = p.heads * p.batch;
+    it.pair = p.num_pairs - 1 - item / bh;
+    const int r = item % bh;
+    it.head = r % p.heads;
+    it.b = r / p.heads;
+    const int nkv = (p.seq_len + 127) >> 7;
+    it.nblk0 = CAUSAL ? min(2 * it.pair + 1, nkv) : nkv;
+    it.nblk1 = CAUSAL ? min(2 * it.pair + 2, nkv) : nkv;
+    it.q0 = it.pair * 256;
+    it.row_base = it.b * p.seq_len;
+    return it;
+}
+
+// POLY: 26 of every 64 element pairs take exp2 through exp2_poly_x2 (FMA pipes) instead of MUFU.EX2 —
+// the split that balances the two pipes for this loop (FA4's trick).
 template <bool CAUSAL, bool POLY, bool TRACE = false>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PP_SMEM_BAR);
-    uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;                      // [3]
-    uint64_t* k_empty = bars + 4;                     // [3]
-    uint64_t* v_full = bars + 7;                      // [3]
-    uint64_t* v_empty = bars + 10;                    // [3]
-    uint64_t* s_full = bars + 13;                     // [2] per tile
-    uint64_t* p_full = bars + 15;                     // [2]
-    uint64_t* o_full = bars + 17;                     // [2]
-    uint64_t* s_free = bars + 19;                     // [2] softmax has read S_w out of TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint64_t* q_full = bars + 0;                      // [2] Q buffers
+    uint64_t* q_empty = bars + 2;                     // [2]
+    uint64_t* k_full = bars + 4;                      // [3]
+    uint64_t* k_empty = bars + 7;                     // [3]
+    uint64_t* v_full = bars + 10;                     // [3]
+    uint64_t* v_empty = bars + 13;                    // [3]
+    uint64_t* s_full = bars + 16;                     // [2] per tile
+    uint64_t* p_full = bars + 18;                     // [2]
+    uint64_t* o_full = bars + 20;                     // [2]
+    uint64_t* s_free = bars + 22;                     // [2] softmax has read S_w out of TMEM
+    uint64_t* o_read = bars + 24;                     // [2] epilogue has read O_w out of TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int pair = p.num_pairs - 1 - blockIdx.y;    // heaviest (longest KV range) pairs are scheduled first
-    const int head = blockIdx.x % p.heads;
-    const int b = blockIdx.x / p.heads;
     const int T = p.seq_len;
-    const int nkv = (T + 127) >> 7;
-    const int nblk0 = CAUSAL ? min(2 * pair + 1, nkv) : nkv;
-    const int nblk1 = CAUSAL ? min(2 * pair + 2, nkv) : nkv;
-    const int row_base = b * T;
-    const int q0 = pair * 256;
+    const int num_items = p.num_pairs * p.heads * p.batch;
+    const int grid = gridDim.x;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023) { printf("kx attn_pp: dynamic smem base not 1024-aligned\n"); __trap(); }
-        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); }
         for (int i = 0; i < PP_KV_STAGES; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2);     // released by both tiles' MMA threads
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
         }
         for (int w = 0; w < 2; ++w) {
-            mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 128); mbar_init(&o_full[w], 1); mbar_init(&s_free[w], 128);
+            mbar_init(&s_full[w], 1); mbar_init(&p_full[w], 128); mbar_init(&o_full[w], 1);
+            mbar_init(&s_free[w], 128); mbar_init(&o_read[w], 128);
         }
         fence_mbar_init();
     }
@@ -114,91 +135,118 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");       // hand registers to the softmax warpgroups
         if (warp == 8) {
             if (elect_one()) {
-                // ================= TMA producer =================
-                mbar_arrive_expect_tx(q_full, 2 * PP_TILE_BYTES);
-                tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q, head * 64, row_base + q0, kEvictFirst);
-                tma_load_2d(&tmQ, q_full, smem + PP_SMEM_Q + PP_TILE_BYTES, head * 64, row_base + q0 + 128, kEvictFirst);
-                int s = 0;
-                uint32_t ph = 0;
-                for (int j = 0; j < nblk1; ++j) {
-                    mbar_wait(&k_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&k_full[s], PP_TILE_BYTES);
-                    tma_load_2d(&tmK, &k_full[s], smem + PP_SMEM_K + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
-                    mbar_wait(&v_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&v_full[s], PP_TILE_BYTES);
-                    tma_load_2d(&tmV, &v_full[s], smem + PP_SMEM_V + s * PP_TILE_BYTES, head * 64, row_base + j * 128, kEvictLast);
-                    if (++s == PP_KV_STAGES) { s = 0; ph ^= 1; }
+                // ================= TMA producer: runs ahead across items (Q double-buffered, K/V rings continue) ========
+                uint32_t kv = 0;                                   // cumulative K/V block index -> ring slot / phase
+                for (int n = 0, item = blockIdx.x; item < num_items; ++n, item += grid) {
+                    const PPItem it = pp_item<CAUSAL>(p, item);
+                    const int qb = n & 1;
+                    mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&q_full[qb], 2 * PP_TILE_BYTES);
+                    uint8_t* qs = smem + PP_SMEM_Q + qb * 2 * PP_TILE_BYTES;
+                    tma_load_2d(&tmQ, &q_full[qb], qs, it.head * 64, it.row_base + it.q0, kEvictFirst);
+                    tma_load_2d(&tmQ, &q_full[qb], qs + PP_TILE_BYTES, it.head * 64, it.row_base + it.q0 + 128, kEvictFirst);
+                    for (int j = 0; j < it.nblk1; ++j, ++kv) {
+                        const uint32_t s = kv % PP_KV_STAGES, ph = (kv / PP_KV_STAGES) & 1;
+                        mbar_wait(&k_empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&k_full[s], PP_TILE_BYTES);
+                        tma_load_2d(&tmK, &k_full[s], smem + PP_SMEM_K + s * PP_TILE_BYTES, it.head * 64, it.row_base + j * 128, kEvictLast);
+                        mbar_wait(&v_empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&v_full[s], PP_TILE_BYTES);
+                        tma_load_2d(&tmV, &v_full[s], smem + PP_SMEM_V + s * PP_TILE_BYTES, it.head * 64, it.row_base + j * 128, kEvictLast);
+                    }
                 }
             }
         } else if (warp <= 10) {
             // ================= MMA issuers: warp 9 drives tile A, warp 10 tile B =================
-            // One elected thread per tile (elect.sync lets ptxas emit UTCHMMA without a divergence loop).  A
-            // single thread issuing all four MMA groups of an iteration was the measured bottleneck (~100
-            // cycles of issue overhead per tcgen05.mma against 32-64 cycles of execution at these tile sizes).
+            // One elected thread per tile (elect.sync lets ptxas emit UTCHMMA without a divergence loop; a single
+            // thread issuing all four MMA groups of an iteration was a measured bottleneck).  The first Q.K^T of the
+            // NEXT item is issued during the last block of the current one, so item boundaries cost no bubble.
             const int w = warp - 9;
-            const int nblk = w ? nblk1 : nblk0;
             if (elect_one()) {
                 constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
                 constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);    // P (TMEM)    x V (MN-major)
                 const uint32_t t_s = tmem_base + w * 128;
                 const uint32_t t_p = tmem_base + PP_TMEM_P + w * 64;
                 const uint32_t t_o = tmem_base + PP_TMEM_O + w * 64;
-                const uint64_t qdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_Q + w * PP_TILE_BYTES));
-                auto issue_s = [&](int slot) {
+                auto issue_s = [&](int qb, uint32_t slot) {
+                    const uint64_t qdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_Q + (qb * 2 + w) * PP_TILE_BYTES));
                     const uint64_t kdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_K + slot * PP_TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16<1>(t_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
                 };
-                auto issue_pv = [&](int slot, bool first) {
+                auto issue_pv = [&](uint32_t slot, bool first) {
                     const uint64_t vdesc = make_desc_sw128(smem_u32(smem + PP_SMEM_V + slot * PP_TILE_BYTES), PP_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)      // 16 keys per step: 8 TMEM columns of P, 16 V rows = 2 KB
                         umma_bf16_ts(t_o, t_p + k * 8, vdesc + k * (2048 >> 4), idesc_o, (!first || k != 0) ? 1u : 0u);
                 };
-                mbar_wait(q_full, 0);
-                mbar_wait(&k_full[0], 0);
-                tc_fence_after();
-                issue_s(0);
-                umma_commit(&s_full[w]);
-                umma_commit(&k_empty[0]);                  // K/V slots are released by BOTH tiles' commits (count 2)
-                int s = 0;
-                uint32_t ph = 0;
-                for (int j = 0; j < nblk1; ++j) {
-                    int sn = s + 1;
-                    uint32_t phn = ph;
-                    if (sn == PP_KV_STAGES) { sn = 0; phn ^= 1; }
-                    if (j < nblk) {
-                        KX_TRACE(2 + w, j, 0);
-                        if (j + 1 < nblk) {                 // next scores: need only S_w(j) to have been read
-                            mbar_wait(&s_free[w], j & 1);
-                            KX_TRACE(2 + w, j, 1);
-                            mbar_wait(&k_full[sn], phn);
-                            tc_fence_after();
-                            issue_s(sn);
-                            umma_commit(&s_full[w]);
-                            umma_commit(&k_empty[sn]);
-                            KX_TRACE(2 + w, j, 2);
-                        }
-                        mbar_wait(&v_full[s], ph);
-                        mbar_wait(&p_full[w], j & 1);
-                        KX_TRACE(2 + w, j, 3);
+                uint32_t cum = 0;                                  // blocks of tile w processed in earlier items
+                uint32_t kvb = 0;                                  // cumulative K/V index of this item's block 0
+                for (int n = 0, item = blockIdx.x; item < num_items; ++n, item += grid) {
+                    const PPItem it = pp_item<CAUSAL>(p, item);
+                    const int nblk = w ? it.nblk1 : it.nblk0;
+                    const int qb = n & 1;
+                    const bool has_next = item + grid < num_items;
+                    if (n == 0) {                                   // only the very first score tile has no predecessor to hide behind
+                        mbar_wait(&q_full[0], 0);
+                        mbar_wait(&k_full[0], 0);
                         tc_fence_after();
-                        issue_pv(s, j == 0);
-                        umma_commit(&o_full[w]);
-                        umma_commit(&v_empty[s]);
-                        KX_TRACE(2 + w, j, 4);
-                    } else {
-                        // tile A has one block fewer than tile B (causal): release the slots it does not use,
-                        // once they have been filled (their previous phase is then complete)
-                        mbar_wait(&v_full[s], ph);
-                        mbar_arrive(&v_empty[s]);
+                        issue_s(0, 0);
+                        umma_commit(&s_full[w]);
+                        umma_commit(&k_empty[0]);                  // K/V slots are released by BOTH tiles (count 2)
+                        if (nblk == 1) umma_commit(&q_empty[0]);
                     }
-                    if (j + 1 < nblk1 && j + 1 >= nblk) {
-                        mbar_wait(&k_full[sn], phn);
-                        mbar_arrive(&k_empty[sn]);
+                    for (int j = 0; j < it.nblk1; ++j) {
+                        const uint32_t kv = kvb + j;
+                        const uint32_t s = kv % PP_KV_STAGES, ph = (kv / PP_KV_STAGES) & 1;
+                        if (j < nblk) {
+                            KX_TRACE(2 + w, j, 0);
+                            if (j + 1 < nblk) {                     // next scores of this item: need only S_w(j) to have been read
+                                const uint32_t kn = kv + 1, sn = kn % PP_KV_STAGES;
+                                mbar_wait(&s_free[w], (cum + j) & 1);
+                                KX_TRACE(2 + w, j, 1);
+                                mbar_wait(&k_full[sn], (kn / PP_KV_STAGES) & 1);
+                                tc_fence_after();
+                                issue_s(qb, sn);
+                                umma_commit(&s_full[w]);
+                                umma_commit(&k_empty[sn]);
+                                if (j + 2 == nblk) umma_commit(&q_empty[qb]);      // that was this item's last read of Q_w
+                                KX_TRACE(2 + w, j, 2);
+                            } else if (has_next) {                  // last block: first scores of the NEXT item
+                                const PPItem nx = pp_item<CAUSAL>(p, item + grid);
+                                const uint32_t kn = kvb + it.nblk1, sn = kn % PP_KV_STAGES;
+                                mbar_wait(&s_free[w], (cum + j) & 1);
+                                mbar_wait(&q_full[qb ^ 1], ((n + 1) >> 1) & 1);
+                                mbar_wait(&k_full[sn], (kn / PP_KV_STAGES) & 1);
+                                tc_fence_after();
+                                issue_s(qb ^ 1, sn);
+                                umma_commit(&s_full[w]);
+                                umma_commit(&k_empty[sn]);
+                                if ((w ? nx.nblk1 : nx.nblk0) == 1) umma_commit(&q_empty[qb ^ 1]);
+                            }
+                            mbar_wait(&v_full[s], ph);
+                            mbar_wait(&p_full[w], (cum + j) & 1);
+                            if (j == 0 && n > 0) mbar_wait(&o_read[w], (n - 1) & 1);   // previous item's O has been read out
+                            KX_TRACE(2 + w, j, 3);
+                            tc_fence_after();
+                            issue_pv(s, j == 0);
+                            umma_commit(&o_full[w]);
+                            umma_commit(&v_empty[s]);
+                            KX_TRACE(2 + w, j, 4);
+                        } else {
+                            // tile A has one block fewer than tile B (causal): release the slots it does not use,
+                            // once they have been filled (their previous phase is then complete)
+                            mbar_wait(&v_full[s], ph);
+                            mbar_arrive(&v_empty[s]);
+                        }
+                        if (j + 1 < it.nblk1 && j + 1 >= nblk) {
+                            const uint32_t kn = kv + 1, sn = kn % PP_KV_STAGES;
+                            mbar_wait(&k_full[sn], (kn / PP_KV_STAGES) & 1);
+                            mbar_arrive(&k_empty[sn]);
+                        }
                     }
-                    s = sn;
-                    ph = phn;
+                    cum += nblk;
+                    kvb += it.nblk1;
                 }
             }
         }
@@ -207,21 +255,27 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // ================= softmax / output: warps 0-3 tile A, warps 4-7 tile B; thread == query row ==========
         const int w = warp >> 2;
         const int r = (warp & 3) * 32 + lane;
-        const int qrow = q0 + w * 128 + r;
-        const int nblk = w ? nblk1 : nblk0;
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t tmem_s = tmem_base + lane_addr + w * 128;
         const uint32_t tmem_p = tmem_base + lane_addr + PP_TMEM_P + w * 64;
         const uint32_t tmem_o = tmem_base + lane_addr + PP_TMEM_O + w * 64;
         const float sl2 = p.scale_log2;
         const uint64_t sl2x2 = pack_f32x2(sl2, sl2);
+        uint32_t cum = 0;
+
+        for (int n = 0, item = blockIdx.x; item < num_items; ++n, item += grid) {
+        const PPItem it = pp_item<CAUSAL>(p, item);
+        const int nblk = w ? it.nblk1 : it.nblk0;
+        const int q0 = it.q0, head = it.head, row_base = it.row_base;
+        const int qrow = q0 + w * 128 + r;
         float m_ref = -INFINITY;      // reference maximum the exponentials are taken against (raw score units)
         float l_run = 0.f;
 
         for (int j = 0; j < nblk; ++j) {
             const int kv0 = j * 128;
+            const uint32_t par = (cum + j) & 1;
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 0);
-            mbar_wait(&s_full[w], j & 1);
+            mbar_wait(&s_full[w], par);
             tc_fence_after();
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 1);
             uint32_t sv[128];
@@ -263,7 +317,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (__any_sync(0xffffffffu, grow)) {
                     // commit the new maximum: O (in TMEM, complete up to block j-1) and l are rescaled
                     const float alpha = (m_new == m_ref) ? 1.f : ex2_approx((m_ref - m_new) * sl2);
-                    mbar_wait(&o_full[w], (j - 1) & 1);
+                    mbar_wait(&o_full[w], par ^ 1);
                     tc_fence_after();
 #pragma unroll
                     for (int hlf = 0; hlf < 2; ++hlf) {
@@ -278,50 +332,36 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     m_ref = m_new;
                 }
             }
-
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 3);
-            // ---- p = exp2(s*scale - m_ref*scale): packed FFMA2, MUFU ex2, packed row sum, bf16x2 pack
+
+            // ---- p = exp2(s*scale - m_ref*scale): packed FFMA2, MUFU ex2 / FMA polynomial, packed row sum, bf16x2 pack
             const float nm = -m_ref * sl2;
             const uint64_t nm2 = pack_f32x2(nm, nm);
             uint64_t acc0 = 0ull, acc1 = 0ull;         // (0.f, 0.f)
             uint32_t pv[64];
-            // Software pipeline over 4 groups of 16 pairs: the exponentials of group g are issued while the
-            // results of group g-1 (16 pairs = 32 MUFU issue slots earlier) are summed and packed, so no
-            // consumer waits on MUFU latency.  The exponentials overwrite the scores in place (sv).
 #pragma unroll
-            for (int g = 0; g <= 4; ++g) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (g < 4) {
-                        const int i = g * 16 + k;
-                        const uint64_t x = ffma2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2x2, nm2);
-                        float x0, x1, e0, e1;
-                        unpack_f32x2(x, x0, x1);
-                        if (POLY && ((i % 5) == 1 || (i % 5) == 3)) {
-                            exp2_poly_x2(x0, x1, e0, e1);
-                        } else {
-                            e0 = ex2_approx(x0);
-                            e1 = ex2_approx(x1);
-                        }
-                        sv[2 * i] = __float_as_uint(e0);
-                        sv[2 * i + 1] = __float_as_uint(e1);
-                    }
-                    if (g > 0) {
-                        const int i = (g - 1) * 16 + k;
-                        const float e0 = __uint_as_float(sv[2 * i]), e1 = __uint_as_float(sv[2 * i + 1]);
-                        const uint64_t e = pack_f32x2(e0, e1);
-                        if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
-                        pv[i] = pack_bf16(e0, e1);
-                    }
+            for (int i = 0; i < 64; ++i) {
+                const uint64_t x = ffma2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2x2, nm2);
+                float x0, x1, e0, e1;
+                unpack_f32x2(x, x0, x1);
+                if (POLY && ((i % 5) == 1 || (i % 5) == 3)) {
+                    exp2_poly_x2(x0, x1, e0, e1);
+                } else {
+                    e0 = ex2_approx(x0);
+                    e1 = ex2_approx(x1);
                 }
+                const uint64_t e = pack_f32x2(e0, e1);
+                if (i & 1) acc1 = fadd2(acc1, e); else acc0 = fadd2(acc0, e);
+                pv[i] = pack_bf16(e0, e1);
             }
             float a0, a1;
             unpack_f32x2(fadd2(acc0, acc1), a0, a1);
             l_run += a0 + a1;
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 4);
-            // P region: element pair (2c, 2c+1) in column c.  P.V of the previous block must have consumed it.
+            // P region: element pair (2c, 2c+1) in column c.  P.V of the previous block must have consumed it
+            // (for j == 0 the previous item's epilogue already waited for its last P.V).
             if (j > 0) {
-                mbar_wait(&o_full[w], (j - 1) & 1);
+                mbar_wait(&o_full[w], par ^ 1);
                 tc_fence_after();
             }
             tmem_st32(tmem_p, reinterpret_cast<uint32_t(&)[32]>(pv[0]));
@@ -333,19 +373,20 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 6);
         }
 
-        // ---- epilogue: O / l -> bf16, head-merged token-major output
-        mbar_wait(&o_full[w], (nblk - 1) & 1);
+        // ---- epilogue of this item: O / l -> bf16, head-merged token-major output
+        mbar_wait(&o_full[w], (cum + nblk - 1) & 1);
         tc_fence_after();
         uint32_t ov[64];
         tmem_ld32(tmem_o, reinterpret_cast<uint32_t(&)[32]>(ov[0]));
         tmem_ld32(tmem_o + 32, reinterpret_cast<uint32_t(&)[32]>(ov[32]));
         tmem_ld_wait();
         tc_fence_before();
+        mbar_arrive(&o_read[w]);                          // the next item's first P.V may overwrite O_w
         if (qrow < T) {
             const float inv_l = 1.0f / l_run;
             __nv_bfloat16* o = p.out + static_cast<long long>(row_base + qrow) * p.ld_out + head * 64;
-#pragma unroll
             float s1 = 0.f, s2 = 0.f;
+#pragma unroll
             for (int g = 0; g < 8; ++g) {
                 uint4 q;
                 q.x = pack_bf16(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
@@ -365,6 +406,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             if (p.stats_out != nullptr) p.stats_out[static_cast<long long>(head) * p.total_rows + row_base + qrow] = make_float2(s1, s2);
         }
+        cum += nblk;
+        }   // items
     }
 
     __syncwarp();
@@ -385,6 +428,7 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.ld_out = ld_out;
     p.seq_len = seq_len;
     p.heads = heads;
+    p.batch = batch;
     p.num_pairs = (seq_len + 255) / 256;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.stats_out = reinterpret_cast<float2*>(stats_out);
@@ -405,8 +449,11 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
         }
         attr_set = true;
     }
-    if (p.num_pairs > 65535) { set_error("kx_attn_fwd: sequence too long"); return KX_ERR_ARG; }
-    dim3 grid(heads * batch, p.num_pairs);
+    const long long items = static_cast<long long>(p.num_pairs) * heads * batch;
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    if (items > 0x7fffffffLL) { set_error("kx_attn_fwd: too many tiles"); return KX_ERR_ARG; }
+    dim3 grid(static_cast<unsigned>(items < sms ? items : sms));    // persistent: one CTA per SM, static item schedule
     if (p.trace != nullptr && causal) {          // profiling aid (kx_attn_set_trace): same kernel with clock64 stamps
         static bool tattr = false;
         if (!tattr) {
