@@ -82,8 +82,9 @@ typedef struct kx_gemm_args {
     const float* ln_c;            /* fp32 [N]: sum_k W[n,k] of the (bf16) folded weight */
     int ln_tiles, ln_cols;
     float ln_eps;
-    /* producer side: per-row partial (sum, sumsq) of the values this GEMM stores, one pair per 128-column
-     * block ([ceil(N/128)][M][2] fp32; forces block_n = 256), and a bf16 copy of an fp32 output; the
+    /* producer side: per-row partial (sum, sumsq) of the values this GEMM stores, one pair per half tile
+     * ([ceil(N/128)][M][2] fp32 with block_n = 256, the default here; [ceil(N/64)][M][2] with block_n = 128),
+     * and a bf16 copy of an fp32 output; the
      * statistics are those of the bf16 copy when one is written.  Both need the staged epilogue. */
     float* stats_out;
     void* out2;

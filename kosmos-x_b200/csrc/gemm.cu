@@ -86,7 +86,7 @@ struct GemmEpi {
     float ln_inv_n, ln_eps;
     // producer side: per-row partial (sum, sumsq) of the values this GEMM stores (after bf16 rounding),
     // one pair per (128-column block, row); and an optional bf16 copy of an fp32 output (staged epilogue only)
-    float2* stats_out;         // [ceil(N/128)][M] or null
+    float2* stats_out;         // [ceil(N/(BN/2))][M] or null
     void* out2;                // bf16 [M, ld_out2] or null
     long long ld_out2;
 };
@@ -803,7 +803,8 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     if (sms <= 0) return KX_ERR_NO_DEVICE;
     int cg = g->cta_group;
     if (cg == 0) cg = (g->M > 128) ? 2 : 1;
-    int bn = g->stats_out ? 256 : g->block_n;
+    int bn = g->block_n;
+    if (g->stats_out && bn == 0) bn = 256;           // partials are per half tile: 128 columns at BN=256, 64 at BN=128
     if (bn == 0) bn = (g->N >= 256 && (long long)((g->M + 127) / 128) * ((g->N + 255) / 256) >= sms / 2) ? 256 : 128;
     const int max_ctas = g->max_ctas > 0 ? std::min(g->max_ctas, sms) : sms;
 

@@ -482,14 +482,13 @@ class Kosmos(_KosmosBase):
         layers = []
         for L in cm.encoder.layers:
             a = L.self_attn
+            # layer_norm1 / layer_norm2 are folded into q|k|v and fc1 (same scheme as the decoder)
             layers.append(dict(
-                w_qkv=_bf16(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
-                b_qkv=_f32(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)),
+                qkv=_fold_ln(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0),
+                             torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0), L.layer_norm1),
                 w_o=_bf16(a.out_proj.weight), b_o=_f32(a.out_proj.bias),
-                w_fc1=_bf16(L.mlp.fc1.weight), b_fc1=_f32(L.mlp.fc1.bias),
+                fc1=_fold_ln(L.mlp.fc1.weight, L.mlp.fc1.bias, L.layer_norm2),
                 w_fc2=_bf16(L.mlp.fc2.weight), b_fc2=_f32(L.mlp.fc2.bias),
-                ln1=(_f32(L.layer_norm1.weight), _f32(L.layer_norm1.bias)),
-                ln2=(_f32(L.layer_norm2.weight), _f32(L.layer_norm2.bias)),
             ))
         pl = []
         for attn, ff in self.perceive.layers:
@@ -521,7 +520,6 @@ class Kosmos(_KosmosBase):
         patches = ws.get("patches", (B * P, vp["k_pad"]), torch.bfloat16, dev)
         emb = ws.get("vemb", (M, Dv), torch.float32, dev)
         x = ws.get("vx", (M, Dv), torch.float32, dev)
-        h = ws.get("vh", (M, Dv), torch.bfloat16, dev)
         qkv = ws.get("vqkv", (M, 3 * Dv), torch.bfloat16, dev)
         att = ws.get("vatt", (M, Dv), torch.bfloat16, dev)
         mid = ws.get("vmid", (M, cfg.vit_mlp), torch.bfloat16, dev)
@@ -530,15 +528,23 @@ class Kosmos(_KosmosBase):
         ops.layernorm(emb, *vp["pre_ln"], x, eps=cfg.eps)                    # fp32 out: the residual stream
         act = _abi.KX_ACT_GELU if cfg.vit_act == "gelu" else _abi.KX_ACT_QUICK_GELU
         scale = (Dv // cfg.vit_heads) ** -0.5
-        for L in vp["layers"]:
-            ops.layernorm(x, *L["ln1"], h, eps=cfg.eps)
-            ops.gemm(h, L["w_qkv"], qkv, bias=L["b_qkv"])
+        xb = ws.get("vxb", (M, Dv), torch.bfloat16, dev)                      # bf16 copy of the stream (GEMM operand)
+        st0 = ws.get("vst0", (1, M, 2), torch.float32, dev)
+        # 64-column partials = 128-wide tiles for the N = Dv GEMMs: twice as many tiles to spread over the SMs
+        st_a = ws.get("vst_a", ((Dv + 63) // 64, M, 2), torch.float32, dev)
+        st_b = ws.get("vst_b", ((Dv + 63) // 64, M, 2), torch.float32, dev)
+        ops.rowstats_cast(x, xb, st0)
+        cur = st0
+        for L in vp["layers"]:                                               # 5 launches per layer, no stand-alone LayerNorm
+            w, c, d = L["qkv"]
+            ops.gemm(xb, w, qkv, bias=d, ln=(cur, c, Dv, cfg.eps))
             ops.attention(qkv[:, :Dv], qkv[:, Dv:2 * Dv], qkv[:, 2 * Dv:], att, batch=B, heads=cfg.vit_heads,
                           seq_len=Tv, causal=False, scale=scale)
-            ops.gemm(att, L["w_o"], x, bias=L["b_o"], res=x)
-            ops.layernorm(x, *L["ln2"], h, eps=cfg.eps)
-            ops.gemm(h, L["w_fc1"], mid, bias=L["b_fc1"], act=act)
-            ops.gemm(mid, L["w_fc2"], x, bias=L["b_fc2"], res=x)
+            ops.gemm(att, L["w_o"], x, bias=L["b_o"], res=x, stats_out=st_a, out2=xb)
+            w, c, d = L["fc1"]
+            ops.gemm(xb, w, mid, bias=d, act=act, ln=(st_a, c, Dv, cfg.eps))
+            ops.gemm(mid, L["w_fc2"], x, bias=L["b_fc2"], res=x, stats_out=st_b, out2=xb)
+            cur = st_b
         return x
 
     def _perceive_project(self, xv: torch.Tensor, B: int, x0: torch.Tensor, T: int, img_start: int):

@@ -109,8 +109,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
         g.ln_part, g.ln_c, g.ln_tiles, g.ln_cols, g.ln_eps = part.data_ptr(), c.data_ptr(), part.shape[0], cols, eps
     if stats_out is not None:
         _req(stats_out, torch.float32, "stats_out")
-        if tuple(stats_out.shape) != ((g.N + 127) // 128, g.M, 2) or not stats_out.is_contiguous():
-            raise ValueError(f"gemm: stats_out must be contiguous [{(g.N + 127) // 128}, {g.M}, 2]")
+        # one partial per half tile: [ceil(N/128), M, 2] selects 256-wide tiles, [ceil(N/64), M, 2] 128-wide ones
+        if not stats_out.is_contiguous() or stats_out.ndim != 3 or tuple(stats_out.shape[1:]) != (g.M, 2):
+            raise ValueError(f"gemm: stats_out must be contiguous [tiles, {g.M}, 2]")
+        if stats_out.shape[0] == (g.N + 127) // 128 and block_n in (0, 256):
+            g.block_n = 256
+        elif stats_out.shape[0] == (g.N + 63) // 64 and block_n in (0, 128):
+            g.block_n = 128
+        else:
+            raise ValueError(f"gemm: stats_out has {stats_out.shape[0]} partials; expected {(g.N + 127) // 128} "
+                             f"(block_n 256) or {(g.N + 63) // 64} (block_n 128)")
         g.stats_out = stats_out.data_ptr()
     if out2 is not None:
         _req(out2, torch.bfloat16, "out2")

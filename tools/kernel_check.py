@@ -297,6 +297,18 @@ def case_ln_fold():
             zf = z.float()
             ok &= report("bf16 producer stats sum", st3[:, :, 0].sum(0), zf.sum(1), 1e-3 * math.sqrt(N2) + 1e-3)
             ok &= report("bf16 producer stats sumsq", st3[:, :, 1].sum(0), (zf * zf).sum(1), 1e-4 * N2)
+    # 128-wide tiles: one partial per 64 columns
+    M3, K3, N3 = 2056, 256, 1024
+    a3 = torch.randn(M3, K3, device=dev).bfloat16()
+    w3 = (torch.randn(N3, K3, device=dev) / math.sqrt(K3)).bfloat16()
+    y3 = torch.randn(M3, N3, device=dev)
+    r3 = y3.clone()
+    yb3 = torch.zeros(M3, N3, device=dev, dtype=torch.bfloat16)
+    st4 = torch.zeros(N3 // 64, M3, 2, device=dev)
+    ops.gemm(a3, w3, y3, res=y3, stats_out=st4, out2=yb3)
+    ok &= report("bn=128 producer out", y3, a3.float() @ w3.float().T + r3, 1e-2)
+    ok &= report("bn=128 producer stats sum", st4[:, :, 0].sum(0), yb3.float().sum(1), 5e-2)
+    ok &= report("bn=128 producer stats sumsq", st4[:, :, 1].sum(0), (yb3.float() ** 2).sum(1), 2e-1)
     # attention: per-head partial statistics of the stored rows
     B, H, T = 2, 4, 300
     qkv = torch.randn(B * T, 3 * H * 64, device=dev).bfloat16()
