@@ -516,6 +516,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (col < BN) { s_vec[col] = bv; s_vec[BN + col] = cv; }
                     named_bar_sync(1, EPI_WARPS * 32);
                 }
+                if (has_res && lane < CPW) {
+                    // the residual comes from HBM (a 134 MB stream): pull the NEXT tile's sub-tiles of this warp into L2 now,
+                    // a whole tile time ahead, so that the single-buffered TMA loads below only see L2 latency
+                    const int tn = t + num_clusters;
+                    if (tn < num_tiles) {
+                        int mb2, nb2;
+                        tile_coords(tn, num_m, num_n, mb2, nb2);
+                        const int mr = mb2 * (BLOCK_M * CG) + rank * BLOCK_M + q * 32;
+                        const int nc = nb2 * BN + (c_begin + lane) * 32;
+                        if (mr < ep.M && nc < ep.N) tma_prefetch_l2_2d(&tmRes, nc, mr);
+                    }
+                }
                 auto issue_res = [&](int c) {               // residual sub-tile of chunk c -> main (freed by wait_main_free)
                     if (lane == 0) {
                         mbar_arrive_expect_tx(rbar, EPI_STAGE_BYTES);
