@@ -566,6 +566,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if constexpr (OUT_F32) {
                         if (has_res) {
                             mbar_wait(rbar, unit & 1);
+                            KX_GT(it, c, 7);
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
                                 const float4 x = *reinterpret_cast<const float4*>(mb + ((g ^ sw) << 4));
@@ -646,7 +647,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
-                KX_GT(it, 7, 7);
+                KX_GT(it, 0, 0 + 8 * 0);
                 if (has_stats && m < ep.M && nb + c_begin * 32 < ep.N) {      // one partial per 128 columns
                     float t1, t2;
                     stats_fold(sacc, t1, t2);

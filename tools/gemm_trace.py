@@ -45,13 +45,13 @@ torch.cuda.synchronize()
 lib.kx_gemm_set_trace(None)
 t = buf.cpu()
 t0 = int(t[t > 0].min())
-print(f"{which}: M={M} N={N} K={K}; points per chunk: 3 chunk start, 4 after store-wait/res-issue, 5 TMEM data ready, 6 math done;"
-      " chunk0 extra: 0 tile start, 1 vectors staged, 2 accumulator ready; (chunk 7, point 7) = tile done")
+print(f"{which}: M={M} N={N} K={K}; points per chunk: 3 chunk start, 4 after store-wait/res-issue, 5 TMEM data ready, 6 math done,"
+      " 7 residual landed; chunk0 extra: 0 tile start (overwritten at tile end), 1 vectors staged, 2 accumulator ready")
 for tile in range(8):
     if int(t[tile].max()) == 0:
         continue
     r0 = t[tile, 0]
-    print(f"tile {tile}: start {int(r0[0]) - t0:7d} vec {int(r0[1]) - t0:7d} acc-ready {int(r0[2]) - t0:7d}  done {int(t[tile, 7, 7]) - t0:7d}")
+    print(f"tile {tile}: end {int(r0[0]) - t0:7d} vec {int(r0[1]) - t0:7d} acc-ready {int(r0[2]) - t0:7d}")
     for ch in range(8):
         r = t[tile, ch]
-        print("    chunk %d: " % ch + " ".join(f"{(int(x) - t0) if int(x) > 0 else -1:7d}" for x in r[3:7]))
+        print("    chunk %d: " % ch + " ".join(f"{(int(x) - t0) if int(x) > 0 else -1:7d}" for x in r[3:8]))
