@@ -516,26 +516,54 @@ class KosmosOracle(nn.Module):
     def set_emulation(self, on: bool):
         self.emu.on = on
 
-    def forward(self, text_tokens, images, **kwargs):
+    def _image_rows(self, images):
+        """ViT -> perceiver -> image_proj: (B,3,H,W) -> (B,1,64,dim); (B,m,3,H,W) -> (B,m,64,dim)."""
+        if images.ndim == 5:                                                   # config 5: m images per sequence
+            B, m = images.shape[:2]
+            feats = self.clip_model(pixel_values=images.flatten(0, 1))         # model.py:230 per image
+            feats = self.perceive(feats.view(B, m, *feats.shape[1:]))          # (B, m, 64, Dv): media index = image index (A.2)
+        else:
+            feats = self.perceive(self.clip_model(pixel_values=images))        # model.py:230-231 (B, 1, 64, Dv)
+        return F.linear(self.emu.r(feats), self.emu.r(self.image_proj.weight)) # model.py:232
+
+    @staticmethod
+    def splice(embed, rows, image_positions):
+        """torch.cat of model.py:239-241, generalised: image i's rows go in front of text token
+        image_positions[i] (the reference is the single-image case image_positions = [2])."""
+        m = rows.shape[1]
+        pos = [2] if image_positions is None else list(image_positions)
+        if len(pos) != m or sorted(pos) != pos or pos[0] < 0 or pos[-1] > embed.shape[1]:
+            raise ValueError(f"image_positions {pos} does not describe {m} ascending text positions")
+        parts, prev = [], 0
+        for i, p in enumerate(pos):
+            parts += [embed[:, prev:p], rows[:, i]]
+            prev = p
+        parts.append(embed[:, prev:])
+        return torch.cat(parts, dim=1)
+
+    def embed_inputs(self, text_tokens, images, image_positions=None):
+        """model.py:230-244: the decoder input x0 (B, T_text + 64*m, dim), positions added."""
+        rows = self._image_rows(images)
+        model_input = self.decoder.forward_embedding(text_tokens)[1]           # model.py:238
+        model_input = self.splice(model_input, rows, image_positions)          # model.py:239-241
+        return self.decoder.forward_embedding(model_input, token_embedding=model_input)[0]   # model.py:242-244
+
+    def forward(self, text_tokens, images, image_positions=None, **kwargs):
         if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):
             raise TypeError("text_tokens and images must be instances of torch.Tensor")
-        images = self.clip_model(pixel_values=images)                          # model.py:230
-        images = self.perceive(images).squeeze(1)                              # model.py:231
-        images = F.linear(self.emu.r(images), self.emu.r(self.image_proj.weight))  # model.py:232
-        model_input = self.decoder.forward_embedding(text_tokens)[1]           # model.py:238
-        model_input = torch.cat([model_input[:, 0:2], images, model_input[:, 2:]], dim=1)
-        model_input = self.decoder.forward_embedding(model_input, token_embedding=model_input)[0]
+        model_input = self.embed_inputs(text_tokens, images, image_positions)
         return self.decoder(model_input, passed_x=model_input)[0]              # model.py:250
 
     @torch.no_grad()
-    def stages(self, text_tokens, images):
+    def stages(self, text_tokens, images, image_positions=None):
         """Intermediate tensors, for per-stage parity tests."""
         out = {}
-        out["vit"] = self.clip_model(pixel_values=images)
-        out["perceive"] = self.perceive(out["vit"]).squeeze(1)
-        out["image_proj"] = F.linear(self.emu.r(out["perceive"]), self.emu.r(self.image_proj.weight))
+        flat = images.flatten(0, 1) if images.ndim == 5 else images
+        out["vit"] = self.clip_model(pixel_values=flat)
+        rows = self._image_rows(images)
+        out["image_proj"] = rows.squeeze(1) if images.ndim == 4 else rows
         emb = self.decoder.forward_embedding(text_tokens)[1]
-        x = torch.cat([emb[:, 0:2], out["image_proj"], emb[:, 2:]], dim=1)
+        x = self.splice(emb, rows, image_positions)
         out["x0"] = self.decoder.forward_embedding(x, token_embedding=x)[0]
         logits, extra = self.decoder(out["x0"], passed_x=out["x0"])
         out["inner_states"] = extra["inner_states"]
@@ -563,11 +591,13 @@ class KosmosLanguageOracle(nn.Module):
 
 
 # --------------------------------------------------------------------------- helpers
-def make_inputs(cfg: OracleConfig, batch: int, t_text: int, seed: int = 1):
-    """Synthetic inputs as README.md:34-37 / example.py:5-8 of the reference."""
+def make_inputs(cfg: OracleConfig, batch: int, t_text: int, seed: int = 1, n_images: int | None = None):
+    """Synthetic inputs as README.md:34-37 / example.py:5-8 of the reference; n_images = m gives the
+    (B, m, 3, H, W) multi-image form of config 5."""
     g = torch.Generator().manual_seed(seed)
     text = torch.randint(0, cfg.vocab, (batch, t_text), dtype=torch.long, generator=g)
-    images = torch.randn(batch, 3, cfg.image, cfg.image, generator=g)
+    shape = (batch, 3, cfg.image, cfg.image) if n_images is None else (batch, n_images, 3, cfg.image, cfg.image)
+    images = torch.randn(*shape, generator=g)
     return text, images
 
 
