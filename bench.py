@@ -45,6 +45,17 @@ T_TEXT = SEQ - N_LATENTS
 BATCH_PER_GPU = 8
 VOCAB = 32002
 
+# --workload: the default is the configuration the metric is quoted on (configs[2]); c5 is the multi-image stress
+# (configs[4]: 4 images per sequence at spliced rows 2, 514, 1026, 1538, B=4 per GPU -> 32 global at 8 GPUs)
+WORKLOADS = {
+    "c3": dict(batch=8, images=1, positions=None, t_text=SEQ - N_LATENTS,
+               name="configs[2]: full Kosmos forward (ViT-L/14 + perceiver + 24-layer decoder + LM head), B=8 per GPU, "
+                    "seq=2048 (1984 text + 64 image latents), 1 image 224x224 per sequence"),
+    "c5": dict(batch=4, images=4, positions=[2, 450, 898, 1346], t_text=SEQ - 4 * N_LATENTS,
+               name="configs[4]: interleaved 4 images/seq (perceiver + image-splice stress), B=4 per GPU, seq=2048 "
+                    "(1792 text + 4x64 image latents at spliced rows 2/514/1026/1538)"),
+}
+
 
 def _peaks():
     try:
@@ -125,9 +136,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU reference (oracle)
-def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0):
+def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0, wl=None):
     """The reference path restated on the CPU (oracle/kosmos_oracle.py), fp32, all host threads.
-    One step = ONE sequence of the benchmark workload (T=2048, one image): 1/8 of a GPU step."""
+    One step = ONE sequence of the benchmark workload (T=2048): 1/B of a GPU step."""
+    wl = wl or WORKLOADS["c3"]
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kosmos_oracle as ko
@@ -136,7 +148,9 @@ def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0):
     cfg = ko.OracleConfig(max_positions=SEQ + 2, multiway=False)    # .B branches never execute
     model = ko.build(cfg, seed=0)
     small = ko.make_inputs(cfg, 1, 50, seed=1)
-    text, images = ko.make_inputs(cfg, 1, T_TEXT, seed=1)
+    multi = wl["images"] > 1
+    text, images = ko.make_inputs(cfg, 1, wl["t_text"], seed=1, n_images=wl["images"] if multi else None)
+    kw = dict(image_positions=wl["positions"]) if multi else {}
     times = []
     t_begin = time.perf_counter()
     with torch.no_grad():
@@ -146,27 +160,29 @@ def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0):
             if i >= warmup + 1 and time.perf_counter() - t_begin > budget_s:
                 break                                              # bounded sample: stop once the budget is spent
             t0 = time.perf_counter()
-            out = model(text, images)
+            out = model(text, images, **kw)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     assert out.shape == (1, SEQ, VOCAB)
     ms = 1e3 * sum(times) / len(times)
     return dict(value=SEQ / (ms / 1e3), ms_per_step=ms, steps_done=len(times), cores=cores,
-                sample=f"1 sequence (T={SEQ}: {T_TEXT} text tokens + 1 image) per step, fp32 eager PyTorch oracle, "
+                sample=f"1 sequence (T={SEQ}: {wl['t_text']} text tokens + {wl['images']} image(s)) per step, fp32 eager PyTorch oracle, "
                        f"{cores} threads, {len(times)} timed step(s)")
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    r = cpu_reference(args.steps, max(args.warmup, 0))
+    wl = WORKLOADS[args.workload]
+    r = cpu_reference(args.steps, max(args.warmup, 0), wl=wl)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps_done"], "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2] sample: Kosmos.forward on 1 sequence, seq=2048 (1984 text + 64 image latents), "
-                               "1 image 224x224, CPU", "global_batch": 1, "seq_len": SEQ, "parallelism": "cpu"},
+        "config": {"workload": wl["name"].split(":")[0] + " sample: Kosmos.forward on 1 sequence, seq=2048 "
+                               f"({wl['t_text']} text + {wl['images']}x64 image latents), {wl['images']} image(s) 224x224, CPU",
+                   "global_batch": 1, "seq_len": SEQ, "parallelism": "cpu"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -189,17 +205,19 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     peaks = _peaks()
-    B = BATCH_PER_GPU
+    wl = WORKLOADS[args.workload]
+    B, n_img, t_text = wl["batch"], wl["images"], wl["t_text"]
+    fkw = dict(image_positions=wl["positions"]) if n_img > 1 else {}
 
     torch.manual_seed(0)                                   # same replicated random-init weights on every rank
     model = Kosmos(config=KosmosConfig(max_positions=SEQ + 2), device=dev, cuda_graph=args.graph)
     g = torch.Generator().manual_seed(1 + rank)            # each rank owns its shard of the global batch
-    h_text = torch.randint(0, VOCAB, (B, T_TEXT), dtype=torch.long, generator=g).pin_memory()
-    h_img = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    h_text = torch.randint(0, VOCAB, (B, t_text), dtype=torch.long, generator=g).pin_memory()
+    h_img = torch.randn(*((B, 3, 224, 224) if n_img == 1 else (B, n_img, 3, 224, 224)), generator=g).pin_memory()
     d_text, d_img = h_text.to(dev), h_img.to(dev)
 
     def step_resident():
-        return model(d_text, d_img)
+        return model(d_text, d_img, **fkw)
 
     for _ in range(max(args.warmup, 3)):
         out = step_resident()
@@ -239,7 +257,7 @@ def run_gpu(args):
         t = h_text.to(dev, non_blocking=True)
         im = h_img.to(dev, non_blocking=True)
         torch.cuda.current_stream().wait_event(done[s])        # the logits slot written now was copied out (step i-2)
-        logits = model(t, im)
+        logits = model(t, im, **fkw)
         d_keep[s] = logits                                     # keep alive until its copy is done
         logits.record_stream(copy_stream)
         ready = torch.cuda.Event(); ready.record()
@@ -270,10 +288,10 @@ def run_gpu(args):
 
     # ---- instrumented step: per-kernel CUDA-event times (roofline leg), graph off
     was_graph, model.cuda_graph = model.cuda_graph, False
-    model(d_text, d_img); torch.cuda.synchronize()
+    model(d_text, d_img, **fkw); torch.cuda.synchronize()
     ops.profile_begin()
     for _ in range(2):
-        model(d_text, d_img)
+        model(d_text, d_img, **fkw)
     recs = ops.profile_end()
     model.cuda_graph = was_graph
     agg, shapes = {}, {}
@@ -297,20 +315,18 @@ def run_gpu(args):
 
     # ---- configs[1]: one decoder layer alone (B=8, T=2048)
     dec = model.decoder
-    x = torch.randn(B * SEQ, 2048, device=dev)
+    x = torch.randn(BATCH_PER_GPU * SEQ, 2048, device=dev)
     one = dec._pack()["layers"][:1]
-    dec_block_ms = _time_decoder_block(torch, dec, one, x, B)
-    flops_seq, dec_layer_flops = forward_flops_per_seq()
-    blk_tflops = dec_layer_flops * B / (dec_block_ms * 1e-3) / 1e12
+    dec_block_ms = _time_decoder_block(torch, dec, one, x, BATCH_PER_GPU)
+    flops_seq, dec_layer_flops = forward_flops_per_seq(images=n_img)
+    blk_tflops = dec_layer_flops * BATCH_PER_GPU / (dec_block_ms * 1e-3) / 1e12
 
     step_tflops = flops_seq * B / (ms_step * 1e-3) / 1e12        # per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "configs[2]: full Kosmos forward (ViT-L/14 + perceiver + 24-layer decoder + LM head), "
-                               "B=8 per GPU, seq=2048 (1984 text + 64 image latents), 1 image 224x224 per sequence, "
-                               "random-init weights, max_positions=2050",
+        "config": {"workload": wl["name"] + ", random-init weights, max_positions=2050",
                    "global_batch": B * world, "seq_len": SEQ, "parallelism": f"dp{world}",
                    "l2": "no flush needed: each step streams 3.3 GB of weights and >10 GB of activations (L2 = 126 MB)",
                    "cuda_graph": bool(args.graph)},
@@ -339,7 +355,7 @@ def run_gpu(args):
     }
     if world == 1 and rank == 0 and not args.no_cpu:
         del x
-        r = cpu_reference(1, 0)
+        r = cpu_reference(1, 0, wl=wl)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"], "ms_per_sample": r["ms_per_step"]}
     if rank == 0:
@@ -376,6 +392,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--graph", type=int, default=1, help="replay the forward as one CUDA graph (default on)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="c3 = configs[2] (the metric's "
+                    "configuration, default); c5 = configs[4], 4 images per sequence")
     args = ap.parse_args()
     if args.steps < 1:
         ap.error("--steps must be >= 1")

@@ -24,6 +24,8 @@
 extern "C" {
 #endif
 
+#define KX_ABI_VERSION 4   /* returned by kx_abi_version(); bumped on any signature change */
+
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
 enum {
@@ -36,6 +38,7 @@ enum {
 
 enum { KX_ACT_NONE = 0, KX_ACT_GELU = 1 /* erf */, KX_ACT_QUICK_GELU = 2 /* x*sigmoid(1.702x) */ };
 enum { KX_EPI_GENERIC = 0, KX_EPI_QKV_XPOS = 1 };
+#define KX_MAX_IMAGES 16   /* images spliced into one sequence (kx_embed_splice_pos) */
 
 /* ---- library ---------------------------------------------------------------------- */
 const char* kx_last_error(void);      /* thread-local text of the last failure */
@@ -137,16 +140,18 @@ int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* 
 /* ---- embedding / splice ----------------------------------------------------------- *
  * x0[b, t, :] for every NON-image row of the spliced sequence (image rows are written by the
  * image_proj GEMM epilogue): token embedding gather + learned position (index t + 2).
- * Row t of the spliced sequence holds text token t (t < img_start), image feature
- * t - img_start (img_start <= t < img_start + n_img), or text token t - n_img.
- * Replaces Decoder.forward_embedding x2 + torch.cat of model.py:238-244.
- * For KosmosLanguage (model.py:310-320) pass n_img = 0.
+ * The spliced sequence has T = t_text + img_count * n_img rows; image i occupies rows
+ * [host_img_rows[i], host_img_rows[i] + n_img) (HOST array of img_count <= KX_MAX_IMAGES ascending,
+ * non-overlapping starts) and the text tokens fill the remaining rows in order.
+ * Replaces Decoder.forward_embedding x2 + torch.cat of model.py:238-244: the reference
+ * is img_count = 1, host_img_rows = {2}; BASELINE.json configs[4] uses four images per sequence.
+ * For KosmosLanguage (model.py:310-320) pass img_count = 0.
  * Token ids outside [0, vocab) set *err_flag (device int, may be NULL) instead of faulting.
  * pos_table NULL = gather only (the `[1]` result of forward_embedding, model.py:238).
  */
 int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
-                        const float* pos_table, int pos_rows, int dim, int img_start, int n_img, float* x0,
-                        int* err_flag, kx_stream_t stream);
+                        const float* pos_table, int pos_rows, int dim, const int* host_img_rows, int img_count,
+                        int n_img, float* x0, int* err_flag, kx_stream_t stream);
 
 /* x[b,t,:] = in[b,t,:] + pos_table[t+2,:]: Decoder.forward_embedding(x, token_embedding=x)[0] of
  * model.py:242-244 as a stand-alone call (the fused path is kx_embed_splice_pos + the image_proj epilogue). */
@@ -156,8 +161,10 @@ int kx_add_positions(const float* in, float* out, int batch, int T, int dim, con
 /* CLIP patch embedding front end ([HF]:202-218): im2col of (B,3,H,W) pixels (fp32) into bf16
  * rows [B*gh*gw, k_pad] (k = c*p*p + dy*p + dx, zero padded to k_pad), and the CLS rows
  * x[b, 0, :] = class_embedding + pos[0] written into the fp32 token buffer x [B, 1+gh*gw, dim].
+ * media > 1: pixels are (B/media, media, 3, H, W) and output slot i*(B/media) + s holds image i of
+ * sequence s (media-major), so that each image index is one contiguous row block downstream.
  */
-int kx_im2col_patches(const float* pixels, int batch, int image, int patch, void* patches_bf16, int k_pad,
+int kx_im2col_patches(const float* pixels, int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
                       const float* class_embedding, const float* pos_table, float* x, int dim, kx_stream_t stream);
 
 /* Row statistics + bf16 copy of an fp32 matrix: xb = bf16(x), stats[m] = (sum, sumsq) of xb's row m

@@ -212,15 +212,21 @@ add_positions_kernel(const float* __restrict__ in, float* __restrict__ out, int 
 }
 
 // ----------------------------------------------------------------------------- embedding + splice + positions
+struct SpliceRows { int count; int start[KX_MAX_IMAGES]; };   // first spliced row of every image, ascending
 __global__ void __launch_bounds__(256)
 embed_splice_pos_kernel(const long long* __restrict__ tokens, int t_text, const float* __restrict__ embed, int vocab,
-                        const float* __restrict__ pos, int dim, int img_start, int n_img, float* __restrict__ x0,
+                        const float* __restrict__ pos, int dim, const SpliceRows img, int n_img, float* __restrict__ x0,
                         int* __restrict__ err_flag) {
-    const int T = t_text + n_img;
+    const int T = t_text + n_img * img.count;
     const int b = blockIdx.x / T;
     const int t = blockIdx.x - b * T;
-    if (t >= img_start && t < img_start + n_img) return;      // written by the image_proj GEMM epilogue
-    const int ti = (t < img_start) ? t : t - n_img;
+    int ti = t;                                               // text index = row - 64 * (images that start before it)
+    for (int i = 0; i < img.count; ++i) {
+        if (t >= img.start[i]) {
+            if (t < img.start[i] + n_img) return;             // image row: written by the image_proj GEMM epilogue
+            ti -= n_img;
+        }
+    }
     long long tok = tokens[static_cast<long long>(b) * t_text + ti];
     if (tok < 0 || tok >= vocab) {
         if (err_flag != nullptr && threadIdx.x == 0) atomicExch(err_flag, 1);
@@ -241,13 +247,15 @@ embed_splice_pos_kernel(const long long* __restrict__ tokens, int t_text, const 
 
 // ----------------------------------------------------------------------------- CLIP patch im2col + CLS rows
 __global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ pixels, int batch, int image, int patch, __nv_bfloat16* __restrict__ patches,
+im2col_kernel(const float* __restrict__ pixels, int batch, int media, int image, int patch, __nv_bfloat16* __restrict__ patches,
               int k_pad, const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x, int dim) {
     const int g = image / patch;
     const int n_patch_rows = batch * g * g;
     if (blockIdx.x < n_patch_rows) {
-        const int b = blockIdx.x / (g * g);
-        const int pi = blockIdx.x - b * g * g;
+        const int slot = blockIdx.x / (g * g);                // output image slot, media-major: slot = i * (batch/media) + seq
+        const int pi = blockIdx.x - slot * g * g;
+        const int seqs = batch / media;
+        const int b = (slot % seqs) * media + slot / seqs;    // source image: pixels are (seq, media, 3, H, W)
         const int py = pi / g, px = pi - py * g;
         const int pp = patch * patch;
         __nv_bfloat16* o = patches + static_cast<long long>(blockIdx.x) * k_pad;
@@ -369,20 +377,32 @@ extern "C" int kx_rowstats_cast(const float* x, long long ld_x, void* xb, long l
 }
 
 extern "C" int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
-                                   const float* pos_table, int pos_rows, int dim, int img_start, int n_img, float* x0,
-                                   int* err_flag, cudaStream_t stream) {
+                                   const float* pos_table, int pos_rows, int dim, const int* host_img_rows, int img_count,
+                                   int n_img, float* x0, int* err_flag, cudaStream_t stream) {
     if (!tokens || !embed_table || !x0) { set_error("kx_embed_splice_pos: null pointer"); return KX_ERR_ARG; }
-    const int T = t_text + n_img;
-    if (batch <= 0 || t_text <= 0 || n_img < 0 || (dim % 4) || img_start < 0 || img_start > t_text) {
-        set_error("kx_embed_splice_pos: bad shape (batch=%d t_text=%d n_img=%d dim=%d img_start=%d)", batch, t_text, n_img, dim, img_start);
+    if (batch <= 0 || t_text <= 0 || n_img < 0 || (dim % 4) || img_count < 0 || img_count > KX_MAX_IMAGES ||
+        (img_count > 0 && !host_img_rows)) {
+        set_error("kx_embed_splice_pos: bad shape (batch=%d t_text=%d n_img=%d dim=%d img_count=%d)", batch, t_text, n_img, dim, img_count);
         return KX_ERR_ARG;
+    }
+    const int T = t_text + n_img * img_count;
+    SpliceRows img = {};
+    img.count = img_count;
+    for (int i = 0; i < img_count; ++i) {
+        const int s = host_img_rows[i];
+        // image i sits in front of text token s - i*n_img: blocks ascend, do not overlap, stay inside the sequence
+        if (s < 0 || s + n_img > T || (i > 0 && s < host_img_rows[i - 1] + n_img)) {
+            set_error("kx_embed_splice_pos: image %d cannot start at spliced row %d (T=%d, %d rows per image)", i, s, T, n_img);
+            return KX_ERR_ARG;
+        }
+        img.start[i] = s;
     }
     if (pos_table && T + 2 > pos_rows) {
         set_error("kx_embed_splice_pos: sequence length %d needs %d position rows, table has %d", T, T + 2, pos_rows);
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    embed_splice_pos_kernel<<<batch * T, 256, 0, stream>>>(tokens, t_text, embed_table, vocab, pos_table, dim, img_start, n_img, x0, err_flag);
+    embed_splice_pos_kernel<<<batch * T, 256, 0, stream>>>(tokens, t_text, embed_table, vocab, pos_table, dim, img, n_img, x0, err_flag);
     return check_launch("kx_embed_splice_pos");
 }
 
@@ -398,17 +418,17 @@ extern "C" int kx_add_positions(const float* in, float* out, int batch, int T, i
     return check_launch("kx_add_positions");
 }
 
-extern "C" int kx_im2col_patches(const float* pixels, int batch, int image, int patch, void* patches_bf16, int k_pad,
+extern "C" int kx_im2col_patches(const float* pixels, int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
                                  const float* class_embedding, const float* pos_table, float* x, int dim,
                                  cudaStream_t stream) {
     if (!pixels || !patches_bf16 || !class_embedding || !pos_table || !x) { set_error("kx_im2col_patches: null pointer"); return KX_ERR_ARG; }
-    if (batch <= 0 || patch <= 0 || image % patch || k_pad < 3 * patch * patch || (k_pad % 8)) {
+    if (batch <= 0 || media <= 0 || batch % media || patch <= 0 || image % patch || k_pad < 3 * patch * patch || (k_pad % 8)) {
         set_error("kx_im2col_patches: bad shape (image=%d patch=%d k_pad=%d)", image, patch, k_pad);
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
     const int g = image / patch;
-    im2col_kernel<<<batch * g * g + batch, 256, 0, stream>>>(pixels, batch, image, patch,
+    im2col_kernel<<<batch * g * g + batch, 256, 0, stream>>>(pixels, batch, media, image, patch,
                                                              reinterpret_cast<__nv_bfloat16*>(patches_bf16), k_pad,
                                                              class_embedding, pos_table, x, dim);
     return check_launch("kx_im2col_patches");

@@ -56,6 +56,6 @@ const DriverApi& driver_api() {
 }  // namespace kx
 
 extern "C" const char* kx_last_error(void) { return kx::g_err; }
-extern "C" int kx_abi_version(void) { return 3; }
+extern "C" int kx_abi_version(void) { return KX_ABI_VERSION; }
 extern "C" int kx_device_check(void) { return kx::device_sm_count() > 0 ? KX_OK : KX_ERR_NO_DEVICE; }
 extern "C" unsigned long long kx_launch_count(void) { return kx::g_launches.load(); }

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("KX_LIB") or os.path.join(os.path.dirname(_HERE), "lib
 KX_OK = 0
 KX_ACT_NONE, KX_ACT_GELU, KX_ACT_QUICK_GELU = 0, 1, 2
 KX_EPI_GENERIC, KX_EPI_QKV_XPOS = 0, 1
+KX_MAX_IMAGES = 16
 
 _f32p = C.c_void_p
 _vp = C.c_void_p
@@ -53,8 +54,8 @@ SIGNATURES = {
     "kx_perceiver_xattn_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "kx_layernorm_fwd": (_i, [_vp, _i, _ll, _f32p, _i, _i, _f32p, _f32p, _f, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
     "kx_add_positions": (_i, [_f32p, _f32p, _i, _i, _i, _f32p, _i, _vp]),
-    "kx_embed_splice_pos": (_i, [_vp, _i, _i, _f32p, _i, _f32p, _i, _i, _i, _i, _f32p, _vp, _vp]),
-    "kx_im2col_patches": (_i, [_f32p, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
+    "kx_embed_splice_pos": (_i, [_vp, _i, _i, _f32p, _i, _f32p, _i, _i, C.POINTER(_i), _i, _i, _f32p, _vp, _vp]),
+    "kx_im2col_patches": (_i, [_f32p, _i, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
     "kx_xpos_tables": (_i, [_f32p, _f32p, _i, _i, _f, _f32p, _f32p, _f32p, _f32p, _vp]),
     "kx_cast_f32_to_bf16": (_i, [_f32p, _vp, _ll, _vp]),
     "kx_broadcast_rows": (_i, [_f32p, _f32p, _ll, _i, _vp]),

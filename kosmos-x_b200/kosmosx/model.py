@@ -335,7 +335,7 @@ class Decoder(nn.Module):
             _require_cuda(tokens, "tokens")
             self._check_tokens(tokens)
             embed = torch.empty(tokens.shape[0], T, self.cfg.dim, dtype=torch.float32, device=tokens.device)
-            ops.embed_splice_pos(tokens, p["embed"], None, embed, img_start=T, n_img=0)
+            ops.embed_splice_pos(tokens, p["embed"], None, embed)
         else:
             _require_cuda(token_embedding, "token_embedding")
             embed = token_embedding.to(torch.float32).contiguous()
@@ -510,8 +510,10 @@ class Kosmos(_KosmosBase):
         return self._vis_packed
 
     # ---- stages -------------------------------------------------------------------------
-    def _vit(self, images: torch.Tensor) -> torch.Tensor:
-        """CLIPVisionTransformer.forward ([HF] modeling_clip.py:667-697) -> fp32 [B*Tv, Dv] (un-normalised)."""
+    def _vit(self, images: torch.Tensor, media: int = 1) -> torch.Tensor:
+        """CLIPVisionTransformer.forward ([HF] modeling_clip.py:667-697) -> fp32 [N*Tv, Dv] (un-normalised) for the
+        N = images.shape[0] images.  media > 1: `images` is (sequences*media, 3, H, W) in (sequence, media) order and
+        the output rows are media-major (image i of every sequence is one contiguous block)."""
         cfg, vp, ws = self.cfg, self._pack_vision(), self._ws
         B = images.shape[0]
         Tv, Dv, P = cfg.vit_tokens, cfg.vit_dim, cfg.vit_tokens - 1
@@ -523,7 +525,8 @@ class Kosmos(_KosmosBase):
         qkv = ws.get("vqkv", (M, 3 * Dv), torch.bfloat16, dev)
         att = ws.get("vatt", (M, Dv), torch.bfloat16, dev)
         mid = ws.get("vmid", (M, cfg.vit_mlp), torch.bfloat16, dev)
-        ops.im2col_patches(images, patches, vp["cls"], vp["vpos"], emb.view(B, Tv, Dv), image=cfg.image, patch=cfg.patch)
+        ops.im2col_patches(images, patches, vp["cls"], vp["vpos"], emb.view(B, Tv, Dv), image=cfg.image, patch=cfg.patch,
+                           media=media)
         ops.gemm(patches, vp["w_patch"], emb, grp=(P, Tv, 1), add_tab=vp["vpos"], add_off=1)
         ops.layernorm(emb, *vp["pre_ln"], x, eps=cfg.eps)                    # fp32 out: the residual stream
         act = _abi.KX_ACT_GELU if cfg.vit_act == "gelu" else _abi.KX_ACT_QUICK_GELU
@@ -547,29 +550,34 @@ class Kosmos(_KosmosBase):
             cur = st_b
         return x
 
-    def _perceive_project(self, xv: torch.Tensor, B: int, x0: torch.Tensor, T: int, img_start: int):
-        """PerceiverResampler + image_proj (model.py:232); the projection's epilogue
-        writes rows [img_start, img_start+64) of every sequence of x0 and adds their positions."""
+    def _perceive_project(self, xv: torch.Tensor, B: int, x0: torch.Tensor, T: int, img_rows=(2,)):
+        """PerceiverResampler + image_proj (model.py:232).  xv holds m = len(img_rows) images per
+        sequence, media-major ([m*B*Tv, Dv]); the projection's epilogue writes rows [img_rows[i], img_rows[i]+64) of
+        every sequence of x0 and adds their positions."""
         cfg, vp, ws = self.cfg, self._pack_vision(), self._ws
         Tv, Dv, Lq, Hp = cfg.vit_tokens, cfg.vit_dim, cfg.p_latents, cfg.p_heads
         inner = Hp * cfg.p_dim_head
         dev = xv.device
-        lat = ws.get("plat", (B * Lq, Dv), torch.float32, dev)
-        cat = ws.get("pcat", (B * (Tv + Lq), Dv), torch.bfloat16, dev)
-        lnl = ws.get("plnl", (B * Lq, Dv), torch.bfloat16, dev)
-        q = ws.get("pq", (B * Lq, inner), torch.bfloat16, dev)
-        kv = ws.get("pkv", (B * (Tv + Lq), 2 * inner), torch.bfloat16, dev)
-        att = ws.get("patt", (B * Lq, inner), torch.bfloat16, dev)
-        mid = ws.get("pmid", (B * Lq, Dv * cfg.p_ff_mult), torch.bfloat16, dev)
-        ops.broadcast_rows(vp["latents"], lat, B)
-        mp0 = vp["media_pos"][0:1]                       # one media => only row 0 is ever added (A.2)
+        m = len(img_rows)
+        if m > cfg.p_media_embeds:
+            raise ValueError(f"{m} images per sequence but media_pos_emb has {cfg.p_media_embeds} rows")
+        N = B * m                                        # every (image, sequence) pair resamples independently (A.2)
+        lat = ws.get("plat", (N * Lq, Dv), torch.float32, dev)
+        cat = ws.get("pcat", (N * (Tv + Lq), Dv), torch.bfloat16, dev)
+        lnl = ws.get("plnl", (N * Lq, Dv), torch.bfloat16, dev)
+        q = ws.get("pq", (N * Lq, inner), torch.bfloat16, dev)
+        kv = ws.get("pkv", (N * (Tv + Lq), 2 * inner), torch.bfloat16, dev)
+        att = ws.get("patt", (N * Lq, inner), torch.bfloat16, dev)
+        mid = ws.get("pmid", (N * Lq, Dv * cfg.p_ff_mult), torch.bfloat16, dev)
+        ops.broadcast_rows(vp["latents"], lat, N)
+        mp = vp["media_pos"][0:m]                        # media_pos_emb[:m]: row i goes to image i (media-major blocks)
         for L in vp["p_layers"]:
-            ops.layernorm(xv, *L["nm"], cat, pre_add=mp0, grp=(Tv, Tv + Lq, 0))
+            ops.layernorm(xv, *L["nm"], cat, pre_add=mp, pre_add_group=Tv * B if m > 1 else 0, grp=(Tv, Tv + Lq, 0))
             ops.layernorm(lat, *L["nl"], cat, grp=(Lq, Tv + Lq, Tv))
             ops.layernorm(lat, *L["nl"], lnl)
             ops.gemm(lnl, L["w_q"], q)
             ops.gemm(cat, L["w_kv"], kv)
-            ops.perceiver_attention(q, kv, att, batch=B, heads=Hp, n_q=Lq, n_kv=Tv + Lq, v_col_off=inner,
+            ops.perceiver_attention(q, kv, att, batch=N, heads=Hp, n_q=Lq, n_kv=Tv + Lq, v_col_off=inner,
                                     scale=cfg.p_dim_head ** -0.5)
             ops.gemm(att, L["w_out"], lat, res=lat)
             ops.layernorm(lat, *L["ff_ln"], lnl)
@@ -577,19 +585,22 @@ class Kosmos(_KosmosBase):
             ops.gemm(mid, L["w_ff2"], lat, res=lat)
         ops.layernorm(lat, *vp["p_norm"], lnl)
         pos = self.decoder._pack()["pos"]
-        ops.gemm(lnl, vp["w_ip"], x0, grp=(Lq, T, img_start), add_tab=pos, add_off=img_start + 2)
+        for i, r0 in enumerate(img_rows):                # image i of all sequences: rows [i*B*64, (i+1)*B*64)
+            ops.gemm(lnl[i * B * Lq:(i + 1) * B * Lq], vp["w_ip"], x0, grp=(Lq, T, r0), add_tab=pos, add_off=r0 + 2)
 
     # ---- forward ------------------------------------------------------------------------
-    def _forward_impl(self, text_tokens: torch.Tensor, images: torch.Tensor, logits: torch.Tensor | None = None):
+    def _forward_impl(self, text_tokens: torch.Tensor, images: torch.Tensor, logits: torch.Tensor | None = None,
+                      img_rows=(2,)):
+        """images: (B*m, 3, H, W) fp32 in (sequence, image) order, m = len(img_rows)."""
         cfg = self.cfg
         B, t_text = text_tokens.shape
-        Lq = cfg.p_latents
-        T = t_text + Lq
+        Lq, m = cfg.p_latents, len(img_rows)
+        T = t_text + Lq * m
         dp = self.decoder._pack()
         x0 = self._ws.get("x0", (B * T, cfg.dim), torch.float32, text_tokens.device)
-        xv = self._vit(images)
-        self._perceive_project(xv, B, x0, T, img_start=2)
-        ops.embed_splice_pos(text_tokens, dp["embed"], dp["pos"], x0, img_start=2, n_img=Lq, err_flag=self._err_flag())
+        xv = self._vit(images, media=m)
+        self._perceive_project(xv, B, x0, T, img_rows)
+        ops.embed_splice_pos(text_tokens, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=Lq, err_flag=self._err_flag())
         return self.decoder.run_layers(x0, B, T, logits)
 
     def _err_flag(self):
@@ -599,7 +610,10 @@ class Kosmos(_KosmosBase):
             self._errf = f
         return f
 
-    def forward(self, text_tokens: torch.Tensor, images: torch.Tensor, **kwargs):
+    def forward(self, text_tokens: torch.Tensor, images: torch.Tensor, image_positions=None, **kwargs):
+        """Reference call (model.py:208-253): images (B,3,H,W), features spliced in front of text token 2.
+        Extension (BASELINE.json configs[4]): images (B,m,3,H,W) with ``image_positions`` = m ascending text-token
+        indices; image i's 64 feature rows are spliced in front of text token image_positions[i]."""
         if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):
             raise TypeError("text_tokens and images must be instances of torch.Tensor")
         cfg = self.cfg
@@ -608,18 +622,26 @@ class Kosmos(_KosmosBase):
             _require_cuda(images, "images")
             if text_tokens.dtype != torch.int64 or text_tokens.ndim != 2:
                 raise TypeError("text_tokens must be an int64 tensor of shape (B, T_text)")
-            if images.ndim != 4 or images.shape[1] != 3 or images.shape[2] != cfg.image or images.shape[3] != cfg.image:
+            if images.ndim not in (4, 5) or tuple(images.shape[-3:]) != (3, cfg.image, cfg.image):
                 raise ValueError(f"Input image size ({tuple(images.shape[1:])}) doesn't match model "
                                  f"(3, {cfg.image}, {cfg.image}).")
             if images.shape[0] != text_tokens.shape[0]:
                 raise ValueError("text_tokens and images must have the same batch size")
-            if text_tokens.shape[1] < 2:
+            m = images.shape[1] if images.ndim == 5 else 1
+            pos = [2] if image_positions is None else [int(p) for p in image_positions]
+            if len(pos) != m or m < 1 or m > _abi.KX_MAX_IMAGES:
+                raise ValueError(f"{m} images per sequence need {m} image_positions (at most {_abi.KX_MAX_IMAGES}), got {pos}")
+            if sorted(pos) != pos or pos[0] < 0 or pos[-1] > text_tokens.shape[1]:
+                raise ValueError(f"image_positions {pos} must be ascending text-token indices in [0, {text_tokens.shape[1]}]")
+            if image_positions is None and text_tokens.shape[1] < 2:
                 raise ValueError("text_tokens needs at least 2 tokens (image features are spliced after token 1)")
-            T = text_tokens.shape[1] + cfg.p_latents
+            img_rows = tuple(p + i * cfg.p_latents for i, p in enumerate(pos))     # first spliced row of each image
+            T = text_tokens.shape[1] + cfg.p_latents * m
             if T + 2 > cfg.max_positions:
                 raise ValueError(f"spliced sequence length {T} exceeds the positional table: max is "
                                  f"{cfg.max_positions - 2} (construct Kosmos(max_positions=...) to extend it)")
-            images = images.to(torch.float32).contiguous()     # HF casts pixels to the weight dtype ([HF]:208-209)
+            # HF casts pixels to the weight dtype ([HF]:208-209)
+            images = images.to(torch.float32).reshape(-1, 3, cfg.image, cfg.image).contiguous()
             text_tokens = text_tokens.contiguous()
         except Exception as e:
             log.error(f"Failed during input validation: {e}")
@@ -627,9 +649,9 @@ class Kosmos(_KosmosBase):
         try:
             B = text_tokens.shape[0]
             if self.cuda_graph:
-                logits = self._forward_graphed(text_tokens, images)
+                logits = self._forward_graphed(text_tokens, images, img_rows)
             else:
-                logits = self._forward_impl(text_tokens, images)
+                logits = self._forward_impl(text_tokens, images, img_rows=img_rows)
             return logits.view(B, T, cfg.vocab)
         except Exception as e:
             log.error(f"Failed during model forward pass: {e}")
@@ -642,25 +664,25 @@ class Kosmos(_KosmosBase):
             raise ValueError(f"token id out of range [0, {self.cfg.vocab})")
 
     # ---- CUDA graph replay ----------------------------------------------------------------
-    def _forward_graphed(self, text_tokens, images):
+    def _forward_graphed(self, text_tokens, images, img_rows=(2,)):
         """One captured graph per input shape and per output slot.  Two output slots alternate, so the
         logits returned by a call stay valid until the second-next call with the same shapes (lets a
         caller overlap a device->host copy of the result with the next forward)."""
-        key = (tuple(text_tokens.shape), tuple(images.shape))
+        key = (tuple(text_tokens.shape), tuple(images.shape), tuple(img_rows))
         g = self._graphs.get(key)
         if g is None:
             st_tok, st_img = text_tokens.clone(), images.clone()
             B, t_text = text_tokens.shape
-            M = B * (t_text + self.cfg.p_latents)
+            M = B * (t_text + self.cfg.p_latents * len(img_rows))
             outs = [torch.empty(M, self.cfg.vocab, dtype=torch.float32, device=text_tokens.device) for _ in range(2)]
-            self._forward_impl(st_tok, st_img, outs[0])           # warm-up: stages weights, allocates workspaces
+            self._forward_impl(st_tok, st_img, outs[0], img_rows)   # warm-up: stages weights, allocates workspaces
             torch.cuda.synchronize()
             graphs = []
             for o in outs:
                 graph = torch.cuda.CUDAGraph()
                 n0 = ops.launch_count()
                 with torch.cuda.graph(graph):
-                    self._forward_impl(st_tok, st_img, o)
+                    self._forward_impl(st_tok, st_img, o, img_rows)
                 nodes = ops.launch_count() - n0
                 graphs.append(graph)
             g = [graphs, st_tok, st_img, outs, 0, nodes]
@@ -711,7 +733,7 @@ class KosmosLanguage(_KosmosBase):
             raise ValueError(f"sequence length {T} exceeds the positional table: max is {self.cfg.max_positions - 2}")
         dp = self.decoder._pack()
         x0 = self._ws.get("x0", (B * T, self.cfg.dim), torch.float32, x.device)
-        ops.embed_splice_pos(x.contiguous(), dp["embed"], dp["pos"], x0, img_start=T, n_img=0)
+        ops.embed_splice_pos(x.contiguous(), dp["embed"], dp["pos"], x0)
         return self.decoder.run_layers(x0, B, T).view(B, T, self.cfg.vocab)
 
 

@@ -191,15 +191,18 @@ def rowstats_cast(x, xb, stats):
     return xb
 
 
-def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_start, n_img, err_flag=None):
+def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_rows=(), n_img=0, err_flag=None):
+    """Text rows of the spliced sequence: gather + position.  img_rows = first spliced row of every image
+    (ascending; the reference is (2,)); each image takes n_img rows, written by the image_proj GEMM."""
     _req(tokens, torch.int64, "tokens")
     B, t_text = tokens.shape
     if not tokens.is_contiguous():
         tokens = tokens.contiguous()
+    rows = (_abi.C.c_int * max(1, len(img_rows)))(*[int(r) for r in img_rows])
     with _Timed("embed_splice_pos", 0.0, 12.0 * B * t_text * embed_table.shape[1]):
         check(lib.kx_embed_splice_pos(tokens.data_ptr(), B, t_text, embed_table.data_ptr(), embed_table.shape[0],
                                       _ptr(pos_table), 0 if pos_table is None else pos_table.shape[0],
-                                      embed_table.shape[1], img_start, n_img,
+                                      embed_table.shape[1], rows, len(img_rows), n_img,
                                       x0.data_ptr(), _ptr(err_flag), _stream()), "kx_embed_splice_pos")
     return x0
 
@@ -211,10 +214,11 @@ def add_positions(x_in, x_out, pos_table):
     return x_out
 
 
-def im2col_patches(pixels, patches, class_embedding, pos_table, x, *, image, patch):
+def im2col_patches(pixels, patches, class_embedding, pos_table, x, *, image, patch, media=1):
+    """pixels fp32 (N,3,H,W), N = sequences*media in (sequence, media) order; output slots are media-major."""
     _req(pixels, torch.float32, "pixels")
     with _Timed("im2col", 0.0, 6.0 * pixels.numel()):
-        check(lib.kx_im2col_patches(pixels.data_ptr(), pixels.shape[0], image, patch, patches.data_ptr(),
+        check(lib.kx_im2col_patches(pixels.data_ptr(), pixels.shape[0], media, image, patch, patches.data_ptr(),
                                     patches.shape[1], class_embedding.data_ptr(), pos_table.data_ptr(), x.data_ptr(),
                                     x.shape[-1], _stream()), "kx_im2col_patches")
     return patches

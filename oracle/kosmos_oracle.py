@@ -516,15 +516,21 @@ class KosmosOracle(nn.Module):
     def set_emulation(self, on: bool):
         self.emu.on = on
 
-    def _image_rows(self, images):
+    def _image_rows(self, images, keep=None):
         """ViT -> perceiver -> image_proj: (B,3,H,W) -> (B,1,64,dim); (B,m,3,H,W) -> (B,m,64,dim)."""
+        feats = self._resample(images)
+        if keep is not None:
+            keep["perceive"] = feats.squeeze(1) if images.ndim == 4 else feats
+        return F.linear(self.emu.r(feats), self.emu.r(self.image_proj.weight)) # model.py:232
+
+    def _resample(self, images):
         if images.ndim == 5:                                                   # config 5: m images per sequence
             B, m = images.shape[:2]
             feats = self.clip_model(pixel_values=images.flatten(0, 1))         # model.py:230 per image
             feats = self.perceive(feats.view(B, m, *feats.shape[1:]))          # (B, m, 64, Dv): media index = image index (A.2)
         else:
             feats = self.perceive(self.clip_model(pixel_values=images))        # model.py:230-231 (B, 1, 64, Dv)
-        return F.linear(self.emu.r(feats), self.emu.r(self.image_proj.weight)) # model.py:232
+        return feats
 
     @staticmethod
     def splice(embed, rows, image_positions):
@@ -560,7 +566,7 @@ class KosmosOracle(nn.Module):
         out = {}
         flat = images.flatten(0, 1) if images.ndim == 5 else images
         out["vit"] = self.clip_model(pixel_values=flat)
-        rows = self._image_rows(images)
+        rows = self._image_rows(images, keep=out)
         out["image_proj"] = rows.squeeze(1) if images.ndim == 4 else rows
         emb = self.decoder.forward_embedding(text_tokens)[1]
         x = self.splice(emb, rows, image_positions)

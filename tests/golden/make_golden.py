@@ -36,5 +36,27 @@ def main():
     print("wrote", os.path.join(HERE, "tiny_golden.pt"), {k: tuple(v["logits"].shape) for k, v in cases.items()})
 
 
+def multi_image():
+    """BASELINE.json configs[4] in small: m images per sequence spliced in front of given text tokens
+    (oracle extension of model.py:239-241) -> tiny_golden_multi.pt."""
+    torch.set_num_threads(4)
+    cfg = ko.OracleConfig.tiny(max_positions=512)         # 4 images x 64 rows + text needs more than tiny's 256 positions
+    model = ko.build(cfg, seed=0)
+    cases = {}
+    for name, (B, t_text, pos) in {"m4": (2, 30, [2, 9, 9, 30]), "m2_edges": (3, 5, [0, 5]), "m3": (1, 60, [1, 20, 41])}.items():
+        text, images = ko.make_inputs(cfg, B, t_text, seed=7, n_images=len(pos))
+        st = model.stages(text, images, pos)
+        model.set_emulation(True)
+        emu = model(text, images, image_positions=pos)
+        model.set_emulation(False)
+        cases[name] = dict(B=B, t_text=t_text, positions=pos, col_step=8, x0=st["x0"][:, ::2].half(),
+                           logits=st["logits"][..., ::8].clone(), logits_emu_bf16=emu[..., ::8].clone())
+    torch.save(dict(cfg=cfg.__dict__, seed_weights=0, seed_inputs=7, cases=cases), os.path.join(HERE, "tiny_golden_multi.pt"))
+    print("wrote tiny_golden_multi.pt", {k: tuple(v["logits"].shape) for k, v in cases.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "multi" in sys.argv[1:]:
+        multi_image()
+    else:
+        main()

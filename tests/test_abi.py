@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in kosmosx_b200.h but not exported"
     assert set(names) == set(_abi.SIGNATURES), "ctypes SIGNATURES and header disagree"
-    assert _abi.lib.kx_abi_version() == 3
+    assert _abi.lib.kx_abi_version() == int(re.search(r"#define KX_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
 
 
 def test_gemm_args_struct_matches_header():

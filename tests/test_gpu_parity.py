@@ -103,14 +103,76 @@ def test_tiny_stages_match_golden(tiny_pair, golden):
         st = ref.stages(text, images)
     dp = mine.decoder._pack()
     x0 = torch.empty(B * T, oc.dim, device="cuda")
-    mine._perceive_project(xv.view(-1, oc.vit_dim), B, x0, T, img_start=2)
+    mine._perceive_project(xv.view(-1, oc.vit_dim), B, x0, T, img_rows=(2,))
     from kosmosx import ops
-    ops.embed_splice_pos(text.cuda(), dp["embed"], dp["pos"], x0, img_start=2, n_img=oc.p_latents)
+    ops.embed_splice_pos(text.cuda(), dp["embed"], dp["pos"], x0, img_rows=(2,), n_img=oc.p_latents)
     x0 = x0.view(B, T, oc.dim)
     assert _err(x0[:, :2], st["x0"][:, :2])[0] <= 1e-6            # text rows: exact gather + fp32 add
     assert _err(x0[:, 66:], st["x0"][:, 66:])[0] <= 1e-6
     assert _err(x0[:, 2:66], st["x0"][:, 2:66])[0] <= 5e-2         # image rows through ViT+perceiver (bf16 operands)
     assert _err(x0[:, ::2], g["x0"])[0] <= 5e-2
+
+
+@pytest.fixture(scope="module")
+def tiny512_pair():
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, KosmosConfig
+    oc = ko.OracleConfig.tiny(max_positions=512)
+    ref = ko.build(oc, seed=0)
+    mine = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
+    mine.load_state_dict(ref.state_dict())
+    return ref, mine.cuda(), oc
+
+
+@pytest.mark.parametrize("name", ["m4", "m2_edges", "m3"])
+def test_tiny_multi_image_splice(tiny512_pair, name):
+    """BASELINE.json configs[4] shape in small: m images per sequence, each resampled with its own
+    media_pos_emb row and spliced in front of text token positions[i] (also: adjacent images, an image at the
+    very start / very end of the text).  Decoder input rows exact for text, bf16-tolerance for image rows;
+    logits against the golden fixture and the live bf16-emulating oracle; CUDA-graph replay identical."""
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, ops
+    ref, mine, oc = tiny512_pair
+    g = torch.load(os.path.join(HERE, "golden", "tiny_golden_multi.pt"), weights_only=False)["cases"][name]
+    B, t_text, positions = g["B"], g["t_text"], g["positions"]
+    m = len(positions)
+    text, images = ko.make_inputs(oc, B, t_text, seed=7, n_images=m)
+    with torch.no_grad():
+        st = ref.stages(text, images, positions)
+        ref.set_emulation(True)
+        want = ref(text, images, image_positions=positions)
+        ref.set_emulation(False)
+    got = mine(text.cuda(), images.cuda(), image_positions=positions).clone()
+    torch.cuda.synchronize()
+    T = t_text + m * oc.p_latents
+    assert got.shape == (B, T, oc.vocab)
+    # the front end alone (the decoder updates the fp32 residual stream in place)
+    xv = mine._vit(images.cuda().float().reshape(-1, 3, oc.image, oc.image), media=m)
+    rows = tuple(p + i * oc.p_latents for i, p in enumerate(positions))
+    x0 = torch.zeros(B * T, oc.dim, device="cuda")
+    mine._perceive_project(xv, B, x0, T, rows)
+    dp = mine.decoder._pack()
+    ops.embed_splice_pos(text.cuda(), dp["embed"], dp["pos"], x0, img_rows=rows, n_img=oc.p_latents)
+    x0 = x0.view(B, T, oc.dim).cpu()
+    is_img = torch.zeros(T, dtype=torch.bool)
+    for r in rows:
+        is_img[r:r + oc.p_latents] = True
+    assert _err(x0[:, ~is_img], st["x0"][:, ~is_img])[0] <= 1e-6
+    assert _err(x0[:, is_img], st["x0"][:, is_img])[0] <= 5e-2
+    assert _err(x0[:, ::2], g["x0"])[0] <= 5e-2
+    e = _err(got, want)
+    eg = _err(got[..., ::g["col_step"]], g["logits_emu_bf16"])
+    print(f"multi-image {name} m={m} at {positions}: vs bf16-emulating oracle max={e[0]:.3e} rms={e[1]:.3e}; golden max={eg[0]:.3e}")
+    assert e[0] <= TOL_EMU_TINY and e[1] <= RMS_EMU_TINY and eg[0] <= TOL_EMU_TINY
+    assert _err(got[..., ::g["col_step"]], g["logits"])[0] <= TOL_F32_TINY
+    graphed = Kosmos(config=mine.cfg, cuda_graph=True)
+    graphed.load_state_dict(ref.state_dict())
+    graphed = graphed.cuda()
+    g1 = graphed(text.cuda(), images.cuda(), image_positions=positions).clone()
+    g2 = graphed(text.cuda(), images.cuda(), image_positions=positions).clone()
+    assert torch.equal(g1, got) and torch.equal(g2, got)
+    with pytest.raises(ValueError, match="image_positions"):
+        mine(text.cuda(), images.cuda(), image_positions=positions[:-1])
 
 
 def test_tiny_properties(tiny_pair):

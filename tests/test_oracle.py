@@ -216,3 +216,77 @@ def test_oracle_matches_golden(tiny):
         with torch.no_grad():
             y = model(text, images)
         assert (y[..., ::c["col_step"]] - c["logits"]).abs().max() < 2e-4, name
+
+
+# --------------------------------------------------------------------------- multi-image splice (configs[4])
+GOLDEN_MULTI = os.path.join(os.path.dirname(__file__), "golden", "tiny_golden_multi.pt")
+
+
+@pytest.fixture(scope="module")
+def tiny512():
+    torch.set_num_threads(4)
+    cfg = ko.OracleConfig.tiny(max_positions=512)
+    return cfg, ko.build(cfg, seed=0)
+
+
+def test_multi_image_default_is_the_reference_splice(tiny):
+    """image_positions=None / [2] and a (B,1,3,H,W) image tensor are all the reference call (model.py:239-241)."""
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 2, 12)
+    with torch.no_grad():
+        a = model(text, images)
+        b = model(text, images, image_positions=[2])
+        c = model(text, images[:, None], image_positions=[2])
+    assert torch.equal(a, b) and torch.allclose(a, c, atol=1e-6)
+
+
+def test_multi_image_rows_and_media_positions(tiny512):
+    """Image i occupies 64 rows in front of text token positions[i]; it is resampled with media_pos_emb[i]
+    (flamingo indexes the table by media index); text rows keep their order."""
+    cfg, model = tiny512
+    pos = [2, 9, 9, 30]
+    text, images = ko.make_inputs(cfg, 2, 30, seed=7, n_images=4)
+    with torch.no_grad():
+        st = model.stages(text, images, pos)
+        assert st["logits"].shape == (2, 30 + 4 * 64, cfg.vocab)
+        rows = [p + 64 * i for i, p in enumerate(pos)]
+        for i in range(4):                                   # perturb one image: exactly its 64 rows of x0 move
+            im2 = images.clone()
+            im2[:, i] *= 0.5
+            moved = (model.stages(text, im2, pos)["x0"] - st["x0"]).abs().amax(-1)[0] > 0
+            want = torch.zeros_like(moved)
+            want[rows[i]:rows[i] + 64] = True
+            assert torch.equal(moved, want), i
+        # text rows: embedding + position t+2 in spliced coordinates
+        emb = model.embed(text)
+        is_img = torch.zeros(st["x0"].shape[1], dtype=torch.bool)
+        for r in rows:
+            is_img[r:r + 64] = True
+        T = is_img.numel()
+        want_text = emb + model.embed_positions.weight[2:T + 2][~is_img]
+        assert torch.allclose(st["x0"][:, ~is_img], want_text, atol=1e-6)
+        # the same picture at media index 0 and 1 gives different rows (media_pos_emb[0] vs [1]) ...
+        same = images[:, :1].expand(-1, 2, -1, -1, -1).contiguous()
+        r = model._image_rows(same)
+        assert (r[:, 0] - r[:, 1]).abs().max() > 1e-3
+        # ... and equal rows once the two table rows are made equal
+        saved = model.perceive.media_pos_emb.data.clone()
+        model.perceive.media_pos_emb.data[1] = saved[0]
+        r = model._image_rows(same)
+        model.perceive.media_pos_emb.data.copy_(saved)
+        assert torch.allclose(r[:, 0], r[:, 1], atol=1e-5)
+    with pytest.raises(ValueError):
+        model(text, images, image_positions=[2, 9])
+    with pytest.raises(ValueError):
+        model(text, images, image_positions=[9, 2, 9, 30])
+
+
+def test_oracle_matches_multi_image_golden(tiny512):
+    cfg, model = tiny512
+    g = torch.load(GOLDEN_MULTI)
+    assert g["cfg"] == cfg.__dict__
+    for name, c in g["cases"].items():
+        text, images = ko.make_inputs(cfg, c["B"], c["t_text"], seed=g["seed_inputs"], n_images=len(c["positions"]))
+        with torch.no_grad():
+            y = model(text, images, image_positions=c["positions"])
+        assert (y[..., ::c["col_step"]] - c["logits"]).abs().max() < 2e-4, name

@@ -330,11 +330,21 @@ def case_embed():
     tok = torch.randint(0, V, (B, t_text), device=dev)
     emb = torch.randn(V, D, device=dev); pos = torch.randn(T + 2, D, device=dev)
     x0 = torch.zeros(B, T, D, device=dev)
-    ops.embed_splice_pos(tok, emb, pos, x0, img_start=2, n_img=n_img)
+    ops.embed_splice_pos(tok, emb, pos, x0, img_rows=(2,), n_img=n_img)
     e = emb[tok]
     ref = torch.cat([e[:, :2], torch.zeros(B, n_img, D, device=dev), e[:, 2:]], 1) + pos[2:T + 2]
     ref[:, 2:2 + n_img] = 0
     ok &= report("embed_splice_pos", x0.view(B * T, D), ref.view(B * T, D), 1e-6)
+    # three images: in front of text tokens 0, 7, 7 (adjacent) -> spliced rows 0, 71, 135
+    T3 = t_text + 3 * n_img
+    pos3 = torch.randn(T3 + 2, D, device=dev)
+    x3 = torch.zeros(B, T3, D, device=dev)
+    ops.embed_splice_pos(tok, emb, pos3, x3, img_rows=(0, 7 + n_img, 7 + 2 * n_img), n_img=n_img)
+    z = torch.zeros(B, n_img, D, device=dev)
+    ref3 = torch.cat([z, e[:, :7], z, z, e[:, 7:]], 1) + pos3[2:T3 + 2]
+    ref3[:, :n_img] = 0
+    ref3[:, 7 + n_img:7 + 3 * n_img] = 0
+    ok &= report("embed_splice_pos 3 images", x3.view(B * T3, D), ref3.view(B * T3, D), 1e-6)
     # im2col
     Bi, image, patch, dim = 2, 56, 14, 128
     px = torch.randn(Bi, 3, image, image, device=dev)
@@ -348,6 +358,14 @@ def case_embed():
     ok &= report("im2col", patches[:, :588], ref.bfloat16(), 0.0)
     ok &= report("im2col pad", patches[:, 588:], torch.zeros(Bi * g * g, kp - 588, device=dev), 0.0)
     ok &= report("cls rows", x[:, 0], (cls + p2[0]).expand(Bi, dim), 1e-6)
+    # media-major slots: pixels (2 sequences, 3 images) -> slot i*2 + s
+    px = torch.randn(6, 3, image, image, device=dev)
+    patches = torch.zeros(6 * g * g, kp, device=dev, dtype=torch.bfloat16)
+    x = torch.zeros(6, g * g + 1, dim, device=dev)
+    ops.im2col_patches(px, patches, cls, p2, x, image=image, patch=patch, media=3)
+    pm = px.view(2, 3, 3, image, image).transpose(0, 1).reshape(6, 3, image, image)
+    ref = torch.nn.functional.unfold(pm, patch, stride=patch).transpose(1, 2).reshape(6 * g * g, 3 * patch * patch)
+    ok &= report("im2col media-major", patches[:, :588], ref.bfloat16(), 0.0)
     # cast / broadcast
     s = torch.randn(1000003, device=dev)
     ok &= report("cast bf16", ops.cast_bf16(s).view(1, -1), s.bfloat16().view(1, -1), 0.0)
