@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 4   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 6   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -92,6 +92,12 @@ typedef struct kx_gemm_args {
     float* stats_out;
     void* out2;
     long long ld_out2;
+    /* operands given transposed in memory (the backward GEMMs read activations / weights where they lie):
+     *   a_trans: A points at a [K, M] row-major matrix (lda >= M);  b_trans: W points at a [K, N] row-major matrix.
+     *   dgrad  dX[M,Kd] = dY[M,N] . W[N,Kd]      -> A = dY, W = the forward weight with b_trans = 1
+     *   wgrad  dW[N,Kd] = dY[M,N]^T . X[M,Kd]    -> A = dY with a_trans = 1, W = X with b_trans = 1
+     * (replaces autograd's mm_backward of every F.linear on the path).  Generic epilogue only. */
+    int a_trans, b_trans;
 } kx_gemm_args;
 
 int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const kx_gemm_args* args,
@@ -184,6 +190,83 @@ int kx_xpos_tables(const float* scale, const float* inv_freq, int T, int min_pos
  * perceiver latents over the batch (A.2: latents.expand). */
 int kx_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, kx_stream_t stream);
 int kx_broadcast_rows(const float* src, float* dst, long long row_elems, int copies, kx_stream_t stream);
+
+/* ==================================================================================== *
+ * Training step (BASELINE.json configs[3]): forward -> cross-entropy over the text rows
+ * -> backward -> gradient clipping -> AdamW / Lion.  The reference reaches these through autograd
+ * (train.py:647-648 `loss = model(...)`, `accelerator.backward(loss)`), torch.nn.utils.clip_grad_norm_
+ * (train.py:652-653) and torch.optim.AdamW / lion_pytorch.Lion (train.py:375-386).  The backward GEMMs are
+ * kx_gemm_bf16 with a_trans / b_trans.
+ * ==================================================================================== */
+
+/* Attention backward (flash, head_dim 64, tcgen05): dq, dk, dv from d(out), q, k, v, out and the row log-sum-exp
+ * written by kx_attn_fwd_lse (fp32 [heads][batch][ceil(seq_len/128)*128], log2 units).  Same layout rules as
+ * kx_attn_fwd; dq/dk/dv are column blocks sharing ld_dqkv.  When the four xPos tables (kx_xpos_tables) are given,
+ * dq and dk are returned as gradients of the UN-rotated projections (the transpose of the KX_EPI_QKV_XPOS rotation is
+ * applied on the way out); NULL tables = plain attention.  Scratch: dq_accum fp32 [batch*seq_len, heads*64] (zeroed
+ * by the call) and delta fp32 (same shape as lse).  Three kernels: delta = rowsum(dO*O), the main kernel (one CTA
+ * per (batch, head, 128-key block)), and the dq/dk finish.  Replaces autograd through bmm / softmax / bmm and
+ * XPOS.forward of torchscale MultiheadAttention. */
+int kx_attn_fwd_lse(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
+                    int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, kx_stream_t stream);
+int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
+                const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv, long long ld_dqkv,
+                float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin, const float* xk_cos,
+                const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale, kx_stream_t stream);
+
+/* out = LayerNorm(act(x)) * gamma + beta in one pass, bf16 in / bf16 out (ffn_layernorm(gelu(fc1 x)), SURVEY A.4:
+ * training keeps the pre-activation u, so GELU and the LayerNorm share one read of it).  n % 8 == 0, n <= 8192. */
+int kx_act_layernorm_fwd(const void* x_bf16, long long ld_x, int act, const float* gamma, const float* beta, float eps,
+                         void* out_bf16, long long ld_out, int rows, int n, kx_stream_t stream);
+
+/* nn.LayerNorm backward for y = LN(act(x)) * gamma + beta, given dy (bf16):
+ *   dx = act'(x) * rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; d_gamma (+)= sum dy*xhat; d_beta (+)= sum dy.
+ * dx_is_f32 = 1: dx is the fp32 residual-stream gradient, dx = dres + (LN gradient) (dres NULL = none; may alias dx),
+ * dxb (NULL or bf16) receives a copy and d_colsum (NULL or fp32 [n]) the column sums of dx — the bias gradient of the
+ * Linear whose output was added to the stream there.  dx_is_f32 = 0: dx is bf16 (dres/dxb must be NULL), d_colsum sums
+ * the stored bf16 values.  partials: fp32 scratch [3][kx_ln_bwd_partials(rows)][n].  accumulate = 1 adds into d_*. */
+int kx_ln_bwd_partials(int rows);
+int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, int act, const void* dy_bf16, long long ld_dy,
+                     const float* gamma, float eps, const float* dres, long long ld_dres, void* dx, int dx_is_f32,
+                     long long ld_dx, void* dxb_bf16, long long ld_dxb, float* partials, int n_partials, float* d_gamma,
+                     float* d_beta, float* d_colsum, int accumulate, int rows, int n, kx_stream_t stream);
+
+/* out[n] += column sums of a bf16 matrix (bias gradients: d(bias) = sum over rows of dY). */
+int kx_colsum_bf16(const void* x_bf16, long long ld, int rows, int n, float* out, kx_stream_t stream);
+
+/* Transpose of the xPos rotation (kx_gemm_args KX_EPI_QKV_XPOS) applied in place to the q and k column blocks
+ * [0, 2*d_model) of a bf16 [rows, ld] gradient matrix; tables from kx_xpos_tables. */
+int kx_xpos_bwd(void* dqkv_bf16, long long ld, int rows, int d_model, int seq_len, const float* q_cos, const float* q_sin,
+                const float* k_cos, const float* k_sin, kx_stream_t stream);
+
+/* Softmax cross-entropy over the text rows of the spliced sequence (same splice description as kx_embed_splice_pos):
+ * the row holding text token i predicts text token i+1; image rows, the last text token and the token directly in
+ * front of an image carry no loss (the reference's intended loss, experimental/model/allModalities/notes.txt:566-574,
+ * keeps row 0 and the rows after the image block).  loss_acc[0] += sum of row losses, loss_acc[1] += rows counted.
+ * dlogits (NULL = loss only): bf16 [batch*T, ld_dlogits], (softmax - onehot) * inv_count, zeros elsewhere
+ * (including the pad columns [vocab, ld_dlogits), so the matrix can feed kx_gemm_bf16 directly). */
+int kx_ce_fwd_bwd(const float* logits, long long ld_logits, const long long* tokens, int batch, int t_text,
+                  const int* host_img_rows, int img_count, int n_img, int vocab, float inv_count, void* dlogits_bf16,
+                  long long ld_dlogits, float* loss_acc, int* err_flag, kx_stream_t stream);
+
+/* Backward of kx_embed_splice_pos: d_embed[token] += dx0[row] for text rows (not for padding_idx), d_pos[t + 2] +=
+ * dx0[row] for every row.  NULL tables are skipped. */
+int kx_embed_bwd(const float* dx0, const long long* tokens, int batch, int t_text, const int* host_img_rows, int img_count,
+                 int n_img, int dim, int vocab, int padding_idx, float* d_embed, float* d_pos, kx_stream_t stream);
+
+/* Gradient clipping (clip_grad_norm_, train.py:652-653) without a host sync: *out += sum g^2; then
+ * scale = pre_scale * min(1, max_norm / (pre_scale * sqrt(sumsq) + 1e-6)), norm_out = pre_scale * sqrt(sumsq)
+ * (pre_scale = 1 / world size turns all-reduced gradient sums into means; max_norm <= 0 = no clipping). */
+int kx_sumsq(const float* g, long long n, float* out, kx_stream_t stream);
+int kx_clip_scale(const float* sumsq, float max_norm, float pre_scale, float* scale_out, float* norm_out, kx_stream_t stream);
+
+/* Fused optimizers over flat fp32 buffers (master weights, gradients, moments); *grad_scale (device, may be NULL)
+ * multiplies every gradient; w_bf16 (may be NULL) receives the bf16 tensor-core copy of the updated weights.
+ * kx_adamw_step = torch.optim.AdamW (step >= 1 for the bias corrections); kx_lion_step = lion_pytorch.Lion. */
+int kx_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, const float* grad_scale, kx_stream_t stream);
+int kx_lion_step(float* p, const float* g, float* m, void* w_bf16, long long n, float lr, float beta1, float beta2,
+                 float weight_decay, const float* grad_scale, kx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -282,7 +282,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 namespace kx {
 int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
-                   int heads, int seq_len, int causal, float scale, float* stats_out, cudaStream_t stream);   // attention_pp.cu
+                   int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, cudaStream_t stream);   // attention_pp.cu
 // KX_ATTN_IMPL=0 selects the first-generation kernel of this file (kept for A/B measurements).
 static int attn_impl() {
     static int impl = -1;
@@ -296,9 +296,27 @@ static int attn_impl() {
 
 using namespace kx;
 
+static int attn_fwd_impl(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
+                         int batch, int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out,
+                         cudaStream_t stream);
+
 extern "C" int kx_attn_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
                            int batch, int heads, int seq_len, int causal, float scale, float* stats_out,
                            cudaStream_t stream) {
+    return attn_fwd_impl(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stats_out, nullptr, stream);
+}
+
+// Training forward: also writes the row log-sum-exp (log2 units, [heads][batch][ceil(T/128)*128] fp32) for kx_attn_bwd.
+extern "C" int kx_attn_fwd_lse(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
+                               int batch, int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out,
+                               cudaStream_t stream) {
+    if (!lse_out || (reinterpret_cast<uintptr_t>(lse_out) & 15)) { set_error("kx_attn_fwd_lse: lse_out must be a 16-byte aligned buffer"); return KX_ERR_ARG; }
+    return attn_fwd_impl(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stats_out, lse_out, stream);
+}
+
+static int attn_fwd_impl(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,
+                         int batch, int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out,
+                         cudaStream_t stream) {
     if (!q || !k || !v || !out) { set_error("kx_attn_fwd: null pointer"); return KX_ERR_ARG; }
     if (batch <= 0 || heads <= 0 || seq_len <= 0) { set_error("kx_attn_fwd: bad shape"); return KX_ERR_ARG; }
     if ((ld_qkv % 8) || (ld_out % 8) || ((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) || ((uintptr_t)out & 15)) {
@@ -307,8 +325,8 @@ extern "C" int kx_attn_fwd(const void* q, const void* k, const void* v, long lon
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
     if (stats_out && (reinterpret_cast<uintptr_t>(stats_out) & 7)) { set_error("kx_attn_fwd: stats_out must be 8-byte aligned"); return KX_ERR_ARG; }
-    if (attn_impl() == 1) return launch_attn_pp(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stats_out, stream);
-    if (stats_out) { set_error("kx_attn_fwd: stats_out is only produced by the default kernel (unset KX_ATTN_IMPL)"); return KX_ERR_ARG; }
+    if (attn_impl() == 1) return launch_attn_pp(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stats_out, lse_out, stream);
+    if (stats_out || lse_out) { set_error("kx_attn_fwd: stats_out is only produced by the default kernel (unset KX_ATTN_IMPL)"); return KX_ERR_ARG; }
     const unsigned long long rows = (unsigned long long)batch * seq_len;
     CUtensorMap tq, tk, tv;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * AT_D, rows, ld_qkv * 2, AT_D, AT_BM)) return KX_ERR_TMAP;

@@ -44,6 +44,8 @@ struct AttnPPParams {
     float scale_log2;                                // scale * log2(e)
     float2* stats_out;                               // [heads][batch*seq_len] partial (sum, sumsq) of the stored row, or null
     long long total_rows;
+    float* lse_out;                                  // [heads][batch][t_pad] row log-sum-exp in log2 units (training), or null
+    int t_pad;
     long long* trace;                                // TRACE builds only: clock64 stamps of CTA (0,0), [4 roles][64 iters][8 points]
 };
 
@@ -415,6 +417,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
             }
             if (p.stats_out != nullptr) p.stats_out[static_cast<long long>(head) * p.total_rows + row_base + qrow] = make_float2(s1, s2);
+            if (p.lse_out != nullptr)              // log2(sum_k 2^(s_k * scale * log2e)): what kx_attn_bwd rebuilds P from
+                p.lse_out[(static_cast<long long>(head) * p.batch + it.b) * p.t_pad + qrow] = fmaf(m_ref, sl2, log2f(l_run));
         }
         cum += nblk;
         }   // items
@@ -427,7 +431,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
-                   int heads, int seq_len, int causal, float scale, float* stats_out, cudaStream_t stream) {
+                   int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, cudaStream_t stream) {
     const unsigned long long rows = (unsigned long long)batch * seq_len;
     CUtensorMap tq, tk, tv;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
@@ -443,6 +447,8 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.scale_log2 = scale * 1.4426950408889634f;
     p.stats_out = reinterpret_cast<float2*>(stats_out);
     p.total_rows = static_cast<long long>(rows);
+    p.lse_out = lse_out;
+    p.t_pad = (seq_len + 127) / 128 * 128;
     p.trace = g_attn_trace;
     static bool attr_set = false;
     static bool poly = true;            // KX_ATTN_POLY=0 keeps every exp2 on the MUFU (A/B measurements)

@@ -305,7 +305,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t
     }
 }
 
-template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI>
+// ATR / BTR: the operand is given TRANSPOSED in memory — A as [K, M] row-major, W as [K, N] row-major — i.e. its
+// MN dimension is the contiguous one.  The tile is then staged as 64-column atoms ([64 k-rows][128 B], SWIZZLE_128B,
+// one TMA box each) and fed to tcgen05.mma as an MN-major operand (instruction-descriptor major bits; descriptor
+// LBO = 8 KB between MN atoms, SBO = 1 KB between 8-row k groups; a UMMA_K step advances 16 rows = 2 KB).
+// This is how the backward GEMMs read their operands where they lie: dgrad dX = dY . W (W as [K', N']) and
+// wgrad dW = dY^T . X (both operands [K', *]) need no transposed copies.
+constexpr int MN_ATOM_BYTES = 64 * 128;
+
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -387,15 +395,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int n0 = n_blk * BN + rank * Cfg::B_ROWS;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* sa = smem_a + s * Cfg::A_BYTES;
+                uint8_t* sb = smem_b + s * Cfg::B_BYTES;
                 if constexpr (CG == 1) {
                     mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                    tma_load_2d(&tmA, &full[s], smem_a + s * Cfg::A_BYTES, kb * BLOCK_K, m0);
-                    tma_load_2d(&tmB, &full[s], smem_b + s * Cfg::B_BYTES, kb * BLOCK_K, n0);
+                    if constexpr (!ATR) tma_load_2d(&tmA, &full[s], sa, kb * BLOCK_K, m0);
+                    else
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(&tmA, &full[s], sa + c * MN_ATOM_BYTES, m0 + c * 64, kb * BLOCK_K);
+                    if constexpr (!BTR) tma_load_2d(&tmB, &full[s], sb, kb * BLOCK_K, n0);
+                    else
+#pragma unroll
+                        for (int c = 0; c < Cfg::B_ROWS / 64; ++c) tma_load_2d(&tmB, &full[s], sb + c * MN_ATOM_BYTES, n0 + c * 64, kb * BLOCK_K);
                 } else {
                     if (leader) mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES * 2);
                     else mbar_arrive_cluster(&full[s], 0);
-                    tma_load_2d_cg2(&tmA, &full[s], smem_a + s * Cfg::A_BYTES, kb * BLOCK_K, m0);
-                    tma_load_2d_cg2(&tmB, &full[s], smem_b + s * Cfg::B_BYTES, kb * BLOCK_K, n0);
+                    if constexpr (!ATR) tma_load_2d_cg2(&tmA, &full[s], sa, kb * BLOCK_K, m0);
+                    else
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d_cg2(&tmA, &full[s], sa + c * MN_ATOM_BYTES, m0 + c * 64, kb * BLOCK_K);
+                    if constexpr (!BTR) tma_load_2d_cg2(&tmB, &full[s], sb, kb * BLOCK_K, n0);
+                    else
+#pragma unroll
+                        for (int c = 0; c < Cfg::B_ROWS / 64; ++c) tma_load_2d_cg2(&tmB, &full[s], sb + c * MN_ATOM_BYTES, n0 + c * 64, kb * BLOCK_K);
                 }
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
@@ -404,7 +426,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         if (leader && elect_one()) {
         // ================= MMA issuer (leader CTA only) =================
-        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BN);
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BN, ATR ? 1u : 0u, BTR ? 1u : 0u);
+        constexpr uint32_t a_step = ATR ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;     // descriptor address units of 16 B
+        constexpr uint32_t b_step = BTR ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
         int s = 0;
         uint32_t ph = 0;
         int it = 0;
@@ -417,11 +441,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint64_t adesc = make_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES));
-                const uint64_t bdesc = make_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES));
+                const uint64_t adesc = make_desc_sw128(smem_u32(smem_a + s * Cfg::A_BYTES), ATR ? MN_ATOM_BYTES : 0);
+                const uint64_t bdesc = make_desc_sw128(smem_u32(smem_b + s * Cfg::B_BYTES), BTR ? MN_ATOM_BYTES : 0);
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                    umma_bf16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_bf16<CG>(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
                 if constexpr (CG == 1) umma_commit(&empty[s]); else umma_commit_cg2(&empty[s], 0b11);
                 if (kb == num_kb - 1) {
                     if constexpr (CG == 1) umma_commit(&tfull[a]); else umma_commit_cg2(&tfull[a], 0b11);
@@ -693,13 +717,15 @@ bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_
     return make_tmap_2d(tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer);
 }
 
-template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI>
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmEpi& ep, int max_ctas,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<CG, BN, TMA_EPI>;
     CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
-    if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP;
-    if (!make_tmap_2d(&tmB, W, ep.K, ep.N, ldw * 2, BLOCK_K, Cfg::B_ROWS)) return KX_ERR_TMAP;
+    if constexpr (!ATR) { if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP; }
+    else { if (!make_tmap_2d(&tmA, A, ep.M, ep.K, lda * 2, 64, BLOCK_K)) return KX_ERR_TMAP; }       // A given as [K, M]
+    if constexpr (!BTR) { if (!make_tmap_2d(&tmB, W, ep.K, ep.N, ldw * 2, BLOCK_K, Cfg::B_ROWS)) return KX_ERR_TMAP; }
+    else { if (!make_tmap_2d(&tmB, W, ep.N, ep.K, ldw * 2, 64, BLOCK_K)) return KX_ERR_TMAP; }       // W given as [K, N]
     if constexpr (TMA_EPI) {
         if (!ep.tma_store) {
             tmOut = tmA;                       // unused: the staged epilogue writes with coalesced float2 stores
@@ -724,7 +750,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
         tmRes = tmA;
         tmOut2 = tmA;
     }
-    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI>;
+    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI, ATR, BTR>;
     static bool attr_set = false;   // per template instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -836,6 +862,24 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     if ((g->stats_out || g->out2) && !ep.tma_store) {
         set_error("kx_gemm_bf16: stats_out / out2 need the staged epilogue (unscattered, 16-byte aligned rows, epi_mode 0)");
         return KX_ERR_ARG;
+    }
+    if (g->a_trans || g->b_trans) {
+        // backward GEMMs: dgrad (W transposed) and wgrad (both transposed); staged epilogue only
+        if (g->a_trans && !g->b_trans) { set_error("kx_gemm_bf16: a_trans without b_trans is not built"); return KX_ERR_ARG; }
+        if (g->epi != KX_EPI_GENERIC || !tma_epi || !ep.tma_store) {
+            set_error("kx_gemm_bf16: transposed operands need the generic staged epilogue (16-byte aligned, unscattered output)");
+            return KX_ERR_ARG;
+        }
+        const bool big = (cg == 2 && bn == 256);
+        if (!big) { cg = 1; bn = 128; }
+#define KX_GEMM_TR(CG_, BN_, ATR_)                                                                                                  \
+        {                                                                                                                           \
+            if (g->out_f32) return launch_gemm<CG_, BN_, true, KX_EPI_GENERIC, true, ATR_, true>(A, lda, W, ldw, ep, max_ctas, stream); \
+            return launch_gemm<CG_, BN_, false, KX_EPI_GENERIC, true, ATR_, true>(A, lda, W, ldw, ep, max_ctas, stream);               \
+        }
+        if (big) { if (g->a_trans) KX_GEMM_TR(2, 256, true) else KX_GEMM_TR(2, 256, false) }
+        else { if (g->a_trans) KX_GEMM_TR(1, 128, true) else KX_GEMM_TR(1, 128, false) }
+#undef KX_GEMM_TR
     }
 #define KX_GEMM_CASE2(CG_, BN_, T_)                                                                          \
     {                                                                                                        \

@@ -1,0 +1,692 @@
+// HBM-bound kernels of the training step (fwd -> CE over text positions -> bwd -> grad clip
+// -> AdamW/Lion).  They replace what autograd + torch.optim do around the reference's modules:
+//   kx_act_layernorm_fwd   ffn_layernorm(gelu(u)) as one pass (training keeps u, the pre-activation)
+//   kx_layernorm_bwd       nn.LayerNorm backward (+ GELU backward, + residual-gradient add, + bf16 copy), with
+//                          per-CTA partial d(gamma), d(beta) and column sums, folded by kx_colpartials_reduce
+//   kx_colsum_bf16         bias gradients
+//   kx_xpos_bwd            transpose of the xPos rotation on dq / dk
+//   kx_ce_fwd_bwd          softmax cross-entropy over the text rows of the spliced sequence, d(logits) in bf16
+//   kx_embed_bwd           scatter-add of d(x0) into the token-embedding and position tables
+//   kx_sumsq / kx_clip_scale / kx_adamw_step / kx_lion_step   gradient-norm clipping and the fused optimizers
+// Everything is fp32 math on 16-byte vector accesses; one pass over each operand.
+#include "kx_internal.h"
+#include "ptx.cuh"
+
+namespace kx {
+
+constexpr int ROW_THREADS = 256;
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float2 f = __bfloat1622float2(h[u]);
+        v[2 * u] = f.x; v[2 * u + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = q;
+}
+
+// sum of (a, b) over the 256 threads of the CTA, result broadcast to every thread.  `red` is 2 x 8 floats of smem;
+// two alternating halves would be needed for back-to-back calls, so every call is followed by a __syncthreads().
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[w] = a; red[8 + w] = b; }
+    __syncthreads();
+    a = 0.f; b = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_THREADS / 32; ++i) { a += red[i]; b += red[8 + i]; }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ----------------------------------------------------------------------------- LN(gelu(u)) forward
+// out = LayerNorm(act(x)) * gamma + beta, x bf16, out bf16.  NCH chunks of 8 columns per thread (n <= NCH * 2048).
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS)
+act_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, int act, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out, long long ld_out,
+                         int rows, int n) {
+    __shared__ float red[16];
+    const float inv_n = 1.0f / static_cast<float>(n);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        float v[NCH][8];
+        float s = 0.f, dummy = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            if (col < n) {
+                load8(x + row * ld_x + col, v[c]);
+                if (act == KX_ACT_GELU)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[c][u] = gelu_exact(v[c][u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[c][u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[c][u] = 0.f;
+            }
+        }
+        block_sum2(s, dummy, red);
+        const float mean = s * inv_n;
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            if (col < n)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const float d = v[c][u] - mean; q = fmaf(d, d, q); }
+        }
+        dummy = 0.f;
+        block_sum2(q, dummy, red);
+        const float rstd = rsqrtf(q * inv_n + eps);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            if (col < n) {
+                float g[8], b[8], o[8];
+                load8(gamma + col, g);
+                load8(beta + col, b);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o[u] = fmaf((v[c][u] - mean) * rstd, g[u], b[u]);
+                store8(out + row * ld_out + col, o);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- LayerNorm backward
+// y = LN(a) * gamma + beta with a = act(x).  Given dy (bf16):
+//   g = dy * gamma;  da = rstd * (g - mean(g) - xhat * mean(g * xhat));  dx = da * act'(x)
+//   d(gamma) += dy * xhat, d(beta) += dy  (per-CTA partials [grid][n], folded by colpartials_reduce_kernel)
+// DX_F32: dx is the fp32 residual-stream gradient: dx_out = dres + dx (dres may alias dx_out), an optional bf16 copy
+// dxb of dx_out is written (the A operand of the next backward GEMMs) and column sums of dx_out are accumulated as a
+// third partial (the bias gradient of the Linear whose output was added to the stream at this point).
+template <typename XT, bool DX_F32, int NCH>
+__global__ void __launch_bounds__(ROW_THREADS)
+layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, int act, const __nv_bfloat16* __restrict__ dy,
+                     long long ld_dy, const float* __restrict__ gamma, float eps, const float* dres, long long ld_dres,
+                     void* dx_out, long long ld_dx, __nv_bfloat16* __restrict__ dxb, long long ld_dxb,
+                     float* __restrict__ part_gamma, float* __restrict__ part_beta, float* __restrict__ part_col,
+                     int rows, int n) {
+    __shared__ float red[16];
+    const float inv_n = 1.0f / static_cast<float>(n);
+    float acc_g[NCH][8], acc_b[NCH][8], acc_c[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc_g[c][u] = 0.f; acc_b[c][u] = 0.f; acc_c[c][u] = 0.f; }
+
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        float a[NCH][8], d[NCH][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            if (col < n) {
+                load8(x + row * ld_x + col, a[c]);
+                load8(dy + row * ld_dy + col, d[c]);
+                if (act == KX_ACT_GELU)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[c][u] = gelu_exact(a[c][u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s1 += a[c][u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a[c][u] = 0.f; d[c][u] = 0.f; }
+            }
+        }
+        block_sum2(s1, s2, red);
+        const float mean = s1 * inv_n;
+        float q = 0.f, z = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            if (col < n)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a[c][u] -= mean; q = fmaf(a[c][u], a[c][u], q); }
+        }
+        block_sum2(q, z, red);
+        const float rstd = rsqrtf(q * inv_n + eps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            if (col < n) {
+                float gm[8];
+                load8(gamma + col, gm);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float xh = a[c][u] * rstd;
+                    a[c][u] = xh;                                   // keep xhat
+                    acc_g[c][u] = fmaf(d[c][u], xh, acc_g[c][u]);
+                    acc_b[c][u] += d[c][u];
+                    const float g = d[c][u] * gm[u];
+                    d[c][u] = g;                                    // keep g = dy * gamma
+                    sg += g;
+                    sgx = fmaf(g, xh, sgx);
+                }
+            }
+        }
+        block_sum2(sg, sgx, red);
+        const float mg = sg * inv_n, mgx = sgx * inv_n;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            if (col < n) {
+                float o[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o[u] = rstd * (d[c][u] - mg - a[c][u] * mgx);
+                if (act == KX_ACT_GELU) {
+                    float xr[8];
+                    load8(x + row * ld_x + col, xr);                 // re-read (L1/L2 hit): keeps register pressure flat
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) o[u] *= gelu_grad(xr[u]);
+                }
+                if constexpr (DX_F32) {
+                    if (dres != nullptr) {
+                        float r[8];
+                        load8(dres + row * ld_dres + col, r);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) o[u] += r[u];
+                    }
+                    store8(reinterpret_cast<float*>(dx_out) + row * ld_dx + col, o);
+                    if (dxb != nullptr) store8(dxb + row * ld_dxb + col, o);
+                    if (part_col != nullptr)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc_c[c][u] += o[u];
+                } else {
+                    store8(reinterpret_cast<__nv_bfloat16*>(dx_out) + row * ld_dx + col, o);
+                    if (part_col != nullptr) {
+                        // column sums of what the next GEMM reads: the bf16-rounded values
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc_c[c][u] += __bfloat162float(__float2bfloat16_rn(o[u]));
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+        if (col < n) {
+            const long long o = static_cast<long long>(blockIdx.x) * n + col;
+            store8(part_gamma + o, acc_g[c]);
+            store8(part_beta + o, acc_b[c]);
+            if (part_col != nullptr) store8(part_col + o, acc_c[c]);
+        }
+    }
+}
+
+// out[col] (+)= sum_p part[p][col]
+__global__ void __launch_bounds__(256)
+colpartials_reduce_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ out, int accumulate) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 3 < parts; p += 4) {
+        s0 += part[static_cast<long long>(p) * n + col];
+        s1 += part[static_cast<long long>(p + 1) * n + col];
+        s2 += part[static_cast<long long>(p + 2) * n + col];
+        s3 += part[static_cast<long long>(p + 3) * n + col];
+    }
+    for (; p < parts; ++p) s0 += part[static_cast<long long>(p) * n + col];
+    const float s = (s0 + s1) + (s2 + s3);
+    out[col] = accumulate ? out[col] + s : s;
+}
+
+// ----------------------------------------------------------------------------- column sums (bias gradients)
+// out[n] += sum_m x[m][n], x bf16.  Grid (ceil(N/256), row splits); a warp reads 64 consecutive columns of a row
+// (128 B), the four warp-columns of the CTA cover 256 columns, two row phases per CTA.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows, int n, float* __restrict__ out) {
+    __shared__ float red[2][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * 256 + (w & 3) * 64 + lane * 2;
+    const int phase = w >> 2;
+    const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+    float a0 = 0.f, a1 = 0.f;
+    if (col < n) {
+        for (int r = r0 + phase; r < r1; r += 2) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + static_cast<long long>(r) * ld + col));
+            a0 += f.x; a1 += f.y;
+        }
+    }
+    const int slot = (w & 3) * 64 + lane * 2;
+    red[phase][slot] = a0; red[phase][slot + 1] = a1;
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < n) atomicAdd(out + c, red[0][threadIdx.x] + red[1][threadIdx.x]);
+}
+
+// ----------------------------------------------------------------------------- xPos backward
+// Forward (GEMM epilogue): o0 = x0*c - x1*s, o1 = x1*c + x0*s on column pairs of q (upscale tables) and k
+// (downscale tables).  Backward: dx0 = d0*c + d1*s, dx1 = d1*c - d0*s, in place on the q|k column blocks.
+__global__ void __launch_bounds__(256)
+xpos_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, long long ld, int rows, int d_model, int seq_len,
+                const float* __restrict__ q_cos, const float* __restrict__ q_sin, const float* __restrict__ k_cos,
+                const float* __restrict__ k_sin) {
+    const int vec_per_row = (2 * d_model) >> 3;
+    const long long total = static_cast<long long>(rows) * vec_per_row;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int row = static_cast<int>(i / vec_per_row);
+        const int col = static_cast<int>(i - static_cast<long long>(row) * vec_per_row) * 8;
+        const int t = row % seq_len;
+        const bool is_k = col >= d_model;
+        const int j0 = (col & 63) >> 1;
+        const float4 c = __ldg(reinterpret_cast<const float4*>((is_k ? k_cos : q_cos) + t * 32 + j0));
+        const float4 s = __ldg(reinterpret_cast<const float4*>((is_k ? k_sin : q_sin) + t * 32 + j0));
+        __nv_bfloat16* p = dqkv + static_cast<long long>(row) * ld + col;
+        float v[8];
+        load8(p, v);
+        const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            o[2 * u] = v[2 * u] * cc[u] + v[2 * u + 1] * ss[u];
+            o[2 * u + 1] = v[2 * u + 1] * cc[u] - v[2 * u] * ss[u];
+        }
+        store8(p, o);
+    }
+}
+
+// ----------------------------------------------------------------------------- cross-entropy over text rows
+struct SpliceRowsT { int count; int start[KX_MAX_IMAGES]; };
+
+// Row t of the spliced sequence predicts text token ti+1 when it holds text token ti, ti+1 exists and row t+1 is not
+// an image row (the reference's intended loss keeps text positions only and drops the token in front of the image,
+// notes.txt:566-574).  Returns the target id, or -1 for "no loss at this row".
+__device__ __forceinline__ long long ce_target(const long long* __restrict__ tokens, int b, int t, int t_text, int n_img,
+                                               const SpliceRowsT& img) {
+    int ti = t;
+    bool next_is_img = false;
+    for (int i = 0; i < img.count; ++i) {
+        if (t >= img.start[i]) {
+            if (t < img.start[i] + n_img) return -1;
+            ti -= n_img;
+        }
+        if (t + 1 == img.start[i]) next_is_img = true;
+    }
+    if (next_is_img || ti + 1 >= t_text) return -1;
+    return tokens[static_cast<long long>(b) * t_text + ti + 1];
+}
+
+// One CTA per row.  Pass 1: online (max, sum exp) over the fp32 logits; pass 2 (L2-resident re-read): d(logits) =
+// (softmax - onehot) * inv_count as bf16, zero for rows without a target and for the pad columns [vocab, ld_d).
+// loss_acc[0] += sum of row losses, loss_acc[1] += number of rows with a target.
+__global__ void __launch_bounds__(256)
+ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld_l, const long long* __restrict__ tokens, int t_text,
+                  int n_img, const SpliceRowsT img, int vocab, float inv_count, __nv_bfloat16* __restrict__ dlogits,
+                  long long ld_d, float* __restrict__ loss_acc, int* __restrict__ err_flag) {
+    __shared__ float red[16];
+    const int T = t_text + n_img * img.count;
+    const int row = blockIdx.x;
+    const int b = row / T, t = row - b * T;
+    long long tgt = ce_target(tokens, b, t, t_text, n_img, img);
+    if (tgt >= vocab || tgt < -1) {
+        if (err_flag != nullptr && threadIdx.x == 0) atomicExch(err_flag, 1);
+        tgt = -1;
+    }
+    __nv_bfloat16* drow = dlogits != nullptr ? dlogits + static_cast<long long>(row) * ld_d : nullptr;
+    if (tgt < 0) {
+        if (drow != nullptr)
+            for (int c = threadIdx.x * 8; c < ld_d; c += 256 * 8) *reinterpret_cast<uint4*>(drow + c) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const float* lrow = logits + static_cast<long long>(row) * ld_l;
+    float m = -INFINITY, s = 0.f;
+    for (int c = threadIdx.x * 2; c < vocab; c += 512) {          // rows are 8-byte aligned (ld even): float2 loads
+        const float2 v = *reinterpret_cast<const float2*>(lrow + c);
+        const float hi = (c + 1 < vocab) ? v.y : -INFINITY;
+        const float nm = fmaxf(m, fmaxf(v.x, hi));
+        s = s * __expf(m - nm) + __expf(v.x - nm) + __expf(hi - nm);
+        m = nm;
+    }
+    // combine (m, s) pairs: first the max, then the rescaled sums
+    float gm = m, dummy = 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gm;
+    __syncthreads();
+    gm = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) gm = fmaxf(gm, red[i]);
+    __syncthreads();
+    float ss = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+    block_sum2(ss, dummy, red);
+    const float lse = gm + logf(ss);
+    if (threadIdx.x == 0) {
+        atomicAdd(loss_acc, lse - lrow[tgt]);
+        atomicAdd(loss_acc + 1, 1.0f);
+    }
+    if (drow == nullptr) return;
+    for (int c = threadIdx.x * 8; c < ld_d; c += 256 * 8) {
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            float2 v = make_float2(0.f, 0.f);
+            if (c + u < vocab) v = *reinterpret_cast<const float2*>(lrow + c + u);
+            o[u] = (c + u < vocab) ? (__expf(v.x - lse) - ((c + u) == tgt ? 1.f : 0.f)) * inv_count : 0.f;
+            o[u + 1] = (c + u + 1 < vocab) ? (__expf(v.y - lse) - ((c + u + 1) == tgt ? 1.f : 0.f)) * inv_count : 0.f;
+        }
+        store8(drow + c, o);
+    }
+}
+
+// ----------------------------------------------------------------------------- embedding backward
+// d(embed)[token] += dx0[row], d(pos)[t + 2] += dx0[row] for every row (image rows take part in the position sum only;
+// their dx0 is also the gradient of the image_proj output).  The padding row (index padding_idx) gets no gradient,
+// as nn.Embedding(padding_idx=...).  fp32 vector atomics.
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ tokens, int t_text, int n_img,
+                 const SpliceRowsT img, int dim, int vocab, int padding_idx, float* __restrict__ d_embed,
+                 float* __restrict__ d_pos) {
+    const int T = t_text + n_img * img.count;
+    const int b = blockIdx.x / T, t = blockIdx.x - b * T;
+    int ti = t;
+    bool is_img = false;
+    for (int i = 0; i < img.count; ++i) {
+        if (t >= img.start[i]) {
+            if (t < img.start[i] + n_img) is_img = true;
+            ti -= n_img;
+        }
+    }
+    const float4* src = reinterpret_cast<const float4*>(dx0 + static_cast<long long>(blockIdx.x) * dim);
+    float4* pos = d_pos != nullptr ? reinterpret_cast<float4*>(d_pos + static_cast<long long>(t + 2) * dim) : nullptr;
+    float4* emb = nullptr;
+    if (!is_img && d_embed != nullptr) {
+        const long long tok = tokens[static_cast<long long>(b) * t_text + ti];
+        if (tok >= 0 && tok < vocab && tok != padding_idx) emb = reinterpret_cast<float4*>(d_embed + tok * dim);
+    }
+    for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
+        const float4 v = src[i];
+        if (pos != nullptr) atomicAdd(pos + i, v);
+        if (emb != nullptr) atomicAdd(emb + i, v);
+    }
+}
+
+// ----------------------------------------------------------------------------- gradient norm + optimizers
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+    __shared__ float red[16];
+    float s = 0.f, dummy = 0.f;
+    const long long nv = n >> 2;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(g)[i];
+        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = nv << 2; i < n; ++i) s = fmaf(g[i], g[i], s);
+    block_sum2(s, dummy, red);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// scale = min(1, max_norm / (sqrt(sumsq * pre_scale^2) + 1e-6)) * pre_scale   (torch.nn.utils.clip_grad_norm_;
+// pre_scale = 1/world averages all-reduced gradient sums); norm_out = the unclipped norm
+__global__ void clip_scale_kernel(const float* __restrict__ sumsq, float max_norm, float pre_scale, float* __restrict__ scale,
+                                  float* __restrict__ norm_out) {
+    const float norm = sqrtf(*sumsq) * pre_scale;
+    if (norm_out != nullptr) *norm_out = norm;
+    float c = 1.0f;
+    if (max_norm > 0.f) c = fminf(1.0f, max_norm / (norm + 1e-6f));
+    *scale = c * pre_scale;
+}
+
+// torch.optim.AdamW (decoupled weight decay), fp32 master weights and moments; writes the bf16 operand copy.
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ wb, long long n, float lr, float b1, float b2, float eps, float wd, float bc1,
+             float bc2, const float* __restrict__ gscale) {
+    const float gs = gscale != nullptr ? *gscale : 1.0f;
+    const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * gs;
+        float pi = p[i];
+        pi *= 1.0f - lr * wd;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        pi -= step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+        p[i] = pi;
+        if (wb != nullptr) wb[i] = __float2bfloat16_rn(pi);
+    }
+}
+
+// lion_pytorch.Lion (train.py:375-379): p *= 1 - lr*wd; p -= lr * sign(b1*m + (1-b1)*g); m = b2*m + (1-b2)*g
+__global__ void __launch_bounds__(256)
+lion_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, __nv_bfloat16* __restrict__ wb,
+            long long n, float lr, float b1, float b2, float wd, const float* __restrict__ gscale) {
+    const float gs = gscale != nullptr ? *gscale : 1.0f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gi = g[i] * gs, mi = m[i];
+        float pi = p[i] * (1.0f - lr * wd);
+        const float u = b1 * mi + (1.0f - b1) * gi;
+        pi -= lr * ((u > 0.f) ? 1.0f : (u < 0.f ? -1.0f : 0.0f));
+        m[i] = b2 * mi + (1.0f - b2) * gi;
+        p[i] = pi;
+        if (wb != nullptr) wb[i] = __float2bfloat16_rn(pi);
+    }
+}
+
+static int grid_for(long long n, int sms, int per_thread = 1) {
+    const long long blocks = (n / per_thread + 255) / 256;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(blocks, static_cast<long long>(sms) * 8)));
+}
+
+static bool fill_splice(SpliceRowsT& img, const int* host_img_rows, int img_count, int n_img, int T, const char* who) {
+    if (img_count < 0 || img_count > KX_MAX_IMAGES || (img_count > 0 && !host_img_rows)) {
+        set_error("%s: bad img_count %d", who, img_count);
+        return false;
+    }
+    img.count = img_count;
+    for (int i = 0; i < img_count; ++i) {
+        const int s = host_img_rows[i];
+        if (s < 0 || s + n_img > T || (i > 0 && s < host_img_rows[i - 1] + n_img)) {
+            set_error("%s: image %d cannot start at spliced row %d (T=%d, %d rows per image)", who, i, s, T, n_img);
+            return false;
+        }
+        img.start[i] = s;
+    }
+    return true;
+}
+
+}  // namespace kx
+
+using namespace kx;
+
+#define KX_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int kx_ln_bwd_partials(int rows) {
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    return std::max(1, std::min(rows, sms * 2));
+}
+
+extern "C" int kx_act_layernorm_fwd(const void* x_bf16, long long ld_x, int act, const float* gamma, const float* beta,
+                                    float eps, void* out_bf16, long long ld_out, int rows, int n, cudaStream_t stream) {
+    if (!x_bf16 || !gamma || !beta || !out_bf16 || rows <= 0 || n <= 0 || (n % 8) || n > 8192 || (ld_x % 8) || (ld_out % 8) ||
+        !KX_ALIGNED16(x_bf16) || !KX_ALIGNED16(out_bf16) || !KX_ALIGNED16(gamma) || !KX_ALIGNED16(beta) ||
+        (act != KX_ACT_NONE && act != KX_ACT_GELU)) {
+        set_error("kx_act_layernorm_fwd: bad argument (rows=%d n=%d: n %% 8 == 0, n <= 8192, 16-byte aligned rows)", rows, n);
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const int grid = std::min(rows, sms * 8);
+    auto xp = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
+    auto op = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+    if (n <= 2048) act_layernorm_fwd_kernel<1><<<grid, ROW_THREADS, 0, stream>>>(xp, ld_x, act, gamma, beta, eps, op, ld_out, rows, n);
+    else if (n <= 4096) act_layernorm_fwd_kernel<2><<<grid, ROW_THREADS, 0, stream>>>(xp, ld_x, act, gamma, beta, eps, op, ld_out, rows, n);
+    else act_layernorm_fwd_kernel<4><<<grid, ROW_THREADS, 0, stream>>>(xp, ld_x, act, gamma, beta, eps, op, ld_out, rows, n);
+    return check_launch("kx_act_layernorm_fwd");
+}
+
+extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, int act, const void* dy_bf16, long long ld_dy,
+                                const float* gamma, float eps, const float* dres, long long ld_dres, void* dx,
+                                int dx_is_f32, long long ld_dx, void* dxb_bf16, long long ld_dxb, float* partials,
+                                int n_partials, float* d_gamma, float* d_beta, float* d_colsum, int accumulate, int rows,
+                                int n, cudaStream_t stream) {
+    if (!x || !dy_bf16 || !gamma || !dx || !partials || !d_gamma || !d_beta || rows <= 0 || n <= 0 || (n % 8) || n > 8192 ||
+        (ld_x % 8) || (ld_dy % 8) || (ld_dx % 8) || !KX_ALIGNED16(x) || !KX_ALIGNED16(dy_bf16) || !KX_ALIGNED16(dx) ||
+        !KX_ALIGNED16(gamma) || !KX_ALIGNED16(partials) || (dres && (!KX_ALIGNED16(dres) || (ld_dres % 4) || !dx_is_f32)) ||
+        (dxb_bf16 && (!KX_ALIGNED16(dxb_bf16) || (ld_dxb % 8) || !dx_is_f32)) || (act != KX_ACT_NONE && act != KX_ACT_GELU)) {
+        set_error("kx_layernorm_bwd: bad argument (rows=%d n=%d; n %% 8 == 0, n <= 8192, 16-byte aligned rows; dres / dxb need fp32 dx)", rows, n);
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const int grid = std::max(1, std::min(rows, sms * 2));
+    if (n_partials < grid) { set_error("kx_layernorm_bwd: partials buffer holds %d rows, needs kx_ln_bwd_partials(rows) = %d", n_partials, grid); return KX_ERR_ARG; }
+    float* pg = partials;
+    float* pb = partials + static_cast<long long>(grid) * n;
+    float* pc = d_colsum ? partials + 2ll * grid * n : nullptr;
+    auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
+    auto dxbp = reinterpret_cast<__nv_bfloat16*>(dxb_bf16);
+#define KX_LNB(XT, F32, NCH)                                                                                              \
+    layernorm_bwd_kernel<XT, F32, NCH><<<grid, ROW_THREADS, 0, stream>>>(reinterpret_cast<const XT*>(x), ld_x, act, dyp, ld_dy, \
+        gamma, eps, dres, ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n)
+#define KX_LNB_N(XT, F32)                                                                                                 \
+    { if (n <= 2048) KX_LNB(XT, F32, 1); else if (n <= 4096) KX_LNB(XT, F32, 2); else KX_LNB(XT, F32, 4); }
+    if (x_is_bf16) { if (dx_is_f32) KX_LNB_N(__nv_bfloat16, true) else KX_LNB_N(__nv_bfloat16, false) }
+    else { if (dx_is_f32) KX_LNB_N(float, true) else KX_LNB_N(float, false) }
+#undef KX_LNB_N
+#undef KX_LNB
+    int st = check_launch("kx_layernorm_bwd");
+    if (st != KX_OK) return st;
+    const int rb = (n + 255) / 256;
+    colpartials_reduce_kernel<<<rb, 256, 0, stream>>>(pg, grid, n, d_gamma, accumulate);
+    colpartials_reduce_kernel<<<rb, 256, 0, stream>>>(pb, grid, n, d_beta, accumulate);
+    if (pc) colpartials_reduce_kernel<<<rb, 256, 0, stream>>>(pc, grid, n, d_colsum, accumulate);
+    st = check_launch("kx_layernorm_bwd (partials)");
+    if (st == KX_OK) count_launch(pc ? 2 : 1);
+    return st;
+}
+
+extern "C" int kx_colsum_bf16(const void* x_bf16, long long ld, int rows, int n, float* out, cudaStream_t stream) {
+    if (!x_bf16 || !out || rows <= 0 || n <= 0 || (n % 2) || (ld % 2) || (reinterpret_cast<uintptr_t>(x_bf16) & 3)) {
+        set_error("kx_colsum_bf16: bad argument (rows=%d n=%d)", rows, n);
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const int cb = (n + 255) / 256;
+    const int splits = std::max(1, std::min((rows + 63) / 64, (sms * 4 + cb - 1) / cb));
+    colsum_bf16_kernel<<<dim3(cb, splits), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, n, out);
+    return check_launch("kx_colsum_bf16");
+}
+
+extern "C" int kx_xpos_bwd(void* dqkv_bf16, long long ld, int rows, int d_model, int seq_len, const float* q_cos,
+                           const float* q_sin, const float* k_cos, const float* k_sin, cudaStream_t stream) {
+    if (!dqkv_bf16 || !q_cos || !q_sin || !k_cos || !k_sin || rows <= 0 || d_model <= 0 || (d_model % 64) || seq_len <= 0 ||
+        (ld % 8) || !KX_ALIGNED16(dqkv_bf16)) {
+        set_error("kx_xpos_bwd: bad argument");
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const long long total = static_cast<long long>(rows) * (2 * d_model / 8);
+    xpos_bwd_kernel<<<grid_for(total, sms), 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), ld, rows, d_model,
+                                                              seq_len, q_cos, q_sin, k_cos, k_sin);
+    return check_launch("kx_xpos_bwd");
+}
+
+extern "C" int kx_ce_fwd_bwd(const float* logits, long long ld_logits, const long long* tokens, int batch, int t_text,
+                             const int* host_img_rows, int img_count, int n_img, int vocab, float inv_count,
+                             void* dlogits_bf16, long long ld_dlogits, float* loss_acc, int* err_flag, cudaStream_t stream) {
+    if (!logits || !tokens || !loss_acc || batch <= 0 || t_text <= 0 || vocab <= 0 || n_img < 0 || (ld_logits % 2) ||
+        (reinterpret_cast<uintptr_t>(logits) & 7) ||
+        (dlogits_bf16 && ((ld_dlogits % 8) || ld_dlogits < vocab || !KX_ALIGNED16(dlogits_bf16)))) {
+        set_error("kx_ce_fwd_bwd: bad argument (logits rows 8-byte aligned; dlogits rows 16-byte aligned, ld >= vocab)");
+        return KX_ERR_ARG;
+    }
+    const int T = t_text + n_img * img_count;
+    SpliceRowsT img = {};
+    if (!fill_splice(img, host_img_rows, img_count, n_img, T, "kx_ce_fwd_bwd")) return KX_ERR_ARG;
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    ce_fwd_bwd_kernel<<<batch * T, 256, 0, stream>>>(logits, ld_logits, tokens, t_text, n_img, img, vocab, inv_count,
+                                                     reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_dlogits, loss_acc, err_flag);
+    return check_launch("kx_ce_fwd_bwd");
+}
+
+extern "C" int kx_embed_bwd(const float* dx0, const long long* tokens, int batch, int t_text, const int* host_img_rows,
+                            int img_count, int n_img, int dim, int vocab, int padding_idx, float* d_embed, float* d_pos,
+                            cudaStream_t stream) {
+    if (!dx0 || !tokens || batch <= 0 || t_text <= 0 || (dim % 4) || !KX_ALIGNED16(dx0) || (d_embed && !KX_ALIGNED16(d_embed)) ||
+        (d_pos && !KX_ALIGNED16(d_pos))) {
+        set_error("kx_embed_bwd: bad argument");
+        return KX_ERR_ARG;
+    }
+    const int T = t_text + n_img * img_count;
+    SpliceRowsT img = {};
+    if (!fill_splice(img, host_img_rows, img_count, n_img, T, "kx_embed_bwd")) return KX_ERR_ARG;
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    embed_bwd_kernel<<<batch * T, 256, 0, stream>>>(dx0, tokens, t_text, n_img, img, dim, vocab, padding_idx, d_embed, d_pos);
+    return check_launch("kx_embed_bwd");
+}
+
+extern "C" int kx_sumsq(const float* g, long long n, float* out, cudaStream_t stream) {
+    if (!g || !out || n <= 0 || !KX_ALIGNED16(g)) { set_error("kx_sumsq: bad argument"); return KX_ERR_ARG; }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    sumsq_kernel<<<grid_for(n, sms, 4), 256, 0, stream>>>(g, n, out);
+    return check_launch("kx_sumsq");
+}
+
+extern "C" int kx_clip_scale(const float* sumsq, float max_norm, float pre_scale, float* scale_out, float* norm_out,
+                             cudaStream_t stream) {
+    if (!sumsq || !scale_out) { set_error("kx_clip_scale: null pointer"); return KX_ERR_ARG; }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    clip_scale_kernel<<<1, 1, 0, stream>>>(sumsq, max_norm, pre_scale, scale_out, norm_out);
+    return check_launch("kx_clip_scale");
+}
+
+extern "C" int kx_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int step, const float* grad_scale,
+                             cudaStream_t stream) {
+    if (!p || !g || !m || !v || n <= 0 || step < 1) { set_error("kx_adamw_step: bad argument"); return KX_ERR_ARG; }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+    adamw_kernel<<<grid_for(n, sms), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, lr, beta1, beta2,
+                                                       eps, weight_decay, bc1, bc2, grad_scale);
+    return check_launch("kx_adamw_step");
+}
+
+extern "C" int kx_lion_step(float* p, const float* g, float* m, void* w_bf16, long long n, float lr, float beta1, float beta2,
+                            float weight_decay, const float* grad_scale, cudaStream_t stream) {
+    if (!p || !g || !m || n <= 0) { set_error("kx_lion_step: bad argument"); return KX_ERR_ARG; }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    lion_kernel<<<grid_for(n, sms), 256, 0, stream>>>(p, g, m, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, lr, beta1, beta2,
+                                                      weight_decay, grad_scale);
+    return check_launch("kx_lion_step");
+}

@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("cta_group", _i), ("block_n", _i), ("max_ctas", _i), ("epi_mode", _i),
         ("ln_part", _f32p), ("ln_c", _f32p), ("ln_tiles", _i), ("ln_cols", _i), ("ln_eps", _f),
         ("stats_out", _f32p), ("out2", _vp), ("ld_out2", _ll),
+        ("a_trans", _i), ("b_trans", _i),
     ]
 
 
@@ -59,6 +60,22 @@ SIGNATURES = {
     "kx_xpos_tables": (_i, [_f32p, _f32p, _i, _i, _f, _f32p, _f32p, _f32p, _f32p, _vp]),
     "kx_cast_f32_to_bf16": (_i, [_f32p, _vp, _ll, _vp]),
     "kx_broadcast_rows": (_i, [_f32p, _f32p, _ll, _i, _vp]),
+    # ---- training step
+    "kx_attn_fwd_lse": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _f32p, _vp]),
+    "kx_attn_bwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _f32p, _vp, _vp, _vp, _ll, _f32p, _f32p,
+                         _f32p, _f32p, _f32p, _f32p, _i, _i, _i, _i, _f, _vp]),
+    "kx_act_layernorm_fwd": (_i, [_vp, _ll, _i, _f32p, _f32p, _f, _vp, _ll, _i, _i, _vp]),
+    "kx_ln_bwd_partials": (_i, [_i]),
+    "kx_layernorm_bwd": (_i, [_vp, _i, _ll, _i, _vp, _ll, _f32p, _f, _f32p, _ll, _vp, _i, _ll, _vp, _ll, _f32p, _i,
+                              _f32p, _f32p, _f32p, _i, _i, _i, _vp]),
+    "kx_colsum_bf16": (_i, [_vp, _ll, _i, _i, _f32p, _vp]),
+    "kx_xpos_bwd": (_i, [_vp, _ll, _i, _i, _i, _f32p, _f32p, _f32p, _f32p, _vp]),
+    "kx_ce_fwd_bwd": (_i, [_f32p, _ll, _vp, _i, _i, C.POINTER(_i), _i, _i, _i, _f, _vp, _ll, _f32p, _vp, _vp]),
+    "kx_embed_bwd": (_i, [_f32p, _vp, _i, _i, C.POINTER(_i), _i, _i, _i, _i, _i, _f32p, _f32p, _vp]),
+    "kx_sumsq": (_i, [_f32p, _ll, _f32p, _vp]),
+    "kx_clip_scale": (_i, [_f32p, _f, _f, _f32p, _f32p, _vp]),
+    "kx_adamw_step": (_i, [_f32p, _f32p, _f32p, _f32p, _vp, _ll, _f, _f, _f, _f, _f, _i, _f32p, _vp]),
+    "kx_lion_step": (_i, [_f32p, _f32p, _f32p, _vp, _ll, _f, _f, _f, _f, _f32p, _vp]),
 }
 
 

@@ -65,8 +65,10 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=None, act=_abi.KX_ACT_NONE,
          grp=None, add_tab=None, add_off=0, xpos=None, seq_len=0, cta_group=0, block_n=0, max_ctas=0, M=None,
-         epi_mode=0, ln=None, stats_out=None, out2=None):
+         epi_mode=0, ln=None, stats_out=None, out2=None, a_trans=False, b_trans=False):
     """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; out bf16 or fp32 (2-D views, row pitch = stride(0)).
+    a_trans / b_trans: the operand is given as [K, M] / [K, N] (backward GEMMs: dgrad = gemm(dY, W, b_trans=True),
+    wgrad = gemm(dY, X, a_trans=True, b_trans=True)).
 
     ln = (partials fp32 [tiles, M, 2], c fp32 [N], cols, eps): LayerNorm of the rows of `a` folded into the
     epilogue (w must carry gamma, bias must be W.beta + b).  stats_out fp32 [ceil(N/128), M, 2] and out2
@@ -74,11 +76,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
     g = GemmArgs()
-    g.M = a.shape[0] if M is None else M
-    g.K = a.shape[1]
-    g.N = w.shape[0]
-    if w.shape[1] != g.K:
-        raise ValueError(f"gemm: K mismatch {a.shape} vs {w.shape}")
+    g.M = (a.shape[1] if a_trans else a.shape[0]) if M is None else M
+    g.K = a.shape[0] if a_trans else a.shape[1]
+    g.N = w.shape[1] if b_trans else w.shape[0]
+    if (w.shape[0] if b_trans else w.shape[1]) != g.K:
+        raise ValueError(f"gemm: K mismatch {tuple(a.shape)} vs {tuple(w.shape)} (a_trans={a_trans}, b_trans={b_trans})")
+    g.a_trans, g.b_trans = int(a_trans), int(b_trans)
     g.bias = _ptr(bias)
     g.res = _ptr(res)
     g.ld_res = res.stride(0) if res is not None else 0
@@ -123,7 +126,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     if out2 is not None:
         _req(out2, torch.bfloat16, "out2")
         g.out2, g.ld_out2 = out2.data_ptr(), out2.stride(0)
-    with _Timed(f"gemm {g.M}x{g.N}x{g.K}" + ("+ln" if ln is not None else "") + ("+xpos" if xpos is not None else "")
+    with _Timed(f"gemm {g.M}x{g.N}x{g.K}" + ("+tn" if a_trans else "+nn" if b_trans else "") + ("+ln" if ln is not None else "") + ("+xpos" if xpos is not None else "")
                 + ("+gelu" if act == _abi.KX_ACT_GELU else "") + ("+res" if res is not None else ""),
                 2.0 * g.M * g.N * g.K,
                 2.0 * (g.M + g.N) * g.K + g.M * g.N * (out.element_size() + (4 if res is not None else 0))):
@@ -131,7 +134,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     return out
 
 
-def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=None):
+def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=None, lse_out=None):
     """q, k, v: bf16 2-D views [batch*seq_len, heads*64] sharing one row pitch; out bf16 [batch*seq_len, >=heads*64].
     stats_out fp32 [heads, batch*seq_len, 2]: per-head partial (sum, sumsq) of every output row."""
     if stats_out is not None:
@@ -144,10 +147,135 @@ def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=N
         raise ValueError("attention: q, k, v must share a row pitch")
     fl = 4.0 * batch * heads * seq_len * seq_len * 64 * (0.5 if causal else 1.0)
     with _Timed("attn_causal" if causal else "attn_full", fl, 8.0 * batch * heads * seq_len * 64):
-        check(lib.kx_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
-                              batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out), _stream()),
-              "kx_attn_fwd")
+        if lse_out is not None:
+            _req(lse_out, torch.float32, "lse_out")
+            if lse_out.numel() != heads * batch * lse_pad(seq_len) or not lse_out.is_contiguous():
+                raise ValueError("attention: lse_out must be contiguous [heads, batch, ceil(seq_len/128)*128]")
+            check(lib.kx_attn_fwd_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                                      batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out),
+                                      lse_out.data_ptr(), _stream()), "kx_attn_fwd_lse")
+        else:
+            check(lib.kx_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                                  batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out), _stream()),
+                  "kx_attn_fwd")
     return out
+
+
+def lse_pad(seq_len: int) -> int:
+    return (seq_len + 127) // 128 * 128
+
+
+# ---- training step ---------------------------------------------------------------------------
+def attention_bwd(q, k, v, out, d_out, lse, dq, dk, dv, dq_accum, delta, *, batch, heads, seq_len, causal, scale, xpos=None):
+    """dq, dk, dv (bf16 column blocks sharing one pitch) from d_out; xpos = the four kx_xpos_tables undoes the rotation."""
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out), ("d_out", d_out), ("dq", dq), ("dk", dk), ("dv", dv)):
+        _req(t, torch.bfloat16, n)
+    _req(lse, torch.float32, "lse"); _req(dq_accum, torch.float32, "dq_accum"); _req(delta, torch.float32, "delta")
+    if not (q.stride(0) == k.stride(0) == v.stride(0)) or not (dq.stride(0) == dk.stride(0) == dv.stride(0)):
+        raise ValueError("attention_bwd: q/k/v and dq/dk/dv must each share a row pitch")
+    if dq_accum.numel() != batch * seq_len * heads * 64 or delta.numel() != lse.numel():
+        raise ValueError("attention_bwd: scratch buffers have the wrong size")
+    tabs = [None] * 4 if xpos is None else [t.data_ptr() for t in xpos]
+    fl = 10.0 * batch * heads * seq_len * seq_len * 64 * (0.5 if causal else 1.0)
+    with _Timed("attn_bwd", fl, 0.0):
+        check(lib.kx_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                              d_out.data_ptr(), d_out.stride(0), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                              dq.stride(0), dq_accum.data_ptr(), delta.data_ptr(), *tabs, batch, heads, seq_len,
+                              1 if causal else 0, float(scale), _stream()), "kx_attn_bwd")
+
+
+def act_layernorm(x, gamma, beta, out, *, act=_abi.KX_ACT_GELU, eps=1e-5):
+    _req(x, torch.bfloat16, "x"); _req(out, torch.bfloat16, "out")
+    with _Timed("act_layernorm", 0.0, 4.0 * x.shape[0] * x.shape[1]):
+        check(lib.kx_act_layernorm_fwd(x.data_ptr(), x.stride(0), act, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                       out.data_ptr(), out.stride(0), x.shape[0], x.shape[1], _stream()), "kx_act_layernorm_fwd")
+    return out
+
+
+def ln_bwd_partials(rows: int) -> int:
+    n = int(lib.kx_ln_bwd_partials(rows))
+    if n <= 0:
+        check(n, "kx_ln_bwd_partials")
+    return n
+
+
+def layernorm_bwd(x, dy, gamma, dx, d_gamma, d_beta, partials, *, act=_abi.KX_ACT_NONE, eps=1e-5, dres=None, dxb=None,
+                  d_colsum=None, accumulate=False):
+    """LayerNorm (+GELU) backward; see kx_layernorm_bwd.  partials: fp32 [3, ln_bwd_partials(rows), n]."""
+    _req(dy, torch.bfloat16, "dy")
+    rows, n = x.shape
+    if partials.ndim != 3 or partials.shape[0] != 3 or partials.shape[2] != n or not partials.is_contiguous():
+        raise ValueError("layernorm_bwd: partials must be contiguous fp32 [3, P, n]")
+    with _Timed("layernorm_bwd", 0.0, float(rows) * n * (x.element_size() + 2 + dx.element_size())):
+        check(lib.kx_layernorm_bwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), act, dy.data_ptr(),
+                                   dy.stride(0), gamma.data_ptr(), float(eps), _ptr(dres), 0 if dres is None else dres.stride(0),
+                                   dx.data_ptr(), 1 if dx.dtype == torch.float32 else 0, dx.stride(0), _ptr(dxb),
+                                   0 if dxb is None else dxb.stride(0), partials.data_ptr(), partials.shape[1],
+                                   d_gamma.data_ptr(), d_beta.data_ptr(), _ptr(d_colsum), 1 if accumulate else 0, rows, n,
+                                   _stream()), "kx_layernorm_bwd")
+    return dx
+
+
+def colsum(x, out):
+    _req(x, torch.bfloat16, "x"); _req(out, torch.float32, "out")
+    with _Timed("colsum", 0.0, 2.0 * x.shape[0] * x.shape[1]):
+        check(lib.kx_colsum_bf16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), _stream()), "kx_colsum_bf16")
+    return out
+
+
+def xpos_bwd(dqkv, d_model, seq_len, tabs):
+    _req(dqkv, torch.bfloat16, "dqkv")
+    check(lib.kx_xpos_bwd(dqkv.data_ptr(), dqkv.stride(0), dqkv.shape[0], d_model, seq_len, *[t.data_ptr() for t in tabs],
+                          _stream()), "kx_xpos_bwd")
+    return dqkv
+
+
+def _rows(img_rows):
+    return (_abi.C.c_int * max(1, len(img_rows)))(*[int(r) for r in img_rows])
+
+
+def ce_fwd_bwd(logits, tokens, loss_acc, *, img_rows=(), n_img=0, inv_count=1.0, dlogits=None, err_flag=None):
+    """loss_acc fp32 [2] += (sum of row losses, rows counted); dlogits bf16 [B*T, ld >= vocab (multiple of 8)] or None."""
+    _req(logits, torch.float32, "logits"); _req(tokens, torch.int64, "tokens"); _req(loss_acc, torch.float32, "loss_acc")
+    B, t_text = tokens.shape
+    with _Timed("ce_fwd_bwd", 0.0, 10.0 * logits.shape[0] * logits.shape[1]):
+        check(lib.kx_ce_fwd_bwd(logits.data_ptr(), logits.stride(0), tokens.data_ptr(), B, t_text, _rows(img_rows),
+                                len(img_rows), n_img, logits.shape[1], float(inv_count), _ptr(dlogits),
+                                0 if dlogits is None else dlogits.stride(0), loss_acc.data_ptr(), _ptr(err_flag), _stream()),
+              "kx_ce_fwd_bwd")
+    return loss_acc
+
+
+def embed_bwd(dx0, tokens, d_embed, d_pos, *, img_rows=(), n_img=0, padding_idx=1):
+    _req(dx0, torch.float32, "dx0"); _req(tokens, torch.int64, "tokens")
+    B, t_text = tokens.shape
+    dim = dx0.shape[-1]
+    vocab = d_embed.shape[0] if d_embed is not None else 0
+    with _Timed("embed_bwd", 0.0, 12.0 * dx0.numel()):
+        check(lib.kx_embed_bwd(dx0.data_ptr(), tokens.data_ptr(), B, t_text, _rows(img_rows), len(img_rows), n_img, dim,
+                               vocab, padding_idx, _ptr(d_embed), _ptr(d_pos), _stream()), "kx_embed_bwd")
+
+
+def sumsq(g, out):
+    check(lib.kx_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "kx_sumsq")
+
+
+def clip_scale(sumsq_t, max_norm, pre_scale, scale_out, norm_out=None):
+    check(lib.kx_clip_scale(sumsq_t.data_ptr(), float(max_norm), float(pre_scale), scale_out.data_ptr(), _ptr(norm_out),
+                            _stream()), "kx_clip_scale")
+
+
+def adamw_step(p, g, m, v, wb, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step=1, grad_scale=None):
+    with _Timed("optimizer", 0.0, 30.0 * p.numel()):
+        check(lib.kx_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(wb), p.numel(), float(lr),
+                                float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                _ptr(grad_scale), _stream()), "kx_adamw_step")
+
+
+def lion_step(p, g, m, wb, *, lr, betas=(0.9, 0.99), weight_decay=0.0, grad_scale=None):
+    with _Timed("optimizer", 0.0, 22.0 * p.numel()):
+        check(lib.kx_lion_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), _ptr(wb), p.numel(), float(lr), float(betas[0]),
+                               float(betas[1]), float(weight_decay), _ptr(grad_scale), _stream()), "kx_lion_step")
 
 
 def perceiver_attention(q, kv, out, *, batch, heads, n_q, n_kv, v_col_off, scale):

@@ -137,6 +137,241 @@ def xpos_ref(T, device):
     return xp, scale.to(device), sin.to(device), cos.to(device)
 
 
+def case_gemm_trans():
+    """Backward GEMMs on operands where they lie: dgrad = dY . W (W as [K', N']), wgrad = dY^T . X (both [K', *])."""
+    torch.manual_seed(11)
+    ok = True
+    for (M, N, K) in ((512, 256, 384), (2048, 2048, 1024), (300, 200, 136), (4096, 1024, 4096), (130, 64, 72)):
+        dy = torch.randn(M, N, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) / math.sqrt(N)).bfloat16()
+        x = torch.randn(M, K, device=dev).bfloat16()
+        for cg, bn in ((2, 256), (1, 128)):
+            dx = torch.full((M + 2, K), 7.0, device=dev, dtype=torch.bfloat16)
+            ops.gemm(dy, w, dx, b_trans=True, cta_group=cg, block_n=bn, M=M)           # dX[M,K] = dY[M,N] . W[N,K]
+            good = report(f"dgrad bf16 cg={cg} bn={bn} {M}x{N}x{K}", dx[:M], dy.float() @ w.float(), 3e-2)
+            ok &= good and bool((dx[M:] == 7.0).all())
+            dw = torch.zeros(N, K, device=dev)
+            ops.gemm(dy, x, dw, a_trans=True, b_trans=True, cta_group=cg, block_n=bn)  # dW[N,K] = dY^T . X
+            ref = dy.float().T @ x.float()
+            ok &= report(f"wgrad fp32 cg={cg} bn={bn} {M}x{N}x{K}", dw / math.sqrt(M), ref / math.sqrt(M), 1e-2)
+            ops.gemm(dy, x, dw, res=dw, a_trans=True, b_trans=True, cta_group=cg, block_n=bn)   # accumulate: dW += dY^T . X
+            ok &= report(f"wgrad accumulate cg={cg} bn={bn} {M}x{N}x{K}", dw / math.sqrt(M), 2 * ref / math.sqrt(M), 2e-2)
+    # LM-head shapes: vocab not a multiple of 64, dlogits rows padded to a multiple of 64 columns with zeros
+    M, V, D = 384, 1002, 256
+    Vp = (V + 63) // 64 * 64
+    dl = torch.zeros(M, Vp, device=dev, dtype=torch.bfloat16)
+    dl[:, :V] = torch.randn(M, V, device=dev).bfloat16()
+    wout = (torch.randn(V, D, device=dev) / math.sqrt(D)).bfloat16()
+    h = torch.randn(M, D, device=dev).bfloat16()
+    dh = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(dl[:, :V], wout, dh, b_trans=True)
+    ok &= report("LM head dgrad (K'=1002)", dh, dl[:, :V].float() @ wout.float(), 6e-2)
+    dwo = torch.zeros(V, D, device=dev)
+    ops.gemm(dl[:, :V], h, dwo, a_trans=True, b_trans=True)
+    ok &= report("LM head wgrad (M'=1002)", dwo / math.sqrt(M), dl[:, :V].float().T @ h.float() / math.sqrt(M), 1e-2)
+    return ok
+
+
+def case_train_elementwise():
+    """Training-step glue kernels against autograd / torch.optim on the same inputs."""
+    torch.manual_seed(21)
+    ok = True
+    F = torch.nn.functional
+    # ---- LayerNorm backward: fp32 residual form (dres add, bf16 copy, column sums) and bf16 forms, n = 2048 / 8192 / ragged 200
+    for (rows, n, xdt, act) in ((1000, 2048, torch.float32, 0), (515, 8192, torch.bfloat16, 1), (300, 200, torch.bfloat16, 0),
+                                (64, 4096, torch.float32, 0)):
+        x = torch.randn(rows, n, device=dev) * 1.5 + 0.3
+        x = x.to(xdt)
+        gamma = torch.rand(n, device=dev) + 0.5
+        beta = torch.randn(n, device=dev)
+        dy = (torch.randn(rows, n, device=dev) / math.sqrt(n)).bfloat16()
+        xr = x.float().clone().requires_grad_(True)
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        a = F.gelu(xr) if act else xr
+        y = F.layer_norm(a, (n,), gr, br, 1e-5)
+        y.backward(dy.float())
+        P = ops.ln_bwd_partials(rows)
+        part = torch.empty(3, P, n, device=dev)
+        dg, db = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        if xdt == torch.float32:
+            dres = torch.randn(rows, n, device=dev) / math.sqrt(n)
+            dx = dres.clone()
+            dxb = torch.zeros(rows, n, device=dev, dtype=torch.bfloat16)
+            dcol = torch.zeros(n, device=dev)
+            ops.layernorm_bwd(x, dy, gamma, dx, dg, db, part, act=act, dres=dx, dxb=dxb, d_colsum=dcol)
+            ok &= report(f"ln_bwd fp32 dx {rows}x{n}", dx * math.sqrt(n), (xr.grad + dres) * math.sqrt(n), 2e-3)
+            ok &= report(f"ln_bwd bf16 copy {rows}x{n}", dxb.float() * math.sqrt(n), (xr.grad + dres) * math.sqrt(n), 3e-2)
+            ok &= report(f"ln_bwd colsum {rows}x{n}", dcol, (xr.grad + dres).sum(0), 2e-3)
+        else:
+            dx = torch.zeros(rows, n, device=dev, dtype=torch.bfloat16)
+            dcol = torch.zeros(n, device=dev)
+            ops.layernorm_bwd(x, dy, gamma, dx, dg, db, part, act=act, d_colsum=dcol)
+            ok &= report(f"ln_bwd bf16 dx act={act} {rows}x{n}", dx.float() * math.sqrt(n), xr.grad * math.sqrt(n), 3e-2)
+            ok &= report(f"ln_bwd bf16 colsum {rows}x{n}", dcol, dx.float().sum(0), 2e-3)
+        ok &= report(f"ln_bwd dgamma {rows}x{n}", dg, gr.grad, 3e-3)
+        ok &= report(f"ln_bwd dbeta {rows}x{n}", db, br.grad, 3e-3)
+        ops.layernorm_bwd(x, dy, gamma, dx if xdt != torch.float32 else dx.clone(), dg, db, part, act=act, accumulate=True)
+        ok &= report(f"ln_bwd dgamma accumulate {rows}x{n}", dg, 2 * gr.grad, 6e-3)
+    # ---- LN(gelu(u)) forward
+    for (rows, n) in ((700, 8192), (333, 256)):
+        u = torch.randn(rows, n, device=dev).bfloat16()
+        gamma, beta = torch.rand(n, device=dev) + 0.5, torch.randn(n, device=dev)
+        out = torch.zeros(rows, n, device=dev, dtype=torch.bfloat16)
+        ops.act_layernorm(u, gamma, beta, out)
+        ok &= report(f"act_layernorm {rows}x{n}", out, F.layer_norm(F.gelu(u.float()), (n,), gamma, beta, 1e-5), 7e-2)   # bf16 output, |y| up to 12
+    # ---- column sums
+    for (rows, n) in ((4096, 6144), (1000, 130), (77, 2048)):
+        xx = torch.randn(rows, n, device=dev).bfloat16()
+        out = torch.ones(n, device=dev)
+        ops.colsum(xx, out)
+        ok &= report(f"colsum {rows}x{n}", out, xx.float().sum(0) + 1, 2e-3)
+    # ---- xPos backward = transpose of the forward rotation: <R x, y> == <x, R^T y>
+    T, D, B = 96, 256, 2
+    scale = (torch.arange(0, 64, 2, device=dev) + 0.4 * 64) / (1.4 * 64)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, 32, device=dev) / 32))
+    tabs = ops.xpos_tables(scale.float(), inv_freq.float(), T, (-T) // 2, 512.0, dev)
+    def rot(z, c, s_):          # forward rotation in fp32 on [B*T, D]
+        z = z.view(B, T, D // 64, 32, 2)
+        c, s_ = c.view(1, T, 1, 32), s_.view(1, T, 1, 32)
+        return torch.stack([z[..., 0] * c - z[..., 1] * s_, z[..., 1] * c + z[..., 0] * s_], -1).view(B * T, D)
+    dqkv = torch.randn(B * T, 3 * D, device=dev).bfloat16()
+    want_q = torch.autograd.functional.vjp(lambda z: rot(z, tabs[0], tabs[1]), torch.zeros(B * T, D, device=dev), dqkv[:, :D].float())[1]
+    want_k = torch.autograd.functional.vjp(lambda z: rot(z, tabs[2], tabs[3]), torch.zeros(B * T, D, device=dev), dqkv[:, D:2 * D].float())[1]
+    v_before = dqkv[:, 2 * D:].clone()
+    ops.xpos_bwd(dqkv, D, T, tabs)
+    ok &= report("xpos_bwd dq", dqkv[:, :D], want_q, 3e-2)
+    ok &= report("xpos_bwd dk", dqkv[:, D:2 * D], want_k, 3e-2)
+    ok &= bool(torch.equal(dqkv[:, 2 * D:], v_before))
+    # ---- cross-entropy over the text rows (two images) + d(logits)
+    Bc, t_text, n_img, V = 3, 20, 8, 1002
+    rows_img = (2, 15)                                          # spliced starts: in front of text tokens 2 and 7
+    Tc = t_text + 2 * n_img
+    tok = torch.randint(0, V, (Bc, t_text), device=dev)
+    logits = torch.randn(Bc * Tc, V, device=dev) * 2
+    is_img = torch.zeros(Tc, dtype=torch.bool)
+    for r0 in rows_img:
+        is_img[r0:r0 + n_img] = True
+    text_rows = (~is_img).nonzero().flatten().tolist()
+    tgt = torch.full((Bc, Tc), -100, device=dev, dtype=torch.long)
+    for ti, t in enumerate(text_rows):
+        if ti + 1 < t_text and not (t + 1 < Tc and is_img[t + 1]):
+            tgt[:, t] = tok[:, ti + 1]
+    count = int((tgt >= 0).sum())
+    lr_ = logits.clone().requires_grad_(True)
+    loss = F.cross_entropy(lr_, tgt.view(-1), ignore_index=-100, reduction="sum")
+    (loss / count).backward()
+    Vp = (V + 63) // 64 * 64
+    dl = torch.full((Bc * Tc, Vp), 7.0, device=dev, dtype=torch.bfloat16)
+    acc = torch.zeros(2, device=dev)
+    ops.ce_fwd_bwd(logits, tok, acc, img_rows=rows_img, n_img=n_img, inv_count=1.0 / count, dlogits=dl)
+    ok &= report("ce loss sum", acc[:1], loss.detach().view(1), 2e-3 * count)
+    ok &= bool(int(acc[1].item()) == count)
+    ok &= report("ce dlogits", dl[:, :V].float() * count, lr_.grad * count, 1e-2)
+    ok &= bool((dl[:, V:] == 0).all())
+    # ---- embedding / position backward
+    D2 = 128
+    dx0 = torch.randn(Bc, Tc, D2, device=dev)
+    tok[0, 3] = 1                                               # a padding token: no gradient to its row
+    d_emb, d_pos = torch.zeros(V, D2, device=dev), torch.zeros(Tc + 2, D2, device=dev)
+    ops.embed_bwd(dx0.view(-1, D2), tok, d_emb, d_pos, img_rows=rows_img, n_img=n_img)
+    want_e = torch.zeros(V, D2, device=dev)
+    want_e.index_add_(0, tok.view(-1), dx0[:, ~is_img].reshape(-1, D2))
+    want_e[1] = 0
+    ok &= report("embed_bwd d_embed", d_emb, want_e, 1e-5)
+    want_p = torch.zeros(Tc + 2, D2, device=dev)
+    want_p[2:] = dx0.sum(0)
+    ok &= report("embed_bwd d_pos", d_pos, want_p, 1e-5)
+    # ---- gradient norm, clipping scale, AdamW, Lion
+    n = 1000003
+    pw = torch.randn(n, device=dev); g = torch.randn(n, device=dev) * 3
+    ss = torch.zeros(1, device=dev); sc = torch.zeros(1, device=dev); nrm = torch.zeros(1, device=dev)
+    ops.sumsq(g, ss)
+    ops.clip_scale(ss, 1.0, 0.5, sc, nrm)
+    ok &= report("grad norm", nrm, (g * 0.5).norm().view(1), 1e-2)
+    ok &= report("clip scale", sc, (0.5 * torch.clamp(1.0 / ((g * 0.5).norm() + 1e-6), max=1.0)).view(1), 1e-7)
+    for name in ("adamw", "lion"):
+        pr = torch.nn.Parameter(pw.clone())
+        if name == "adamw":
+            opt = torch.optim.AdamW([pr], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+        m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+        mine = pw.clone(); wb = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+        ref_m = torch.zeros(n, device=dev)
+        for step in (1, 2, 3):
+            gs = g * (0.5 + step) * sc
+            if name == "adamw":
+                pr.grad = gs.clone()
+                opt.step()
+                ops.adamw_step(mine, g * (0.5 + step), m, v, wb, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, step=step, grad_scale=sc)
+            else:
+                with torch.no_grad():                     # lion_pytorch.Lion update rule
+                    pr.mul_(1 - 1e-3 * 0.1)
+                    pr.add_(torch.sign(ref_m * 0.9 + gs * 0.1), alpha=-1e-3)
+                    ref_m.mul_(0.99).add_(gs, alpha=0.01)
+                ops.lion_step(mine, g * (0.5 + step), m, wb, lr=1e-3, betas=(0.9, 0.99), weight_decay=0.1, grad_scale=sc)
+        ok &= report(f"{name} 3 steps", mine, pr.detach(), 2e-5)
+        ok &= report(f"{name} bf16 copy", wb, mine.bfloat16(), 0.0)
+    return ok
+
+
+def case_attn_bwd():
+    """Flash attention backward (with and without the fused xPos transpose) against autograd on the eager formula."""
+    torch.manual_seed(31)
+    ok = True
+    for (B, H, T, causal, use_xpos) in ((2, 2, 256, True, False), (1, 3, 200, True, True), (2, 2, 114, True, True),
+                                        (1, 2, 384, False, False), (1, 32, 1024, True, True)):
+        D = H * 64
+        M = B * T
+        qkv = (torch.randn(M, 3 * D, device=dev) * 0.8).bfloat16()
+        d_out = (torch.randn(M, D, device=dev) * 0.5).bfloat16()
+        scale = 0.125
+        tabs = None
+        if use_xpos:
+            sc_ = (torch.arange(0, 64, 2, device=dev) + 0.4 * 64) / (1.4 * 64)
+            inv_freq = 1.0 / (10000 ** (torch.arange(0, 32, device=dev) / 32))
+            tabs = ops.xpos_tables(sc_.float(), inv_freq.float(), T, (-T) // 2, 512.0, dev)
+
+        def rot(z, c, s_):
+            z = z.view(B, T, H, 32, 2)
+            c, s_ = c.view(1, T, 1, 32), s_.view(1, T, 1, 32)
+            return torch.stack([z[..., 0] * c - z[..., 1] * s_, z[..., 1] * c + z[..., 0] * s_], -1).view(M, D)
+
+        # the kernel differentiates w.r.t. the UN-rotated q, k when tables are given; its inputs are the rotated ones
+        q0 = qkv[:, :D].float().clone().requires_grad_(True)
+        k0 = qkv[:, D:2 * D].float().clone().requires_grad_(True)
+        v0 = qkv[:, 2 * D:].float().clone().requires_grad_(True)
+        qr = rot(q0, tabs[0], tabs[1]) if use_xpos else q0
+        kr = rot(k0, tabs[2], tabs[3]) if use_xpos else k0
+        qkv_rot = torch.cat([qr.detach(), kr.detach(), v0.detach()], 1).bfloat16().contiguous()
+        # reference on the bf16-rounded rotated operands (what the kernel reads), gradient routed through the rotation
+        qb = qr + (qkv_rot[:, :D].float() - qr).detach()
+        kb = kr + (qkv_rot[:, D:2 * D].float() - kr).detach()
+        def heads(t):
+            return t.view(B, T, H, 64).transpose(1, 2)
+        sc = heads(qb) @ heads(kb).transpose(-1, -2) * scale
+        if causal:
+            sc = sc + torch.triu(torch.full((T, T), float("-inf"), device=dev), 1)
+        o_ref = (sc.softmax(-1) @ heads(v0)).transpose(1, 2).reshape(M, D)
+        o_ref.backward(d_out.float())
+        out = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
+        lse = torch.full((H, B, ops.lse_pad(T)), float("nan"), device=dev)
+        ops.attention(qkv_rot[:, :D], qkv_rot[:, D:2 * D], qkv_rot[:, 2 * D:], out, batch=B, heads=H, seq_len=T, causal=causal,
+                      scale=scale, lse_out=lse)
+        ok &= report(f"attn fwd (lse path) B={B} H={H} T={T}", out, o_ref.detach(), 2e-2)
+        lse_ref = torch.logsumexp(sc.detach(), -1) * 1.4426950408889634          # [B, H, T] in log2 units
+        ok &= report(f"attn lse B={B} H={H} T={T}", lse[:, :, :T], lse_ref.transpose(0, 1), 2e-2)
+        dqkv = torch.full((M, 3 * D), 9.0, device=dev, dtype=torch.bfloat16)
+        acc = torch.empty(M, D, device=dev)
+        delta = torch.empty_like(lse)
+        ops.attention_bwd(qkv_rot[:, :D], qkv_rot[:, D:2 * D], qkv_rot[:, 2 * D:], out, d_out, lse, dqkv[:, :D], dqkv[:, D:2 * D],
+                          dqkv[:, 2 * D:], acc, delta, batch=B, heads=H, seq_len=T, causal=causal, scale=scale, xpos=tabs)
+        torch.cuda.synchronize()
+        tag = f"B={B} H={H} T={T} causal={causal} xpos={use_xpos}"
+        ok &= report(f"attn_bwd dv {tag}", dqkv[:, 2 * D:], v0.grad, 3e-2)
+        ok &= report(f"attn_bwd dk {tag}", dqkv[:, D:2 * D], k0.grad, 3e-2)
+        ok &= report(f"attn_bwd dq {tag}", dqkv[:, :D], q0.grad, 3e-2)
+    return ok
+
+
 def case_xpos():
     ok = True
     for T in (5, 114, 2048):
