@@ -550,7 +550,7 @@ class Kosmos(_KosmosBase):
             cur = st_b
         return x
 
-    def _perceive_project(self, xv: torch.Tensor, B: int, x0: torch.Tensor, T: int, img_rows=(2,)):
+    def _perceive_project(self, xv: torch.Tensor, B: int, x0: torch.Tensor, T: int, img_rows=(2,), pos_table=None):
         """PerceiverResampler + image_proj (model.py:232).  xv holds m = len(img_rows) images per
         sequence, media-major ([m*B*Tv, Dv]); the projection's epilogue writes rows [img_rows[i], img_rows[i]+64) of
         every sequence of x0 and adds their positions."""
@@ -584,7 +584,7 @@ class Kosmos(_KosmosBase):
             ops.gemm(lnl, L["w_ff1"], mid, act=_abi.KX_ACT_GELU)
             ops.gemm(mid, L["w_ff2"], lat, res=lat)
         ops.layernorm(lat, *vp["p_norm"], lnl)
-        pos = self.decoder._pack()["pos"]
+        pos = pos_table if pos_table is not None else self.decoder._pack()["pos"]
         for i, r0 in enumerate(img_rows):                # image i of all sequences: rows [i*B*64, (i+1)*B*64)
             ops.gemm(lnl[i * B * Lq:(i + 1) * B * Lq], vp["w_ip"], x0, grp=(Lq, T, r0), add_tab=pos, add_off=r0 + 2)
 

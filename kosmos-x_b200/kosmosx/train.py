@@ -1,0 +1,393 @@
+"""Data-parallel training step of the Kosmos-X path on the sm_100a kernels.
+
+Shape of the reference's step (train.py:643-657): forward -> loss -> backward -> clip_grad_norm_(1.0) ->
+optimizer.step() -> zero_grad(), with AdamW or Lion over a decay / no-decay split (train.py:257-398) and one
+gradient all-reduce per step across the data-parallel ranks.  The reference script itself cannot run
+(`model(inputs, return_loss=True)` at train.py:647 passes no images and Kosmos returns no loss — SURVEY.md
+fact 8); the loss is the intended one of experimental/model/allModalities/notes.txt:566-574: next-token
+cross-entropy over the text rows of the spliced sequence.
+
+Everything arithmetic is a C-ABI call (ops.*): the training forward keeps what backward needs (LayerNorm outputs
+are materialised instead of folded, the FFN keeps its pre-activation), backward is hand-scheduled — no autograd.
+Gradients live in one flat fp32 buffer that is all-reduced in per-layer buckets while backward is still running.
+
+Trained here: the decoder (.A branches), the final LayerNorm, the LM head, the token-embedding and position
+tables.  Frozen: the CLIP tower (as the reference's notes.txt:537 `clip_model.requires_grad_(False)`), and in this
+round also the perceiver resampler and image_proj (their backward is not built yet — DESIGN.md §7).
+Dropout (p = 0.1 in the reference's train mode) is not applied.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _abi, ops
+from .model import Kosmos, _live
+
+_ALIGN = 64          # elements: keeps every parameter 256-byte aligned in the fp32 buffers (128 in the bf16 copy)
+
+
+def _round_up(n, a=_ALIGN):
+    return (n + a - 1) // a * a
+
+
+class _Seg:
+    __slots__ = ("off", "shape", "numel")
+
+    def __init__(self, off, shape):
+        self.off, self.shape = off, tuple(shape)
+        self.numel = 1
+        for s in self.shape:
+            self.numel *= s
+
+
+class KosmosTrainer:
+    """One object per process (one process per GPU).  ``step(text_tokens, images)`` runs a whole optimisation step
+    and returns the mean loss as a device scalar (no host sync)."""
+
+    def __init__(self, model: Kosmos, *, optimizer: str = "adamw", lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
+                 weight_decay: float = 0.1, max_grad_norm: float = 1.0, process_group=None, overlap_all_reduce: bool = True,
+                 layout_only: bool = False):
+        if optimizer not in ("adamw", "lion"):
+            raise ValueError("optimizer must be 'adamw' or 'lion' (train.py:375-386)")
+        self.model = model
+        self.cfg = model.cfg
+        self.opt, self.lr, self.betas, self.eps, self.wd = optimizer, lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.pg = process_group
+        self.overlap = overlap_all_reduce
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.t = 0
+        self._ws = {}
+        self._flatten(layout_only)
+
+    # ------------------------------------------------------------------ flat parameter / gradient buffers
+    def _flatten(self, layout_only=False):
+        """Lay every trained parameter out in one flat buffer: [decay segment | no-decay segment], per-layer blocks
+        first.  layout_only (tests of the bucket plan on a CPU box) stops before anything touches the device."""
+        m, cfg = self.model, self.cfg
+        dev = m.embed.weight.device
+        if dev.type != "cuda" and not layout_only:
+            raise RuntimeError("KosmosTrainer: move the model to a B200 first (there is no CPU path)")
+        dec = m.decoder
+        decay, nodecay = [], []                 # (param, key) in buffer order
+        self.layers = []
+        for L in dec.layers:
+            sa = L.self_attn
+            q, k, v, o = (_live(x) for x in (sa.q_proj, sa.k_proj, sa.v_proj, sa.out_proj))
+            ffn = _live(L.ffn)
+            ln_a, ln_i, ln_f = _live(L.self_attn_layer_norm), _live(sa.inner_attn_ln), _live(L.final_layer_norm)
+            decay += [q.weight, k.weight, v.weight, o.weight, ffn.fc1.weight, ffn.fc2.weight]      # q|k|v adjacent: one [3D, D] view
+            nodecay += [q.bias, k.bias, v.bias, o.bias, ffn.fc1.bias, ffn.fc2.bias, ln_a.weight, ln_a.bias, ln_i.weight,
+                        ln_i.bias, ln_f.weight, ln_f.bias, ffn.ffn_layernorm.weight, ffn.ffn_layernorm.bias]
+            self.layers.append(dict(q=q, k=k, v=v, o=o, fc1=ffn.fc1, fc2=ffn.fc2, ln_a=ln_a, ln_i=ln_i, ln_f=ln_f,
+                                    ln_ffn=ffn.ffn_layernorm))
+        decay.append(m.output_projection.weight)
+        nodecay += [dec.layer_norm.weight, dec.layer_norm.bias, m.embed.weight, m.embed_positions.weight]
+        if m.output_projection.bias is not None:
+            nodecay.append(m.output_projection.bias)
+        d = cfg.dim
+        for q, k, v in ((L["q"], L["k"], L["v"]) for L in self.layers):
+            if q.weight.numel() % _ALIGN or q.bias.numel() % _ALIGN:
+                raise ValueError("dim must be a multiple of 64")
+        self.seg = {}
+        off = 0
+        for p in decay:
+            self.seg[id(p)] = _Seg(off, p.shape)
+            off += _round_up(p.numel())
+        self.n_decay = off
+        for p in nodecay:
+            self.seg[id(p)] = _Seg(off, p.shape)
+            off += _round_up(p.numel())
+        self.n_total = off
+        self.params = decay + nodecay
+        if layout_only:
+            return
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.P = torch.zeros(off, **f32)
+        self.G = torch.zeros(off, **f32)
+        self.M1 = torch.zeros(off, **f32)
+        self.M2 = torch.zeros(off, **f32) if self.opt == "adamw" else None
+        self.W16 = torch.zeros(self.n_decay, dtype=torch.bfloat16, device=dev)
+        with torch.no_grad():
+            for p in self.params:
+                s = self.seg[id(p)]
+                view = self.P[s.off:s.off + s.numel].view(s.shape)
+                view.copy_(p.data)
+                p.data = view                                            # the module now lives in the flat buffer
+                p.grad = self.G[s.off:s.off + s.numel].view(s.shape)
+        # every parameter of the model that is NOT trained here stays frozen
+        trained = {id(p) for p in self.params}
+        for p in m.parameters():
+            if id(p) not in trained:
+                p.requires_grad_(False)
+        self.scalars = torch.zeros(8, **f32)       # [0:2] loss sum / rows, [2] sum g^2, [3] clip scale, [4] grad norm
+        self.sync_weights()
+
+    def sync_weights(self):
+        """Re-derive the bf16 tensor-core copies from the fp32 master weights (after load_state_dict or any
+        in-place edit of the parameters).  The optimizer kernels keep them in sync afterwards."""
+        ops.cast_bf16(self.P[:self.n_decay], self.W16)
+        self.model.decoder._packed = None            # the inference path re-stages its folded weights lazily
+
+    def _w16(self, p):
+        s = self.seg[id(p)]
+        return self.W16[s.off:s.off + s.numel].view(s.shape)
+
+    def _g(self, p):
+        s = self.seg[id(p)]
+        return self.G[s.off:s.off + s.numel].view(s.shape)
+
+    def _qkv(self, L, what):
+        """q|k|v as one [3D, D] matrix / [3D] vector (adjacent segments, no padding between them)."""
+        s = self.seg[id(getattr(L["q"], what))]
+        n = s.numel * 3
+        if what == "weight":
+            return (self.W16[s.off:s.off + n].view(3 * s.shape[0], s.shape[1]), self.G[s.off:s.off + n].view(3 * s.shape[0], s.shape[1]))
+        return self.P[s.off:s.off + n], self.G[s.off:s.off + n]
+
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        b = self._ws.get(key)
+        if b is None:
+            b = torch.empty(shape, dtype=dtype, device=self.P.device)
+            self._ws[key] = b
+        return b
+
+    # ------------------------------------------------------------------ forward (keeps what backward needs)
+    def _forward(self, text_tokens, images, img_rows):
+        m, cfg = self.model, self.cfg
+        B, t_text = text_tokens.shape
+        Lq = cfg.p_latents
+        T = t_text + Lq * len(img_rows)
+        M, D, F, H, V = B * T, cfg.dim, cfg.ffn, cfg.heads, cfg.vocab
+        bf, f32 = torch.bfloat16, torch.float32
+        dp = m.decoder
+        # frozen vision side on the inference kernels: image rows of x0 (+ their positions)
+        x = self._buf("x0", (M, D), f32)
+        xv = m._vit(images, media=len(img_rows))
+        pos = m.embed_positions.weight
+        m._perceive_project(xv, B, x, T, img_rows, pos_table=pos)
+        ops.embed_splice_pos(text_tokens, m.embed.weight, pos, x, img_rows=img_rows, n_img=Lq, err_flag=m._err_flag())
+        tabs = dp._xpos(T, x.device)
+        scale = (D // H) ** -0.5
+        saved = []
+        for li, L in enumerate(self.layers):
+            s = dict(x_in=x)
+            s["h1"] = self._buf(f"h1_{li}", (M, D), bf)
+            s["qkv"] = self._buf(f"qkv_{li}", (M, 3 * D), bf)
+            s["att"] = self._buf(f"att_{li}", (M, D), bf)
+            s["lse"] = self._buf(f"lse_{li}", (H, B, ops.lse_pad(T)), f32)
+            s["a_ln"] = self._buf(f"aln_{li}", (M, D), bf)
+            s["x_mid"] = self._buf(f"xmid_{li}", (M, D), f32)
+            s["h2"] = self._buf(f"h2_{li}", (M, D), bf)
+            s["u"] = self._buf(f"u_{li}", (M, F), bf)
+            s["g_ln"] = self._buf(f"gln_{li}", (M, F), bf)
+            x_out = self._buf(f"xout_{li}", (M, D), f32)
+            wqkv, _ = self._qkv(L, "weight")
+            bqkv, _ = self._qkv(L, "bias")
+            ops.layernorm(x, L["ln_a"].weight, L["ln_a"].bias, s["h1"], eps=cfg.eps)
+            ops.gemm(s["h1"], wqkv, s["qkv"], bias=bqkv, xpos=tuple(tabs), seq_len=T)
+            qkv = s["qkv"]
+            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], s["att"], batch=B, heads=H, seq_len=T, causal=True,
+                          scale=scale, lse_out=s["lse"])
+            ops.layernorm(s["att"], L["ln_i"].weight, L["ln_i"].bias, s["a_ln"], eps=cfg.eps)
+            ops.gemm(s["a_ln"], self._w16(L["o"].weight), s["x_mid"], bias=L["o"].bias, res=x)
+            ops.layernorm(s["x_mid"], L["ln_f"].weight, L["ln_f"].bias, s["h2"], eps=cfg.eps)
+            ops.gemm(s["h2"], self._w16(L["fc1"].weight), s["u"], bias=L["fc1"].bias)
+            ops.act_layernorm(s["u"], L["ln_ffn"].weight, L["ln_ffn"].bias, s["g_ln"], eps=cfg.eps)
+            ops.gemm(s["g_ln"], self._w16(L["fc2"].weight), x_out, bias=L["fc2"].bias, res=s["x_mid"])
+            saved.append(s)
+            x = x_out
+        hF = self._buf("hF", (M, D), bf)
+        ops.layernorm(x, dp.layer_norm.weight, dp.layer_norm.bias, hF, eps=cfg.eps)
+        logits = self._buf("logits", (M, V), f32)
+        ops.gemm(hF, self._w16(m.output_projection.weight), logits, bias=m.output_projection.bias)
+        return dict(saved=saved, x_last=x, hF=hF, logits=logits, B=B, T=T, M=M, tabs=tabs, scale=scale)
+
+    # ------------------------------------------------------------------ loss + backward
+    @staticmethod
+    def n_loss_rows(B, t_text, img_rows, n_lat):
+        """Rows that carry a loss (host arithmetic on shapes only): every text token except the last one and the
+        ones whose next row starts an image block (same rule as kx_ce_fwd_bwd)."""
+        T = t_text + n_lat * len(img_rows)
+        img = [False] * T
+        for r in img_rows:
+            for i in range(r, r + n_lat):
+                img[i] = True
+        text_rows = [t for t in range(T) if not img[t]]
+        dropped = 1 + sum(1 for t in text_rows[:-1] if t + 1 in set(img_rows))
+        return B * (t_text - dropped)
+
+    def _backward(self, fw, text_tokens, img_rows):
+        m, cfg = self.model, self.cfg
+        B, T, M = fw["B"], fw["T"], fw["M"]
+        D, F, H, V = cfg.dim, cfg.ffn, cfg.heads, cfg.vocab
+        bf, f32 = torch.bfloat16, torch.float32
+        Lq = cfg.p_latents
+        dp = m.decoder
+        n_rows = self.n_loss_rows(B, text_tokens.shape[1], img_rows, Lq)
+        Vp = _round_up(V)
+        dlogits = self._buf("dlogits", (M, Vp), bf)
+        self.scalars.zero_()
+        self.G.zero_()
+        ops.ce_fwd_bwd(fw["logits"], text_tokens, self.scalars[0:2], img_rows=img_rows, n_img=Lq, inv_count=1.0 / max(n_rows, 1),
+                       dlogits=dlogits, err_flag=m._err_flag())
+        dl = dlogits[:, :V]
+        P = ops.ln_bwd_partials(M)
+        part_d = self._buf("part_d", (3, P, D), f32)
+        part_f = self._buf("part_f", (3, P, F), f32)
+        dx = self._buf("dx", (M, D), f32)
+        dxb = self._buf("dxb", (M, D), bf)
+        dh = self._buf("dh", (M, D), bf)            # gradient w.r.t. a LayerNorm output of width D (dgrad result)
+        dgl = self._buf("dgl", (M, F), bf)
+        du = self._buf("du", (M, F), bf)
+        datt = self._buf("datt", (M, D), bf)
+        dqkv = self._buf("dqkv", (M, 3 * D), bf)
+        dq_acc = self._buf("dq_acc", (M, D), f32)
+        delta = self._buf("delta", (H, B, ops.lse_pad(T)), f32)
+        # LM head
+        wout = m.output_projection.weight
+        ops.gemm(dl, self._w16(wout), dh, b_trans=True)
+        ops.gemm(dl, fw["hF"], self._g(wout), a_trans=True, b_trans=True)
+        if m.output_projection.bias is not None:
+            ops.colsum(dl, self._g(m.output_projection.bias))
+        last = self.layers[-1] if self.layers else None
+        ops.layernorm_bwd(fw["x_last"], dh, dp.layer_norm.weight, dx, self._g(dp.layer_norm.weight), self._g(dp.layer_norm.bias),
+                          part_d, eps=cfg.eps, dxb=dxb, d_colsum=self._g(last["fc2"].bias) if last else None)
+        works = []
+        self._bucket_ready("head", works)                     # the LM head gradient is complete
+        for li in range(len(self.layers) - 1, -1, -1):
+            L, s = self.layers[li], fw["saved"][li]
+            # ---- FFN: x_out = x_mid + fc2(LN_ffn(gelu(fc1(LN_f(x_mid)))))
+            ops.gemm(dxb, self._w16(L["fc2"].weight), dgl, b_trans=True)
+            ops.gemm(dxb, s["g_ln"], self._g(L["fc2"].weight), a_trans=True, b_trans=True)
+            ops.layernorm_bwd(s["u"], dgl, L["ln_ffn"].weight, du, self._g(L["ln_ffn"].weight), self._g(L["ln_ffn"].bias), part_f,
+                              act=_abi.KX_ACT_GELU, eps=cfg.eps, d_colsum=self._g(L["fc1"].bias))
+            ops.gemm(du, self._w16(L["fc1"].weight), dh, b_trans=True)
+            ops.gemm(du, s["h2"], self._g(L["fc1"].weight), a_trans=True, b_trans=True)
+            ops.layernorm_bwd(s["x_mid"], dh, L["ln_f"].weight, dx, self._g(L["ln_f"].weight), self._g(L["ln_f"].bias), part_d,
+                              eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(L["o"].bias))
+            # ---- attention: x_mid = x_in + out_proj(LN_i(attn(xpos(qkv(LN_a(x_in))))))
+            ops.gemm(dxb, self._w16(L["o"].weight), dh, b_trans=True)
+            ops.gemm(dxb, s["a_ln"], self._g(L["o"].weight), a_trans=True, b_trans=True)
+            ops.layernorm_bwd(s["att"], dh, L["ln_i"].weight, datt, self._g(L["ln_i"].weight), self._g(L["ln_i"].bias), part_d,
+                              eps=cfg.eps)
+            qkv = s["qkv"]
+            ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], s["att"], datt, s["lse"], dqkv[:, :D], dqkv[:, D:2 * D],
+                              dqkv[:, 2 * D:], dq_acc, delta, batch=B, heads=H, seq_len=T, causal=True, scale=fw["scale"],
+                              xpos=tuple(fw["tabs"]))
+            wqkv, gwqkv = self._qkv(L, "weight")
+            _, gbqkv = self._qkv(L, "bias")
+            ops.colsum(dqkv, gbqkv)
+            ops.gemm(dqkv, wqkv, dh, b_trans=True)
+            ops.gemm(dqkv, s["h1"], gwqkv, a_trans=True, b_trans=True)
+            prev = self.layers[li - 1] if li > 0 else None
+            ops.layernorm_bwd(s["x_in"], dh, L["ln_a"].weight, dx, self._g(L["ln_a"].weight), self._g(L["ln_a"].bias), part_d,
+                              eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(prev["fc2"].bias) if prev else None)
+            self._bucket_ready(li, works)                     # (fc2.bias of layer li was written by layer li+1's LayerNorm backward)
+        ops.embed_bwd(dx, text_tokens, self._g(m.embed.weight), self._g(m.embed_positions.weight), img_rows=img_rows, n_img=Lq,
+                      padding_idx=m.embed.padding_idx if m.embed.padding_idx is not None else -1)
+        self._bucket_ready("tail", works)
+        for w in works:
+            w.wait()
+
+    # ------------------------------------------------------------------ gradient all-reduce (data parallel)
+    def bucket_plan(self):
+        """[(name, lo, hi)] slices of the flat gradient buffer in the order backward completes them: the LM head, then
+        the layers from last to first (decay block + no-decay block each), then the tail (final LayerNorm, embedding
+        and position tables).  The slices tile [0, n_total) exactly."""
+        nl = len(self.layers)
+        plan = [("head", self._layer_span(nl, True)[0], self.n_decay)]
+        for li in range(nl - 1, -1, -1):
+            plan.append((f"layer{li}.decay", *self._layer_span(li, True)))
+            plan.append((f"layer{li}.nodecay", *self._layer_span(li, False)))
+        plan.append(("tail", self._layer_span(nl, False)[0], self.n_total))
+        return [(n, lo, hi) for n, lo, hi in plan if hi > lo]
+
+    def _bucket_ready(self, which, works):
+        """Overlapped all-reduce (sum): as soon as a bucket of bucket_plan() can no longer change, it goes out on
+        NCCL's stream while backward continues on the compute stream.  which = "head" | layer index | "tail"."""
+        if self.world == 1:
+            return
+        dist = torch.distributed
+        if not self.overlap:
+            if which == "tail":
+                works.append(dist.all_reduce(self.G, group=self.pg, async_op=True))
+            return
+        key = f"layer{which}." if isinstance(which, int) else which
+        for name, lo, hi in self.bucket_plan():
+            if name == key or (isinstance(which, int) and name.startswith(key)):
+                works.append(dist.all_reduce(self.G[lo:hi], group=self.pg, async_op=True))
+
+    def _layer_span(self, li, decay):
+        """[lo, hi) of layer li in the decay / no-decay segment (li == len(layers): the start of what follows them)."""
+        nl = len(self.layers)
+        if decay:
+            first = self.seg[id(self.layers[0]["q"].weight)].off if nl else 0
+            per = (self.seg[id(self.layers[1]["q"].weight)].off - first) if nl > 1 else \
+                  (self.seg[id(self.model.output_projection.weight)].off - first)
+        else:
+            first = self.seg[id(self.layers[0]["q"].bias)].off if nl else self.n_decay
+            per = (self.seg[id(self.layers[1]["q"].bias)].off - first) if nl > 1 else \
+                  (self.seg[id(self.model.decoder.layer_norm.weight)].off - first)
+        return first + li * per, first + (li + 1) * per
+
+    # ------------------------------------------------------------------ optimizer
+    def _optimize(self):
+        self.t += 1
+        sc = self.scalars
+        ops.sumsq(self.G, sc[2:3])
+        ops.clip_scale(sc[2:3], self.max_grad_norm, 1.0 / self.world, sc[3:4], sc[4:5])
+        nd = self.n_decay
+        segs = ((0, nd, self.wd, self.W16), (nd, self.n_total, 0.0, None))
+        for lo, hi, wd, wb in segs:
+            if hi <= lo:
+                continue
+            if self.opt == "adamw":
+                ops.adamw_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], self.M2[lo:hi], wb, lr=self.lr, betas=self.betas,
+                               eps=self.eps, weight_decay=wd, step=self.t, grad_scale=sc[3:4])
+            else:
+                ops.lion_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], wb, lr=self.lr, betas=self.betas, weight_decay=wd,
+                              grad_scale=sc[3:4])
+        self.model.decoder._packed = None
+
+    # ------------------------------------------------------------------ public API
+    def _prepare(self, text_tokens, images, image_positions):
+        cfg = self.cfg
+        if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):
+            raise TypeError("text_tokens and images must be instances of torch.Tensor")
+        if not text_tokens.is_cuda or not images.is_cuda:
+            raise RuntimeError("KosmosTrainer: inputs must be on the GPU (no CPU path)")
+        if text_tokens.dtype != torch.int64 or text_tokens.ndim != 2:
+            raise TypeError("text_tokens must be an int64 tensor of shape (B, T_text)")
+        mcount = images.shape[1] if images.ndim == 5 else 1
+        pos = [2] if image_positions is None else [int(p) for p in image_positions]
+        if len(pos) != mcount or sorted(pos) != pos or pos[0] < 0 or pos[-1] > text_tokens.shape[1]:
+            raise ValueError(f"image_positions {pos} must be {mcount} ascending text-token indices")
+        T = text_tokens.shape[1] + cfg.p_latents * mcount
+        if T + 2 > cfg.max_positions:
+            raise ValueError(f"spliced sequence length {T} exceeds the positional table (max {cfg.max_positions - 2})")
+        img_rows = tuple(p + i * cfg.p_latents for i, p in enumerate(pos))
+        images = images.to(torch.float32).reshape(-1, 3, cfg.image, cfg.image).contiguous()
+        return text_tokens.contiguous(), images, img_rows
+
+    def loss_and_grads(self, text_tokens, images, image_positions=None):
+        """Forward + backward (+ all-reduce) without the optimizer: fills ``param.grad`` (views of the flat buffer,
+        SUMMED over ranks) and returns the local mean loss (device scalar)."""
+        text_tokens, images, img_rows = self._prepare(text_tokens, images, image_positions)
+        fw = self._forward(text_tokens, images, img_rows)
+        self._backward(fw, text_tokens, img_rows)
+        return self.scalars[0] / torch.clamp(self.scalars[1], min=1.0)
+
+    def step(self, text_tokens, images, image_positions=None):
+        loss = self.loss_and_grads(text_tokens, images, image_positions)
+        self._optimize()
+        return loss
+
+    @property
+    def grad_norm(self):
+        """Global gradient norm of the last step before clipping (device scalar)."""
+        return self.scalars[4]

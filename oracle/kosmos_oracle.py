@@ -560,6 +560,34 @@ class KosmosOracle(nn.Module):
         model_input = self.embed_inputs(text_tokens, images, image_positions)
         return self.decoder(model_input, passed_x=model_input)[0]              # model.py:250
 
+    @staticmethod
+    def loss_targets(text_tokens, n_latents, image_positions=None, n_images=1):
+        """Next-token targets per row of the spliced sequence, -100 = no loss.  The row holding text token i
+        predicts text token i+1; image rows, the last text token and the token directly in front of an image are
+        dropped — the intent of the reference's training loop (experimental/model/allModalities/notes.txt:566-574:
+        keep row 0 and the rows after the image block, "tokens < n predict n"), with the class dimension on the
+        vocabulary (the pasted loop feeds CrossEntropyLoss a (B, T, C) tensor, i.e. classes on dim 1 — SURVEY App. C)."""
+        B, t_text = text_tokens.shape
+        pos = [2] * n_images if image_positions is None else list(image_positions)
+        T = t_text + n_latents * len(pos)
+        starts = [p + i * n_latents for i, p in enumerate(pos)]
+        is_img = torch.zeros(T, dtype=torch.bool)
+        for r in starts:
+            is_img[r:r + n_latents] = True
+        text_rows = (~is_img).nonzero().flatten().tolist()
+        tgt = torch.full((B, T), -100, dtype=torch.long)
+        for ti, t in enumerate(text_rows):
+            if ti + 1 < t_text and not (t + 1 < T and bool(is_img[t + 1])):
+                tgt[:, t] = text_tokens[:, ti + 1]
+        return tgt
+
+    def loss(self, text_tokens, images, image_positions=None):
+        """Mean cross-entropy over the text rows (train.py:647 `loss = model(...)`; see loss_targets)."""
+        logits = self.forward(text_tokens, images, image_positions=image_positions)
+        m = images.shape[1] if images.ndim == 5 else 1
+        tgt = self.loss_targets(text_tokens, self.cfg.p_latents, image_positions, m)
+        return F.cross_entropy(logits.reshape(-1, logits.shape[-1]), tgt.reshape(-1), ignore_index=-100)
+
     @torch.no_grad()
     def stages(self, text_tokens, images, image_positions=None):
         """Intermediate tensors, for per-stage parity tests."""

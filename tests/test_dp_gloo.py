@@ -59,3 +59,82 @@ def test_two_rank_gloo_sharding_and_reductions():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: (True, 11.0, 5.0), 1: (True, 11.0, 5.0)}
+
+
+# --------------------------------------------------------------------------- training step: gradient buckets
+def _tiny_trainer_layout():
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, KosmosConfig, KosmosTrainer
+    oc = ko.OracleConfig.tiny(layers=3)
+    torch.manual_seed(0)
+    model = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
+    return model, KosmosTrainer(model, layout_only=True)
+
+
+def test_gradient_bucket_plan_tiles_the_flat_buffer():
+    """ONE all-reduce over the trainable gradients per step, issued as buckets in the order backward
+    completes them (LM head, layers last to first, tables).  The buckets must tile the flat buffer exactly, keep every
+    parameter inside one bucket, and hold exactly the trained set (.A branches, no .B, no vision tower)."""
+    model, tr = _tiny_trainer_layout()
+    plan = tr.bucket_plan()
+    spans = sorted((lo, hi) for _, lo, hi in plan)
+    assert spans[0][0] == 0 and spans[-1][1] == tr.n_total
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+    names = [n for n, _, _ in plan]
+    assert names[0] == "head" and names[-1] == "tail" and names[1].startswith("layer2.") and names[-2].startswith("layer0.")
+    by_id = {id(p): n for n, p in model.named_parameters()}
+    for p in tr.params:
+        s = tr.seg[id(p)]
+        inside = [n for n, lo, hi in plan if lo <= s.off and s.off + s.numel <= hi]
+        assert len(inside) == 1, by_id[id(p)]
+        name = by_id[id(p)]
+        assert ".B." not in name and not name.startswith(("clip_model", "perceive", "image_proj"))
+        if name.startswith("decoder.layers."):
+            assert inside[0].startswith(f"layer{name.split('.')[2]}.")
+    # q|k|v are adjacent so that one [3D, D] GEMM operand / gradient view exists
+    L = tr.layers[1]
+    sq, sk, sv = (tr.seg[id(L[n].weight)] for n in "qkv")
+    assert sk.off == sq.off + sq.numel and sv.off == sk.off + sk.numel
+    # decay split of the reference (train.py:257-398): Linear weights decay, biases / LayerNorm / embeddings do not
+    for p in tr.params:
+        assert (tr.seg[id(p)].off < tr.n_decay) == (p.ndim == 2 and by_id[id(p)].endswith("weight")
+                                                    and "embed" not in by_id[id(p)])
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    kd.init_from_env("gloo")
+    _, tr = _tiny_trainer_layout()
+    tr.world, tr.overlap = world, True
+    g = torch.Generator().manual_seed(100 + rank)
+    tr.G = torch.randn(tr.n_total, generator=g)
+    want = tr.G.clone()
+    dist.all_reduce(want)
+    works = []
+    tr._bucket_ready("head", works)
+    for li in range(len(tr.layers) - 1, -1, -1):
+        tr._bucket_ready(li, works)
+    tr._bucket_ready("tail", works)
+    for w in works:
+        w.wait()
+    ok_overlap = torch.equal(tr.G, want) and len(works) == len(tr.bucket_plan())
+    tr.G = torch.randn(tr.n_total, generator=torch.Generator().manual_seed(100 + rank))
+    tr.overlap = False
+    works = []
+    tr._bucket_ready("head", works)
+    tr._bucket_ready(0, works)
+    tr._bucket_ready("tail", works)
+    for w in works:
+        w.wait()
+    out[rank] = (ok_overlap, torch.equal(tr.G, want), len(works))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bucketed_gradient_all_reduce():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bucket_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: (True, True, 1), 1: (True, True, 1)}
