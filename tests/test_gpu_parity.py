@@ -337,3 +337,37 @@ def test_full_size_seq2048_properties(full_pair):
     e = _err(one, want)
     print(f"C3 sequence 3 (T=2048) vs bf16-emulating oracle: max={e[0]:.3e} rms={e[1]:.3e}")
     assert e[0] <= 2 * TOL_EMU_FULL
+
+
+def test_full_size_training_gradients_vs_oracle(full_pair):
+    """configs[3] arithmetic at the reference size (24 layers, d=2048, 32 heads, vocab 32002) on the README-sized
+    input (B=1, T=114) where CPU autograd through the oracle finishes in seconds: loss and the gradient of every
+    trained parameter.  Tolerances as tests/test_gpu_train.py (bf16 operands, fp32 accumulate)."""
+    import kosmos_oracle as ko
+    from kosmosx import KosmosTrainer
+    ref, mine, oc = full_pair
+    text, images = ko.make_inputs(oc, 1, 50, seed=2)
+    trainer = KosmosTrainer(mine)
+    loss = trainer.loss_and_grads(text.cuda(), images.cuda())
+    torch.cuda.synchronize()
+    names = {id(p): n for n, p in mine.named_parameters()}
+    trained = {names[id(p)] for p in trainer.params}
+    for n, p in ref.named_parameters():
+        p.requires_grad_(n in trained)
+    ref.set_emulation(True)
+    want = ref.loss(text, images)
+    want.backward()
+    ref.set_emulation(False)
+    print(f"full-size training: loss cuda {loss.item():.5f} oracle {want.item():.5f}")
+    assert abs(loss.item() - want.item()) <= 1e-2
+    ref_named = dict(ref.named_parameters())
+    worst = (0.0, "")
+    for p in trainer.params:
+        n = names[id(p)]
+        g, g_ref = p.grad.detach().float().cpu(), ref_named[n].grad
+        rel = ((g - g_ref).norm() / (g_ref.norm() + 1e-12)).item()
+        worst = max(worst, (rel, n))
+        assert rel <= 6e-2, f"{n}: relative gradient error {rel:.3e}"
+    print(f"full-size training: {len(trainer.params)} gradient tensors, worst relative error {worst[0]:.3e} ({worst[1]})")
+    for p in ref.parameters():
+        p.grad = None
