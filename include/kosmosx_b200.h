@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 6   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 7   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -204,7 +204,7 @@ int kx_broadcast_rows(const float* src, float* dst, long long row_elems, int cop
  * kx_attn_fwd; dq/dk/dv are column blocks sharing ld_dqkv.  When the four xPos tables (kx_xpos_tables) are given,
  * dq and dk are returned as gradients of the UN-rotated projections (the transpose of the KX_EPI_QKV_XPOS rotation is
  * applied on the way out); NULL tables = plain attention.  Scratch: dq_accum fp32 [batch*seq_len, heads*64] (zeroed
- * by the call) and delta fp32 (same shape as lse).  Three kernels: delta = rowsum(dO*O), the main kernel (one CTA
+ * by the call) and delta fp32 (TWICE the size of lse: (-lse, -rowsum(dO*O)) pairs).  Three kernels: delta = rowsum(dO*O), the main kernel (one CTA
  * per (batch, head, 128-key block)), and the dq/dk finish.  Replaces autograd through bmm / softmax / bmm and
  * XPOS.forward of torchscale MultiheadAttention. */
 int kx_attn_fwd_lse(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
@@ -213,6 +213,10 @@ int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, c
                 const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv, long long ld_dqkv,
                 float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin, const float* xk_cos,
                 const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale, kx_stream_t stream);
+
+/* Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 int64 installed, CTA 0 of every launch records
+ * clock64 stamps [role: compute thread 0, MMA thread][iteration][point]; NULL = off. */
+int kx_attn_bwd_set_trace(long long* device_buffer);
 
 /* out = LayerNorm(act(x)) * gamma + beta in one pass, bf16 in / bf16 out (ffn_layernorm(gelu(fc1 x)), SURVEY A.4:
  * training keeps the pre-activation u, so GELU and the LayerNorm share one read of it).  n % 8 == 0, n <= 8192. */

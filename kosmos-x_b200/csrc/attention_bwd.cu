@@ -9,43 +9,68 @@
 //   S^T  = K_j . Q_i^T            SS   (A = K tile, B = Q tile, both K-major)                 -> TMEM [0,128)
 //   dP^T = V_j . dO_i^T           SS                                                          -> TMEM [128,256)
 //   P^T  = exp2(S^T*scale*log2e - lse_i)   dS^T = P^T * (dP^T - delta_i)                      (registers)
-//   dV_j += P^T . dO_i            TS   (A = P^T bf16 in TMEM over S^T, B = dO tile MN-major)  -> TMEM [256,320)
-//   dK_j += dS^T . Q_i            TS   (A = dS^T bf16 in TMEM over dP^T, B = Q tile MN-major) -> TMEM [320,384)
-//   dQ_i  = dS . K_j              SS   (A = dS^T staged in smem, read MN-major; B = K tile MN-major) -> TMEM [384,448)
-// dQ_i is added to an fp32 accumulator in global memory with vector atomics (the only cross-CTA reduction);
+//   dV_j += P^T . dO_i            TS   (A = P^T bf16 in TMEM [448,512), B = dO tile MN-major)  -> TMEM [256,320)
+//   dK_j += dS^T . Q_i            SS   (A = dS^T staged in smem, read K-major;  B = Q tile MN-major) -> TMEM [320,384)
+//   dQ_i  = dS . K_j              SS   (A = the same smem bytes, read MN-major; B = K tile MN-major) -> TMEM [384,448)
+// Neither S^T nor dP^T is overwritten by the compute warps, so the tensor core computes the scores of block i+1 while
+// block i is still in the softmax math (S^T / dP^T are released as soon as they are in registers).
+// dQ_i is added to an fp32 accumulator in global memory by TMA reduction (cp.reduce.async.bulk.tensor .add from a
+// swizzled smem staging tile: the only cross-CTA reduction, off the SM's load/store path);
 // dK_j / dV_j leave through the epilogue as bf16.  `scale` is applied on the way out.
-//   warps 0-7  compute: thread = key row (TMEM lane), warpgroup g owns query columns [64g, 64g+64)
-//   warp 8     TMA producer: K_j, V_j once; Q_i, dO_i, lse_i, delta_i through a 2-slot ring
-//   warp 9     MMA issuer (one elected thread)
+//   warps 0-15 compute: thread = key row (TMEM lane), warpgroup g owns query columns [32g, 32g+32); the per-element
+//              work is packed f32x2: one LDS.128 brings (-lse, -delta) of a query pair, then FFMA2, 2 x MUFU.EX2, FADD2,
+//              FMUL2 and two bf16x2 packs (the first version spent 13 instructions per element and was issue-bound
+//              with 2 warps per scheduler: ncu showed the tensor pipe 19 % busy)
+//   warp 16    TMA producer: K_j, V_j once; Q_i, dO_i and the (-lse, -delta) rows of block i through a 2-slot ring
+//   warp 17    MMA issuer (one elected thread).  Issue order per iteration: dV_i, S^T_{i+1}, dK_i, dP^T_{i+1}, dQ_i — the
+//              next block's scores are ready while the compute warps are still storing, and dQ leaves the critical path
+//   warps 20-23 dQ drain: TMEM -> swizzled smem staging -> TMA reduce-add, concurrent with the next block's softmax math
+//              (clock64 timeline, profiles/r1_attn_bwd_trace_*.txt: with the compute warps draining dQ themselves an
+//              iteration cost 4840 cycles, 1450 of them in the drain)
 #include "kx_internal.h"
 #include "ptx.cuh"
 
 namespace kx {
 
-constexpr int BW_THREADS = 384;
+constexpr int BW_THREADS = 768;                       // 6 warpgroups: 4 compute, 1 {TMA, MMA, 2 idle warps}, 1 dQ drain
+constexpr int BW_COMPUTE = 512;
+constexpr int BW_W_TMA = 16, BW_W_MMA = 17, BW_W_DRAIN = 20;
 constexpr int BW_TILE = 128 * 64 * 2;                 // [128 x 64] bf16
 constexpr int BW_SMEM_K = 0;
 constexpr int BW_SMEM_V = BW_SMEM_K + BW_TILE;
-constexpr int BW_SMEM_Q = BW_SMEM_V + BW_TILE;        // 2 slots
-constexpr int BW_SMEM_DO = BW_SMEM_Q + 2 * BW_TILE;   // 2 slots
-constexpr int BW_SMEM_DS = BW_SMEM_DO + 2 * BW_TILE;  // dS^T: 2 MN atoms of [128 keys][64 queries]
-constexpr int BW_SMEM_LSE = BW_SMEM_DS + 2 * BW_TILE; // [2][128] fp32
-constexpr int BW_SMEM_DELTA = BW_SMEM_LSE + 2 * 512;
-constexpr int BW_SMEM_BAR = BW_SMEM_DELTA + 2 * 512;
+constexpr int BW_SLOTS = 3;                           // Q / dO / (-lse, -delta) ring: a slot is released at the END of its iteration
+                                                      // (dK, dV read it last), so two slots exposed the whole TMA latency every block
+constexpr int BW_SMEM_Q = BW_SMEM_V + BW_TILE;
+constexpr int BW_SMEM_DO = BW_SMEM_Q + BW_SLOTS * BW_TILE;
+constexpr int BW_SMEM_DS = BW_SMEM_DO + BW_SLOTS * BW_TILE;  // dS^T: 2 MN atoms of [128 keys][64 queries]
+constexpr int BW_SMEM_DQ = BW_SMEM_DS + 2 * BW_TILE;  // dQ staging: 2 column halves of [128 queries][32 fp32], SWIZZLE_128B
+constexpr int BW_SMEM_LD = BW_SMEM_DQ + 2 * BW_TILE;  // [slots][128 queries] (-lse, -delta) fp32 pairs
+constexpr int BW_SMEM_BAR = BW_SMEM_LD + BW_SLOTS * 1024;
+static_assert(BW_SMEM_BAR + 128 <= 227 * 1024, "shared memory budget");
 constexpr int BW_SMEM_BYTES = BW_SMEM_BAR + 128;
 constexpr int BW_TMEM_COLS = 512;
-constexpr int BW_T_S = 0, BW_T_DP = 128, BW_T_DV = 256, BW_T_DK = 320, BW_T_DQ = 384;
+constexpr int BW_T_S = 0, BW_T_DP = 128, BW_T_DV = 256, BW_T_DK = 320, BW_T_DQ = 384, BW_T_P = 448;
 
 struct AttnBwdParams {
-    const float* lse;          // [heads][batch][t_pad], log2 units (kx_attn_fwd_lse)
-    const float* delta;        // [heads][batch][t_pad], rowsum(dO * O)
+    const float2* nld;         // [heads][batch][t_pad] pairs (-lse in log2 units, -rowsum(dO * O)), from attn_delta_kernel
     float* dq_accum;           // fp32 [batch*seq_len, heads*64]
     __nv_bfloat16* dk;
     __nv_bfloat16* dv;
     long long ld_dkv;
     int seq_len, heads, batch, t_pad;
     float scale, scale_log2;
+    long long* trace;          // TRACE builds only: clock64 stamps of CTA 0, [role: 0 compute thread 0, 1 MMA thread][iteration][16 points]
 };
+
+static long long* g_attn_bwd_trace = nullptr;         // kx_attn_bwd_set_trace
+
+#define KX_BT(role, iter, point)                                                                      \
+    do {                                                                                              \
+        if constexpr (TRACE) {                                                                        \
+            if (p.trace != nullptr && blockIdx.x == 0 && (iter) < 32)                                 \
+                p.trace[((role) * 32 + (iter)) * 16 + (point)] = clock64();                           \
+        }                                                                                             \
+    } while (0)
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -53,23 +78,25 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                  : "memory");
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool TRACE = false>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BW_SMEM_BAR);
     uint64_t* kv_full = bars + 0;
-    uint64_t* full = bars + 1;        // [2] Q/dO/lse/delta slot filled
-    uint64_t* empty = bars + 3;       // [2] slot consumed by the MMAs
-    uint64_t* bar_s = bars + 5;       // S^T complete
-    uint64_t* bar_dp = bars + 6;      // dP^T complete
-    uint64_t* bar_pds = bars + 7;     // P^T, dS^T written (256 compute threads)
-    uint64_t* bar_dq = bars + 8;      // dV, dK, dQ MMAs of the iteration complete
-    uint64_t* bar_dqr = bars + 9;     // dQ read out of TMEM (256 compute threads)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-    float* s_lse = reinterpret_cast<float*>(smem + BW_SMEM_LSE);
-    float* s_delta = reinterpret_cast<float*>(smem + BW_SMEM_DELTA);
+    uint64_t* full = bars + 1;        // [BW_SLOTS] Q/dO/lse/delta slot filled
+    uint64_t* empty = bars + 4;       // [BW_SLOTS] slot consumed by the MMAs
+    uint64_t* bar_s = bars + 7;       // S^T complete
+    uint64_t* bar_dp = bars + 8;      // dP^T complete
+    uint64_t* bar_pds = bars + 9;     // P^T, dS^T written (compute threads)
+    uint64_t* bar_dq = bars + 10;     // dV, dK, dQ MMAs of the iteration complete
+    uint64_t* bar_dqr = bars + 11;    // dQ read out of TMEM (128 drain threads)
+    uint64_t* bar_fin = bars + 12;    // every MMA of the CTA complete (epilogue may read dV, dK)
+    uint64_t* bar_sfree = bars + 13;  // S^T and dP^T are in registers (compute threads): the next scores may be issued
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    float4* s_ld = reinterpret_cast<float4*>(smem + BW_SMEM_LD);          // [2][64] {-lse0, -delta0, -lse1, -delta1}
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -87,12 +114,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023) { printf("kx attn_bwd: dynamic smem base not 1024-aligned\n"); __trap(); }
         mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_pds, 256); mbar_init(bar_dq, 1); mbar_init(bar_dqr, 256);
+        for (int s = 0; s < BW_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_pds, BW_COMPUTE); mbar_init(bar_dq, 1); mbar_init(bar_dqr, 128); mbar_init(bar_fin, 1); mbar_init(bar_sfree, BW_COMPUTE);
         fence_mbar_init();
     }
-    if (warp == 8) {
-        if (lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO); }
+    if (warp == BW_W_TMA) {
+        if (lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO); prefetch_tmap(&tmDQ); }
         tmem_alloc<1>(tmem_slot, BW_TMEM_COLS);
         tmem_relinquish<1>();
     }
@@ -101,25 +128,59 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (warp == 8) {
+    if (warp >= BW_W_DRAIN) {
+        // ================= dQ drain: thread = query row r =================
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const int sw = r & 7;
+        const bool issuer = (threadIdx.x == BW_W_DRAIN * 32);
+        for (int it = 0; it < n_it; ++it) {
+            const int i = i0 + it;
+            mbar_wait_lean(bar_dq, it & 1);
+            tc_fence_after();
+            if (issuer) tma_store_wait_read<0>();                    // the previous reduction has read the staging tiles
+            named_bar_sync(2, 128);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {                            // 16 columns at a time
+                uint32_t qv[16];
+                tmem_ld16(tmem_base + lane_addr + BW_T_DQ + h * 16, qv);
+                tmem_ld_wait();
+                uint8_t* dq_row = smem + BW_SMEM_DQ + (h >> 1) * BW_TILE + r * 128;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<float4*>(dq_row + ((((h & 1) * 4 + u) ^ sw) << 4)) =
+                        make_float4(__uint_as_float(qv[4 * u]) * p.scale, __uint_as_float(qv[4 * u + 1]) * p.scale,
+                                    __uint_as_float(qv[4 * u + 2]) * p.scale, __uint_as_float(qv[4 * u + 3]) * p.scale);
+            }
+            tc_fence_before();
+            mbar_arrive(bar_dqr);                                    // the next dQ MMA may overwrite the accumulator
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            // rows of the tile beyond T are exact zeros (their dS is masked); rows beyond the matrix are clipped by TMA
+            if (issuer) {
+                tma_reduce_add_2d(&tmDQ, smem + BW_SMEM_DQ, head * 64, row_base + i * 128);
+                tma_reduce_add_2d(&tmDQ, smem + BW_SMEM_DQ + BW_TILE, head * 64 + 32, row_base + i * 128);
+                tma_store_commit();
+            }
+        }
+        if (issuer) tma_store_wait<0>();
+    } else if (warp >= BW_W_TMA) {
+        if (warp == BW_W_TMA) {
             if (elect_one()) {
                 // ================= TMA producer =================
                 mbar_arrive_expect_tx(kv_full, 2 * BW_TILE);
                 tma_load_2d(&tmK, kv_full, smem + BW_SMEM_K, head * 64, row_base + j * 128, kEvictFirst);
                 tma_load_2d(&tmV, kv_full, smem + BW_SMEM_V, head * 64, row_base + j * 128, kEvictFirst);
                 for (int it = 0; it < n_it; ++it) {
-                    const int i = i0 + it, s = it & 1;
-                    mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[s], 2 * BW_TILE + 2 * 512);
+                    const int i = i0 + it, s = it % BW_SLOTS;
+                    mbar_wait_lean(&empty[s], ((it / BW_SLOTS) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[s], 2 * BW_TILE + 1024);
                     tma_load_2d(&tmQ, &full[s], smem + BW_SMEM_Q + s * BW_TILE, head * 64, row_base + i * 128, kEvictLast);
                     tma_load_2d(&tmDO, &full[s], smem + BW_SMEM_DO + s * BW_TILE, head * 64, row_base + i * 128, kEvictLast);
-                    bulk_load_1d(s_lse + s * 128, p.lse + vec_base + i * 128, 512, &full[s]);
-                    bulk_load_1d(s_delta + s * 128, p.delta + vec_base + i * 128, 512, &full[s]);
+                    bulk_load_1d(s_ld + s * 64, p.nld + vec_base + i * 128, 1024, &full[s]);
                 }
             }
-        } else if (warp == 9) {
+        } else if (warp == BW_W_MMA) {
             if (elect_one()) {
                 // ================= MMA issuer =================
                 constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);    // [keys x queries] = A(K-major) . B(K-major)^T
@@ -131,139 +192,174 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const uint64_t v_kmaj = make_desc_sw128(smem_u32(smem + BW_SMEM_V));
                 const uint64_t k_mn = make_desc_sw128(smem_u32(smem + BW_SMEM_K), BW_TILE);
                 const uint64_t ds_mn = make_desc_sw128(smem_u32(smem + BW_SMEM_DS), BW_TILE);   // LBO = 16 KB between the two query atoms
-                auto issue_scores = [&](int s) {
-                    const uint64_t q_kmaj = make_desc_sw128(smem_u32(smem + BW_SMEM_Q + s * BW_TILE));
-                    const uint64_t do_kmaj = make_desc_sw128(smem_u32(smem + BW_SMEM_DO + s * BW_TILE));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16<1>(t_s, k_kmaj + 2 * k, q_kmaj + 2 * k, idesc_s, k != 0);
-                    umma_commit(bar_s);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16<1>(t_dp, v_kmaj + 2 * k, do_kmaj + 2 * k, idesc_s, k != 0);
-                    umma_commit(bar_dp);
-                };
-                mbar_wait(kv_full, 0);
-                mbar_wait(&full[0], 0);
-                tc_fence_after();
-                issue_scores(0);
-                for (int it = 0; it < n_it; ++it) {
-                    const int s = it & 1;
-                    const uint64_t q_mn = make_desc_sw128(smem_u32(smem + BW_SMEM_Q + s * BW_TILE), BW_TILE);
-                    const uint64_t do_mn = make_desc_sw128(smem_u32(smem + BW_SMEM_DO + s * BW_TILE), BW_TILE);
-                    mbar_wait(bar_pds, it & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)          // 16 queries per step: 8 TMEM columns of bf16 pairs, 16 dO rows = 2 KB
-                        umma_bf16_ts(t_dv, t_s + k * 8, do_mn + k * 128, idesc_kv, (it > 0 || k > 0) ? 1u : 0u);
+                // Straight-line issue (a rolled loop made every UTCHMMA cost ~90 cycles on a scheduler shared with five busy
+                // warps); descriptors travel as (low, high) words so the unrolled steps need no 64-bit register pairs.
+                auto lo = [](uint64_t d) { return static_cast<uint32_t>(d); };
+                auto hi = [](uint64_t d) { return static_cast<uint32_t>(d >> 32); };
+                auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t astep, uint32_t bstep, int steps, uint32_t idesc, uint32_t acc0) {
+                    const uint32_t al = lo(a), ah = hi(a), bl = lo(b), bh = hi(b);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_bf16_ts(t_dk, t_dp + k * 8, q_mn + k * 128, idesc_kv, (it > 0 || k > 0) ? 1u : 0u);
-                    if (it > 0) {                        // dQ of the previous iteration has been read out of TMEM
-                        mbar_wait(bar_dqr, (it - 1) & 1);
-                        tc_fence_after();
-                    }
+                        if (k < steps) umma_bf16_lohi(d, al + k * astep, ah, bl + k * bstep, bh, idesc, (k > 0) ? 1u : acc0);
+                };
+                auto mma_ts = [&](uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t acc0) {
+                    const uint32_t bl = lo(b), bh = hi(b);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)          // 16 keys per step: 16 rows of dS^T / K = 2 KB
-                        umma_bf16<1>(t_dq, ds_mn + k * 128, k_mn + k * 128, idesc_dq, k != 0);
-                    umma_commit(bar_dq);
-                    umma_commit(&empty[s]);
-                    if (it + 1 < n_it) {
-                        mbar_wait(&full[s ^ 1], ((it + 1) >> 1) & 1);
+                    for (int k = 0; k < 8; ++k) umma_bf16_ts_lohi(d, a_tmem + k * 8, bl + k * 128, bh, idesc_kv, (k > 0) ? 1u : acc0);
+                };
+                const uint32_t slot_step = BW_TILE >> 4;           // descriptor address units (16 B) between ring slots
+                const uint64_t q_kmaj0 = make_desc_sw128(smem_u32(smem + BW_SMEM_Q));
+                const uint64_t do_kmaj0 = make_desc_sw128(smem_u32(smem + BW_SMEM_DO));
+                const uint64_t q_mn0 = make_desc_sw128(smem_u32(smem + BW_SMEM_Q), BW_TILE);
+                const uint64_t do_mn0 = make_desc_sw128(smem_u32(smem + BW_SMEM_DO), BW_TILE);
+                mbar_wait_lean(kv_full, 0);
+                mbar_wait_lean(&full[0], 0);
+                tc_fence_after();
+                mma_ss(t_s, k_kmaj, q_kmaj0, 2, 2, 4, idesc_s, 0u);
+                umma_commit(bar_s);
+                mma_ss(t_dp, v_kmaj, do_kmaj0, 2, 2, 4, idesc_s, 0u);
+                umma_commit(bar_dp);
+                const uint32_t t_p = tmem_base + BW_T_P;
+                const uint64_t ds_kmaj = make_desc_sw128(smem_u32(smem + BW_SMEM_DS));       // dS^T as a K-major A operand (rows = keys)
+                for (int it = 0; it < n_it; ++it) {
+                    const int s = it % BW_SLOTS, sn = (it + 1) % BW_SLOTS;
+                    const bool has_next = it + 1 < n_it;
+                    const uint32_t acc = it > 0 ? 1u : 0u;
+                    KX_BT(1, it, 0);
+                    if (has_next) {                      // scores of the next block as soon as this block's are in registers
+                        mbar_wait_lean(bar_sfree, it & 1);
+                        mbar_wait_lean(&full[sn], ((it + 1) / BW_SLOTS) & 1);
                         tc_fence_after();
-                        issue_scores(s ^ 1);
+                        mma_ss(t_s, k_kmaj, q_kmaj0 + sn * slot_step, 2, 2, 4, idesc_s, 0u);
+                        umma_commit(bar_s);
+                        mma_ss(t_dp, v_kmaj, do_kmaj0 + sn * slot_step, 2, 2, 4, idesc_s, 0u);
+                        umma_commit(bar_dp);
                     }
+                    KX_BT(1, it, 1);
+                    mbar_wait_lean(bar_pds, it & 1);
+                    tc_fence_after();
+                    KX_BT(1, it, 2);
+                    mma_ts(t_dv, t_p, do_mn0 + s * slot_step, acc);          // dV: 16 queries per step = 8 TMEM columns of bf16 pairs, 16 dO rows = 2 KB
+                    {                                                         // dK: A = dS^T from smem, K-major: 4 steps of 32 B in each 64-query atom
+                        const uint32_t al = lo(ds_kmaj), ah = hi(ds_kmaj);
+                        const uint64_t qm = q_mn0 + s * slot_step;
+                        const uint32_t bl = lo(qm), bh = hi(qm);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16_lohi(t_dk, al + (k >> 2) * slot_step + (k & 3) * 2, ah, bl + k * 128, bh, idesc_kv, (k > 0) ? 1u : acc);
+                    }
+                    KX_BT(1, it, 3);
+                    if (it > 0) {                        // dQ of the previous iteration has been read out of TMEM
+                        mbar_wait_lean(bar_dqr, (it - 1) & 1);
+                        tc_fence_after();
+                    }
+                    KX_BT(1, it, 4);
+                    mma_ss(t_dq, ds_mn, k_mn, 128, 128, 8, idesc_dq, 0u);   // dQ: 16 keys per step = 16 rows of dS^T (smem) / K = 2 KB
+                    umma_commit(bar_dq);                 // also: P^T and the smem copy of dS^T may be overwritten
+                    umma_commit(&empty[s]);
+                    if (!has_next) umma_commit(bar_fin);
+                    KX_BT(1, it, 5);
                 }
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        // ================= compute: thread = key row r (TMEM lane), warpgroup g = query column half =================
+        // ================= compute: thread = key row r (TMEM lane), warpgroup g = query column quarter =================
         const int g = warp >> 2;
         const int r = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const int kg = j * 128 + r;
-        const float sl2 = p.scale_log2;
-        uint8_t* ds_row = smem + BW_SMEM_DS + g * BW_TILE + r * 128;
+        const uint64_t sl2x2 = pack_f32x2(p.scale_log2, p.scale_log2);
         const int sw = r & 7;
+        // dS^T staging: queries [32g, 32g+32) = chunks 4*(g&1) .. +3 of row r in MN atom g>>1
+        uint8_t* ds_row = smem + BW_SMEM_DS + (g >> 1) * BW_TILE + r * 128;
+        const int ch0 = (g & 1) * 4;
 
         for (int it = 0; it < n_it; ++it) {
-            const int i = i0 + it, s = it & 1;
-            mbar_wait(&full[s], (it >> 1) & 1);                  // lse / delta of this query block are in smem
-            mbar_wait(bar_s, it & 1);
+            const int i = i0 + it, s = it % BW_SLOTS;
+            if (threadIdx.x == 0) KX_BT(0, it, 0);
+            mbar_wait_lean(&full[s], (it / BW_SLOTS) & 1);                  // (-lse, -delta) of this query block are in smem
+            mbar_wait_lean(bar_s, it & 1);
             tc_fence_after();
-            uint32_t sv[64], dpv[64];
-            tmem_ld32(tmem_base + lane_addr + BW_T_S + g * 64, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
-            tmem_ld32(tmem_base + lane_addr + BW_T_S + g * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
-            mbar_wait(bar_dp, it & 1);
-            tc_fence_after();
-            tmem_ld32(tmem_base + lane_addr + BW_T_DP + g * 64, reinterpret_cast<uint32_t(&)[32]>(dpv[0]));
-            tmem_ld32(tmem_base + lane_addr + BW_T_DP + g * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(dpv[32]));
-            tmem_ld_wait();
-            tc_fence_before();
-            named_bar_sync(1, 256);                              // both warpgroups hold S^T / dP^T: the regions may be overwritten
-
-            const float* lse = s_lse + s * 128 + g * 64;
-            const float* dl = s_delta + s * 128 + g * 64;
+            if (threadIdx.x == 0) KX_BT(0, it, 1);
+            const float4* ld = s_ld + s * 64 + g * 16;          // {-lse(q0), -lse(q1), -delta(q0), -delta(q1)} per query pair
             const bool edge = (CAUSAL && i == j) || (i * 128 + 128 > T) || (j * 128 + 128 > T);
-            uint32_t pp[32], dd[32];
+            mbar_wait_lean(bar_dp, it & 1);
+            tc_fence_after();
+            if (threadIdx.x == 0) KX_BT(0, it, 2);
+            uint32_t pp[16], dd[16];
+            // P^T = exp2(S^T * scale * log2e - lse), dS^T = P^T * (dP^T - delta) in fp32, both packed to bf16; masked entries
+            // of the diagonal / tail blocks become exact zeros.  Two 16-column halves: the live set has to fit the 80
+            // registers that 768 threads leave per thread.
 #pragma unroll
-            for (int c = 0; c < 64; c += 2) {
-                const float2 l2 = *reinterpret_cast<const float2*>(lse + c);
-                const float2 d2 = *reinterpret_cast<const float2*>(dl + c);
-                float p0 = ex2_approx(fmaf(__uint_as_float(sv[c]), sl2, -l2.x));
-                float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), sl2, -l2.y));
-                if (edge) {
-                    const int q0 = i * 128 + g * 64 + c;
-                    const bool ok0 = kg < T && q0 < T && (!CAUSAL || q0 >= kg);
-                    const bool ok1 = kg < T && q0 + 1 < T && (!CAUSAL || q0 + 1 >= kg);
-                    p0 = ok0 ? p0 : 0.f;
-                    p1 = ok1 ? p1 : 0.f;
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t sv[16], dpv[16];
+                tmem_ld16(tmem_base + lane_addr + BW_T_S + g * 32 + hf * 16, sv);
+                tmem_ld16(tmem_base + lane_addr + BW_T_DP + g * 32 + hf * 16, dpv);
+                tmem_ld_wait();
+                if (hf == 1) {                                    // S^T and dP^T of this block are in registers everywhere soon
+                    tc_fence_before();
+                    mbar_arrive(bar_sfree);
                 }
-                float ds0 = p0 * (__uint_as_float(dpv[c]) - d2.x);
-                float ds1 = p1 * (__uint_as_float(dpv[c + 1]) - d2.y);
-                if (edge) {                                       // garbage rows beyond T may hold inf/nan in dP or delta
-                    ds0 = (p0 == 0.f) ? 0.f : ds0;
-                    ds1 = (p1 == 0.f) ? 0.f : ds1;
+                if (!edge) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 l = ld[hf * 8 + c];
+                        float x0, x1;
+                        unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), sl2x2, pack_f32x2(l.x, l.y)), x0, x1);
+                        float e0, e1;
+                        if (c == 1 || c == 4 || c == 6) {             // 3 of 8 pairs on the FMA pipes: the loop is MUFU-bound otherwise
+                            exp2_poly_x2(x0, x1, e0, e1);
+                        } else {
+                            e0 = ex2_approx(x0);
+                            e1 = ex2_approx(x1);
+                        }
+                        const uint64_t t = fadd2(pack_f32x2(__uint_as_float(dpv[2 * c]), __uint_as_float(dpv[2 * c + 1])), pack_f32x2(l.z, l.w));
+                        float d0, d1;
+                        unpack_f32x2(fmul2(pack_f32x2(e0, e1), t), d0, d1);
+                        pp[hf * 8 + c] = pack_bf16(e0, e1);
+                        dd[hf * 8 + c] = pack_bf16(d0, d1);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 l = ld[hf * 8 + c];
+                        const int q0 = i * 128 + g * 32 + hf * 16 + 2 * c;
+                        const bool ok0 = kg < T && q0 < T && (!CAUSAL || q0 >= kg);
+                        const bool ok1 = kg < T && q0 + 1 < T && (!CAUSAL || q0 + 1 >= kg);
+                        const float p0 = ok0 ? ex2_approx(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, l.x)) : 0.f;
+                        const float p1 = ok1 ? ex2_approx(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, l.y)) : 0.f;
+                        // rows beyond T may hold inf / nan in dP or delta: never form 0 * nan
+                        const float d0 = ok0 ? p0 * (__uint_as_float(dpv[2 * c]) + l.z) : 0.f;
+                        const float d1 = ok1 ? p1 * (__uint_as_float(dpv[2 * c + 1]) + l.w) : 0.f;
+                        pp[hf * 8 + c] = pack_bf16(p0, p1);
+                        dd[hf * 8 + c] = pack_bf16(d0, d1);
+                    }
                 }
-                pp[c >> 1] = pack_bf16(p0, p1);
-                dd[c >> 1] = pack_bf16(ds0, ds1);
             }
-            tmem_st32(tmem_base + lane_addr + BW_T_S + g * 32, pp);        // P^T over S^T (bf16 pairs)
-            tmem_st32(tmem_base + lane_addr + BW_T_DP + g * 32, dd);       // dS^T over dP^T
+            if (threadIdx.x == 0) KX_BT(0, it, 4);
+            if (it > 0) mbar_wait_lean(bar_dq, (it - 1) & 1);               // dV_{i-1} / dK_{i-1} / dQ_{i-1} have consumed P^T and the smem dS^T
+            if (threadIdx.x == 0) KX_BT(0, it, 5);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch)                                  // dS^T row -> smem atom g, SWIZZLE_128B
-                *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) = make_uint4(dd[4 * ch], dd[4 * ch + 1], dd[4 * ch + 2], dd[4 * ch + 3]);
+            for (int ch = 0; ch < 4; ++ch)                                   // dS^T row -> smem (A of the dK and dQ MMAs), SWIZZLE_128B
+                *reinterpret_cast<uint4*>(ds_row + (((ch0 + ch) ^ sw) << 4)) = make_uint4(dd[4 * ch], dd[4 * ch + 1], dd[4 * ch + 2], dd[4 * ch + 3]);
+            fence_proxy_async_smem();
+            tmem_st16(tmem_base + lane_addr + BW_T_P + g * 16, pp);         // P^T (bf16 pairs), its own TMEM region
             tmem_st_wait();
             tc_fence_before();
-            fence_proxy_async_smem();
             mbar_arrive(bar_pds);
-
-            // ---- dQ_i (rows = queries now): TMEM -> fp32 accumulator in global memory
-            mbar_wait(bar_dq, it & 1);
-            tc_fence_after();
-            uint32_t qv[32];
-            tmem_ld32(tmem_base + lane_addr + BW_T_DQ + g * 32, qv);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(bar_dqr);
-            const int qg = i * 128 + r;
-            if (qg < T) {
-                float4* dst = reinterpret_cast<float4*>(p.dq_accum + static_cast<long long>(row_base + qg) * (p.heads * 64) + head * 64 + g * 32);
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    atomicAdd(dst + u, make_float4(__uint_as_float(qv[4 * u]) * p.scale, __uint_as_float(qv[4 * u + 1]) * p.scale,
-                                                   __uint_as_float(qv[4 * u + 2]) * p.scale, __uint_as_float(qv[4 * u + 3]) * p.scale));
-            }
+            if (threadIdx.x == 0) KX_BT(0, it, 6);
         }
-        // ---- epilogue: dV_j, dK_j (bar_dq of the last iteration covers every MMA)
+        // ---- epilogue: dV_j, dK_j
+        mbar_wait_lean(bar_fin, 0);
         tc_fence_after();
-        uint32_t vv[32], kk[32];
-        tmem_ld32(tmem_base + lane_addr + BW_T_DV + g * 32, vv);
-        tmem_ld32(tmem_base + lane_addr + BW_T_DK + g * 32, kk);
+        uint32_t vv[16], kk[16];
+        tmem_ld16(tmem_base + lane_addr + BW_T_DV + g * 16, vv);
+        tmem_ld16(tmem_base + lane_addr + BW_T_DK + g * 16, kk);
         tmem_ld_wait();
         if (kg < T) {
-            const long long off = static_cast<long long>(row_base + kg) * p.ld_dkv + head * 64 + g * 32;
+            const long long off = static_cast<long long>(row_base + kg) * p.ld_dkv + head * 64 + g * 16;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 uint4 a, c;
                 a.x = pack_bf16(__uint_as_float(vv[8 * u]), __uint_as_float(vv[8 * u + 1]));
                 a.y = pack_bf16(__uint_as_float(vv[8 * u + 2]), __uint_as_float(vv[8 * u + 3]));
@@ -282,13 +378,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<1>(tmem_base, BW_TMEM_COLS);
+    if (warp == BW_W_TMA) tmem_dealloc<1>(tmem_base, BW_TMEM_COLS);
 }
 
-// delta[h][b][t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (8 lanes per (row, head), 16-byte loads)
+// nld[h][b][t/2] = {-lse(t0), -lse(t1), -delta(t0), -delta(t1)}, delta = sum_d dO[b,t,h,d] * O[b,t,h,d]  (8 lanes per (row, head)).
+// Both come out negated so that the main kernel's packed FFMA2 / FADD2 take them as plain addends.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ld_o, const __nv_bfloat16* __restrict__ d_o, long long ld_do,
-                  float* __restrict__ delta, int batch, int heads, int seq_len, int t_pad) {
+                  const float* __restrict__ lse, float2* __restrict__ nld, int batch, int heads, int seq_len, int t_pad) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(batch) * seq_len * heads * 8;
     const bool active = idx < total;
@@ -312,7 +409,10 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ld_o, const __n
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     if (active && sub == 0) {
         const int b = static_cast<int>(row / seq_len), t = static_cast<int>(row - static_cast<long long>(b) * seq_len);
-        delta[(static_cast<long long>(head) * batch + b) * t_pad + t] = s;
+        const long long o_ = (static_cast<long long>(head) * batch + b) * t_pad + t;
+        float* dst = reinterpret_cast<float*>(nld) + ((o_ >> 1) << 2) + (o_ & 1);      // per query pair: {-lse0, -lse1, -delta0, -delta1}
+        dst[0] = -lse[o_];
+        dst[2] = -s;
     }
 }
 
@@ -367,6 +467,13 @@ attn_bwd_finish_kernel(const float* __restrict__ dq_accum, __nv_bfloat16* __rest
 
 using namespace kx;
 
+// Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 int64 installed, CTA 0 of every launch records
+// clock64 stamps [role: compute thread 0, MMA thread][iteration][point]; NULL = off.
+extern "C" int kx_attn_bwd_set_trace(long long* device_buffer) {
+    g_attn_bwd_trace = device_buffer;
+    return KX_OK;
+}
+
 extern "C" int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
                            const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv,
                            long long ld_dqkv, float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin,
@@ -387,7 +494,8 @@ extern "C" int kx_attn_bwd(const void* q, const void* k, const void* v, long lon
     const unsigned long long rows = static_cast<unsigned long long>(batch) * seq_len;
     const int nblk = (seq_len + 127) / 128;
     const int t_pad = nblk * 128;
-    CUtensorMap tq, tk, tv, tdo;
+    CUtensorMap tq, tk, tv, tdo, tdq;
+    if (!make_tmap_f32_2d(&tdq, dq_accum, (uint64_t)heads * 64, rows, (uint64_t)heads * 64 * 4, 32, 128)) return KX_ERR_TMAP;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
     if (!make_tmap_bf16_2d(&tk, k, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
     if (!make_tmap_bf16_2d(&tv, v, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
@@ -405,20 +513,25 @@ extern "C" int kx_attn_bwd(const void* q, const void* k, const void* v, long lon
     {
         const long long total = static_cast<long long>(rows) * heads * 8;
         attn_delta_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-            reinterpret_cast<const __nv_bfloat16*>(out), ld_out, reinterpret_cast<const __nv_bfloat16*>(d_out), ld_dout, delta,
-            batch, heads, seq_len, t_pad);
+            reinterpret_cast<const __nv_bfloat16*>(out), ld_out, reinterpret_cast<const __nv_bfloat16*>(d_out), ld_dout, lse,
+            reinterpret_cast<float2*>(delta), batch, heads, seq_len, t_pad);
         int st = check_launch("kx_attn_bwd (delta)");
         if (st != KX_OK) return st;
     }
     AttnBwdParams p;
-    p.lse = lse; p.delta = delta; p.dq_accum = dq_accum;
+    p.nld = reinterpret_cast<const float2*>(delta); p.dq_accum = dq_accum;
     p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.ld_dkv = ld_dqkv;
     p.seq_len = seq_len; p.heads = heads; p.batch = batch; p.t_pad = t_pad;
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+    p.trace = g_attn_bwd_trace;
     const long long ctas = static_cast<long long>(nblk) * heads * batch;
     if (ctas > 0x7fffffffLL) { set_error("kx_attn_bwd: too many tiles"); return KX_ERR_ARG; }
-    if (causal) attn_bwd_kernel<true><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
-    else attn_bwd_kernel<false><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, p);
+    if (causal && p.trace != nullptr) {           // profiling aid (kx_attn_bwd_set_trace): same kernel with clock64 stamps
+        static bool tattr = false;
+        if (!tattr) { cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_BYTES); tattr = true; }
+        attn_bwd_kernel<true, true><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, p);
+    } else if (causal) attn_bwd_kernel<true><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, p);
+    else attn_bwd_kernel<false><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, p);
     int st = check_launch("kx_attn_bwd");
     if (st != KX_OK) return st;
     {

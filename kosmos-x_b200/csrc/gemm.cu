@@ -716,6 +716,10 @@ bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_
                        uint32_t box_inner, uint32_t box_outer) {
     return make_tmap_2d(tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer);
 }
+bool make_tmap_f32_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+    return make_tmap_2d(tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
 
 template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmEpi& ep, int max_ctas,

@@ -56,11 +56,40 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
     __syncthreads();
 }
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float gelu_grad(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+// sums of four values over the CTA in one exchange (one __syncthreads pair): red holds 4 x 8 floats
+__device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& d, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[w] = a; red[8 + w] = b; red[16 + w] = c; red[24 + w] = d; }
+    __syncthreads();
+    a = 0.f; b = 0.f; c = 0.f; d = 0.f;
+#pragma unroll
+    for (int i = 0; i < ROW_THREADS / 32; ++i) { a += red[i]; b += red[8 + i]; c += red[16 + i]; d += red[24 + i]; }
+    __syncthreads();
+}
+
+// Phi(x) = 0.5 * (1 + erf(x / sqrt2)) with ONE MUFU: erfc(a) = 2^(-Q(a)), a = |x| / sqrt2, Q the degree-5 fit of
+// ptx.cuh's gelu_erf_x2 (max |erf error| 8.9e-7).  erff() costs ~25 FP32 instructions per element, which made the
+// GELU kernels issue-bound instead of HBM-bound.
+__device__ __forceinline__ float gelu_cdf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float q = fmaf(z, -0.003024620935320854f, 0.029882797971367836f);
+    q = fmaf(q, z, -0.14901681244373322f);
+    q = fmaf(q, z, -0.9183504581451416f);
+    q = fmaf(q, z, -1.6279104948043823f);
+    const float e = 0.5f * ex2_approx(q * z);               // 0.5 * erfc(|x| / sqrt2)
+    return x >= 0.f ? 1.0f - e : e;
+}
+__device__ __forceinline__ float gelu_exact(float x) { return x * gelu_cdf(x); }
+__device__ __forceinline__ float gelu_grad(float x) {       // Phi(x) + x * phi(x)
+    const float pdf = 0.3989422804014327f * ex2_approx(-0.72134752044448170368f * x * x);
+    return fmaf(x, pdf, gelu_cdf(x));
 }
 
 // ----------------------------------------------------------------------------- LN(gelu(u)) forward
@@ -72,37 +101,39 @@ act_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, in
                          int rows, int n) {
     __shared__ float red[16];
     const float inv_n = 1.0f / static_cast<float>(n);
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        float v[NCH][8];
-        float s = 0.f, dummy = 0.f;
+    uint4 raw[NCH];                                    // the next row's loads are in flight during this row's math
+    auto fetch = [&](int row) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            raw[c] = (row < rows && col < n) ? *reinterpret_cast<const uint4*>(x + row * ld_x + col) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    fetch(blockIdx.x);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        float v[NCH][8];
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[c]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 f = __bfloat1622float2(h[u]);
+                v[c][2 * u] = f.x; v[c][2 * u + 1] = f.y;
+            }
             if (col < n) {
-                load8(x + row * ld_x + col, v[c]);
                 if (act == KX_ACT_GELU)
 #pragma unroll
                     for (int u = 0; u < 8; ++u) v[c][u] = gelu_exact(v[c][u]);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) s += v[c][u];
-            } else {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[c][u] = 0.f;
+                for (int u = 0; u < 8; ++u) { s += v[c][u]; q = fmaf(v[c][u], v[c][u], q); }
             }
         }
-        block_sum2(s, dummy, red);
+        fetch(row + gridDim.x);
+        block_sum2(s, q, red);
         const float mean = s * inv_n;
-        float q = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-            if (col < n)
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { const float d = v[c][u] - mean; q = fmaf(d, d, q); }
-        }
-        dummy = 0.f;
-        block_sum2(q, dummy, red);
-        const float rstd = rsqrtf(q * inv_n + eps);
+        const float rstd = rsqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + eps);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int col = (threadIdx.x + c * ROW_THREADS) * 8;
@@ -119,169 +150,256 @@ act_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, in
 }
 
 // ----------------------------------------------------------------------------- LayerNorm backward
-// y = LN(a) * gamma + beta with a = act(x).  Given dy (bf16):
-//   g = dy * gamma;  da = rstd * (g - mean(g) - xhat * mean(g * xhat));  dx = da * act'(x)
+// y = LN(a) * gamma + beta with a = act(x).  Given dy (bf16), with g = dy * gamma:
+//   da = rstd * (g - mean(g) - xhat * mean(g * xhat));  dx = da * act'(x)
 //   d(gamma) += dy * xhat, d(beta) += dy  (per-CTA partials [grid][n], folded by colpartials_reduce_kernel)
+// One pass, ONE block reduction per row: sum a, sum a^2, sum g, sum g*a give mean, rstd and
+//   mean(g * xhat) = rstd * (sum(g*a) - mean * sum(g)) / n.
+// gamma lives in registers across rows; the next row's loads are issued before the reduction (NCH == 1); the three
+// column accumulators are registers for NCH == 1 and shared memory for wide rows (keeps two CTAs per SM at n = 8192).
 // DX_F32: dx is the fp32 residual-stream gradient: dx_out = dres + dx (dres may alias dx_out), an optional bf16 copy
 // dxb of dx_out is written (the A operand of the next backward GEMMs) and column sums of dx_out are accumulated as a
 // third partial (the bias gradient of the Linear whose output was added to the stream at this point).
 template <typename XT, bool DX_F32, int NCH>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, (NCH == 1) ? 3 : 2)
 layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, int act, const __nv_bfloat16* __restrict__ dy,
                      long long ld_dy, const float* __restrict__ gamma, float eps, const float* dres, long long ld_dres,
                      void* dx_out, long long ld_dx, __nv_bfloat16* __restrict__ dxb, long long ld_dxb,
                      float* __restrict__ part_gamma, float* __restrict__ part_beta, float* __restrict__ part_col,
                      int rows, int n) {
-    __shared__ float red[16];
+    constexpr bool SMEM_ACC = (NCH > 1);
+    constexpr bool PREFETCH = (NCH == 1);
+    extern __shared__ float s_acc[];                   // SMEM_ACC: [3][NCH * 2048]
+    __shared__ float red[32];
     const float inv_n = 1.0f / static_cast<float>(n);
-    float acc_g[NCH][8], acc_b[NCH][8], acc_c[NCH][8];
+    float acc_g[SMEM_ACC ? 1 : NCH][8], acc_b[SMEM_ACC ? 1 : NCH][8], acc_c[SMEM_ACC ? 1 : NCH][8];
+    float gm[NCH][8];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
+    for (int c = 0; c < NCH; ++c) {
+        const int col = (threadIdx.x + c * ROW_THREADS) * 8;
+        if (col < n) load8(gamma + col, gm[c]);
+        else
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { acc_g[c][u] = 0.f; acc_b[c][u] = 0.f; acc_c[c][u] = 0.f; }
+            for (int u = 0; u < 8; ++u) gm[c][u] = 0.f;
+        if constexpr (SMEM_ACC) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s_acc[k * NCH * 2048 + col + u] = 0.f;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc_g[c][u] = 0.f; acc_b[c][u] = 0.f; acc_c[c][u] = 0.f; }
+        }
+    }
+    // (each thread only ever touches its own columns of s_acc: no synchronisation needed for it)
 
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        float a[NCH][8], d[NCH][8];
-        float s1 = 0.f, s2 = 0.f;
+    float a[NCH][8], d[NCH][8], r[PREFETCH ? NCH : 1][8];
+    auto fetch = [&](int row) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-            if (col < n) {
+            if (row < rows && col < n) {
                 load8(x + row * ld_x + col, a[c]);
                 load8(dy + row * ld_dy + col, d[c]);
-                if (act == KX_ACT_GELU)
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) a[c][u] = gelu_exact(a[c][u]);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) s1 += a[c][u];
+                if constexpr (PREFETCH && DX_F32) {
+                    if (dres != nullptr) load8(dres + row * ld_dres + col, r[c]);
+                }
             } else {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { a[c][u] = 0.f; d[c][u] = 0.f; }
             }
         }
-        block_sum2(s1, s2, red);
-        const float mean = s1 * inv_n;
-        float q = 0.f, z = 0.f;
+    };
+    fetch(blockIdx.x);
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        // PREFETCH: a/d/r are about to be overwritten by the next row's loads, so this row moves to copies;
+        // otherwise the row is processed in place (wide rows: registers are the scarce resource)
+        float xa_s[PREFETCH ? NCH : 1][8], dy_s[PREFETCH ? NCH : 1][8], rr[PREFETCH ? NCH : 1][8];
+        float (*xa)[8];
+        float (*dyv)[8];
+        if constexpr (PREFETCH) { xa = xa_s; dyv = dy_s; } else { xa = a; dyv = d; }
+        float s1 = 0.f, s2 = 0.f, sg = 0.f, sga = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-            if (col < n)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { a[c][u] -= mean; q = fmaf(a[c][u], a[c][u], q); }
-        }
-        block_sum2(q, z, red);
-        const float rstd = rsqrtf(q * inv_n + eps);
-        float sg = 0.f, sgx = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-            if (col < n) {
-                float gm[8];
-                load8(gamma + col, gm);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const float xh = a[c][u] * rstd;
-                    a[c][u] = xh;                                   // keep xhat
-                    acc_g[c][u] = fmaf(d[c][u], xh, acc_g[c][u]);
-                    acc_b[c][u] += d[c][u];
-                    const float g = d[c][u] * gm[u];
-                    d[c][u] = g;                                    // keep g = dy * gamma
-                    sg += g;
-                    sgx = fmaf(g, xh, sgx);
-                }
+            for (int u = 0; u < 8; ++u) {
+                const float av = (act == KX_ACT_GELU) ? gelu_exact(a[c][u]) : a[c][u];
+                const float dv = d[c][u];
+                const float gv = dv * gm[c][u];
+                xa[c][u] = av; dyv[c][u] = dv;
+                s1 += av; s2 = fmaf(av, av, s2); sg += gv; sga = fmaf(gv, av, sga);
+                if constexpr (PREFETCH && DX_F32) rr[c][u] = r[c][u];
             }
         }
-        block_sum2(sg, sgx, red);
-        const float mg = sg * inv_n, mgx = sgx * inv_n;
+        if constexpr (PREFETCH) fetch(row + gridDim.x);          // next row's loads fly during the reduction and the stores
+        block_sum4(s1, s2, sg, sga, red);
+        const float mean = s1 * inv_n;
+        const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
+        const float mg = sg * inv_n;
+        const float mgx = rstd * (sga - mean * sg) * inv_n;       // mean(g * xhat)
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int col = (threadIdx.x + c * ROW_THREADS) * 8;
             if (col < n) {
-                float o[8];
+                float o[8], xh[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) o[u] = rstd * (d[c][u] - mg - a[c][u] * mgx);
+                for (int u = 0; u < 8; ++u) {
+                    xh[u] = (xa[c][u] - mean) * rstd;
+                    o[u] = rstd * (dyv[c][u] * gm[c][u] - mg - xh[u] * mgx);
+                }
                 if (act == KX_ACT_GELU) {
                     float xr[8];
-                    load8(x + row * ld_x + col, xr);                 // re-read (L1/L2 hit): keeps register pressure flat
+                    load8(x + row * ld_x + col, xr);                 // the pre-activation again (L1 / L2 hit)
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] *= gelu_grad(xr[u]);
                 }
+                float cs[8];
                 if constexpr (DX_F32) {
                     if (dres != nullptr) {
-                        float r[8];
-                        load8(dres + row * ld_dres + col, r);
+                        if constexpr (PREFETCH) {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) o[u] += r[u];
+                            for (int u = 0; u < 8; ++u) o[u] += rr[c][u];
+                        } else {
+                            float t[8];
+                            load8(dres + row * ld_dres + col, t);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) o[u] += t[u];
+                        }
                     }
                     store8(reinterpret_cast<float*>(dx_out) + row * ld_dx + col, o);
                     if (dxb != nullptr) store8(dxb + row * ld_dxb + col, o);
-                    if (part_col != nullptr)
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) acc_c[c][u] += o[u];
+                    for (int u = 0; u < 8; ++u) cs[u] = o[u];
                 } else {
                     store8(reinterpret_cast<__nv_bfloat16*>(dx_out) + row * ld_dx + col, o);
-                    if (part_col != nullptr) {
-                        // column sums of what the next GEMM reads: the bf16-rounded values
+                    // column sums of what the next GEMM reads: the bf16-rounded values
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) acc_c[c][u] += __bfloat162float(__float2bfloat16_rn(o[u]));
+                    for (int u = 0; u < 8; ++u) cs[u] = __bfloat162float(__float2bfloat16_rn(o[u]));
+                }
+                if constexpr (SMEM_ACC) {
+                    float* sg_ = s_acc + col;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        sg_[u] = fmaf(dyv[c][u], xh[u], sg_[u]);
+                        sg_[NCH * 2048 + u] += dyv[c][u];
+                        if (part_col != nullptr) sg_[2 * NCH * 2048 + u] += cs[u];
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        acc_g[c][u] = fmaf(dyv[c][u], xh[u], acc_g[c][u]);
+                        acc_b[c][u] += dyv[c][u];
+                        acc_c[c][u] += cs[u];
                     }
                 }
             }
         }
+        if constexpr (!PREFETCH) fetch(row + gridDim.x);
     }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int col = (threadIdx.x + c * ROW_THREADS) * 8;
         if (col < n) {
             const long long o = static_cast<long long>(blockIdx.x) * n + col;
-            store8(part_gamma + o, acc_g[c]);
-            store8(part_beta + o, acc_b[c]);
-            if (part_col != nullptr) store8(part_col + o, acc_c[c]);
+            if constexpr (SMEM_ACC) {
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = s_acc[col + u];
+                store8(part_gamma + o, t);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = s_acc[NCH * 2048 + col + u];
+                store8(part_beta + o, t);
+                if (part_col != nullptr) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = s_acc[2 * NCH * 2048 + col + u];
+                    store8(part_col + o, t);
+                }
+            } else {
+                store8(part_gamma + o, acc_g[c]);
+                store8(part_beta + o, acc_b[c]);
+                if (part_col != nullptr) store8(part_col + o, acc_c[c]);
+            }
         }
     }
 }
 
-// out[col] (+)= sum_p part[p][col]
+// out_k[col] (+)= sum_p part_k[p][col] for up to three partial matrices (blockIdx.y = k).  A CTA owns 32 columns; its 8
+// warps stride the partial rows (128-byte coalesced row segments, four loads in flight), then fold through smem.
 __global__ void __launch_bounds__(256)
-colpartials_reduce_kernel(const float* __restrict__ part, int parts, int n, float* __restrict__ out, int accumulate) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= n) return;
+colpartials_reduce_kernel(const float* __restrict__ part, long long part_stride, int parts, int n, float* out0, float* out1,
+                          float* out2, int accumulate) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const float* src = part + static_cast<long long>(blockIdx.y) * part_stride;
+    float* out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = 0;
-    for (; p + 3 < parts; p += 4) {
-        s0 += part[static_cast<long long>(p) * n + col];
-        s1 += part[static_cast<long long>(p + 1) * n + col];
-        s2 += part[static_cast<long long>(p + 2) * n + col];
-        s3 += part[static_cast<long long>(p + 3) * n + col];
+    if (col < n) {
+        int p = w;
+        for (; p + 24 < parts; p += 32) {
+            s0 += src[static_cast<long long>(p) * n + col];
+            s1 += src[static_cast<long long>(p + 8) * n + col];
+            s2 += src[static_cast<long long>(p + 16) * n + col];
+            s3 += src[static_cast<long long>(p + 24) * n + col];
+        }
+        for (; p < parts; p += 8) s0 += src[static_cast<long long>(p) * n + col];
     }
-    for (; p < parts; ++p) s0 += part[static_cast<long long>(p) * n + col];
-    const float s = (s0 + s1) + (s2 + s3);
-    out[col] = accumulate ? out[col] + s : s;
+    red[w][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && col < n) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][lane];
+        out[col] = accumulate ? out[col] + s : s;
+    }
 }
 
 // ----------------------------------------------------------------------------- column sums (bias gradients)
-// out[n] += sum_m x[m][n], x bf16.  Grid (ceil(N/256), row splits); a warp reads 64 consecutive columns of a row
-// (128 B), the four warp-columns of the CTA cover 256 columns, two row phases per CTA.
+// out[n] += sum_m x[m][n], x bf16.  Grid (ceil(N/256), row splits): a warp reads 256 consecutive columns of a row
+// (16 bytes per lane), the 8 warps of a CTA take 8 rows at a time, four row groups in flight per thread.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows, int n, float* __restrict__ out) {
-    __shared__ float red[2][256];
+    __shared__ float red[8][256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int col = blockIdx.x * 256 + (w & 3) * 64 + lane * 2;
-    const int phase = w >> 2;
+    const int col = blockIdx.x * 256 + lane * 8;
     const int rows_per = (rows + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
-    float a0 = 0.f, a1 = 0.f;
-    if (col < n) {
-        for (int r = r0 + phase; r < r1; r += 2) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + static_cast<long long>(r) * ld + col));
-            a0 += f.x; a1 += f.y;
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    if (col < n) {                                       // n % 8 == 0: a lane's 8 columns are all inside or all outside
+        int r = r0 + w;
+        for (; r + 24 < r1; r += 32) {
+            uint4 q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 8 * i) * ld + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[i]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 f = __bfloat1622float2(h[u]);
+                    acc[2 * u] += f.x; acc[2 * u + 1] += f.y;
+                }
+            }
+        }
+        for (; r < r1; r += 8) {
+            float v[8];
+            load8(x + static_cast<long long>(r) * ld + col, v);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] += v[u];
         }
     }
-    const int slot = (w & 3) * 64 + lane * 2;
-    red[phase][slot] = a0; red[phase][slot + 1] = a1;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) red[w][lane * 8 + u] = acc[u];
     __syncthreads();
     const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c < n) atomicAdd(out + c, red[0][threadIdx.x] + red[1][threadIdx.x]);
+    if (c < n) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+        atomicAdd(out + c, s);
+    }
 }
 
 // ----------------------------------------------------------------------------- xPos backward
@@ -528,7 +646,7 @@ using namespace kx;
 extern "C" int kx_ln_bwd_partials(int rows) {
     const int sms = device_sm_count();
     if (sms <= 0) return KX_ERR_NO_DEVICE;
-    return std::max(1, std::min(rows, sms * 2));
+    return std::max(1, std::min(rows, sms * 3));
 }
 
 extern "C" int kx_act_layernorm_fwd(const void* x_bf16, long long ld_x, int act, const float* gamma, const float* beta,
@@ -564,7 +682,7 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, in
     }
     const int sms = device_sm_count();
     if (sms <= 0) return KX_ERR_NO_DEVICE;
-    const int grid = std::max(1, std::min(rows, sms * 2));
+    const int grid = std::max(1, std::min(rows, sms * (n <= 2048 ? 3 : 2)));
     if (n_partials < grid) { set_error("kx_layernorm_bwd: partials buffer holds %d rows, needs kx_ln_bwd_partials(rows) = %d", n_partials, grid); return KX_ERR_ARG; }
     float* pg = partials;
     float* pb = partials + static_cast<long long>(grid) * n;
@@ -572,34 +690,38 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, in
     auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
     auto dxbp = reinterpret_cast<__nv_bfloat16*>(dxb_bf16);
 #define KX_LNB(XT, F32, NCH)                                                                                              \
-    layernorm_bwd_kernel<XT, F32, NCH><<<grid, ROW_THREADS, 0, stream>>>(reinterpret_cast<const XT*>(x), ld_x, act, dyp, ld_dy, \
-        gamma, eps, dres, ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n)
+    {                                                                                                                     \
+        constexpr int smem = (NCH > 1) ? 3 * NCH * 2048 * 4 : 0;                                                          \
+        auto kern = layernorm_bwd_kernel<XT, F32, NCH>;                                                                   \
+        if (smem + 1024 > 48 * 1024) {                                                                                    \
+            static bool attr = false;                                                                                     \
+            if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }    \
+        }                                                                                                                 \
+        kern<<<grid, ROW_THREADS, smem, stream>>>(reinterpret_cast<const XT*>(x), ld_x, act, dyp, ld_dy, gamma, eps, dres, \
+                                                  ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n);                 \
+    }
 #define KX_LNB_N(XT, F32)                                                                                                 \
-    { if (n <= 2048) KX_LNB(XT, F32, 1); else if (n <= 4096) KX_LNB(XT, F32, 2); else KX_LNB(XT, F32, 4); }
+    { if (n <= 2048) KX_LNB(XT, F32, 1) else if (n <= 4096) KX_LNB(XT, F32, 2) else KX_LNB(XT, F32, 4) }
     if (x_is_bf16) { if (dx_is_f32) KX_LNB_N(__nv_bfloat16, true) else KX_LNB_N(__nv_bfloat16, false) }
     else { if (dx_is_f32) KX_LNB_N(float, true) else KX_LNB_N(float, false) }
 #undef KX_LNB_N
 #undef KX_LNB
     int st = check_launch("kx_layernorm_bwd");
     if (st != KX_OK) return st;
-    const int rb = (n + 255) / 256;
-    colpartials_reduce_kernel<<<rb, 256, 0, stream>>>(pg, grid, n, d_gamma, accumulate);
-    colpartials_reduce_kernel<<<rb, 256, 0, stream>>>(pb, grid, n, d_beta, accumulate);
-    if (pc) colpartials_reduce_kernel<<<rb, 256, 0, stream>>>(pc, grid, n, d_colsum, accumulate);
-    st = check_launch("kx_layernorm_bwd (partials)");
-    if (st == KX_OK) count_launch(pc ? 2 : 1);
-    return st;
+    colpartials_reduce_kernel<<<dim3((n + 31) / 32, pc ? 3 : 2), 256, 0, stream>>>(pg, static_cast<long long>(grid) * n, grid, n,
+                                                                                   d_gamma, d_beta, d_colsum, accumulate);
+    return check_launch("kx_layernorm_bwd (partials)");
 }
 
 extern "C" int kx_colsum_bf16(const void* x_bf16, long long ld, int rows, int n, float* out, cudaStream_t stream) {
-    if (!x_bf16 || !out || rows <= 0 || n <= 0 || (n % 2) || (ld % 2) || (reinterpret_cast<uintptr_t>(x_bf16) & 3)) {
-        set_error("kx_colsum_bf16: bad argument (rows=%d n=%d)", rows, n);
+    if (!x_bf16 || !out || rows <= 0 || n <= 0 || (n % 8) || (ld % 8) || !KX_ALIGNED16(x_bf16)) {
+        set_error("kx_colsum_bf16: bad argument (rows=%d n=%d; n %% 8 == 0 and 16-byte aligned rows)", rows, n);
         return KX_ERR_ARG;
     }
     const int sms = device_sm_count();
     if (sms <= 0) return KX_ERR_NO_DEVICE;
     const int cb = (n + 255) / 256;
-    const int splits = std::max(1, std::min((rows + 63) / 64, (sms * 4 + cb - 1) / cb));
+    const int splits = std::max(1, std::min((rows + 63) / 64, (sms * 8 + cb - 1) / cb));
     colsum_bf16_kernel<<<dim3(cb, splits), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), ld, rows, n, out);
     return check_launch("kx_colsum_bf16");
 }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "kx_attn_fwd_lse": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _f32p, _vp]),
     "kx_attn_bwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _f32p, _vp, _vp, _vp, _ll, _f32p, _f32p,
                          _f32p, _f32p, _f32p, _f32p, _i, _i, _i, _i, _f, _vp]),
+    "kx_attn_bwd_set_trace": (_i, [_vp]),
     "kx_act_layernorm_fwd": (_i, [_vp, _ll, _i, _f32p, _f32p, _f, _vp, _ll, _i, _i, _vp]),
     "kx_ln_bwd_partials": (_i, [_i]),
     "kx_layernorm_bwd": (_i, [_vp, _i, _ll, _i, _vp, _ll, _f32p, _f, _f32p, _ll, _vp, _i, _ll, _vp, _ll, _f32p, _i,

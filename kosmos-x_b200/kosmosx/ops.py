@@ -173,7 +173,7 @@ def attention_bwd(q, k, v, out, d_out, lse, dq, dk, dv, dq_accum, delta, *, batc
     _req(lse, torch.float32, "lse"); _req(dq_accum, torch.float32, "dq_accum"); _req(delta, torch.float32, "delta")
     if not (q.stride(0) == k.stride(0) == v.stride(0)) or not (dq.stride(0) == dk.stride(0) == dv.stride(0)):
         raise ValueError("attention_bwd: q/k/v and dq/dk/dv must each share a row pitch")
-    if dq_accum.numel() != batch * seq_len * heads * 64 or delta.numel() != lse.numel():
+    if dq_accum.numel() != batch * seq_len * heads * 64 or delta.numel() != 2 * lse.numel():
         raise ValueError("attention_bwd: scratch buffers have the wrong size")
     tabs = [None] * 4 if xpos is None else [t.data_ptr() for t in xpos]
     fl = 10.0 * batch * heads * seq_len * seq_len * 64 * (0.5 if causal else 1.0)

@@ -247,7 +247,7 @@ class KosmosTrainer:
         datt = self._buf("datt", (M, D), bf)
         dqkv = self._buf("dqkv", (M, 3 * D), bf)
         dq_acc = self._buf("dq_acc", (M, D), f32)
-        delta = self._buf("delta", (H, B, ops.lse_pad(T)), f32)
+        delta = self._buf("delta", (H, B, ops.lse_pad(T), 2), f32)
         # LM head
         wout = m.output_projection.weight
         ops.gemm(dl, self._w16(wout), dh, b_trans=True)

@@ -220,7 +220,7 @@ def case_train_elementwise():
         ops.act_layernorm(u, gamma, beta, out)
         ok &= report(f"act_layernorm {rows}x{n}", out, F.layer_norm(F.gelu(u.float()), (n,), gamma, beta, 1e-5), 7e-2)   # bf16 output, |y| up to 12
     # ---- column sums
-    for (rows, n) in ((4096, 6144), (1000, 130), (77, 2048)):
+    for (rows, n) in ((4096, 6144), (1000, 136), (77, 2048)):
         xx = torch.randn(rows, n, device=dev).bfloat16()
         out = torch.ones(n, device=dev)
         ops.colsum(xx, out)
@@ -361,7 +361,7 @@ def case_attn_bwd():
         ok &= report(f"attn lse B={B} H={H} T={T}", lse[:, :, :T], lse_ref.transpose(0, 1), 2e-2)
         dqkv = torch.full((M, 3 * D), 9.0, device=dev, dtype=torch.bfloat16)
         acc = torch.empty(M, D, device=dev)
-        delta = torch.empty_like(lse)
+        delta = torch.empty(*lse.shape, 2, device=dev)
         ops.attention_bwd(qkv_rot[:, :D], qkv_rot[:, D:2 * D], qkv_rot[:, 2 * D:], out, d_out, lse, dqkv[:, :D], dqkv[:, D:2 * D],
                           dqkv[:, 2 * D:], acc, delta, batch=B, heads=H, seq_len=T, causal=causal, scale=scale, xpos=tabs)
         torch.cuda.synchronize()
@@ -680,6 +680,68 @@ def bench_attn(B, H, T, causal):
     fl = 2.0 * B * H * T * T * 64 * 2 / (2 if causal else 1)
     print(f"attn causal={causal} B={B} H={H} T={T}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s "
           f"({'causal-halved' if causal else 'full'}) impl={os.environ.get('KX_ATTN_IMPL', '1')}")
+    return True
+
+
+def _time(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def case_bench_train():
+    """Stand-alone timings of the training-step kernels at configs[3] shapes (M = 8 x 2048 rows)."""
+    B, H, T = 8, 32, 2048
+    D, F, M = H * 64, 8192, B * T
+    qkv = torch.randn(M, 3 * D, device=dev).bfloat16()
+    out = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(H, B, ops.lse_pad(T), device=dev)
+    ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125, lse_out=lse)
+    d_out = torch.randn(M, D, device=dev).bfloat16()
+    dqkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+    acc = torch.empty(M, D, device=dev); delta = torch.empty(*lse.shape, 2, device=dev)
+    ms = _time(lambda: ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, d_out, lse, dqkv[:, :D], dqkv[:, D:2 * D],
+                                         dqkv[:, 2 * D:], acc, delta, batch=B, heads=H, seq_len=T, causal=True, scale=0.125))
+    fl = 10.0 * B * H * T * T * 64 / 2
+    print(f"attn_bwd B={B} H={H} T={T}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s (causal-halved, 5 MMAs)")
+    # LayerNorm backward, residual form (n = 2048) and FFN form (n = 8192, GELU)
+    x = torch.randn(M, D, device=dev); dy = torch.randn(M, D, device=dev).bfloat16()
+    gamma = torch.ones(D, device=dev); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev); dc = torch.zeros(D, device=dev)
+    dx = torch.randn(M, D, device=dev); dxb = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    part = torch.empty(3, ops.ln_bwd_partials(M), D, device=dev)
+    ms = _time(lambda: ops.layernorm_bwd(x, dy, gamma, dx, dg, db, part, dres=dx, dxb=dxb, d_colsum=dc))
+    by = M * D * (4 + 2 + 4 + 4 + 2)
+    print(f"layernorm_bwd fp32 residual form {M}x{D}: {ms*1e3:.1f} us  {by/ms/1e6:.0f} GB/s")
+    u = torch.randn(M, F, device=dev).bfloat16(); dgl = torch.randn(M, F, device=dev).bfloat16()
+    gf = torch.ones(F, device=dev); dgf = torch.zeros(F, device=dev); dbf = torch.zeros(F, device=dev); dcf = torch.zeros(F, device=dev)
+    du = torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+    partf = torch.empty(3, ops.ln_bwd_partials(M), F, device=dev)
+    ms = _time(lambda: ops.layernorm_bwd(u, dgl, gf, du, dgf, dbf, partf, act=_abi.KX_ACT_GELU, d_colsum=dcf))
+    print(f"layernorm_bwd GELU form {M}x{F}: {ms*1e3:.1f} us  {M*F*6/ms/1e6:.0f} GB/s")
+    gl = torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+    ms = _time(lambda: ops.act_layernorm(u, gf, dbf, gl))
+    print(f"act_layernorm {M}x{F}: {ms*1e3:.1f} us  {M*F*4/ms/1e6:.0f} GB/s")
+    h = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    ms = _time(lambda: ops.layernorm(x, gamma, db, h))
+    print(f"layernorm fwd {M}x{D}: {ms*1e3:.1f} us  {M*D*6/ms/1e6:.0f} GB/s")
+    ms = _time(lambda: ops.colsum(dqkv, torch.zeros(3 * D, device=dev)))
+    print(f"colsum {M}x{3*D}: {ms*1e3:.1f} us")
+    # backward GEMMs
+    w1 = torch.randn(F, D, device=dev).bfloat16(); h2 = torch.randn(M, D, device=dev).bfloat16()
+    dh = torch.empty(M, D, device=dev, dtype=torch.bfloat16); dw = torch.empty(F, D, device=dev)
+    ms = _time(lambda: ops.gemm(du, w1, dh, b_trans=True))
+    print(f"dgrad {M}x{D}x{F}: {ms*1e3:.1f} us  {2.0*M*D*F/ms/1e9:.0f} TFLOP/s")
+    ms = _time(lambda: ops.gemm(du, h2, dw, a_trans=True, b_trans=True))
+    print(f"wgrad {F}x{D}x{M}: {ms*1e3:.1f} us  {2.0*M*D*F/ms/1e9:.0f} TFLOP/s")
+    wo = torch.randn(D, D, device=dev).bfloat16(); dwo = torch.empty(D, D, device=dev)
+    ms = _time(lambda: ops.gemm(dxb, h2, dwo, a_trans=True, b_trans=True))
+    print(f"wgrad {D}x{D}x{M}: {ms*1e3:.1f} us  {2.0*M*D*D/ms/1e9:.0f} TFLOP/s")
     return True
 
 
