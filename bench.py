@@ -193,11 +193,31 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def _init_dist(torch, kdist):
+    """Rendezvous + the first collective with fd 1 pointed at stderr: NCCL prints its version banner on stdout when the
+    communicator is created, and stdout must carry exactly one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local, world = kdist.init_from_env("nccl")
+        torch.cuda.set_device(local)
+        if world > 1:
+            t = torch.ones(1, device=torch.device("cuda", local))
+            torch.distributed.all_reduce(t)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return rank, local, world
+
+
 def run_gpu(args):
     import torch
     from kosmosx import Kosmos, KosmosConfig, ops
     from kosmosx import dist as kdist
-    rank, local, world = kdist.init_from_env("nccl")
+    rank, local, world = _init_dist(torch, kdist)
     if world != args.gpus:
         if rank == 0:
             print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun for N>1", file=sys.stderr)
@@ -454,7 +474,7 @@ def run_train(args):
     import torch
     from kosmosx import Kosmos, KosmosConfig
     from kosmosx import dist as kdist
-    rank, local, world = kdist.init_from_env("nccl")
+    rank, local, world = _init_dist(torch, kdist)
     args.gpus = world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

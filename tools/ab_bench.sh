@@ -6,7 +6,7 @@ out="gpurun_out/$tag"; mkdir -p "$out"
 for r in $(seq 1 "$rounds"); do
   for v in A B; do
     lib="${!v}"
-    KX_LIB="$lib" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > "$out/bench_${v}_$r.json" 2> "$out/bench_${v}_$r.err" || tail -3 "$out/bench_${v}_$r.err"
+    KX_LIB="$lib" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --train-leg 0 > "$out/bench_${v}_$r.json" 2> "$out/bench_${v}_$r.err" || tail -3 "$out/bench_${v}_$r.err"
     python - "$out/bench_${v}_$r.json" "$v" "$lib" <<'PY'
 import json, sys
 d = json.load(open(sys.argv[1]))
