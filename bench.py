@@ -439,8 +439,8 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
     step_flops = (3.0 * dec_flops + (162.02e9 + 4.115e9) * n_img) * B           # frozen vision side: forward only
     tfl = step_flops / (ms * 1e-3) / 1e12
     out = {"config": "configs[3]: data-parallel training step, B=%d per GPU, seq=2048, %d image(s)/seq, bf16 operands / fp32 "
-                     "master weights, %s, grad clip 1.0, decoder + LM head + embedding tables trained (CLIP, perceiver and "
-                     "image_proj frozen), no dropout, no activation recompute" % (B, n_img, optimizer),
+                     "master weights, %s, grad clip 1.0, decoder + LM head + embedding tables + perceiver resampler + image_proj "
+                     "trained (CLIP tower frozen), no dropout, no activation recompute" % (B, n_img, optimizer),
            "value": tokens / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "global_batch": B * world,
            "step_tflops_per_gpu": tfl, "step_frac_of_bf16_peak": {"burst": tfl / peaks["burst"], "sustained": tfl / peaks["sustained"]},
            "flops_per_step_per_gpu": step_flops,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 7   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 8   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -228,9 +228,11 @@ int kx_act_layernorm_fwd(const void* x_bf16, long long ld_x, int act, const floa
  * dx_is_f32 = 1: dx is the fp32 residual-stream gradient, dx = dres + (LN gradient) (dres NULL = none; may alias dx),
  * dxb (NULL or bf16) receives a copy and d_colsum (NULL or fp32 [n]) the column sums of dx — the bias gradient of the
  * Linear whose output was added to the stream there.  dx_is_f32 = 0: dx is bf16 (dres/dxb must be NULL), d_colsum sums
- * the stored bf16 values.  partials: fp32 scratch [3][kx_ln_bwd_partials(rows)][n].  accumulate = 1 adds into d_*. */
+ * the stored bf16 values.  partials: fp32 scratch [3][kx_ln_bwd_partials(rows)][n].  accumulate = 1 adds into d_*.
+ * pre_add (NULL or fp32 [n], n <= 2048, act none): the LayerNorm input is x + pre_add (the perceiver's
+ * `x + media_pos_emb[i]`; d_colsum is then the gradient of that table row when dres is NULL). */
 int kx_ln_bwd_partials(int rows);
-int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, int act, const void* dy_bf16, long long ld_dy,
+int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, int act, const void* dy_bf16, long long ld_dy,
                      const float* gamma, float eps, const float* dres, long long ld_dres, void* dx, int dx_is_f32,
                      long long ld_dx, void* dxb_bf16, long long ld_dxb, float* partials, int n_partials, float* d_gamma,
                      float* d_beta, float* d_colsum, int accumulate, int rows, int n, kx_stream_t stream);
@@ -257,6 +259,20 @@ int kx_ce_fwd_bwd(const float* logits, long long ld_logits, const long long* tok
  * dx0[row] for every row.  NULL tables are skipped. */
 int kx_embed_bwd(const float* dx0, const long long* tokens, int batch, int t_text, const int* host_img_rows, int img_count,
                  int n_img, int dim, int vocab, int padding_idx, float* d_embed, float* d_pos, kx_stream_t stream);
+
+/* Perceiver resampler pieces of the backward pass (flamingo_pytorch PerceiverResampler is trainable in the reference,
+ * model.py:196-203): the cross-attention backward (dq like q; dkv like kv, k and v blocks), the GELU of its
+ * feed-forward (which has no LayerNorm behind it), a row gather dst[r] (+)= src[(r/grp_rows)*grp_stride + grp_off +
+ * r%grp_rows] (fp32 or bf16 -> bf16: image rows of the decoder-input gradient; media / latent rows of the
+ * [media | latents] gradient) and a sum over rows in fp32 (gradient of the broadcast latents). */
+int kx_perceiver_xattn_bwd(const void* q, long long ld_q, const void* kv, long long ld_kv, int v_col_off, const void* out,
+                           long long ld_out, const void* d_out, long long ld_dout, void* dq, long long ld_dq, void* dkv,
+                           long long ld_dkv, int batch, int heads, int n_q, int n_kv, float scale, kx_stream_t stream);
+int kx_gelu_fwd(const void* u_bf16, void* out_bf16, long long n, kx_stream_t stream);
+int kx_gelu_bwd(const void* u_bf16, const void* dmid_bf16, void* du_bf16, long long n, kx_stream_t stream);
+int kx_gather_rows(const void* src, int src_is_f32, long long ld_src, void* dst_bf16, long long ld_dst, int rows, int n,
+                   int grp_rows, int grp_stride, int grp_off, int accumulate, kx_stream_t stream);
+int kx_sum_rows_f32(const float* src, long long ld, int rows, long long n, float* out, int accumulate, kx_stream_t stream);
 
 /* Gradient clipping (clip_grad_norm_, train.py:652-653) without a host sync: *out += sum g^2; then
  * scale = pre_scale * min(1, max_norm / (pre_scale * sqrt(sumsq) + 1e-6)), norm_out = pre_scale * sqrt(sumsq)

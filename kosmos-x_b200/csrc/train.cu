@@ -162,8 +162,9 @@ act_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, in
 // third partial (the bias gradient of the Linear whose output was added to the stream at this point).
 template <typename XT, bool DX_F32, int NCH>
 __global__ void __launch_bounds__(ROW_THREADS, (NCH == 1) ? 3 : 2)
-layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, int act, const __nv_bfloat16* __restrict__ dy,
-                     long long ld_dy, const float* __restrict__ gamma, float eps, const float* dres, long long ld_dres,
+layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ pre_add, int act,
+                     const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ gamma, float eps,
+                     const float* dres, long long ld_dres,
                      void* dx_out, long long ld_dx, __nv_bfloat16* __restrict__ dxb, long long ld_dxb,
                      float* __restrict__ part_gamma, float* __restrict__ part_beta, float* __restrict__ part_col,
                      int rows, int n) {
@@ -174,6 +175,10 @@ layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, int act, const __
     const float inv_n = 1.0f / static_cast<float>(n);
     float acc_g[SMEM_ACC ? 1 : NCH][8], acc_b[SMEM_ACC ? 1 : NCH][8], acc_c[SMEM_ACC ? 1 : NCH][8];
     float gm[NCH][8];
+    float pa[(NCH == 1) ? 1 : 1][8];                   // pre_add row (x + media_pos_emb[i] of the perceiver): narrow rows only
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pa[0][u] = 0.f;
+    if (NCH == 1 && pre_add != nullptr && threadIdx.x * 8 < n) load8(pre_add + threadIdx.x * 8, pa[0]);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const int col = (threadIdx.x + c * ROW_THREADS) * 8;
@@ -223,7 +228,8 @@ layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, int act, const __
         for (int c = 0; c < NCH; ++c) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const float av = (act == KX_ACT_GELU) ? gelu_exact(a[c][u]) : a[c][u];
+                float av = (act == KX_ACT_GELU) ? gelu_exact(a[c][u]) : a[c][u];
+                if constexpr (NCH == 1) av += pa[0][u];
                 const float dv = d[c][u];
                 const float gv = dv * gm[c][u];
                 xa[c][u] = av; dyv[c][u] = dv;
@@ -615,6 +621,63 @@ lion_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
+// ----------------------------------------------------------------------------- perceiver feed-forward GELU (no LayerNorm behind it)
+// mid = gelu(u);  du = dmid * gelu'(u)   (bf16, 8 elements per thread)
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ out, long long nvec) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float v[8];
+        load8(u + i * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = gelu_exact(v[k]);
+        store8(out + i * 8, v);
+    }
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ dmid, __nv_bfloat16* __restrict__ du, long long nvec) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float v[8], d[8];
+        load8(u + i * 8, v);
+        load8(dmid + i * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] *= gelu_grad(v[k]);
+        store8(du + i * 8, d);
+    }
+}
+
+// dst[r] (+)= src[(r / grp_rows) * grp_stride + grp_off + r % grp_rows]  (bf16 dst; src fp32 or bf16): picks the image rows
+// out of the decoder-input gradient, and the media / latent rows out of the [media | latents] gradient of the resampler.
+template <typename ST>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const ST* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst, long long ld_dst, int rows, int n,
+                   int grp_rows, int grp_stride, int grp_off, int accumulate) {
+    const int vec_per_row = n >> 3;
+    const long long total = static_cast<long long>(rows) * vec_per_row;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / vec_per_row), col = static_cast<int>(i - static_cast<long long>(r) * vec_per_row) * 8;
+        const long long sr = grp_rows > 0 ? static_cast<long long>(r / grp_rows) * grp_stride + grp_off + r % grp_rows : r;
+        float v[8];
+        load8(src + sr * ld_src + col, v);
+        if (accumulate) {
+            float o[8];
+            load8(dst + static_cast<long long>(r) * ld_dst + col, o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += o[k];
+        }
+        store8(dst + static_cast<long long>(r) * ld_dst + col, v);
+    }
+}
+
+// out[c] (+)= sum_r src[r][c]  (fp32; gradient of the broadcast perceiver latents: sum over the images)
+__global__ void __launch_bounds__(256)
+sum_rows_f32_kernel(const float* __restrict__ src, long long ld, int rows, long long n, float* __restrict__ out, int accumulate) {
+    const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (c >= n) return;
+    float s = accumulate ? out[c] : 0.f;
+    for (int r = 0; r < rows; ++r) s += src[static_cast<long long>(r) * ld + c];
+    out[c] = s;
+}
+
 static int grid_for(long long n, int sms, int per_thread = 1) {
     const long long blocks = (n / per_thread + 255) / 256;
     return static_cast<int>(std::max<long long>(1, std::min<long long>(blocks, static_cast<long long>(sms) * 8)));
@@ -668,7 +731,7 @@ extern "C" int kx_act_layernorm_fwd(const void* x_bf16, long long ld_x, int act,
     return check_launch("kx_act_layernorm_fwd");
 }
 
-extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, int act, const void* dy_bf16, long long ld_dy,
+extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, int act, const void* dy_bf16, long long ld_dy,
                                 const float* gamma, float eps, const float* dres, long long ld_dres, void* dx,
                                 int dx_is_f32, long long ld_dx, void* dxb_bf16, long long ld_dxb, float* partials,
                                 int n_partials, float* d_gamma, float* d_beta, float* d_colsum, int accumulate, int rows,
@@ -676,7 +739,8 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, in
     if (!x || !dy_bf16 || !gamma || !dx || !partials || !d_gamma || !d_beta || rows <= 0 || n <= 0 || (n % 8) || n > 8192 ||
         (ld_x % 8) || (ld_dy % 8) || (ld_dx % 8) || !KX_ALIGNED16(x) || !KX_ALIGNED16(dy_bf16) || !KX_ALIGNED16(dx) ||
         !KX_ALIGNED16(gamma) || !KX_ALIGNED16(partials) || (dres && (!KX_ALIGNED16(dres) || (ld_dres % 4) || !dx_is_f32)) ||
-        (dxb_bf16 && (!KX_ALIGNED16(dxb_bf16) || (ld_dxb % 8) || !dx_is_f32)) || (act != KX_ACT_NONE && act != KX_ACT_GELU)) {
+        (dxb_bf16 && (!KX_ALIGNED16(dxb_bf16) || (ld_dxb % 8) || !dx_is_f32)) || (act != KX_ACT_NONE && act != KX_ACT_GELU) ||
+        (pre_add && (n > 2048 || act != KX_ACT_NONE || !KX_ALIGNED16(pre_add)))) {
         set_error("kx_layernorm_bwd: bad argument (rows=%d n=%d; n %% 8 == 0, n <= 8192, 16-byte aligned rows; dres / dxb need fp32 dx)", rows, n);
         return KX_ERR_ARG;
     }
@@ -697,7 +761,7 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, in
             static bool attr = false;                                                                                     \
             if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }    \
         }                                                                                                                 \
-        kern<<<grid, ROW_THREADS, smem, stream>>>(reinterpret_cast<const XT*>(x), ld_x, act, dyp, ld_dy, gamma, eps, dres, \
+        kern<<<grid, ROW_THREADS, smem, stream>>>(reinterpret_cast<const XT*>(x), ld_x, pre_add, act, dyp, ld_dy, gamma, eps, dres, \
                                                   ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n);                 \
     }
 #define KX_LNB_N(XT, F32)                                                                                                 \
@@ -811,4 +875,47 @@ extern "C" int kx_lion_step(float* p, const float* g, float* m, void* w_bf16, lo
     lion_kernel<<<grid_for(n, sms), 256, 0, stream>>>(p, g, m, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, lr, beta1, beta2,
                                                       weight_decay, grad_scale);
     return check_launch("kx_lion_step");
+}
+
+extern "C" int kx_gelu_fwd(const void* u_bf16, void* out_bf16, long long n, cudaStream_t stream) {
+    if (!u_bf16 || !out_bf16 || n <= 0 || (n % 8) || !KX_ALIGNED16(u_bf16) || !KX_ALIGNED16(out_bf16)) { set_error("kx_gelu_fwd: bad argument"); return KX_ERR_ARG; }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    gelu_fwd_kernel<<<grid_for(n / 8, sms), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 8);
+    return check_launch("kx_gelu_fwd");
+}
+
+extern "C" int kx_gelu_bwd(const void* u_bf16, const void* dmid_bf16, void* du_bf16, long long n, cudaStream_t stream) {
+    if (!u_bf16 || !dmid_bf16 || !du_bf16 || n <= 0 || (n % 8) || !KX_ALIGNED16(u_bf16) || !KX_ALIGNED16(dmid_bf16) || !KX_ALIGNED16(du_bf16)) {
+        set_error("kx_gelu_bwd: bad argument");
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    gelu_bwd_kernel<<<grid_for(n / 8, sms), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u_bf16), reinterpret_cast<const __nv_bfloat16*>(dmid_bf16),
+                                                              reinterpret_cast<__nv_bfloat16*>(du_bf16), n / 8);
+    return check_launch("kx_gelu_bwd");
+}
+
+extern "C" int kx_gather_rows(const void* src, int src_is_f32, long long ld_src, void* dst_bf16, long long ld_dst, int rows, int n,
+                              int grp_rows, int grp_stride, int grp_off, int accumulate, cudaStream_t stream) {
+    if (!src || !dst_bf16 || rows <= 0 || n <= 0 || (n % 8) || (ld_src % 8) || (ld_dst % 8) || !KX_ALIGNED16(src) || !KX_ALIGNED16(dst_bf16) ||
+        grp_rows < 0) {
+        set_error("kx_gather_rows: bad argument (n %% 8 == 0, 16-byte aligned rows)");
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const long long total = static_cast<long long>(rows) * (n / 8);
+    auto d = reinterpret_cast<__nv_bfloat16*>(dst_bf16);
+    if (src_is_f32) gather_rows_kernel<float><<<grid_for(total, sms), 256, 0, stream>>>(reinterpret_cast<const float*>(src), ld_src, d, ld_dst, rows, n, grp_rows, grp_stride, grp_off, accumulate);
+    else gather_rows_kernel<__nv_bfloat16><<<grid_for(total, sms), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld_src, d, ld_dst, rows, n, grp_rows, grp_stride, grp_off, accumulate);
+    return check_launch("kx_gather_rows");
+}
+
+extern "C" int kx_sum_rows_f32(const float* src, long long ld, int rows, long long n, float* out, int accumulate, cudaStream_t stream) {
+    if (!src || !out || rows <= 0 || n <= 0) { set_error("kx_sum_rows_f32: bad argument"); return KX_ERR_ARG; }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    sum_rows_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, ld, rows, n, out, accumulate);
+    return check_launch("kx_sum_rows_f32");
 }

@@ -67,8 +67,13 @@ SIGNATURES = {
     "kx_attn_bwd_set_trace": (_i, [_vp]),
     "kx_act_layernorm_fwd": (_i, [_vp, _ll, _i, _f32p, _f32p, _f, _vp, _ll, _i, _i, _vp]),
     "kx_ln_bwd_partials": (_i, [_i]),
-    "kx_layernorm_bwd": (_i, [_vp, _i, _ll, _i, _vp, _ll, _f32p, _f, _f32p, _ll, _vp, _i, _ll, _vp, _ll, _f32p, _i,
+    "kx_layernorm_bwd": (_i, [_vp, _i, _ll, _f32p, _i, _vp, _ll, _f32p, _f, _f32p, _ll, _vp, _i, _ll, _vp, _ll, _f32p, _i,
                               _f32p, _f32p, _f32p, _i, _i, _i, _vp]),
+    "kx_perceiver_xattn_bwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
+    "kx_gelu_fwd": (_i, [_vp, _vp, _ll, _vp]),
+    "kx_gelu_bwd": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "kx_gather_rows": (_i, [_vp, _i, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    "kx_sum_rows_f32": (_i, [_f32p, _ll, _i, _ll, _f32p, _i, _vp]),
     "kx_colsum_bf16": (_i, [_vp, _ll, _i, _i, _f32p, _vp]),
     "kx_xpos_bwd": (_i, [_vp, _ll, _i, _i, _i, _f32p, _f32p, _f32p, _f32p, _vp]),
     "kx_ce_fwd_bwd": (_i, [_f32p, _ll, _vp, _i, _i, C.POINTER(_i), _i, _i, _i, _f, _vp, _ll, _f32p, _vp, _vp]),

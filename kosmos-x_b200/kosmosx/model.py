@@ -470,8 +470,26 @@ class Kosmos(_KosmosBase):
         self.eval()
 
     # ---- staging ------------------------------------------------------------------------
+    def _pack_resampler(self):
+        """Staged weights of the perceiver resampler + image_proj (re-derived alone after a training step)."""
+        cfg = self.cfg
+        pl = []
+        for attn, ff in self.perceive.layers:
+            pl.append(dict(
+                nm=(_f32(attn.norm_media.weight), _f32(attn.norm_media.bias)),
+                nl=(_f32(attn.norm_latents.weight), _f32(attn.norm_latents.bias)),
+                w_q=_bf16(attn.to_q.weight), w_kv=_bf16(attn.to_kv.weight), w_out=_bf16(attn.to_out.weight),
+                ff_ln=(_f32(ff[0].weight), _f32(ff[0].bias)), w_ff1=_bf16(ff[1].weight), w_ff2=_bf16(ff[3].weight),
+            ))
+        return dict(p_layers=pl, latents=_f32(self.perceive.latents),
+                    media_pos=_f32(self.perceive.media_pos_emb).view(-1, cfg.vit_dim),
+                    p_norm=(_f32(self.perceive.norm.weight), _f32(self.perceive.norm.bias)), w_ip=_bf16(self.image_proj.weight))
+
     def _pack_vision(self):
         if self._vis_packed is not None:
+            if getattr(self, "_resampler_dirty", False):
+                self._vis_packed.update(self._pack_resampler())
+                self._resampler_dirty = False
             return self._vis_packed
         cfg, cm = self.cfg, self.clip_model
         _require_cuda(cm.pre_layrnorm.weight, "Kosmos parameters")
@@ -490,23 +508,14 @@ class Kosmos(_KosmosBase):
                 fc1=_fold_ln(L.mlp.fc1.weight, L.mlp.fc1.bias, L.layer_norm2),
                 w_fc2=_bf16(L.mlp.fc2.weight), b_fc2=_f32(L.mlp.fc2.bias),
             ))
-        pl = []
-        for attn, ff in self.perceive.layers:
-            pl.append(dict(
-                nm=(_f32(attn.norm_media.weight), _f32(attn.norm_media.bias)),
-                nl=(_f32(attn.norm_latents.weight), _f32(attn.norm_latents.bias)),
-                w_q=_bf16(attn.to_q.weight), w_kv=_bf16(attn.to_kv.weight), w_out=_bf16(attn.to_out.weight),
-                ff_ln=(_f32(ff[0].weight), _f32(ff[0].bias)), w_ff1=_bf16(ff[1].weight), w_ff2=_bf16(ff[3].weight),
-            ))
         self._vis_packed = dict(
             k_pad=k_pad, w_patch=_bf16(wp), cls=_f32(cm.embeddings.class_embedding),
             vpos=_f32(cm.embeddings.position_embedding.weight),
             pre_ln=(_f32(cm.pre_layrnorm.weight), _f32(cm.pre_layrnorm.bias)),
-            layers=layers, p_layers=pl,
-            latents=_f32(self.perceive.latents), media_pos=_f32(self.perceive.media_pos_emb).view(-1, cfg.vit_dim),
-            p_norm=(_f32(self.perceive.norm.weight), _f32(self.perceive.norm.bias)),
-            w_ip=_bf16(self.image_proj.weight),
+            layers=layers,
         )
+        self._vis_packed.update(self._pack_resampler())
+        self._resampler_dirty = False
         return self._vis_packed
 
     # ---- stages -------------------------------------------------------------------------

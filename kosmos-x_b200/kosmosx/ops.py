@@ -200,20 +200,59 @@ def ln_bwd_partials(rows: int) -> int:
 
 
 def layernorm_bwd(x, dy, gamma, dx, d_gamma, d_beta, partials, *, act=_abi.KX_ACT_NONE, eps=1e-5, dres=None, dxb=None,
-                  d_colsum=None, accumulate=False):
+                  d_colsum=None, accumulate=False, pre_add=None):
     """LayerNorm (+GELU) backward; see kx_layernorm_bwd.  partials: fp32 [3, ln_bwd_partials(rows), n]."""
     _req(dy, torch.bfloat16, "dy")
     rows, n = x.shape
     if partials.ndim != 3 or partials.shape[0] != 3 or partials.shape[2] != n or not partials.is_contiguous():
         raise ValueError("layernorm_bwd: partials must be contiguous fp32 [3, P, n]")
     with _Timed("layernorm_bwd", 0.0, float(rows) * n * (x.element_size() + 2 + dx.element_size())):
-        check(lib.kx_layernorm_bwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), act, dy.data_ptr(),
+        check(lib.kx_layernorm_bwd(x.data_ptr(), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _ptr(pre_add), act, dy.data_ptr(),
                                    dy.stride(0), gamma.data_ptr(), float(eps), _ptr(dres), 0 if dres is None else dres.stride(0),
                                    dx.data_ptr(), 1 if dx.dtype == torch.float32 else 0, dx.stride(0), _ptr(dxb),
                                    0 if dxb is None else dxb.stride(0), partials.data_ptr(), partials.shape[1],
                                    d_gamma.data_ptr(), d_beta.data_ptr(), _ptr(d_colsum), 1 if accumulate else 0, rows, n,
                                    _stream()), "kx_layernorm_bwd")
     return dx
+
+
+def perceiver_attention_bwd(q, kv, out, d_out, dq, dkv, *, batch, heads, n_q, n_kv, v_col_off, scale):
+    for n, t in (("q", q), ("kv", kv), ("out", out), ("d_out", d_out), ("dq", dq), ("dkv", dkv)):
+        _req(t, torch.bfloat16, n)
+    with _Timed("perceiver_xattn_bwd", 10.0 * batch * heads * n_q * n_kv * 64):
+        check(lib.kx_perceiver_xattn_bwd(q.data_ptr(), q.stride(0), kv.data_ptr(), kv.stride(0), v_col_off, out.data_ptr(),
+                                         out.stride(0), d_out.data_ptr(), d_out.stride(0), dq.data_ptr(), dq.stride(0),
+                                         dkv.data_ptr(), dkv.stride(0), batch, heads, n_q, n_kv, float(scale), _stream()),
+              "kx_perceiver_xattn_bwd")
+
+
+def gelu_fwd(u, out):
+    _req(u, torch.bfloat16, "u"); _req(out, torch.bfloat16, "out")
+    check(lib.kx_gelu_fwd(u.data_ptr(), out.data_ptr(), u.numel(), _stream()), "kx_gelu_fwd")
+    return out
+
+
+def gelu_bwd(u, dmid, du):
+    for n, t in (("u", u), ("dmid", dmid), ("du", du)):
+        _req(t, torch.bfloat16, n)
+    check(lib.kx_gelu_bwd(u.data_ptr(), dmid.data_ptr(), du.data_ptr(), u.numel(), _stream()), "kx_gelu_bwd")
+    return du
+
+
+def gather_rows(src, dst, *, grp=None, accumulate=False):
+    """dst[r] (+)= src[(r // grp_rows) * grp_stride + grp_off + r % grp_rows]; src fp32 or bf16, dst bf16."""
+    _req(dst, torch.bfloat16, "dst")
+    g = grp or (0, 0, 0)
+    check(lib.kx_gather_rows(src.data_ptr(), 1 if src.dtype == torch.float32 else 0, src.stride(0), dst.data_ptr(), dst.stride(0),
+                             dst.shape[0], dst.shape[1], g[0], g[1], g[2], 1 if accumulate else 0, _stream()), "kx_gather_rows")
+    return dst
+
+
+def sum_rows_f32(src, out, *, accumulate=False):
+    _req(src, torch.float32, "src"); _req(out, torch.float32, "out")
+    check(lib.kx_sum_rows_f32(src.data_ptr(), src.stride(0), src.shape[0], src.shape[1], out.data_ptr(), 1 if accumulate else 0,
+                              _stream()), "kx_sum_rows_f32")
+    return out
 
 
 def colsum(x, out):

@@ -11,10 +11,10 @@ Everything arithmetic is a C-ABI call (ops.*): the training forward keeps what b
 are materialised instead of folded, the FFN keeps its pre-activation), backward is hand-scheduled — no autograd.
 Gradients live in one flat fp32 buffer that is all-reduced in per-layer buckets while backward is still running.
 
-Trained here: the decoder (.A branches), the final LayerNorm, the LM head, the token-embedding and position
-tables.  Frozen: the CLIP tower (as the reference's notes.txt:537 `clip_model.requires_grad_(False)`), and in this
-round also the perceiver resampler and image_proj (their backward is not built yet — DESIGN.md §7).
-Dropout (p = 0.1 in the reference's train mode) is not applied.
+Trained here (SURVEY.md §8(e) trainable set): the decoder (.A branches), the final LayerNorm, the LM head, the
+token-embedding and position tables, the perceiver resampler and image_proj.  Frozen: the CLIP tower (the reference's
+notes.txt:537 `clip_model.requires_grad_(False)`; its optional last-layer fine-tuning is not built) and the multiway
+.B branches (never executed).  Dropout (p = 0.1 in the reference's train mode) is not applied.
 """
 from __future__ import annotations
 
@@ -47,7 +47,7 @@ class KosmosTrainer:
 
     def __init__(self, model: Kosmos, *, optimizer: str = "adamw", lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
                  weight_decay: float = 0.1, max_grad_norm: float = 1.0, process_group=None, overlap_all_reduce: bool = True,
-                 layout_only: bool = False):
+                 train_resampler: bool = True, layout_only: bool = False):
         if optimizer not in ("adamw", "lion"):
             raise ValueError("optimizer must be 'adamw' or 'lion' (train.py:375-386)")
         self.model = model
@@ -56,6 +56,7 @@ class KosmosTrainer:
         self.max_grad_norm = max_grad_norm
         self.pg = process_group
         self.overlap = overlap_all_reduce
+        self.train_resampler = train_resampler
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
@@ -88,6 +89,18 @@ class KosmosTrainer:
         nodecay += [dec.layer_norm.weight, dec.layer_norm.bias, m.embed.weight, m.embed_positions.weight]
         if m.output_projection.bias is not None:
             nodecay.append(m.output_projection.bias)
+        self.n_vision_decay_params = 0
+        if self.train_resampler:                 # perceiver resampler + image_proj: behind everything the decoder owns
+            pv = m.perceive
+            vd = []
+            for attn, ff in pv.layers:
+                vd += [attn.to_q.weight, attn.to_kv.weight, attn.to_out.weight, ff[1].weight, ff[3].weight]
+                nodecay += [attn.norm_media.weight, attn.norm_media.bias, attn.norm_latents.weight, attn.norm_latents.bias,
+                            ff[0].weight, ff[0].bias]
+            vd.append(m.image_proj.weight)
+            decay += vd
+            self.n_vision_decay_params = len(vd)
+            nodecay += [pv.norm.weight, pv.norm.bias, pv.latents, pv.media_pos_emb]
         d = cfg.dim
         for q, k, v in ((L["q"], L["k"], L["v"]) for L in self.layers):
             if q.weight.numel() % _ALIGN or q.bias.numel() % _ALIGN:
@@ -98,6 +111,8 @@ class KosmosTrainer:
             self.seg[id(p)] = _Seg(off, p.shape)
             off += _round_up(p.numel())
         self.n_decay = off
+        # where the resampler's Linear weights start inside the decay segment (they complete last, after the decoder)
+        self.vision_decay_off = self.seg[id(decay[-self.n_vision_decay_params])].off if self.n_vision_decay_params else off
         for p in nodecay:
             self.seg[id(p)] = _Seg(off, p.shape)
             off += _round_up(p.numel())
@@ -131,6 +146,7 @@ class KosmosTrainer:
         in-place edit of the parameters).  The optimizer kernels keep them in sync afterwards."""
         ops.cast_bf16(self.P[:self.n_decay], self.W16)
         self.model.decoder._packed = None            # the inference path re-stages its folded weights lazily
+        self.model._resampler_dirty = True
 
     def _w16(self, p):
         s = self.seg[id(p)]
@@ -169,7 +185,11 @@ class KosmosTrainer:
         x = self._buf("x0", (M, D), f32)
         xv = m._vit(images, media=len(img_rows))
         pos = m.embed_positions.weight
-        m._perceive_project(xv, B, x, T, img_rows, pos_table=pos)
+        vis = None
+        if self.train_resampler:
+            vis = self._resampler_forward(xv, B, x, T, img_rows, pos)
+        else:
+            m._perceive_project(xv, B, x, T, img_rows, pos_table=pos)
         ops.embed_splice_pos(text_tokens, m.embed.weight, pos, x, img_rows=img_rows, n_img=Lq, err_flag=m._err_flag())
         tabs = dp._xpos(T, x.device)
         scale = (D // H) ** -0.5
@@ -205,7 +225,116 @@ class KosmosTrainer:
         ops.layernorm(x, dp.layer_norm.weight, dp.layer_norm.bias, hF, eps=cfg.eps)
         logits = self._buf("logits", (M, V), f32)
         ops.gemm(hF, self._w16(m.output_projection.weight), logits, bias=m.output_projection.bias)
-        return dict(saved=saved, x_last=x, hF=hF, logits=logits, B=B, T=T, M=M, tabs=tabs, scale=scale)
+        return dict(saved=saved, x_last=x, hF=hF, logits=logits, B=B, T=T, M=M, tabs=tabs, scale=scale, vis=vis)
+
+    # ------------------------------------------------------------------ perceiver resampler + image_proj (trainable)
+    def _resampler_forward(self, xv, B, x0, T, img_rows, pos):
+        """PerceiverResampler + image_proj (model.py:232) on the trainer's bf16 weight copies, keeping
+        what the backward needs.  xv: ViT output, media-major [m*B*Tv, Dv] fp32 (frozen: no gradient flows into it)."""
+        m, cfg = self.model, self.cfg
+        Tv, Dv, Lq, Hp = cfg.vit_tokens, cfg.vit_dim, cfg.p_latents, cfg.p_heads
+        inner, Fv = Hp * cfg.p_dim_head, cfg.vit_dim * cfg.p_ff_mult
+        nm = len(img_rows)
+        N = B * nm
+        bf, f32 = torch.bfloat16, torch.float32
+        pv = m.perceive
+        mp = pv.media_pos_emb.view(-1, Dv)[0:nm]
+        lat = self._buf("v_lat0", (N * Lq, Dv), f32)
+        ops.broadcast_rows(pv.latents, lat, N)
+        saved = []
+        for li, (attn, ff) in enumerate(pv.layers):
+            s = dict(lat_in=lat)
+            s["cat"] = self._buf(f"v_cat{li}", (N * (Tv + Lq), Dv), bf)
+            s["lnl"] = self._buf(f"v_lnl{li}", (N * Lq, Dv), bf)
+            s["q"] = self._buf(f"v_q{li}", (N * Lq, inner), bf)
+            s["kv"] = self._buf(f"v_kv{li}", (N * (Tv + Lq), 2 * inner), bf)
+            s["att"] = self._buf(f"v_att{li}", (N * Lq, inner), bf)
+            s["lat_mid"] = self._buf(f"v_latmid{li}", (N * Lq, Dv), f32)
+            s["h"] = self._buf(f"v_h{li}", (N * Lq, Dv), bf)
+            s["u"] = self._buf(f"v_u{li}", (N * Lq, Fv), bf)
+            s["mid"] = self._buf(f"v_mid{li}", (N * Lq, Fv), bf)
+            lat_out = self._buf(f"v_latout{li}", (N * Lq, Dv), f32)
+            ops.layernorm(xv, attn.norm_media.weight, attn.norm_media.bias, s["cat"], pre_add=mp,
+                          pre_add_group=Tv * B if nm > 1 else 0, grp=(Tv, Tv + Lq, 0))
+            ops.layernorm(lat, attn.norm_latents.weight, attn.norm_latents.bias, s["cat"], grp=(Lq, Tv + Lq, Tv))
+            ops.layernorm(lat, attn.norm_latents.weight, attn.norm_latents.bias, s["lnl"])
+            ops.gemm(s["lnl"], self._w16(attn.to_q.weight), s["q"])
+            ops.gemm(s["cat"], self._w16(attn.to_kv.weight), s["kv"])
+            ops.perceiver_attention(s["q"], s["kv"], s["att"], batch=N, heads=Hp, n_q=Lq, n_kv=Tv + Lq, v_col_off=inner,
+                                    scale=cfg.p_dim_head ** -0.5)
+            ops.gemm(s["att"], self._w16(attn.to_out.weight), s["lat_mid"], res=lat)
+            ops.layernorm(s["lat_mid"], ff[0].weight, ff[0].bias, s["h"])
+            ops.gemm(s["h"], self._w16(ff[1].weight), s["u"])
+            ops.gelu_fwd(s["u"], s["mid"])
+            ops.gemm(s["mid"], self._w16(ff[3].weight), lat_out, res=s["lat_mid"])
+            saved.append(s)
+            lat = lat_out
+        out_n = self._buf("v_outn", (N * Lq, Dv), bf)
+        ops.layernorm(lat, pv.norm.weight, pv.norm.bias, out_n)
+        wip = self._w16(m.image_proj.weight)
+        for i, r0 in enumerate(img_rows):                # image i of all sequences: rows [i*B*64, (i+1)*B*64)
+            ops.gemm(out_n[i * B * Lq:(i + 1) * B * Lq], wip, x0, grp=(Lq, T, r0), add_tab=pos, add_off=r0 + 2)
+        return dict(saved=saved, lat_last=lat, out_n=out_n, xv=xv, N=N, nm=nm)
+
+    def _resampler_backward(self, vs, dx, B, T, img_rows):
+        """Gradients of image_proj and the resampler from dx = d(loss)/d(decoder input) (its image rows)."""
+        m, cfg = self.model, self.cfg
+        Tv, Dv, Lq, Hp, D = cfg.vit_tokens, cfg.vit_dim, cfg.p_latents, cfg.p_heads, cfg.dim
+        inner, Fv = Hp * cfg.p_dim_head, cfg.vit_dim * cfg.p_ff_mult
+        N, nm = vs["N"], vs["nm"]
+        bf, f32 = torch.bfloat16, torch.float32
+        pv = m.perceive
+        R = N * Lq
+        d_rows = self._buf("v_drows", (R, D), bf)
+        for i, r0 in enumerate(img_rows):
+            ops.gather_rows(dx, d_rows[i * B * Lq:(i + 1) * B * Lq], grp=(Lq, T, r0))
+        ops.gemm(d_rows, vs["out_n"], self._g(m.image_proj.weight), a_trans=True, b_trans=True)
+        dh = self._buf("v_dh", (R, Dv), bf)
+        ops.gemm(d_rows, self._w16(m.image_proj.weight), dh, b_trans=True)
+        dlat = self._buf("v_dlat", (R, Dv), f32)
+        dlatb = self._buf("v_dlatb", (R, Dv), bf)
+        part = self._buf("v_part", (3, ops.ln_bwd_partials(R), Dv), f32)
+        ops.layernorm_bwd(vs["lat_last"], dh, pv.norm.weight, dlat, self._g(pv.norm.weight), self._g(pv.norm.bias), part, dxb=dlatb)
+        dmid = self._buf("v_dmid", (R, Fv), bf)
+        du = self._buf("v_du", (R, Fv), bf)
+        datt = self._buf("v_datt", (R, inner), bf)
+        dq = self._buf("v_dq", (R, inner), bf)
+        dkv = self._buf("v_dkv", (N * (Tv + Lq), 2 * inner), bf)
+        dcat = self._buf("v_dcat", (N * (Tv + Lq), Dv), bf)
+        dxn = self._buf("v_dxn", (N * Tv, Dv), bf)
+        dxm = self._buf("v_dxm", (B * Tv, Dv), f32)
+        part_m = self._buf("v_partm", (3, ops.ln_bwd_partials(B * Tv), Dv), f32)
+        g_mp = self._g(pv.media_pos_emb).view(-1, Dv)
+        mp = pv.media_pos_emb.view(-1, Dv)
+        for li in range(len(pv.layers) - 1, -1, -1):
+            attn, ff = pv.layers[li]
+            s = vs["saved"][li]
+            # feed-forward: lat_out = lat_mid + W2 gelu(W1 LN(lat_mid))
+            ops.gemm(dlatb, self._w16(ff[3].weight), dmid, b_trans=True)
+            ops.gemm(dlatb, s["mid"], self._g(ff[3].weight), a_trans=True, b_trans=True)
+            ops.gelu_bwd(s["u"], dmid, du)
+            ops.gemm(du, self._w16(ff[1].weight), dh, b_trans=True)
+            ops.gemm(du, s["h"], self._g(ff[1].weight), a_trans=True, b_trans=True)
+            ops.layernorm_bwd(s["lat_mid"], dh, ff[0].weight, dlat, self._g(ff[0].weight), self._g(ff[0].bias), part, dres=dlat, dxb=dlatb)
+            # cross-attention: lat_mid = lat_in + to_out(attn(to_q(LN_l(lat_in)), to_kv([LN_m(x + mp) | LN_l(lat_in)])))
+            ops.gemm(dlatb, self._w16(attn.to_out.weight), datt, b_trans=True)
+            ops.gemm(dlatb, s["att"], self._g(attn.to_out.weight), a_trans=True, b_trans=True)
+            ops.perceiver_attention_bwd(s["q"], s["kv"], s["att"], datt, dq, dkv, batch=N, heads=Hp, n_q=Lq, n_kv=Tv + Lq,
+                                        v_col_off=inner, scale=cfg.p_dim_head ** -0.5)
+            ops.gemm(dq, s["lnl"], self._g(attn.to_q.weight), a_trans=True, b_trans=True)
+            ops.gemm(dq, self._w16(attn.to_q.weight), dh, b_trans=True)
+            ops.gemm(dkv, s["cat"], self._g(attn.to_kv.weight), a_trans=True, b_trans=True)
+            ops.gemm(dkv, self._w16(attn.to_kv.weight), dcat, b_trans=True)
+            ops.gather_rows(dcat, dh, grp=(Lq, Tv + Lq, Tv), accumulate=True)        # latents enter through q AND through k|v
+            ops.layernorm_bwd(s["lat_in"], dh, attn.norm_latents.weight, dlat, self._g(attn.norm_latents.weight),
+                              self._g(attn.norm_latents.bias), part, dres=dlat, dxb=dlatb)
+            # media side: only parameter gradients (norm_media, media_pos_emb[i]); the ViT output itself is frozen
+            ops.gather_rows(dcat, dxn, grp=(Tv, Tv + Lq, 0))
+            for i in range(nm):
+                blk = slice(i * B * Tv, (i + 1) * B * Tv)
+                ops.layernorm_bwd(vs["xv"][blk], dxn[blk], attn.norm_media.weight, dxm, self._g(attn.norm_media.weight),
+                                  self._g(attn.norm_media.bias), part_m, pre_add=mp[i], d_colsum=g_mp[i], accumulate=True)
+        ops.sum_rows_f32(dlat.view(N, Lq * Dv), self._g(pv.latents).view(-1))
 
     # ------------------------------------------------------------------ loss + backward
     @staticmethod
@@ -290,6 +419,8 @@ class KosmosTrainer:
             self._bucket_ready(li, works)                     # (fc2.bias of layer li was written by layer li+1's LayerNorm backward)
         ops.embed_bwd(dx, text_tokens, self._g(m.embed.weight), self._g(m.embed_positions.weight), img_rows=img_rows, n_img=Lq,
                       padding_idx=m.embed.padding_idx if m.embed.padding_idx is not None else -1)
+        if fw["vis"] is not None:
+            self._resampler_backward(fw["vis"], dx, B, T, img_rows)
         self._bucket_ready("tail", works)
         for w in works:
             w.wait()
@@ -300,11 +431,12 @@ class KosmosTrainer:
         the layers from last to first (decay block + no-decay block each), then the tail (final LayerNorm, embedding
         and position tables).  The slices tile [0, n_total) exactly."""
         nl = len(self.layers)
-        plan = [("head", self._layer_span(nl, True)[0], self.n_decay)]
+        plan = [("head", self._layer_span(nl, True)[0], self.vision_decay_off)]
         for li in range(nl - 1, -1, -1):
             plan.append((f"layer{li}.decay", *self._layer_span(li, True)))
             plan.append((f"layer{li}.nodecay", *self._layer_span(li, False)))
-        plan.append(("tail", self._layer_span(nl, False)[0], self.n_total))
+        plan.append(("tail", self.vision_decay_off, self.n_decay))              # resampler + image_proj weights
+        plan.append(("tail", self._layer_span(nl, False)[0], self.n_total))     # final LN, tables, resampler vectors
         return [(n, lo, hi) for n, lo, hi in plan if hi > lo]
 
     def _bucket_ready(self, which, works):
@@ -353,6 +485,8 @@ class KosmosTrainer:
                 ops.lion_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], wb, lr=self.lr, betas=self.betas, weight_decay=wd,
                               grad_scale=sc[3:4])
         self.model.decoder._packed = None
+        if self.train_resampler:
+            self.model._resampler_dirty = True
 
     # ------------------------------------------------------------------ public API
     def _prepare(self, text_tokens, images, image_positions):

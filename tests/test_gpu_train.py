@@ -68,9 +68,10 @@ def test_loss_and_gradients_match_oracle_autograd(B, t_text, m, positions):
     assert abs(loss.item() - want.item()) <= LOSS_TOL
     n, worst = _check_grads(ref, mine, trainer)
     print(f"  {n} parameter tensors checked; worst relative gradient error {worst[0]:.3e} ({worst[1]})")
-    assert n == 14 * oc.layers + 6 * oc.layers + 5
-    # frozen parts have no gradient and are not in the flat buffer
-    assert mine.clip_model.pre_layrnorm.weight.grad is None and not mine.image_proj.weight.requires_grad
+    assert n == 20 * oc.layers + 5 + 11 * oc.p_depth + 5        # decoder + head/tables + resampler layers + its norm/latents/media_pos/image_proj
+    # the CLIP tower is frozen: no gradient, not in the flat buffer
+    assert mine.clip_model.pre_layrnorm.weight.grad is None and not mine.clip_model.pre_layrnorm.weight.requires_grad
+    assert mine.image_proj.weight.grad is not None and mine.perceive.media_pos_emb.grad is not None
     # multiway .B branches get no gradient
     for name, p in mine.named_parameters():
         if ".B." in name:
@@ -139,3 +140,16 @@ def test_training_reduces_the_loss_and_inference_follows():
     mine.load_state_dict(sd)
     trainer.sync_weights()
     assert abs(trainer.loss_and_grads(tg, ig).item() - ce.item()) < 3e-2
+
+
+def test_decoder_only_training_freezes_the_resampler():
+    import kosmos_oracle as ko
+    ref, mine, trainer, oc = _pair(train_resampler=False)
+    text, images = ko.make_inputs(oc, 2, 20, seed=3)
+    loss = trainer.loss_and_grads(text.cuda(), images.cuda())
+    ref.zero_grad()
+    want = ref.loss(text, images)
+    want.backward()
+    assert abs(loss.item() - want.item()) <= LOSS_TOL
+    n, worst = _check_grads(ref, mine, trainer)
+    assert n == 20 * oc.layers + 5 and mine.image_proj.weight.grad is None

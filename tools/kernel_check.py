@@ -313,6 +313,70 @@ def case_train_elementwise():
     return ok
 
 
+def case_perceiver_bwd():
+    """Perceiver cross-attention backward and the small resampler helpers against autograd."""
+    torch.manual_seed(41)
+    ok = True
+    F = torch.nn.functional
+    for (B, H, nq, nkv) in ((2, 8, 64, 321), (3, 2, 64, 81), (1, 2, 40, 130)):
+        inner = H * 64
+        q0 = (torch.randn(B * nq, inner, device=dev) * 0.7).bfloat16()
+        kv0 = (torch.randn(B * nkv, 2 * inner, device=dev) * 0.7).bfloat16()
+        d_out = torch.randn(B * nq, inner, device=dev).bfloat16()
+        q = q0.float().requires_grad_(True)
+        kv = kv0.float().requires_grad_(True)
+        qh = q.view(B, nq, H, 64).transpose(1, 2) * 0.125
+        kh = kv[:, :inner].reshape(B, nkv, H, 64).transpose(1, 2)
+        vh = kv[:, inner:].reshape(B, nkv, H, 64).transpose(1, 2)
+        sim = qh @ kh.transpose(-1, -2)
+        o_ref = ((sim - sim.amax(-1, keepdim=True).detach()).softmax(-1) @ vh).transpose(1, 2).reshape(B * nq, inner)
+        o_ref.backward(d_out.float())
+        out = torch.zeros(B * nq, inner, device=dev, dtype=torch.bfloat16)
+        ops.perceiver_attention(q0, kv0, out, batch=B, heads=H, n_q=nq, n_kv=nkv, v_col_off=inner, scale=0.125)
+        dq = torch.full((B * nq, inner), 9.0, device=dev, dtype=torch.bfloat16)
+        dkv = torch.full((B * nkv, 2 * inner), 9.0, device=dev, dtype=torch.bfloat16)
+        ops.perceiver_attention_bwd(q0, kv0, out, d_out, dq, dkv, batch=B, heads=H, n_q=nq, n_kv=nkv, v_col_off=inner, scale=0.125)
+        tag = f"B={B} H={H} nq={nq} nkv={nkv}"
+        ok &= report(f"perceiver xattn bwd dq {tag}", dq, q.grad, 2e-2)
+        ok &= report(f"perceiver xattn bwd dk {tag}", dkv[:, :inner], kv.grad[:, :inner], 2e-2)
+        ok &= report(f"perceiver xattn bwd dv {tag}", dkv[:, inner:], kv.grad[:, inner:], 3e-2)
+    # GELU forward / backward (bf16)
+    u = (torch.randn(300, 4096, device=dev) * 2).bfloat16()
+    dm = torch.randn(300, 4096, device=dev).bfloat16()
+    ur = u.float().requires_grad_(True)
+    F.gelu(ur).backward(dm.float())
+    mid = torch.zeros_like(u); du = torch.zeros_like(u)
+    ops.gelu_fwd(u, mid); ops.gelu_bwd(u, dm, du)
+    ok &= report("gelu_fwd", mid, F.gelu(u.float()), 4e-2)
+    ok &= report("gelu_bwd", du, ur.grad, 3e-2)
+    # row gather (fp32 and bf16 sources, accumulate) and row sums
+    src = torch.randn(5 * 30, 256, device=dev)
+    dst = torch.zeros(5 * 8, 256, device=dev, dtype=torch.bfloat16)
+    ops.gather_rows(src, dst, grp=(8, 30, 7))
+    want = src.view(5, 30, 256)[:, 7:15].reshape(40, 256)
+    ok &= report("gather_rows fp32 -> bf16", dst, want.bfloat16(), 0.0)
+    ops.gather_rows(src.bfloat16(), dst, grp=(8, 30, 2), accumulate=True)
+    want2 = want.bfloat16().float() + src.bfloat16().float().view(5, 30, 256)[:, 2:10].reshape(40, 256)
+    ok &= report("gather_rows bf16 accumulate", dst, want2.bfloat16(), 0.0)
+    mat = torch.randn(6, 64 * 128, device=dev)
+    outv = torch.zeros(64 * 128, device=dev)
+    ops.sum_rows_f32(mat, outv)
+    ok &= report("sum_rows_f32", outv.view(1, -1), mat.sum(0).view(1, -1), 1e-5)
+    # LayerNorm backward with a pre-added row (x + media_pos_emb[i]) and its column-sum gradient
+    rows, n = 514, 1024
+    x = torch.randn(rows, n, device=dev); pa = torch.randn(n, device=dev)
+    gamma = torch.rand(n, device=dev) + 0.5; beta = torch.randn(n, device=dev)
+    dy = (torch.randn(rows, n, device=dev) / 32).bfloat16()
+    par = pa.clone().requires_grad_(True); gr = gamma.clone().requires_grad_(True)
+    F.layer_norm(x + par, (n,), gr, beta, 1e-5).backward(dy.float())
+    part = torch.empty(3, ops.ln_bwd_partials(rows), n, device=dev)
+    dxs = torch.empty(rows, n, device=dev); dg = torch.zeros(n, device=dev); db = torch.zeros(n, device=dev); dpa = torch.zeros(n, device=dev)
+    ops.layernorm_bwd(x, dy, gamma, dxs, dg, db, part, pre_add=pa, d_colsum=dpa, accumulate=True)
+    ok &= report("ln_bwd pre_add: d(pre_add) = colsum(dx)", dpa.view(1, -1), par.grad.view(1, -1), 2e-3)
+    ok &= report("ln_bwd pre_add: dgamma", dg.view(1, -1), gr.grad.view(1, -1), 3e-3)
+    return ok
+
+
 def case_attn_bwd():
     """Flash attention backward (with and without the fused xPos transpose) against autograd on the eager formula."""
     torch.manual_seed(31)
