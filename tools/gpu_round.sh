@@ -17,6 +17,11 @@ for w in $what; do
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 4 -o "$out/prof_gemm" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_gemm.log" 2>&1; echo "ncu_gemm exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_gemm.log";;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_pp -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
     kcheck)   bash tools/run_kernel_checks.sh bench;;
+    bench_train) timeout 900 python bench.py --workload train --steps 5 --warmup 3 > "$out/bench_train.json" 2> "$out/bench_train.err"; echo "bench_train exit $?" | tee -a "$out/summary.txt"; cut -c1-400 "$out/bench_train.json"; tail -3 "$out/bench_train.err";;
+    launches_train) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 1200 --csv --log-file "$out/launches_train.csv" python tools/profile_step.py --train --steps 3 > "$out/launches_train.log" 2>&1; echo "launches_train exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/launches_train.log";;
+    ncu_attn_bwd) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_kernel -s 2 -c 1 -o "$out/prof_attn_bwd" -f python tools/kernel_check.py bench_train > "$out/ncu_attn_bwd.log" 2>&1; echo "ncu_attn_bwd exit $?" | tee -a "$out/summary.txt";;
+    ncu_wgrad) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 1 -o "$out/prof_wgrad" -f python tools/kernel_check.py bench_train > "$out/ncu_wgrad.log" 2>&1; echo "ncu_wgrad exit $?" | tee -a "$out/summary.txt";
+               timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 4 -c 1 -o "$out/prof_dgrad" -f python tools/kernel_check.py bench_train > "$out/ncu_dgrad.log" 2>&1; echo "ncu_dgrad exit $?" | tee -a "$out/summary.txt";;
     attn_dbg) for d in 0 1 2 3; do for poly in 1 0; do echo "dbg=$d poly=$poly"; KX_ATTN_DEBUG=$d KX_ATTN_POLY=$poly timeout 300 python tools/kernel_check.py bench_attn 2>&1 | grep -E "attn causal=True B=8|rror"; done; done | tee "$out/attn_dbg.log";;
     attn_poly) for poly in 1 0; do KX_ATTN_POLY=$poly timeout 300 python tools/kernel_check.py attn > "$out/attn_poly$poly.log" 2>&1; echo "attn poly=$poly exit $?" | tee -a "$out/summary.txt"; grep -E "FAIL|^==|rror" "$out/attn_poly$poly.log" | tail -5;
                 KX_ATTN_POLY=$poly timeout 300 python tools/kernel_check.py bench_attn > "$out/bench_attn_poly$poly.log" 2>&1; grep -E "attn " "$out/bench_attn_poly$poly.log"; done;;
