@@ -150,182 +150,176 @@ act_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, in
 }
 
 // ----------------------------------------------------------------------------- LayerNorm backward
-// y = LN(a) * gamma + beta with a = act(x).  Given dy (bf16), with g = dy * gamma:
+// y = LN(a) * gamma + beta with a = act(x) (+ pre_add).  Given dy (bf16), with g = dy * gamma:
 //   da = rstd * (g - mean(g) - xhat * mean(g * xhat));  dx = da * act'(x)
 //   d(gamma) += dy * xhat, d(beta) += dy  (per-CTA partials [grid][n], folded by colpartials_reduce_kernel)
 // One pass, ONE block reduction per row: sum a, sum a^2, sum g, sum g*a give mean, rstd and
 //   mean(g * xhat) = rstd * (sum(g*a) - mean * sum(g)) / n.
-// gamma lives in registers across rows; the next row's loads are issued before the reduction (NCH == 1); the three
-// column accumulators are registers for NCH == 1 and shared memory for wide rows (keeps two CTAs per SM at n = 8192).
+// Rows travel through a 3-stage shared-memory ring filled by 1-D bulk copies (cp.async.bulk + mbarrier, issued by
+// thread 0 two rows ahead): ncu showed the register-prefetch version latency-bound (24 warps/SM, one row in flight per
+// CTA, 3.3 TB/s) and the wide-row version issue-bound on its shared-memory accumulators.  Every thread owns 8 columns
+// (THREADS = 256 for n <= 2048, 1024 for n <= 8192), so d(gamma) / d(beta) / column-sum accumulators are registers.
 // DX_F32: dx is the fp32 residual-stream gradient: dx_out = dres + dx (dres may alias dx_out), an optional bf16 copy
 // dxb of dx_out is written (the A operand of the next backward GEMMs) and column sums of dx_out are accumulated as a
 // third partial (the bias gradient of the Linear whose output was added to the stream at this point).
-template <typename XT, bool DX_F32, int NCH>
-__global__ void __launch_bounds__(ROW_THREADS, (NCH == 1) ? 3 : 2)
-layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ pre_add, int act,
-                     const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ gamma, float eps,
-                     const float* dres, long long ld_dres,
-                     void* dx_out, long long ld_dx, __nv_bfloat16* __restrict__ dxb, long long ld_dxb,
-                     float* __restrict__ part_gamma, float* __restrict__ part_beta, float* __restrict__ part_col,
-                     int rows, int n) {
-    constexpr bool SMEM_ACC = (NCH > 1);
-    constexpr bool PREFETCH = (NCH == 1);
-    extern __shared__ float s_acc[];                   // SMEM_ACC: [3][NCH * 2048]
-    __shared__ float red[32];
-    const float inv_n = 1.0f / static_cast<float>(n);
-    float acc_g[SMEM_ACC ? 1 : NCH][8], acc_b[SMEM_ACC ? 1 : NCH][8], acc_c[SMEM_ACC ? 1 : NCH][8];
-    float gm[NCH][8];
-    float pa[(NCH == 1) ? 1 : 1][8];                   // pre_add row (x + media_pos_emb[i] of the perceiver): narrow rows only
+constexpr int LNB_STAGES = 3;
+
+template <int THREADS>
+__device__ __forceinline__ void block_sum4_t(float& a, float& b, float& c, float& d, float* red) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) pa[0][u] = 0.f;
-    if (NCH == 1 && pre_add != nullptr && threadIdx.x * 8 < n) load8(pre_add + threadIdx.x * 8, pa[0]);
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    constexpr int W = THREADS / 32;
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[w] = a; red[W + w] = b; red[2 * W + w] = c; red[3 * W + w] = d; }
+    __syncthreads();
+    if constexpr (W <= 8) {
+        a = 0.f; b = 0.f; c = 0.f; d = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-        if (col < n) load8(gamma + col, gm[c]);
-        else
+        for (int i = 0; i < W; ++i) { a += red[i]; b += red[W + i]; c += red[2 * W + i]; d += red[3 * W + i]; }
+    } else {                                             // 32 warps: every warp folds the 4 x 32 partials with shuffles
+        const int l = threadIdx.x & 31;
+        a = red[l]; b = red[W + l]; c = red[2 * W + l]; d = red[3 * W + l];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) gm[c][u] = 0.f;
-        if constexpr (SMEM_ACC) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int u = 0; u < 8; ++u) s_acc[k * NCH * 2048 + col + u] = 0.f;
-        } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { acc_g[c][u] = 0.f; acc_b[c][u] = 0.f; acc_c[c][u] = 0.f; }
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            d += __shfl_xor_sync(0xffffffffu, d, o);
         }
     }
-    // (each thread only ever touches its own columns of s_acc: no synchronisation needed for it)
+    __syncthreads();
+}
 
-    float a[NCH][8], d[NCH][8], r[PREFETCH ? NCH : 1][8];
-    auto fetch = [&](int row) {
+__device__ __forceinline__ void lnb_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <typename XT, bool DX_F32, int THREADS, bool GELU>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 1)
+layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __restrict__ pre_add,
+                     const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ gamma, float eps,
+                     const float* dres, long long ld_dres, void* dx_out, long long ld_dx, __nv_bfloat16* __restrict__ dxb,
+                     long long ld_dxb, float* __restrict__ part_gamma, float* __restrict__ part_beta,
+                     float* __restrict__ part_col, int rows, int n) {
+    extern __shared__ __align__(128) uint8_t lnb_smem[];
+    __shared__ float red[4 * (THREADS / 32)];
+    __shared__ __align__(8) uint64_t full[LNB_STAGES];
+    const uint32_t x_bytes = static_cast<uint32_t>(n) * sizeof(XT), dy_bytes = static_cast<uint32_t>(n) * 2;
+    const bool has_res = DX_F32 && dres != nullptr;
+    const uint32_t res_bytes = has_res ? static_cast<uint32_t>(n) * 4 : 0;
+    const uint32_t stage_bytes = x_bytes + dy_bytes + res_bytes;           // multiples of 16 (n % 8 == 0)
+    const float inv_n = 1.0f / static_cast<float>(n);
+    const int col = threadIdx.x * 8;
+    const bool live = col < n;
+
+    auto issue = [&](int row, int s) {                  // thread 0 only
+        uint8_t* st = lnb_smem + static_cast<size_t>(s) * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        lnb_bulk_load(st, x + static_cast<long long>(row) * ld_x, x_bytes, &full[s]);
+        lnb_bulk_load(st + x_bytes, dy + static_cast<long long>(row) * ld_dy, dy_bytes, &full[s]);
+        if (has_res) lnb_bulk_load(st + x_bytes + dy_bytes, dres + static_cast<long long>(row) * ld_dres, res_bytes, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LNB_STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        for (int s = 0; s < LNB_STAGES; ++s) {
+            const int row = blockIdx.x + s * gridDim.x;
+            if (row < rows) issue(row, s);
+        }
+    }
+    __syncthreads();
+
+    constexpr bool PRE_ADD = (THREADS == 256) && !GELU;          // x + media_pos_emb[i] only exists on narrow rows
+    float gm[8], pa[PRE_ADD ? 8 : 1], acc_g[8], acc_b[8], acc_c[8];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-            if (row < rows && col < n) {
-                load8(x + row * ld_x + col, a[c]);
-                load8(dy + row * ld_dy + col, d[c]);
-                if constexpr (PREFETCH && DX_F32) {
-                    if (dres != nullptr) load8(dres + row * ld_dres + col, r[c]);
-                }
-            } else {
+    for (int u = 0; u < 8; ++u) { gm[u] = 0.f; acc_g[u] = 0.f; acc_b[u] = 0.f; acc_c[u] = 0.f; }
+    if constexpr (PRE_ADD) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { a[c][u] = 0.f; d[c][u] = 0.f; }
+        for (int u = 0; u < 8; ++u) pa[u] = 0.f;
+    }
+    if (live) {
+        load8(gamma + col, gm);
+        if constexpr (PRE_ADD) {
+            if (pre_add != nullptr) load8(pre_add + col, pa);
+        }
+    }
+
+    int it = 0;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+        const int s = it % LNB_STAGES;
+        const uint8_t* st = lnb_smem + static_cast<size_t>(s) * stage_bytes;
+        mbar_wait_lean(&full[s], (it / LNB_STAGES) & 1);
+        float xr[8], d[8], r[DX_F32 ? 8 : 1], a[8], cdf[GELU ? 8 : 1];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xr[u] = 0.f; d[u] = 0.f; }
+        if constexpr (DX_F32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = 0.f;
+        }
+        if (live) {
+            load8(reinterpret_cast<const XT*>(st) + col, xr);
+            load8(reinterpret_cast<const __nv_bfloat16*>(st + x_bytes) + col, d);
+            if constexpr (DX_F32) {
+                if (has_res) load8(reinterpret_cast<const float*>(st + x_bytes + dy_bytes) + col, r);
             }
         }
-    };
-    fetch(blockIdx.x);
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        // PREFETCH: a/d/r are about to be overwritten by the next row's loads, so this row moves to copies;
-        // otherwise the row is processed in place (wide rows: registers are the scarce resource)
-        float xa_s[PREFETCH ? NCH : 1][8], dy_s[PREFETCH ? NCH : 1][8], rr[PREFETCH ? NCH : 1][8];
-        float (*xa)[8];
-        float (*dyv)[8];
-        if constexpr (PREFETCH) { xa = xa_s; dyv = dy_s; } else { xa = a; dyv = d; }
         float s1 = 0.f, s2 = 0.f, sg = 0.f, sga = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                float av = (act == KX_ACT_GELU) ? gelu_exact(a[c][u]) : a[c][u];
-                if constexpr (NCH == 1) av += pa[0][u];
-                const float dv = d[c][u];
-                const float gv = dv * gm[c][u];
-                xa[c][u] = av; dyv[c][u] = dv;
-                s1 += av; s2 = fmaf(av, av, s2); sg += gv; sga = fmaf(gv, av, sga);
-                if constexpr (PREFETCH && DX_F32) rr[c][u] = r[c][u];
-            }
+        for (int u = 0; u < 8; ++u) {
+            if constexpr (GELU) { cdf[u] = gelu_cdf(xr[u]); a[u] = xr[u] * cdf[u]; }
+            else if constexpr (PRE_ADD) a[u] = xr[u] + pa[u];
+            else a[u] = xr[u];
+            const float gv = d[u] * gm[u];
+            s1 += a[u]; s2 = fmaf(a[u], a[u], s2); sg += gv; sga = fmaf(gv, a[u], sga);
         }
-        if constexpr (PREFETCH) fetch(row + gridDim.x);          // next row's loads fly during the reduction and the stores
-        block_sum4(s1, s2, sg, sga, red);
+        block_sum4_t<THREADS>(s1, s2, sg, sga, red);     // (its barriers also order this row's smem reads before the refill)
+        if (threadIdx.x == 0) {
+            const int nxt = row + LNB_STAGES * gridDim.x;
+            if (nxt < rows) issue(nxt, s);
+        }
         const float mean = s1 * inv_n;
         const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
         const float mg = sg * inv_n;
         const float mgx = rstd * (sga - mean * sg) * inv_n;       // mean(g * xhat)
+        if (live) {
+            float o[8], xh[8];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-            if (col < n) {
-                float o[8], xh[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    xh[u] = (xa[c][u] - mean) * rstd;
-                    o[u] = rstd * (dyv[c][u] * gm[c][u] - mg - xh[u] * mgx);
-                }
-                if (act == KX_ACT_GELU) {
-                    float xr[8];
-                    load8(x + row * ld_x + col, xr);                 // the pre-activation again (L1 / L2 hit)
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) o[u] *= gelu_grad(xr[u]);
-                }
-                float cs[8];
-                if constexpr (DX_F32) {
-                    if (dres != nullptr) {
-                        if constexpr (PREFETCH) {
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) o[u] += rr[c][u];
-                        } else {
-                            float t[8];
-                            load8(dres + row * ld_dres + col, t);
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) o[u] += t[u];
-                        }
-                    }
-                    store8(reinterpret_cast<float*>(dx_out) + row * ld_dx + col, o);
-                    if (dxb != nullptr) store8(dxb + row * ld_dxb + col, o);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) cs[u] = o[u];
-                } else {
-                    store8(reinterpret_cast<__nv_bfloat16*>(dx_out) + row * ld_dx + col, o);
-                    // column sums of what the next GEMM reads: the bf16-rounded values
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) cs[u] = __bfloat162float(__float2bfloat16_rn(o[u]));
-                }
-                if constexpr (SMEM_ACC) {
-                    float* sg_ = s_acc + col;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        sg_[u] = fmaf(dyv[c][u], xh[u], sg_[u]);
-                        sg_[NCH * 2048 + u] += dyv[c][u];
-                        if (part_col != nullptr) sg_[2 * NCH * 2048 + u] += cs[u];
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        acc_g[c][u] = fmaf(dyv[c][u], xh[u], acc_g[c][u]);
-                        acc_b[c][u] += dyv[c][u];
-                        acc_c[c][u] += cs[u];
-                    }
-                }
+            for (int u = 0; u < 8; ++u) {
+                xh[u] = (a[u] - mean) * rstd;
+                o[u] = rstd * (d[u] * gm[u] - mg - xh[u] * mgx);
+                if constexpr (GELU)                                // gelu'(x) = Phi(x) + x * phi(x)
+                    o[u] *= fmaf(xr[u], 0.3989422804014327f * ex2_approx(-0.72134752044448170368f * xr[u] * xr[u]), cdf[u]);
+                acc_g[u] = fmaf(d[u], xh[u], acc_g[u]);
+                acc_b[u] += d[u];
             }
-        }
-        if constexpr (!PREFETCH) fetch(row + gridDim.x);
-    }
+            if constexpr (DX_F32) {
+                if (has_res)
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int col = (threadIdx.x + c * ROW_THREADS) * 8;
-        if (col < n) {
-            const long long o = static_cast<long long>(blockIdx.x) * n + col;
-            if constexpr (SMEM_ACC) {
-                float t[8];
+                    for (int u = 0; u < 8; ++u) o[u] += r[u];
+                store8(reinterpret_cast<float*>(dx_out) + static_cast<long long>(row) * ld_dx + col, o);
+                if (dxb != nullptr) store8(dxb + static_cast<long long>(row) * ld_dxb + col, o);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = s_acc[col + u];
-                store8(part_gamma + o, t);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = s_acc[NCH * 2048 + col + u];
-                store8(part_beta + o, t);
-                if (part_col != nullptr) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) t[u] = s_acc[2 * NCH * 2048 + col + u];
-                    store8(part_col + o, t);
-                }
+                for (int u = 0; u < 8; ++u) acc_c[u] += o[u];
             } else {
-                store8(part_gamma + o, acc_g[c]);
-                store8(part_beta + o, acc_b[c]);
-                if (part_col != nullptr) store8(part_col + o, acc_c[c]);
+                store8(reinterpret_cast<__nv_bfloat16*>(dx_out) + static_cast<long long>(row) * ld_dx + col, o);
+                // column sums of what the next GEMM reads: the bf16-rounded values
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc_c[u] += __bfloat162float(__float2bfloat16_rn(o[u]));
             }
         }
+    }
+    if (live) {
+        const long long o = static_cast<long long>(blockIdx.x) * n + col;
+        store8(part_gamma + o, acc_g);
+        store8(part_beta + o, acc_b);
+        if (part_col != nullptr) store8(part_col + o, acc_c);
     }
 }
 
@@ -746,28 +740,40 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, co
     }
     const int sms = device_sm_count();
     if (sms <= 0) return KX_ERR_NO_DEVICE;
-    const int grid = std::max(1, std::min(rows, sms * (n <= 2048 ? 3 : 2)));
+    const bool wide = n > 2048;
+    const int grid = std::max(1, std::min(rows, sms * (wide ? 1 : 3)));
     if (n_partials < grid) { set_error("kx_layernorm_bwd: partials buffer holds %d rows, needs kx_ln_bwd_partials(rows) = %d", n_partials, grid); return KX_ERR_ARG; }
+    if ((ld_x * (x_is_bf16 ? 2 : 4)) % 16 || (ld_dy * 2) % 16 || (dres && (ld_dres * 4) % 16)) {
+        set_error("kx_layernorm_bwd: rows must be 16-byte aligned for the bulk copies");
+        return KX_ERR_ARG;
+    }
     float* pg = partials;
     float* pb = partials + static_cast<long long>(grid) * n;
     float* pc = d_colsum ? partials + 2ll * grid * n : nullptr;
     auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy_bf16);
     auto dxbp = reinterpret_cast<__nv_bfloat16*>(dxb_bf16);
-#define KX_LNB(XT, F32, NCH)                                                                                              \
+    const int smem = LNB_STAGES * n * ((x_is_bf16 ? 2 : 4) + 2 + ((dx_is_f32 && dres) ? 4 : 0));
+#define KX_LNB(XT, F32, TH, GE)                                                                                           \
     {                                                                                                                     \
-        constexpr int smem = (NCH > 1) ? 3 * NCH * 2048 * 4 : 0;                                                          \
-        auto kern = layernorm_bwd_kernel<XT, F32, NCH>;                                                                   \
-        if (smem + 1024 > 48 * 1024) {                                                                                    \
-            static bool attr = false;                                                                                     \
-            if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }    \
+        auto kern = layernorm_bwd_kernel<XT, F32, TH, GE>;                                                                \
+        static int attr = 0;                                                                                              \
+        if (smem > attr) {                                                                                                \
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {           \
+                set_error("kx_layernorm_bwd: cudaFuncSetAttribute(smem=%d) failed", smem);                                \
+                return KX_ERR_LAUNCH;                                                                                     \
+            }                                                                                                             \
+            attr = smem;                                                                                                  \
         }                                                                                                                 \
-        kern<<<grid, ROW_THREADS, smem, stream>>>(reinterpret_cast<const XT*>(x), ld_x, pre_add, act, dyp, ld_dy, gamma, eps, dres, \
-                                                  ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n);                 \
+        kern<<<grid, TH, smem, stream>>>(reinterpret_cast<const XT*>(x), ld_x, pre_add, dyp, ld_dy, gamma, eps, dres,     \
+                                         ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n);                          \
     }
-#define KX_LNB_N(XT, F32)                                                                                                 \
-    { if (n <= 2048) KX_LNB(XT, F32, 1) else if (n <= 4096) KX_LNB(XT, F32, 2) else KX_LNB(XT, F32, 4) }
-    if (x_is_bf16) { if (dx_is_f32) KX_LNB_N(__nv_bfloat16, true) else KX_LNB_N(__nv_bfloat16, false) }
-    else { if (dx_is_f32) KX_LNB_N(float, true) else KX_LNB_N(float, false) }
+#define KX_LNB_N(XT, F32, GE)                                                                                             \
+    { if (!wide) KX_LNB(XT, F32, 256, GE) else KX_LNB(XT, F32, 1024, GE) }
+    if (act == KX_ACT_GELU) {
+        if (!x_is_bf16 || dx_is_f32) { set_error("kx_layernorm_bwd: the GELU form takes a bf16 pre-activation and writes a bf16 gradient"); return KX_ERR_ARG; }
+        KX_LNB_N(__nv_bfloat16, false, true)
+    } else if (x_is_bf16) { if (dx_is_f32) KX_LNB_N(__nv_bfloat16, true, false) else KX_LNB_N(__nv_bfloat16, false, false) }
+    else { if (dx_is_f32) KX_LNB_N(float, true, false) else KX_LNB_N(float, false, false) }
 #undef KX_LNB_N
 #undef KX_LNB
     int st = check_launch("kx_layernorm_bwd");

@@ -17,6 +17,8 @@ for w in $what; do
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 4 -o "$out/prof_gemm" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_gemm.log" 2>&1; echo "ncu_gemm exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_gemm.log";;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_pp -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
     kcheck)   bash tools/run_kernel_checks.sh bench;;
+    kernel_table) timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread --clock-control none --csv --log-file "$out/kernel_table.csv" python tools/profile_step.py --train --steps 2 --layers 2 --vit-layers 2 > "$out/kernel_table.log" 2>&1; echo "kernel_table exit $?" | tee -a "$out/summary.txt"; tail -2 "$out/kernel_table.log";
+                  timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread --clock-control none --csv --log-file "$out/kernel_table_fwd.csv" python tools/profile_step.py --steps 2 --layers 2 --vit-layers 2 > "$out/kernel_table_fwd.log" 2>&1; echo "kernel_table_fwd exit $?" | tee -a "$out/summary.txt";;
     bench_train) timeout 900 python bench.py --workload train --steps 5 --warmup 3 > "$out/bench_train.json" 2> "$out/bench_train.err"; echo "bench_train exit $?" | tee -a "$out/summary.txt"; cut -c1-400 "$out/bench_train.json"; tail -3 "$out/bench_train.err";;
     launches_train) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 1200 --csv --log-file "$out/launches_train.csv" python tools/profile_step.py --train --steps 3 > "$out/launches_train.log" 2>&1; echo "launches_train exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/launches_train.log";;
     ncu_attn_bwd) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_kernel -s 2 -c 1 -o "$out/prof_attn_bwd" -f python tools/kernel_check.py bench_train > "$out/ncu_attn_bwd.log" 2>&1; echo "ncu_attn_bwd exit $?" | tee -a "$out/summary.txt";;
