@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 8   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 9   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -287,6 +287,75 @@ int kx_adamw_step(float* p, const float* g, float* m, float* v, void* w_bf16, lo
                   float beta2, float eps, float weight_decay, int step, const float* grad_scale, kx_stream_t stream);
 int kx_lion_step(float* p, const float* g, float* m, void* w_bf16, long long n, float lr, float beta1, float beta2,
                  float weight_decay, const float* grad_scale, kx_stream_t stream);
+
+/* ==================================================================================== *
+ * Incremental decoding: torchscale's `incremental_state` protocol of Decoder.forward /
+ * MultiheadAttention.forward (SURVEY A.4, A.5 [recall]; reached through the decoder built at model.py:186-191).
+ * The prompt pass is the ordinary forward plus kx_kv_cache_store per layer; every later step processes ONE new token
+ * per sequence.  The cache holds, per layer, the xPos-ROTATED keys and the values as bf16 [batch, t_max, d_model]
+ * (head h at columns h*64..h*64+63).  torchscale caches un-rotated keys and re-rotates the whole key sequence with a
+ * re-centred scale every step; q.k depends on the position DIFFERENCE only (A.5), so rotating each key once with the
+ * prompt's centre gives the same products.  The current position (= number of cached tokens) lives in DEVICE memory
+ * (`pos`), so one captured CUDA graph serves every step with no host round trip.
+ * ==================================================================================== */
+enum { KX_DEC_PLAIN = 0, KX_DEC_RESIDUAL = 1, KX_DEC_QKV = 2 };
+#define KX_DECODE_MAX_BATCH 32
+
+/* y[batch, N] = epilogue(a[batch, K] . W[N, K]^T) for batch <= KX_DECODE_MAX_BATCH rows: the weight-streaming
+ * (HBM-bound) form of kx_gemm_bf16.  ln_c != NULL folds the LayerNorm in front of the Linear exactly as
+ * kx_gemm_args.ln_part does (W carries gamma, bias = W.beta + b, ln_c = row sums of the bf16 W), with mean / rstd taken
+ * over the K bf16 values of each row of `a` inside the kernel.
+ *   KX_DEC_PLAIN     out (bf16 or fp32) = act(y)                      fc1 (+GELU), output_projection
+ *   KX_DEC_RESIDUAL  x (fp32, in place) += y; xb = bf16(x)            out_proj, fc2 (+ residual)
+ *   KX_DEC_QKV       N = 3*d_model: q (rotated with xq tables at *pos) -> q_out [batch, ld_q]; k (rotated with the xk
+ *                    tables) and v -> row *pos of k_cache / v_cache [batch, t_max, d_model]
+ * Replaces, for one-token steps: q/k/v/out_proj, fc1, fc2 of torchscale MultiheadAttention / FeedForwardNetwork together
+ * with self_attn_layer_norm / inner_attn_ln / final_layer_norm / ffn_layernorm, XPOS.forward(offset = src_len - 1), the
+ * `prev_key` / `prev_value` torch.cat, decoder.layer_norm + output_projection. */
+typedef struct kx_decode_linear_args {
+    int mode;                     /* KX_DEC_* */
+    int act;                      /* KX_ACT_* (KX_DEC_PLAIN) */
+    const float* bias;            /* fp32 [N] or NULL */
+    const float* ln_c;            /* fp32 [N] or NULL = no LayerNorm fold */
+    float ln_eps;
+    void* out; long long ld_out; int out_f32;                  /* KX_DEC_PLAIN */
+    float* x; long long ld_x; void* xb; long long ld_xb;       /* KX_DEC_RESIDUAL */
+    void* q_out; long long ld_q; void* k_cache; void* v_cache; /* KX_DEC_QKV */
+    int t_max, d_model;
+    const int* pos;               /* device: position of the new token = tokens already cached */
+    const float *xq_cos, *xq_sin, *xk_cos, *xk_sin;            /* kx_xpos_tables with >= t_max rows */
+} kx_decode_linear_args;
+
+int kx_decode_linear(const void* a_bf16, long long lda, int batch, const void* w_bf16, long long ldw, int N, int K,
+                     const kx_decode_linear_args* args, kx_stream_t stream);
+
+/* softmax(q . K^T * scale) . V of the new token against keys 0..*pos of the cache (flash-decoding: one CTA per
+ * (128-key chunk, head, batch), the last CTA of a (batch, head) merges the chunk partials).  q bf16 [batch, ld_q],
+ * out bf16 [batch, ld_out], head_dim 64.  scratch: kx_decode_attn_scratch_bytes(); counters: int [batch*heads],
+ * zeroed once by the caller (the kernel leaves them zero).  Replaces the bmm / softmax(fp32) / bmm of torchscale
+ * MultiheadAttention when incremental_state holds prev_key / prev_value (no mask: SURVEY A.4). */
+size_t kx_decode_attn_scratch_bytes(int batch, int heads, int t_max);
+int kx_decode_attn(const void* q_bf16, long long ld_q, const void* k_cache, const void* v_cache, int t_max, int batch,
+                   int heads, const int* pos, float scale, float* scratch, int* counters, void* out_bf16, long long ld_out,
+                   kx_stream_t stream);
+
+/* Prompt pass: copy the k and v column blocks ([d_model, 3*d_model) of a layer's rotated q|k|v matrix, rows b*seq_len+t)
+ * into rows 0..seq_len-1 of the cache (`incremental_state[idx]["prev_key"/"prev_value"] = k, v` of the first step). */
+int kx_kv_cache_store(const void* qkv_bf16, long long ld_qkv, int batch, int seq_len, int d_model, void* k_cache,
+                      void* v_cache, int t_max, kx_stream_t stream);
+
+/* x[b] = embed_table[tokens[b]] + pos_table[*pos + 2] (fp32) and its bf16 copy: Decoder.forward_embedding for
+ * `tokens[:, -1:]` with the last position.  err_flag bit 0: token id out of range; bit 1: position table
+ * exhausted. */
+int kx_decode_embed(const long long* tokens, int batch, const float* embed_table, int vocab, const float* pos_table,
+                    int pos_rows, const int* pos, int dim, float* x, void* xb_bf16, int* err_flag, kx_stream_t stream);
+
+/* Greedy choice on the device: tokens_out[b] = argmax_v logits[b, v] (lowest index on ties) or forced[b, *step] when
+ * `forced` (int64 [batch, history_ld]) is given; history[b, *step] = the choice; then *step += 1 and *pos += 1 (pos
+ * may be NULL).  counter: one int, zeroed once by the caller. */
+int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, const long long* forced,
+                      long long* tokens_out, long long* history, int history_ld, int* pos, int* step, int* counter,
+                      kx_stream_t stream);
 
 #ifdef __cplusplus
 }

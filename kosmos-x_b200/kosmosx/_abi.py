@@ -16,6 +16,8 @@ KX_OK = 0
 KX_ACT_NONE, KX_ACT_GELU, KX_ACT_QUICK_GELU = 0, 1, 2
 KX_EPI_GENERIC, KX_EPI_QKV_XPOS = 0, 1
 KX_MAX_IMAGES = 16
+KX_DEC_PLAIN, KX_DEC_RESIDUAL, KX_DEC_QKV = 0, 1, 2
+KX_DECODE_MAX_BATCH = 32
 
 _f32p = C.c_void_p
 _vp = C.c_void_p
@@ -39,6 +41,19 @@ class GemmArgs(C.Structure):
         ("ln_part", _f32p), ("ln_c", _f32p), ("ln_tiles", _i), ("ln_cols", _i), ("ln_eps", _f),
         ("stats_out", _f32p), ("out2", _vp), ("ld_out2", _ll),
         ("a_trans", _i), ("b_trans", _i),
+    ]
+
+
+class DecodeLinearArgs(C.Structure):
+    """struct kx_decode_linear_args (include/kosmosx_b200.h)."""
+
+    _fields_ = [
+        ("mode", _i), ("act", _i), ("bias", _f32p), ("ln_c", _f32p), ("ln_eps", _f),
+        ("out", _vp), ("ld_out", _ll), ("out_f32", _i),
+        ("x", _f32p), ("ld_x", _ll), ("xb", _vp), ("ld_xb", _ll),
+        ("q_out", _vp), ("ld_q", _ll), ("k_cache", _vp), ("v_cache", _vp),
+        ("t_max", _i), ("d_model", _i), ("pos", _vp),
+        ("xq_cos", _f32p), ("xq_sin", _f32p), ("xk_cos", _f32p), ("xk_sin", _f32p),
     ]
 
 
@@ -82,6 +97,13 @@ SIGNATURES = {
     "kx_clip_scale": (_i, [_f32p, _f, _f, _f32p, _f32p, _vp]),
     "kx_adamw_step": (_i, [_f32p, _f32p, _f32p, _f32p, _vp, _ll, _f, _f, _f, _f, _f, _i, _f32p, _vp]),
     "kx_lion_step": (_i, [_f32p, _f32p, _f32p, _vp, _ll, _f, _f, _f, _f, _f32p, _vp]),
+    # ---- incremental decoding
+    "kx_decode_linear": (_i, [_vp, _ll, _i, _vp, _ll, _i, _i, C.POINTER(DecodeLinearArgs), _vp]),
+    "kx_decode_attn_scratch_bytes": (C.c_size_t, [_i, _i, _i]),
+    "kx_decode_attn": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _vp, _f, _f32p, _vp, _vp, _ll, _vp]),
+    "kx_kv_cache_store": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "kx_decode_embed": (_i, [_vp, _i, _f32p, _i, _f32p, _i, _vp, _i, _f32p, _vp, _vp, _vp]),
+    "kx_argmax_advance": (_i, [_f32p, _ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -251,6 +251,43 @@ class _Workspace:
         self._bufs.clear()
 
 
+# --------------------------------------------------------------------------- incremental decoding state
+class DecodeState:
+    """KV cache and device-side counters of one generation — what torchscale keeps as
+    ``incremental_state[layer]["prev_key" / "prev_value"]``.  Per layer the xPos-rotated keys and the values are bf16
+    ``[B, t_max, D]``; ``pos`` (device int32) is the number of cached tokens = the position of the next one, read by the
+    kernels themselves so a decoding step needs no host value; ``length`` is its host mirror for argument checks."""
+
+    def __init__(self, cfg: KosmosConfig, batch: int, t_max: int, device):
+        if batch > _abi.KX_DECODE_MAX_BATCH:
+            raise ValueError(f"incremental decoding handles at most {_abi.KX_DECODE_MAX_BATCH} sequences per call, got {batch}")
+        if t_max + 2 > cfg.max_positions:
+            raise ValueError(f"prompt + new tokens = {t_max} exceeds the positional table: max is {cfg.max_positions - 2} "
+                             "(construct the model with max_positions=... to extend it)")
+        bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+        L, D, F, H = cfg.layers, cfg.dim, cfg.ffn, cfg.heads
+        self.batch, self.t_max, self.length = batch, t_max, 0
+        self.k = torch.empty(L, batch, t_max, D, dtype=bf, device=device)
+        self.v = torch.empty(L, batch, t_max, D, dtype=bf, device=device)
+        self.pos = torch.zeros(1, dtype=i32, device=device)
+        self.step = torch.zeros(1, dtype=i32, device=device)
+        self.counter = torch.zeros(1, dtype=i32, device=device)
+        self.err = torch.zeros(1, dtype=i32, device=device)
+        self.tok = torch.zeros(batch, dtype=torch.int64, device=device)
+        self.x = torch.empty(batch, D, dtype=f32, device=device)
+        self.xb = torch.empty(batch, D, dtype=bf, device=device)
+        self.q = torch.empty(batch, D, dtype=bf, device=device)
+        self.att = torch.empty(batch, D, dtype=bf, device=device)
+        self.mid = torch.empty(batch, F, dtype=bf, device=device)
+        self.logits = torch.empty(batch, cfg.vocab, dtype=f32, device=device)
+        self.scratch, self.counters = ops.decode_attn_scratch(batch, H, t_max, device)
+        self.tabs = None          # xPos tables [4, t_max, 32], centred like the prompt's (set by the prompt pass)
+        self.graph = None         # captured (one step + greedy choice), replayed by Kosmos.generate
+
+    def cache_bytes(self) -> int:
+        return 2 * self.k.numel() * 2
+
+
 # --------------------------------------------------------------------------- decoder
 class Decoder(nn.Module):
     """torchscale ``Decoder`` surface used by the reference (model.py:186-191,238,242,250) with the
@@ -347,7 +384,8 @@ class Decoder(nn.Module):
         if tokens.dtype != torch.int64:
             raise TypeError("token ids must be int64")
 
-    def run_layers(self, x: torch.Tensor, B: int, T: int, logits: torch.Tensor | None = None, head: bool = True):
+    def run_layers(self, x: torch.Tensor, B: int, T: int, logits: torch.Tensor | None = None, head: bool = True,
+                   state: DecodeState | None = None):
         """24 x (sub-LN attention + sub-LN FFN) in place on the fp32 residual stream x [B*T, D], then (``head``)
         final LayerNorm + LM head -> fp32 logits [B*T, vocab].  5 launches per layer: every LayerNorm is folded
         into its consumer GEMM (row statistics travel as partial sums from the producer's epilogue)."""
@@ -365,14 +403,18 @@ class Decoder(nn.Module):
         st_b = ws.get("st_b", ((D + 127) // 128, M, 2), f32, dev)
         st_att = ws.get("st_att", (H, M, 2), f32, dev)
         st_mid = ws.get("st_mid", ((F + 127) // 128, M, 2), f32, dev)
-        tabs = self._xpos(T, dev)
+        # prompt pass of a generation (``state``): the tables extend to t_max rows with the prompt's centre, so rows
+        # 0..T-1 are the ordinary ones, and every layer's rotated k / v go into the cache
+        tabs = self._xpos(T, dev) if state is None else state.tabs
         scale = (D // H) ** -0.5
         eps = cfg.eps
         ops.rowstats_cast(x, xb, st_in)
         cur = st_in
-        for L in p["layers"]:
+        for li, L in enumerate(p["layers"]):
             w, c, d = L["qkv"]                                   # self_attn_layer_norm -> q|k|v (+bias, xPos)
             ops.gemm(xb, w, qkv, bias=d, ln=(cur, c, D, eps), xpos=(tabs[0], tabs[1], tabs[2], tabs[3]), seq_len=T)
+            if state is not None:
+                ops.kv_cache_store(qkv, state.k[li], state.v[li], batch=B, seq_len=T, d_model=D, t_max=state.t_max)
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, batch=B, heads=H, seq_len=T, causal=True,
                           scale=scale, stats_out=st_att)
             w, c, d = L["o"]                                     # inner_attn_ln -> out_proj (+bias, +residual)
@@ -390,17 +432,111 @@ class Decoder(nn.Module):
         ops.gemm(xb, w, logits, bias=d, ln=(cur, c, D, eps))
         return logits
 
-    def forward(self, prev_output_tokens, **kwargs):
-        """Returns ``(logits, extra)``; ``passed_x`` (B,T,D) skips the embedding (README.md:179-193)."""
+    # ---- incremental decoding ------------------------------------------
+    def begin_generation(self, x: torch.Tensor, B: int, T: int, t_max: int, head="all") -> tuple[DecodeState, torch.Tensor]:
+        """Prompt pass: the ordinary layers over x [B*T, D] (updated in place) with every layer's rotated k / v stored
+        in a fresh cache of t_max rows.  head = "all": logits of every row [B*T, vocab]; "last": only the last row of
+        each sequence, in state.logits [B, vocab] (what a generation loop needs)."""
+        if t_max < T:
+            raise ValueError(f"t_max {t_max} is shorter than the prompt ({T})")
+        cfg, p = self.cfg, self._pack()
+        state = DecodeState(cfg, B, t_max, x.device)
+        half = cfg.dim // cfg.heads // 2
+        inv_freq = (1.0 / (10000 ** (torch.arange(0, half) / half))).to(device=x.device, dtype=torch.float32)
+        state.tabs = ops.xpos_tables(p["xpos_scale"], inv_freq, t_max, (-T) // 2, float(cfg.xpos_scale_base), x.device)
+        if head == "all":
+            out = self.run_layers(x, B, T, state=state)
+        else:
+            self.run_layers(x, B, T, head=False, state=state)
+            xb = self._ws.get("xb", (B * T, cfg.dim), torch.bfloat16, x.device)
+            w, c, d = p["out"]                               # decoder.layer_norm -> output_projection, last rows only
+            ops.decode_linear(xb.view(B, T, cfg.dim)[:, T - 1], w, bias=d, ln_c=c, eps=cfg.eps, out=state.logits)
+            out = state.logits
+        state.pos.fill_(T)
+        state.length = T
+        return state, out
+
+    def decode_step(self, state: DecodeState):
+        """One new token per sequence: embeds state.tok at position state.pos, appends its k / v to the cache, leaves
+        the next-token logits in state.logits.  Does not advance the position (kx_argmax_advance does).  5 launches
+        per layer, all reading the position from device memory, so the sequence is CUDA-graph replayable."""
+        p = self._pack()
+        ops.decode_embed(state.tok, p["embed"], p["pos"], state.pos, state.x, state.xb, state.err)
+        self._decode_layers(state)
+
+    def _decode_layers(self, state: DecodeState):
+        cfg, p = self.cfg, self._pack()
+        D, H, eps = cfg.dim, cfg.heads, cfg.eps
+        scale = (D // H) ** -0.5
+        for li, L in enumerate(p["layers"]):
+            w, c, d = L["qkv"]
+            ops.decode_linear(state.xb, w, bias=d, ln_c=c, eps=eps,
+                              qkv=(state.q, state.k[li], state.v[li], state.t_max, state.pos, state.tabs))
+            ops.decode_attention(state.q, state.k[li], state.v[li], state.att, t_max=state.t_max, heads=H, pos=state.pos,
+                                 scale=scale, scratch=state.scratch, counters=state.counters)
+            w, c, d = L["o"]
+            ops.decode_linear(state.att, w, bias=d, ln_c=c, eps=eps, res=(state.x, state.xb))
+            w, c, d = L["fc1"]
+            ops.decode_linear(state.xb, w, bias=d, ln_c=c, eps=eps, act=_abi.KX_ACT_GELU, out=state.mid)
+            w, c, d = L["fc2"]
+            ops.decode_linear(state.mid, w, bias=d, ln_c=c, eps=eps, res=(state.x, state.xb))
+        w, c, d = p["out"]
+        ops.decode_linear(state.xb, w, bias=d, ln_c=c, eps=eps, out=state.logits)
+
+    def advance(self, state: DecodeState, history=None, forced=None, move=True):
+        """Greedy choice from state.logits into state.tok (or the forced token), optional history column, position += 1."""
+        ops.argmax_advance(state.logits, state.tok, step=state.step, counter=state.counter,
+                           pos=state.pos if move else None, history=history, forced=forced)
+        if move:
+            state.length += 1
+
+    def forward(self, prev_output_tokens, incremental_state=None, token_embeddings=None, **kwargs):
+        """Returns ``(logits, extra)``; ``passed_x`` (B,T,D) skips the embedding (README.md:179-193).
+
+        ``incremental_state`` follows torchscale's generation protocol (SURVEY.md A.4 [recall]): create it as
+        ``{"is_first_step": True}`` for the prompt pass (all rows run and are cached; optional ``"max_length"`` sizes the
+        cache, default = the positional table), set ``is_first_step`` to ``False`` and call again with the whole prefix
+        (only its last token is embedded, at position ``len(prefix) + 1``) for every following token; logits are then
+        (B, 1, vocab).  The cache lives under ``incremental_state["kx_state"]`` (a DecodeState)."""
         passed = kwargs.get("passed_x", None)
+        extra = {"inner_states": None, "l_aux": [None] * len(self.layers), "attn": None}
+        if incremental_state is not None and not incremental_state.get("is_first_step", False):
+            state = incremental_state.get("kx_state")
+            if state is None:
+                raise ValueError("incremental_state has no cache: run the prompt pass with is_first_step=True first")
+            if state.length + 1 > state.t_max:
+                raise ValueError(f"the KV cache is full ({state.t_max} rows); pass a larger incremental_state['max_length']")
+            if passed is not None:                                          # an already embedded (B,1,D) row
+                _require_cuda(passed, "passed_x")
+                if passed.shape[0] != state.batch or passed.shape[1] != 1:
+                    raise ValueError("after the first step passed_x must be (B, 1, D)")
+                state.x.copy_(passed[:, 0])
+                ops.cast_bf16(state.x, state.xb)
+                self._decode_layers(state)
+            else:
+                _require_cuda(prev_output_tokens, "prev_output_tokens")
+                self._check_tokens(prev_output_tokens)
+                if prev_output_tokens.shape[0] != state.batch or prev_output_tokens.shape[1] != state.length + 1:
+                    raise ValueError(f"prev_output_tokens must be the whole prefix, (B={state.batch}, {state.length + 1}); got "
+                                     f"{tuple(prev_output_tokens.shape)}")
+                state.tok.copy_(prev_output_tokens[:, -1])
+                self.decode_step(state)
+            logits = state.logits.clone()
+            self.advance(state)
+            return logits.view(state.batch, 1, -1), extra
         if passed is None:
-            x, _ = self.forward_embedding(prev_output_tokens)
+            x, _ = self.forward_embedding(prev_output_tokens, token_embeddings)
         else:
             _require_cuda(passed, "passed_x")
             x = passed.to(torch.float32).clone()          # layers update the stream in place
         B, T, D = x.shape
+        if incremental_state is not None:                 # prompt pass of a generation
+            t_max = int(incremental_state.get("max_length", self.cfg.max_positions - 2))
+            state, logits = self.begin_generation(x.view(B * T, D), B, T, t_max)
+            incremental_state["kx_state"] = state
+            return logits.view(B, T, -1), extra
         logits = self.run_layers(x.view(B * T, D), B, T).view(B, T, -1)
-        return logits, {"inner_states": None, "l_aux": [None] * len(self.layers), "attn": None}
+        return logits, extra
 
 
 # --------------------------------------------------------------------------- shared top-level plumbing
@@ -425,6 +561,52 @@ class _KosmosBase(nn.Module):
         r = super().load_state_dict(*a, **kw)
         self.refresh_weights()
         return r
+
+    def _generate(self, x0: torch.Tensor, B: int, T: int, max_new_tokens: int, forced=None, return_logits=False,
+                  cuda_graph=True):
+        """Greedy continuation of the embedded prompt x0 [B*T, D]: prompt pass with cache fill and
+        the LM head on the last rows only, then max_new_tokens - 1 one-token steps.  The step + greedy choice is
+        captured once as a CUDA graph and replayed (the position is device-resident), so no host value is read until
+        the token history is returned.  ``forced`` (B, n) int64 replaces the greedy choice (teacher forcing);
+        ``return_logits`` also returns the (B, n, vocab) distributions (eager steps, one clone per step)."""
+        if max_new_tokens < 1:
+            raise ValueError("max_new_tokens must be >= 1")
+        dec = self.decoder
+        dev = x0.device
+        state, _ = dec.begin_generation(x0, B, T, T + max_new_tokens, head="last")
+        history = torch.zeros(B, max_new_tokens, dtype=torch.int64, device=dev)
+        if forced is not None:
+            _require_cuda(forced, "forced tokens")
+            if forced.dtype != torch.int64 or tuple(forced.shape) != (B, max_new_tokens):
+                raise TypeError(f"forced tokens must be int64 (B={B}, {max_new_tokens})")
+            forced = forced.contiguous()
+        outs = [state.logits.clone()] if return_logits else None
+        dec.advance(state, history=history, forced=forced, move=False)       # token 0 comes from the prompt's last row
+        steps = max_new_tokens - 1
+        if return_logits or not cuda_graph or steps < 2:
+            for _ in range(steps):
+                dec.decode_step(state)
+                if return_logits:
+                    outs.append(state.logits.clone())
+                dec.advance(state, history=history, forced=forced)
+        else:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):                # capture only records: nothing runs, the cache is untouched
+                dec.decode_step(state)
+                dec.advance(state, history=history, forced=forced)
+            nodes = ops.launch_count() - n0
+            state.length -= 1                            # the captured call counted a step that has not run yet
+            state.graph = graph
+            for _ in range(steps):
+                graph.replay()
+                ops.count_graph_replay(nodes)
+                state.length += 1
+        self._last_decode_state = state
+        if return_logits:
+            return history, torch.stack(outs, 1)
+        return history
 
 
 def _embed_init(emb: nn.Embedding):
@@ -619,6 +801,35 @@ class Kosmos(_KosmosBase):
             self._errf = f
         return f
 
+    def _prepare_inputs(self, text_tokens, images, image_positions, extra_rows=0):
+        """Argument checks shared by forward and generate -> (text_tokens, images (B*m,3,H,W) fp32, img_rows, T)."""
+        cfg = self.cfg
+        _require_cuda(text_tokens, "text_tokens")
+        _require_cuda(images, "images")
+        if text_tokens.dtype != torch.int64 or text_tokens.ndim != 2:
+            raise TypeError("text_tokens must be an int64 tensor of shape (B, T_text)")
+        if images.ndim not in (4, 5) or tuple(images.shape[-3:]) != (3, cfg.image, cfg.image):
+            raise ValueError(f"Input image size ({tuple(images.shape[1:])}) doesn't match model "
+                             f"(3, {cfg.image}, {cfg.image}).")
+        if images.shape[0] != text_tokens.shape[0]:
+            raise ValueError("text_tokens and images must have the same batch size")
+        m = images.shape[1] if images.ndim == 5 else 1
+        pos = [2] if image_positions is None else [int(p) for p in image_positions]
+        if len(pos) != m or m < 1 or m > _abi.KX_MAX_IMAGES:
+            raise ValueError(f"{m} images per sequence need {m} image_positions (at most {_abi.KX_MAX_IMAGES}), got {pos}")
+        if sorted(pos) != pos or pos[0] < 0 or pos[-1] > text_tokens.shape[1]:
+            raise ValueError(f"image_positions {pos} must be ascending text-token indices in [0, {text_tokens.shape[1]}]")
+        if image_positions is None and text_tokens.shape[1] < 2:
+            raise ValueError("text_tokens needs at least 2 tokens (image features are spliced after token 1)")
+        img_rows = tuple(p + i * cfg.p_latents for i, p in enumerate(pos))     # first spliced row of each image
+        T = text_tokens.shape[1] + cfg.p_latents * m
+        if T + extra_rows + 2 > cfg.max_positions:
+            raise ValueError(f"spliced sequence length {T + extra_rows} exceeds the positional table: max is "
+                             f"{cfg.max_positions - 2} (construct Kosmos(max_positions=...) to extend it)")
+        # HF casts pixels to the weight dtype ([HF]:208-209)
+        images = images.to(torch.float32).reshape(-1, 3, cfg.image, cfg.image).contiguous()
+        return text_tokens.contiguous(), images, img_rows, T
+
     def forward(self, text_tokens: torch.Tensor, images: torch.Tensor, image_positions=None, **kwargs):
         """Reference call (model.py:208-253): images (B,3,H,W), features spliced in front of text token 2.
         Extension (BASELINE.json configs[4]): images (B,m,3,H,W) with ``image_positions`` = m ascending text-token
@@ -627,31 +838,7 @@ class Kosmos(_KosmosBase):
             raise TypeError("text_tokens and images must be instances of torch.Tensor")
         cfg = self.cfg
         try:
-            _require_cuda(text_tokens, "text_tokens")
-            _require_cuda(images, "images")
-            if text_tokens.dtype != torch.int64 or text_tokens.ndim != 2:
-                raise TypeError("text_tokens must be an int64 tensor of shape (B, T_text)")
-            if images.ndim not in (4, 5) or tuple(images.shape[-3:]) != (3, cfg.image, cfg.image):
-                raise ValueError(f"Input image size ({tuple(images.shape[1:])}) doesn't match model "
-                                 f"(3, {cfg.image}, {cfg.image}).")
-            if images.shape[0] != text_tokens.shape[0]:
-                raise ValueError("text_tokens and images must have the same batch size")
-            m = images.shape[1] if images.ndim == 5 else 1
-            pos = [2] if image_positions is None else [int(p) for p in image_positions]
-            if len(pos) != m or m < 1 or m > _abi.KX_MAX_IMAGES:
-                raise ValueError(f"{m} images per sequence need {m} image_positions (at most {_abi.KX_MAX_IMAGES}), got {pos}")
-            if sorted(pos) != pos or pos[0] < 0 or pos[-1] > text_tokens.shape[1]:
-                raise ValueError(f"image_positions {pos} must be ascending text-token indices in [0, {text_tokens.shape[1]}]")
-            if image_positions is None and text_tokens.shape[1] < 2:
-                raise ValueError("text_tokens needs at least 2 tokens (image features are spliced after token 1)")
-            img_rows = tuple(p + i * cfg.p_latents for i, p in enumerate(pos))     # first spliced row of each image
-            T = text_tokens.shape[1] + cfg.p_latents * m
-            if T + 2 > cfg.max_positions:
-                raise ValueError(f"spliced sequence length {T} exceeds the positional table: max is "
-                                 f"{cfg.max_positions - 2} (construct Kosmos(max_positions=...) to extend it)")
-            # HF casts pixels to the weight dtype ([HF]:208-209)
-            images = images.to(torch.float32).reshape(-1, 3, cfg.image, cfg.image).contiguous()
-            text_tokens = text_tokens.contiguous()
+            text_tokens, images, img_rows, T = self._prepare_inputs(text_tokens, images, image_positions)
         except Exception as e:
             log.error(f"Failed during input validation: {e}")
             raise
@@ -665,6 +852,26 @@ class Kosmos(_KosmosBase):
         except Exception as e:
             log.error(f"Failed during model forward pass: {e}")
             raise
+
+    @torch.no_grad()
+    def generate(self, text_tokens: torch.Tensor, images: torch.Tensor, max_new_tokens: int, image_positions=None,
+                 forced_tokens=None, return_logits: bool = False, cuda_graph: bool = True):
+        """Greedy continuation (the reference stops at logits, torchscale's ``incremental_state`` is the
+        decoding path it would use): vision tower -> resampler -> splice -> prompt pass with KV-cache fill, then one-token
+        steps on the weight-streaming kernels.  Returns int64 (B, max_new_tokens) on the device (and the (B, n, vocab)
+        logits with ``return_logits``).  New tokens continue the spliced sequence: positions T+2, T+3, ..."""
+        if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):
+            raise TypeError("text_tokens and images must be instances of torch.Tensor")
+        text_tokens, images, img_rows, T = self._prepare_inputs(text_tokens, images, image_positions, int(max_new_tokens))
+        cfg = self.cfg
+        B, m = text_tokens.shape[0], len(img_rows)
+        dp = self.decoder._pack()
+        x0 = self._ws.get("x0", (B * T, cfg.dim), torch.float32, text_tokens.device)
+        xv = self._vit(images, media=m)
+        self._perceive_project(xv, B, x0, T, img_rows)
+        ops.embed_splice_pos(text_tokens, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=cfg.p_latents,
+                             err_flag=self._err_flag())
+        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph)
 
     def check_tokens(self):
         """Host-side check (one sync) that no token id of any forward so far was out of range."""
@@ -744,6 +951,22 @@ class KosmosLanguage(_KosmosBase):
         x0 = self._ws.get("x0", (B * T, self.cfg.dim), torch.float32, x.device)
         ops.embed_splice_pos(x.contiguous(), dp["embed"], dp["pos"], x0)
         return self.decoder.run_layers(x0, B, T).view(B, T, self.cfg.vocab)
+
+    @torch.no_grad()
+    def generate(self, x: torch.Tensor, max_new_tokens: int, forced_tokens=None, return_logits: bool = False,
+                 cuda_graph: bool = True):
+        """Greedy continuation of the token prefix x (B, T) through the KV-cache path (see Kosmos.generate)."""
+        _require_cuda(x, "x")
+        if x.dtype != torch.int64 or x.ndim != 2:
+            raise TypeError("x must be an int64 tensor of shape (B, T)")
+        B, T = x.shape
+        if T + int(max_new_tokens) + 2 > self.cfg.max_positions:
+            raise ValueError(f"sequence length {T + int(max_new_tokens)} exceeds the positional table: max is "
+                             f"{self.cfg.max_positions - 2}")
+        dp = self.decoder._pack()
+        x0 = self._ws.get("x0", (B * T, self.cfg.dim), torch.float32, x.device)
+        ops.embed_splice_pos(x.contiguous(), dp["embed"], dp["pos"], x0)
+        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph)
 
 
 class _nullctx:

@@ -412,6 +412,82 @@ def broadcast_rows(src, dst, copies):
     return dst
 
 
+# ---- incremental decoding ----------------------------------------------------------------------
+def decode_linear(a, w, *, bias=None, ln_c=None, eps=1e-5, act=_abi.KX_ACT_NONE, out=None, res=None, qkv=None):
+    """One-token Linear for batch <= 32 rows (kx_decode_linear).  Exactly one of:
+      out=tensor (bf16 / fp32 [B, >=N])            plain (+act)
+      res=(x fp32 [B, N], xb bf16 [B, N])          x += y in place, xb = bf16(x)
+      qkv=(q_out, k_cache, v_cache, t_max, pos, tabs)   q|k|v with xPos at *pos, k / v written into the cache."""
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    g = _abi.DecodeLinearArgs()
+    g.act, g.bias, g.ln_c, g.ln_eps = act, _ptr(bias), _ptr(ln_c), eps
+    N, K = w.shape
+    if a.shape[1] != K:
+        raise ValueError(f"decode_linear: K mismatch {tuple(a.shape)} vs {tuple(w.shape)}")
+    if out is not None:
+        g.mode, g.out, g.ld_out, g.out_f32 = _abi.KX_DEC_PLAIN, out.data_ptr(), out.stride(0), int(out.dtype == torch.float32)
+        if out.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("decode_linear: out must be fp32 or bf16")
+    elif res is not None:
+        x, xb = res
+        _req(x, torch.float32, "x"); _req(xb, torch.bfloat16, "xb")
+        g.mode, g.x, g.ld_x, g.xb, g.ld_xb = _abi.KX_DEC_RESIDUAL, x.data_ptr(), x.stride(0), xb.data_ptr(), xb.stride(0)
+    elif qkv is not None:
+        q_out, k_cache, v_cache, t_max, pos, tabs = qkv
+        _req(q_out, torch.bfloat16, "q_out"); _req(k_cache, torch.bfloat16, "k_cache"); _req(v_cache, torch.bfloat16, "v_cache")
+        if tabs.shape[1] < t_max:
+            raise ValueError("decode_linear: the xPos tables must cover t_max positions")
+        g.mode, g.q_out, g.ld_q = _abi.KX_DEC_QKV, q_out.data_ptr(), q_out.stride(0)
+        g.k_cache, g.v_cache, g.t_max, g.d_model, g.pos = k_cache.data_ptr(), v_cache.data_ptr(), t_max, N // 3, pos.data_ptr()
+        g.xq_cos, g.xq_sin, g.xk_cos, g.xk_sin = (t.data_ptr() for t in tabs)
+    else:
+        raise ValueError("decode_linear: give out, res or qkv")
+    with _Timed(f"decode_linear {N}x{K}", 2.0 * a.shape[0] * N * K, 2.0 * N * K):
+        check(lib.kx_decode_linear(a.data_ptr(), a.stride(0), a.shape[0], w.data_ptr(), w.stride(0), N, K, g, _stream()),
+              "kx_decode_linear")
+
+
+def decode_attn_scratch(batch, heads, t_max, device):
+    n = int(lib.kx_decode_attn_scratch_bytes(batch, heads, t_max))
+    return (torch.empty(max(n // 4, 1), dtype=torch.float32, device=device),
+            torch.zeros(batch * heads, dtype=torch.int32, device=device))
+
+
+def decode_attention(q, k_cache, v_cache, out, *, t_max, heads, pos, scale, scratch, counters):
+    _req(q, torch.bfloat16, "q"); _req(out, torch.bfloat16, "out")
+    B = q.shape[0]
+    with _Timed("decode_attn", 0.0, 0.0):
+        check(lib.kx_decode_attn(q.data_ptr(), q.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), t_max, B, heads,
+                                 pos.data_ptr(), float(scale), scratch.data_ptr(), counters.data_ptr(), out.data_ptr(),
+                                 out.stride(0), _stream()), "kx_decode_attn")
+    return out
+
+
+def kv_cache_store(qkv, k_cache, v_cache, *, batch, seq_len, d_model, t_max):
+    _req(qkv, torch.bfloat16, "qkv")
+    with _Timed("kv_cache_store", 0.0, 8.0 * batch * seq_len * d_model):
+        check(lib.kx_kv_cache_store(qkv.data_ptr(), qkv.stride(0), batch, seq_len, d_model, k_cache.data_ptr(),
+                                    v_cache.data_ptr(), t_max, _stream()), "kx_kv_cache_store")
+
+
+def decode_embed(tokens, embed_table, pos_table, pos, x, xb, err_flag=None):
+    _req(tokens, torch.int64, "tokens")
+    check(lib.kx_decode_embed(tokens.data_ptr(), tokens.numel(), embed_table.data_ptr(), embed_table.shape[0],
+                              pos_table.data_ptr(), pos_table.shape[0], pos.data_ptr(), embed_table.shape[1], x.data_ptr(),
+                              xb.data_ptr(), _ptr(err_flag), _stream()), "kx_decode_embed")
+
+
+def argmax_advance(logits, tokens_out, *, step, counter, pos=None, history=None, forced=None):
+    _req(logits, torch.float32, "logits")
+    hist_ld = history.shape[1] if history is not None else (forced.shape[1] if forced is not None else 0)
+    if history is not None and forced is not None and forced.shape[1] != history.shape[1]:
+        raise ValueError("argmax_advance: forced and history must have the same row length")
+    check(lib.kx_argmax_advance(logits.data_ptr(), logits.stride(0), logits.shape[0], logits.shape[1], _ptr(forced),
+                                tokens_out.data_ptr(), _ptr(history), hist_ld, _ptr(pos), step.data_ptr(),
+                                counter.data_ptr(), _stream()), "kx_argmax_advance")
+
+
 _graph_launches = 0
 
 

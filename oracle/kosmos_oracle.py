@@ -387,7 +387,11 @@ class MultiheadAttention(nn.Module):
         self.xpos = XPOS(self.hd, cfg.xpos_scale_base)
         self.use_xpos = True            # tests switch it off to cross-check against HF Kosmos-2's block
 
-    def forward(self, x, attn_mask):
+    def forward(self, x, attn_mask, incremental_state=None, is_first_step=False):
+        """``incremental_state`` (a per-layer dict) follows torchscale's MultiheadAttention [recall]: the UN-rotated
+        keys / values of every step are appended to ``prev_key`` / ``prev_value`` (B, heads, src_len, head_dim) and
+        xPos is re-applied to the whole key sequence each step; after the first step the single query is rotated
+        with ``offset = src_len - 1``."""
         B, T, D = x.shape
         e = self.emu
         q = _linear(e, x, _inner(self.q_proj))
@@ -399,13 +403,23 @@ class MultiheadAttention(nn.Module):
             return t.view(B, T, self.h, self.hd).transpose(1, 2).reshape(B * self.h, T, self.hd)
 
         q, k, v = heads(q), heads(k), e.r(heads(v))
+        offset = 0
+        if incremental_state is not None:
+            if "prev_key" in incremental_state:
+                k = torch.cat([incremental_state["prev_key"].view(B * self.h, -1, self.hd), k], dim=1)
+                v = torch.cat([incremental_state["prev_value"].view(B * self.h, -1, self.hd), v], dim=1)
+            incremental_state["prev_key"] = k.view(B, self.h, -1, self.hd)
+            incremental_state["prev_value"] = v.view(B, self.h, -1, self.hd)
+            if not is_first_step:
+                offset = k.size(1) - 1
         if self.use_xpos:
             k = self.xpos(k, offset=0, downscale=True)
-            q = self.xpos(q, offset=0, downscale=False)
+            q = self.xpos(q, offset=offset, downscale=False)
         k, q = e.r(k), e.r(q)
         w = torch.bmm(q, k.transpose(1, 2))
         w = torch.nan_to_num(w)
-        w = w + attn_mask[None]
+        if attn_mask is not None:
+            w = w + attn_mask[None]
         m = w.amax(-1, keepdim=True)
         p = torch.exp(w - m)                                 # == softmax(w, dtype=fp32) numerator
         a = torch.bmm(e.r(p), v) / p.sum(-1, keepdim=True)
@@ -424,9 +438,9 @@ class DecoderLayer(nn.Module):
         self.ffn = _wrap(cfg, lambda: FeedForwardNetwork(cfg, emu))
         self.final_layer_norm = _wrap(cfg, lambda: nn.LayerNorm(cfg.dim, eps=cfg.eps))
 
-    def forward(self, x, mask):
+    def forward(self, x, mask, incremental_state=None, is_first_step=False):
         r = x
-        x = self.self_attn(_inner(self.self_attn_layer_norm)(x), mask)
+        x = self.self_attn(_inner(self.self_attn_layer_norm)(x), mask, incremental_state, is_first_step)
         x = r + x
         r = x
         x = _inner(self.ffn)(_inner(self.final_layer_norm)(x))
@@ -437,7 +451,7 @@ class PositionalEmbedding(nn.Embedding):
     """torchscale.component.embedding.PositionalEmbedding: positions start
     at 2 ("consistent with fairseq"); only ``x.size(1)`` of the argument is used."""
 
-    def forward(self, x, positions=None):
+    def forward(self, x, positions=None, **kwargs):
         if positions is None:
             positions = torch.arange(2, x.size(1) + 2, device=x.device).long().unsqueeze(0)
         return F.embedding(positions, self.weight, self.padding_idx)
@@ -462,24 +476,47 @@ class Decoder(nn.Module):
             if "fc1" in name or "fc2" in name or "out_proj" in name or "v_proj" in name:
                 p.data.mul_(init_scale)
 
+    @staticmethod
+    def is_first_step(incremental_state):
+        if incremental_state is None:
+            return False
+        return incremental_state.get("is_first_step", False)
+
     def forward_embedding(self, tokens, token_embedding=None, incremental_state=None):
-        positions = self.embed_positions(tokens)
+        positions = self.embed_positions(tokens, incremental_state=incremental_state)
+        if incremental_state is not None and not self.is_first_step(incremental_state):
+            # later decoding steps: the caller passes the whole prefix (fairseq style), only its last
+            # token is embedded and it takes the last position, len + 1  [recall: torchscale decoder.py]
+            tokens = tokens[:, -1:]
+            positions = positions[:, -1:]
+            if token_embedding is not None:
+                token_embedding = token_embedding[:, -1:]
         if token_embedding is None:
             token_embedding = self.embed_tokens(tokens)
         x = embed = self.embed_scale * token_embedding
         x = x + positions
         return x, embed                                      # dropout p=0.1 is identity in eval
 
-    def forward(self, prev_output_tokens, **kwargs):
+    def forward(self, prev_output_tokens, incremental_state=None, token_embeddings=None, **kwargs):
+        """``incremental_state``: torchscale's generation protocol [recall] — a dict the caller creates as
+        ``{"is_first_step": True}`` for the prompt pass (all positions run, causal mask, K/V cached per layer under
+        integer keys) and flips to ``False`` for the following one-token steps (no mask, K/V appended)."""
         if kwargs.get("passed_x", None) is None:
-            x, _ = self.forward_embedding(prev_output_tokens)
+            x, _ = self.forward_embedding(prev_output_tokens, token_embeddings, incremental_state)
         else:
             x = kwargs["passed_x"]
+        first = self.is_first_step(incremental_state)
         T = x.size(1)
         inner_states = [x]
-        for layer in self.layers:
-            mask = torch.triu(torch.zeros([T, T]).float().fill_(float("-inf")).type_as(x), 1)
-            x = layer(x, mask)
+        for idx, layer in enumerate(self.layers):
+            if incremental_state is None or first:
+                mask = torch.triu(torch.zeros([T, T]).float().fill_(float("-inf")).type_as(x), 1)
+            else:
+                mask = None
+            st = None
+            if incremental_state is not None:
+                st = incremental_state.setdefault(idx, {})
+            x = layer(x, mask, st, first)
             inner_states.append(x)
         x = self.layer_norm(x)
         x = F.linear(self.emu.r(x), self.emu.r(self.output_projection.weight))
@@ -559,6 +596,28 @@ class KosmosOracle(nn.Module):
             raise TypeError("text_tokens and images must be instances of torch.Tensor")
         model_input = self.embed_inputs(text_tokens, images, image_positions)
         return self.decoder(model_input, passed_x=model_input)[0]              # model.py:250
+
+    @torch.no_grad()
+    def generate(self, text_tokens, images, max_new_tokens, image_positions=None, forced=None):
+        """Greedy continuation through torchscale's incremental protocol: the prompt pass runs
+        ``decoder(x, incremental_state={"is_first_step": True}, passed_x=x)`` on the spliced input of model.py:230-244,
+        every later step ``decoder(prefix, incremental_state=st)`` with only the prefix's last token embedded at
+        position ``len(prefix) + 1``.  ``forced`` (B, n) replaces the argmax choice (teacher forcing for parity
+        tests).  Returns (tokens (B, n), logits (B, n, vocab)); logits[:, i] is the distribution token i was drawn from."""
+        x = self.embed_inputs(text_tokens, images, image_positions)
+        st = {"is_first_step": True}
+        logits = self.decoder(x, incremental_state=st, passed_x=x)[0][:, -1]
+        st["is_first_step"] = False
+        prefix = torch.zeros(x.size(0), x.size(1), dtype=torch.long)      # only its length and last token are read
+        toks, outs = [], []
+        for i in range(max_new_tokens):
+            nxt = logits.argmax(-1) if forced is None else forced[:, i]
+            toks.append(nxt)
+            outs.append(logits)
+            if i + 1 < max_new_tokens:
+                prefix = torch.cat([prefix, nxt[:, None]], dim=1)
+                logits = self.decoder(prefix, incremental_state=st)[0][:, -1]
+        return torch.stack(toks, 1), torch.stack(outs, 1)
 
     @staticmethod
     def loss_targets(text_tokens, n_latents, image_positions=None, n_images=1):

@@ -44,6 +44,46 @@ def test_gemm_args_struct_matches_header():
     assert fields == [f[0] for f in _abi.GemmArgs._fields_]
 
 
+def test_decode_linear_args_struct_matches_header():
+    from kosmosx import _abi
+    src = open(HEADER).read()
+    body = re.search(r"typedef struct kx_decode_linear_args \{(.*?)\} kx_decode_linear_args;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            fields.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+    assert fields == [f[0] for f in _abi.DecodeLinearArgs._fields_]
+
+
+def test_decode_entry_points_validate_arguments():
+    """Incremental-decoding entry points: bad shapes are rejected before any launch; without a GPU a
+    well-formed call reports KX_ERR_NO_DEVICE (no CPU path)."""
+    from kosmosx import _abi
+    buf = (ctypes.c_char * 65536)()
+    addr = (ctypes.addressof(buf) + 255) & ~255
+    g = _abi.DecodeLinearArgs()
+    g.mode, g.out, g.ld_out, g.out_f32 = _abi.KX_DEC_PLAIN, addr, 64, 1
+    assert _abi.lib.kx_decode_linear(addr, 48, 4, addr, 48, 64, 48, g, None) == -1            # K % 32 != 0
+    assert "K % 32" in _abi.last_error()
+    assert _abi.lib.kx_decode_linear(addr, 64, 33, addr, 64, 64, 64, g, None) == -1           # batch > KX_DECODE_MAX_BATCH
+    g.mode = _abi.KX_DEC_QKV
+    assert _abi.lib.kx_decode_linear(addr, 64, 4, addr, 64, 192, 64, g, None) == -1           # caches / tables missing
+    assert "KX_DEC_QKV" in _abi.last_error()
+    g.mode = 7
+    assert _abi.lib.kx_decode_linear(addr, 64, 4, addr, 64, 64, 64, g, None) == -1
+    assert _abi.lib.kx_kv_cache_store(addr, 192, 1, 9, 64, addr, addr, 8, None) == -1         # prompt longer than the cache
+    assert _abi.lib.kx_decode_attn(addr, 64, addr, addr, 0, 1, 1, addr, 0.125, addr, addr, addr, 64, None) == -1
+    assert _abi.lib.kx_decode_attn_scratch_bytes(2, 4, 300) == 2 * 4 * 3 * 66 * 4
+    if not torch.cuda.is_available():
+        g.mode = _abi.KX_DEC_PLAIN
+        assert _abi.lib.kx_decode_linear(addr, 64, 4, addr, 64, 64, 64, g, None) == -2
+        assert _abi.lib.kx_kv_cache_store(addr, 192, 1, 8, 64, addr, addr, 8, None) == -2
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_entry_points_fail_loudly_without_gpu():
     from kosmosx import _abi

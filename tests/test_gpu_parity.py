@@ -53,7 +53,7 @@ def _kernel_cases():
 
 @pytest.mark.parametrize("case", ["gemm_basic", "gemm_shapes", "gemm_epilogue", "xpos", "gemm_qkv", "attn", "layernorm",
                                   "ln_fold", "embed", "perceiver_attn", "gemm_trans", "train_elementwise", "attn_bwd",
-                                  "perceiver_bwd"])
+                                  "perceiver_bwd", "decode"])
 def test_kernel_against_torch_fp32(case):
     """Each kernel alone against a plain PyTorch fp32 restatement of the same op (tools/kernel_check.py)."""
     import kernel_check as kc
@@ -273,6 +273,91 @@ def test_language_model_matches_oracle():
 
 
 # --------------------------------------------------------------------------- full size (BASELINE.json configs)
+
+# --------------------------------------------------------------------------- incremental decoding
+TOL_DEC_SELF = 3e-2      # KV-cache path vs the same model's full forward (bf16 operands both ways; measured ~1e-2)
+
+
+def test_tiny_incremental_decoding_vs_oracle(tiny_pair):
+    """generate() through the KV-cache kernels against the oracle's restatement of torchscale's incremental protocol
+    (teacher-forced so both see the same tokens), against the model's own full forward over prompt + continuation,
+    graph replay against eager stepping, and the torchscale calling protocol through Decoder.forward."""
+    import kosmos_oracle as ko
+    ref, mine, oc = tiny_pair
+    B, t_text, n = 2, 12, 7
+    text, images = ko.make_inputs(oc, B, t_text, seed=1)
+    forced = torch.randint(0, oc.vocab, (B, n), generator=torch.Generator().manual_seed(5))
+    ref.set_emulation(True)
+    _, want = ref.generate(text, images, n, forced=forced)
+    ref.set_emulation(False)
+    n0 = __import__("kosmosx").ops.launch_count()
+    toks, got = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True)
+    torch.cuda.synchronize()
+    assert __import__("kosmosx").ops.launch_count() > n0
+    assert torch.equal(toks.cpu(), forced) and got.shape == (B, n, oc.vocab) and torch.isfinite(got).all()
+    e = _err(got, want)
+    print(f"incremental decoding vs bf16-emulating oracle: max={e[0]:.3e} rms={e[1]:.3e}")
+    assert e[0] <= TOL_EMU_TINY and e[1] <= RMS_EMU_TINY
+    # the model's own full forward over prompt + forced continuation: rows T0-1 .. T0+n-2
+    t0 = t_text + oc.p_latents
+    full = mine(torch.cat([text, forced[:, :-1]], 1).cuda(), images.cuda())
+    es = _err(got, full[:, t0 - 1:])
+    print(f"incremental decoding vs own full forward: max={es[0]:.3e} rms={es[1]:.3e}")
+    assert es[0] <= TOL_DEC_SELF
+    # greedy: CUDA-graph replay == eager stepping, and deterministic
+    g1 = mine.generate(text.cuda(), images.cuda(), n)
+    g2 = mine.generate(text.cuda(), images.cuda(), n, cuda_graph=False)
+    g3 = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda())
+    assert torch.equal(g1, g2) and torch.equal(g3.cpu(), forced)
+    assert torch.equal(g1[:, 0], mine(text.cuda(), images.cuda())[:, -1].argmax(-1))
+    # torchscale's protocol: decoder(x, incremental_state={"is_first_step": True}, passed_x=x), then whole prefixes
+    with torch.no_grad():
+        x = ref.embed_inputs(text, images).cuda()
+    st = {"is_first_step": True, "max_length": t0 + n}
+    first, extra = mine.decoder(x, incremental_state=st, passed_x=x)
+    assert first.shape == (B, t0, oc.vocab) and "kx_state" in st and st["kx_state"].length == t0
+    assert _err(first[:, -1], got[:, 0])[0] <= TOL_DEC_SELF
+    st["is_first_step"] = False
+    prefix = torch.zeros(B, t0, dtype=torch.int64, device="cuda")
+    for i in range(n - 1):
+        prefix = torch.cat([prefix, forced[:, i:i + 1].cuda()], 1)
+        step_logits, _ = mine.decoder(prefix, incremental_state=st)
+        assert step_logits.shape == (B, 1, oc.vocab)
+        # (the prompt rows came from the oracle's fp32 ViT / resampler here, from the bf16 kernels in generate())
+        assert _err(step_logits[:, 0], got[:, i + 1])[0] <= TOL_DEC_SELF, "Decoder.forward protocol and generate() disagree"
+    with pytest.raises(ValueError):
+        mine.decoder(prefix, incremental_state=st)                    # prefix did not grow
+    with pytest.raises(ValueError):
+        mine.decoder(prefix, incremental_state={"is_first_step": False})
+    with pytest.raises(ValueError):
+        mine.generate(text.cuda(), images.cuda(), oc.max_positions)   # beyond the position table
+
+
+def test_language_model_generate_batches(tiny_cfgs):
+    """KosmosLanguage.generate at batch sizes that use every batch-group width of kx_decode_linear (<=8, <=16, <=32)."""
+    import kosmos_oracle as ko
+    from kosmosx import KosmosLanguage
+    oc, _ = tiny_cfgs
+    lm_ref = ko.KosmosLanguageOracle(oc)
+    lm = KosmosLanguage(vocab_size=oc.vocab, dim=oc.dim, depth=oc.layers, ffn_dim=oc.ffn, decoder_heads=oc.heads,
+                        max_positions=oc.max_positions)
+    lm.load_state_dict(lm_ref.state_dict())
+    lm = lm.cuda()
+    for B in (1, 11, 32):
+        x = torch.randint(0, oc.vocab, (B, 9), generator=torch.Generator().manual_seed(B))
+        n = 5
+        forced = torch.randint(0, oc.vocab, (B, n), generator=torch.Generator().manual_seed(100 + B))
+        toks, got = lm.generate(x.cuda(), n, forced_tokens=forced.cuda(), return_logits=True)
+        full = lm(torch.cat([x, forced[:, :-1]], 1).cuda())
+        e = _err(got, full[:, 8:])
+        print(f"KosmosLanguage.generate B={B}: vs own full forward max={e[0]:.3e}")
+        assert e[0] <= TOL_DEC_SELF
+        with torch.no_grad():
+            want = lm_ref(torch.cat([x, forced[:, :-1]], 1))[:, 8:]
+        assert _err(got, want)[0] <= TOL_F32_TINY
+    with pytest.raises(ValueError):
+        lm.generate(torch.zeros(33, 4, dtype=torch.int64, device="cuda"), 2)
+
 @pytest.fixture(scope="module")
 def full_pair():
     """Reference-size model (24-layer ViT-L/14 + perceiver + 24-layer d=2048 decoder), weights from the
@@ -338,6 +423,34 @@ def test_full_size_seq2048_properties(full_pair):
     e = _err(one, want)
     print(f"C3 sequence 3 (T=2048) vs bf16-emulating oracle: max={e[0]:.3e} rms={e[1]:.3e}")
     assert e[0] <= 2 * TOL_EMU_FULL
+
+
+def test_full_size_generate_vs_forward_and_oracle(full_pair):
+    """Reference-size decoding (24 layers, d=2048, 32 heads, vocab 32002): KV-cache steps against the model's own full
+    forward over prompt + continuation, and against the CPU oracle's incremental path on one sequence."""
+    import kosmos_oracle as ko
+    ref, mine, oc = full_pair
+    B, t_text, n = 8, 40, 6
+    text, images = ko.make_inputs(oc, B, t_text, seed=3)
+    forced = torch.randint(0, oc.vocab, (B, n), generator=torch.Generator().manual_seed(7))
+    toks, got = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True)
+    t0 = t_text + oc.p_latents
+    full = mine(torch.cat([text, forced[:, :-1]], 1).cuda(), images.cuda())
+    e = _err(got, full[:, t0 - 1:])
+    print(f"full-size incremental decoding vs own full forward: max={e[0]:.3e} rms={e[1]:.3e}")
+    assert e[0] <= TOL_EMU_FULL
+    agree = (got.argmax(-1) == full[:, t0 - 1:].argmax(-1)).float().mean().item()
+    assert agree >= 0.9, agree
+    with torch.no_grad():
+        ref.set_emulation(True)
+        _, want = ref.generate(text[:1], images[:1], n, forced=forced[:1])
+        ref.set_emulation(False)
+    e16 = _err(got[:1], want)
+    print(f"full-size incremental decoding vs bf16-emulating oracle (sequence 0): max={e16[0]:.3e} rms={e16[1]:.3e}")
+    assert e16[0] <= TOL_EMU_FULL
+    g1 = mine.generate(text.cuda(), images.cuda(), n)
+    g2 = mine.generate(text.cuda(), images.cuda(), n, cuda_graph=False)
+    assert torch.equal(g1, g2)
 
 
 def test_full_size_training_gradients_vs_oracle(full_pair):

@@ -195,6 +195,38 @@ def test_language_model_oracle():
     assert y.shape == (2, 9, 777)
 
 
+def test_incremental_decoding_equals_the_full_forward(tiny):
+    """torchscale's incremental_state protocol restated in the oracle: K/V cached un-rotated,
+    xPos re-applied each step with offset = src_len - 1 for the query.  Because xPos is relative, step i's logits must
+    equal row T0-1+i of one full forward over prompt + generated tokens — the property that pins the incremental path."""
+    oc, ref = tiny
+    text, images = ko.make_inputs(oc, 2, 12, seed=1)
+    n = 6
+    toks, lg = ref.generate(text, images, n)
+    assert toks.shape == (2, n) and lg.shape == (2, n, oc.vocab)
+    with torch.no_grad():
+        full = ref(torch.cat([text, toks[:, :-1]], 1), images)
+    t0 = text.shape[1] + oc.p_latents
+    for i in range(n):
+        assert (full[:, t0 - 1 + i] - lg[:, i]).abs().max() < 2e-5
+        assert torch.equal(full[:, t0 - 1 + i].argmax(-1), toks[:, i])
+    # teacher forcing: the forced tokens are what gets embedded, the logits follow them
+    forced = torch.randint(0, oc.vocab, (2, n), generator=torch.Generator().manual_seed(5))
+    ftoks, flg = ref.generate(text, images, n, forced=forced)
+    assert torch.equal(ftoks, forced)
+    with torch.no_grad():
+        full = ref(torch.cat([text, forced[:, :-1]], 1), images)
+    assert (full[:, t0 - 1:] - flg).abs().max() < 2e-5
+    # protocol details: later steps embed only the last token, at position len(prefix) + 1
+    dec = ref.decoder
+    st = {"is_first_step": False}
+    prefix = torch.randint(0, oc.vocab, (1, 9))
+    x, _ = dec.forward_embedding(prefix, None, st)
+    assert x.shape == (1, 1, oc.dim)
+    want = dec.embed_tokens(prefix[:, -1:]) + dec.embed_positions.weight[9 + 1][None, None]
+    assert torch.allclose(x, want)
+
+
 def test_emulation_changes_little_but_something(tiny):
     cfg, model = tiny
     text, images = ko.make_inputs(cfg, 1, 10)

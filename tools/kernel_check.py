@@ -809,6 +809,118 @@ def case_bench_train():
     return True
 
 
+def case_decode():
+    """Incremental-decoding kernels against plain fp32 PyTorch on the same bf16 inputs."""
+    ok = True
+    F = torch.nn.functional
+    g = torch.Generator(device=dev).manual_seed(0)
+    # --- decode_linear: plain / LayerNorm fold / GELU / ragged N / every batch-group width
+    for (B, N, K, ln, act, f32o) in ((8, 2048, 2048, True, 0, False), (3, 1002, 128, True, 1, True), (16, 512, 8192, True, 1, False),
+                                     (32, 320, 256, False, 0, True), (1, 32002, 2048, True, 0, True), (8, 8192, 2048, True, 1, False)):
+        a = (torch.randn(B + 2, K, device=dev, generator=g) * 1.5 + 0.3).bfloat16()[1:B + 1]        # offset rows
+        w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=dev, generator=g)
+        c = w.double().sum(1).float()
+        out = torch.full((B, N + 8), float("nan"), device=dev, dtype=torch.float32 if f32o else torch.bfloat16)[:, :N]
+        ops.decode_linear(a, w, bias=bias, ln_c=c if ln else None, act=_abi.KX_ACT_GELU if act else _abi.KX_ACT_NONE, out=out)
+        af = a.float()
+        h = F.layer_norm(af, (K,), eps=1e-5) if ln else af
+        ref = h @ w.float().T + bias
+        if act:
+            ref = F.gelu(ref)
+        tol = 3e-3 * max(1.0, ref.abs().max().item()) if f32o else 1.2e-2 * max(1.0, ref.abs().max().item())
+        ok &= report(f"decode_linear B={B} N={N} K={K} ln={ln} act={act} f32={f32o}", out, ref, tol)
+    # --- residual mode
+    B, N, K = 5, 256, 512
+    a = torch.randn(B, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    x = torch.randn(B, N, device=dev, generator=g)
+    x0 = x.clone()
+    xb = torch.empty(B, N, device=dev, dtype=torch.bfloat16)
+    ops.decode_linear(a, w, bias=bias, ln_c=w.double().sum(1).float(), res=(x, xb))
+    ref = x0 + F.layer_norm(a.float(), (K,)) @ w.float().T + bias
+    ok &= report("decode_linear residual x", x, ref, 3e-3)
+    ok &= report("decode_linear residual xb", xb, ref, 2e-2)
+    # --- q|k|v mode: xPos at *pos, cache write
+    B, D, T_MAX, P = 4, 128, 40, 17
+    xp, scale, sin, cos = xpos_ref(T_MAX, dev)
+    inv_freq = (1.0 / (10000 ** (torch.arange(0, 32) / 32))).to(dev)
+    tabs = ops.xpos_tables(xp.scale.to(dev), inv_freq, T_MAX, (-T_MAX) // 2, 512.0, dev)
+    a = torch.randn(B, D, device=dev, generator=g).bfloat16()
+    w = (torch.randn(3 * D, D, device=dev, generator=g) / math.sqrt(D)).bfloat16()
+    bias = torch.randn(3 * D, device=dev, generator=g)
+    qo = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
+    kc = torch.zeros(B, T_MAX, D, device=dev, dtype=torch.bfloat16)
+    vc = torch.zeros(B, T_MAX, D, device=dev, dtype=torch.bfloat16)
+    pos = torch.tensor([P], device=dev, dtype=torch.int32)
+    ops.decode_linear(a, w, bias=bias, ln_c=w.double().sum(1).float(), qkv=(qo, kc, vc, T_MAX, pos, tabs))
+    y = F.layer_norm(a.float(), (D,)) @ w.float().T + bias
+    q, k, v = y[:, :D], y[:, D:2 * D], y[:, 2 * D:]
+
+    def rot(t, up):
+        th = t.view(B, D // 64, 32, 2)
+        s_ = scale[P] if up else 1.0 / scale[P]
+        c_, n_ = (cos[P] * s_)[None, None], (sin[P] * s_)[None, None]
+        o0 = th[..., 0] * c_ - th[..., 1] * n_
+        o1 = th[..., 1] * c_ + th[..., 0] * n_
+        return torch.stack([o0, o1], -1).view(B, D)
+
+    ok &= report("decode qkv: q rotated", qo, rot(q, True), 3e-2)
+    ok &= report("decode qkv: k rotated -> cache row", kc[:, P], rot(k, False), 3e-2)
+    ok &= report("decode qkv: v -> cache row", vc[:, P], v, 3e-2)
+    kc[:, P] = 0; vc[:, P] = 0
+    ok &= bool((kc == 0).all() and (vc == 0).all())          # nothing else was touched
+    # --- decode attention against eager softmax, several cache fills (1 chunk, ragged, many chunks)
+    for (B, H, T_MAX, n_keys) in ((2, 4, 64, 1), (3, 2, 300, 131), (2, 32, 2048, 2048), (8, 32, 640, 517)):
+        D = H * 64
+        q = torch.randn(B, D, device=dev, generator=g).bfloat16()
+        kc = torch.randn(B, T_MAX, D, device=dev, generator=g).bfloat16()
+        vc = torch.randn(B, T_MAX, D, device=dev, generator=g).bfloat16()
+        out = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
+        scratch, counters = ops.decode_attn_scratch(B, H, T_MAX, dev)
+        pos = torch.tensor([n_keys - 1], device=dev, dtype=torch.int32)
+        for _ in range(2):                                   # twice: the counters must come back to zero
+            ops.decode_attention(q, kc, vc, out, t_max=T_MAX, heads=H, pos=pos, scale=0.125, scratch=scratch, counters=counters)
+        qh = q.float().view(B, H, 1, 64)
+        kh = kc[:, :n_keys].float().view(B, n_keys, H, 64).transpose(1, 2)
+        vh = vc[:, :n_keys].float().view(B, n_keys, H, 64).transpose(1, 2)
+        ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).view(B, D)
+        ok &= report(f"decode_attn B={B} H={H} keys={n_keys}/{T_MAX}", out, ref, 1.5e-2)
+        ok &= bool((counters == 0).all())
+    # --- cache fill from a q|k|v matrix, embed, greedy choice
+    B, T, D, T_MAX = 3, 21, 128, 30
+    qkv = torch.randn(B * T, 3 * D, device=dev, generator=g).bfloat16()
+    kc = torch.zeros(B, T_MAX, D, device=dev, dtype=torch.bfloat16); vc = torch.zeros_like(kc)
+    ops.kv_cache_store(qkv, kc, vc, batch=B, seq_len=T, d_model=D, t_max=T_MAX)
+    ok &= bool(torch.equal(kc[:, :T], qkv[:, D:2 * D].view(B, T, D)) and torch.equal(vc[:, :T], qkv[:, 2 * D:].view(B, T, D)))
+    ok &= bool((kc[:, T:] == 0).all())
+    V = 1002
+    emb = torch.randn(V, D, device=dev, generator=g); ptab = torch.randn(64, D, device=dev, generator=g)
+    tok = torch.tensor([5, 1001, 77], device=dev)
+    pos = torch.tensor([9], device=dev, dtype=torch.int32)
+    x = torch.empty(B, D, device=dev); xb = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    ops.decode_embed(tok, emb, ptab, pos, x, xb, err)
+    ok &= bool(torch.equal(x, emb[tok] + ptab[11]) and torch.equal(xb, x.bfloat16()) and int(err.item()) == 0)
+    ops.decode_embed(torch.tensor([5, 1002, 77], device=dev), emb, ptab, pos, x, xb, err)
+    ok &= int(err.item()) == 1
+    logits = torch.randn(B, V, device=dev, generator=g)
+    logits[1, 700] = logits[1, 300] = 50.0                   # tie -> lowest index
+    hist = torch.full((B, 4), -1, device=dev, dtype=torch.int64)
+    step = torch.zeros(1, device=dev, dtype=torch.int32); counter = torch.zeros(1, device=dev, dtype=torch.int32)
+    tok_out = torch.zeros(B, device=dev, dtype=torch.int64)
+    ops.argmax_advance(logits, tok_out, step=step, counter=counter, pos=pos, history=hist)
+    want = logits.argmax(-1); want[1] = 300
+    ok &= bool(torch.equal(tok_out, want) and torch.equal(hist[:, 0], want) and int(step.item()) == 1 and int(pos.item()) == 10)
+    forced = torch.arange(B * 4, device=dev).view(B, 4)
+    ops.argmax_advance(logits, tok_out, step=step, counter=counter, pos=None, history=hist, forced=forced)
+    ok &= bool(torch.equal(tok_out, forced[:, 1]) and torch.equal(hist[:, 1], forced[:, 1]) and int(pos.item()) == 10
+               and int(counter.item()) == 0)
+    print(f"[{'OK' if ok else 'FAIL'}] cache fill / embed / greedy choice")
+    return ok
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 if __name__ == "__main__":
