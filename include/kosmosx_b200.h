@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 9   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 10   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -293,7 +293,7 @@ int kx_lion_step(float* p, const float* g, float* m, void* w_bf16, long long n, 
  * MultiheadAttention.forward (SURVEY A.4, A.5 [recall]; reached through the decoder built at model.py:186-191).
  * The prompt pass is the ordinary forward plus kx_kv_cache_store per layer; every later step processes ONE new token
  * per sequence.  The cache holds, per layer, the xPos-ROTATED keys and the values as bf16 [batch, t_max, d_model]
- * (head h at columns h*64..h*64+63).  torchscale caches un-rotated keys and re-rotates the whole key sequence with a
+ * (stored head-major, [batch, heads, t_max, 64], so one (batch, head) is one contiguous stream).  torchscale caches un-rotated keys and re-rotates the whole key sequence with a
  * re-centred scale every step; q.k depends on the position DIFFERENCE only (A.5), so rotating each key once with the
  * prompt's centre gives the same products.  The current position (= number of cached tokens) lives in DEVICE memory
  * (`pos`), so one captured CUDA graph serves every step with no host round trip.
@@ -319,6 +319,8 @@ typedef struct kx_decode_linear_args {
     const float* ln_c;            /* fp32 [N] or NULL = no LayerNorm fold */
     float ln_eps;
     void* out; long long ld_out; int out_f32;                  /* KX_DEC_PLAIN */
+    unsigned long long* argmax_keys; /* KX_DEC_PLAIN, may be NULL: [batch] order-preserving (value, index) keys, atomicMax-reduced
+                                      * over N by this launch (the greedy choice fused into output_projection); zero before use */
     float* x; long long ld_x; void* xb; long long ld_xb;       /* KX_DEC_RESIDUAL */
     void* q_out; long long ld_q; void* k_cache; void* v_cache; /* KX_DEC_QKV */
     int t_max, d_model;
@@ -352,10 +354,12 @@ int kx_decode_embed(const long long* tokens, int batch, const float* embed_table
 
 /* Greedy choice on the device: tokens_out[b] = argmax_v logits[b, v] (lowest index on ties) or forced[b, *step] when
  * `forced` (int64 [batch, history_ld]) is given; history[b, *step] = the choice; then *step += 1 and *pos += 1 (pos
- * may be NULL).  counter: one int, zeroed once by the caller. */
+ * may be NULL).  counter: one int, zeroed once by the caller.  argmax_keys (may be NULL): the keys reduced by the
+ * output_projection launch (kx_decode_linear_args.argmax_keys) — the logits are then not re-read and the keys are
+ * reset to zero for the next step. */
 int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, const long long* forced,
                       long long* tokens_out, long long* history, int history_ld, int* pos, int* step, int* counter,
-                      kx_stream_t stream);
+                      unsigned long long* argmax_keys, kx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ struct DecLin {
     const __nv_bfloat16* w; long long ldw; int N, K;
     const float* ln_c; const float* bias; float eps; int ln;
     int mode, act;
-    void* out; long long ld_out; int out_f32;
+    void* out; long long ld_out; int out_f32; unsigned long long* argmax_keys;
     float* x; long long ld_x; __nv_bfloat16* xb; long long ld_xb;
     __nv_bfloat16* q_out; long long ld_q;
     __nv_bfloat16* k_cache; __nv_bfloat16* v_cache; int t_max; int d_model;
@@ -49,6 +49,13 @@ __device__ __forceinline__ void bf16x2_stats(uint32_t v, float& s1, float& s2) {
     s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
 }
 
+// activations were written by the previous kernel of the chain (possibly still resident under PDL): plain coherent loads
+__device__ __forceinline__ uint4 ld_act(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // weights are read exactly once per step: streaming loads, do not keep them in L1
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 v;
@@ -57,14 +64,51 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     return v;
 }
 
+// Programmatic dependent launch: the next kernel of a decoding step is scheduled while this one drains; everything a
+// kernel does before pdl_wait() may only touch memory no earlier kernel of the step writes (weights, tables).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("KX_DECODE_PDL");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+int check_chain(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+        return KX_ERR_LAUNCH;
+    }
+    count_launch();
+    return KX_OK;
+}
+
 }  // namespace
 
 // One CTA = 16 rows of W (16 output features) x the whole K, 8 warps splitting K; NB groups of 8 batch rows.
-template <int NB>
-__global__ void __launch_bounds__(256, NB == 1 ? 3 : (NB == 2 ? 2 : 1))
+// U = 32-wide k steps (2 x 16-byte weight loads each) a thread keeps in flight; MINB = CTAs per SM the registers allow.
+// Wide N (>= one CTA per SM slot): U = 4, 3 CTAs/SM.  Narrow N (fewer tiles than SMs): one CTA per SM has to keep the
+// whole 45 KB/SM in flight alone, U = 8.
+template <int NB, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 decode_linear_kernel(const DecLin p) {
     constexpr int NBC = NB * 8;
-    constexpr int U = 4;                                   // 32-wide k steps in flight per thread
     __shared__ float red[8][16][NBC];
     __shared__ float st[8][NBC][2];
     __shared__ float fin[16][NBC];
@@ -95,6 +139,8 @@ decode_linear_kernel(const DecLin p) {
         s1[nb] = s2[nb] = 0.f;
     }
 
+    pdl_launch_dependents();
+    bool waited = false;
     for (int s = s_begin; s < s_end; s += U) {
         uint4 wa[U], wb[U], av[U][NB];
 #pragma unroll
@@ -103,9 +149,15 @@ decode_linear_kernel(const DecLin p) {
             const int o = (s + u) * 4;                     // uint4 index of this step's first k (32 k = 4 x 16 bytes)
             wa[u] = ok ? ld_stream(w0 + o) : make_uint4(0, 0, 0, 0);
             wb[u] = ok ? ld_stream(w1 + o) : make_uint4(0, 0, 0, 0);
+        }
+        if (!waited) { pdl_wait(); waited = true; }        // weights do not depend on the previous kernel; `a` does
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = s + u < s_end;
+            const int o = (s + u) * 4;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb)
-                av[u][nb] = (ok && aok[nb]) ? __ldg(ap[nb] + o) : make_uint4(0, 0, 0, 0);
+                av[u][nb] = (ok && aok[nb]) ? ld_act(ap[nb] + o) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -123,6 +175,7 @@ decode_linear_kernel(const DecLin p) {
         }
     }
 
+    if (!waited) pdl_wait();
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
         red[warp][g][nb * 8 + 2 * t] = acc[nb][0];
@@ -163,12 +216,29 @@ decode_linear_kernel(const DecLin p) {
     for (int o = tid; o < 16 * NBC; o += 256) {
         const int b = o >> 4, r = o & 15;
         const int n = n0 + r;
-        if (b >= p.B || n >= p.N) continue;
+        const bool live = b < p.B && n < p.N;
         float v = fin[r][b];
+        if (p.argmax_keys != nullptr) {
+            // greedy choice fused into output_projection: order-preserving (value, lowest index wins) 64-bit keys,
+            // reduced over the tile's 16 features (one half-warp per batch row), one atomicMax per (tile, row)
+            unsigned long long key = 0ull;
+            if (live) {
+                const uint32_t u = __float_as_uint(v);
+                key = (static_cast<unsigned long long>((u & 0x80000000u) ? ~u : (u | 0x80000000u)) << 32) |
+                      static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(n));
+            }
+#pragma unroll
+            for (int sft = 8; sft > 0; sft >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, sft);
+                key = other > key ? other : key;
+            }
+            if (r == 0 && b < p.B) atomicMax(p.argmax_keys + b, key);
+        }
+        if (!live) continue;
         if (p.mode == KX_DEC_QKV) {
             const int which = n / p.d_model;
             const int col = n - which * p.d_model;
-            const int pos = __ldg(p.pos);
+            const int pos = *p.pos;
             if (which < 2) {                               // xPos rotation of the (2j, 2j+1) pair at position pos
                 const int j = (n & 63) >> 1;
                 const float c = __ldg((which == 0 ? p.xq_cos : p.xk_cos) + pos * 32 + j);
@@ -180,7 +250,9 @@ decode_linear_kernel(const DecLin p) {
                 p.q_out[static_cast<long long>(b) * p.ld_q + col] = __float2bfloat16_rn(v);
             } else if (pos < p.t_max) {
                 __nv_bfloat16* dst = (which == 1 ? p.k_cache : p.v_cache);
-                dst[(static_cast<long long>(b) * p.t_max + pos) * p.d_model + col] = __float2bfloat16_rn(v);
+                // cache layout [batch, heads, t_max, 64]: one (batch, head) is one contiguous stream for kx_decode_attn
+                const int hh = col >> 6;
+                dst[((static_cast<long long>(b) * (p.d_model >> 6) + hh) * p.t_max + pos) * 64 + (col & 63)] = __float2bfloat16_rn(v);
             }
         } else if (p.mode == KX_DEC_RESIDUAL) {
             float* px = p.x + static_cast<long long>(b) * p.ld_x + n;
@@ -206,7 +278,9 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, long long ld_q, con
                         const __nv_bfloat16* __restrict__ v_cache, int t_max, int d_model, const int* __restrict__ pos_ptr,
                         float scale_log2, float* __restrict__ part, int* __restrict__ counters,
                         __nv_bfloat16* __restrict__ out, long long ld_out, int max_chunks) {
-    const int n_keys = min(__ldg(pos_ptr) + 1, t_max);      // the new token attends to itself and everything before
+    pdl_launch_dependents();
+    pdl_wait();
+    const int n_keys = min(*pos_ptr + 1, t_max);             // the new token attends to itself and everything before
     const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z, H = gridDim.y;
     const int n_act = (n_keys + DA_CHUNK - 1) / DA_CHUNK;
     if (chunk >= n_act) return;
@@ -218,7 +292,7 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, long long ld_q, con
 
     float qf[8];
     {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(q + static_cast<long long>(b) * ld_q + h * 64) + sub);
+        const uint4 raw = ld_act(reinterpret_cast<const uint4*>(q + static_cast<long long>(b) * ld_q + h * 64) + sub);
         const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -227,18 +301,18 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, long long ld_q, con
         }
     }
     const int key0 = chunk * DA_CHUNK + warp * 32 + kq;
-    const long long base = static_cast<long long>(b) * t_max * d_model + h * 64;
+    const long long base = (static_cast<long long>(b) * H + h) * t_max * 64;
     uint4 kr[8], vr[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int j = key0 + it * 4;
-        kr[it] = j < n_keys ? __ldg(reinterpret_cast<const uint4*>(k_cache + base + static_cast<long long>(j) * d_model) + sub)
+        kr[it] = j < n_keys ? ld_act(reinterpret_cast<const uint4*>(k_cache + base + static_cast<long long>(j) * 64) + sub)
                             : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int j = key0 + it * 4;
-        vr[it] = j < n_keys ? __ldg(reinterpret_cast<const uint4*>(v_cache + base + static_cast<long long>(j) * d_model) + sub)
+        vr[it] = j < n_keys ? ld_act(reinterpret_cast<const uint4*>(v_cache + base + static_cast<long long>(j) * 64) + sub)
                             : make_uint4(0, 0, 0, 0);
     }
     float sc[8];
@@ -313,13 +387,29 @@ decode_attention_kernel(const __nv_bfloat16* __restrict__ q, long long ld_q, con
     __threadfence();
     if (threadIdx.x < 64) {
         const float* all = part + (static_cast<long long>(b) * H + h) * max_chunks * 66;
-        float M = -INFINITY;
-        for (int c = 0; c < n_act; ++c) M = fmaxf(M, __ldcg(all + c * 66 + 64));
-        float L = 0.f, O = 0.f;
-        for (int c = 0; c < n_act; ++c) {
-            const float f = ex2_approx(__ldcg(all + c * 66 + 64) - M);
-            L = fmaf(__ldcg(all + c * 66 + 65), f, L);
-            O = fmaf(__ldcg(all + c * 66 + threadIdx.x), f, O);
+        float M = -INFINITY, L = 0.f, O = 0.f;
+        for (int c0 = 0; c0 < n_act; c0 += 8) {             // 24 independent L2 loads in flight per pass
+            float mc[8], lc[8], oc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool ok = c0 + i < n_act;
+                const float* pc = all + (ok ? c0 + i : c0) * 66;
+                mc[i] = ok ? __ldcg(pc + 64) : -INFINITY;
+                lc[i] = __ldcg(pc + 65);
+                oc[i] = __ldcg(pc + threadIdx.x);
+            }
+            float Mn = M;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Mn = fmaxf(Mn, mc[i]);
+            const float f0 = M > -INFINITY ? ex2_approx(M - Mn) : 0.f;
+            L *= f0; O *= f0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float f = mc[i] > -INFINITY ? ex2_approx(mc[i] - Mn) : 0.f;
+                L = fmaf(lc[i], f, L);
+                O = fmaf(oc[i], f, O);
+            }
+            M = Mn;
         }
         out[static_cast<long long>(b) * ld_out + h * 64 + threadIdx.x] = __float2bfloat16_rn(O / L);
     }
@@ -340,7 +430,8 @@ kv_cache_store_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int b
         const int b = static_cast<int>(row / seq_len), t = static_cast<int>(row - static_cast<long long>(b) * seq_len);
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(qkv + row * ld + static_cast<long long>(which + 1) * d_model) + c);
         __nv_bfloat16* dst = which ? v_cache : k_cache;
-        reinterpret_cast<uint4*>(dst + (static_cast<long long>(b) * t_max + t) * d_model)[c] = v;
+        const int hh = c >> 3;                              // 8 x 16 bytes per 64-wide head
+        reinterpret_cast<uint4*>(dst + ((static_cast<long long>(b) * (d_model >> 6) + hh) * t_max + t) * 64)[c & 7] = v;
     }
 }
 
@@ -349,13 +440,15 @@ __global__ void __launch_bounds__(256)
 decode_embed_kernel(const long long* __restrict__ tok, const float* __restrict__ embed, int vocab,
                     const float* __restrict__ pos_tab, int pos_rows, const int* __restrict__ pos_ptr, int dim,
                     float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int* __restrict__ err_flag) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     long long id = tok[b];
     if (id < 0 || id >= vocab) {
         if (threadIdx.x == 0 && err_flag != nullptr) atomicOr(err_flag, 1);
         id = 0;
     }
-    int pr = __ldg(pos_ptr) + 2;                            // "positions start from 2" 
+    int pr = *pos_ptr + 2;                            // "positions start from 2" 
     if (pr >= pos_rows) {
         if (threadIdx.x == 0 && err_flag != nullptr) atomicOr(err_flag, 2);
         pr = pos_rows - 1;
@@ -376,7 +469,27 @@ decode_embed_kernel(const long long* __restrict__ tok, const float* __restrict__
 __global__ void __launch_bounds__(256)
 argmax_advance_kernel(const float* __restrict__ logits, long long ld, int vocab, const long long* __restrict__ forced,
                       long long* __restrict__ tok_out, long long* __restrict__ history, int hist_ld,
-                      int* __restrict__ pos_ptr, int* __restrict__ step_ptr, int* __restrict__ counter) {
+                      int* __restrict__ pos_ptr, int* __restrict__ step_ptr, int* __restrict__ counter,
+                      unsigned long long* __restrict__ keys, int batch) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (keys != nullptr) {                                  // the LM head already reduced (value, index) keys: one CTA
+        const int step = *step_ptr;
+        __syncthreads();
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            long long choice = static_cast<long long>(0xffffffffu - static_cast<uint32_t>(keys[b] & 0xffffffffull));
+            keys[b] = 0ull;
+            if (forced != nullptr && step < hist_ld) choice = forced[static_cast<long long>(b) * hist_ld + step];
+            tok_out[b] = choice;
+            if (history != nullptr && step < hist_ld) history[static_cast<long long>(b) * hist_ld + step] = choice;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *step_ptr = step + 1;
+            if (pos_ptr != nullptr) *pos_ptr += 1;
+        }
+        return;
+    }
     const int b = blockIdx.x;
     const int step = *step_ptr;
     __shared__ float sv[8];
@@ -432,7 +545,7 @@ extern "C" int kx_decode_linear(const void* a, long long lda, int batch, const v
     p.mode = g->mode; p.act = g->act;
     if (g->mode == KX_DEC_PLAIN) {
         if (!g->out || g->ld_out < N) { set_error("kx_decode_linear: KX_DEC_PLAIN needs out with ld_out >= N"); return KX_ERR_ARG; }
-        p.out = g->out; p.ld_out = g->ld_out; p.out_f32 = g->out_f32;
+        p.out = g->out; p.ld_out = g->ld_out; p.out_f32 = g->out_f32; p.argmax_keys = g->argmax_keys;
     } else if (g->mode == KX_DEC_RESIDUAL) {
         if (!g->x || !g->xb || g->ld_x < N || g->ld_xb < N) { set_error("kx_decode_linear: KX_DEC_RESIDUAL needs x and xb"); return KX_ERR_ARG; }
         p.x = g->x; p.ld_x = g->ld_x; p.xb = reinterpret_cast<__nv_bfloat16*>(g->xb); p.ld_xb = g->ld_xb;
@@ -450,12 +563,19 @@ extern "C" int kx_decode_linear(const void* a, long long lda, int batch, const v
         set_error("kx_decode_linear: unknown mode %d", g->mode);
         return KX_ERR_ARG;
     }
-    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
     const int tiles = (N + 15) / 16;
-    if (batch <= 8) decode_linear_kernel<1><<<tiles, 256, 0, stream>>>(p);
-    else if (batch <= 16) decode_linear_kernel<2><<<tiles, 256, 0, stream>>>(p);
-    else decode_linear_kernel<4><<<tiles, 256, 0, stream>>>(p);
-    return check_launch("kx_decode_linear");
+    cudaError_t e;
+    if (batch <= 8) {
+        if (tiles <= sms + sms / 4) e = launch_chain(decode_linear_kernel<1, 8, 1>, dim3(tiles), dim3(256), stream, p);
+        else e = launch_chain(decode_linear_kernel<1, 4, 3>, dim3(tiles), dim3(256), stream, p);
+    } else if (batch <= 16) {
+        e = launch_chain(decode_linear_kernel<2, 4, 2>, dim3(tiles), dim3(256), stream, p);
+    } else {
+        e = launch_chain(decode_linear_kernel<4, 4, 1>, dim3(tiles), dim3(256), stream, p);
+    }
+    return check_chain(e, "kx_decode_linear");
 }
 
 extern "C" size_t kx_decode_attn_scratch_bytes(int batch, int heads, int t_max) {
@@ -475,16 +595,16 @@ extern "C" int kx_decode_attn(const void* q, long long ld_q, const void* k_cache
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
     const int chunks = (t_max + DA_CHUNK - 1) / DA_CHUNK;
-    decode_attention_kernel<<<dim3(chunks, heads, batch), 128, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(q), ld_q, reinterpret_cast<const __nv_bfloat16*>(k_cache),
-        reinterpret_cast<const __nv_bfloat16*>(v_cache), t_max, heads * 64, pos, scale * 1.4426950408889634f, scratch,
-        counters, reinterpret_cast<__nv_bfloat16*>(out), ld_out, chunks);
-    return check_launch("kx_decode_attn");
+    return check_chain(launch_chain(decode_attention_kernel, dim3(chunks, heads, batch), dim3(128), stream,
+                                    reinterpret_cast<const __nv_bfloat16*>(q), ld_q, reinterpret_cast<const __nv_bfloat16*>(k_cache),
+                                    reinterpret_cast<const __nv_bfloat16*>(v_cache), t_max, heads * 64, pos,
+                                    scale * 1.4426950408889634f, scratch, counters, reinterpret_cast<__nv_bfloat16*>(out), ld_out,
+                                    chunks), "kx_decode_attn");
 }
 
 extern "C" int kx_kv_cache_store(const void* qkv, long long ld_qkv, int batch, int seq_len, int d_model, void* k_cache,
                                  void* v_cache, int t_max, cudaStream_t stream) {
-    if (!qkv || !k_cache || !v_cache || batch <= 0 || seq_len <= 0 || seq_len > t_max || d_model <= 0 || (d_model & 7) ||
+    if (!qkv || !k_cache || !v_cache || batch <= 0 || seq_len <= 0 || seq_len > t_max || d_model <= 0 || (d_model & 63) ||
         (ld_qkv & 7) || ld_qkv < 3LL * d_model || ((uintptr_t)qkv & 15) || ((uintptr_t)k_cache & 15) || ((uintptr_t)v_cache & 15)) {
         set_error("kx_kv_cache_store: bad argument (seq_len %d, t_max %d, d_model %d)", seq_len, t_max, d_model);
         return KX_ERR_ARG;
@@ -507,21 +627,20 @@ extern "C" int kx_decode_embed(const long long* tokens, int batch, const float* 
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    decode_embed_kernel<<<batch, 256, 0, stream>>>(tokens, embed_table, vocab, pos_table, pos_rows, pos, dim, x,
-                                                  reinterpret_cast<__nv_bfloat16*>(xb), err_flag);
-    return check_launch("kx_decode_embed");
+    return check_chain(launch_chain(decode_embed_kernel, dim3(batch), dim3(256), stream, tokens, embed_table, vocab, pos_table,
+                                    pos_rows, pos, dim, x, reinterpret_cast<__nv_bfloat16*>(xb), err_flag), "kx_decode_embed");
 }
 
 extern "C" int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, const long long* forced,
                                  long long* tokens_out, long long* history, int history_ld, int* pos, int* step,
-                                 int* counter, cudaStream_t stream) {
-    if (!logits || !tokens_out || !step || !counter || batch <= 0 || vocab <= 0 || ld < vocab || (history && history_ld <= 0) ||
+                                 int* counter, unsigned long long* argmax_keys, cudaStream_t stream) {
+    if ((!logits && !argmax_keys) || !tokens_out || !step || !counter || batch <= 0 || vocab <= 0 || ld < vocab || (history && history_ld <= 0) ||
         (forced && history_ld <= 0)) {
         set_error("kx_argmax_advance: bad argument");
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    argmax_advance_kernel<<<batch, 256, 0, stream>>>(logits, ld, vocab, forced, tokens_out, history, history_ld, pos, step,
-                                                    counter);
-    return check_launch("kx_argmax_advance");
+    return check_chain(launch_chain(argmax_advance_kernel, dim3(argmax_keys ? 1 : batch), dim3(argmax_keys ? 32 : 256), stream, logits,
+                                    ld, vocab, forced, tokens_out, history, history_ld, pos, step, counter, argmax_keys, batch),
+                       "kx_argmax_advance");
 }

@@ -49,7 +49,7 @@ class DecodeLinearArgs(C.Structure):
 
     _fields_ = [
         ("mode", _i), ("act", _i), ("bias", _f32p), ("ln_c", _f32p), ("ln_eps", _f),
-        ("out", _vp), ("ld_out", _ll), ("out_f32", _i),
+        ("out", _vp), ("ld_out", _ll), ("out_f32", _i), ("argmax_keys", _vp),
         ("x", _f32p), ("ld_x", _ll), ("xb", _vp), ("ld_xb", _ll),
         ("q_out", _vp), ("ld_q", _ll), ("k_cache", _vp), ("v_cache", _vp),
         ("t_max", _i), ("d_model", _i), ("pos", _vp),
@@ -103,7 +103,7 @@ SIGNATURES = {
     "kx_decode_attn": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _vp, _f, _f32p, _vp, _vp, _ll, _vp]),
     "kx_kv_cache_store": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kx_decode_embed": (_i, [_vp, _i, _f32p, _i, _f32p, _i, _vp, _i, _f32p, _vp, _vp, _vp]),
-    "kx_argmax_advance": (_i, [_f32p, _ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "kx_argmax_advance": (_i, [_f32p, _ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

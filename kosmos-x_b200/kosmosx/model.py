@@ -267,8 +267,9 @@ class DecodeState:
         bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
         L, D, F, H = cfg.layers, cfg.dim, cfg.ffn, cfg.heads
         self.batch, self.t_max, self.length = batch, t_max, 0
-        self.k = torch.empty(L, batch, t_max, D, dtype=bf, device=device)
-        self.v = torch.empty(L, batch, t_max, D, dtype=bf, device=device)
+        self.k = torch.empty(L, batch, H, t_max, D // H, dtype=bf, device=device)      # head-major (kx_decode_attn)
+        self.v = torch.empty(L, batch, H, t_max, D // H, dtype=bf, device=device)
+        self.keys = torch.zeros(batch, dtype=torch.int64, device=device)               # fused greedy-choice keys
         self.pos = torch.zeros(1, dtype=i32, device=device)
         self.step = torch.zeros(1, dtype=i32, device=device)
         self.counter = torch.zeros(1, dtype=i32, device=device)
@@ -450,7 +451,8 @@ class Decoder(nn.Module):
             self.run_layers(x, B, T, head=False, state=state)
             xb = self._ws.get("xb", (B * T, cfg.dim), torch.bfloat16, x.device)
             w, c, d = p["out"]                               # decoder.layer_norm -> output_projection, last rows only
-            ops.decode_linear(xb.view(B, T, cfg.dim)[:, T - 1], w, bias=d, ln_c=c, eps=cfg.eps, out=state.logits)
+            ops.decode_linear(xb.view(B, T, cfg.dim)[:, T - 1], w, bias=d, ln_c=c, eps=cfg.eps, out=state.logits,
+                              argmax_keys=state.keys)
             out = state.logits
         state.pos.fill_(T)
         state.length = T
@@ -480,13 +482,14 @@ class Decoder(nn.Module):
             ops.decode_linear(state.xb, w, bias=d, ln_c=c, eps=eps, act=_abi.KX_ACT_GELU, out=state.mid)
             w, c, d = L["fc2"]
             ops.decode_linear(state.mid, w, bias=d, ln_c=c, eps=eps, res=(state.x, state.xb))
-        w, c, d = p["out"]
-        ops.decode_linear(state.xb, w, bias=d, ln_c=c, eps=eps, out=state.logits)
+        w, c, d = p["out"]                                   # + the greedy choice, reduced into state.keys
+        ops.decode_linear(state.xb, w, bias=d, ln_c=c, eps=eps, out=state.logits, argmax_keys=state.keys)
 
     def advance(self, state: DecodeState, history=None, forced=None, move=True):
-        """Greedy choice from state.logits into state.tok (or the forced token), optional history column, position += 1."""
+        """Greedy choice (reduced by the LM-head launch into state.keys) or the forced token into state.tok, optional
+        history column, position += 1."""
         ops.argmax_advance(state.logits, state.tok, step=state.step, counter=state.counter,
-                           pos=state.pos if move else None, history=history, forced=forced)
+                           pos=state.pos if move else None, history=history, forced=forced, keys=state.keys)
         if move:
             state.length += 1
 

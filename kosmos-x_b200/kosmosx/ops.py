@@ -413,7 +413,8 @@ def broadcast_rows(src, dst, copies):
 
 
 # ---- incremental decoding ----------------------------------------------------------------------
-def decode_linear(a, w, *, bias=None, ln_c=None, eps=1e-5, act=_abi.KX_ACT_NONE, out=None, res=None, qkv=None):
+def decode_linear(a, w, *, bias=None, ln_c=None, eps=1e-5, act=_abi.KX_ACT_NONE, out=None, res=None, qkv=None,
+                  argmax_keys=None):
     """One-token Linear for batch <= 32 rows (kx_decode_linear).  Exactly one of:
       out=tensor (bf16 / fp32 [B, >=N])            plain (+act)
       res=(x fp32 [B, N], xb bf16 [B, N])          x += y in place, xb = bf16(x)
@@ -427,6 +428,7 @@ def decode_linear(a, w, *, bias=None, ln_c=None, eps=1e-5, act=_abi.KX_ACT_NONE,
         raise ValueError(f"decode_linear: K mismatch {tuple(a.shape)} vs {tuple(w.shape)}")
     if out is not None:
         g.mode, g.out, g.ld_out, g.out_f32 = _abi.KX_DEC_PLAIN, out.data_ptr(), out.stride(0), int(out.dtype == torch.float32)
+        g.argmax_keys = _ptr(argmax_keys)
         if out.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError("decode_linear: out must be fp32 or bf16")
     elif res is not None:
@@ -478,14 +480,14 @@ def decode_embed(tokens, embed_table, pos_table, pos, x, xb, err_flag=None):
                               xb.data_ptr(), _ptr(err_flag), _stream()), "kx_decode_embed")
 
 
-def argmax_advance(logits, tokens_out, *, step, counter, pos=None, history=None, forced=None):
+def argmax_advance(logits, tokens_out, *, step, counter, pos=None, history=None, forced=None, keys=None):
     _req(logits, torch.float32, "logits")
     hist_ld = history.shape[1] if history is not None else (forced.shape[1] if forced is not None else 0)
     if history is not None and forced is not None and forced.shape[1] != history.shape[1]:
         raise ValueError("argmax_advance: forced and history must have the same row length")
     check(lib.kx_argmax_advance(logits.data_ptr(), logits.stride(0), logits.shape[0], logits.shape[1], _ptr(forced),
                                 tokens_out.data_ptr(), _ptr(history), hist_ld, _ptr(pos), step.data_ptr(),
-                                counter.data_ptr(), _stream()), "kx_argmax_advance")
+                                counter.data_ptr(), _ptr(keys), _stream()), "kx_argmax_advance")
 
 
 _graph_launches = 0

