@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 10   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 12   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -360,6 +360,44 @@ int kx_decode_embed(const long long* tokens, int batch, const float* embed_table
 int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, const long long* forced,
                       long long* tokens_out, long long* history, int history_ld, int* pos, int* step, int* counter,
                       unsigned long long* argmax_keys, kx_stream_t stream);
+
+/* One decoding step as ONE persistent cooperative kernel (batch <= 8): embedding, every layer's q|k|v / attention /
+ * out_proj / fc1 / fc2, decoder.layer_norm + output_projection and the greedy choice, separated by grid barriers, with
+ * the next phase's first weight loads issued before each barrier wait.  Same arithmetic as the kx_decode_* calls above
+ * (which remain the path for 8 < batch <= 32 and for per-kernel profiling).
+ *   kx_decode_plan_build  one-time setup per generation: flattens the arguments into `device_plan`
+ *                         (kx_decode_plan_bytes(layers) bytes).  Copies from a temporary host buffer, so it
+ *                         SYNCHRONISES `stream` — the only call of this library that does.
+ *   kx_decode_step        one launch = one new token per sequence; tokens[b] is consumed, the next choice is written
+ *                         back to tokens[b] and history[b, *step]; *pos and *step advance.
+ * Per-layer arrays are HOST arrays of `layers` DEVICE pointers.  scratch: kx_decode_step_scratch_floats() floats;
+ * counters: kx_decode_step_counters() ints, zeroed once; barrier: 32 x uint64, zeroed once and then owned by the kernel;
+ * err_flag bit 2 = a barrier timed out (logic error, results invalid). */
+typedef struct kx_decode_step_args {
+    int batch, layers, d_model, ffn, heads, vocab, t_max, pos_rows;
+    float eps, scale;
+    const void* const* w_qkv; const float* const* c_qkv; const float* const* d_qkv;      /* [layers] */
+    const void* const* w_o;   const float* const* c_o;   const float* const* d_o;
+    const void* const* w_fc1; const float* const* c_fc1; const float* const* d_fc1;
+    const void* const* w_fc2; const float* const* c_fc2; const float* const* d_fc2;
+    void* const* k_cache; void* const* v_cache;                                          /* [layers], head-major caches */
+    const void* w_out; const float* c_out; const float* d_out;                           /* d_out may be NULL */
+    const float* embed_table; const float* pos_table;
+    const float *xq_cos, *xq_sin, *xk_cos, *xk_sin;
+    long long* tokens; float* x; void* xb; void* q; void* att; void* mid;                /* per-step activations */
+    float* logits; long long ld_logits;
+    unsigned long long* argmax_keys; int* pos; int* step; int* err_flag;
+    const long long* forced; long long* history; int history_ld;                         /* forced / history may be NULL */
+    float* scratch; int* counters; unsigned long long* barrier;
+    long long* trace;   /* optional profiling aid: int64 [2 * phases]; CTA 0 stamps %globaltimer when its own work of a phase
+                         * is done and when it leaves the barrier behind it (phases = 1 + 5*layers + 2) */
+} kx_decode_step_args;
+
+size_t kx_decode_plan_bytes(int layers);
+size_t kx_decode_step_scratch_floats(int batch, int heads, int t_max);
+size_t kx_decode_step_counters(int batch, int heads);
+int kx_decode_plan_build(const kx_decode_step_args* args, void* device_plan, kx_stream_t stream);
+int kx_decode_step(const void* device_plan, kx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,31 @@ class DecodeLinearArgs(C.Structure):
     ]
 
 
+_pp = C.POINTER(C.c_void_p)
+
+
+class DecodeStepArgs(C.Structure):
+    """struct kx_decode_step_args (include/kosmosx_b200.h)."""
+
+    _fields_ = [
+        ("batch", _i), ("layers", _i), ("d_model", _i), ("ffn", _i), ("heads", _i), ("vocab", _i), ("t_max", _i), ("pos_rows", _i),
+        ("eps", _f), ("scale", _f),
+        ("w_qkv", _pp), ("c_qkv", _pp), ("d_qkv", _pp),
+        ("w_o", _pp), ("c_o", _pp), ("d_o", _pp),
+        ("w_fc1", _pp), ("c_fc1", _pp), ("d_fc1", _pp),
+        ("w_fc2", _pp), ("c_fc2", _pp), ("d_fc2", _pp),
+        ("k_cache", _pp), ("v_cache", _pp),
+        ("w_out", _vp), ("c_out", _f32p), ("d_out", _f32p),
+        ("embed_table", _f32p), ("pos_table", _f32p),
+        ("xq_cos", _f32p), ("xq_sin", _f32p), ("xk_cos", _f32p), ("xk_sin", _f32p),
+        ("tokens", _vp), ("x", _f32p), ("xb", _vp), ("q", _vp), ("att", _vp), ("mid", _vp),
+        ("logits", _f32p), ("ld_logits", _ll),
+        ("argmax_keys", _vp), ("pos", _vp), ("step", _vp), ("err_flag", _vp),
+        ("forced", _vp), ("history", _vp), ("history_ld", _i),
+        ("scratch", _f32p), ("counters", _vp), ("barrier", _vp), ("trace", _vp),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol of include/kosmosx_b200.h
 SIGNATURES = {
     "kx_last_error": (C.c_char_p, []),
@@ -104,6 +129,11 @@ SIGNATURES = {
     "kx_kv_cache_store": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kx_decode_embed": (_i, [_vp, _i, _f32p, _i, _f32p, _i, _vp, _i, _f32p, _vp, _vp, _vp]),
     "kx_argmax_advance": (_i, [_f32p, _ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "kx_decode_plan_bytes": (C.c_size_t, [_i]),
+    "kx_decode_step_scratch_floats": (C.c_size_t, [_i, _i, _i]),
+    "kx_decode_step_counters": (C.c_size_t, [_i, _i]),
+    "kx_decode_plan_build": (_i, [C.POINTER(DecodeStepArgs), _vp, _vp]),
+    "kx_decode_step": (_i, [_vp, _vp]),
 }
 
 

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -284,6 +285,7 @@ class DecodeState:
         self.scratch, self.counters = ops.decode_attn_scratch(batch, H, t_max, device)
         self.tabs = None          # xPos tables [4, t_max, 32], centred like the prompt's (set by the prompt pass)
         self.graph = None         # captured (one step + greedy choice), replayed by Kosmos.generate
+        self.plan = None          # flattened arguments of the one-kernel step (kx_decode_plan_build)
 
     def cache_bytes(self) -> int:
         return 2 * self.k.numel() * 2
@@ -485,6 +487,20 @@ class Decoder(nn.Module):
         w, c, d = p["out"]                                   # + the greedy choice, reduced into state.keys
         ops.decode_linear(state.xb, w, bias=d, ln_c=c, eps=eps, out=state.logits, argmax_keys=state.keys)
 
+    def build_step_plan(self, state: DecodeState, history=None, forced=None, trace=None):
+        """Flatten one generation's arguments for the persistent one-kernel step (kx_decode_step; batch <= 8)."""
+        cfg, p = self.cfg, self._pack()
+        plan, scratch, counters, barrier = ops.decode_step_buffers(state.batch, cfg.heads, state.t_max, cfg.layers, state.x.device)
+        state.step_bufs = (scratch, counters, barrier)
+        state.plan = ops.decode_plan_build(
+            plan, layers=p["layers"], out=p["out"], embed_table=p["embed"], pos_table=p["pos"], tabs=state.tabs,
+            k_cache=[state.k[i] for i in range(cfg.layers)], v_cache=[state.v[i] for i in range(cfg.layers)],
+            tokens=state.tok, x=state.x, xb=state.xb, q=state.q, att=state.att, mid=state.mid, logits=state.logits,
+            keys=state.keys, pos=state.pos, step=state.step, err_flag=state.err, scratch=scratch, counters=counters,
+            barrier=barrier, heads=cfg.heads, ffn=cfg.ffn, t_max=state.t_max, eps=cfg.eps,
+            scale=(cfg.dim // cfg.heads) ** -0.5, forced=forced, history=history, trace=trace)
+        return state.plan
+
     def advance(self, state: DecodeState, history=None, forced=None, move=True):
         """Greedy choice (reduced by the LM-head launch into state.keys) or the forced token into state.tok, optional
         history column, position += 1."""
@@ -566,7 +582,7 @@ class _KosmosBase(nn.Module):
         return r
 
     def _generate(self, x0: torch.Tensor, B: int, T: int, max_new_tokens: int, forced=None, return_logits=False,
-                  cuda_graph=True):
+                  cuda_graph=True, one_kernel=None):
         """Greedy continuation of the embedded prompt x0 [B*T, D]: prompt pass with cache fill and
         the LM head on the last rows only, then max_new_tokens - 1 one-token steps.  The step + greedy choice is
         captured once as a CUDA graph and replayed (the position is device-resident), so no host value is read until
@@ -586,7 +602,19 @@ class _KosmosBase(nn.Module):
         outs = [state.logits.clone()] if return_logits else None
         dec.advance(state, history=history, forced=forced, move=False)       # token 0 comes from the prompt's last row
         steps = max_new_tokens - 1
-        if return_logits or not cuda_graph or steps < 2:
+        if one_kernel is None:
+            one_kernel = B <= 8 and os.environ.get("KX_DECODE_ONE_KERNEL", "0") != "0"
+        if one_kernel and steps > 0:
+            # the whole step (embedding .. greedy choice) is ONE persistent cooperative launch per token
+            if B > 8:
+                raise ValueError("the one-kernel decoding step handles at most 8 sequences")
+            plan = dec.build_step_plan(state, history=history, forced=forced)
+            for _ in range(steps):
+                ops.decode_step(plan)
+                state.length += 1
+                if return_logits:
+                    outs.append(state.logits.clone())
+        elif return_logits or not cuda_graph or steps < 2:
             for _ in range(steps):
                 dec.decode_step(state)
                 if return_logits:
@@ -858,7 +886,7 @@ class Kosmos(_KosmosBase):
 
     @torch.no_grad()
     def generate(self, text_tokens: torch.Tensor, images: torch.Tensor, max_new_tokens: int, image_positions=None,
-                 forced_tokens=None, return_logits: bool = False, cuda_graph: bool = True):
+                 forced_tokens=None, return_logits: bool = False, cuda_graph: bool = True, one_kernel=None):
         """Greedy continuation (the reference stops at logits, torchscale's ``incremental_state`` is the
         decoding path it would use): vision tower -> resampler -> splice -> prompt pass with KV-cache fill, then one-token
         steps on the weight-streaming kernels.  Returns int64 (B, max_new_tokens) on the device (and the (B, n, vocab)
@@ -874,7 +902,7 @@ class Kosmos(_KosmosBase):
         self._perceive_project(xv, B, x0, T, img_rows)
         ops.embed_splice_pos(text_tokens, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=cfg.p_latents,
                              err_flag=self._err_flag())
-        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph)
+        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph, one_kernel)
 
     def check_tokens(self):
         """Host-side check (one sync) that no token id of any forward so far was out of range."""
@@ -957,7 +985,7 @@ class KosmosLanguage(_KosmosBase):
 
     @torch.no_grad()
     def generate(self, x: torch.Tensor, max_new_tokens: int, forced_tokens=None, return_logits: bool = False,
-                 cuda_graph: bool = True):
+                 cuda_graph: bool = True, one_kernel=None):
         """Greedy continuation of the token prefix x (B, T) through the KV-cache path (see Kosmos.generate)."""
         _require_cuda(x, "x")
         if x.dtype != torch.int64 or x.ndim != 2:
@@ -969,7 +997,7 @@ class KosmosLanguage(_KosmosBase):
         dp = self.decoder._pack()
         x0 = self._ws.get("x0", (B * T, self.cfg.dim), torch.float32, x.device)
         ops.embed_splice_pos(x.contiguous(), dp["embed"], dp["pos"], x0)
-        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph)
+        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph, one_kernel)
 
 
 class _nullctx:

@@ -490,6 +490,54 @@ def argmax_advance(logits, tokens_out, *, step, counter, pos=None, history=None,
                                 counter.data_ptr(), _ptr(keys), _stream()), "kx_argmax_advance")
 
 
+def _ptr_array(tensors):
+    return (_abi.C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def decode_step_buffers(batch, heads, t_max, layers, device):
+    """(plan bytes, scratch fp32, counters int32 (zeroed), barrier 32 x int64 (zeroed)) for kx_decode_plan_build."""
+    return (torch.empty(int(lib.kx_decode_plan_bytes(layers)), dtype=torch.uint8, device=device),
+            torch.empty(int(lib.kx_decode_step_scratch_floats(batch, heads, t_max)), dtype=torch.float32, device=device),
+            torch.zeros(int(lib.kx_decode_step_counters(batch, heads)), dtype=torch.int32, device=device),
+            torch.zeros(32, dtype=torch.int64, device=device))
+
+
+def decode_plan_build(plan, *, layers, out, embed_table, pos_table, tabs, k_cache, v_cache, tokens, x, xb, q, att, mid, logits,
+                      keys, pos, step, err_flag, scratch, counters, barrier, heads, ffn, t_max, eps, scale, forced=None,
+                      history=None, trace=None):
+    """layers: list of dicts with (w, c, d) triples under "qkv", "o", "fc1", "fc2"; out: the (w, c, d) of the LM head."""
+    g = _abi.DecodeStepArgs()
+    B, D = x.shape
+    g.batch, g.layers, g.d_model, g.ffn, g.heads, g.vocab, g.t_max = B, len(layers), D, ffn, heads, out[0].shape[0], t_max
+    g.pos_rows, g.eps, g.scale = pos_table.shape[0], eps, scale
+    keep = []
+    for name in ("qkv", "o", "fc1", "fc2"):
+        for j, letter in enumerate("wcd"):
+            arr = _ptr_array([L[name][j] for L in layers])
+            keep.append(arr)
+            setattr(g, f"{letter}_{name}", _abi.C.cast(arr, _abi._pp))
+    ka, va = _ptr_array(list(k_cache)), _ptr_array(list(v_cache))
+    g.k_cache, g.v_cache = _abi.C.cast(ka, _abi._pp), _abi.C.cast(va, _abi._pp)
+    g.w_out, g.c_out, g.d_out = out[0].data_ptr(), out[1].data_ptr(), _ptr(out[2])
+    g.embed_table, g.pos_table = embed_table.data_ptr(), pos_table.data_ptr()
+    g.xq_cos, g.xq_sin, g.xk_cos, g.xk_sin = (t.data_ptr() for t in tabs)
+    g.tokens, g.x, g.xb, g.q, g.att, g.mid = (t.data_ptr() for t in (tokens, x, xb, q, att, mid))
+    g.logits, g.ld_logits = logits.data_ptr(), logits.stride(0)
+    g.argmax_keys, g.pos, g.step, g.err_flag = keys.data_ptr(), pos.data_ptr(), step.data_ptr(), _ptr(err_flag)
+    g.forced, g.history = _ptr(forced), _ptr(history)
+    g.history_ld = history.shape[1] if history is not None else (forced.shape[1] if forced is not None else 0)
+    g.scratch, g.counters, g.barrier = scratch.data_ptr(), counters.data_ptr(), barrier.data_ptr()
+    g.trace = _ptr(trace)
+    check(lib.kx_decode_plan_build(g, plan.data_ptr(), _stream()), "kx_decode_plan_build")
+    return plan
+
+
+def decode_step(plan):
+    """One new token per sequence: one persistent cooperative kernel (kx_decode_step)."""
+    with _Timed("decode_step", 0.0, 0.0):
+        check(lib.kx_decode_step(plan.data_ptr(), _stream()), "kx_decode_step")
+
+
 _graph_launches = 0
 
 

@@ -22,7 +22,7 @@ def decode_bytes(cfg, batch, n_cached):
     return weights, kv
 
 
-def run(model, batch, prompt, new, layers_note=""):
+def run(model, batch, prompt, new, layers_note="", one_kernel=True):
     cfg = model.cfg
     dev = "cuda"
     g = torch.Generator().manual_seed(1)
@@ -45,13 +45,25 @@ def run(model, batch, prompt, new, layers_note=""):
     dec.advance(state, history=history, move=False)
     ep.record()
     torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    n0 = ops.launch_count()
-    with torch.cuda.graph(graph):
-        dec.decode_step(state)
-        dec.advance(state, history=history)
-    nodes = ops.launch_count() - n0
-    for _ in range(3):                                              # warm-up replays (advance the position too)
+    trace = None
+    if one_kernel:
+        n_ph = 1 + 5 * cfg.layers + 2
+        trace = torch.zeros(2 * n_ph, dtype=torch.int64, device=dev) if os.environ.get("KX_STEP_TRACE") else None
+        plan = dec.build_step_plan(state, history=history, trace=trace)
+
+        class _One:
+            @staticmethod
+            def replay():
+                ops.decode_step(plan)
+        graph, nodes = _One, 1
+    else:
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(graph):
+            dec.decode_step(state)
+            dec.advance(state, history=history)
+        nodes = ops.launch_count() - n0
+    for _ in range(3):                                              # warm-up steps (advance the position too)
         graph.replay()
     torch.cuda.synchronize()
     first_pos = int(state.pos.item())
@@ -62,6 +74,20 @@ def run(model, batch, prompt, new, layers_note=""):
     e2.record()
     torch.cuda.synchronize()
     ms_step = e1.elapsed_time(e2) / steps
+    if trace is not None:                                           # per-phase timeline of CTA 0 in the LAST step
+        t = trace.cpu().view(-1, 2).tolist()
+        names = ["embed"] + ["qkv", "attn", "out", "fc1", "fc2"] * cfg.layers + ["head", "pick"]
+        agg = {}
+        prev_leave = None
+        for i, (done, leave) in enumerate(t):
+            if prev_leave is not None and done:
+                a = agg.setdefault(names[i], [0, 0.0, 0.0])
+                a[0] += 1; a[1] += (done - prev_leave) / 1e3
+                if leave:
+                    a[2] += (leave - done) / 1e3
+            prev_leave = leave if leave else None
+        for k, (n, work, wait) in agg.items():
+            print(f"trace {k:6s} x{n:3d}: CTA0 work {work / n:7.2f} us, barrier wait {wait / n:7.2f} us", file=sys.stderr)
     ms_prompt = e0.elapsed_time(ep)
     last_pos = int(state.pos.item())
     w_bytes, kv_lo = decode_bytes(cfg, batch, first_pos)
@@ -75,7 +101,9 @@ def run(model, batch, prompt, new, layers_note=""):
     peak = float(peaks.get("hbm_gbs", 6530.6))
     out = dict(batch=batch, prompt=T, new_tokens=new, timed_steps=steps, kernels_per_step=nodes, ms_prompt_pass=ms_prompt, ms_per_step=ms_step,
                tokens_per_s=batch / ms_step * 1e3, weight_bytes=w_bytes, kv_bytes_mean=0.5 * (kv_lo + kv_hi),
-               achieved_gbs=by / ms_step / 1e6, peak_gbs=peak, frac=by / ms_step / 1e6 / peak, note=layers_note)
+               achieved_gbs=by / ms_step / 1e6, peak_gbs=peak, frac=by / ms_step / 1e6 / peak,
+               path="one persistent kernel per step" if one_kernel else "per-kernel step, CUDA-graph replay",
+               err_flag=int(state.err.item()), tokens_head=history[0, :8].tolist())
     return out
 
 
@@ -86,11 +114,12 @@ def main():
     ap.add_argument("--new", type=int, default=128)
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--per-kernel", action="store_true", help="also time every launch of one eager step")
+    ap.add_argument("--mode", default="one", choices=["one", "graph"], help="one persistent kernel per step, or per-kernel graph")
     a = ap.parse_args()
     cfg = KosmosConfig(max_positions=2050, layers=a.layers)
     torch.manual_seed(0)
     model = Kosmos(config=cfg, device="cuda")
-    r = run(model, a.batch, a.prompt, a.new)
+    r = run(model, a.batch, a.prompt, a.new, one_kernel=(a.mode == "one"))
     print(json.dumps(r))
     if a.per_kernel:
         st = model._last_decode_state
