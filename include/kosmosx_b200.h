@@ -389,8 +389,9 @@ typedef struct kx_decode_step_args {
     unsigned long long* argmax_keys; int* pos; int* step; int* err_flag;
     const long long* forced; long long* history; int history_ld;                         /* forced / history may be NULL */
     float* scratch; int* counters; unsigned long long* barrier;
-    long long* trace;   /* optional profiling aid: int64 [2 * phases]; CTA 0 stamps %globaltimer when its own work of a phase
-                         * is done and when it leaves the barrier behind it (phases = 1 + 5*layers + 2) */
+    long long* trace;   /* optional profiling aid: int64 [2 * phases + 17]; CTA 0 stamps %globaltimer when its own work of a
+                         * phase is done and when it leaves the barrier behind it (phases = 1 + 5*layers + 2); entry
+                         * [2*phases] selects one Linear phase (-1 = none) whose item gets 16 finer stamps after it */
 } kx_decode_step_args;
 
 size_t kx_decode_plan_bytes(int layers);

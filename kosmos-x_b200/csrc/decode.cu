@@ -140,6 +140,30 @@ decode_linear_kernel(const DecLin p) {
     }
 
     pdl_launch_dependents();
+    // Epilogue operands of this thread's first output (batch row tid / 16, feature tid % 16) are requested up front so
+    // that their DRAM round trips overlap the weight stream: the folded-LayerNorm / bias vectors are immutable (before
+    // the dependency wait), the xPos table entries and the residual value right after it.
+    const int e_n = min(n0 + (tid & 15), p.N - 1);
+    const int e_b = tid >> 4;
+    float e_lnc = 0.f, e_bias = 0.f, e_c = 1.f, e_s = 0.f, e_x = 0.f;
+    if (tid < 16 * NBC) {
+        if (p.ln) e_lnc = __ldg(p.ln_c + e_n);
+        if (p.bias != nullptr) e_bias = __ldg(p.bias + e_n);
+    }
+    auto after_wait = [&]() {
+        if (tid >= 16 * NBC || e_b >= p.B) return;
+        if (p.mode == KX_DEC_QKV) {
+            const int which = e_n / p.d_model;
+            if (which < 2) {
+                const int pos = *p.pos;
+                const int j = (e_n & 63) >> 1;
+                e_c = __ldg((which == 0 ? p.xq_cos : p.xk_cos) + pos * 32 + j);
+                e_s = __ldg((which == 0 ? p.xq_sin : p.xk_sin) + pos * 32 + j);
+            }
+        } else if (p.mode == KX_DEC_RESIDUAL) {
+            e_x = p.x[static_cast<long long>(e_b) * p.ld_x + e_n];
+        }
+    };
     bool waited = false;
     for (int s = s_begin; s < s_end; s += U) {
         uint4 wa[U], wb[U], av[U][NB];
@@ -150,7 +174,7 @@ decode_linear_kernel(const DecLin p) {
             wa[u] = ok ? ld_stream(w0 + o) : make_uint4(0, 0, 0, 0);
             wb[u] = ok ? ld_stream(w1 + o) : make_uint4(0, 0, 0, 0);
         }
-        if (!waited) { pdl_wait(); waited = true; }        // weights do not depend on the previous kernel; `a` does
+        if (!waited) { pdl_wait(); waited = true; after_wait(); }   // weights do not depend on the previous kernel; `a` does
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool ok = s + u < s_end;
@@ -175,7 +199,7 @@ decode_linear_kernel(const DecLin p) {
         }
     }
 
-    if (!waited) pdl_wait();
+    if (!waited) { pdl_wait(); after_wait(); }
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
         red[warp][g][nb * 8 + 2 * t] = acc[nb][0];
@@ -206,9 +230,9 @@ decode_linear_kernel(const DecLin p) {
             const float mean = a1 * inv_n;
             const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
             const float rstd = rsqrtf(var + p.eps);
-            v = fmaf(-mean * rstd, __ldg(p.ln_c + n), v * rstd);
+            v = fmaf(-mean * rstd, o == tid ? e_lnc : __ldg(p.ln_c + n), v * rstd);
         }
-        if (p.bias != nullptr) v += __ldg(p.bias + n);
+        if (p.bias != nullptr) v += (o == tid ? e_bias : __ldg(p.bias + n));
         fin[r][b] = v;
     }
     __syncthreads();
@@ -241,8 +265,8 @@ decode_linear_kernel(const DecLin p) {
             const int pos = *p.pos;
             if (which < 2) {                               // xPos rotation of the (2j, 2j+1) pair at position pos
                 const int j = (n & 63) >> 1;
-                const float c = __ldg((which == 0 ? p.xq_cos : p.xk_cos) + pos * 32 + j);
-                const float s = __ldg((which == 0 ? p.xq_sin : p.xk_sin) + pos * 32 + j);
+                const float c = o == tid ? e_c : __ldg((which == 0 ? p.xq_cos : p.xk_cos) + pos * 32 + j);
+                const float s = o == tid ? e_s : __ldg((which == 0 ? p.xq_sin : p.xk_sin) + pos * 32 + j);
                 const float x0 = fin[r & ~1][b], x1 = fin[r | 1][b];
                 v = (r & 1) ? fmaf(x1, c, x0 * s) : fmaf(x0, c, -(x1 * s));
             }
@@ -256,7 +280,7 @@ decode_linear_kernel(const DecLin p) {
             }
         } else if (p.mode == KX_DEC_RESIDUAL) {
             float* px = p.x + static_cast<long long>(b) * p.ld_x + n;
-            v += *px;
+            v += (o == tid ? e_x : *px);
             *px = v;
             p.xb[static_cast<long long>(b) * p.ld_xb + n] = __float2bfloat16_rn(v);
         } else {

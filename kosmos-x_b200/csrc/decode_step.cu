@@ -1,19 +1,28 @@
 // One decoding step as ONE persistent cooperative kernel.
 //
-// The per-kernel path (decode.cu) spends more time between kernels than inside them: a step is 123 launches of 5-35 MB
-// each, and at 6.5 TB/s a 25 MB weight matrix is 4 us of work next to a launch + drain + first-load latency chain of
-// about the same length.  Here the whole step — embedding, 24 x (q|k|v, attention, out_proj, fc1, fc2), LM head, greedy
-// choice — runs in one grid of 3 CTAs per SM.  Phases are separated by a grid barrier (one 64-bit arrival counter,
-// never reset: the target of barrier i in launch e is (e * barriers + i + 1) * gridDim.x), and before a CTA waits at a
-// barrier it has already issued the first weight loads of its first work item of the NEXT phase — weights do not depend
-// on the previous phase, so HBM stays busy while the barrier drains.  Work items: a Linear phase is cut into 16-row
-// weight tiles (x split-K for the narrow out_proj / fc2 so that enough bytes are in flight; the last split to arrive
-// sums the partials in a fixed order and runs the epilogue), the attention phase into (batch, head, 256-key chunk)
-// items merged by the last arriver.  The tile arithmetic is the same as decode_linear_kernel / decode_attention_kernel
-// (same MMA k-permutation, same folded LayerNorm, same fixed summation order within a tile).
+// A decoding step streams 2.55 GB of weights plus the KV cache and does almost no arithmetic: the only thing that
+// matters is that HBM never idles.  The per-kernel path (decode.cu) cannot keep it busy: 123 launches of 5-35 MB each
+// are latency-bound streams (ncu: long-scoreboard stalls, 24 warps/SM) separated by launch / drain gaps.  Here the whole
+// step — embedding, 24 x (q|k|v, attention, out_proj, fc1, fc2), LM head, greedy choice — is one grid of 2 CTAs per SM:
 //
-// Activations written in one phase are read in the next by other SMs: they are read with ld.global.cg (L2), never
-// through the non-coherent L1; weights and tables are immutable and use the streaming / read-only paths.
+//   * warp 8 of every CTA is a PRODUCER: one thread walks the CTA's whole work list of the step and moves it through a
+//     3-stage, 33 KB-per-stage shared-memory ring with bulk copies (cp.async.bulk, mbarrier complete_tx): 16 weight
+//     rows x 1024 k per stage for a Linear item, 256 keys of K or of V for an attention item.  Weights and the history
+//     rows of the cache are immutable during the launch, so the producer never waits for a phase boundary: while the
+//     consumers of a CTA sit in a grid barrier its ring is already filling with the NEXT phase's bytes (200 KB per SM
+//     in flight, several times what Little's law asks for at 6.5 TB/s).
+//   * warps 0-7 are CONSUMERS: mma.sync m16n8k16 with the weight rows as the M dimension and the (<= 8) sequences as N,
+//     fragments read from the ring with conflict-free 16-byte LDS (rows padded by 64 bytes), the same k-permutation,
+//     folded LayerNorm, fixed-order reductions and epilogues as decode_linear_kernel; attention reads its 256-key chunk
+//     from the ring and the single NEW key/value row (written by the q|k|v phase of this launch) straight from L2.
+//   * phases are separated by a grid barrier over the consumers (arrivals on one line, release flag on another).
+//     Every dependent L2 round trip inside a phase is on the critical path of the whole GPU, so the work is cut to
+//     keep those chains short: a Linear phase is ONE pass (a CTA takes one 16-row tile, or two tiles that share the
+//     activation fragments when there are more tiles than CTAs; no split-K exchange), activations of the next k chunk
+//     are fetched while the current one is multiplied, and an attention item is a whole (batch, head) — its chunks are
+//     folded with an online softmax inside the CTA, so there is no cross-CTA merge.
+//
+// Activations written in one phase are read in the next by other SMs with ld.global.cg (L2), never through L1.
 #include "kx_internal.h"
 #include "ptx.cuh"
 
@@ -24,13 +33,18 @@ namespace kx {
 namespace {
 
 enum { PH_EMBED = 0, PH_LINEAR = 1, PH_ATTN = 2, PH_PICK = 3 };
-constexpr int STEP_THREADS = 256;
-// Two register / occupancy trade-offs of the same kernel (KX_DECODE_STEP_VARIANT selects; default 0):
-//   variant 0: 3 CTAs/SM, SU = 4 k-steps (8 x 16-byte weight loads) in flight per thread   (<= 80 registers)
-//   variant 1: 2 CTAs/SM, SU = 8                                                             (<= 128 registers)
-constexpr int ATTN_CHUNK = 256;             // keys per attention item (8 warps x 32)
-constexpr int PART_STRIDE = 16 * 8 + 8 * 2; // split-K partial: 16x8 sums + 8 (sum, sumsq) pairs
-constexpr int SPLITK_MAX_ITEMS = 2048;      // split phases have items <= grid (pick_ksplit), grid <= 3 * SMs
+constexpr int CONSUMER_WARPS = 8;
+constexpr int CONSUMERS = CONSUMER_WARPS * 32;
+constexpr int STEP_THREADS = CONSUMERS + 32;
+constexpr int STEP_CTAS_PER_SM = 2;
+constexpr int NS = 3;                           // ring stages
+constexpr int CHUNK_K = 1024;                   // k per weight stage
+constexpr int W_PITCH = CHUNK_K * 2 + 64;       // bytes per staged weight row (+64: the quad-row LDS.128 pattern hits all banks)
+constexpr int STAGE_BYTES = 16 * W_PITCH;       // 33792 >= 256 keys x 128 bytes
+constexpr int ATTN_CHUNK = 256;                 // keys per attention item (8 warps x 32)
+constexpr int PART_STRIDE = 16 * 8 + 8 * 2;     // split-K partial: 16x8 sums + 8 (sum, sumsq) pairs
+constexpr int SPLITK_MAX_ITEMS = 2048;          // split phases have items <= grid (pick_ksplit)
+static_assert(STAGE_BYTES >= ATTN_CHUNK * 128 && STAGE_BYTES % 128 == 0, "ring stage geometry");
 
 struct Phase {
     int type, items;
@@ -38,7 +52,7 @@ struct Phase {
     const __nv_bfloat16* a; long long lda;
     const __nv_bfloat16* w; long long ldw; int N, K;
     const float* ln_c; const float* bias;
-    int mode, act, ksplit;
+    int mode, act, nt;                       // nt: weight tiles per item (1, or 2 sharing the activation fragments)
     void* out; long long ld_out; int out_f32; unsigned long long* argmax_keys;
     // attention: q_out = q, k_cache, v_cache, out = attention output (bf16, ld_out)
     __nv_bfloat16* q_out; __nv_bfloat16* k_cache; __nv_bfloat16* v_cache;
@@ -65,13 +79,22 @@ struct StepPlan {
 };
 
 struct StepSmem {
-    float red[8][16][8];
+    float red[2][8][16][8];
     float st[8][8][2];
-    float fin[16][8];
+    float fin[2][16][8];
     float att_o[8][64];
     float att_ml[8][2];
     int flag;
+    uint64_t full[NS], empty[NS];
+    StepCommon c;                           // the plan, staged: field reads are LDS, not dependent global loads
+    Phase ph[2];                            // current / next phase (the next one is fetched before the barrier)
 };
+
+__device__ __forceinline__ void stage_words(void* dst_smem, const void* src_global, int bytes, int tid, int nthreads) {
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst_smem);
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(src_global);
+    for (int i = tid; i < bytes / 4; i += nthreads) d[i] = __ldg(g + i);
+}
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -84,15 +107,14 @@ __device__ __forceinline__ void stats2(uint32_t v, float& s1, float& s2) {
     s1 += lo + hi;
     s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
 }
-__device__ __forceinline__ uint4 ldw_stream(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ uint4 ld_cg4(const uint4* p) {
     uint4 v;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ int ld_cg_i(const int* p) {
@@ -105,164 +127,276 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// Polling load: relaxed, so that ptxas does not attach an L1 invalidation (CCTL.IVALL) to every iteration — ncu showed
+// the acquire version flushing L1 on each poll, which turned every later read of the plan into an L2 round trip.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// global -> shared bulk copy completing on an mbarrier (bytes % 16 == 0, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { named_bar_sync(1, CONSUMERS); }
+// mbarrier wait without a diagnostic printf (its argument block is a stack frame, and local memory is an L2 round trip
+// in this kernel); a pipeline bug still traps instead of hanging.
+__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (3ll << 31)) __trap();
+    }
+}
+// fine-grained profiling stamps of CTA 0 / thread 0 inside one chosen phase (trace[2*n_phases + 1 + k]; the chosen phase
+// index is read from trace[2*n_phases], -1 = none)
+__device__ __forceinline__ void stamp(long long* dbg, int k) {
+#ifdef KX_STEP_FINE_TRACE                   // costs registers: the kernel spills with it (and spills are L2 round trips here,
+    if (dbg != nullptr) dbg[k] = static_cast<long long>(globaltimer_ns());     // L1 is invalidated at every grid barrier)
+#else
+    (void)dbg; (void)k;
+#endif
+}
 
-// All CTAs of the (cooperative, co-resident) grid arrive; a bounded spin so that a logic error cannot hang the GPU.
-// Arrivals are counted on one line; the last arriver publishes the barrier's target on ANOTHER line (ctr[16]) that the
-// waiters poll, so the polls do not queue behind the arrival atomics.
-__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target, int* err_flag) {
-    __syncthreads();
+// Grid barrier over the consumers of all (co-resident) CTAs.  Arrivals are counted on one line; the last arriver
+// publishes the target on ANOTHER line (ctr[16]) that the waiters poll.  Bounded spin: a logic error cannot hang the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target, int* err_flag, long long* dbg) {
+    consumer_sync();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long old = atomicAdd(ctr, 1ull);
+        stamp(dbg, 8);
+        // release on the arrival itself (cumulative over the CTA's writes ordered before it by the bar.sync above) instead
+        // of a stand-alone MEMBAR.SC: the full fence also waited for the producer's in-flight bulk copies to drain
+        unsigned long long old;
+        asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;\n" : "=l"(old) : "l"(ctr) : "memory");
+        stamp(dbg, 9);
         if (old + 1 == target) {
             asm volatile("st.release.gpu.global.u64 [%0], %1;\n" :: "l"(ctr + 16), "l"(target) : "memory");
         } else {
             const long long t0 = clock64();
-            while (ld_acquire_u64(ctr + 16) < target) {
-                if (clock64() - t0 > (3ll << 30)) {         // ~2 s at 1.7 GHz
+            while (ld_relaxed_u64(ctr + 16) < target) {
+                if (clock64() - t0 > (3ll << 30)) {         // ~2 s
                     if (err_flag != nullptr) atomicOr(err_flag, 4);
                     break;
                 }
             }
+            (void)ld_acquire_u64(ctr + 16);                 // one acquire (one L1 invalidation) once the flag is seen
         }
-        __threadfence();
     }
-    __syncthreads();
+    consumer_sync();
 }
 
-__device__ __forceinline__ long long global_ns() {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-    return t;
-}
-
-struct LinItem {
-    int tile, split, s_begin, s_end;
-    const uint4 *w0, *w1;
+// ---- the work list of one CTA, walked identically by its producer and its consumers -------------------------------
+struct Ring {
+    uint32_t base;                          // shared address of stage 0
+    uint64_t* full;
+    uint64_t* empty;
+    uint32_t i;                             // stages used so far
+    __device__ __forceinline__ uint32_t slot() const { return i % NS; }
+    __device__ __forceinline__ uint32_t parity() const { return (i / NS) & 1; }
+    __device__ __forceinline__ uint32_t addr() const { return base + slot() * STAGE_BYTES; }
 };
 
-__device__ __forceinline__ LinItem lin_item(const Phase& p, int item) {
-    LinItem it;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    it.tile = item / p.ksplit;
-    it.split = item - it.tile * p.ksplit;
-    const int sps = (p.K >> 5) / p.ksplit;
-    const int spw = (sps + 7) >> 3;
-    const int s0 = it.split * sps;
-    it.s_begin = s0 + warp * spw;
-    it.s_end = min(s0 + sps, it.s_begin + spw);
-    const int n0 = it.tile * 16;
-    const int r0 = min(n0 + g, p.N - 1), r1 = min(n0 + g + 8, p.N - 1);
-    it.w0 = reinterpret_cast<const uint4*>(p.w + static_cast<long long>(r0) * p.ldw) + t;
-    it.w1 = reinterpret_cast<const uint4*>(p.w + static_cast<long long>(r1) * p.ldw) + t;
-    return it;
-}
-
-template <int SU>
-__device__ __forceinline__ void lin_load_w(const LinItem& it, int s, uint4 (&wa)[SU], uint4 (&wb)[SU]) {
-#pragma unroll
-    for (int u = 0; u < SU; ++u) {
-        const bool ok = s + u < it.s_end;
-        wa[u] = ok ? ldw_stream(it.w0 + (s + u) * 4) : make_uint4(0, 0, 0, 0);
-        wb[u] = ok ? ldw_stream(it.w1 + (s + u) * 4) : make_uint4(0, 0, 0, 0);
+// Producer warp, all 32 lanes: lane 0 waits for the slot and arms the barrier, then lane `row` issues that row's copy —
+// sixteen bulk copies leave in one warp instruction instead of sixteen dependent issues by one thread (measured: the
+// single-thread version needed ~1.3 us per 32 KB stage, i.e. 25 GB/s per CTA).
+__device__ __forceinline__ void produce_linear(const Phase& p, int item, Ring& r, int lane) {
+    const int tiles = (p.N + 15) >> 4;
+    const int K = p.K, N = p.N, nt = p.nt, items = p.items;
+    const long long ldw = p.ldw;
+    const __nv_bfloat16* w = p.w;
+    for (int kc = 0; kc < K; kc += CHUNK_K) {
+        const int ck = min(CHUNK_K, K - kc);
+        for (int tt = 0; tt < nt; ++tt) {
+            const int tile = item + tt * items;
+            if (tile >= tiles) break;
+            const int n0 = tile * 16;
+            const int rows = min(16, N - n0);
+            if (lane == 0) {
+                ring_wait(r.empty + r.slot(), r.parity() ^ 1);
+                mbar_arrive_expect_tx(r.full + r.slot(), static_cast<uint32_t>(rows * ck * 2));
+            }
+            __syncwarp();
+            if (lane < rows)
+                bulk_g2s(r.addr() + lane * W_PITCH, w + static_cast<long long>(n0 + lane) * ldw + kc, static_cast<uint32_t>(ck * 2),
+                         r.full + r.slot());
+            ++r.i;
+        }
     }
 }
 
-// One (tile, split) item of a Linear phase.  `pre`: wa / wb already hold the first batch (loaded before the barrier).
-template <int SU>
-__device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C, int item, bool pre, uint4 (&wa)[SU],
-                                            uint4 (&wb)[SU], StepSmem& sm) {
+// Attention item: the K and V chunks are contiguous 32 KB streams; 8 lanes x 4 KB each.
+__device__ __forceinline__ void produce_attn(const Phase& p, const StepCommon& C, int bh, int n_keys, Ring& r, int lane) {
+    const int n_chunks = (n_keys + ATTN_CHUNK - 1) / ATTN_CHUNK;
+    const __nv_bfloat16* kc_ptr = p.k_cache;
+    const __nv_bfloat16* vc_ptr = p.v_cache;
+    for (int c = 0; c < n_chunks; ++c) {
+        // history rows only (keys < n_keys - 1): the newest row is written by this launch and read from L2 by the consumers
+        const int rows = min(n_keys - 1, (c + 1) * ATTN_CHUNK) - c * ATTN_CHUNK;
+        const long long off = (static_cast<long long>(bh) * C.t_max + static_cast<long long>(c) * ATTN_CHUNK) * 64;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            if (lane == 0) {
+                ring_wait(r.empty + r.slot(), r.parity() ^ 1);
+                if (rows > 0) mbar_arrive_expect_tx(r.full + r.slot(), static_cast<uint32_t>(rows * 128));
+                else mbar_arrive(r.full + r.slot());
+            }
+            __syncwarp();
+            const int r_lo = lane * 32, r_n = min(32, rows - r_lo);          // 32 rows = 4 KB per lane
+            if (lane < 8 && r_n > 0)
+                bulk_g2s(r.addr() + r_lo * 128, (which ? vc_ptr : kc_ptr) + off + r_lo * 64, static_cast<uint32_t>(r_n * 128),
+                         r.full + r.slot());
+            ++r.i;
+        }
+    }
+}
+
+__device__ void producer(const StepPlan* plan, const StepCommon& C, Ring r) {
+    const int lane = threadIdx.x & 31;
+    const int n_keys = min(ld_cg_i(C.pos) + 1, C.t_max);     // pos only changes in the last phase of a launch
+    const int n_phases = C.n_phases;
+    for (int ph = 0; ph < n_phases; ++ph) {
+        const Phase& P = plan->ph[ph];
+        const int type = P.type, items = P.items;
+        if (type == PH_LINEAR) {
+            for (int item = blockIdx.x; item < items; item += gridDim.x) produce_linear(P, item, r, lane);
+        } else if (type == PH_ATTN) {
+            for (int item = blockIdx.x; item < items; item += gridDim.x) produce_attn(P, C, item, n_keys, r, lane);
+        }
+    }
+}
+
+// One item of a Linear phase (consumer warps): NT weight tiles against the same activation fragments.
+template <int NT>
+__device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C, int item, Ring& r, StepSmem& sm, long long* dbg) {
+    stamp(dbg, 0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const LinItem it = lin_item(p, item);
+    const int tiles = (p.N + 15) >> 4;
     const bool aok = g < C.batch;
     const uint4* ap = reinterpret_cast<const uint4*>(p.a + static_cast<long long>(aok ? g : 0) * p.lda) + t;
     const bool ln = p.ln_c != nullptr;
+    bool tile_ok[NT];
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) tile_ok[tt] = item + tt * p.items < tiles;
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float s1 = 0.f, s2 = 0.f;
-    for (int s = it.s_begin; s < it.s_end; s += SU) {
-        if (!pre) lin_load_w(it, s, wa, wb);
-        pre = false;
-        uint4 av[SU];
-#pragma unroll
-        for (int u = 0; u < SU; ++u)
-            av[u] = (aok && s + u < it.s_end) ? ld_cg4(ap + (s + u) * 4) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int u = 0; u < SU; ++u) {
-            mma16816(acc, wa[u].x, wb[u].x, wa[u].y, wb[u].y, av[u].x, av[u].y);
-            mma16816(acc, wa[u].z, wb[u].z, wa[u].w, wb[u].w, av[u].z, av[u].w);
-            if (ln) { stats2(av[u].x, s1, s2); stats2(av[u].y, s1, s2); stats2(av[u].z, s1, s2); stats2(av[u].w, s1, s2); }
+    // Everything the epilogue of this thread's (tile, batch row, feature) needs is requested NOW, so that those DRAM /
+    // L2 round trips overlap the k loop instead of sitting on the phase's critical path.
+    const int e_tt = tid >> 7, e_idx = tid & 127;
+    const int e_b = e_idx >> 4, e_r = e_idx & 15;
+    const bool e_mine = e_tt < NT && item + e_tt * p.items < tiles;
+    const int e_n = min((item + e_tt * p.items) * 16 + e_r, p.N - 1);
+    float e_lnc = 0.f, e_bias = 0.f, e_c = 1.f, e_s = 0.f, e_x = 0.f;
+    int e_pos = 0;
+    if (e_mine) {
+        if (ln) e_lnc = __ldg(p.ln_c + e_n);
+        if (p.bias != nullptr) e_bias = __ldg(p.bias + e_n);
+        if (p.mode == KX_DEC_QKV) {
+            e_pos = ld_cg_i(C.pos);
+            const int which = e_n / C.d_model;
+            if (which < 2) {
+                const int j = (e_n & 63) >> 1;
+                e_c = __ldg((which == 0 ? C.xq_cos : C.xk_cos) + e_pos * 32 + j);
+                e_s = __ldg((which == 0 ? C.xq_sin : C.xk_sin) + e_pos * 32 + j);
+            }
+        } else if (p.mode == KX_DEC_RESIDUAL && e_b < C.batch) {
+            e_x = __ldcg(C.x + static_cast<long long>(e_b) * C.d_model + e_n);     // last written two phases ago
         }
     }
-    sm.red[warp][g][2 * t] = acc[0];
-    sm.red[warp][g][2 * t + 1] = acc[1];
-    sm.red[warp][g + 8][2 * t] = acc[2];
-    sm.red[warp][g + 8][2 * t + 1] = acc[3];
+
+    float acc[NT][4];
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) acc[tt][0] = acc[tt][1] = acc[tt][2] = acc[tt][3] = 0.f;
+    float s1 = 0.f, s2 = 0.f;
+
+    auto load_a = [&](int kc, uint4 (&av)[4]) {
+        const int steps = min(CHUNK_K, p.K - kc) >> 5;
+        const int spw = (steps + CONSUMER_WARPS - 1) / CONSUMER_WARPS;
+        const int s_lo = warp * spw, s_hi = min(steps, s_lo + spw);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            av[u] = (aok && s_lo + u < s_hi) ? ld_cg4(ap + ((kc >> 3) + (s_lo + u) * 4)) : make_uint4(0, 0, 0, 0);
+    };
+    uint4 av[4];
+    for (int kc = -CHUNK_K; kc < p.K; kc += CHUNK_K) {      // the first pass only requests chunk 0's activations
+        const bool more = kc + CHUNK_K < p.K;
+        const int steps = kc < 0 ? 0 : (min(CHUNK_K, p.K - kc) >> 5);
+        const int spw = (steps + CONSUMER_WARPS - 1) / CONSUMER_WARPS;        // <= 4
+        const int s_lo = warp * spw, s_hi = min(steps, s_lo + spw);
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) {
+            if (kc < 0) break;
+            if (!tile_ok[tt]) continue;
+            ring_wait(r.full + r.slot(), r.parity());
+            if (kc == 0 && tt == 0) stamp(dbg, 2);
+            const uint32_t wrow = r.addr() + g * W_PITCH + t * 16;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (s_lo + u < s_hi) {
+                    const uint4 wa = lds4(wrow + (s_lo + u) * 64);
+                    const uint4 wb = lds4(wrow + 8 * W_PITCH + (s_lo + u) * 64);
+                    mma16816(acc[tt], wa.x, wb.x, wa.y, wb.y, av[u].x, av[u].y);
+                    mma16816(acc[tt], wa.z, wb.z, wa.w, wb.w, av[u].z, av[u].w);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(r.empty + r.slot());
+            ++r.i;
+        }
+        if (ln) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (s_lo + u < s_hi) { stats2(av[u].x, s1, s2); stats2(av[u].y, s1, s2); stats2(av[u].z, s1, s2); stats2(av[u].w, s1, s2); }
+        }
+        // next chunk's activations: requested as soon as these registers are free (a second register set made the
+        // kernel spill, and a spill is an L2 round trip here)
+        if (more) load_a(kc + CHUNK_K, av);
+    }
+    stamp(dbg, 3);
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) {
+        sm.red[tt][warp][g][2 * t] = acc[tt][0];
+        sm.red[tt][warp][g][2 * t + 1] = acc[tt][1];
+        sm.red[tt][warp][g + 8][2 * t] = acc[tt][2];
+        sm.red[tt][warp][g + 8][2 * t + 1] = acc[tt][3];
+    }
     if (ln) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
         s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
         if (t == 0) { sm.st[warp][g][0] = s1; sm.st[warp][g][1] = s2; }
     }
-    __syncthreads();
+    consumer_sync();
+    stamp(dbg, 4);
 
-    const int b = tid >> 4, r = tid & 15;                   // threads 0..127: (batch row b, feature r)
-    float v = 0.f, a1 = 0.f, a2 = 0.f;
-    if (tid < 128) {
+    // threads 0..127 finish tile 0, threads 128..255 tile 1: (batch row b, feature r16)
+    const int tt = tid >> 7, idx = tid & 127;
+    const int b = idx >> 4, r16 = idx & 15;
+    const bool mine = tt < NT && item + tt * p.items < tiles;
+    const int n0 = (item + tt * p.items) * 16;
+    float v = 0.f;
+    if (mine) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += sm.red[w][r][b];
+        for (int w = 0; w < 8; ++w) v += sm.red[tt][w][r16][b];
         if (ln) {
+            float a1 = 0.f, a2 = 0.f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) { a1 += sm.st[w][b][0]; a2 += sm.st[w][b][1]; }
-        }
-    }
-    if (p.ksplit > 1) {                                     // exchange split-K partials; the last arriver continues
-        float* mine = C.splitk_part + static_cast<long long>(item) * PART_STRIDE;
-        if (tid < 128) {
-            mine[r * 8 + b] = v;
-            if (r == 0) { mine[128 + 2 * b] = a1; mine[128 + 2 * b + 1] = a2; }
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const int done = atomicAdd(C.splitk_counters + it.tile, 1);
-            sm.flag = (done == p.ksplit - 1);
-            if (sm.flag) C.splitk_counters[it.tile] = 0;
-        }
-        __syncthreads();
-        if (!sm.flag) return;
-        __threadfence();
-        if (tid < 128) {
-            v = 0.f; a1 = 0.f; a2 = 0.f;
-            const float* base = C.splitk_part + static_cast<long long>(it.tile) * p.ksplit * PART_STRIDE;
-            for (int sp = 0; sp < p.ksplit; ++sp) {         // fixed order: bit-reproducible
-                v += __ldcg(base + sp * PART_STRIDE + r * 8 + b);
-                a1 += __ldcg(base + sp * PART_STRIDE + 128 + 2 * b);
-                a2 += __ldcg(base + sp * PART_STRIDE + 128 + 2 * b + 1);
-            }
-        }
-    }
-    const int n0 = it.tile * 16;
-    if (tid < 128) {
-        const int n = min(n0 + r, p.N - 1);
-        if (ln) {
             const float inv_n = 1.0f / static_cast<float>(p.K);
             const float mean = a1 * inv_n;
             const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
             const float rstd = rsqrtf(var + C.eps);
-            v = fmaf(-mean * rstd, __ldg(p.ln_c + n), v * rstd);
+            v = fmaf(-mean * rstd, e_lnc, v * rstd);
         }
-        if (p.bias != nullptr) v += __ldg(p.bias + n);
-        sm.fin[r][b] = v;
+        v += e_bias;
+        sm.fin[tt][r16][b] = v;
     }
-    __syncthreads();
+    consumer_sync();
+    stamp(dbg, 5);
 
-    if (tid < 128) {
-        const int n = n0 + r;
-        const bool live = b < C.batch && n < p.N;
-        v = sm.fin[r][b];
-        if (p.argmax_keys != nullptr) {
+    {
+        const int n = n0 + r16;
+        const bool live = mine && b < C.batch && n < p.N;
+        if (p.argmax_keys != nullptr) {                     // all 32 lanes take part in the shuffles
             unsigned long long key = 0ull;
             if (live) {
                 const uint32_t u = __float_as_uint(v);
@@ -274,19 +408,16 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, sft);
                 key = other > key ? other : key;
             }
-            if (r == 0 && b < C.batch) atomicMax(p.argmax_keys + b, key);
+            if (mine && r16 == 0 && b < C.batch && key != 0ull) atomicMax(p.argmax_keys + b, key);
         }
         if (live) {
             if (p.mode == KX_DEC_QKV) {
                 const int which = n / C.d_model;
                 const int col = n - which * C.d_model;
-                const int pos = ld_cg_i(C.pos);
+                const int pos = e_pos;
                 if (which < 2) {
-                    const int j = (n & 63) >> 1;
-                    const float c = __ldg((which == 0 ? C.xq_cos : C.xk_cos) + pos * 32 + j);
-                    const float s = __ldg((which == 0 ? C.xq_sin : C.xk_sin) + pos * 32 + j);
-                    const float x0 = sm.fin[r & ~1][b], x1 = sm.fin[r | 1][b];
-                    v = (r & 1) ? fmaf(x1, c, x0 * s) : fmaf(x0, c, -(x1 * s));
+                    const float x0 = sm.fin[tt][r16 & ~1][b], x1 = sm.fin[tt][r16 | 1][b];
+                    v = (r16 & 1) ? fmaf(x1, e_c, x0 * e_s) : fmaf(x0, e_c, -(x1 * e_s));
                 }
                 if (which == 0) {
                     p.q_out[static_cast<long long>(b) * C.d_model + col] = __float2bfloat16_rn(v);
@@ -297,7 +428,7 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
                 }
             } else if (p.mode == KX_DEC_RESIDUAL) {
                 float* px = C.x + static_cast<long long>(b) * C.d_model + n;
-                v += __ldcg(px);
+                v += e_x;
                 *px = v;
                 C.xb[static_cast<long long>(b) * C.d_model + n] = __float2bfloat16_rn(v);
             } else {
@@ -308,98 +439,123 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
             }
         }
     }
-    // the next item of this CTA writes sm.red only after its own k loop and a __syncthreads: no extra barrier needed,
-    // but sm.fin is read above and rewritten after that barrier, and sm.flag after two: safe.
+    stamp(dbg, 6);
+    // sm.red / sm.st are rewritten by this CTA's next item only after its k loop, sm.fin only after a further
+    // consumer_sync: the reads above are ordered before those writes by the barriers in between.
 }
 
-// One (batch, head, 256-key chunk) item of the attention phase.
-__device__ __forceinline__ void attn_item(const Phase& p, const StepCommon& C, int item, StepSmem& sm) {
-    const int H = C.heads, chunks = C.attn_chunks;
-    const int chunk = item % chunks;
-    const int bh = item / chunks;
+// One (batch, head) item of the attention phase (consumer warps): all 256-key chunks, online softmax per lane.
+__device__ __forceinline__ void attn_item(const Phase& p, const StepCommon& C, int bh, int n_keys, Ring& r, StepSmem& sm) {
+    const int H = C.heads;
     const int b = bh / H, h = bh - b * H;
-    const int n_keys = min(ld_cg_i(C.pos) + 1, C.t_max);
-    const int n_act = (n_keys + ATTN_CHUNK - 1) / ATTN_CHUNK;
-    if (chunk >= n_act) return;                              // uniform over the CTA
+    const int n_chunks = (n_keys + ATTN_CHUNK - 1) / ATTN_CHUNK;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane & 7, kq = lane >> 3;
+    const int newest = n_keys - 1;
 
     float qf[8];
     {
         const uint4 raw = ld_cg4(reinterpret_cast<const uint4*>(p.q_out + static_cast<long long>(b) * C.d_model + h * 64) + sub);
-        const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
+        const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            qf[2 * i] = __uint_as_float(r[i] << 16) * C.scale_log2;
-            qf[2 * i + 1] = __uint_as_float(r[i] & 0xffff0000u) * C.scale_log2;
+            qf[2 * i] = __uint_as_float(rr[i] << 16) * C.scale_log2;
+            qf[2 * i + 1] = __uint_as_float(rr[i] & 0xffff0000u) * C.scale_log2;
         }
     }
-    const int key0 = chunk * ATTN_CHUNK + warp * 32 + kq;
-    const long long base = (static_cast<long long>(b) * H + h) * C.t_max * 64;
-    float sc[8];
-    float m = -INFINITY;
-    {
-        uint4 kr[8];
+    // the newest key / value row is written by this launch's q|k|v phase: read it from L2 (one lane group owns it)
+    const long long new_off = (static_cast<long long>(bh) * C.t_max + newest) * 64;
+    const int lane_key = warp * 32 + kq;                     // key of iteration 0 within a chunk
+    const int rel = (newest & (ATTN_CHUNK - 1)) - lane_key;  // newest == chunk*256 + lane_key + it*4  <=>  it = rel / 4
+    const bool has_new = rel >= 0 && rel < 32 && (rel & 3) == 0;
+    uint4 knew = make_uint4(0, 0, 0, 0);
+    if (has_new) knew = ld_cg4(reinterpret_cast<const uint4*>(p.k_cache + new_off) + sub);
+    float m = -INFINITY, l = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < n_chunks; ++c) {
+        const int key0 = c * ATTN_CHUNK + lane_key;
+        float sc[8];
+        float mc = m;
+        ring_wait(r.full + r.slot(), r.parity());
+        {
+            const uint32_t kbase = r.addr() + lane_key * 128 + sub * 16;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int j = key0 + it * 4;
-            kr[it] = j < n_keys ? ld_cg4(reinterpret_cast<const uint4*>(p.k_cache + base + static_cast<long long>(j) * 64) + sub)
-                                : make_uint4(0, 0, 0, 0);
-        }
+            for (int it = 0; it < 8; ++it) {
+                const int j = key0 + it * 4;
+                uint4 kr = make_uint4(0, 0, 0, 0);
+                if (j < newest) kr = lds4(kbase + it * 512);
+                else if (j == newest) kr = knew;
+                const uint32_t rr[4] = {kr.x, kr.y, kr.z, kr.w};
+                float d = 0.f;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const uint32_t r[4] = {kr[it].x, kr[it].y, kr[it].z, kr[it].w};
-            float d = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                d = fmaf(qf[2 * i], __uint_as_float(r[i] << 16), d);
-                d = fmaf(qf[2 * i + 1], __uint_as_float(r[i] & 0xffff0000u), d);
-            }
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            sc[it] = (key0 + it * 4 < n_keys) ? d : -INFINITY;
-            m = fmaxf(m, sc[it]);
-        }
-    }
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-    float l = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (m > -INFINITY) {
-        uint4 vr[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int j = key0 + it * 4;
-            vr[it] = j < n_keys ? ld_cg4(reinterpret_cast<const uint4*>(p.v_cache + base + static_cast<long long>(j) * 64) + sub)
-                                : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const float pj = ex2_approx(sc[it] - m);
-            l += pj;
-            const uint32_t r[4] = {vr[it].x, vr[it].y, vr[it].z, vr[it].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                o[2 * i] = fmaf(pj, __uint_as_float(r[i] << 16), o[2 * i]);
-                o[2 * i + 1] = fmaf(pj, __uint_as_float(r[i] & 0xffff0000u), o[2 * i + 1]);
+                for (int i = 0; i < 4; ++i) {
+                    d = fmaf(qf[2 * i], __uint_as_float(rr[i] << 16), d);
+                    d = fmaf(qf[2 * i + 1], __uint_as_float(rr[i] & 0xffff0000u), d);
+                }
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                sc[it] = (j < n_keys) ? d : -INFINITY;
+                mc = fmaxf(mc, sc[it]);
             }
         }
-    }
-    l += __shfl_xor_sync(0xffffffffu, l, 8);
-    l += __shfl_xor_sync(0xffffffffu, l, 16);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r.empty + r.slot());
+        ++r.i;
+        if (mc > m) {                                        // online softmax: rescale what this lane has so far
+            const float f = m > -INFINITY ? ex2_approx(m - mc) : 0.f;
+            l *= f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
-        o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+            for (int i = 0; i < 8; ++i) o[i] *= f;
+            m = mc;
+        }
+        uint4 vnew = make_uint4(0, 0, 0, 0);
+        if (has_new && c == n_chunks - 1) vnew = ld_cg4(reinterpret_cast<const uint4*>(p.v_cache + new_off) + sub);
+        ring_wait(r.full + r.slot(), r.parity());
+        {
+            const uint32_t vbase = r.addr() + lane_key * 128 + sub * 16;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int j = key0 + it * 4;
+                uint4 vr = make_uint4(0, 0, 0, 0);
+                if (j < newest) vr = lds4(vbase + it * 512);
+                else if (j == newest) vr = vnew;
+                const float pj = (j < n_keys) ? ex2_approx(sc[it] - m) : 0.f;
+                l += pj;
+                const uint32_t rr[4] = {vr.x, vr.y, vr.z, vr.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    o[2 * i] = fmaf(pj, __uint_as_float(rr[i] << 16), o[2 * i]);
+                    o[2 * i + 1] = fmaf(pj, __uint_as_float(rr[i] & 0xffff0000u), o[2 * i + 1]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(r.empty + r.slot());
+        ++r.i;
     }
-    __syncthreads();                                         // previous item's readers of att_o / att_ml are done
+    // merge the four key groups of the warp (different keys, different running maxima)
+#pragma unroll
+    for (int sft = 8; sft <= 16; sft <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, sft);
+        const float lo = __shfl_xor_sync(0xffffffffu, l, sft);
+        const float M = fmaxf(m, mo);
+        const float f = m > -INFINITY ? ex2_approx(m - M) : 0.f;
+        const float fo = mo > -INFINITY ? ex2_approx(mo - M) : 0.f;
+        l = l * f + lo * fo;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float oo = __shfl_xor_sync(0xffffffffu, o[i], sft);
+            o[i] = o[i] * f + oo * fo;
+        }
+        m = M;
+    }
+    consumer_sync();                                         // previous item's readers of att_o / att_ml are done
     if (kq == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) sm.att_o[warp][sub * 8 + i] = o[i];
         if (sub == 0) { sm.att_ml[warp][0] = m; sm.att_ml[warp][1] = l; }
     }
-    __syncthreads();
-    float* mine = C.attn_part + (static_cast<long long>(bh) * chunks + chunk) * 66;
+    consumer_sync();
     if (threadIdx.x < 64) {
         float M = -INFINITY;
 #pragma unroll
@@ -410,51 +566,6 @@ __device__ __forceinline__ void attn_item(const Phase& p, const StepCommon& C, i
             const float f = sm.att_ml[w][0] > -INFINITY ? ex2_approx(sm.att_ml[w][0] - M) : 0.f;
             L = fmaf(sm.att_ml[w][1], f, L);
             O = fmaf(sm.att_o[w][threadIdx.x], f, O);
-        }
-        if (n_act == 1) {                                    // single chunk: no exchange
-            reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(b) * p.ld_out + h * 64 + threadIdx.x] =
-                __float2bfloat16_rn(O / L);
-        } else {
-            mine[threadIdx.x] = O;
-            if (threadIdx.x == 0) { mine[64] = M; mine[65] = L; }
-        }
-    }
-    if (n_act == 1) return;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int done = atomicAdd(C.attn_counters + bh, 1);
-        sm.flag = (done == n_act - 1);
-        if (sm.flag) C.attn_counters[bh] = 0;
-    }
-    __syncthreads();
-    if (!sm.flag) return;
-    __threadfence();
-    if (threadIdx.x < 64) {
-        const float* all = C.attn_part + static_cast<long long>(bh) * chunks * 66;
-        float M = -INFINITY, L = 0.f, O = 0.f;
-        for (int c0 = 0; c0 < n_act; c0 += 8) {
-            float mc[8], lc[8], oc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const bool ok = c0 + i < n_act;
-                const float* pc = all + (ok ? c0 + i : c0) * 66;
-                mc[i] = ok ? __ldcg(pc + 64) : -INFINITY;
-                lc[i] = __ldcg(pc + 65);
-                oc[i] = __ldcg(pc + threadIdx.x);
-            }
-            float Mn = M;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) Mn = fmaxf(Mn, mc[i]);
-            const float f0 = M > -INFINITY ? ex2_approx(M - Mn) : 0.f;
-            L *= f0; O *= f0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float f = mc[i] > -INFINITY ? ex2_approx(mc[i] - Mn) : 0.f;
-                L = fmaf(lc[i], f, L);
-                O = fmaf(oc[i], f, O);
-            }
-            M = Mn;
         }
         reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(b) * p.ld_out + h * 64 + threadIdx.x] =
             __float2bfloat16_rn(O / L);
@@ -474,20 +585,21 @@ __device__ __forceinline__ void embed_row(const StepCommon& C, int b) {
     }
     const float4* e = reinterpret_cast<const float4*>(C.embed_table + id * C.d_model);
     const float4* pp = reinterpret_cast<const float4*>(C.pos_table + static_cast<long long>(pr) * C.d_model);
-    for (int i = threadIdx.x; i < (C.d_model >> 2); i += blockDim.x) {
+    for (int i = threadIdx.x; i < (C.d_model >> 2); i += CONSUMERS) {
         const float4 a = __ldg(e + i), c = __ldg(pp + i);
-        const float4 r = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
-        reinterpret_cast<float4*>(C.x + static_cast<long long>(b) * C.d_model)[i] = r;
+        const float4 rr = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+        reinterpret_cast<float4*>(C.x + static_cast<long long>(b) * C.d_model)[i] = rr;
         uint2 pk;
-        pk.x = pack_bf16(r.x, r.y); pk.y = pack_bf16(r.z, r.w);
+        pk.x = pack_bf16(rr.x, rr.y); pk.y = pack_bf16(rr.z, rr.w);
         reinterpret_cast<uint2*>(C.xb + static_cast<long long>(b) * C.d_model)[i] = pk;
     }
 }
 
 __device__ __forceinline__ void pick_tokens(const StepCommon& C) {
     const int step = ld_cg_i(C.step);
-    __syncthreads();
-    for (int b = threadIdx.x; b < C.batch; b += blockDim.x) {
+    const int pos = ld_cg_i(C.pos);
+    consumer_sync();
+    for (int b = threadIdx.x; b < C.batch; b += CONSUMERS) {
         const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(C.argmax_keys + b);
         long long choice = static_cast<long long>(0xffffffffu - static_cast<uint32_t>(key & 0xffffffffull));
         C.argmax_keys[b] = 0ull;
@@ -495,55 +607,72 @@ __device__ __forceinline__ void pick_tokens(const StepCommon& C) {
         C.tokens[b] = choice;
         if (C.history != nullptr && step < C.hist_ld) C.history[static_cast<long long>(b) * C.hist_ld + step] = choice;
     }
-    __syncthreads();
+    consumer_sync();
     if (threadIdx.x == 0) {
         *C.step = step + 1;
-        *C.pos = ld_cg_i(C.pos) + 1;
+        *C.pos = pos + 1;
     }
 }
 
 }  // namespace
 
-template <int CPS, int SU>
-__global__ void __launch_bounds__(STEP_THREADS, CPS)
+__global__ void __maxnreg__(112)                         // 2 CTAs x 288 threads x 112 registers = 63 K
 decode_step_kernel(const StepPlan* __restrict__ plan) {
+    extern __shared__ __align__(128) unsigned char ring_mem[];
     __shared__ StepSmem sm;
-    const StepCommon& C = plan->c;
+    static_assert(sizeof(StepCommon) % 4 == 0 && sizeof(Phase) % 4 == 0, "plan structs are copied as 32-bit words");
+    stage_words(&sm.c, &plan->c, sizeof(StepCommon), threadIdx.x, STEP_THREADS);
+    stage_words(&sm.ph[0], &plan->ph[0], sizeof(Phase), threadIdx.x, STEP_THREADS);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { mbar_init(sm.full + s, 1); mbar_init(sm.empty + s, CONSUMER_WARPS); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const StepCommon& C = sm.c;
+    Ring r;
+    r.base = smem_u32(ring_mem); r.full = sm.full; r.empty = sm.empty; r.i = 0;
+    if (threadIdx.x >= CONSUMERS) {                          // producer warp: runs ahead through the whole step
+        producer(plan, C, r);
+        return;
+    }
     const int n_phases = C.n_phases;
     unsigned long long* bar = C.barrier;
     const unsigned long long epoch = ld_acquire_u64(bar + 1);
-    const unsigned long long per_launch = static_cast<unsigned long long>(n_phases - 1) * gridDim.x;
-    unsigned long long target = epoch * per_launch;
+    unsigned long long target = epoch * static_cast<unsigned long long>(n_phases - 1) * gridDim.x;
+    const int n_keys = min(ld_cg_i(C.pos) + 1, C.t_max);
 
-    uint4 wa[SU], wb[SU];
-    bool pre = false;
     for (int ph = 0; ph < n_phases; ++ph) {
-        const Phase& P = plan->ph[ph];
+        const Phase& P = sm.ph[ph & 1];
         const int type = P.type, items = P.items;
+        long long* dbg = nullptr;
+#ifdef KX_STEP_FINE_TRACE
+        if (C.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && C.trace[2 * n_phases] == ph) dbg = C.trace + 2 * n_phases + 1;
+#endif
+        stamp(dbg, 11);
         if (type == PH_LINEAR) {
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                linear_item(P, C, item, pre, wa, wb, sm);
-                pre = false;
+            // (one shared instantiation for both item kinds was measured too, to shrink the 56 KB kernel towards the 32 KB
+            // L1.5 instruction cache: no gain, the one-tile phases just ran the longer code)
+            if (P.nt == 2) {
+                for (int item = blockIdx.x; item < items; item += gridDim.x) linear_item<2>(P, C, item, r, sm, dbg);
+            } else {
+                for (int item = blockIdx.x; item < items; item += gridDim.x) linear_item<1>(P, C, item, r, sm, dbg);
             }
         } else if (type == PH_ATTN) {
-            for (int item = blockIdx.x; item < items; item += gridDim.x) attn_item(P, C, item, sm);
+            for (int item = blockIdx.x; item < items; item += gridDim.x) attn_item(P, C, item, n_keys, r, sm);
         } else if (type == PH_EMBED) {
             if (static_cast<int>(blockIdx.x) < C.batch) embed_row(C, blockIdx.x);
         } else {
             if (blockIdx.x == 0) pick_tokens(C);
         }
-        pre = false;
-        if (C.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) C.trace[2 * ph] = global_ns();
+        if (C.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) C.trace[2 * ph] = static_cast<long long>(globaltimer_ns());
         if (ph + 1 < n_phases) {
-            const Phase& Nx = plan->ph[ph + 1];
-            if (Nx.type == PH_LINEAR && static_cast<int>(blockIdx.x) < Nx.items) {
-                const LinItem it = lin_item(Nx, blockIdx.x);  // weights are immutable: stream them in while the barrier drains
-                lin_load_w(it, it.s_begin, wa, wb);
-                pre = true;
-            }
+            // the next phase's descriptor travels while the barrier drains (its buffer was last read in phase ph - 1)
+            stage_words(&sm.ph[(ph + 1) & 1], &plan->ph[ph + 1], sizeof(Phase), threadIdx.x, CONSUMERS);
             target += gridDim.x;
-            grid_barrier(bar, target, C.err_flag);
-            if (C.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) C.trace[2 * ph + 1] = global_ns();
+            grid_barrier(bar, target, C.err_flag, dbg);
+            stamp(dbg, 10);
+            if (C.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) C.trace[2 * ph + 1] = static_cast<long long>(globaltimer_ns());
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -554,31 +683,18 @@ decode_step_kernel(const StepPlan* __restrict__ plan) {
 
 namespace {
 
-int step_variant() {
-    static const int v = [] {
-        const char* e = getenv("KX_DECODE_STEP_VARIANT");
-        return (e != nullptr && e[0] == '1') ? 1 : 0;
-    }();
-    return v;
-}
+constexpr size_t STEP_DYN_SMEM = static_cast<size_t>(NS) * STAGE_BYTES;
 
 int step_grid(int sms) {
     static int per_sm = -1;
     if (per_sm < 0) {
         int n = 0;
-        const cudaError_t e = step_variant() == 1
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_step_kernel<2, 8>, STEP_THREADS, 0)
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_step_kernel<3, 4>, STEP_THREADS, 0);
-        if (e != cudaSuccess) n = 0;
-        per_sm = std::min(n, step_variant() == 1 ? 2 : 3);
+        cudaError_t e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(STEP_DYN_SMEM));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_step_kernel, STEP_THREADS, STEP_DYN_SMEM);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+        per_sm = std::min(n, STEP_CTAS_PER_SM);
     }
     return per_sm * sms;
-}
-
-int pick_ksplit(int tiles, int steps, int grid) {
-    int ks = 1;
-    while (ks < 8 && tiles * ks * 2 <= grid && steps % (ks * 2) == 0 && steps / (ks * 2) >= 8) ks *= 2;
-    return ks;
 }
 
 }  // namespace
@@ -655,8 +771,9 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
         P.w = reinterpret_cast<const __nv_bfloat16*>(w); P.ldw = K; P.N = N; P.K = K;
         P.ln_c = c; P.bias = d; P.mode = mode; P.act = act;
         const int tiles = (N + 15) / 16;
-        P.ksplit = allow_split ? pick_ksplit(tiles, K >> 5, grid) : 1;
-        P.items = tiles * P.ksplit;
+        (void)allow_split;
+        P.nt = tiles > grid ? 2 : 1;                        // more tiles than CTAs: pair them so the phase stays one pass
+        P.items = (tiles + P.nt - 1) / P.nt;
         return P;
     };
     plan->ph[k].type = PH_EMBED; plan->ph[k].items = g->batch; ++k;
@@ -665,7 +782,7 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
         q.q_out = reinterpret_cast<__nv_bfloat16*>(g->q);
         q.k_cache = reinterpret_cast<__nv_bfloat16*>(g->k_cache[l]); q.v_cache = reinterpret_cast<__nv_bfloat16*>(g->v_cache[l]);
         Phase& at = plan->ph[k++];
-        at.type = PH_ATTN; at.items = g->batch * g->heads * chunks;
+        at.type = PH_ATTN; at.items = g->batch * g->heads;
         at.q_out = reinterpret_cast<__nv_bfloat16*>(g->q);
         at.k_cache = reinterpret_cast<__nv_bfloat16*>(g->k_cache[l]); at.v_cache = reinterpret_cast<__nv_bfloat16*>(g->v_cache[l]);
         at.out = g->att; at.ld_out = D;
@@ -678,7 +795,7 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
     hd.out = g->logits; hd.ld_out = g->ld_logits; hd.out_f32 = 1; hd.argmax_keys = g->argmax_keys;
     plan->ph[k].type = PH_PICK; plan->ph[k].items = 1; ++k;
     for (int i = 0; i < k; ++i)
-        if (plan->ph[i].type == PH_LINEAR && ((plan->ph[i].K & 31) || (plan->ph[i].ksplit > 1 && plan->ph[i].items > SPLITK_MAX_ITEMS))) {
+        if (plan->ph[i].type == PH_LINEAR && (plan->ph[i].K & 31)) {
             set_error("kx_decode_plan_build: unsupported Linear shape (K %d)", plan->ph[i].K);
             return KX_ERR_ARG;
         }
@@ -696,14 +813,13 @@ extern "C" int kx_decode_step(const void* device_plan, cudaStream_t stream) {
     const int grid = step_grid(sms);
     if (grid <= 0) { set_error("kx_decode_step: decode_step_kernel does not fit on an SM"); return KX_ERR_LAUNCH; }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(STEP_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(STEP_THREADS); cfg.dynamicSmemBytes = STEP_DYN_SMEM; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;              // co-residency of the whole grid is what the barrier relies on
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     const StepPlan* plan = reinterpret_cast<const StepPlan*>(device_plan);
-    const cudaError_t e = step_variant() == 1 ? cudaLaunchKernelEx(&cfg, decode_step_kernel<2, 8>, plan)
-                                              : cudaLaunchKernelEx(&cfg, decode_step_kernel<3, 4>, plan);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, decode_step_kernel, plan);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("kx_decode_step launch failed: %s", cudaGetErrorString(e));

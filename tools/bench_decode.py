@@ -48,7 +48,9 @@ def run(model, batch, prompt, new, layers_note="", one_kernel=True):
     trace = None
     if one_kernel:
         n_ph = 1 + 5 * cfg.layers + 2
-        trace = torch.zeros(2 * n_ph, dtype=torch.int64, device=dev) if os.environ.get("KX_STEP_TRACE") else None
+        trace = torch.zeros(2 * n_ph + 1 + 16, dtype=torch.int64, device=dev) if os.environ.get("KX_STEP_TRACE") else None
+        if trace is not None:
+            trace[2 * n_ph] = int(os.environ.get("KX_STEP_TRACE_PHASE", "-1"))
         plan = dec.build_step_plan(state, history=history, trace=trace)
 
         class _One:
@@ -75,7 +77,14 @@ def run(model, batch, prompt, new, layers_note="", one_kernel=True):
     torch.cuda.synchronize()
     ms_step = e1.elapsed_time(e2) / steps
     if trace is not None:                                           # per-phase timeline of CTA 0 in the LAST step
-        t = trace.cpu().view(-1, 2).tolist()
+        n_ph = 1 + 5 * cfg.layers + 2
+        fine = trace[2 * n_ph + 1:].cpu().tolist()
+        if fine[0]:
+            lab = ["enter", "a issued", "ring 0 full", "k loop done", "sync1", "sync2", "epilogue done", "-", "barrier enter",
+                   "arrived", "barrier left", "phase start", "is linear", "is nt2"]
+            print("fine trace (us since item entry): " + ", ".join(f"{lab[i]}={(fine[i] - fine[0]) / 1e3:.2f}" for i in range(14) if fine[i]),
+                  file=sys.stderr)
+        t = trace[:2 * n_ph].cpu().view(-1, 2).tolist()
         names = ["embed"] + ["qkv", "attn", "out", "fc1", "fc2"] * cfg.layers + ["head", "pick"]
         agg = {}
         prev_leave = None
@@ -86,6 +95,10 @@ def run(model, batch, prompt, new, layers_note="", one_kernel=True):
                 if leave:
                     a[2] += (leave - done) / 1e3
             prev_leave = leave if leave else None
+        if os.environ.get("KX_STEP_TRACE_RAW"):
+            t0 = t[0][0]
+            for i in range(56, 72):
+                print(f"raw {i:3d} {names[i]:5s} done={(t[i][0] - t0) / 1e3:9.2f} leave={(t[i][1] - t0) / 1e3:9.2f}", file=sys.stderr)
         for k, (n, work, wait) in agg.items():
             print(f"trace {k:6s} x{n:3d}: CTA0 work {work / n:7.2f} us, barrier wait {wait / n:7.2f} us", file=sys.stderr)
     ms_prompt = e0.elapsed_time(ep)
