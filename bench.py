@@ -20,6 +20,9 @@ Rank 0 prints ONE JSON line.  Keys beyond the base contract:
   cpu_baseline  the oracle (CPU restatement of the reference path) timed on this box's host cores, N=1 only
   e2e           same metric through Kosmos.forward with pinned HOST buffers: per step H2D of tokens+images
                 and D2H of the full logits, all inside the timed region
+  train_step    BASELINE.json configs[3]: the data-parallel training step on the same shapes (short run)
+  decode        SURVEY §8(f)2: greedy decoding against the KV cache (B=8, 512-row prompt), generated tokens/s and
+                its own HBM roofline (weights + cache bytes per step vs the measured copy bandwidth); N=1 only
 ``--impl reference`` times the oracle on the host cores (the reference's own dependencies are not
 installable offline: SURVEY.md §8(c)); it is the only other place bench.py executes oracle/.
 """
@@ -383,6 +386,14 @@ def run_gpu(args):
         except Exception as e:                                  # the forward line must still be printed
             line["train_step"] = {"error": f"{type(e).__name__}: {e}"}
         x = None
+    if args.decode_leg and args.workload == "c3" and world == 1:
+        # SURVEY §8(f)2 beside the headline: greedy decoding against a KV cache (HBM-bound; its own roofline)
+        try:
+            model._ws.clear(); model._graphs = {}; model.decoder._ws.clear()
+            torch.cuda.empty_cache()
+            line["decode"] = decode_measure(torch, model)
+        except Exception as e:
+            line["decode"] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and rank == 0 and not args.no_cpu:
         del x
         r = cpu_reference(1, 0, wl=wl)
@@ -391,6 +402,26 @@ def run_gpu(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     kdist.barrier()
+
+
+def decode_measure(torch, model, batch=8, prompt=512, new=96):
+    """Incremental decoding (Kosmos.generate's step): B=8 sequences, 512-token multimodal prompt, one token per sequence
+    per step from the KV cache.  Timed with CUDA events around the replays of the captured step (per-kernel path: 123
+    kernels of libkosmosx_sm100.so per step).  Roofline: HBM — algorithmic bytes of a step = every decoder weight matrix
+    once (bf16) + the K/V rows of the cache, against the measured copy bandwidth."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_decode
+    r = bench_decode.run(model, batch, prompt, new, one_kernel=False)
+    return {
+        "config": f"greedy decoding, B={batch}, prompt {r['prompt']} rows (1 image + text), {r['timed_steps']} timed one-token steps, "
+                  "KV cache bf16 head-major, CUDA-graph replay of the step",
+        "value": r["tokens_per_s"], "unit": "generated tokens/s", "ms_per_step": r["ms_per_step"],
+        "ms_prompt_pass": r["ms_prompt_pass"], "gpu_launches_per_step": r["kernels_per_step"],
+        "roofline": {"bound": "hbm", "kernel": "decode_linear_kernel + decode_attention_kernel (whole step)",
+                     "achieved": r["achieved_gbs"], "peak": r["peak_gbs"], "unit": "GB/s", "frac": r["frac"],
+                     "bytes_per_step": r["weight_bytes"] + r["kv_bytes_mean"], "traffic": None,
+                     "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)"},
+    }
 
 
 def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peaks, optimizer="adamw", detail=True):
@@ -539,6 +570,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["train"], help="c3 = configs[2] (the metric's "
                     "configuration, default); c5 = configs[4], 4 images per sequence; train = configs[3], the training step")
     ap.add_argument("--optimizer", default="adamw", choices=["adamw", "lion"])
+    ap.add_argument("--decode-leg", type=int, default=1, help="also time incremental decoding (SURVEY 8(f)2) and report it as "
+                    "'decode' inside the forward line (default on, single GPU)")
     ap.add_argument("--train-leg", type=int, default=1, help="also time a few training steps (configs[3]) and report them "
                     "as 'train_step' inside the forward line (default on)")
     args = ap.parse_args()
