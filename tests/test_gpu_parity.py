@@ -312,7 +312,7 @@ def test_tiny_incremental_decoding_vs_oracle(tiny_pair):
     _, want = ref.generate(text, images, n, forced=forced)
     ref.set_emulation(False)
     n0 = __import__("kosmosx").ops.launch_count()
-    toks, got = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True)
+    toks, got = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True, one_kernel=True)
     torch.cuda.synchronize()
     assert __import__("kosmosx").ops.launch_count() > n0
     assert torch.equal(toks.cpu(), forced) and got.shape == (B, n, oc.vocab) and torch.isfinite(got).all()
@@ -332,11 +332,11 @@ def test_tiny_incremental_decoding_vs_oracle(tiny_pair):
     print(f"per-kernel decoding vs one-kernel step: max={ep[0]:.3e}")
     assert ep[0] <= TOL_DEC_SELF and _err(got_pk, want)[0] <= TOL_EMU_TINY and torch.equal(toks_pk.cpu(), forced)
     # greedy: one-kernel step, CUDA-graph replay of the per-kernel step and eager stepping agree; deterministic
-    g0 = mine.generate(text.cuda(), images.cuda(), n)
+    g0 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=True)
     g1 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=False)
     g2 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=False, cuda_graph=False)
     g3 = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda())
-    assert torch.equal(g1, g2) and torch.equal(g3.cpu(), forced) and torch.equal(g0, mine.generate(text.cuda(), images.cuda(), n))
+    assert torch.equal(g1, g2) and torch.equal(g3.cpu(), forced) and torch.equal(g0, mine.generate(text.cuda(), images.cuda(), n, one_kernel=True))
     assert (g0 == g1).float().mean() >= 0.8            # (different summation order: a near-tie may flip)
     assert int(mine._last_decode_state.err.item()) == 0
     assert torch.equal(g1[:, 0], mine(text.cuda(), images.cuda())[:, -1].argmax(-1))
@@ -361,6 +361,36 @@ def test_tiny_incremental_decoding_vs_oracle(tiny_pair):
         mine.decoder(prefix, incremental_state={"is_first_step": False})
     with pytest.raises(ValueError):
         mine.generate(text.cuda(), images.cuda(), oc.max_positions)   # beyond the position table
+
+
+def test_generate_edge_cases(tiny512_pair):
+    """Decoding after a multi-image prompt (the cache continues the spliced sequence), a single sequence, a single new
+    token, a cache that crosses attention-chunk boundaries (128 / 256 keys), and the per-kernel and one-kernel paths on
+    each — all against the oracle's incremental restatement with forced tokens."""
+    import kosmos_oracle as ko
+    ref, mine, oc = tiny512_pair
+    cases = [  # (B, t_text, image positions, new tokens)
+        (2, 30, [2, 17], 5),          # two images: T0 = 158, crosses the 128-key chunk of kx_decode_attn
+        (1, 60, None, 9),             # T0 = 124 -> 133: the newest row opens a new 128-key chunk mid-generation
+        (3, 190, None, 6),            # T0 = 254 -> 260: crosses the 256-key chunk of the one-kernel step
+        (2, 12, None, 1),             # a single new token: the prompt pass alone
+    ]
+    for B, t_text, positions, n in cases:
+        m = 1 if positions is None else len(positions)
+        text, images = ko.make_inputs(oc, B, t_text, seed=11, n_images=None if positions is None else m)
+        forced = torch.randint(0, oc.vocab, (B, n), generator=torch.Generator().manual_seed(3))
+        ref.set_emulation(True)
+        _, want = ref.generate(text, images, n, image_positions=positions, forced=forced)
+        ref.set_emulation(False)
+        for one in (False, True):
+            toks, got = mine.generate(text.cuda(), images.cuda(), n, image_positions=positions, forced_tokens=forced.cuda(),
+                                      return_logits=True, one_kernel=one)
+            e = _err(got, want)
+            print(f"generate B={B} T0={t_text + 64 * m} n={n} one_kernel={one}: max={e[0]:.3e} rms={e[1]:.3e}")
+            assert torch.equal(toks.cpu(), forced) and e[0] <= TOL_EMU_TINY and e[1] <= RMS_EMU_TINY
+            free = mine.generate(text.cuda(), images.cuda(), n, image_positions=positions, one_kernel=one)
+            assert free.shape == (B, n) and int(free.min()) >= 0 and int(free.max()) < oc.vocab
+            assert int(mine._last_decode_state.err.item()) == 0
 
 
 def test_language_model_generate_batches(tiny_cfgs):
@@ -479,14 +509,15 @@ def test_full_size_generate_vs_forward_and_oracle(full_pair):
     print(f"full-size incremental decoding vs bf16-emulating oracle (sequence 0): max={e16[0]:.3e} rms={e16[1]:.3e}")
     assert e16[0] <= TOL_EMU_FULL
     _, got_pk = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True, one_kernel=False)
-    ep = _err(got_pk, got)
+    _, got_one = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True, one_kernel=True)
+    ep = _err(got_pk, got_one)
     print(f"full-size per-kernel decoding vs one-kernel step: max={ep[0]:.3e} rms={ep[1]:.3e}")
-    assert ep[0] <= TOL_EMU_FULL
+    assert ep[0] <= TOL_EMU_FULL and _err(got_one, full[:, t0 - 1:])[0] <= TOL_EMU_FULL
     g1 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=False)
     g2 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=False, cuda_graph=False)
     assert torch.equal(g1, g2)
-    g0 = mine.generate(text.cuda(), images.cuda(), n)
-    assert torch.equal(g0, mine.generate(text.cuda(), images.cuda(), n)), "one-kernel decoding is not deterministic"
+    g0 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=True)
+    assert torch.equal(g0, mine.generate(text.cuda(), images.cuda(), n, one_kernel=True)), "one-kernel decoding is not deterministic"
     assert int(mine._last_decode_state.err.item()) == 0
 
 
