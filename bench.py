@@ -20,6 +20,7 @@ Rank 0 prints ONE JSON line.  Keys beyond the base contract:
   cpu_baseline  the oracle (CPU restatement of the reference path) timed on this box's host cores, N=1 only
   e2e           same metric through Kosmos.forward with pinned HOST buffers: per step H2D of tokens+images
                 and D2H of the full logits, all inside the timed region
+  gpu_eager_baseline  SURVEY §8(d): the restated reference path in stock eager PyTorch bf16 on the same GPU and batch
   train_step    BASELINE.json configs[3]: the data-parallel training step on the same shapes (short run)
   decode        SURVEY §8(f)2: greedy decoding against the KV cache (B=8, 512-row prompt), generated tokens/s and
                 its own HBM roofline (weights + cache bytes per step vs the measured copy bandwidth); N=1 only
@@ -172,6 +173,39 @@ def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0, wl=None):
     return dict(value=SEQ / (ms / 1e3), ms_per_step=ms, steps_done=len(times), cores=cores,
                 sample=f"1 sequence (T={SEQ}: {wl['t_text']} text tokens + {wl['images']} image(s)) per step, fp32 eager PyTorch oracle, "
                        f"{cores} threads, {len(times)} timed step(s)")
+
+
+def gpu_eager_reference(torch, wl, steps=3):
+    """the restated reference path (oracle) in stock eager PyTorch, bf16, on the SAME B200 and the same
+    batch — what the reference's own nn.Module stack dispatches to (cuBLAS GEMMs, eager softmax / LayerNorm / xPos
+    kernels, the per-layer CPU->GPU mask upload).  A like-for-like GPU baseline next to the CPU one; checker code, timed
+    here only as a baseline."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kosmos_oracle as ko
+    cfg = ko.OracleConfig(max_positions=SEQ + 2, multiway=False)
+    with torch.device("cuda"):
+        ref = ko.KosmosOracle(cfg)
+    ref = ref.to(dtype=torch.bfloat16).eval()
+    B = wl["batch"]
+    multi = wl["images"] > 1
+    text, images = ko.make_inputs(cfg, B, wl["t_text"], seed=1, n_images=wl["images"] if multi else None)
+    text, images = text.cuda(), images.cuda().to(torch.bfloat16)
+    kw = dict(image_positions=wl["positions"]) if multi else {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        out = ref(text, images, **kw)                               # warm-up (cuBLAS heuristics, allocator)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            out = ref(text, images, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+    assert out.shape == (B, SEQ, VOCAB)
+    ms = e0.elapsed_time(e1) / steps
+    del ref, out
+    torch.cuda.empty_cache()
+    return {"value": B * SEQ / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "kind": "port",
+            "what": f"oracle (restated reference path) in eager PyTorch bf16 on the same GPU, B={B}, seq={SEQ}"}
 
 
 def run_reference(args, rank):
@@ -394,6 +428,13 @@ def run_gpu(args):
             line["decode"] = decode_measure(torch, model)
         except Exception as e:
             line["decode"] = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1 and rank == 0 and not args.no_cpu:
+        try:
+            model._ws.clear(); model._graphs = {}; model.decoder._ws.clear()
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_reference(torch, wl)
+        except Exception as e:
+            line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and rank == 0 and not args.no_cpu:
         del x
         r = cpu_reference(1, 0, wl=wl)

@@ -158,6 +158,28 @@ def test_state_dict_layout_matches_oracle_and_appendix_b(tiny_cfgs):
     assert torch.equal(mine.state_dict()["decoder.layers.0.ffn.A.fc1.weight"], b["decoder.layers.0.ffn.A.fc1.weight"])
 
 
+def test_hf_clip_checkpoint_loads_into_the_vision_tower(tiny_cfgs):
+    """the reference takes its vision weights from ``CLIPModel.from_pretrained(...).vision_model``
+    (model.py:154-156).  Offline there is no checkpoint, but the installed HF class defines the key layout: its
+    state_dict must load into ``Kosmos().clip_model`` key for key (a non-persistent ``position_ids`` buffer aside)."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from kosmosx import Kosmos
+    oc, kc = tiny_cfgs
+    hf = CLIPVisionModel(CLIPVisionConfig(hidden_size=oc.vit_dim, intermediate_size=oc.vit_mlp,
+                                          num_hidden_layers=oc.vit_layers, num_attention_heads=oc.vit_heads,
+                                          patch_size=oc.patch, image_size=oc.image, hidden_act="gelu")).vision_model
+    mine = Kosmos(config=kc)
+    sd = hf.state_dict()
+    res = mine.clip_model.load_state_dict(sd, strict=False)
+    assert not res.missing_keys, res.missing_keys
+    assert set(res.unexpected_keys) <= {"embeddings.position_ids"}, res.unexpected_keys
+    own = mine.clip_model.state_dict()
+    assert all(torch.equal(own[k], v) for k, v in sd.items() if k in own)
+    # and the whole-model layout: clip_model.* keys of Kosmos.state_dict() are exactly HF's
+    full = {k[len("clip_model."):] for k in mine.state_dict() if k.startswith("clip_model.")}
+    assert full == set(own)
+
+
 def test_reference_error_behaviour(tiny_cfgs):
     from kosmosx import Kosmos, KosmosLanguage, KosmosTokenizer
     _, kc = tiny_cfgs
