@@ -5,7 +5,7 @@ This file restates, in plain eager PyTorch (fp32), the algorithm that
 (/root/reference/kosmosx/model.py:208-253).  It exists so that the CUDA path in
 ``kosmos-x_b200/`` can be checked against the reference semantics; it is never
 imported by the product package.  Only ``tests/``, ``__graft_entry__.smoke()``
-and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.
+and ``bench.py``'s baseline legs (``cpu_baseline``, ``gpu_eager_baseline``, ``--impl reference``) may import it.
 
 PARITY UNPINNED: the reference's hot-path arithmetic lives in
 three third-party packages that are NOT vendored in /root/reference and are NOT
