@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 12   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 13   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -370,8 +370,8 @@ int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, c
  *                         SYNCHRONISES `stream` — the only call of this library that does.
  *   kx_decode_step        one launch = one new token per sequence; tokens[b] is consumed, the next choice is written
  *                         back to tokens[b] and history[b, *step]; *pos and *step advance.
- * Per-layer arrays are HOST arrays of `layers` DEVICE pointers.  scratch: kx_decode_step_scratch_floats() floats;
- * counters: kx_decode_step_counters() ints, zeroed once; barrier: 32 x uint64, zeroed once and then owned by the kernel;
+ * Per-layer arrays are HOST arrays of `layers` DEVICE pointers.  barrier: 32 x uint64, zeroed once and then owned by
+ * the kernel;
  * err_flag bit 2 = a barrier timed out (logic error, results invalid). */
 typedef struct kx_decode_step_args {
     int batch, layers, d_model, ffn, heads, vocab, t_max, pos_rows;
@@ -388,15 +388,13 @@ typedef struct kx_decode_step_args {
     float* logits; long long ld_logits;
     unsigned long long* argmax_keys; int* pos; int* step; int* err_flag;
     const long long* forced; long long* history; int history_ld;                         /* forced / history may be NULL */
-    float* scratch; int* counters; unsigned long long* barrier;
+    unsigned long long* barrier;
     long long* trace;   /* optional profiling aid: int64 [2 * phases + 17]; CTA 0 stamps %globaltimer when its own work of a
                          * phase is done and when it leaves the barrier behind it (phases = 1 + 5*layers + 2); entry
                          * [2*phases] selects one Linear phase (-1 = none) whose item gets 16 finer stamps after it */
 } kx_decode_step_args;
 
 size_t kx_decode_plan_bytes(int layers);
-size_t kx_decode_step_scratch_floats(int batch, int heads, int t_max);
-size_t kx_decode_step_counters(int batch, int heads);
 int kx_decode_plan_build(const kx_decode_step_args* args, void* device_plan, kx_stream_t stream);
 int kx_decode_step(const void* device_plan, kx_stream_t stream);
 

@@ -5,9 +5,10 @@
 // are latency-bound streams (ncu: long-scoreboard stalls, 24 warps/SM) separated by launch / drain gaps.  Here the whole
 // step — embedding, 24 x (q|k|v, attention, out_proj, fc1, fc2), LM head, greedy choice — is one grid of 2 CTAs per SM:
 //
-//   * warp 8 of every CTA is a PRODUCER: one thread walks the CTA's whole work list of the step and moves it through a
-//     3-stage, 33 KB-per-stage shared-memory ring with bulk copies (cp.async.bulk, mbarrier complete_tx): 16 weight
-//     rows x 1024 k per stage for a Linear item, 256 keys of K or of V for an attention item.  Weights and the history
+//   * warp 8 of every CTA is a PRODUCER: it walks the CTA's whole work list of the step and moves it through a
+//     3-stage, 33 KB-per-stage shared-memory ring with bulk copies (cp.async.bulk, mbarrier complete_tx; lane 0 arms the
+//     barrier, 16 lanes issue the row copies at once): 16 weight rows x 1024 k per stage for a Linear item, 256 keys
+//     of K or of V for an attention item.  Weights and the history
 //     rows of the cache are immutable during the launch, so the producer never waits for a phase boundary: while the
 //     consumers of a CTA sit in a grid barrier its ring is already filling with the NEXT phase's bytes (200 KB per SM
 //     in flight, several times what Little's law asks for at 6.5 TB/s).
@@ -23,6 +24,9 @@
 //     folded with an online softmax inside the CTA, so there is no cross-CTA merge.
 //
 // Activations written in one phase are read in the next by other SMs with ld.global.cg (L2), never through L1.
+//
+// Status (profiles/r1_decode_bench.md): bit-identical to the per-kernel path on the test model, 1.22 ms per step at B = 8
+// against 1.03 ms for the CUDA graph of separate kernels, so generate() uses it only on request (one_kernel=True).
 #include "kx_internal.h"
 #include "ptx.cuh"
 
@@ -42,8 +46,6 @@ constexpr int CHUNK_K = 1024;                   // k per weight stage
 constexpr int W_PITCH = CHUNK_K * 2 + 64;       // bytes per staged weight row (+64: the quad-row LDS.128 pattern hits all banks)
 constexpr int STAGE_BYTES = 16 * W_PITCH;       // 33792 >= 256 keys x 128 bytes
 constexpr int ATTN_CHUNK = 256;                 // keys per attention item (8 warps x 32)
-constexpr int PART_STRIDE = 16 * 8 + 8 * 2;     // split-K partial: 16x8 sums + 8 (sum, sumsq) pairs
-constexpr int SPLITK_MAX_ITEMS = 2048;          // split phases have items <= grid (pick_ksplit)
 static_assert(STAGE_BYTES >= ATTN_CHUNK * 128 && STAGE_BYTES % 128 == 0, "ring stage geometry");
 
 struct Phase {
@@ -59,7 +61,7 @@ struct Phase {
 };
 
 struct StepCommon {
-    int batch, d_model, heads, t_max, vocab, pos_rows, hist_ld, n_phases, attn_chunks;
+    int batch, d_model, heads, t_max, vocab, pos_rows, hist_ld, n_phases;
     float eps, scale_log2;
     const long long* forced; long long* tokens; long long* history;
     const float* embed_table; const float* pos_table;
@@ -67,8 +69,6 @@ struct StepCommon {
     float* x; __nv_bfloat16* xb;
     int* pos; int* step; int* err_flag;
     unsigned long long* argmax_keys;
-    float* attn_part; int* attn_counters;
-    float* splitk_part; int* splitk_counters;
     unsigned long long* barrier;            // [0] arrivals (monotonic), [1] launches completed, [16] release flag
     long long* trace;                       // optional: CTA 0 stamps globaltimer (work done, barrier left) per phase
 };
@@ -84,7 +84,6 @@ struct StepSmem {
     float fin[2][16][8];
     float att_o[8][64];
     float att_ml[8][2];
-    int flag;
     uint64_t full[NS], empty[NS];
     StepCommon c;                           // the plan, staged: field reads are LDS, not dependent global loads
     Phase ph[2];                            // current / next phase (the next one is fetched before the barrier)
@@ -318,14 +317,15 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
             av[u] = (aok && s_lo + u < s_hi) ? ld_cg4(ap + ((kc >> 3) + (s_lo + u) * 4)) : make_uint4(0, 0, 0, 0);
     };
     uint4 av[4];
-    for (int kc = -CHUNK_K; kc < p.K; kc += CHUNK_K) {      // the first pass only requests chunk 0's activations
+    load_a(0, av);
+    stamp(dbg, 1);
+    for (int kc = 0; kc < p.K; kc += CHUNK_K) {
         const bool more = kc + CHUNK_K < p.K;
-        const int steps = kc < 0 ? 0 : (min(CHUNK_K, p.K - kc) >> 5);
+        const int steps = min(CHUNK_K, p.K - kc) >> 5;
         const int spw = (steps + CONSUMER_WARPS - 1) / CONSUMER_WARPS;        // <= 4
         const int s_lo = warp * spw, s_hi = min(steps, s_lo + spw);
 #pragma unroll
         for (int tt = 0; tt < NT; ++tt) {
-            if (kc < 0) break;
             if (!tile_ok[tt]) continue;
             ring_wait(r.full + r.slot(), r.parity());
             if (kc == 0 && tt == 0) stamp(dbg, 2);
@@ -710,17 +710,6 @@ extern "C" size_t kx_decode_plan_bytes(int layers) {
     return sizeof(StepPlan) + sizeof(Phase) * static_cast<size_t>(step_phase_count(layers));
 }
 
-extern "C" size_t kx_decode_step_scratch_floats(int batch, int heads, int t_max) {
-    if (batch <= 0 || heads <= 0 || t_max <= 0) return 0;
-    const size_t chunks = (static_cast<size_t>(t_max) + ATTN_CHUNK - 1) / ATTN_CHUNK;
-    return static_cast<size_t>(batch) * heads * chunks * 66 + static_cast<size_t>(SPLITK_MAX_ITEMS) * PART_STRIDE;
-}
-
-extern "C" size_t kx_decode_step_counters(int batch, int heads) {
-    if (batch <= 0 || heads <= 0) return 0;
-    return static_cast<size_t>(batch) * heads + SPLITK_MAX_ITEMS;
-}
-
 extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_plan, cudaStream_t stream) {
     if (!g || !device_plan) { set_error("kx_decode_plan_build: null argument"); return KX_ERR_ARG; }
     if (g->batch <= 0 || g->batch > 8 || g->layers < 0 || g->d_model <= 0 || (g->d_model & 63) || g->ffn <= 0 || (g->ffn & 31) ||
@@ -732,7 +721,7 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
     const void* need[] = {g->w_qkv, g->c_qkv, g->d_qkv, g->w_o, g->c_o, g->d_o, g->w_fc1, g->c_fc1, g->d_fc1, g->w_fc2, g->c_fc2,
                           g->d_fc2, g->k_cache, g->v_cache, g->w_out, g->c_out, g->embed_table, g->pos_table, g->xq_cos, g->xq_sin,
                           g->xk_cos, g->xk_sin, g->tokens, g->x, g->xb, g->q, g->att, g->mid, g->logits, g->argmax_keys, g->pos,
-                          g->step, g->scratch, g->counters, g->barrier};
+                          g->step, g->barrier};
     for (const void* q : need)
         if (q == nullptr) { set_error("kx_decode_plan_build: a required pointer is NULL"); return KX_ERR_ARG; }
     if ((g->forced || g->history) && g->history_ld <= 0) { set_error("kx_decode_plan_build: history_ld"); return KX_ERR_ARG; }
@@ -746,19 +735,14 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
     std::vector<unsigned char> host(bytes, 0);
     StepPlan* plan = reinterpret_cast<StepPlan*>(host.data());
     StepCommon& C = plan->c;
-    const int chunks = (g->t_max + ATTN_CHUNK - 1) / ATTN_CHUNK;
     C.batch = g->batch; C.d_model = D; C.heads = g->heads; C.t_max = g->t_max; C.vocab = g->vocab; C.pos_rows = g->pos_rows;
-    C.hist_ld = g->history_ld; C.n_phases = n_ph; C.attn_chunks = chunks;
+    C.hist_ld = g->history_ld; C.n_phases = n_ph;
     C.eps = g->eps; C.scale_log2 = g->scale * 1.4426950408889634f;
     C.forced = g->forced; C.tokens = g->tokens; C.history = g->history;
     C.embed_table = g->embed_table; C.pos_table = g->pos_table;
     C.xq_cos = g->xq_cos; C.xq_sin = g->xq_sin; C.xk_cos = g->xk_cos; C.xk_sin = g->xk_sin;
     C.x = g->x; C.xb = reinterpret_cast<__nv_bfloat16*>(g->xb);
     C.pos = g->pos; C.step = g->step; C.err_flag = g->err_flag; C.argmax_keys = g->argmax_keys;
-    C.attn_part = g->scratch;
-    C.splitk_part = g->scratch + static_cast<size_t>(g->batch) * g->heads * chunks * 66;
-    C.attn_counters = g->counters;
-    C.splitk_counters = g->counters + g->batch * g->heads;
     C.barrier = g->barrier;
     C.trace = g->trace;
 

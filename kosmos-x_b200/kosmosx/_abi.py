@@ -78,7 +78,7 @@ class DecodeStepArgs(C.Structure):
         ("logits", _f32p), ("ld_logits", _ll),
         ("argmax_keys", _vp), ("pos", _vp), ("step", _vp), ("err_flag", _vp),
         ("forced", _vp), ("history", _vp), ("history_ld", _i),
-        ("scratch", _f32p), ("counters", _vp), ("barrier", _vp), ("trace", _vp),
+        ("barrier", _vp), ("trace", _vp),
     ]
 
 
@@ -130,8 +130,6 @@ SIGNATURES = {
     "kx_decode_embed": (_i, [_vp, _i, _f32p, _i, _f32p, _i, _vp, _i, _f32p, _vp, _vp, _vp]),
     "kx_argmax_advance": (_i, [_f32p, _ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "kx_decode_plan_bytes": (C.c_size_t, [_i]),
-    "kx_decode_step_scratch_floats": (C.c_size_t, [_i, _i, _i]),
-    "kx_decode_step_counters": (C.c_size_t, [_i, _i]),
     "kx_decode_plan_build": (_i, [C.POINTER(DecodeStepArgs), _vp, _vp]),
     "kx_decode_step": (_i, [_vp, _vp]),
 }

@@ -490,14 +490,13 @@ class Decoder(nn.Module):
     def build_step_plan(self, state: DecodeState, history=None, forced=None, trace=None):
         """Flatten one generation's arguments for the persistent one-kernel step (kx_decode_step; batch <= 8)."""
         cfg, p = self.cfg, self._pack()
-        plan, scratch, counters, barrier = ops.decode_step_buffers(state.batch, cfg.heads, state.t_max, cfg.layers, state.x.device)
-        state.step_bufs = (scratch, counters, barrier)
+        plan, barrier = ops.decode_step_buffers(cfg.layers, state.x.device)
+        state.step_bufs = (barrier,)
         state.plan = ops.decode_plan_build(
             plan, layers=p["layers"], out=p["out"], embed_table=p["embed"], pos_table=p["pos"], tabs=state.tabs,
             k_cache=[state.k[i] for i in range(cfg.layers)], v_cache=[state.v[i] for i in range(cfg.layers)],
             tokens=state.tok, x=state.x, xb=state.xb, q=state.q, att=state.att, mid=state.mid, logits=state.logits,
-            keys=state.keys, pos=state.pos, step=state.step, err_flag=state.err, scratch=scratch, counters=counters,
-            barrier=barrier, heads=cfg.heads, ffn=cfg.ffn, t_max=state.t_max, eps=cfg.eps,
+            keys=state.keys, pos=state.pos, step=state.step, err_flag=state.err, barrier=barrier, heads=cfg.heads, ffn=cfg.ffn, t_max=state.t_max, eps=cfg.eps,
             scale=(cfg.dim // cfg.heads) ** -0.5, forced=forced, history=history, trace=trace)
         return state.plan
 

@@ -494,17 +494,14 @@ def _ptr_array(tensors):
     return (_abi.C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
-def decode_step_buffers(batch, heads, t_max, layers, device):
-    """(plan bytes, scratch fp32, counters int32 (zeroed), barrier 32 x int64 (zeroed)) for kx_decode_plan_build."""
+def decode_step_buffers(layers, device):
+    """(plan bytes, barrier 32 x int64 (zeroed)) for kx_decode_plan_build."""
     return (torch.empty(int(lib.kx_decode_plan_bytes(layers)), dtype=torch.uint8, device=device),
-            torch.empty(int(lib.kx_decode_step_scratch_floats(batch, heads, t_max)), dtype=torch.float32, device=device),
-            torch.zeros(int(lib.kx_decode_step_counters(batch, heads)), dtype=torch.int32, device=device),
             torch.zeros(32, dtype=torch.int64, device=device))
 
 
 def decode_plan_build(plan, *, layers, out, embed_table, pos_table, tabs, k_cache, v_cache, tokens, x, xb, q, att, mid, logits,
-                      keys, pos, step, err_flag, scratch, counters, barrier, heads, ffn, t_max, eps, scale, forced=None,
-                      history=None, trace=None):
+                      keys, pos, step, err_flag, barrier, heads, ffn, t_max, eps, scale, forced=None, history=None, trace=None):
     """layers: list of dicts with (w, c, d) triples under "qkv", "o", "fc1", "fc2"; out: the (w, c, d) of the LM head."""
     g = _abi.DecodeStepArgs()
     B, D = x.shape
@@ -526,7 +523,7 @@ def decode_plan_build(plan, *, layers, out, embed_table, pos_table, tabs, k_cach
     g.argmax_keys, g.pos, g.step, g.err_flag = keys.data_ptr(), pos.data_ptr(), step.data_ptr(), _ptr(err_flag)
     g.forced, g.history = _ptr(forced), _ptr(history)
     g.history_ld = history.shape[1] if history is not None else (forced.shape[1] if forced is not None else 0)
-    g.scratch, g.counters, g.barrier = scratch.data_ptr(), counters.data_ptr(), barrier.data_ptr()
+    g.barrier = barrier.data_ptr()
     g.trace = _ptr(trace)
     check(lib.kx_decode_plan_build(g, plan.data_ptr(), _stream()), "kx_decode_plan_build")
     return plan
