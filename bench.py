@@ -460,7 +460,7 @@ def decode_measure(torch, model, batch=8, prompt=512, new=96):
         "ms_prompt_pass": r["ms_prompt_pass"], "gpu_launches_per_step": r["kernels_per_step"],
         "roofline": {"bound": "hbm", "kernel": "decode_linear_kernel + decode_attention_kernel (whole step)",
                      "achieved": r["achieved_gbs"], "peak": r["peak_gbs"], "unit": "GB/s", "frac": r["frac"],
-                     "bytes_per_step": r["weight_bytes"] + r["kv_bytes_mean"], "traffic": None,
+                     "bytes_per_step": r["weight_bytes"] + r["kv_bytes_mean"], "traffic": _ncu_traffic("decode_step"),
                      "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)"},
     }
 
