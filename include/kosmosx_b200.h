@@ -395,6 +395,7 @@ typedef struct kx_decode_step_args {
 } kx_decode_step_args;
 
 size_t kx_decode_plan_bytes(int layers);
+int kx_decode_step_ctas(void);   /* grid size of the cooperative kernel on the current device (CTAs per SM x SMs), < 0 on error */
 int kx_decode_plan_build(const kx_decode_step_args* args, void* device_plan, kx_stream_t stream);
 int kx_decode_step(const void* device_plan, kx_stream_t stream);
 

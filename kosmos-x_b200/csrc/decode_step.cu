@@ -40,8 +40,8 @@ enum { PH_EMBED = 0, PH_LINEAR = 1, PH_ATTN = 2, PH_PICK = 3 };
 constexpr int CONSUMER_WARPS = 8;
 constexpr int CONSUMERS = CONSUMER_WARPS * 32;
 constexpr int STEP_THREADS = CONSUMERS + 32;
-constexpr int STEP_CTAS_PER_SM = 2;
-constexpr int NS = 3;                           // ring stages
+constexpr int STEP_CTAS_PER_SM = 1;
+constexpr int NS = 6;                           // ring stages
 constexpr int CHUNK_K = 1024;                   // k per weight stage
 constexpr int W_PITCH = CHUNK_K * 2 + 64;       // bytes per staged weight row (+64: the quad-row LDS.128 pattern hits all banks)
 constexpr int STAGE_BYTES = 16 * W_PITCH;       // 33792 >= 256 keys x 128 bytes
@@ -79,9 +79,9 @@ struct StepPlan {
 };
 
 struct StepSmem {
-    float red[2][8][16][8];
+    float red[4][8][16][8];
     float st[8][8][2];
-    float fin[2][16][8];
+    float fin[4][16][8];
     float att_o[8][64];
     float att_ml[8][2];
     uint64_t full[NS], empty[NS];
@@ -284,25 +284,29 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
 
     // Everything the epilogue of this thread's (tile, batch row, feature) needs is requested NOW, so that those DRAM /
     // L2 round trips overlap the k loop instead of sitting on the phase's critical path.
-    const int e_tt = tid >> 7, e_idx = tid & 127;
+    constexpr int ROUNDS = (NT + 1) / 2;                    // 256 threads finish two tiles per round
+    const int e_half = tid >> 7, e_idx = tid & 127;
     const int e_b = e_idx >> 4, e_r = e_idx & 15;
-    const bool e_mine = e_tt < NT && item + e_tt * p.items < tiles;
-    const int e_n = min((item + e_tt * p.items) * 16 + e_r, p.N - 1);
-    float e_lnc = 0.f, e_bias = 0.f, e_c = 1.f, e_s = 0.f, e_x = 0.f;
-    int e_pos = 0;
-    if (e_mine) {
-        if (ln) e_lnc = __ldg(p.ln_c + e_n);
-        if (p.bias != nullptr) e_bias = __ldg(p.bias + e_n);
-        if (p.mode == KX_DEC_QKV) {
-            e_pos = pos0;                                   // read once at kernel start: no dependent round trip here
-            const int which = e_n / C.d_model;
-            if (which < 2) {
-                const int j = (e_n & 63) >> 1;
-                e_c = __ldg((which == 0 ? C.xq_cos : C.xk_cos) + e_pos * 32 + j);
-                e_s = __ldg((which == 0 ? C.xq_sin : C.xk_sin) + e_pos * 32 + j);
+    float e_lnc[ROUNDS], e_bias[ROUNDS], e_c[ROUNDS], e_s[ROUNDS], e_x[ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int e_tt = 2 * rd + e_half;
+        const bool e_mine = e_tt < NT && item + e_tt * p.items < tiles;
+        const int e_n = min((item + e_tt * p.items) * 16 + e_r, p.N - 1);
+        e_lnc[rd] = 0.f; e_bias[rd] = 0.f; e_c[rd] = 1.f; e_s[rd] = 0.f; e_x[rd] = 0.f;
+        if (e_mine) {
+            if (ln) e_lnc[rd] = __ldg(p.ln_c + e_n);
+            if (p.bias != nullptr) e_bias[rd] = __ldg(p.bias + e_n);
+            if (p.mode == KX_DEC_QKV) {
+                const int which = e_n / C.d_model;
+                if (which < 2) {                            // pos0 was read once at kernel start: no dependent round trip here
+                    const int j = (e_n & 63) >> 1;
+                    e_c[rd] = __ldg((which == 0 ? C.xq_cos : C.xk_cos) + pos0 * 32 + j);
+                    e_s[rd] = __ldg((which == 0 ? C.xq_sin : C.xk_sin) + pos0 * 32 + j);
+                }
+            } else if (p.mode == KX_DEC_RESIDUAL && e_b < C.batch) {
+                e_x[rd] = __ldcg(C.x + static_cast<long long>(e_b) * C.d_model + e_n);     // last written two phases ago
             }
-        } else if (p.mode == KX_DEC_RESIDUAL && e_b < C.batch) {
-            e_x = __ldcg(C.x + static_cast<long long>(e_b) * C.d_model + e_n);     // last written two phases ago
         }
     }
 
@@ -351,8 +355,8 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
             for (int u = 0; u < 4; ++u)
                 if (s_lo + u < s_hi) { stats2(av[u].x, s1, s2); stats2(av[u].y, s1, s2); stats2(av[u].z, s1, s2); stats2(av[u].w, s1, s2); }
         }
-        // next chunk's activations: requested as soon as these registers are free (a second register set made the
-        // kernel spill, and a spill is an L2 round trip here)
+        // next chunk's activations: requested as soon as these registers are free (a second register set was measured:
+        // no gain)
         if (more) load_a(kc + CHUNK_K, av);
     }
     stamp(dbg, 3);
@@ -371,34 +375,43 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
     consumer_sync();
     stamp(dbg, 4);
 
-    // threads 0..127 finish tile 0, threads 128..255 tile 1: (batch row b, feature r16)
-    const int tt = tid >> 7, idx = tid & 127;
+    // per round, threads 0..127 finish tile 2*rd, threads 128..255 tile 2*rd + 1: (batch row b, feature r16)
+    const int idx = tid & 127;
     const int b = idx >> 4, r16 = idx & 15;
-    const bool mine = tt < NT && item + tt * p.items < tiles;
-    const int n0 = (item + tt * p.items) * 16;
-    float v = 0.f;
-    if (mine) {
+    float vv[ROUNDS];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += sm.red[tt][w][r16][b];
-        if (ln) {
-            float a1 = 0.f, a2 = 0.f;
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int tt = 2 * rd + (tid >> 7);
+        const bool mine = tt < NT && item + tt * p.items < tiles;
+        float v = 0.f;
+        if (mine) {
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { a1 += sm.st[w][b][0]; a2 += sm.st[w][b][1]; }
-            const float inv_n = 1.0f / static_cast<float>(p.K);
-            const float mean = a1 * inv_n;
-            const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + C.eps);
-            v = fmaf(-mean * rstd, e_lnc, v * rstd);
+            for (int w = 0; w < 8; ++w) v += sm.red[tt][w][r16][b];
+            if (ln) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { a1 += sm.st[w][b][0]; a2 += sm.st[w][b][1]; }
+                const float inv_n = 1.0f / static_cast<float>(p.K);
+                const float mean = a1 * inv_n;
+                const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + C.eps);
+                v = fmaf(-mean * rstd, e_lnc[rd], v * rstd);
+            }
+            v += e_bias[rd];
+            sm.fin[tt][r16][b] = v;
         }
-        v += e_bias;
-        sm.fin[tt][r16][b] = v;
+        vv[rd] = v;
     }
     consumer_sync();
     stamp(dbg, 5);
 
-    {
-        const int n = n0 + r16;
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int tt = 2 * rd + (tid >> 7);
+        const bool mine = tt < NT && item + tt * p.items < tiles;
+        const int n = (item + tt * p.items) * 16 + r16;
         const bool live = mine && b < C.batch && n < p.N;
+        float v = vv[rd];
         if (p.argmax_keys != nullptr) {                     // all 32 lanes take part in the shuffles
             unsigned long long key = 0ull;
             if (live) {
@@ -417,21 +430,20 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
             if (p.mode == KX_DEC_QKV) {
                 const int which = n / C.d_model;
                 const int col = n - which * C.d_model;
-                const int pos = e_pos;
                 if (which < 2) {
                     const float x0 = sm.fin[tt][r16 & ~1][b], x1 = sm.fin[tt][r16 | 1][b];
-                    v = (r16 & 1) ? fmaf(x1, e_c, x0 * e_s) : fmaf(x0, e_c, -(x1 * e_s));
+                    v = (r16 & 1) ? fmaf(x1, e_c[rd], x0 * e_s[rd]) : fmaf(x0, e_c[rd], -(x1 * e_s[rd]));
                 }
                 if (which == 0) {
                     p.q_out[static_cast<long long>(b) * C.d_model + col] = __float2bfloat16_rn(v);
-                } else if (pos < C.t_max) {
+                } else if (pos0 < C.t_max) {
                     __nv_bfloat16* dst = (which == 1 ? p.k_cache : p.v_cache);
-                    dst[((static_cast<long long>(b) * C.heads + (col >> 6)) * C.t_max + pos) * 64 + (col & 63)] =
+                    dst[((static_cast<long long>(b) * C.heads + (col >> 6)) * C.t_max + pos0) * 64 + (col & 63)] =
                         __float2bfloat16_rn(v);
                 }
             } else if (p.mode == KX_DEC_RESIDUAL) {
                 float* px = C.x + static_cast<long long>(b) * C.d_model + n;
-                v += e_x;
+                v += e_x[rd];
                 *px = v;
                 C.xb[static_cast<long long>(b) * C.d_model + n] = __float2bfloat16_rn(v);
             } else {
@@ -619,7 +631,7 @@ __device__ __forceinline__ void pick_tokens(const StepCommon& C) {
 
 }  // namespace
 
-__global__ void __maxnreg__(112)                         // 2 CTAs x 288 threads x 112 registers = 63 K
+__global__ void __maxnreg__(160)                         // one CTA of 9 warps per SM (the 6-stage ring fills shared memory); 3 warps share a 16 K-register sub-partition
 decode_step_kernel(const StepPlan* __restrict__ plan) {
     extern __shared__ __align__(128) unsigned char ring_mem[];
     __shared__ StepSmem sm;
@@ -657,7 +669,9 @@ decode_step_kernel(const StepPlan* __restrict__ plan) {
         if (type == PH_LINEAR) {
             // (one shared instantiation for both item kinds was measured too, to shrink the 56 KB kernel towards the 32 KB
             // L1.5 instruction cache: no gain, the one-tile phases just ran the longer code)
-            if (P.nt == 2) {
+            if (P.nt > 2) {                                 // 3 or 4 tiles per item (the fourth predicated off when nt == 3)
+                for (int item = blockIdx.x; item < items; item += gridDim.x) linear_item<4>(P, C, item, pos0, r, sm, dbg);
+            } else if (P.nt == 2) {
                 for (int item = blockIdx.x; item < items; item += gridDim.x) linear_item<2>(P, C, item, pos0, r, sm, dbg);
             } else {
                 for (int item = blockIdx.x; item < items; item += gridDim.x) linear_item<1>(P, C, item, pos0, r, sm, dbg);
@@ -694,6 +708,9 @@ int step_grid(int sms) {
     if (per_sm < 0) {
         int n = 0;
         cudaError_t e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(STEP_DYN_SMEM));
+        // two CTAs of 114 KB only fit with the full 228 KB carve-out; the default heuristic sized it for ONE block (the ncu
+        // launch table showed a 148-CTA grid: half the intended parallelism and prefetch depth)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, decode_step_kernel, STEP_THREADS, STEP_DYN_SMEM);
         if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
         per_sm = std::min(n, STEP_CTAS_PER_SM);
@@ -760,7 +777,7 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
         P.ln_c = c; P.bias = d; P.mode = mode; P.act = act;
         const int tiles = (N + 15) / 16;
         (void)allow_split;
-        P.nt = tiles > grid ? 2 : 1;                        // more tiles than CTAs: pair them so the phase stays one pass
+        P.nt = std::min(4, (tiles + grid - 1) / grid);      // more tiles than CTAs: group them so the phase stays one pass
         P.items = (tiles + P.nt - 1) / P.nt;
         return P;
     };
@@ -792,6 +809,12 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { set_error("kx_decode_plan_build: %s", cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
     return KX_OK;
+}
+
+extern "C" int kx_decode_step_ctas(void) {
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    return step_grid(sms);
 }
 
 extern "C" int kx_decode_step(const void* device_plan, cudaStream_t stream) {

@@ -130,6 +130,7 @@ SIGNATURES = {
     "kx_decode_embed": (_i, [_vp, _i, _f32p, _i, _f32p, _i, _vp, _i, _f32p, _vp, _vp, _vp]),
     "kx_argmax_advance": (_i, [_f32p, _ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "kx_decode_plan_bytes": (C.c_size_t, [_i]),
+    "kx_decode_step_ctas": (_i, []),
     "kx_decode_plan_build": (_i, [C.POINTER(DecodeStepArgs), _vp, _vp]),
     "kx_decode_step": (_i, [_vp, _vp]),
 }

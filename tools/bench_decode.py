@@ -115,7 +115,8 @@ def run(model, batch, prompt, new, layers_note="", one_kernel=True):
     out = dict(batch=batch, prompt=T, new_tokens=new, timed_steps=steps, kernels_per_step=nodes, ms_prompt_pass=ms_prompt, ms_per_step=ms_step,
                tokens_per_s=batch / ms_step * 1e3, weight_bytes=w_bytes, kv_bytes_mean=0.5 * (kv_lo + kv_hi),
                achieved_gbs=by / ms_step / 1e6, peak_gbs=peak, frac=by / ms_step / 1e6 / peak,
-               path="one persistent kernel per step" if one_kernel else "per-kernel step, CUDA-graph replay",
+               path=(f"one persistent kernel per step ({int(ops.lib.kx_decode_step_ctas())} CTAs)" if one_kernel
+                     else "per-kernel step, CUDA-graph replay"),
                err_flag=int(state.err.item()), tokens_head=history[0, :8].tolist())
     return out
 

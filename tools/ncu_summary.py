@@ -35,9 +35,12 @@ def to_bytes(v, unit):
 groups = defaultdict(list)
 for k, m in per.items():
     name = names[k][0]
-    if "kx::" not in name:
+    if "kx::" in name:
+        short = name.split("kx::", 1)[1].split("(")[0]
+    elif "_kernel" in name:                              # ncu's base-name demangling drops the namespace
+        short = name.replace("void ", "").split("(")[0]
+    else:
         continue
-    short = name.split("kx::", 1)[1].split("(")[0]
     groups[short].append((m, names[k]))
 peaks = {}
 try:
