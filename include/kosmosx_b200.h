@@ -370,7 +370,7 @@ int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, c
  *                         SYNCHRONISES `stream` — the only call of this library that does.
  *   kx_decode_step        one launch = one new token per sequence; tokens[b] is consumed, the next choice is written
  *                         back to tokens[b] and history[b, *step]; *pos and *step advance.
- * Per-layer arrays are HOST arrays of `layers` DEVICE pointers.  barrier: 32 x uint64, zeroed once and then owned by
+ * Per-layer arrays are HOST arrays of `layers` DEVICE pointers.  barrier: 288 x uint64 (heads <= 256), zeroed once and then owned by
  * the kernel;
  * err_flag bit 2 = a barrier timed out (logic error, results invalid). */
 typedef struct kx_decode_step_args {

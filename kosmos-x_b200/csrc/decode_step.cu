@@ -46,6 +46,8 @@ constexpr int CHUNK_K = 1024;                   // k per weight stage
 constexpr int W_PITCH = CHUNK_K * 2 + 64;       // bytes per staged weight row (+64: the quad-row LDS.128 pattern hits all banks)
 constexpr int STAGE_BYTES = 16 * W_PITCH;       // 33792 >= 256 keys x 128 bytes
 constexpr int ATTN_CHUNK = 256;                 // keys per attention item (8 warps x 32)
+constexpr int HEAD_CNT0 = 32;                   // first per-head counter in the barrier buffer (uint64 index)
+constexpr int TILES_PER_HEAD = 12;              // 64 features / 16 per tile, for each of q, k, v
 static_assert(STAGE_BYTES >= ATTN_CHUNK * 128 && STAGE_BYTES % 128 == 0, "ring stage geometry");
 
 struct Phase {
@@ -54,7 +56,8 @@ struct Phase {
     const __nv_bfloat16* a; long long lda;
     const __nv_bfloat16* w; long long ldw; int N, K;
     const float* ln_c; const float* bias;
-    int mode, act, nt;                       // nt: weight tiles per item (1, or 2 sharing the activation fragments)
+    int mode, act, nt;                       // nt: weight tiles per item (1..4, sharing the activation fragments)
+    int layer, no_barrier;                   // q|k|v phases: the attention phase behind them waits per head, not at a grid barrier
     void* out; long long ld_out; int out_f32; unsigned long long* argmax_keys;
     // attention: q_out = q, k_cache, v_cache, out = attention output (bf16, ld_out)
     __nv_bfloat16* q_out; __nv_bfloat16* k_cache; __nv_bfloat16* v_cache;
@@ -69,7 +72,9 @@ struct StepCommon {
     float* x; __nv_bfloat16* xb;
     int* pos; int* step; int* err_flag;
     unsigned long long* argmax_keys;
-    unsigned long long* barrier;            // [0] arrivals (monotonic), [1] launches completed, [16] release flag
+    unsigned long long* barrier;            // [0] arrivals (monotonic), [1] launches completed, [16] release flag,
+                                            // [HEAD_CNT0 + h] q|k|v tiles of head h stored so far (monotonic, 12 per layer)
+    int layers;
     long long* trace;                       // optional: CTA 0 stamps globaltimer (work done, barrier left) per phase
 };
 
@@ -454,15 +459,43 @@ __device__ __forceinline__ void linear_item(const Phase& p, const StepCommon& C,
             }
         }
     }
+    if (p.mode == KX_DEC_QKV) {
+        // tell the attention items of this layer that one more tile of their head is in memory: release on the atomic,
+        // cumulative over the CTA's stores ordered before it by the bar.sync (no grid barrier between q|k|v and attention)
+        consumer_sync();
+        if (tid < NT) {
+            const int tile = item + tid * p.items;
+            if (tile < tiles) {
+                const int head = ((tile * 16) % C.d_model) >> 6;
+                asm volatile("red.release.gpu.global.add.u64 [%0], 1;\n" :: "l"(C.barrier + HEAD_CNT0 + head) : "memory");
+            }
+        }
+    }
     stamp(dbg, 6);
     // sm.red / sm.st are rewritten by this CTA's next item only after its k loop, sm.fin only after a further
     // consumer_sync: the reads above are ordered before those writes by the barriers in between.
 }
 
 // One (batch, head) item of the attention phase (consumer warps): all 256-key chunks, online softmax per lane.
-__device__ __forceinline__ void attn_item(const Phase& p, const StepCommon& C, int bh, int n_keys, Ring& r, StepSmem& sm) {
+__device__ __forceinline__ void attn_item(const Phase& p, const StepCommon& C, int bh, int n_keys, unsigned long long epoch,
+                                          Ring& r, StepSmem& sm) {
     const int H = C.heads;
     const int b = bh / H, h = bh - b * H;
+    // q and the newest k / v row of this head come from the q|k|v phase of this layer: wait for its 12 tiles (all other
+    // heads may still be in flight — there is no grid barrier in front of the attention phase)
+    if (threadIdx.x == 0) {
+        const unsigned long long want = (epoch * C.layers + p.layer + 1) * TILES_PER_HEAD;
+        const unsigned long long* cnt = C.barrier + HEAD_CNT0 + h;
+        const long long t0 = clock64();
+        while (ld_relaxed_u64(cnt) < want) {
+            if (clock64() - t0 > (3ll << 30)) {
+                if (C.err_flag != nullptr) atomicOr(C.err_flag, 4);
+                break;
+            }
+        }
+        (void)ld_acquire_u64(cnt);
+    }
+    consumer_sync();
     const int n_chunks = (n_keys + ATTN_CHUNK - 1) / ATTN_CHUNK;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane & 7, kq = lane >> 3;
@@ -654,7 +687,7 @@ decode_step_kernel(const StepPlan* __restrict__ plan) {
     const int n_phases = C.n_phases;
     unsigned long long* bar = C.barrier;
     const unsigned long long epoch = ld_acquire_u64(bar + 1);
-    unsigned long long target = epoch * static_cast<unsigned long long>(n_phases - 1) * gridDim.x;
+    unsigned long long target = epoch * static_cast<unsigned long long>(n_phases - 1 - C.layers) * gridDim.x;
     const int pos0 = ld_cg_i(C.pos);                       // only the last phase of a launch changes it
     const int n_keys = min(pos0 + 1, C.t_max);
 
@@ -677,14 +710,19 @@ decode_step_kernel(const StepPlan* __restrict__ plan) {
                 for (int item = blockIdx.x; item < items; item += gridDim.x) linear_item<1>(P, C, item, pos0, r, sm, dbg);
             }
         } else if (type == PH_ATTN) {
-            for (int item = blockIdx.x; item < items; item += gridDim.x) attn_item(P, C, item, n_keys, r, sm);
+            for (int item = blockIdx.x; item < items; item += gridDim.x) attn_item(P, C, item, n_keys, epoch, r, sm);
         } else if (type == PH_EMBED) {
             if (static_cast<int>(blockIdx.x) < C.batch) embed_row(C, blockIdx.x);
         } else {
             if (blockIdx.x == 0) pick_tokens(C);
         }
         if (C.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) C.trace[2 * ph] = static_cast<long long>(globaltimer_ns());
-        if (ph + 1 < n_phases) {
+        if (ph + 1 < n_phases && P.no_barrier) {            // q|k|v -> attention: per-head counters instead of a grid barrier
+            consumer_sync();                                // everybody is done reading sm.ph[(ph + 1) & 1] (phase ph - 1)
+            stage_words(&sm.ph[(ph + 1) & 1], &plan->ph[ph + 1], sizeof(Phase), threadIdx.x, CONSUMERS);
+            consumer_sync();
+            if (C.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) C.trace[2 * ph + 1] = static_cast<long long>(globaltimer_ns());
+        } else if (ph + 1 < n_phases) {
             // the next phase's descriptor travels while the barrier drains (its buffer was last read in phase ph - 1)
             stage_words(&sm.ph[(ph + 1) & 1], &plan->ph[ph + 1], sizeof(Phase), threadIdx.x, CONSUMERS);
             target += gridDim.x;
@@ -734,7 +772,7 @@ extern "C" size_t kx_decode_plan_bytes(int layers) {
 extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_plan, cudaStream_t stream) {
     if (!g || !device_plan) { set_error("kx_decode_plan_build: null argument"); return KX_ERR_ARG; }
     if (g->batch <= 0 || g->batch > 8 || g->layers < 0 || g->d_model <= 0 || (g->d_model & 63) || g->ffn <= 0 || (g->ffn & 31) ||
-        g->heads * 64 != g->d_model || g->vocab <= 0 || g->t_max <= 0 || g->pos_rows <= 2) {
+        g->heads * 64 != g->d_model || g->heads > 256 || g->vocab <= 0 || g->t_max <= 0 || g->pos_rows <= 2) {
         set_error("kx_decode_plan_build: need 1 <= batch <= 8, d_model == heads*64, ffn %% 32 == 0 (batch %d, d_model %d, heads %d)",
                   g->batch, g->d_model, g->heads);
         return KX_ERR_ARG;
@@ -765,6 +803,7 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
     C.x = g->x; C.xb = reinterpret_cast<__nv_bfloat16*>(g->xb);
     C.pos = g->pos; C.step = g->step; C.err_flag = g->err_flag; C.argmax_keys = g->argmax_keys;
     C.barrier = g->barrier;
+    C.layers = L;
     C.trace = g->trace;
 
     int k = 0;
@@ -786,8 +825,9 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
         Phase& q = lin(g->xb, D, g->w_qkv[l], 3 * D, D, g->c_qkv[l], g->d_qkv[l], KX_DEC_QKV, KX_ACT_NONE, false);
         q.q_out = reinterpret_cast<__nv_bfloat16*>(g->q);
         q.k_cache = reinterpret_cast<__nv_bfloat16*>(g->k_cache[l]); q.v_cache = reinterpret_cast<__nv_bfloat16*>(g->v_cache[l]);
+        q.layer = l; q.no_barrier = 1;
         Phase& at = plan->ph[k++];
-        at.type = PH_ATTN; at.items = g->batch * g->heads;
+        at.type = PH_ATTN; at.items = g->batch * g->heads; at.layer = l;
         at.q_out = reinterpret_cast<__nv_bfloat16*>(g->q);
         at.k_cache = reinterpret_cast<__nv_bfloat16*>(g->k_cache[l]); at.v_cache = reinterpret_cast<__nv_bfloat16*>(g->v_cache[l]);
         at.out = g->att; at.ld_out = D;

@@ -495,9 +495,9 @@ def _ptr_array(tensors):
 
 
 def decode_step_buffers(layers, device):
-    """(plan bytes, barrier 32 x int64 (zeroed)) for kx_decode_plan_build."""
+    """(plan bytes, barrier 288 x int64 (zeroed)) for kx_decode_plan_build."""
     return (torch.empty(int(lib.kx_decode_plan_bytes(layers)), dtype=torch.uint8, device=device),
-            torch.zeros(32, dtype=torch.int64, device=device))
+            torch.zeros(288, dtype=torch.int64, device=device))
 
 
 def decode_plan_build(plan, *, layers, out, embed_table, pos_table, tabs, k_cache, v_cache, tokens, x, xb, q, att, mid, logits,
