@@ -3,29 +3,30 @@
 // A decoding step streams 2.55 GB of weights plus the KV cache and does almost no arithmetic: the only thing that
 // matters is that HBM never idles.  The per-kernel path (decode.cu) cannot keep it busy: 123 launches of 5-35 MB each
 // are latency-bound streams (ncu: long-scoreboard stalls, 24 warps/SM) separated by launch / drain gaps.  Here the whole
-// step — embedding, 24 x (q|k|v, attention, out_proj, fc1, fc2), LM head, greedy choice — is one grid of 2 CTAs per SM:
+// step — embedding, 24 x (q|k|v, attention, out_proj, fc1, fc2), LM head, greedy choice — is one grid of ONE CTA (9 warps)
+// per SM (two do not fit: 3 + 3 warps of 112 registers exceed a 16 K-register sub-partition — found in the ncu launch table):
 //
 //   * warp 8 of every CTA is a PRODUCER: it walks the CTA's whole work list of the step and moves it through a
-//     3-stage, 33 KB-per-stage shared-memory ring with bulk copies (cp.async.bulk, mbarrier complete_tx; lane 0 arms the
+//     6-stage, 33 KB-per-stage (200 KB) shared-memory ring with bulk copies (cp.async.bulk, mbarrier complete_tx; lane 0 arms the
 //     barrier, 16 lanes issue the row copies at once): 16 weight rows x 1024 k per stage for a Linear item, 256 keys
 //     of K or of V for an attention item.  Weights and the history
 //     rows of the cache are immutable during the launch, so the producer never waits for a phase boundary: while the
 //     consumers of a CTA sit in a grid barrier its ring is already filling with the NEXT phase's bytes (200 KB per SM
-//     in flight, several times what Little's law asks for at 6.5 TB/s).
+//     in flight, several times what Little's law asks for at 6.5 TB/s; a whole phase's share of a CTA fits the ring).
 //   * warps 0-7 are CONSUMERS: mma.sync m16n8k16 with the weight rows as the M dimension and the (<= 8) sequences as N,
 //     fragments read from the ring with conflict-free 16-byte LDS (rows padded by 64 bytes), the same k-permutation,
 //     folded LayerNorm, fixed-order reductions and epilogues as decode_linear_kernel; attention reads its 256-key chunk
 //     from the ring and the single NEW key/value row (written by the q|k|v phase of this launch) straight from L2.
 //   * phases are separated by a grid barrier over the consumers (arrivals on one line, release flag on another).
 //     Every dependent L2 round trip inside a phase is on the critical path of the whole GPU, so the work is cut to
-//     keep those chains short: a Linear phase is ONE pass (a CTA takes one 16-row tile, or two tiles that share the
-//     activation fragments when there are more tiles than CTAs; no split-K exchange), activations of the next k chunk
-//     are fetched while the current one is multiplied, and an attention item is a whole (batch, head) — its chunks are
-//     folded with an online softmax inside the CTA, so there is no cross-CTA merge.
+//     keep those chains short: a Linear phase is ONE pass (a CTA takes up to four 16-row tiles that share the
+//     activation fragments; no split-K exchange), the epilogue operands are requested at item entry, an attention item
+//     is a whole (batch, head) — its chunks are folded with an online softmax inside the CTA, no cross-CTA merge — and
+//     the attention phase does not wait at a grid barrier at all: it waits for the 12 q|k|v tiles of ITS head.
 //
 // Activations written in one phase are read in the next by other SMs with ld.global.cg (L2), never through L1.
 //
-// Status (profiles/r1_decode_bench.md): bit-identical to the per-kernel path on the test model, 1.22 ms per step at B = 8
+// Status (profiles/r1_decode_bench.md): bit-identical to the per-kernel path on the test model, 1.08 ms per step at B = 8
 // against 1.03 ms for the CUDA graph of separate kernels, so generate() uses it only on request (one_kernel=True).
 #include "kx_internal.h"
 #include "ptx.cuh"
