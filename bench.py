@@ -447,18 +447,18 @@ def run_gpu(args):
 
 def decode_measure(torch, model, batch=8, prompt=512, new=96):
     """Incremental decoding (Kosmos.generate's step): B=8 sequences, 512-token multimodal prompt, one token per sequence
-    per step from the KV cache.  Timed with CUDA events around the replays of the captured step (per-kernel path: 123
-    kernels of libkosmosx_sm100.so per step).  Roofline: HBM — algorithmic bytes of a step = every decoder weight matrix
+    per step from the KV cache.  Timed with CUDA events around the steps (default path for B <= 8: ONE persistent
+    cooperative kernel of libkosmosx_sm100.so per step).  Roofline: HBM — algorithmic bytes of a step = every decoder weight matrix
     once (bf16) + the K/V rows of the cache, against the measured copy bandwidth."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_decode
-    r = bench_decode.run(model, batch, prompt, new, one_kernel=False)
+    r = bench_decode.run(model, batch, prompt, new, one_kernel=True)
     return {
         "config": f"greedy decoding, B={batch}, prompt {r['prompt']} rows (1 image + text), {r['timed_steps']} timed one-token steps, "
-                  "KV cache bf16 head-major, CUDA-graph replay of the step",
+                  "KV cache bf16 head-major, " + r["path"],
         "value": r["tokens_per_s"], "unit": "generated tokens/s", "ms_per_step": r["ms_per_step"],
         "ms_prompt_pass": r["ms_prompt_pass"], "gpu_launches_per_step": r["kernels_per_step"],
-        "roofline": {"bound": "hbm", "kernel": "decode_linear_kernel + decode_attention_kernel (whole step)",
+        "roofline": {"bound": "hbm", "kernel": "decode_step_kernel (the whole step: embedding, 24 x (q|k|v, attention, out_proj, fc1, fc2), LM head, greedy choice)",
                      "achieved": r["achieved_gbs"], "peak": r["peak_gbs"], "unit": "GB/s", "frac": r["frac"],
                      "bytes_per_step": r["weight_bytes"] + r["kv_bytes_mean"], "traffic": _ncu_traffic("decode_step"),
                      "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)"},

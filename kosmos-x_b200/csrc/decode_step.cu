@@ -26,8 +26,9 @@
 //
 // Activations written in one phase are read in the next by other SMs with ld.global.cg (L2), never through L1.
 //
-// Status (profiles/r1_decode_bench.md): bit-identical to the per-kernel path on the test model, 1.08 ms per step at B = 8
-// against 1.03 ms for the CUDA graph of separate kernels, so generate() uses it only on request (one_kernel=True).
+// Status (profiles/r1_decode_bench.md): bit-identical to the per-kernel path on the test model, 1.00 ms per step at B = 8
+// against 1.03 ms for the CUDA graph of separate kernels (1.37 vs 1.41 ms at a 1920-row prompt): generate()'s default for
+// batches of at most 8 sequences.
 #include "kx_internal.h"
 #include "ptx.cuh"
 
@@ -164,10 +165,11 @@ __device__ __forceinline__ void stamp(long long* dbg, int k) {
 #endif
 }
 
-// (A two-level variant — 8 shard counters, last arriver of a shard arrives on a top counter — was measured: the second
-// dependent atomic costs more than the contention it removes, 3.1-4.0 us of barrier wait per phase instead of 2.3-3.2.)
-// Grid barrier over the consumers of all (co-resident) CTAs.  Arrivals are counted on one line; the last arriver
-// publishes the target on ANOTHER line (ctr[16]) that the waiters poll.  Bounded spin: a logic error cannot hang the GPU.
+// Measured alternatives: a separate release line written by the last arriver and polled by everybody (one more hop:
+// +0.8 us per barrier, 1.08 vs 1.00 ms per step); a two-level variant with 8 shard counters (the second dependent atomic
+// costs more than the contention it removes: 3.1-4.0 us of barrier wait per phase).
+// Grid barrier over the consumers of all (co-resident) CTAs: one monotonic arrival counter, polled with relaxed loads by
+// thread 0 of every CTA (one acquire at the end).  Bounded spin: a logic error cannot hang the GPU.
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target, int* err_flag, long long* dbg) {
     consumer_sync();
     if (threadIdx.x == 0) {
@@ -177,17 +179,15 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
         unsigned long long old;
         asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;\n" : "=l"(old) : "l"(ctr) : "memory");
         stamp(dbg, 9);
-        if (old + 1 == target) {
-            asm volatile("st.release.gpu.global.u64 [%0], %1;\n" :: "l"(ctr + 16), "l"(target) : "memory");
-        } else {
+        if (old + 1 != target) {                            // poll the arrival counter itself: one hop from the last arrival
             const long long t0 = clock64();
-            while (ld_relaxed_u64(ctr + 16) < target) {
+            while (ld_relaxed_u64(ctr) < target) {
                 if (clock64() - t0 > (3ll << 30)) {         // ~2 s
                     if (err_flag != nullptr) atomicOr(err_flag, 4);
                     break;
                 }
             }
-            (void)ld_acquire_u64(ctr + 16);                 // one acquire (one L1 invalidation) once the flag is seen
+            (void)ld_acquire_u64(ctr);                      // one acquire (one L1 invalidation) once the count is seen
         }
     }
     consumer_sync();

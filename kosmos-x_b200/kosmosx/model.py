@@ -602,12 +602,22 @@ class _KosmosBase(nn.Module):
         dec.advance(state, history=history, forced=forced, move=False)       # token 0 comes from the prompt's last row
         steps = max_new_tokens - 1
         if one_kernel is None:
-            one_kernel = B <= 8 and os.environ.get("KX_DECODE_ONE_KERNEL", "0") != "0"
+            one_kernel = B <= 8 and os.environ.get("KX_DECODE_ONE_KERNEL", "1") != "0"
+            auto = True
+        else:
+            auto = False
+        plan = None
         if one_kernel and steps > 0:
             # the whole step (embedding .. greedy choice) is ONE persistent cooperative launch per token
             if B > 8:
                 raise ValueError("the one-kernel decoding step handles at most 8 sequences")
-            plan = dec.build_step_plan(state, history=history, forced=forced)
+            try:
+                plan = dec.build_step_plan(state, history=history, forced=forced)
+            except RuntimeError:
+                if not auto:                                 # asked for explicitly: report it
+                    raise
+                log.warning("one-kernel decoding step unavailable (cooperative launch does not fit); using the per-kernel step")
+        if plan is not None:
             for _ in range(steps):
                 ops.decode_step(plan)
                 state.length += 1
