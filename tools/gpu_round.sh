@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # One gpurun call: GPU parity tests, bench, ncu launch list + full captures.  Logs under gpurun_out/<tag>/.
-# Usage: tools/gpu_round.sh <tag> [tests] [bench] [launches] [ncu_gemm] [ncu_attn] [smoke]
+# Usage: tools/gpu_round.sh <tag> [tests] [bench] [launches] [ncu_gemm] [ncu_attn] [smoke] [decode] ...
 cd "$(dirname "$0")/.."
 tag="${1:-r1}"; shift || true
 what="${*:-smoke tests bench launches ncu_gemm ncu_attn}"
@@ -17,6 +17,9 @@ for w in $what; do
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 4 -o "$out/prof_gemm" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_gemm.log" 2>&1; echo "ncu_gemm exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_gemm.log";;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_pp -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
     kcheck)   bash tools/run_kernel_checks.sh bench;;
+    decode)   timeout 300 python tools/kernel_check.py decode > "$out/kcheck_decode.log" 2>&1; echo "kcheck decode exit $?" | tee -a "$out/summary.txt";
+              timeout 600 python -m pytest tests -m gpu -x -q -s -k "incremental or generate" > "$out/pytest_decode.log" 2>&1; echo "pytest decode exit $?" | tee -a "$out/summary.txt"; grep -E "max=|passed|failed" "$out/pytest_decode.log" | tail -20;
+              for mode in one graph; do KX_STEP_TRACE=1 timeout 300 python tools/bench_decode.py --mode $mode > "$out/bench_decode_$mode.log" 2>&1; grep "^trace" "$out/bench_decode_$mode.log"; tail -1 "$out/bench_decode_$mode.log" | cut -c1-400; done;;
     kernel_table) timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread --clock-control none --csv --log-file "$out/kernel_table.csv" python tools/profile_step.py --train --steps 2 --layers 2 --vit-layers 2 > "$out/kernel_table.log" 2>&1; echo "kernel_table exit $?" | tee -a "$out/summary.txt"; tail -2 "$out/kernel_table.log";
                   timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread --clock-control none --csv --log-file "$out/kernel_table_fwd.csv" python tools/profile_step.py --steps 2 --layers 2 --vit-layers 2 > "$out/kernel_table_fwd.log" 2>&1; echo "kernel_table_fwd exit $?" | tee -a "$out/summary.txt";;
     bench_train) timeout 900 python bench.py --workload train --steps 5 --warmup 3 > "$out/bench_train.json" 2> "$out/bench_train.err"; echo "bench_train exit $?" | tee -a "$out/summary.txt"; cut -c1-400 "$out/bench_train.json"; tail -3 "$out/bench_train.err";;
