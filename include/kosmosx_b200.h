@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 13   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 14   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -172,6 +172,21 @@ int kx_add_positions(const float* in, float* out, int batch, int T, int dim, con
  */
 int kx_im2col_patches(const float* pixels, int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
                       const float* class_embedding, const float* pos_table, float* x, int dim, kx_stream_t stream);
+
+/* Host preprocessing moved onto the device: CLIPImageProcessor's rescale + normalise, which
+ * KosmosTokenizer.tokenize_images applies on the host (kosmosx/model.py:81-97), for uint8 images that already have
+ * the model's size.  pixels: (N,3,H,W) (channels_last = 0) or (N,H,W,3) (channels_last = 1) uint8;
+ * pixel_values[n,c,y,x] = (float32(float64(u8) * (1/255)) - mean[c]) / std[c] with float32 subtract / divide,
+ * the roundings of HF 4.35 image_transforms.rescale / normalize.  mean3 / std3 are HOST arrays of 3 floats
+ * (passed to the kernel by value).  image % 4 == 0. */
+int kx_clip_normalize_u8(const unsigned char* pixels, int channels_last, int batch, int image, const float* mean3,
+                         const float* std3, float* pixel_values, kx_stream_t stream);
+
+/* kx_clip_normalize_u8 fused into kx_im2col_patches: uint8 pixels -> normalised bf16 patch rows + CLS rows; the
+ * result is bit-identical to kx_im2col_patches applied to kx_clip_normalize_u8's output.  media as there. */
+int kx_im2col_patches_u8(const unsigned char* pixels, int channels_last, const float* mean3, const float* std3, int batch,
+                         int media, int image, int patch, void* patches_bf16, int k_pad, const float* class_embedding,
+                         const float* pos_table, float* x, int dim, kx_stream_t stream);
 
 /* Row statistics + bf16 copy of an fp32 matrix: xb = bf16(x), stats[m] = (sum, sumsq) of xb's row m
  * ([1][rows][2] fp32).  Seeds the folded-LayerNorm chain (kx_gemm_args.ln_part) for the first decoder layer,

@@ -275,6 +275,86 @@ im2col_kernel(const float* __restrict__ pixels, int batch, int media, int image,
     }
 }
 
+// ----------------------------------------------------------------------------- CLIP pixel preprocessing on device
+// CLIPImageProcessor's rescale + normalise for images that already have the model's size (SURVEY.md §8(f)4;
+// reference call site kosmosx/model.py:81-97; HF 4.35 image_transforms.py rescale(): uint8 * (1/255) in float64,
+// rounded to float32; normalize(): (x - mean) / std in float32).  Every step is written with explicit
+// round-to-nearest intrinsics so that no FMA contraction changes the reference's roundings.
+struct ClipNorm {
+    float mean[3];
+    float std[3];
+};
+
+// kernel parameters live in the constant bank: select instead of indexing dynamically (no local-memory copy)
+__device__ __forceinline__ float pick3(const float (&a)[3], int c) { return c == 0 ? a[0] : (c == 1 ? a[1] : a[2]); }
+
+__device__ __forceinline__ float clip_pixel(unsigned char u, float mean, float std) {
+    const float r = __double2float_rn(__dmul_rn(static_cast<double>(u), 1.0 / 255.0));
+    return __fdiv_rn(__fsub_rn(r, mean), std);
+}
+
+__device__ __forceinline__ long long u8_index(int channels_last, long long b, int c, int y, int x, int image) {
+    return channels_last ? ((b * image + y) * image + x) * 3 + c : ((b * 3 + c) * image + y) * image + x;
+}
+
+// pixel_values (N,3,H,W) fp32 from uint8 (N,3,H,W) or (N,H,W,3): one thread per 4 consecutive output pixels
+// (16-byte stores; the uint8 loads of a warp cover 128 consecutive bytes in the planar layout).
+__global__ void __launch_bounds__(256)
+clip_normalize_u8_kernel(const unsigned char* __restrict__ pixels, int channels_last, long long n_quads, int image, ClipNorm nm,
+                         float* __restrict__ out) {
+    const int plane4 = image * image / 4;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n_quads; i += gridDim.x * 256ll) {
+        const long long bc = i / plane4;
+        const int r = static_cast<int>(i - bc * plane4) * 4;
+        const long long b = bc / 3;
+        const int c = static_cast<int>(bc - b * 3);
+        const int y = r / image, x = r - y * image;            // image % 4 == 0: the 4 pixels share a row
+        const float mu = pick3(nm.mean, c), sd = pick3(nm.std, c);
+        float4 v;
+        if (channels_last) {
+            const unsigned char* p = pixels + u8_index(1, b, c, y, x, image);
+            v = make_float4(clip_pixel(p[0], mu, sd), clip_pixel(p[3], mu, sd), clip_pixel(p[6], mu, sd), clip_pixel(p[9], mu, sd));
+        } else {
+            const uchar4 q = *reinterpret_cast<const uchar4*>(pixels + u8_index(0, b, c, y, x, image));
+            v = make_float4(clip_pixel(q.x, mu, sd), clip_pixel(q.y, mu, sd), clip_pixel(q.z, mu, sd), clip_pixel(q.w, mu, sd));
+        }
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+// The same arithmetic fused into the patch pack: uint8 pixels -> normalised bf16 im2col rows + CLS rows, so the
+// fp32 pixel_values tensor never exists in HBM (0.15 MB read per image instead of 0.6 MB written and read back).
+__global__ void __launch_bounds__(256)
+im2col_u8_kernel(const unsigned char* __restrict__ pixels, int channels_last, ClipNorm nm, int batch, int media, int image,
+                 int patch, __nv_bfloat16* __restrict__ patches, int k_pad, const float* __restrict__ cls,
+                 const float* __restrict__ pos, float* __restrict__ x, int dim) {
+    const int g = image / patch;
+    const int n_patch_rows = batch * g * g;
+    if (blockIdx.x < n_patch_rows) {
+        const int slot = blockIdx.x / (g * g);                // media-major output slot, as in im2col_kernel
+        const int pi = blockIdx.x - slot * g * g;
+        const int seqs = batch / media;
+        const int b = (slot % seqs) * media + slot / seqs;
+        const int py = pi / g, px = pi - py * g;
+        const int pp = patch * patch;
+        __nv_bfloat16* o = patches + static_cast<long long>(blockIdx.x) * k_pad;
+        for (int k = threadIdx.x; k < k_pad; k += blockDim.x) {
+            float val = 0.f;
+            if (k < 3 * pp) {
+                const int c = k / pp, r = k - c * pp;
+                const int dy = r / patch, dx = r - dy * patch;
+                val = clip_pixel(pixels[u8_index(channels_last, b, c, py * patch + dy, px * patch + dx, image)],
+                                 pick3(nm.mean, c), pick3(nm.std, c));
+            }
+            o[k] = __float2bfloat16_rn(val);
+        }
+    } else {
+        const int b = blockIdx.x - n_patch_rows;
+        float* o = x + static_cast<long long>(b) * (g * g + 1) * dim;
+        for (int i = threadIdx.x; i < dim; i += blockDim.x) o[i] = cls[i] + pos[i];
+    }
+}
+
 // ----------------------------------------------------------------------------- xPos tables
 __global__ void xpos_tables_kernel(const float* __restrict__ scale, const float* __restrict__ inv_freq, int T,
                                    int min_pos, float scale_base, float* q_cos, float* q_sin, float* k_cos,
@@ -432,6 +512,55 @@ extern "C" int kx_im2col_patches(const float* pixels, int batch, int media, int 
                                                              reinterpret_cast<__nv_bfloat16*>(patches_bf16), k_pad,
                                                              class_embedding, pos_table, x, dim);
     return check_launch("kx_im2col_patches");
+}
+
+static bool clip_norm_from_host(const float* mean3, const float* std3, ClipNorm* nm, const char* what) {
+    if (!mean3 || !std3) { set_error("%s: null mean / std", what); return false; }
+    for (int c = 0; c < 3; ++c) {
+        if (!(std3[c] > 0.f)) { set_error("%s: std[%d] must be positive", what, c); return false; }
+        nm->mean[c] = mean3[c];
+        nm->std[c] = std3[c];
+    }
+    return true;
+}
+
+extern "C" int kx_clip_normalize_u8(const unsigned char* pixels, int channels_last, int batch, int image, const float* mean3,
+                                    const float* std3, float* pixel_values, cudaStream_t stream) {
+    if (!pixels || !pixel_values) { set_error("kx_clip_normalize_u8: null pointer"); return KX_ERR_ARG; }
+    if (batch <= 0 || image <= 0 || (image % 4) || (reinterpret_cast<uintptr_t>(pixels) & 3) ||
+        (reinterpret_cast<uintptr_t>(pixel_values) & 15)) {
+        set_error("kx_clip_normalize_u8: bad shape or alignment (batch=%d image=%d; image %% 4 == 0, 4-byte aligned input, "
+                  "16-byte aligned output)", batch, image);
+        return KX_ERR_ARG;
+    }
+    ClipNorm nm;
+    if (!clip_norm_from_host(mean3, std3, &nm, "kx_clip_normalize_u8")) return KX_ERR_ARG;
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const long long n_quads = static_cast<long long>(batch) * 3 * image * image / 4;
+    const long long blocks = std::min<long long>((n_quads + 255) / 256, static_cast<long long>(sms) * 8);
+    clip_normalize_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pixels, channels_last != 0, n_quads, image, nm,
+                                                                               pixel_values);
+    return check_launch("kx_clip_normalize_u8");
+}
+
+extern "C" int kx_im2col_patches_u8(const unsigned char* pixels, int channels_last, const float* mean3, const float* std3,
+                                    int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
+                                    const float* class_embedding, const float* pos_table, float* x, int dim,
+                                    cudaStream_t stream) {
+    if (!pixels || !patches_bf16 || !class_embedding || !pos_table || !x) { set_error("kx_im2col_patches_u8: null pointer"); return KX_ERR_ARG; }
+    if (batch <= 0 || media <= 0 || batch % media || patch <= 0 || image % patch || k_pad < 3 * patch * patch || (k_pad % 8)) {
+        set_error("kx_im2col_patches_u8: bad shape (image=%d patch=%d k_pad=%d)", image, patch, k_pad);
+        return KX_ERR_ARG;
+    }
+    ClipNorm nm;
+    if (!clip_norm_from_host(mean3, std3, &nm, "kx_im2col_patches_u8")) return KX_ERR_ARG;
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    const int g = image / patch;
+    im2col_u8_kernel<<<batch * g * g + batch, 256, 0, stream>>>(pixels, channels_last != 0, nm, batch, media, image, patch,
+                                                                reinterpret_cast<__nv_bfloat16*>(patches_bf16), k_pad,
+                                                                class_embedding, pos_table, x, dim);
+    return check_launch("kx_im2col_patches_u8");
 }
 
 extern "C" int kx_xpos_tables(const float* scale, const float* inv_freq, int T, int min_pos, float scale_base,

@@ -97,6 +97,8 @@ SIGNATURES = {
     "kx_add_positions": (_i, [_f32p, _f32p, _i, _i, _i, _f32p, _i, _vp]),
     "kx_embed_splice_pos": (_i, [_vp, _i, _i, _f32p, _i, _f32p, _i, _i, C.POINTER(_i), _i, _i, _f32p, _vp, _vp]),
     "kx_im2col_patches": (_i, [_f32p, _i, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
+    "kx_clip_normalize_u8": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f32p, _vp]),
+    "kx_im2col_patches_u8": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
     "kx_xpos_tables": (_i, [_f32p, _f32p, _i, _i, _f, _f32p, _f32p, _f32p, _f32p, _vp]),
     "kx_cast_f32_to_bf16": (_i, [_f32p, _vp, _ll, _vp]),
     "kx_broadcast_rows": (_i, [_f32p, _f32p, _ll, _i, _vp]),

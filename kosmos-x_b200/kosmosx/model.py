@@ -580,6 +580,67 @@ class _KosmosBase(nn.Module):
         self.refresh_weights()
         return r
 
+    # ---- checkpoint interchange ------------------------------------------
+    _WRAPPER_PREFIXES = ("module.", "_fsdp_wrapped_module.", "_orig_mod.")     # DDP / FSDP / torch.compile wrappers
+    _TIED = (("embed.weight", "decoder.embed_tokens.weight"),                  # Appendix B: same tensor, both keys saved
+             ("embed_positions.weight", "decoder.embed_positions.weight"),
+             ("output_projection.weight", "decoder.output_projection.weight"))
+
+    def save_checkpoint(self, path):
+        """The reference's format (train.py:688-695): ``torch.save(unwrapped_model.state_dict(), final_model.pt)``."""
+        torch.save(self.state_dict(), path)
+
+    def load_checkpoint(self, checkpoint, strict: bool = True, resize_positions: bool = False):
+        """Load a reference ``final_model.pt`` (train.py:688-695) or an already loaded state_dict.
+
+        Beyond ``load_state_dict``: wrapper prefixes left by DDP / FSDP / torch.compile are stripped; HF's legacy
+        ``embeddings.position_ids`` buffer is dropped; a tied pair saved under only one of its two names (Appendix B)
+        is completed; a plain (non-multiway) torchscale decoder checkpoint is mapped onto the live ``.A`` branches;
+        dtypes are converted by ``copy_``.  ``resize_positions`` copies the overlapping rows of a positional table of
+        another length (the reference's has 2048 rows) instead of failing.  Returns the
+        ``(missing_keys, unexpected_keys)`` result of ``load_state_dict``."""
+        if not isinstance(checkpoint, dict):
+            checkpoint = torch.load(checkpoint, map_location="cpu", weights_only=True)
+        if "state_dict" in checkpoint and isinstance(checkpoint["state_dict"], dict):
+            checkpoint = checkpoint["state_dict"]
+        own = self.state_dict()
+        sd = {}
+        for k, v in checkpoint.items():
+            for w in self._WRAPPER_PREFIXES[1:]:
+                k = k.replace(w, "")
+            while k.startswith("module."):
+                k = k[len("module."):]
+            if k.endswith("embeddings.position_ids"):
+                continue
+            sd[k] = v
+        for a, b in self._TIED:
+            if a in own and b in own:
+                if a in sd and b not in sd:
+                    sd[b] = sd[a]
+                elif b in sd and a not in sd:
+                    sd[a] = sd[b]
+        plain = {}
+        for k, v in sd.items():                          # non-multiway torchscale layer: x.weight -> x.A.weight
+            if k not in own and k.startswith("decoder.layers."):
+                head, _, leaf = k.rpartition(".")
+                for cand in (f"{head}.A.{leaf}",                                           # q_proj.weight -> q_proj.A.weight
+                             ".".join(head.split(".")[:-1] + ["A", head.split(".")[-1], leaf])):  # ffn.fc1.weight -> ffn.A.fc1.weight
+                    if cand in own and cand not in sd:
+                        plain[k] = cand
+                        break
+        for k, cand in plain.items():
+            sd[cand] = sd.pop(k)
+        if plain:
+            strict = False                               # the .B branches keep their initial values (never run, a17)
+        if resize_positions:
+            for k in ("embed_positions.weight", "decoder.embed_positions.weight"):
+                if k in sd and k in own and sd[k].shape != own[k].shape and sd[k].shape[1:] == own[k].shape[1:]:
+                    rows = min(sd[k].shape[0], own[k].shape[0])
+                    merged = own[k].detach().clone()
+                    merged[:rows] = sd[k][:rows].to(merged.dtype)
+                    sd[k] = merged
+        return self.load_state_dict(sd, strict=strict)
+
     def _generate(self, x0: torch.Tensor, B: int, T: int, max_new_tokens: int, forced=None, return_logits=False,
                   cuda_graph=True, one_kernel=None):
         """Greedy continuation of the embedded prompt x0 [B*T, D]: prompt pass with cache fill and
@@ -744,7 +805,8 @@ class Kosmos(_KosmosBase):
     def _vit(self, images: torch.Tensor, media: int = 1) -> torch.Tensor:
         """CLIPVisionTransformer.forward ([HF] modeling_clip.py:667-697) -> fp32 [N*Tv, Dv] (un-normalised) for the
         N = images.shape[0] images.  media > 1: `images` is (sequences*media, 3, H, W) in (sequence, media) order and
-        the output rows are media-major (image i of every sequence is one contiguous block)."""
+        the output rows are media-major (image i of every sequence is one contiguous block).  uint8 `images`
+        ((N,3,H,W) or (N,H,W,3)) are raw pixels: CLIP's rescale + normalise is fused into the patch pack."""
         cfg, vp, ws = self.cfg, self._pack_vision(), self._ws
         B = images.shape[0]
         Tv, Dv, P = cfg.vit_tokens, cfg.vit_dim, cfg.vit_tokens - 1
@@ -756,8 +818,8 @@ class Kosmos(_KosmosBase):
         qkv = ws.get("vqkv", (M, 3 * Dv), torch.bfloat16, dev)
         att = ws.get("vatt", (M, Dv), torch.bfloat16, dev)
         mid = ws.get("vmid", (M, cfg.vit_mlp), torch.bfloat16, dev)
-        ops.im2col_patches(images, patches, vp["cls"], vp["vpos"], emb.view(B, Tv, Dv), image=cfg.image, patch=cfg.patch,
-                           media=media)
+        pack = ops.im2col_patches_u8 if images.dtype == torch.uint8 else ops.im2col_patches   # uint8: raw pixels (§8(f)4)
+        pack(images, patches, vp["cls"], vp["vpos"], emb.view(B, Tv, Dv), image=cfg.image, patch=cfg.patch, media=media)
         ops.gemm(patches, vp["w_patch"], emb, grp=(P, Tv, 1), add_tab=vp["vpos"], add_off=1)
         ops.layernorm(emb, *vp["pre_ln"], x, eps=cfg.eps)                    # fp32 out: the residual stream
         act = _abi.KX_ACT_GELU if cfg.vit_act == "gelu" else _abi.KX_ACT_QUICK_GELU
@@ -822,7 +884,7 @@ class Kosmos(_KosmosBase):
     # ---- forward ------------------------------------------------------------------------
     def _forward_impl(self, text_tokens: torch.Tensor, images: torch.Tensor, logits: torch.Tensor | None = None,
                       img_rows=(2,)):
-        """images: (B*m, 3, H, W) fp32 in (sequence, image) order, m = len(img_rows)."""
+        """images: (B*m, 3, H, W) fp32 (or raw uint8, planar / channels-last) in (sequence, image) order, m = len(img_rows)."""
         cfg = self.cfg
         B, t_text = text_tokens.shape
         Lq, m = cfg.p_latents, len(img_rows)
@@ -841,14 +903,22 @@ class Kosmos(_KosmosBase):
             self._errf = f
         return f
 
-    def _prepare_inputs(self, text_tokens, images, image_positions, extra_rows=0):
-        """Argument checks shared by forward and generate -> (text_tokens, images (B*m,3,H,W) fp32, img_rows, T)."""
+    def _prepare_inputs(self, text_tokens, images, image_positions, extra_rows=0, normalize_images=False):
+        """Argument checks shared by forward and generate -> (text_tokens, images, img_rows, T).  images come back as
+        (B*m,3,H,W) fp32, or, with ``normalize_images``, as the caller's uint8 pixels (B*m,3,H,W) / (B*m,H,W,3)."""
         cfg = self.cfg
         _require_cuda(text_tokens, "text_tokens")
         _require_cuda(images, "images")
         if text_tokens.dtype != torch.int64 or text_tokens.ndim != 2:
             raise TypeError("text_tokens must be an int64 tensor of shape (B, T_text)")
-        if images.ndim not in (4, 5) or tuple(images.shape[-3:]) != (3, cfg.image, cfg.image):
+        planar = (3, cfg.image, cfg.image)
+        if normalize_images:
+            if images.dtype != torch.uint8:
+                raise TypeError("normalize_images=True takes raw uint8 pixels (CLIP rescale + normalise run on the device)")
+            shapes = (planar, (cfg.image, cfg.image, 3))
+        else:
+            shapes = (planar,)
+        if images.ndim not in (4, 5) or tuple(images.shape[-3:]) not in shapes:
             raise ValueError(f"Input image size ({tuple(images.shape[1:])}) doesn't match model "
                              f"(3, {cfg.image}, {cfg.image}).")
         if images.shape[0] != text_tokens.shape[0]:
@@ -866,19 +936,27 @@ class Kosmos(_KosmosBase):
         if T + extra_rows + 2 > cfg.max_positions:
             raise ValueError(f"spliced sequence length {T + extra_rows} exceeds the positional table: max is "
                              f"{cfg.max_positions - 2} (construct Kosmos(max_positions=...) to extend it)")
-        # HF casts pixels to the weight dtype ([HF]:208-209)
-        images = images.to(torch.float32).reshape(-1, 3, cfg.image, cfg.image).contiguous()
+        if normalize_images:
+            images = images.reshape(-1, *images.shape[-3:]).contiguous()
+        else:   # HF casts pixels to the weight dtype ([HF]:208-209)
+            images = images.to(torch.float32).reshape(-1, 3, cfg.image, cfg.image).contiguous()
         return text_tokens.contiguous(), images, img_rows, T
 
-    def forward(self, text_tokens: torch.Tensor, images: torch.Tensor, image_positions=None, **kwargs):
+    def forward(self, text_tokens: torch.Tensor, images: torch.Tensor, image_positions=None, normalize_images: bool = False,
+                **kwargs):
         """Reference call (model.py:208-253): images (B,3,H,W), features spliced in front of text token 2.
         Extension (BASELINE.json configs[4]): images (B,m,3,H,W) with ``image_positions`` = m ascending text-token
-        indices; image i's 64 feature rows are spliced in front of text token image_positions[i]."""
+        indices; image i's 64 feature rows are spliced in front of text token image_positions[i].
+        ``normalize_images=True``: images are raw uint8 pixels of the model's size, planar or
+        channels-last; the CLIPImageProcessor rescale + normalise that ``KosmosTokenizer.tokenize_images`` would have
+        applied on the host (model.py:81-97) runs inside the patch-pack kernel.  Without it a uint8 tensor is cast
+        to float as HF does ([HF]:208-209)."""
         if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):
             raise TypeError("text_tokens and images must be instances of torch.Tensor")
         cfg = self.cfg
         try:
-            text_tokens, images, img_rows, T = self._prepare_inputs(text_tokens, images, image_positions)
+            text_tokens, images, img_rows, T = self._prepare_inputs(text_tokens, images, image_positions,
+                                                                    normalize_images=normalize_images)
         except Exception as e:
             log.error(f"Failed during input validation: {e}")
             raise
@@ -895,14 +973,16 @@ class Kosmos(_KosmosBase):
 
     @torch.no_grad()
     def generate(self, text_tokens: torch.Tensor, images: torch.Tensor, max_new_tokens: int, image_positions=None,
-                 forced_tokens=None, return_logits: bool = False, cuda_graph: bool = True, one_kernel=None):
+                 forced_tokens=None, return_logits: bool = False, cuda_graph: bool = True, one_kernel=None,
+                 normalize_images: bool = False):
         """Greedy continuation (the reference stops at logits, torchscale's ``incremental_state`` is the
         decoding path it would use): vision tower -> resampler -> splice -> prompt pass with KV-cache fill, then one-token
         steps on the weight-streaming kernels.  Returns int64 (B, max_new_tokens) on the device (and the (B, n, vocab)
         logits with ``return_logits``).  New tokens continue the spliced sequence: positions T+2, T+3, ..."""
         if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):
             raise TypeError("text_tokens and images must be instances of torch.Tensor")
-        text_tokens, images, img_rows, T = self._prepare_inputs(text_tokens, images, image_positions, int(max_new_tokens))
+        text_tokens, images, img_rows, T = self._prepare_inputs(text_tokens, images, image_positions, int(max_new_tokens),
+                                                                normalize_images=normalize_images)
         cfg = self.cfg
         B, m = text_tokens.shape[0], len(img_rows)
         dp = self.decoder._pack()
@@ -924,7 +1004,7 @@ class Kosmos(_KosmosBase):
         """One captured graph per input shape and per output slot.  Two output slots alternate, so the
         logits returned by a call stay valid until the second-next call with the same shapes (lets a
         caller overlap a device->host copy of the result with the next forward)."""
-        key = (tuple(text_tokens.shape), tuple(images.shape), tuple(img_rows))
+        key = (tuple(text_tokens.shape), tuple(images.shape), images.dtype, tuple(img_rows))
         g = self._graphs.get(key)
         if g is None:
             st_tok, st_img = text_tokens.clone(), images.clone()
@@ -1018,10 +1098,87 @@ class _nullctx:
 
 
 class KosmosTokenizer:
-    """Host-side preprocessing of the reference (model.py:23-129) needs hub downloads (CLIPProcessor,
-    gpt-neox tokenizer) and is outside the accelerated path."""
+    """``kosmosx.model.KosmosTokenizer`` (reference model.py:23-129): host-side preprocessing, SURVEY.md §8(f)4.
 
-    def __init__(self, *a, **kw):
-        raise NotImplementedError(
-            "KosmosTokenizer wraps HF hub tokenizers (reference model.py:36-46) and is out of scope for the "
-            "B200 forward-path build; tokenize with the reference's own class and pass tensors to Kosmos.forward")
+    ``KosmosTokenizer()`` does what the reference does: it loads the CLIP processor and the gpt-neox tokenizer from the
+    hub (model.py:36-46) and re-raises, after ``logging.error``, when that fails (no network here).  Keyword-only
+    extras for offline use: ``tokenizer`` / ``processor`` inject already-built objects with the HF call conventions
+    (``tokenizer(texts, return_tensors="pt", padding=True, truncation=True).input_ids``,
+    ``tokenizer.convert_tokens_to_ids``, ``tokenizer.pad_token_id``, ``processor(images=..., return_tensors="pt")
+    .pixel_values``).  Attributes as in the reference: ``processor``, ``tokenizer``, ``im_idx``, ``im_end_idx``.
+
+    B200 addition: ``tokenize_images`` given a uint8 CUDA tensor of model-sized images ((N,3,H,W) or (N,H,W,3)) runs the
+    processor's rescale + normalise on the device (``kx_clip_normalize_u8``) and returns the same fp32 ``pixel_values``;
+    ``Kosmos.forward(..., normalize_images=True)`` fuses that step into the patch pack instead.  Anything else
+    (PIL images, other sizes: resize / centre crop) goes through the injected processor on the host, as in the reference.
+    """
+
+    CLIP_REPO = "laion/CLIP-ViT-L-14-laion2B-s32B-b82K"      # model.py:37
+    TEXT_REPO = "EleutherAI/gpt-neox-20b"                    # model.py:40
+    N_IMAGE_FEATURES = 64                                    # model.py:117 (dummy_image_features)
+
+    def __init__(self, *, tokenizer=None, processor=None, image_size: int = 224):
+        try:
+            if processor is None:
+                from transformers import CLIPProcessor
+                processor = CLIPProcessor.from_pretrained(self.CLIP_REPO)
+            if tokenizer is None:
+                from transformers import AutoTokenizer
+                tokenizer = AutoTokenizer.from_pretrained(
+                    self.TEXT_REPO, additional_special_tokens=["<image>", "</image>"], eos_token="<eos>",
+                    pad_token="<pad>", extra_ids=0, model_max_length=8192)
+        except Exception as e:
+            log.error(f"Failed to initialize KosmosTokenizer: {e}")
+            raise
+        self.processor = processor
+        self.tokenizer = tokenizer
+        self.image_size = image_size
+        self.im_idx, self.im_end_idx = self.tokenizer.convert_tokens_to_ids(["<image>", "</image>"])   # model.py:51-53
+
+    def _image_norm(self):
+        """(mean, std) of the processor in use (CLIPProcessor keeps them on ``.image_processor``)."""
+        ip = getattr(self.processor, "image_processor", self.processor)
+        mean, std = getattr(ip, "image_mean", None), getattr(ip, "image_std", None)
+        return (tuple(mean) if mean is not None else ops.CLIP_MEAN, tuple(std) if std is not None else ops.CLIP_STD)
+
+    def tokenize_texts(self, texts):
+        """-> (tokens with ``<image> </image>`` inserted after the first token, the text tokens alone): model.py:55-80."""
+        try:
+            texts = self.tokenizer(texts, return_tensors="pt", padding=True, truncation=True).input_ids
+            image_tokens = torch.tensor([[self.im_idx, self.im_end_idx]] * texts.shape[0], dtype=texts.dtype,
+                                        device=texts.device)
+            return torch.cat([texts[:, 0:1], image_tokens, texts[:, 1:]], dim=1), texts
+        except Exception as e:
+            log.error(f"Failed to tokenize texts: {e}")
+            raise
+
+    def tokenize_images(self, images):
+        """-> fp32 ``pixel_values`` (N,3,H,W): model.py:82-97.  uint8 CUDA tensors of the model's size are normalised on
+        the device; everything else is the processor's job."""
+        try:
+            if isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8:
+                mean, std = self._image_norm()
+                return ops.clip_normalize_u8(images.contiguous(), image=self.image_size, mean=mean, std=std)
+            return self.processor(images=images, return_tensors="pt").pixel_values
+        except Exception as e:
+            log.error(f"Failed to tokenize images: {e}")
+            raise
+
+    def tokenize(self, sample):
+        """{"target_text", "image"} -> {"text_tokens", "images", "labels", "attention_mask"}: model.py:99-129, including the
+        reference's mask layout (64 ones in FRONT of the text mask although the features are spliced after token 1,
+        SURVEY.md Appendix C item 4; ``Kosmos.forward`` ignores the mask either way)."""
+        try:
+            text_tokens, only_text_tokens = self.tokenize_texts(sample["target_text"])
+            attention_mask = text_tokens != self.tokenizer.pad_token_id
+            dummy_image_features = torch.ones((text_tokens.shape[0], self.N_IMAGE_FEATURES), device=text_tokens.device)
+            attention_mask = torch.cat([dummy_image_features, attention_mask], dim=1)
+            return {
+                "text_tokens": text_tokens,
+                "images": self.tokenize_images(sample["image"]),
+                "labels": only_text_tokens,
+                "attention_mask": attention_mask,
+            }
+        except Exception as e:
+            log.error(f"Failed to tokenize sample: {e}")
+            raise

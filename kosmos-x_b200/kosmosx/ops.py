@@ -1,6 +1,8 @@
 """Thin Python wrappers over the C ABI: tensors in, raw pointers out.  No arithmetic here."""
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _abi
@@ -379,6 +381,55 @@ def add_positions(x_in, x_out, pos_table):
     check(lib.kx_add_positions(x_in.data_ptr(), x_out.data_ptr(), B, T, D, pos_table.data_ptr(), pos_table.shape[0],
                                _stream()), "kx_add_positions")
     return x_out
+
+
+# CLIPImageProcessor defaults of the reference's checkpoint (laion/CLIP-ViT-L-14-laion2B-s32B-b82K, model.py:36-38):
+# OPENAI_CLIP_MEAN / OPENAI_CLIP_STD of HF image_utils.py
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def _u8_layout(pixels, image):
+    """(N,3,H,W) -> 0, (N,H,W,3) -> 1 for a contiguous uint8 tensor of model-sized images."""
+    _req(pixels, torch.uint8, "pixels")
+    if pixels.ndim != 4 or not pixels.is_contiguous():
+        raise ValueError("uint8 pixels must be a contiguous 4-D tensor")
+    if tuple(pixels.shape[1:]) == (3, image, image):
+        return 0
+    if tuple(pixels.shape[1:]) == (image, image, 3):
+        return 1
+    raise ValueError(f"uint8 pixels must be (N,3,{image},{image}) or (N,{image},{image},3), got {tuple(pixels.shape)}")
+
+
+def _f3(v, what):
+    if len(v) != 3:
+        raise ValueError(f"{what} needs 3 channel values")
+    return (C.c_float * 3)(*[float(a) for a in v])
+
+
+def clip_normalize_u8(pixels, out=None, *, image, mean=CLIP_MEAN, std=CLIP_STD):
+    """uint8 (N,3,H,W) / (N,H,W,3) -> fp32 pixel_values (N,3,H,W): CLIPImageProcessor's rescale + normalise
+    (reference model.py:81-97) on the device, for images that already have the model's size."""
+    cl = _u8_layout(pixels, image)
+    if out is None:
+        out = torch.empty(pixels.shape[0], 3, image, image, dtype=torch.float32, device=pixels.device)
+    _req(out, torch.float32, "pixel_values")
+    with _Timed("clip_normalize", 0.0, 5.0 * pixels.numel()):
+        check(lib.kx_clip_normalize_u8(pixels.data_ptr(), cl, pixels.shape[0], image, _f3(mean, "mean"), _f3(std, "std"),
+                                       out.data_ptr(), _stream()), "kx_clip_normalize_u8")
+    return out
+
+
+def im2col_patches_u8(pixels, patches, class_embedding, pos_table, x, *, image, patch, media=1, mean=CLIP_MEAN,
+                      std=CLIP_STD):
+    """im2col_patches with clip_normalize_u8 fused in front: uint8 pixels, N = sequences*media in (sequence, media) order."""
+    cl = _u8_layout(pixels, image)
+    with _Timed("im2col", 0.0, 3.0 * pixels.numel()):
+        check(lib.kx_im2col_patches_u8(pixels.data_ptr(), cl, _f3(mean, "mean"), _f3(std, "std"), pixels.shape[0], media,
+                                       image, patch, patches.data_ptr(), patches.shape[1], class_embedding.data_ptr(),
+                                       pos_table.data_ptr(), x.data_ptr(), x.shape[-1], _stream()),
+              "kx_im2col_patches_u8")
+    return patches
 
 
 def im2col_patches(pixels, patches, class_embedding, pos_table, x, *, image, patch, media=1):

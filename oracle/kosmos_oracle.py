@@ -684,6 +684,42 @@ class KosmosLanguageOracle(nn.Module):
 
 
 # --------------------------------------------------------------------------- helpers
+# --------------------------------------------------------------------------- host preprocessing
+OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)     # HF image_utils.py; the laion ViT-L/14 processor's values
+OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def clip_preprocess_u8(pixels, channels_last: bool = False, mean=OPENAI_CLIP_MEAN, std=OPENAI_CLIP_STD) -> torch.Tensor:
+    """``KosmosTokenizer.tokenize_images`` (reference model.py:82-97 -> ``CLIPProcessor``, transformers 4.35 slow
+    image processor) for uint8 images that already have the model's size, so that resize / centre crop are
+    identities: ``rescale`` = uint8 -> float64, * (1/255), -> float32; ``normalize`` = (x - mean) / std in float32
+    (HF image_transforms.py ``rescale`` / ``normalize``; tests/test_oracle.py pins this function bit for bit
+    against those two functions of the installed transformers, and to 1e-6 against ``CLIPImageProcessor``).
+    pixels: uint8 (N,3,H,W), or (N,H,W,3) with ``channels_last``.  -> fp32 pixel_values (N,3,H,W)."""
+    import numpy as np
+    a = pixels.cpu().numpy() if isinstance(pixels, torch.Tensor) else np.asarray(pixels)
+    assert a.dtype == np.uint8 and a.ndim == 4
+    if channels_last:
+        a = a.transpose(0, 3, 1, 2)
+    x = (a.astype(np.float64) * (1 / 255)).astype(np.float32)
+    m = np.array(mean, dtype=np.float32).reshape(1, 3, 1, 1)
+    s = np.array(std, dtype=np.float32).reshape(1, 3, 1, 1)
+    return torch.from_numpy(np.ascontiguousarray((x - m) / s))
+
+
+def tokenize_texts(input_ids: torch.Tensor, im_idx: int, im_end_idx: int):
+    """``KosmosTokenizer.tokenize_texts`` after the HF tokenizer call (reference model.py:68-76):
+    ``<s> <image> </image> text </s>`` -> (tokens with the two image tokens after position 0, the text tokens)."""
+    image_tokens = torch.tensor([[im_idx, im_end_idx]] * input_ids.shape[0])
+    return torch.cat([input_ids[:, 0:1], image_tokens, input_ids[:, 1:]], dim=1), input_ids
+
+
+def tokenize_attention_mask(text_tokens: torch.Tensor, pad_token_id: int, n_image_features: int = 64):
+    """The mask of ``KosmosTokenizer.tokenize`` (reference model.py:113-120): 64 ones in front of (tokens != pad)."""
+    attention_mask = text_tokens != pad_token_id
+    return torch.cat([torch.ones((text_tokens.shape[0], n_image_features)), attention_mask], dim=1)
+
+
 def make_inputs(cfg: OracleConfig, batch: int, t_text: int, seed: int = 1, n_images: int | None = None):
     """Synthetic inputs as README.md:34-37 / example.py:5-8 of the reference; n_images = m gives the
     (B, m, 3, H, W) multi-image form of config 5."""

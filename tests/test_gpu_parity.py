@@ -418,6 +418,108 @@ def test_language_model_generate_batches(tiny_cfgs):
     with pytest.raises(ValueError):
         lm.generate(torch.zeros(33, 4, dtype=torch.int64, device="cuda"), 2)
 
+# --------------------------------------------------------------------------- device-side preprocessing
+def _u8_images(n, image, channels_last, seed):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randint(0, 256, (n, 3, image, image), dtype=torch.uint8, generator=g)
+    img[0, :, :16, :16] = torch.arange(256, dtype=torch.uint8).view(1, 16, 16)      # every (value, channel) pair
+    return img.permute(0, 2, 3, 1).contiguous() if channels_last else img
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("image", [56, 224])
+def test_clip_normalize_u8_is_bit_exact_vs_oracle(image, channels_last):
+    """kx_clip_normalize_u8 against the oracle's restatement of CLIPImageProcessor's rescale + normalise (itself pinned
+    bit for bit against the installed transformers in tests/test_preprocess.py): fp32, bit-exact."""
+    import kosmos_oracle as ko
+    from kosmosx import ops
+    img = _u8_images(3, image, channels_last, seed=image)
+    want = ko.clip_preprocess_u8(img, channels_last)
+    got = ops.clip_normalize_u8(img.cuda(), image=image)
+    assert got.dtype == torch.float32 and torch.equal(got.cpu(), want)
+    # other statistics (a processor with its own image_mean / image_std)
+    mean, std = (0.5, 0.25, 0.125), (0.5, 0.3, 0.7)
+    assert torch.equal(ops.clip_normalize_u8(img.cuda(), image=image, mean=mean, std=std).cpu(),
+                       ko.clip_preprocess_u8(img, channels_last, mean, std))
+    with pytest.raises(ValueError):
+        ops.clip_normalize_u8(torch.zeros(1, 3, image, image + 4, dtype=torch.uint8, device="cuda"), image=image)
+    with pytest.raises(RuntimeError, match="std"):
+        ops.clip_normalize_u8(img.cuda(), image=image, std=(1.0, 0.0, 1.0))
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fused_u8_patch_pack_equals_normalize_then_pack(tiny_pair, channels_last):
+    """kx_im2col_patches_u8 == kx_im2col_patches(kx_clip_normalize_u8(.)) bit for bit, including the media-major slot
+    order of the multi-image form and the CLS rows."""
+    from kosmosx import ops
+    _, mine, oc = tiny_pair
+    vp = mine._pack_vision()
+    n, media = 6, 2
+    P, Tv, Dv = oc.vit_tokens - 1, oc.vit_tokens, oc.vit_dim
+    img = _u8_images(n, oc.image, channels_last, seed=11).cuda()
+    outs = []
+    for fused in (False, True):
+        patches = torch.full((n * P, vp["k_pad"]), 7.0, dtype=torch.bfloat16, device="cuda")
+        x = torch.zeros(n, Tv, Dv, dtype=torch.float32, device="cuda")
+        if fused:
+            ops.im2col_patches_u8(img, patches, vp["cls"], vp["vpos"], x, image=oc.image, patch=oc.patch, media=media)
+        else:
+            ops.im2col_patches(ops.clip_normalize_u8(img, image=oc.image), patches, vp["cls"], vp["vpos"], x,
+                               image=oc.image, patch=oc.patch, media=media)
+        outs.append((patches, x))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert outs[1][0].float().abs().max().item() > 1.0          # not all zeros: values up to (1 - mean) / std ~ 2.1
+
+
+def test_forward_on_raw_uint8_images_equals_forward_on_processor_output(tiny512_pair):
+    """Kosmos.forward(normalize_images=True) on raw pixels == Kosmos.forward on KosmosTokenizer.tokenize_images' fp32
+    pixel_values (device kernel) == the oracle fed the oracle's preprocessing, single- and multi-image, eager and
+    graph replay; generate() takes the same flag.  Without the flag uint8 is cast to float like HF does."""
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, KosmosTokenizer
+    ref, mine, oc = tiny512_pair
+
+    class _Tok:
+        pad_token_id = 1
+
+        def convert_tokens_to_ids(self, t):
+            return [oc.vocab - 2, oc.vocab - 1]
+
+    tk = KosmosTokenizer(tokenizer=_Tok(), processor=object(), image_size=oc.image)
+    text, _ = ko.make_inputs(oc, 2, 40, seed=4)
+    graphed = Kosmos(config=mine.cfg, cuda_graph=True)
+    graphed.load_state_dict(ref.state_dict())
+    graphed = graphed.cuda()
+    for m, cl, pos in ((1, True, None), (1, False, None), (3, True, [1, 7, 40])):
+        raw = _u8_images(2 * m, oc.image, cl, seed=20 + m)
+        pv = tk.tokenize_images(raw.cuda())                               # fp32 (2m,3,H,W), device kernel
+        assert torch.equal(pv.cpu(), ko.clip_preprocess_u8(raw, cl))
+        if m > 1:
+            raw, pv = raw.view(2, m, *raw.shape[1:]), pv.view(2, m, *pv.shape[1:])
+        want_mine = mine(text.cuda(), pv, image_positions=pos).clone()
+        got = mine(text.cuda(), raw.cuda(), image_positions=pos, normalize_images=True).clone()
+        assert torch.equal(got, want_mine)
+        with torch.no_grad():
+            ref.set_emulation(True)
+            want = ref(text, pv.cpu(), image_positions=pos)
+            ref.set_emulation(False)
+        e = _err(got, want)
+        print(f"raw uint8 forward m={m} channels_last={cl}: vs bf16-emulating oracle max={e[0]:.3e}")
+        assert e[0] <= TOL_EMU_TINY
+        g1 = graphed(text.cuda(), raw.cuda(), image_positions=pos, normalize_images=True).clone()
+        g2 = graphed(text.cuda(), raw.cuda(), image_positions=pos, normalize_images=True).clone()   # replay, other slot
+        assert torch.equal(g1, got) and torch.equal(g2, got)
+        t1 = mine.generate(text.cuda(), raw.cuda(), 3, image_positions=pos, normalize_images=True)
+        t2 = mine.generate(text.cuda(), pv, 3, image_positions=pos)
+        assert torch.equal(t1, t2)
+    raw = _u8_images(2, oc.image, False, seed=31)
+    assert torch.equal(mine(text.cuda(), raw.cuda()), mine(text.cuda(), raw.float().cuda()))      # [HF]:208-209 cast
+    with pytest.raises(TypeError, match="uint8"):
+        mine(text.cuda(), raw.float().cuda(), normalize_images=True)
+    with pytest.raises(ValueError, match="doesn't match model"):
+        mine(text.cuda(), torch.zeros(2, oc.image, oc.image, 3, dtype=torch.uint8, device="cuda"))   # channels-last needs the flag
+
+
 @pytest.fixture(scope="module")
 def full_pair():
     """Reference-size model (24-layer ViT-L/14 + perceiver + 24-layer d=2048 decoder), weights from the

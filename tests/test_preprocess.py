@@ -1,0 +1,133 @@
+"""Host preprocessing (reference kosmosx/model.py:23-129), CPU side: the oracle's restatement of
+CLIPImageProcessor's rescale + normalise pinned against the installed transformers, and ``KosmosTokenizer``'s
+token / mask layout with injected (offline) tokenizer and processor objects.  The device kernels are checked
+against the same oracle in tests/test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+os.environ.setdefault("HF_HUB_OFFLINE", "1")
+
+
+def _all_values(channels_last):
+    """Every (uint8 value, channel) pair at least once, plus noise: (2, 3, 16, 16) or (2, 16, 16, 3)."""
+    g = torch.Generator().manual_seed(3)
+    img = torch.randint(0, 256, (2, 3, 16, 16), dtype=torch.uint8, generator=g)
+    img[0] = torch.arange(256, dtype=torch.uint8).view(1, 16, 16)
+    return img.permute(0, 2, 3, 1).contiguous() if channels_last else img
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_oracle_preprocess_is_hf_rescale_then_normalize_bit_for_bit(channels_last):
+    """transformers.image_transforms.rescale / normalize are the functions the reference's pinned slow CLIP
+    processor calls; they are importable here, so this part of the oracle IS pinned."""
+    import kosmos_oracle as ko
+    from transformers import image_transforms as it
+    from transformers.image_utils import ChannelDimension
+    img = _all_values(channels_last)
+    fmt = ChannelDimension.LAST if channels_last else ChannelDimension.FIRST
+    want = []
+    for a in img.numpy():
+        r = it.rescale(a, 1 / 255, input_data_format=fmt)
+        n = it.normalize(r, ko.OPENAI_CLIP_MEAN, ko.OPENAI_CLIP_STD, input_data_format=fmt)
+        want.append(n.transpose(2, 0, 1) if channels_last else n)
+    want = torch.from_numpy(np.stack(want))
+    got = ko.clip_preprocess_u8(img, channels_last)
+    assert got.dtype == torch.float32 and got.shape == (2, 3, 16, 16)
+    assert torch.equal(got, want)
+
+
+def test_oracle_preprocess_matches_the_installed_clip_image_processor():
+    """End to end through ``CLIPImageProcessor`` (default = the OpenAI CLIP statistics of the laion checkpoint) at the
+    model's size, where resize and centre crop are identities: <= 2 fp32 ulp (the installed version fuses the two
+    steps), and identical once rounded to the bf16 the patch GEMM consumes."""
+    import kosmos_oracle as ko
+    from transformers import CLIPImageProcessor
+    proc = CLIPImageProcessor()
+    assert tuple(proc.image_mean) == ko.OPENAI_CLIP_MEAN and tuple(proc.image_std) == ko.OPENAI_CLIP_STD
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8, generator=g)
+    img[0, :16, :16] = torch.arange(256, dtype=torch.uint8).view(16, 16, 1)
+    want = proc(images=list(img.numpy()), return_tensors="pt").pixel_values
+    got = ko.clip_preprocess_u8(img, channels_last=True)
+    assert (got - want).abs().max().item() <= 5e-7
+    assert torch.equal(got.bfloat16(), want.bfloat16())
+
+
+class _Enc:
+    def __init__(self, ids):
+        self.input_ids = ids
+
+
+class _WordTokenizer:
+    """Offline stand-in with the HF call convention: ``<s> words </s>``, right-padded with ``<pad>``."""
+
+    def __init__(self):
+        self.vocab = {"<pad>": 1, "<s>": 0, "</s>": 2, "<image>": 900, "</image>": 901}
+        self.pad_token_id = 1
+
+    def convert_tokens_to_ids(self, toks):
+        return [self.vocab[t] for t in toks]
+
+    def __call__(self, texts, return_tensors=None, padding=False, truncation=False):
+        assert return_tensors == "pt" and padding and truncation        # the reference's arguments, model.py:69-71
+        texts = [texts] if isinstance(texts, str) else texts
+        rows = [[0] + [10 + (sum(map(ord, w)) % 800) for w in t.split()] + [2] for t in texts]
+        n = max(map(len, rows))
+        return _Enc(torch.tensor([r + [1] * (n - len(r)) for r in rows], dtype=torch.long))
+
+
+def _tokenizer(**kw):
+    from kosmosx import KosmosTokenizer
+    from transformers import CLIPImageProcessor
+    return KosmosTokenizer(tokenizer=_WordTokenizer(), processor=CLIPImageProcessor(), **kw)
+
+
+def test_tokenizer_text_layout_matches_the_reference():
+    import kosmos_oracle as ko
+    tk = _tokenizer()
+    assert (tk.im_idx, tk.im_end_idx) == (900, 901)
+    texts = ["a photo of a cat", "two dogs"]
+    both, only = tk.tokenize_texts(texts)
+    ids = tk.tokenizer(texts, return_tensors="pt", padding=True, truncation=True).input_ids
+    want_both, want_only = ko.tokenize_texts(ids, 900, 901)
+    assert torch.equal(both, want_both) and torch.equal(only, want_only)
+    assert both.shape == (2, 9) and both[:, 0].tolist() == [0, 0] and both[:, 1].tolist() == [900, 900] \
+        and both[:, 2].tolist() == [901, 901]
+    assert torch.equal(both[:, 3:], ids[:, 1:])
+
+
+def test_tokenizer_sample_dict_matches_the_reference():
+    import kosmos_oracle as ko
+    tk = _tokenizer()
+    g = torch.Generator().manual_seed(9)
+    imgs = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8, generator=g)
+    out = tk.tokenize({"target_text": ["a photo of a cat", "two dogs"], "image": list(imgs.numpy())})
+    assert set(out) == {"text_tokens", "images", "labels", "attention_mask"}
+    assert out["text_tokens"].shape == (2, 9) and out["labels"].shape == (2, 7)
+    assert out["images"].shape == (2, 3, 224, 224) and out["images"].dtype == torch.float32
+    assert (out["images"] - ko.clip_preprocess_u8(imgs, channels_last=True)).abs().max().item() <= 5e-7
+    # the reference's mask: 64 ones in FRONT, then tokens != pad (model.py:113-120)
+    mask = out["attention_mask"]
+    assert torch.equal(mask, ko.tokenize_attention_mask(out["text_tokens"], 1))
+    assert mask.shape == (2, 64 + 9) and mask[:, :64].all() and mask[0].all() and mask[1, -3:].tolist() == [0, 0, 0]
+
+
+def test_tokenizer_without_injection_fails_like_the_reference_offline(caplog):
+    """No network: the hub loads of model.py:36-46 raise; the error is logged and re-raised (model.py:47-49)."""
+    from kosmosx import KosmosTokenizer
+    with caplog.at_level("ERROR", logger="kosmosx"):
+        with pytest.raises(Exception):
+            KosmosTokenizer()
+    assert "Failed to initialize KosmosTokenizer" in caplog.text
+
+
+def test_device_preprocessing_has_no_cpu_path():
+    """uint8 pixels on the host go to the processor (reference behaviour); the device kernel is never emulated."""
+    from kosmosx import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_parity.py")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.clip_normalize_u8(torch.zeros(1, 3, 224, 224, dtype=torch.uint8), image=224)
