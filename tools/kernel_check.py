@@ -721,6 +721,14 @@ def case_bench():
     return case_bench_attn()
 
 
+def case_bench_vit():
+    """Tile-shape sweep for the ViT GEMMs (M = 8 x 257 rows, K = 1024 / 4096) and the out_proj shape."""
+    for M, N, K in ((2056, 3072, 1024), (2056, 4096, 1024), (2056, 1024, 1024), (2056, 1024, 4096), (16384, 2048, 2048)):
+        for cg, bn in ((1, 128), (1, 256), (2, 128), (2, 256)):
+            bench_gemm(M, N, K, cg, bn, iters=50)
+    return True
+
+
 def case_bench_attn():
     for B, H, T, causal in ((8, 32, 2048, True), (8, 32, 1024, True), (8, 32, 4096, True), (8, 32, 256, True),
                             (8, 16, 257, False), (1, 32, 114, True)):
@@ -933,6 +941,64 @@ def case_decode():
     ok &= bool(torch.equal(tok2, want2) and int(tok2[2]) == 40 and (keys == 0).all() and int(pos.item()) == 11)
     print(f"[{'OK' if ok else 'FAIL'}] cache fill / embed / greedy choice")
     return ok
+
+
+def _clip_ref(u8, channels_last, mean=ops.CLIP_MEAN, std=ops.CLIP_STD):
+    """HF image_transforms.rescale + normalize in plain torch: float64 multiply -> float32, float32 subtract / divide."""
+    x = u8.permute(0, 3, 1, 2) if channels_last else u8
+    x = (x.double() * (1 / 255)).float()
+    m = torch.tensor(mean, dtype=torch.float32, device=u8.device).view(1, 3, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32, device=u8.device).view(1, 3, 1, 1)
+    return ((x - m) / s).contiguous()
+
+
+def case_preprocess():
+    """CLIP rescale + normalise of raw uint8 pixels: stand-alone and fused into the patch pack, bit-exact."""
+    ok = True
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for image, patch, n, media in ((224, 14, 4, 1), (56, 14, 6, 3), (28, 7, 2, 2)):
+        for cl in (False, True):
+            u8 = torch.randint(0, 256, (n, image, image, 3) if cl else (n, 3, image, image), dtype=torch.uint8, generator=g).to(dev)
+            ref = _clip_ref(u8, cl)
+            got = ops.clip_normalize_u8(u8, image=image)
+            ok &= report(f"clip_normalize_u8 image={image} channels_last={cl}", got, ref, 0.0)
+            gp = image // patch
+            P, dim, k_pad = gp * gp, 64, (3 * patch * patch + 63) // 64 * 64
+            cls, pos = torch.randn(dim, device=dev), torch.randn(P + 1, dim, device=dev)
+            outs = []
+            for fused in (False, True):
+                patches = torch.full((n * P, k_pad), 3.0, dtype=torch.bfloat16, device=dev)
+                x = torch.zeros(n, P + 1, dim, device=dev)
+                if fused:
+                    ops.im2col_patches_u8(u8, patches, cls, pos, x, image=image, patch=patch, media=media)
+                else:
+                    ops.im2col_patches(ref, patches, cls, pos, x, image=image, patch=patch, media=media)
+                outs.append((patches, x))
+            ok &= report(f"im2col_patches_u8 image={image} media={media} channels_last={cl}", outs[1][0], outs[0][0], 0.0)
+            ok &= report(f"  CLS rows", outs[1][1].view(n, -1), outs[0][1].view(n, -1), 0.0)
+    return ok
+
+
+def case_bench_preprocess():
+    """Achieved HBM bandwidth of the preprocessing kernels at the model's size (algorithmic bytes: uint8 in + output)."""
+    image, patch, dim, k_pad = 224, 14, 1024, 640
+    P = (image // patch) ** 2
+    for n in (8, 64, 512):
+        for cl in (False, True):
+            u8 = torch.randint(0, 256, (n, image, image, 3) if cl else (n, 3, image, image), dtype=torch.uint8, device=dev)
+            out = torch.empty(n, 3, image, image, device=dev)
+            patches = torch.empty(n * P, k_pad, dtype=torch.bfloat16, device=dev)
+            x = torch.empty(n, P + 1, dim, device=dev)
+            cls, pos = torch.randn(dim, device=dev), torch.randn(P + 1, dim, device=dev)
+            t_n = _time(lambda: ops.clip_normalize_u8(u8, out, image=image), iters=20)
+            t_f = _time(lambda: ops.im2col_patches_u8(u8, patches, cls, pos, x, image=image, patch=patch), iters=20)
+            t_p = _time(lambda: ops.im2col_patches(out, patches, cls, pos, x, image=image, patch=patch), iters=20)
+            b_n = u8.numel() * 5
+            b_f = u8.numel() + patches.numel() * 2
+            b_p = out.numel() * 4 + patches.numel() * 2
+            print(f"preprocess N={n} channels_last={cl}: normalize {t_n*1e3:7.1f} us ({b_n/t_n/1e6:6.0f} GB/s)  "
+                  f"fused u8 pack {t_f*1e3:7.1f} us ({b_f/t_f/1e6:6.0f} GB/s)  fp32 pack {t_p*1e3:7.1f} us ({b_p/t_p/1e6:6.0f} GB/s)")
+    return True
 
 
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
