@@ -169,6 +169,8 @@ int kx_add_positions(const float* in, float* out, int batch, int T, int dim, con
  * x[b, 0, :] = class_embedding + pos[0] written into the fp32 token buffer x [B, 1+gh*gw, dim].
  * media > 1: pixels are (B/media, media, 3, H, W) and output slot i*(B/media) + s holds image i of
  * sequence s (media-major), so that each image index is one contiguous row block downstream.
+ * image % 4 == 0; pixels and patches_bf16 16-byte aligned (one CTA stages a strip of `patch` pixel rows in
+ * shared memory with 16-byte loads and writes the patch rows as 16-byte chunks).
  */
 int kx_im2col_patches(const float* pixels, int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
                       const float* class_embedding, const float* pos_table, float* x, int dim, kx_stream_t stream);
@@ -183,7 +185,8 @@ int kx_clip_normalize_u8(const unsigned char* pixels, int channels_last, int bat
                          const float* std3, float* pixel_values, kx_stream_t stream);
 
 /* kx_clip_normalize_u8 fused into kx_im2col_patches: uint8 pixels -> normalised bf16 patch rows + CLS rows; the
- * result is bit-identical to kx_im2col_patches applied to kx_clip_normalize_u8's output.  media as there. */
+ * result is bit-identical to kx_im2col_patches applied to kx_clip_normalize_u8's output.  media and shape rules as
+ * there; pixels 4-byte aligned. */
 int kx_im2col_patches_u8(const unsigned char* pixels, int channels_last, const float* mean3, const float* std3, int batch,
                          int media, int image, int patch, void* patches_bf16, int k_pad, const float* class_embedding,
                          const float* pos_table, float* x, int dim, kx_stream_t stream);

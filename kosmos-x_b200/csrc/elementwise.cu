@@ -245,36 +245,6 @@ embed_splice_pos_kernel(const long long* __restrict__ tokens, int t_text, const 
     }
 }
 
-// ----------------------------------------------------------------------------- CLIP patch im2col + CLS rows
-__global__ void __launch_bounds__(256)
-im2col_kernel(const float* __restrict__ pixels, int batch, int media, int image, int patch, __nv_bfloat16* __restrict__ patches,
-              int k_pad, const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x, int dim) {
-    const int g = image / patch;
-    const int n_patch_rows = batch * g * g;
-    if (blockIdx.x < n_patch_rows) {
-        const int slot = blockIdx.x / (g * g);                // output image slot, media-major: slot = i * (batch/media) + seq
-        const int pi = blockIdx.x - slot * g * g;
-        const int seqs = batch / media;
-        const int b = (slot % seqs) * media + slot / seqs;    // source image: pixels are (seq, media, 3, H, W)
-        const int py = pi / g, px = pi - py * g;
-        const int pp = patch * patch;
-        __nv_bfloat16* o = patches + static_cast<long long>(blockIdx.x) * k_pad;
-        for (int k = threadIdx.x; k < k_pad; k += blockDim.x) {
-            float val = 0.f;
-            if (k < 3 * pp) {
-                const int c = k / pp, r = k - c * pp;
-                const int dy = r / patch, dx = r - dy * patch;
-                val = pixels[((static_cast<long long>(b) * 3 + c) * image + (py * patch + dy)) * image + px * patch + dx];
-            }
-            o[k] = __float2bfloat16_rn(val);
-        }
-    } else {
-        const int b = blockIdx.x - n_patch_rows;
-        float* o = x + static_cast<long long>(b) * (g * g + 1) * dim;
-        for (int i = threadIdx.x; i < dim; i += blockDim.x) o[i] = cls[i] + pos[i];
-    }
-}
-
 // ----------------------------------------------------------------------------- CLIP pixel preprocessing on device
 // CLIPImageProcessor's rescale + normalise for images that already have the model's size (SURVEY.md §8(f)4;
 // reference call site kosmosx/model.py:81-97; HF 4.35 image_transforms.py rescale(): uint8 * (1/255) in float64,
@@ -293,6 +263,16 @@ __device__ __forceinline__ float clip_pixel(unsigned char u, float mean, float s
     return __fdiv_rn(__fsub_rn(r, mean), std);
 }
 
+// 3 x 256 table of clip_pixel for one CTA: every later conversion is a shared-memory lookup of the same values
+// (the float64 multiply and the IEEE divide would otherwise bound these kernels, not HBM)
+__device__ __forceinline__ void build_clip_lut(float* lut, const ClipNorm& nm) {
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8;
+        lut[i] = clip_pixel(static_cast<unsigned char>(i & 255), pick3(nm.mean, c), pick3(nm.std, c));
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ long long u8_index(int channels_last, long long b, int c, int y, int x, int image) {
     return channels_last ? ((b * image + y) * image + x) * 3 + c : ((b * 3 + c) * image + y) * image + x;
 }
@@ -302,6 +282,8 @@ __device__ __forceinline__ long long u8_index(int channels_last, long long b, in
 __global__ void __launch_bounds__(256)
 clip_normalize_u8_kernel(const unsigned char* __restrict__ pixels, int channels_last, long long n_quads, int image, ClipNorm nm,
                          float* __restrict__ out) {
+    __shared__ float lut[768];
+    build_clip_lut(lut, nm);
     const int plane4 = image * image / 4;
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n_quads; i += gridDim.x * 256ll) {
         const long long bc = i / plane4;
@@ -309,49 +291,115 @@ clip_normalize_u8_kernel(const unsigned char* __restrict__ pixels, int channels_
         const long long b = bc / 3;
         const int c = static_cast<int>(bc - b * 3);
         const int y = r / image, x = r - y * image;            // image % 4 == 0: the 4 pixels share a row
-        const float mu = pick3(nm.mean, c), sd = pick3(nm.std, c);
+        const float* t = lut + (c << 8);
         float4 v;
         if (channels_last) {
             const unsigned char* p = pixels + u8_index(1, b, c, y, x, image);
-            v = make_float4(clip_pixel(p[0], mu, sd), clip_pixel(p[3], mu, sd), clip_pixel(p[6], mu, sd), clip_pixel(p[9], mu, sd));
+            v = make_float4(t[p[0]], t[p[3]], t[p[6]], t[p[9]]);
         } else {
             const uchar4 q = *reinterpret_cast<const uchar4*>(pixels + u8_index(0, b, c, y, x, image));
-            v = make_float4(clip_pixel(q.x, mu, sd), clip_pixel(q.y, mu, sd), clip_pixel(q.z, mu, sd), clip_pixel(q.w, mu, sd));
+            v = make_float4(t[q.x], t[q.y], t[q.z], t[q.w]);
         }
         reinterpret_cast<float4*>(out)[i] = v;
     }
 }
 
-// The same arithmetic fused into the patch pack: uint8 pixels -> normalised bf16 im2col rows + CLS rows, so the
-// fp32 pixel_values tensor never exists in HBM (0.15 MB read per image instead of 0.6 MB written and read back).
+// ----------------------------------------------------------------------------- CLIP patch im2col + CLS rows
+// Patch pack for the conv-as-GEMM patch embedding ([HF]:202-218), one CTA per strip of `patch` pixel rows of one image
+// (image/patch patches): the strip is read once with coalesced 16-byte (fp32) / 4-byte (uint8) loads into shared memory
+// as fp32 [c][dy][x] (uint8 through a per-CTA 3 x 256 table of the normalised values); then every patch row (k = c*p*p + dy*p + dx, zero padded to k_pad) is written as 16-byte chunks of
+// 8 bf16, consecutive threads on consecutive chunks.  The k -> strip offset map is built once per CTA (no per-element
+// divisions).  MODE 0: fp32 pixel_values (N,3,H,W).  MODE 1 / 2: raw uint8 pixels, planar / channels-last, with the
+// rescale + normalise above fused in - the fp32 pixel_values tensor never exists in HBM.
+// Blocks past the strips write the CLS rows x[b, 0, :] = class_embedding + pos[0].
+template <int MODE>
 __global__ void __launch_bounds__(256)
-im2col_u8_kernel(const unsigned char* __restrict__ pixels, int channels_last, ClipNorm nm, int batch, int media, int image,
-                 int patch, __nv_bfloat16* __restrict__ patches, int k_pad, const float* __restrict__ cls,
-                 const float* __restrict__ pos, float* __restrict__ x, int dim) {
+im2col_strip_kernel(const void* __restrict__ pixels_, ClipNorm nm, int batch, int media, int image, int patch,
+                    __nv_bfloat16* __restrict__ patches, int k_pad, const float* __restrict__ cls,
+                    const float* __restrict__ pos, float* __restrict__ x, int dim) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int g = image / patch;
-    const int n_patch_rows = batch * g * g;
-    if (blockIdx.x < n_patch_rows) {
-        const int slot = blockIdx.x / (g * g);                // media-major output slot, as in im2col_kernel
-        const int pi = blockIdx.x - slot * g * g;
-        const int seqs = batch / media;
-        const int b = (slot % seqs) * media + slot / seqs;
-        const int py = pi / g, px = pi - py * g;
-        const int pp = patch * patch;
-        __nv_bfloat16* o = patches + static_cast<long long>(blockIdx.x) * k_pad;
-        for (int k = threadIdx.x; k < k_pad; k += blockDim.x) {
-            float val = 0.f;
-            if (k < 3 * pp) {
-                const int c = k / pp, r = k - c * pp;
-                const int dy = r / patch, dx = r - dy * patch;
-                val = clip_pixel(pixels[u8_index(channels_last, b, c, py * patch + dy, px * patch + dx, image)],
-                                 pick3(nm.mean, c), pick3(nm.std, c));
-            }
-            o[k] = __float2bfloat16_rn(val);
-        }
-    } else {
-        const int b = blockIdx.x - n_patch_rows;
+    const int n_strips = batch * g;
+    if (static_cast<int>(blockIdx.x) >= n_strips) {
+        const int b = blockIdx.x - n_strips;
         float* o = x + static_cast<long long>(b) * (g * g + 1) * dim;
         for (int i = threadIdx.x; i < dim; i += blockDim.x) o[i] = cls[i] + pos[i];
+        return;
+    }
+    const int strip_elems = 3 * patch * image;                // fp32 strip [3][patch][image]
+    float* strip = reinterpret_cast<float*>(smem_raw);
+    int* kmap = reinterpret_cast<int*>(strip + strip_elems);  // k -> offset of (c, dy, dx) inside the strip, -1 = padding
+    float* lut = reinterpret_cast<float*>(kmap + k_pad);       // MODE 1 / 2 only
+    if constexpr (MODE != 0) build_clip_lut(lut, nm);
+    const int slot = blockIdx.x / g;                          // output image slot, media-major: slot = i * (batch/media) + seq
+    const int py = blockIdx.x - slot * g;
+    const int seqs = batch / media;
+    const long long b = (slot % seqs) * media + slot / seqs;  // source image: pixels are (seq, media, ...)
+    const int pp = patch * patch;
+    for (int k = threadIdx.x; k < k_pad; k += blockDim.x) {
+        int off = -1;
+        if (k < 3 * pp) {
+            const int c = k / pp, r = k - c * pp;
+            const int dy = r / patch, dx = r - dy * patch;
+            off = (c * patch + dy) * image + dx;
+        }
+        kmap[k] = off;
+    }
+    const int row4 = image >> 2;                              // image % 4 == 0 (checked on the host)
+    if constexpr (MODE == 0) {
+        const float* px = reinterpret_cast<const float*>(pixels_);
+        for (int i = threadIdx.x; i < 3 * patch * row4; i += blockDim.x) {
+            const int r = i / row4, q = i - r * row4;         // r = c * patch + dy
+            const int c = r / patch, dy = r - c * patch;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(px + ((b * 3 + c) * image + py * patch + dy) * image) + q);
+            reinterpret_cast<float4*>(strip)[i] = v;
+        }
+    } else if constexpr (MODE == 1) {
+        const unsigned char* px = reinterpret_cast<const unsigned char*>(pixels_);
+        for (int i = threadIdx.x; i < 3 * patch * row4; i += blockDim.x) {
+            const int r = i / row4, q = i - r * row4;
+            const int c = r / patch, dy = r - c * patch;
+            const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(px + ((b * 3 + c) * image + py * patch + dy) * image) + q);
+            const float* t = lut + (c << 8);
+            reinterpret_cast<float4*>(strip)[i] = make_float4(t[u.x], t[u.y], t[u.z], t[u.w]);
+        }
+    } else {
+        // channels-last: the strip is one contiguous run of patch * image * 3 bytes (a multiple of 4)
+        const unsigned char* px = reinterpret_cast<const unsigned char*>(pixels_) + (b * image + py * patch) * image * 3;
+        const int row_bytes = image * 3;
+        for (int w = threadIdx.x; w < (patch * row_bytes) >> 2; w += blockDim.x) {
+            const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(px) + w);
+            const unsigned char bytes[4] = {u.x, u.y, u.z, u.w};
+            int j = w << 2;
+            int dy = j / row_bytes;
+            int rem = j - dy * row_bytes;
+            int xx = rem / 3, c = rem - xx * 3;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                strip[(c * patch + dy) * image + xx] = lut[(c << 8) + bytes[e]];
+                if (++c == 3) { c = 0; if (++xx == image) { xx = 0; ++dy; } }
+            }
+        }
+    }
+    __syncthreads();
+    const int chunks = k_pad >> 3;
+    __nv_bfloat16* out = patches + (static_cast<long long>(slot) * g * g + static_cast<long long>(py) * g) * k_pad;
+    for (int i = threadIdx.x; i < g * chunks; i += blockDim.x) {
+        const int pxi = i / chunks, j = i - pxi * chunks;
+        const float* src = strip + pxi * patch;
+        const int* km = kmap + (j << 3);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int off = km[e];
+            v[e] = off >= 0 ? src[off] : 0.f;
+        }
+        uint4 o;
+        o.x = pack_bf16(v[0], v[1]);
+        o.y = pack_bf16(v[2], v[3]);
+        o.z = pack_bf16(v[4], v[5]);
+        o.w = pack_bf16(v[6], v[7]);
+        reinterpret_cast<uint4*>(out + static_cast<long long>(pxi) * k_pad)[j] = o;
     }
 }
 
@@ -498,22 +546,6 @@ extern "C" int kx_add_positions(const float* in, float* out, int batch, int T, i
     return check_launch("kx_add_positions");
 }
 
-extern "C" int kx_im2col_patches(const float* pixels, int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
-                                 const float* class_embedding, const float* pos_table, float* x, int dim,
-                                 cudaStream_t stream) {
-    if (!pixels || !patches_bf16 || !class_embedding || !pos_table || !x) { set_error("kx_im2col_patches: null pointer"); return KX_ERR_ARG; }
-    if (batch <= 0 || media <= 0 || batch % media || patch <= 0 || image % patch || k_pad < 3 * patch * patch || (k_pad % 8)) {
-        set_error("kx_im2col_patches: bad shape (image=%d patch=%d k_pad=%d)", image, patch, k_pad);
-        return KX_ERR_ARG;
-    }
-    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    const int g = image / patch;
-    im2col_kernel<<<batch * g * g + batch, 256, 0, stream>>>(pixels, batch, media, image, patch,
-                                                             reinterpret_cast<__nv_bfloat16*>(patches_bf16), k_pad,
-                                                             class_embedding, pos_table, x, dim);
-    return check_launch("kx_im2col_patches");
-}
-
 static bool clip_norm_from_host(const float* mean3, const float* std3, ClipNorm* nm, const char* what) {
     if (!mean3 || !std3) { set_error("%s: null mean / std", what); return false; }
     for (int c = 0; c < 3; ++c) {
@@ -544,23 +576,59 @@ extern "C" int kx_clip_normalize_u8(const unsigned char* pixels, int channels_la
     return check_launch("kx_clip_normalize_u8");
 }
 
+// shared launch of the strip kernel: mode 0 fp32 planar, 1 uint8 planar, 2 uint8 channels-last
+static int launch_im2col(const char* what, int mode, const void* pixels, const ClipNorm& nm, int batch, int media, int image,
+                         int patch, void* patches_bf16, int k_pad, const float* class_embedding, const float* pos_table,
+                         float* x, int dim, cudaStream_t stream) {
+    if (!pixels || !patches_bf16 || !class_embedding || !pos_table || !x) { set_error("%s: null pointer", what); return KX_ERR_ARG; }
+    if (batch <= 0 || media <= 0 || batch % media || patch <= 0 || image % patch || (image % 4) || k_pad < 3 * patch * patch ||
+        (k_pad % 8)) {
+        set_error("%s: bad shape (image=%d patch=%d k_pad=%d; image %% patch == 0, image %% 4 == 0, k_pad %% 8 == 0)", what, image,
+                  patch, k_pad);
+        return KX_ERR_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(pixels) & (mode == 0 ? 15 : 3)) || (reinterpret_cast<uintptr_t>(patches_bf16) & 15)) {
+        set_error("%s: pixels must be %d-byte aligned and the patch rows 16-byte aligned", what, mode == 0 ? 16 : 4);
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    const size_t smem = static_cast<size_t>(3) * patch * image * sizeof(float) + static_cast<size_t>(k_pad) * sizeof(int) +
+                        (mode != 0 ? 768 * sizeof(float) : 0);
+    if (smem > 200 * 1024) { set_error("%s: a %d-row strip of a %d-wide image does not fit in shared memory", what, patch, image); return KX_ERR_ARG; }
+    const int g = image / patch;
+    const unsigned blocks = static_cast<unsigned>(batch * g + batch);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(patches_bf16);
+    cudaError_t e = cudaSuccess;
+#define KX_IM2COL(MODE_)                                                                                                     \
+    {                                                                                                                        \
+        if (smem > 48 * 1024)                                                                                                \
+            e = cudaFuncSetAttribute(im2col_strip_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        if (e == cudaSuccess)                                                                                                \
+            im2col_strip_kernel<MODE_><<<blocks, 256, smem, stream>>>(pixels, nm, batch, media, image, patch, out, k_pad,    \
+                                                                      class_embedding, pos_table, x, dim);                   \
+    }
+    if (mode == 0) KX_IM2COL(0) else if (mode == 1) KX_IM2COL(1) else KX_IM2COL(2)
+#undef KX_IM2COL
+    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute failed: %s", what, cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
+    return check_launch(what);
+}
+
+extern "C" int kx_im2col_patches(const float* pixels, int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
+                                 const float* class_embedding, const float* pos_table, float* x, int dim,
+                                 cudaStream_t stream) {
+    ClipNorm nm = {{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+    return launch_im2col("kx_im2col_patches", 0, pixels, nm, batch, media, image, patch, patches_bf16, k_pad, class_embedding,
+                         pos_table, x, dim, stream);
+}
+
 extern "C" int kx_im2col_patches_u8(const unsigned char* pixels, int channels_last, const float* mean3, const float* std3,
                                     int batch, int media, int image, int patch, void* patches_bf16, int k_pad,
                                     const float* class_embedding, const float* pos_table, float* x, int dim,
                                     cudaStream_t stream) {
-    if (!pixels || !patches_bf16 || !class_embedding || !pos_table || !x) { set_error("kx_im2col_patches_u8: null pointer"); return KX_ERR_ARG; }
-    if (batch <= 0 || media <= 0 || batch % media || patch <= 0 || image % patch || k_pad < 3 * patch * patch || (k_pad % 8)) {
-        set_error("kx_im2col_patches_u8: bad shape (image=%d patch=%d k_pad=%d)", image, patch, k_pad);
-        return KX_ERR_ARG;
-    }
     ClipNorm nm;
     if (!clip_norm_from_host(mean3, std3, &nm, "kx_im2col_patches_u8")) return KX_ERR_ARG;
-    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    const int g = image / patch;
-    im2col_u8_kernel<<<batch * g * g + batch, 256, 0, stream>>>(pixels, channels_last != 0, nm, batch, media, image, patch,
-                                                                reinterpret_cast<__nv_bfloat16*>(patches_bf16), k_pad,
-                                                                class_embedding, pos_table, x, dim);
-    return check_launch("kx_im2col_patches_u8");
+    return launch_im2col("kx_im2col_patches_u8", channels_last ? 2 : 1, pixels, nm, batch, media, image, patch, patches_bf16, k_pad,
+                         class_embedding, pos_table, x, dim, stream);
 }
 
 extern "C" int kx_xpos_tables(const float* scale, const float* inv_freq, int T, int min_pos, float scale_base,

@@ -411,6 +411,8 @@ def clip_normalize_u8(pixels, out=None, *, image, mean=CLIP_MEAN, std=CLIP_STD):
     """uint8 (N,3,H,W) / (N,H,W,3) -> fp32 pixel_values (N,3,H,W): CLIPImageProcessor's rescale + normalise
     (reference model.py:81-97) on the device, for images that already have the model's size."""
     cl = _u8_layout(pixels, image)
+    if pixels.data_ptr() % 4:
+        pixels = pixels.clone()
     if out is None:
         out = torch.empty(pixels.shape[0], 3, image, image, dtype=torch.float32, device=pixels.device)
     _req(out, torch.float32, "pixel_values")
@@ -424,6 +426,8 @@ def im2col_patches_u8(pixels, patches, class_embedding, pos_table, x, *, image, 
                       std=CLIP_STD):
     """im2col_patches with clip_normalize_u8 fused in front: uint8 pixels, N = sequences*media in (sequence, media) order."""
     cl = _u8_layout(pixels, image)
+    if pixels.data_ptr() % 4:
+        pixels = pixels.clone()                       # an offset view: the kernel reads 4-byte words
     with _Timed("im2col", 0.0, 3.0 * pixels.numel()):
         check(lib.kx_im2col_patches_u8(pixels.data_ptr(), cl, _f3(mean, "mean"), _f3(std, "std"), pixels.shape[0], media,
                                        image, patch, patches.data_ptr(), patches.shape[1], class_embedding.data_ptr(),
@@ -435,6 +439,8 @@ def im2col_patches_u8(pixels, patches, class_embedding, pos_table, x, *, image, 
 def im2col_patches(pixels, patches, class_embedding, pos_table, x, *, image, patch, media=1):
     """pixels fp32 (N,3,H,W), N = sequences*media in (sequence, media) order; output slots are media-major."""
     _req(pixels, torch.float32, "pixels")
+    if pixels.data_ptr() % 16:
+        pixels = pixels.clone()                       # an offset view: the kernel reads 16-byte vectors
     with _Timed("im2col", 0.0, 6.0 * pixels.numel()):
         check(lib.kx_im2col_patches(pixels.data_ptr(), pixels.shape[0], media, image, patch, patches.data_ptr(),
                                     patches.shape[1], class_embedding.data_ptr(), pos_table.data_ptr(), x.data_ptr(),

@@ -975,6 +975,10 @@ def case_preprocess():
                     ops.im2col_patches(ref, patches, cls, pos, x, image=image, patch=patch, media=media)
                 outs.append((patches, x))
             ok &= report(f"im2col_patches_u8 image={image} media={media} channels_last={cl}", outs[1][0], outs[0][0], 0.0)
+            pm = ref.view(n // media, media, 3, image, image).transpose(0, 1).reshape(n, 3, image, image)      # media-major slots
+            want = torch.nn.functional.unfold(pm, patch, stride=patch).transpose(1, 2).reshape(n * P, 3 * patch * patch)
+            ok &= report(f"  vs unfold of the normalised pixels", outs[1][0][:, :3 * patch * patch], want.bfloat16(), 0.0)
+            ok &= report(f"  padding columns", outs[1][0][:, 3 * patch * patch:], torch.zeros(n * P, k_pad - 3 * patch * patch, device=dev), 0.0)
             ok &= report(f"  CLS rows", outs[1][1].view(n, -1), outs[0][1].view(n, -1), 0.0)
     return ok
 
