@@ -962,6 +962,8 @@ class Kosmos(_KosmosBase):
             raise
         try:
             B = text_tokens.shape[0]
+            if self.training and torch.is_grad_enabled():
+                return self._forward_train(text_tokens, images, img_rows)
             if self.cuda_graph:
                 logits = self._forward_graphed(text_tokens, images, img_rows)
             else:
@@ -970,6 +972,20 @@ class Kosmos(_KosmosBase):
         except Exception as e:
             log.error(f"Failed during model forward pass: {e}")
             raise
+
+    def _forward_train(self, text_tokens, images, img_rows):
+        """``model.train()`` with grad enabled (the reference's training loop, train.py:640-657: forward, a loss written
+        in PyTorch, ``loss.backward()``, any ``torch.optim`` optimizer): the training forward of ``KosmosTrainer`` (keeps
+        the activations backward needs), returned as ONE autograd node whose backward is the hand-scheduled sm_100a
+        backward pass.  Gradients land in ``param.grad`` (views of the trainer's flat buffer) and are OVERWRITTEN by each
+        backward, not accumulated; call backward once per forward; the CLIP tower and the multiway ``.B`` branches are
+        frozen; dropout is not applied.  A ``KosmosTrainer`` built on this model beforehand is used, else one is made
+        (``KosmosTrainer(model)``: flat fp32 master / gradient buffers)."""
+        tr = getattr(self, "_trainer", None)
+        if tr is None:
+            from .train import KosmosTrainer
+            tr = KosmosTrainer(self)
+        return tr.autograd_forward(text_tokens, images, img_rows)
 
     @torch.no_grad()
     def generate(self, text_tokens: torch.Tensor, images: torch.Tensor, max_new_tokens: int, image_positions=None,

@@ -62,7 +62,10 @@ class KosmosTrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.t = 0
         self._ws = {}
+        self._fw_serial = 0                      # autograd bridge: which forward the saved activations belong to
         self._flatten(layout_only)
+        if not layout_only:
+            model._trainer = self                # Kosmos.forward in train mode builds its autograd graph on this trainer
 
     # ------------------------------------------------------------------ flat parameter / gradient buffers
     def _flatten(self, layout_only=False):
@@ -350,7 +353,9 @@ class KosmosTrainer:
         dropped = 1 + sum(1 for t in text_rows[:-1] if t + 1 in set(img_rows))
         return B * (t_text - dropped)
 
-    def _backward(self, fw, text_tokens, img_rows):
+    def _backward(self, fw, text_tokens, img_rows, dlogits_in=None):
+        """dlogits_in = None: the fused cross-entropy (loss + its gradient) starts the backward pass; otherwise the
+        caller's gradient w.r.t. the logits (B, T, V) does (the autograd bridge of ``Kosmos.forward`` in train mode)."""
         m, cfg = self.model, self.cfg
         B, T, M = fw["B"], fw["T"], fw["M"]
         D, F, H, V = cfg.dim, cfg.ffn, cfg.heads, cfg.vocab
@@ -362,8 +367,13 @@ class KosmosTrainer:
         dlogits = self._buf("dlogits", (M, Vp), bf)
         self.scalars.zero_()
         self.G.zero_()
-        ops.ce_fwd_bwd(fw["logits"], text_tokens, self.scalars[0:2], img_rows=img_rows, n_img=Lq, inv_count=1.0 / max(n_rows, 1),
-                       dlogits=dlogits, err_flag=m._err_flag())
+        if dlogits_in is None:
+            ops.ce_fwd_bwd(fw["logits"], text_tokens, self.scalars[0:2], img_rows=img_rows, n_img=Lq,
+                           inv_count=1.0 / max(n_rows, 1), dlogits=dlogits, err_flag=m._err_flag())
+        else:       # the caller's loss lives in PyTorch: one cast of its gradient into the bf16 GEMM operand (rows padded to Vp)
+            if tuple(dlogits_in.shape) != (B, T, V) or not dlogits_in.is_cuda:
+                raise ValueError(f"gradient w.r.t. the logits must be a CUDA tensor of shape {(B, T, V)}")
+            dlogits[:, :V].copy_(dlogits_in.reshape(M, V))
         dl = dlogits[:, :V]
         P = ops.ln_bwd_partials(M)
         part_d = self._buf("part_d", (3, P, D), f32)
@@ -508,6 +518,21 @@ class KosmosTrainer:
         images = images.to(torch.float32).reshape(-1, 3, cfg.image, cfg.image).contiguous()
         return text_tokens.contiguous(), images, img_rows
 
+    def attach_grads(self):
+        """Point every trained ``param.grad`` at its slice of the flat gradient buffer again (``optimizer.zero_grad()``
+        with ``set_to_none=True``, torch's default, drops the views)."""
+        for p in self.params:
+            g = self._g(p)
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g
+
+    def autograd_forward(self, text_tokens, images, img_rows):
+        """Training forward whose result is part of a PyTorch autograd graph: ``logits.backward(...)`` (through any loss
+        written in PyTorch) runs the hand-scheduled backward and leaves the gradients in ``param.grad``.  See
+        ``Kosmos.forward``."""
+        self.sync_weights()                      # an external optimizer updates the fp32 masters only
+        return _KosmosAutograd.apply(self.model.output_projection.weight, self, text_tokens, images, img_rows)
+
     def loss_and_grads(self, text_tokens, images, image_positions=None):
         """Forward + backward (+ all-reduce) without the optimizer: fills ``param.grad`` (views of the flat buffer,
         SUMMED over ranks) and returns the local mean loss (device scalar)."""
@@ -525,3 +550,27 @@ class KosmosTrainer:
     def grad_norm(self):
         """Global gradient norm of the last step before clipping (device scalar)."""
         return self.scalars[4]
+
+
+class _KosmosAutograd(torch.autograd.Function):
+    """Bridge between PyTorch autograd and the hand-scheduled backward: the graph has ONE node for the whole model.
+    ``anchor`` (a trained parameter) only makes the output require grad; the parameter gradients are written where the
+    trainer always writes them (the flat buffer that every ``param.grad`` views), so the node returns no gradients."""
+
+    @staticmethod
+    def forward(ctx, anchor, trainer, text_tokens, images, img_rows):
+        fw = trainer._forward(text_tokens, images, img_rows)
+        trainer._fw_serial += 1
+        ctx.trainer, ctx.fw, ctx.text_tokens, ctx.img_rows, ctx.serial = trainer, fw, text_tokens, img_rows, trainer._fw_serial
+        return fw["logits"].view(fw["B"], fw["T"], -1)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        tr = ctx.trainer
+        if ctx.fw is None or ctx.serial != tr._fw_serial:
+            raise RuntimeError("kosmosx: the activations of this forward are gone (a later forward re-used the buffers, or "
+                               "backward ran twice); call backward once, before the next training forward")
+        tr._backward(ctx.fw, ctx.text_tokens, ctx.img_rows, dlogits_in=dlogits)
+        ctx.fw = None
+        tr.attach_grads()
+        return None, None, None, None, None

@@ -153,3 +153,61 @@ def test_decoder_only_training_freezes_the_resampler():
     assert abs(loss.item() - want.item()) <= LOSS_TOL
     n, worst = _check_grads(ref, mine, trainer)
     assert n == 20 * oc.layers + 5 and mine.image_proj.weight.grad is None
+
+
+@pytest.mark.parametrize("m,positions", [(1, None), (2, [2, 17])])
+def test_pytorch_training_loop_through_autograd(m, positions):
+    """The reference's own loop shape (train.py:640-657; tests/test_kosmos.py:27-57 of the reference): ``model.train()``,
+    logits = model(...), a loss written in PyTorch, ``loss.backward()``, a stock ``torch.optim`` optimizer.  The one
+    autograd node behind the logits runs the hand-scheduled backward: gradients equal the trainer's fused-loss path and
+    the oracle's autograd, survive ``zero_grad(set_to_none=True)``, and AdamW on them reduces the loss."""
+    import kosmos_oracle as ko
+    ref, mine, trainer, oc = _pair(max_positions=512)
+    text, images = ko.make_inputs(oc, 2, 30, seed=3, n_images=None if m == 1 else m)
+    tg, ig = text.cuda(), images.cuda()
+    tgt = ko.KosmosOracle.loss_targets(text, oc.p_latents, positions, m).cuda()
+
+    def torch_loss(logits):
+        return torch.nn.functional.cross_entropy(logits.reshape(-1, oc.vocab), tgt.reshape(-1), ignore_index=-100)
+
+    fused = trainer.loss_and_grads(tg, ig, image_positions=positions).item()
+    g_fused = {id(p): p.grad.detach().clone() for p in trainer.params}
+    assert not mine(tg, ig, image_positions=positions).requires_grad            # eval mode (the default): inference path
+    mine.train()
+    with torch.no_grad():
+        assert not mine(tg, ig, image_positions=positions).requires_grad        # no_grad: inference path as well
+    opt = torch.optim.AdamW([p for p in mine.parameters() if p.requires_grad], lr=3e-3, weight_decay=0.0)
+    opt.zero_grad()                                                             # set_to_none: drops the .grad views
+    logits = mine(tg, ig, image_positions=positions)
+    assert logits.requires_grad and logits.shape == (2, 30 + m * oc.p_latents, oc.vocab)
+    loss = torch_loss(logits)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - fused) <= 1e-4
+    for p in trainer.params:
+        assert p.grad is not None and p.grad.data_ptr() == trainer._g(p).data_ptr()
+        rel = ((p.grad - g_fused[id(p)]).norm() / (g_fused[id(p)].norm() + 1e-12)).item()
+        assert rel <= 1e-2, f"autograd-bridge gradient differs from the fused-loss path: {rel:.3e}"      # bf16 dlogits either way
+    ref.zero_grad()
+    want = ref.loss(text, images, image_positions=positions)
+    want.backward()
+    assert abs(loss.item() - want.item()) <= LOSS_TOL
+    n, worst = _check_grads(ref, mine, trainer)
+    print(f"autograd bridge m={m}: loss {loss.item():.5f} (fused {fused:.5f}, oracle {want.item():.5f}); {n} tensors, worst rel {worst[0]:.3e} ({worst[1]})")
+    with pytest.raises(RuntimeError, match="activations of this forward are gone"):
+        loss2 = torch_loss(mine(tg, ig, image_positions=positions))
+        mine(tg, ig, image_positions=positions)                                 # a later forward re-uses the buffers
+        loss2.backward()
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = torch_loss(mine(tg, ig, image_positions=positions))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print("torch.optim.AdamW through the bridge:", " ".join(f"{x:.3f}" for x in losses))
+    assert losses[-1] < losses[0] - 1.0
+    mine.eval()
+    trainer.sync_weights()          # the external optimizer moved the fp32 masters after the last bridge forward synced
+    ce = torch_loss(mine(tg, ig, image_positions=positions).float())             # the inference path sees the updated weights
+    assert abs(ce.item() - trainer.loss_and_grads(tg, ig, image_positions=positions).item()) < 3e-2
