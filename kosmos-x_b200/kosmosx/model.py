@@ -977,8 +977,8 @@ class Kosmos(_KosmosBase):
         """``model.train()`` with grad enabled (the reference's training loop, train.py:640-657: forward, a loss written
         in PyTorch, ``loss.backward()``, any ``torch.optim`` optimizer): the training forward of ``KosmosTrainer`` (keeps
         the activations backward needs), returned as ONE autograd node whose backward is the hand-scheduled sm_100a
-        backward pass.  Gradients land in ``param.grad`` (views of the trainer's flat buffer) and are OVERWRITTEN by each
-        backward, not accumulated; call backward once per forward; the CLIP tower and the multiway ``.B`` branches are
+        backward pass.  Gradients land in ``param.grad`` (views of the trainer's flat buffer) and accumulate across
+        backward calls like autograd's do until ``zero_grad()``; call backward once per forward; the CLIP tower and the multiway ``.B`` branches are
         frozen; dropout is not applied.  A ``KosmosTrainer`` built on this model beforehand is used, else one is made
         (``KosmosTrainer(model)``: flat fp32 master / gradient buffers)."""
         tr = getattr(self, "_trainer", None)

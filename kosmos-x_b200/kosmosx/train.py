@@ -353,10 +353,17 @@ class KosmosTrainer:
         dropped = 1 + sum(1 for t in text_rows[:-1] if t + 1 in set(img_rows))
         return B * (t_text - dropped)
 
-    def _backward(self, fw, text_tokens, img_rows, dlogits_in=None):
+    def _backward(self, fw, text_tokens, img_rows, dlogits_in=None, accumulate=False):
         """dlogits_in = None: the fused cross-entropy (loss + its gradient) starts the backward pass; otherwise the
-        caller's gradient w.r.t. the logits (B, T, V) does (the autograd bridge of ``Kosmos.forward`` in train mode)."""
+        caller's gradient w.r.t. the logits (B, T, V) does (the autograd bridge of ``Kosmos.forward`` in train mode).
+        accumulate: add this pass's (all-reduced) gradient to what the flat buffer already holds (gradient accumulation
+        over micro-batches, the reference's GRADIENT_ACCUMULATE_EVERY, train.py:55,492) instead of replacing it; the kernels
+        write rather than accumulate, so the previous sum is parked in a second buffer for the duration of the pass."""
         m, cfg = self.model, self.cfg
+        g_prev = None
+        if accumulate:
+            g_prev = self._buf("g_prev", (self.n_total,), torch.float32)
+            g_prev.copy_(self.G)
         B, T, M = fw["B"], fw["T"], fw["M"]
         D, F, H, V = cfg.dim, cfg.ffn, cfg.heads, cfg.vocab
         bf, f32 = torch.bfloat16, torch.float32
@@ -434,6 +441,8 @@ class KosmosTrainer:
         self._bucket_ready("tail", works)
         for w in works:
             w.wait()
+        if g_prev is not None:
+            self.G.add_(g_prev)
 
     # ------------------------------------------------------------------ gradient all-reduce (data parallel)
     def bucket_plan(self):
@@ -478,11 +487,12 @@ class KosmosTrainer:
         return first + li * per, first + (li + 1) * per
 
     # ------------------------------------------------------------------ optimizer
-    def _optimize(self):
+    def _optimize(self, micro_batches: int = 1):
+        """Clip + optimizer over the flat buffers; the gradient is the SUM over ranks and micro-batches: scale by their count."""
         self.t += 1
         sc = self.scalars
         ops.sumsq(self.G, sc[2:3])
-        ops.clip_scale(sc[2:3], self.max_grad_norm, 1.0 / self.world, sc[3:4], sc[4:5])
+        ops.clip_scale(sc[2:3], self.max_grad_norm, 1.0 / (self.world * max(int(micro_batches), 1)), sc[3:4], sc[4:5])
         nd = self.n_decay
         segs = ((0, nd, self.wd, self.W16), (nd, self.n_total, 0.0, None))
         for lo, hi, wd, wb in segs:
@@ -533,13 +543,27 @@ class KosmosTrainer:
         self.sync_weights()                      # an external optimizer updates the fp32 masters only
         return _KosmosAutograd.apply(self.model.output_projection.weight, self, text_tokens, images, img_rows)
 
-    def loss_and_grads(self, text_tokens, images, image_positions=None):
+    def loss_and_grads(self, text_tokens, images, image_positions=None, accumulate: bool = False):
         """Forward + backward (+ all-reduce) without the optimizer: fills ``param.grad`` (views of the flat buffer,
-        SUMMED over ranks) and returns the local mean loss (device scalar)."""
+        SUMMED over ranks; with ``accumulate`` also added to what was there) and returns the local mean loss (device scalar)."""
         text_tokens, images, img_rows = self._prepare(text_tokens, images, image_positions)
         fw = self._forward(text_tokens, images, img_rows)
-        self._backward(fw, text_tokens, img_rows)
+        self._backward(fw, text_tokens, img_rows, accumulate=accumulate)
         return self.scalars[0] / torch.clamp(self.scalars[1], min=1.0)
+
+    def step_accumulated(self, micro_batches):
+        """One optimisation step over several micro-batches (gradient accumulation, train.py:55,492): ``micro_batches`` is a
+        sequence of ``(text_tokens, images)`` or ``(text_tokens, images, image_positions)``; the update uses the mean of
+        their gradients.  Returns the mean of the micro-batch losses (device scalar)."""
+        micro_batches = list(micro_batches)
+        if not micro_batches:
+            raise ValueError("step_accumulated needs at least one micro-batch")
+        total = None
+        for i, mb in enumerate(micro_batches):
+            loss = self.loss_and_grads(*mb, accumulate=i > 0).clone()
+            total = loss if total is None else total + loss
+        self._optimize(len(micro_batches))
+        return total / len(micro_batches)
 
     def step(self, text_tokens, images, image_positions=None):
         loss = self.loss_and_grads(text_tokens, images, image_positions)
@@ -570,7 +594,9 @@ class _KosmosAutograd(torch.autograd.Function):
         if ctx.fw is None or ctx.serial != tr._fw_serial:
             raise RuntimeError("kosmosx: the activations of this forward are gone (a later forward re-used the buffers, or "
                                "backward ran twice); call backward once, before the next training forward")
-        tr._backward(ctx.fw, ctx.text_tokens, ctx.img_rows, dlogits_in=dlogits)
+        # autograd semantics: add to the gradients that are there; after zero_grad(set_to_none=True) nothing is there
+        accumulate = all(p.grad is not None and p.grad.data_ptr() == tr._g(p).data_ptr() for p in tr.params)
+        tr._backward(ctx.fw, ctx.text_tokens, ctx.img_rows, dlogits_in=dlogits, accumulate=accumulate)
         ctx.fw = None
         tr.attach_grads()
         return None, None, None, None, None

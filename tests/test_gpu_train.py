@@ -211,3 +211,51 @@ def test_pytorch_training_loop_through_autograd(m, positions):
     trainer.sync_weights()          # the external optimizer moved the fp32 masters after the last bridge forward synced
     ce = torch_loss(mine(tg, ig, image_positions=positions).float())             # the inference path sees the updated weights
     assert abs(ce.item() - trainer.loss_and_grads(tg, ig, image_positions=positions).item()) < 3e-2
+
+
+def test_gradient_accumulation_over_micro_batches():
+    """GRADIENT_ACCUMULATE_EVERY of the reference (train.py:55,492): gradients of successive micro-batches add up, in the
+    fused path (``loss_and_grads(accumulate=True)`` / ``step_accumulated``) and through the autograd bridge (backward
+    without ``zero_grad`` in between), and the optimizer uses their mean."""
+    import kosmos_oracle as ko
+    ref, mine, trainer, oc = _pair(lr=1e-2, weight_decay=0.0)
+    ta, ia = (t.cuda() for t in ko.make_inputs(oc, 2, 24, seed=5))
+    tb, ib = (t.cuda() for t in ko.make_inputs(oc, 2, 24, seed=6))
+    la = trainer.loss_and_grads(ta, ia).item()
+    ga = trainer.G.clone()
+    lb = trainer.loss_and_grads(tb, ib).item()
+    gb = trainer.G.clone()
+    assert not torch.equal(ga, gb)
+    trainer.loss_and_grads(ta, ia)
+    trainer.loss_and_grads(tb, ib, accumulate=True)
+    assert ((trainer.G - (ga + gb)).norm() / (ga + gb).norm()).item() <= 1e-5
+    # the bridge: two backward calls without zero_grad in between
+    tgt_a = ko.KosmosOracle.loss_targets(ta.cpu(), oc.p_latents).cuda()
+    tgt_b = ko.KosmosOracle.loss_targets(tb.cpu(), oc.p_latents).cuda()
+    mine.train()
+    trainer.G.zero_()
+    for tok, img, tgt in ((ta, ia, tgt_a), (tb, ib, tgt_b)):
+        logits = mine(tok, img)
+        torch.nn.functional.cross_entropy(logits.reshape(-1, oc.vocab), tgt.reshape(-1), ignore_index=-100).backward()
+    rel = ((trainer.G - (ga + gb)).norm() / (ga + gb).norm()).item()
+    print(f"accumulated through the bridge vs fused sum: rel {rel:.3e}")
+    assert rel <= 1e-2
+    for p in trainer.params:                                   # zero_grad(set_to_none=True) starts a fresh sum
+        p.grad = None
+    logits = mine(ta, ia)
+    torch.nn.functional.cross_entropy(logits.reshape(-1, oc.vocab), tgt_a.reshape(-1), ignore_index=-100).backward()
+    assert ((trainer.G - ga).norm() / ga.norm()).item() <= 1e-2
+    mine.eval()
+    # step_accumulated: the update is the one of the mean gradient (clipped), the loss the mean loss
+    before = trainer.P.clone()
+    loss = trainer.step_accumulated([(ta, ia), (tb, ib)])
+    torch.cuda.synchronize()
+    assert abs(loss.item() - 0.5 * (la + lb)) <= 1e-4
+    mean = 0.5 * (ga + gb)
+    assert abs(trainer.grad_norm.item() - mean.norm().item()) <= 1e-3 * mean.norm().item()
+    w = mine.output_projection.weight
+    q = torch.nn.Parameter(before[trainer.seg[id(w)].off:trainer.seg[id(w)].off + w.numel()].view(w.shape).clone())
+    g = trainer._g(w).detach()
+    q.grad = 0.5 * g * torch.clamp(1.0 / (mean.norm() + 1e-6), max=1.0)
+    torch.optim.AdamW([q], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0).step()
+    assert torch.allclose(w.detach(), q.detach(), atol=2e-6, rtol=0)
