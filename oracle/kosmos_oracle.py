@@ -19,7 +19,13 @@ What *is* pinned:
   * the sub-LN decoder block (xPos off) is checked against the installed
     ``transformers`` Kosmos-2 text block, an independent port of the same
     torchscale layer (same parameter names);
-  * xPos is checked for its defining relative-position (Toeplitz) property.
+  * xPos is checked for its defining relative-position (Toeplitz) property and, elementwise, against the
+    xPos of the installed ``flash_attn`` (``RotaryEmbedding(scale_base=512, interleaved=True)``), an
+    independent implementation of the same paper;
+  * the perceiver attention and the whole resampler loop are checked against the installed
+    ``transformers`` Idefics port of the same flamingo-pytorch modules (weights copied in; the port's ReLU
+    swapped for flamingo's GELU, media position embedding zeroed);
+  * ``clip_preprocess_u8`` equals ``transformers.image_transforms.rescale`` + ``normalize`` bit for bit.
 Everything else follows the published algorithms of those packages as recorded
 in SURVEY.md Appendix A; each class cites the reference call site it serves.
 

@@ -322,3 +322,101 @@ def test_oracle_matches_multi_image_golden(tiny512):
         with torch.no_grad():
             y = model(text, images, image_positions=c["positions"])
         assert (y[..., ::c["col_step"]] - c["logits"]).abs().max() < 2e-4, name
+
+
+# --------------------------------------------------------------------------- pins against independent implementations
+def test_xpos_matches_flash_attn_xpos_rotary():
+    """The xPos restatement (torchscale XPOS, SURVEY A.5 — torchscale itself is not installable here) against an
+    independent implementation that IS installed: flash_attn.layers.rotary.RotaryEmbedding(scale_base=512,
+    interleaved=True), the FlashAttention authors' xPos (same ζ = (2i + 0.4d)/(1.4d), base 10000, pair-interleaved
+    rotation, q scaled up / k scaled down, positions centred on the sequence).  Even T: the rotated q and k agree
+    elementwise.  Odd T: torchscale centres with floor(-T/2), flash_attn with T//2 — a constant shift of every position,
+    which cancels in q·kᵀ (the relative-position property), so the score matrices agree."""
+    import kosmos_oracle as ko
+    rot = pytest.importorskip("flash_attn.layers.rotary")
+    hd = 64
+    x = ko.XPOS(hd, 512)
+    for T in (128, 513):
+        r = rot.RotaryEmbedding(hd, interleaved=True, scale_base=512)
+        r._update_cos_sin_cache(T, device="cpu", dtype=torch.float32)
+        g = torch.Generator().manual_seed(T)
+        q, k = torch.randn(3, T, hd, generator=g), torch.randn(3, T, hd, generator=g)
+        fq = rot.apply_rotary_emb_torch(q.unsqueeze(2), r._cos_cached, r._sin_cached, interleaved=True).squeeze(2)
+        fk = rot.apply_rotary_emb_torch(k.unsqueeze(2), r._cos_k_cached, r._sin_k_cached, interleaved=True).squeeze(2)
+        oq, ok = x(q, downscale=False), x(k, downscale=True)
+        if T % 2 == 0:
+            assert (oq - fq).abs().max().item() <= 2e-5 and (ok - fk).abs().max().item() <= 2e-5
+        s_o, s_f = oq @ ok.transpose(1, 2), fq @ fk.transpose(1, 2)
+        assert (s_o - s_f).abs().max().item() <= 2e-4 * s_f.abs().max().item()
+
+
+def test_perceiver_attention_matches_hf_idefics_port():
+    """flamingo_pytorch is not installable here; transformers' IdeficsPerceiverAttention is an independent port of the
+    same PerceiverAttention (LayerNorm of media and latents, keys / values over [media ‖ latents], q·scale, amax-stabilised
+    softmax, bias-free projections).  With the oracle's weights copied in (to_kv split into k / v) the outputs agree."""
+    import kosmos_oracle as ko
+    from transformers.models.idefics.perceiver import IdeficsPerceiverAttention
+    cfg = ko.OracleConfig.tiny()
+    torch.manual_seed(0)
+    mine = ko._PerceiverAttention(cfg, ko._Emu())
+    for ln in (mine.norm_media, mine.norm_latents):
+        torch.nn.init.normal_(ln.weight, 1.0, 0.2)
+        torch.nn.init.normal_(ln.bias, 0.0, 0.2)
+    inner = cfg.p_heads * cfg.p_dim_head
+    hf = IdeficsPerceiverAttention(cfg.vit_dim, cfg.p_heads, cfg.p_dim_head, qk_layer_norms=False)
+    sd = mine.state_dict()
+    hf.load_state_dict({
+        "context_layer_norm.weight": sd["norm_media.weight"], "context_layer_norm.bias": sd["norm_media.bias"],
+        "latents_layer_norm.weight": sd["norm_latents.weight"], "latents_layer_norm.bias": sd["norm_latents.bias"],
+        "q_proj.weight": sd["to_q.weight"], "k_proj.weight": sd["to_kv.weight"][:inner], "v_proj.weight": sd["to_kv.weight"][inner:],
+        "output_proj.weight": sd["to_out.weight"]})
+    x = torch.randn(2, 1, cfg.vit_tokens, cfg.vit_dim)
+    lat = torch.randn(2, 1, cfg.p_latents, cfg.vit_dim)
+    with torch.no_grad():
+        got = mine(x, lat)
+        want = hf(x[:, 0], lat[:, 0])                       # the port has no media-time axis: (B, n, D)
+    assert got.shape == (2, 1, cfg.p_latents, cfg.vit_dim) and want.shape == (2, cfg.p_latents, cfg.vit_dim)
+    assert (got[:, 0] - want).abs().max().item() <= 2e-5
+
+
+def test_perceiver_resampler_structure_matches_hf_idefics_port():
+    """The whole resampler against transformers' IdeficsPerceiverResampler (same lineage: lucidrains' flamingo-pytorch):
+    learned latents broadcast over the batch, depth x [latents += attn(media, latents); latents += ff(latents)], final
+    LayerNorm, FF = LN -> Linear -> act -> Linear without biases.  Two things differ by construction and are neutralised:
+    the port's FF activation is ReLU (flamingo: GELU) — swapped on the HF instance; the port has no media position
+    embedding — the oracle's is zeroed (its broadcast rule is covered by test_multi_image_rows_and_media_positions)."""
+    import kosmos_oracle as ko
+    from transformers import IdeficsConfig
+    from transformers.models.idefics.perceiver import IdeficsPerceiverResampler
+    cfg = ko.OracleConfig.tiny()
+    torch.manual_seed(0)
+    mine = ko.PerceiverResampler(cfg, ko._Emu()).eval()
+    with torch.no_grad():
+        mine.media_pos_emb.zero_()
+        for mod in mine.modules():
+            if isinstance(mod, torch.nn.LayerNorm):
+                torch.nn.init.normal_(mod.weight, 1.0, 0.2)
+                torch.nn.init.normal_(mod.bias, 0.0, 0.2)
+    hc = IdeficsConfig()
+    hc.vision_config.embed_dim = cfg.vit_dim
+    hf = IdeficsPerceiverResampler(hc, cfg.vit_dim, cfg.p_depth, cfg.p_heads, cfg.p_dim_head, cfg.p_latents).eval()
+    inner = cfg.p_heads * cfg.p_dim_head
+    sd = mine.state_dict()
+    new = {"latents": sd["latents"], "layer_norm.weight": sd["norm.weight"], "layer_norm.bias": sd["norm.bias"]}
+    for i in range(cfg.p_depth):
+        a, f = f"layers.{i}.0.", f"layers.{i}.1."
+        new.update({
+            f"blocks.{i}.0.context_layer_norm.weight": sd[a + "norm_media.weight"], f"blocks.{i}.0.context_layer_norm.bias": sd[a + "norm_media.bias"],
+            f"blocks.{i}.0.latents_layer_norm.weight": sd[a + "norm_latents.weight"], f"blocks.{i}.0.latents_layer_norm.bias": sd[a + "norm_latents.bias"],
+            f"blocks.{i}.0.q_proj.weight": sd[a + "to_q.weight"], f"blocks.{i}.0.k_proj.weight": sd[a + "to_kv.weight"][:inner],
+            f"blocks.{i}.0.v_proj.weight": sd[a + "to_kv.weight"][inner:], f"blocks.{i}.0.output_proj.weight": sd[a + "to_out.weight"],
+            f"blocks.{i}.1.ln.weight": sd[f + "0.weight"], f"blocks.{i}.1.ln.bias": sd[f + "0.bias"],
+            f"blocks.{i}.1.fc.weight": sd[f + "1.weight"], f"blocks.{i}.1.c_proj.weight": sd[f + "3.weight"]})
+    hf.load_state_dict(new)
+    for blk in hf.blocks:
+        blk[1].act = torch.nn.GELU()
+    x = torch.randn(2, cfg.vit_tokens, cfg.vit_dim)
+    with torch.no_grad():
+        got, want = mine(x), hf(x)
+    assert got.shape == (2, 1, cfg.p_latents, cfg.vit_dim) and want.shape == (2, cfg.p_latents, cfg.vit_dim)
+    assert (got[:, 0] - want).abs().max().item() <= 5e-5
