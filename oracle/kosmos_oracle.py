@@ -16,9 +16,9 @@ What *is* pinned:
   * the CLIP ViT-L/14 tower restated here is checked weight-for-weight against
     the installed ``transformers`` implementation (tests/test_oracle.py), which
     is the real dependency the reference calls at model.py:154-156,230;
-  * the sub-LN decoder block (xPos off) is checked against the installed
-    ``transformers`` Kosmos-2 text block, an independent port of the same
-    torchscale layer (same parameter names);
+  * the sub-LN decoder block and the whole decoder stack (xPos off) are checked against the installed
+    ``transformers`` Kosmos-2 text block / ``Kosmos2TextForCausalLM``, an independent port of the same
+    torchscale decoder (same parameter names);
   * xPos is checked for its defining relative-position (Toeplitz) property and, elementwise, against the
     xPos of the installed ``flash_attn`` (``RotaryEmbedding(scale_base=512, interleaved=True)``), an
     independent implementation of the same paper;

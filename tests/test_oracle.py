@@ -420,3 +420,47 @@ def test_perceiver_resampler_structure_matches_hf_idefics_port():
         got, want = mine(x), hf(x)
     assert got.shape == (2, 1, cfg.p_latents, cfg.vit_dim) and want.shape == (2, cfg.p_latents, cfg.vit_dim)
     assert (got[:, 0] - want).abs().max().item() <= 5e-5
+
+
+def test_decoder_stack_matches_hf_kosmos2_text_model(tiny):
+    """The glue of torchscale's ``Decoder`` (token embedding x 1.0, positions starting at padding_idx + 1 = 2, per-layer
+    causal mask, layer loop, final ``layer_norm``, bias-free ``output_projection``) against HF's Kosmos-2 text model —
+    an independent port of the same torchscale decoder.  xPos is switched off (Kosmos-2 has none) and the oracle's
+    learned position table is loaded with the port's sinusoidal rows, so that both see the same inputs."""
+    from transformers.models.kosmos2.configuration_kosmos2 import Kosmos2TextConfig
+    from transformers.models.kosmos2.modeling_kosmos2 import Kosmos2TextForCausalLM
+    cfg, _ = tiny
+    torch.manual_seed(4)
+    model = ko.KosmosOracle(cfg).eval()
+    dec = model.decoder
+    for layer in dec.layers:
+        layer.self_attn.use_xpos = False
+    hc = Kosmos2TextConfig(vocab_size=cfg.vocab, embed_dim=cfg.dim, attention_heads=cfg.heads, ffn_dim=cfg.ffn, layers=cfg.layers,
+                           dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, activation_function="gelu", scale_embedding=False,
+                           max_position_embeddings=cfg.max_positions, layerdrop=0.0, pad_token_id=1)
+    hc._attn_implementation = "eager"
+    hf = Kosmos2TextForCausalLM(hc).eval()
+    sd = {}
+    for k, v in dec.state_dict().items():
+        if ".B." in k or "xpos" in k or k.startswith("embed_positions"):
+            continue
+        k = k.replace(".A.", ".")
+        sd[("lm_head." + k[len("output_projection."):]) if k.startswith("output_projection.") else "model." + k] = v
+    res = hf.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all("embed_positions" in k for k in res.missing_keys), (res.missing_keys, res.unexpected_keys)
+    T = 23
+    g = torch.Generator().manual_seed(7)
+    tokens = torch.randint(2, cfg.vocab, (2, T), generator=g)                  # no padding (id 1): positions are 2 .. T+1
+    pos_mod = hf.model.embed_positions
+    ids = pos_mod.create_position_ids_from_input_ids(tokens, padding_idx=1) if hasattr(pos_mod, "create_position_ids_from_input_ids") \
+        else None
+    if ids is not None:
+        assert torch.equal(ids, torch.arange(2, T + 2).expand(2, T))              # the "+2" of PositionalEmbedding.forward
+    with torch.no_grad():
+        table = pos_mod.weights if hasattr(pos_mod, "weights") else pos_mod.weight
+        dec.embed_positions.weight[: cfg.max_positions].copy_(table[: cfg.max_positions].to(torch.float32))
+        want = hf(input_ids=tokens).logits
+        got, extra = dec(tokens)
+    assert got.shape == want.shape == (2, T, cfg.vocab)
+    assert (got - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())
+    assert len(extra["inner_states"]) == cfg.layers + 1
