@@ -619,19 +619,19 @@ class _KosmosBase(nn.Module):
                     sd[b] = sd[a]
                 elif b in sd and a not in sd:
                     sd[a] = sd[b]
-        plain = {}
-        for k, v in sd.items():                          # non-multiway torchscale layer: x.weight -> x.A.weight
-            if k not in own and k.startswith("decoder.layers."):
-                head, _, leaf = k.rpartition(".")
-                for cand in (f"{head}.A.{leaf}",                                           # q_proj.weight -> q_proj.A.weight
-                             ".".join(head.split(".")[:-1] + ["A", head.split(".")[-1], leaf])):  # ffn.fc1.weight -> ffn.A.fc1.weight
-                    if cand in own and cand not in sd:
-                        plain[k] = cand
-                        break
+        def live_branch(k):                              # non-multiway torchscale name -> the live .A branch's name
+            head, _, leaf = k.rpartition(".")
+            parent, _, mod = head.rpartition(".")
+            for cand in (f"{head}.A.{leaf}",             # self_attn.q_proj.weight -> self_attn.q_proj.A.weight
+                         f"{parent}.A.{mod}.{leaf}"):    # ffn.fc1.weight -> ffn.A.fc1.weight
+                if cand in own and cand not in sd:
+                    return cand
+            return None
+
+        plain = {k: live_branch(k) for k in sd if k not in own and k.startswith("decoder.layers.")}
+        plain = {k: c for k, c in plain.items() if c is not None}
         for k, cand in plain.items():
             sd[cand] = sd.pop(k)
-        if plain:
-            strict = False                               # the .B branches keep their initial values (never run, a17)
         if resize_positions:
             for k in ("embed_positions.weight", "decoder.embed_positions.weight"):
                 if k in sd and k in own and sd[k].shape != own[k].shape and sd[k].shape[1:] == own[k].shape[1:]:
@@ -639,7 +639,12 @@ class _KosmosBase(nn.Module):
                     merged = own[k].detach().clone()
                     merged[:rows] = sd[k][:rows].to(merged.dtype)
                     sd[k] = merged
-        return self.load_state_dict(sd, strict=strict)
+        res = self.load_state_dict(sd, strict=strict and not plain)
+        if plain and strict:                             # the .B branches (never run, a17) may keep their initial values; nothing else
+            missing = [k for k in res.missing_keys if ".B." not in k]
+            if missing or res.unexpected_keys:
+                raise RuntimeError(f"load_checkpoint: missing keys {missing}, unexpected keys {list(res.unexpected_keys)}")
+        return res
 
     def _generate(self, x0: torch.Tensor, B: int, T: int, max_new_tokens: int, forced=None, return_logits=False,
                   cuda_graph=True, one_kernel=None):

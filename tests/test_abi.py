@@ -267,6 +267,8 @@ def test_plain_torchscale_and_resized_position_checkpoints(tiny_cfgs):
     assert not res.unexpected_keys and all(".B." in k for k in res.missing_keys)
     own = mine.state_dict()
     assert all(torch.equal(own[k], v) for k, v in sd.items() if ".B." not in k)
+    with pytest.raises(RuntimeError, match="missing keys"):           # a plain checkpoint still has to be complete
+        Kosmos(config=kc).load_checkpoint({k: v for k, v in plain.items() if "image_proj" not in k})
     longer = KosmosConfig(**{**{k: getattr(kc, k) for k in KosmosConfig.__dataclass_fields__}, "max_positions": kc.max_positions + 2})
     big = Kosmos(config=longer)
     with pytest.raises(RuntimeError, match="size mismatch"):
