@@ -277,3 +277,62 @@ def test_plain_torchscale_and_resized_position_checkpoints(tiny_cfgs):
     big.load_checkpoint(sd, resize_positions=True)
     pos = big.state_dict()["embed_positions.weight"]
     assert torch.equal(pos[:kc.max_positions], sd["embed_positions.weight"]) and torch.equal(pos[-2:], keep)
+
+
+def test_autograd_bridge_mechanics_with_a_stub_trainer():
+    """The autograd node behind ``Kosmos.forward`` in train mode (kosmosx/train.py: _KosmosAutograd), exercised on the CPU
+    with a stand-in for the trainer (a one-matrix model whose hand-written backward fills a flat gradient buffer): the
+    output requires grad, a PyTorch loss drives the hand-written backward, ``param.grad`` is re-attached to the flat buffer
+    after ``zero_grad(set_to_none=True)``, and a backward whose activations were re-used fails loudly.  The real trainer
+    is checked on the GPU (tests/test_gpu_train.py::test_pytorch_training_loop_through_autograd)."""
+    from kosmosx.train import _KosmosAutograd
+
+    class Stub:
+        def __init__(self):
+            self.w = torch.nn.Parameter(torch.randn(5, 3))
+            self.G = torch.zeros(15)
+            self.buf = torch.zeros(8, 5)
+            self._fw_serial = 0
+            self.params = [self.w]
+            self.accumulate_seen = []
+
+        def _g(self, p):
+            return self.G.view(5, 3)
+
+        def _forward(self, tokens, images, rows):
+            self.x = images.reshape(8, 3)
+            self.buf.copy_(self.x @ self.w.detach().t())
+            return dict(logits=self.buf, B=2, T=4)
+
+        def _backward(self, fw, tokens, rows, dlogits_in=None, accumulate=False):
+            self.accumulate_seen.append(accumulate)
+            g = dlogits_in.reshape(8, 5).t() @ self.x
+            self.G.copy_((self.G.view(5, 3) + g if accumulate else g).reshape(-1))
+
+        def attach_grads(self):
+            for p in self.params:
+                if p.grad is None or p.grad.data_ptr() != self._g(p).data_ptr():
+                    p.grad = self._g(p)
+
+    tr = Stub()
+    images, tokens = torch.randn(2, 4, 3), torch.zeros(2, 4, dtype=torch.long)
+    target = torch.randint(0, 5, (8,))
+    opt = torch.optim.SGD([tr.w], lr=0.1)
+    opt.zero_grad()                                              # .grad is None from here
+    out = _KosmosAutograd.apply(tr.w, tr, tokens, images, (2,))
+    assert out.requires_grad and out.shape == (2, 4, 5)
+    torch.nn.functional.cross_entropy(out.reshape(-1, 5), target).backward()
+    w2 = tr.w.detach().clone().requires_grad_(True)
+    torch.nn.functional.cross_entropy(images.reshape(8, 3) @ w2.t(), target).backward()
+    assert tr.w.grad.data_ptr() == tr.G.data_ptr() and torch.allclose(tr.w.grad, w2.grad, atol=1e-6)
+    assert tr.accumulate_seen == [False]
+    out = _KosmosAutograd.apply(tr.w, tr, tokens, images, (2,))     # no zero_grad in between: accumulate
+    torch.nn.functional.cross_entropy(out.reshape(-1, 5), target).backward()
+    assert tr.accumulate_seen == [False, True] and torch.allclose(tr.w.grad, 2 * w2.grad, atol=1e-6)
+    before = tr.w.detach().clone()
+    opt.step()
+    assert not torch.equal(before, tr.w.detach())
+    stale = _KosmosAutograd.apply(tr.w, tr, tokens, images, (2,)).sum()
+    _KosmosAutograd.apply(tr.w, tr, tokens, images, (2,))
+    with pytest.raises(RuntimeError, match="activations of this forward are gone"):
+        stale.backward()
