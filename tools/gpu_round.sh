@@ -17,6 +17,10 @@ for w in $what; do
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 4 -o "$out/prof_gemm" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_gemm.log" 2>&1; echo "ncu_gemm exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_gemm.log";;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_pp -s 1 -c 1 -o "$out/prof_attn" -f python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1 > "$out/ncu_attn.log" 2>&1; echo "ncu_attn exit $?" | tee -a "$out/summary.txt"; tail -3 "$out/ncu_attn.log";;
     kcheck)   bash tools/run_kernel_checks.sh bench;;
+    preprocess) for c in embed preprocess bench_preprocess; do timeout 100 python tools/kernel_check.py $c > "$out/kcheck_$c.log" 2>&1; echo "kcheck $c exit $?" | tee -a "$out/summary.txt"; done; grep "^preprocess" "$out/kcheck_bench_preprocess.log";
+                timeout 100 compute-sanitizer --tool memcheck python tools/kernel_check.py preprocess > "$out/sanitizer_preprocess.log" 2>&1; grep "ERROR SUMMARY" "$out/sanitizer_preprocess.log";;
+    bench_vit) timeout 150 python tools/kernel_check.py bench_vit > "$out/bench_vit.log" 2>&1; grep "^gemm" "$out/bench_vit.log";;
+    train_tests) timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -x -q -s > "$out/pytest_train.log" 2>&1; echo "train tests exit $?" | tee -a "$out/summary.txt"; grep -E "bridge|accumulated|passed|failed" "$out/pytest_train.log" | tail -8;;
     decode)   timeout 300 python tools/kernel_check.py decode > "$out/kcheck_decode.log" 2>&1; echo "kcheck decode exit $?" | tee -a "$out/summary.txt";
               timeout 600 python -m pytest tests -m gpu -x -q -s -k "incremental or generate" > "$out/pytest_decode.log" 2>&1; echo "pytest decode exit $?" | tee -a "$out/summary.txt"; grep -E "max=|passed|failed" "$out/pytest_decode.log" | tail -20;
               for mode in one graph; do KX_STEP_TRACE=1 timeout 300 python tools/bench_decode.py --mode $mode > "$out/bench_decode_$mode.log" 2>&1; grep "^trace" "$out/bench_decode_$mode.log"; tail -1 "$out/bench_decode_$mode.log" | cut -c1-400; done;;
