@@ -131,3 +131,32 @@ def test_device_preprocessing_has_no_cpu_path():
         pytest.skip("GPU present: covered by tests/test_gpu_parity.py")
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.clip_normalize_u8(torch.zeros(1, 3, 224, 224, dtype=torch.uint8), image=224)
+
+
+def test_tokenizer_with_a_real_hf_fast_tokenizer_built_offline():
+    """The same layout through a genuine ``PreTrainedTokenizerFast`` (word-level vocabulary built in memory, special tokens
+    declared the way the reference declares them, model.py:39-46): the HF call convention the class relies on is the real one."""
+    tokenizers = pytest.importorskip("tokenizers")
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import Whitespace
+    from tokenizers.processors import TemplateProcessing
+    from transformers import CLIPImageProcessor, PreTrainedTokenizerFast
+    from kosmosx import KosmosTokenizer
+    words = ["a", "photo", "of", "cat", "two", "dogs"]
+    vocab = {"<s>": 0, "<pad>": 1, "<eos>": 2, "<unk>": 3, **{w: 4 + i for i, w in enumerate(words)}}
+    tok = tokenizers.Tokenizer(WordLevel(vocab, unk_token="<unk>"))
+    tok.pre_tokenizer = Whitespace()
+    tok.post_processor = TemplateProcessing(single="<s> $A <eos>", special_tokens=[("<s>", 0), ("<eos>", 2)])
+    hf = PreTrainedTokenizerFast(tokenizer_object=tok, bos_token="<s>", eos_token="<eos>", pad_token="<pad>", unk_token="<unk>",
+                                 additional_special_tokens=["<image>", "</image>"], model_max_length=8192)
+    tk = KosmosTokenizer(tokenizer=hf, processor=CLIPImageProcessor())
+    assert tk.im_idx == hf.convert_tokens_to_ids("<image>") and tk.im_end_idx == hf.convert_tokens_to_ids("</image>")
+    assert tk.im_idx >= len(vocab) and tk.im_end_idx == tk.im_idx + 1          # appended after the base vocabulary
+    both, only = tk.tokenize_texts(["a photo of a cat", "two dogs"])
+    assert only.tolist() == [[0, 4, 5, 6, 4, 7, 2], [0, 8, 9, 2, 1, 1, 1]]
+    assert both.tolist() == [[0, tk.im_idx, tk.im_end_idx, 4, 5, 6, 4, 7, 2], [0, tk.im_idx, tk.im_end_idx, 8, 9, 2, 1, 1, 1]]
+    g = torch.Generator().manual_seed(2)
+    imgs = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8, generator=g)
+    out = tk.tokenize({"target_text": ["a photo of a cat", "two dogs"], "image": list(imgs.numpy())})
+    assert out["attention_mask"].shape == (2, 64 + 9) and out["attention_mask"][1, -3:].tolist() == [0, 0, 0]
+    assert out["images"].shape == (2, 3, 224, 224)
