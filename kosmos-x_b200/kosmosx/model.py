@@ -69,6 +69,8 @@ class KosmosConfig:
                 raise ValueError(f"{name} must be a multiple of 64")
         if self.vit_act not in ("gelu", "quick_gelu"):
             raise ValueError("vit_act must be 'gelu' or 'quick_gelu'")
+        if self.patch <= 0 or self.image % self.patch or self.image % 4:
+            raise ValueError("image must be a multiple of patch and of 4 (the patch pack reads 16-byte pixel vectors)")
 
 
 # --------------------------------------------------------------------------- parameter containers

@@ -202,6 +202,10 @@ def test_config_validation():
     from kosmosx import KosmosConfig
     with pytest.raises(ValueError):
         KosmosConfig(dim=2048, heads=16).validate()       # head_dim 128
+    with pytest.raises(ValueError, match="multiple of patch"):
+        KosmosConfig(image=225).validate()
+    with pytest.raises(ValueError, match="multiple of patch"):
+        KosmosConfig(image=42, patch=14).validate()       # 42 % 4 != 0: the patch pack reads 16-byte pixel vectors
     KosmosConfig().validate()
 
 
