@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 14   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 15   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -153,11 +153,17 @@ int kx_layernorm_fwd(const void* x, int x_is_bf16, long long ld_x, const float* 
  * is img_count = 1, host_img_rows = {2}; BASELINE.json configs[4] uses four images per sequence.
  * For KosmosLanguage (model.py:310-320) pass img_count = 0.
  * Token ids outside [0, vocab) set *err_flag (device int, may be NULL) instead of faulting.
- * pos_table NULL = gather only (the `[1]` result of forward_embedding, model.py:238).
+ * pos_table NULL = gather only.
+ * alias_positions = 1 reproduces torchscale's in-place add: forward_embedding does `x = embed = embed_scale *
+ * token_embedding; x += positions`, so the `[1]` result taken at model.py:238 ALREADY carries positions 2..t_text+1 of
+ * the un-spliced text, and the second call (model.py:242-244) adds the spliced positions on top: a text row holding
+ * text token i at spliced row t gets embed[token] + pos[i + 2] + pos[t + 2] (image rows only pos[t + 2], from the
+ * image_proj epilogue).  alias_positions = 0: a single add of pos[t + 2] (KosmosLanguage, model.py:310-320, which
+ * calls forward_embedding once and takes `[0]`).
  */
 int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
                         const float* pos_table, int pos_rows, int dim, const int* host_img_rows, int img_count,
-                        int n_img, float* x0, int* err_flag, kx_stream_t stream);
+                        int n_img, int alias_positions, float* x0, int* err_flag, kx_stream_t stream);
 
 /* x[b,t,:] = in[b,t,:] + pos_table[t+2,:]: Decoder.forward_embedding(x, token_embedding=x)[0] of
  * model.py:242-244 as a stand-alone call (the fused path is kx_embed_splice_pos + the image_proj epilogue). */
@@ -207,7 +213,31 @@ int kx_xpos_tables(const float* scale, const float* inv_freq, int T, int min_pos
 /* fp32 -> bf16 conversion of a parameter tensor (weight staging), and broadcast of the
  * perceiver latents over the batch (A.2: latents.expand). */
 int kx_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, kx_stream_t stream);
+/* bf16 -> fp32 (16-byte aligned): the received sums of a bf16 gradient exchange go back into the flat fp32 gradient
+ * buffer (2.76 GB of bf16 gradients per all-reduce; the reference's FSDP reduce_dtype is 16-bit,
+ * train.py:156-162). */
+int kx_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, kx_stream_t stream);
 int kx_broadcast_rows(const float* src, float* dst, long long row_elems, int copies, kx_stream_t stream);
+
+/* ---- verification precision ("bf16x3") ------------------------------------------------ *
+ * BASELINE.json states the parity tolerance as logits max-abs-diff <= 1e-3 against the reference's PyTorch path
+ * (kosmosx/model.py:208-253).  bf16 operands cannot reach it (one ulp at 1.0 is 7.8e-3), so the SAME tcgen05 GEMM is
+ * also driven with split operands: x = hi + lo, hi = bf16(x), lo = bf16(x - hi), and A.W^T ~= Ah.Wh^T + Ah.Wl^T +
+ * Al.Wh^T as ONE kx_gemm_bf16 launch over K' = 3*n_pad (three passes accumulating in one TMEM tile).
+ * kx_split_bf16x3 writes that layout: dst[r, s*n_pad + k], s = 0,1,2 = (hi, hi, lo) for activations (weights = 0) or
+ * (hi, lo, hi) for weights (weights = 1); columns k in [n, n_pad) are zero.  The remaining fp32 pieces of that mode:
+ * kx_attn_f32 (softmax(q.k^T*scale [+causal]).v in fp32 FMAs, head_dim 64; q rows [batch*n_q, ld_q], k/v rows
+ * [batch*n_kv, ld_kv], head h at columns h*64.. of the given pointers; serves the decoder (causal, n_q == n_kv), the ViT
+ * and the perceiver cross-attention), kx_xpos_apply_f32 (the KX_EPI_QKV_XPOS rotation in place on the q|k blocks of an
+ * fp32 [rows, ld] matrix) and kx_im2col_patches_f32 (kx_im2col_patches with fp32 patch rows). */
+int kx_split_bf16x3(const float* src, long long ld_src, int rows, int n, int n_pad, void* dst_bf16, long long ld_dst,
+                    int weights, kx_stream_t stream);
+int kx_attn_f32(const float* q, long long ld_q, const float* k, const float* v, long long ld_kv, float* out,
+                long long ld_out, int batch, int heads, int n_q, int n_kv, int causal, float scale, kx_stream_t stream);
+int kx_xpos_apply_f32(float* qkv, long long ld, int rows, int d_model, int seq_len, const float* q_cos, const float* q_sin,
+                      const float* k_cos, const float* k_sin, kx_stream_t stream);
+int kx_im2col_patches_f32(const float* pixels, int batch, int media, int image, int patch, float* patches, int k_pad,
+                          const float* class_embedding, const float* pos_table, float* x, int dim, kx_stream_t stream);
 
 /* ==================================================================================== *
  * Training step (BASELINE.json configs[3]): forward -> cross-entropy over the text rows
@@ -263,20 +293,37 @@ int kx_colsum_bf16(const void* x_bf16, long long ld, int rows, int n, float* out
 int kx_xpos_bwd(void* dqkv_bf16, long long ld, int rows, int d_model, int seq_len, const float* q_cos, const float* q_sin,
                 const float* k_cos, const float* k_sin, kx_stream_t stream);
 
-/* Softmax cross-entropy over the text rows of the spliced sequence (same splice description as kx_embed_splice_pos):
- * the row holding text token i predicts text token i+1; image rows, the last text token and the token directly in
- * front of an image carry no loss (the reference's intended loss, experimental/model/allModalities/notes.txt:566-574,
- * keeps row 0 and the rows after the image block).  loss_acc[0] += sum of row losses, loss_acc[1] += rows counted.
- * dlogits (NULL = loss only): bf16 [batch*T, ld_dlogits], (softmax - onehot) * inv_count, zeros elsewhere
- * (including the pad columns [vocab, ld_dlogits), so the matrix can feed kx_gemm_bf16 directly). */
-int kx_ce_fwd_bwd(const float* logits, long long ld_logits, const long long* tokens, int batch, int t_text,
-                  const int* host_img_rows, int img_count, int n_img, int vocab, float inv_count, void* dlogits_bf16,
-                  long long ld_dlogits, float* loss_acc, int* err_flag, kx_stream_t stream);
+/* Next-token targets of the spliced sequence (same splice description as kx_embed_splice_pos), one int64 per row,
+ * -100 = no loss (torch's ignore_index), and *count += rows with a target (device fp32, may be NULL).
+ *   KX_LOSS_REFERENCE   the reference's intended loss, experimental/model/allModalities/notes.txt:566-574:
+ *       `outputs = cat([outputs[:, :1], outputs[:, 67:]])`, `loss(outputs[:, :-1], labels[:, 1:])` with labels = the text
+ *       WITHOUT the `<image>` `</image>` markers (model.py:70-77).  Generalised to any image position p (features in
+ *       front of text token p): text tokens p-1 and p are the markers; marker rows and feature rows carry no loss and
+ *       markers are never targets; every other text row predicts the next non-marker text token.  For the reference
+ *       layout (p = 2) that is exactly rows 0 and 67.., row 0 predicting text token 3.
+ *   KX_LOSS_NEXT_TOKEN  plain next-token rule: the row of text token i predicts text token i+1; feature rows, the last
+ *       token and the token directly in front of an image carry no loss.
+ * ignore_token >= 0: targets equal to it (the tokenizer's <pad>) are dropped as well; -1 = keep everything (the
+ * reference's loop does no pad masking). */
+enum { KX_LOSS_REFERENCE = 0, KX_LOSS_NEXT_TOKEN = 1 };
+int kx_loss_targets(const long long* tokens, int batch, int t_text, const int* host_img_rows, int img_count, int n_img,
+                    int rule, long long ignore_token, long long* targets, float* count, kx_stream_t stream);
+
+/* Softmax cross-entropy (torch.nn.functional.cross_entropy, reduction = mean over the rows with a target):
+ * loss_acc[0] += sum of row losses, loss_acc[1] += rows counted.  targets: int64 [rows], negative = ignored.
+ * dlogits (NULL = loss only): bf16 [rows, ld_dlogits], (softmax - onehot) / max(*count, 1), zeros for ignored rows and
+ * for the pad columns [vocab, ld_dlogits), so the matrix can feed kx_gemm_bf16 directly.  count: DEVICE fp32 scalar
+ * (kx_loss_targets), read by the kernel — the normalisation needs no host value.  Targets >= vocab set *err_flag. */
+int kx_ce_fwd_bwd(const float* logits, long long ld_logits, const long long* targets, int rows, int vocab,
+                  const float* count, void* dlogits_bf16, long long ld_dlogits, float* loss_acc, int* err_flag,
+                  kx_stream_t stream);
 
 /* Backward of kx_embed_splice_pos: d_embed[token] += dx0[row] for text rows (not for padding_idx), d_pos[t + 2] +=
- * dx0[row] for every row.  NULL tables are skipped. */
+ * dx0[row] for every row, and with alias_positions also d_pos[i + 2] += dx0[row] for the row of text token i.
+ * NULL tables are skipped. */
 int kx_embed_bwd(const float* dx0, const long long* tokens, int batch, int t_text, const int* host_img_rows, int img_count,
-                 int n_img, int dim, int vocab, int padding_idx, float* d_embed, float* d_pos, kx_stream_t stream);
+                 int n_img, int dim, int vocab, int padding_idx, int alias_positions, float* d_embed, float* d_pos,
+                 kx_stream_t stream);
 
 /* Perceiver resampler pieces of the backward pass (flamingo_pytorch PerceiverResampler is trainable in the reference,
  * model.py:196-203): the cross-attention backward (dq like q; dkv like kv, k and v blocks), the GELU of its
@@ -365,10 +412,14 @@ int kx_kv_cache_store(const void* qkv_bf16, long long ld_qkv, int batch, int seq
                       void* v_cache, int t_max, kx_stream_t stream);
 
 /* x[b] = embed_table[tokens[b]] + pos_table[*pos + 2] (fp32) and its bf16 copy: Decoder.forward_embedding for
- * `tokens[:, -1:]` with the last position.  err_flag bit 0: token id out of range; bit 1: position table
- * exhausted. */
+ * `tokens[:, -1:]` with the last position.  text_index_off >= 0 additionally adds
+ * pos_table[*pos + 2 - text_index_off]: the new token continues a sequence embedded with alias_positions
+ * (kx_embed_splice_pos), whose text index trails the spliced row by the feature rows in front of it, so that a
+ * generation step equals Kosmos.forward over the grown text; -1 = single add (torchscale's own incremental step).
+ * err_flag bit 0: token id out of range; bit 1: position table exhausted. */
 int kx_decode_embed(const long long* tokens, int batch, const float* embed_table, int vocab, const float* pos_table,
-                    int pos_rows, const int* pos, int dim, float* x, void* xb_bf16, int* err_flag, kx_stream_t stream);
+                    int pos_rows, const int* pos, int text_index_off, int dim, float* x, void* xb_bf16, int* err_flag,
+                    kx_stream_t stream);
 
 /* Greedy choice on the device: tokens_out[b] = argmax_v logits[b, v] (lowest index on ties) or forced[b, *step] when
  * `forced` (int64 [batch, history_ld]) is given; history[b, *step] = the choice; then *step += 1 and *pos += 1 (pos
@@ -393,6 +444,7 @@ int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, c
  * err_flag bit 2 = a barrier timed out (logic error, results invalid). */
 typedef struct kx_decode_step_args {
     int batch, layers, d_model, ffn, heads, vocab, t_max, pos_rows;
+    int text_index_off;           /* as kx_decode_embed (-1 = single positional add) */
     float eps, scale;
     const void* const* w_qkv; const float* const* c_qkv; const float* const* d_qkv;      /* [layers] */
     const void* const* w_o;   const float* const* c_o;   const float* const* d_o;

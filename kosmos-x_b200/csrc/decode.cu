@@ -584,7 +584,7 @@ kv_cache_store_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int b
 // ----------------------------------------------------------------------------- new-token embedding
 __global__ void __launch_bounds__(256)
 decode_embed_kernel(const long long* __restrict__ tok, const float* __restrict__ embed, int vocab,
-                    const float* __restrict__ pos_tab, int pos_rows, const int* __restrict__ pos_ptr, int dim,
+                    const float* __restrict__ pos_tab, int pos_rows, const int* __restrict__ pos_ptr, int text_off, int dim,
                     float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int* __restrict__ err_flag) {
     pdl_launch_dependents();
     pdl_wait();
@@ -601,8 +601,12 @@ decode_embed_kernel(const long long* __restrict__ tok, const float* __restrict__
     }
     const float4* e = reinterpret_cast<const float4*>(embed + id * dim);
     const float4* pp = reinterpret_cast<const float4*>(pos_tab + static_cast<long long>(pr) * dim);
+    // text_off >= 0: the sequence was embedded with alias_positions (kx_embed_splice_pos) — the text-index position first
+    const float4* p1 = text_off >= 0 ? reinterpret_cast<const float4*>(pos_tab + static_cast<long long>(max(pr - text_off, 0)) * dim) : nullptr;
     for (int i = threadIdx.x; i < (dim >> 2); i += blockDim.x) {
-        const float4 a = __ldg(e + i), c = __ldg(pp + i);
+        float4 a = __ldg(e + i);
+        const float4 c = __ldg(pp + i);
+        if (p1 != nullptr) { const float4 c1 = __ldg(p1 + i); a.x += c1.x; a.y += c1.y; a.z += c1.z; a.w += c1.w; }
         const float4 r = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
         reinterpret_cast<float4*>(x + static_cast<long long>(b) * dim)[i] = r;
         uint2 pk;
@@ -784,7 +788,8 @@ extern "C" int kx_kv_cache_store(const void* qkv, long long ld_qkv, int batch, i
 }
 
 extern "C" int kx_decode_embed(const long long* tokens, int batch, const float* embed_table, int vocab, const float* pos_table,
-                               int pos_rows, const int* pos, int dim, float* x, void* xb, int* err_flag, cudaStream_t stream) {
+                               int pos_rows, const int* pos, int text_index_off, int dim, float* x, void* xb, int* err_flag,
+                               cudaStream_t stream) {
     if (!tokens || !embed_table || !pos_table || !pos || !x || !xb || batch <= 0 || vocab <= 0 || pos_rows <= 2 || dim <= 0 ||
         (dim & 3) || ((uintptr_t)embed_table & 15) || ((uintptr_t)pos_table & 15) || ((uintptr_t)x & 15) || ((uintptr_t)xb & 7)) {
         set_error("kx_decode_embed: bad argument");
@@ -792,7 +797,8 @@ extern "C" int kx_decode_embed(const long long* tokens, int batch, const float* 
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
     return check_chain(launch_chain(decode_embed_kernel, dim3(batch), dim3(256), stream, tokens, embed_table, vocab, pos_table,
-                                    pos_rows, pos, dim, x, reinterpret_cast<__nv_bfloat16*>(xb), err_flag), "kx_decode_embed");
+                                    pos_rows, pos, text_index_off, dim, x, reinterpret_cast<__nv_bfloat16*>(xb), err_flag),
+                       "kx_decode_embed");
 }
 
 extern "C" int kx_argmax_advance(const float* logits, long long ld, int batch, int vocab, const long long* forced,

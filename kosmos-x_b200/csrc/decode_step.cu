@@ -67,6 +67,7 @@ struct Phase {
 
 struct StepCommon {
     int batch, d_model, heads, t_max, vocab, pos_rows, hist_ld, n_phases;
+    int text_off;                           // >= 0: second positional add at (*pos + 2 - text_off), see kx_decode_embed
     float eps, scale_log2;
     const long long* forced; long long* tokens; long long* history;
     const float* embed_table; const float* pos_table;
@@ -175,9 +176,11 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
     if (threadIdx.x == 0) {
         stamp(dbg, 8);
         // release on the arrival itself (cumulative over the CTA's writes ordered before it by the bar.sync above) instead
-        // of a stand-alone MEMBAR.SC: the full fence also waited for the producer's in-flight bulk copies to drain
+        // of a stand-alone MEMBAR.SC: the full fence also waited for the producer's in-flight bulk copies to drain.
+        // acq_rel, not release: the LAST arriver skips the polling loop below, and its arrival must itself synchronise-with
+        // the other CTAs' releases (it is off the critical path: everybody else is still spinning on its increment).
         unsigned long long old;
-        asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;\n" : "=l"(old) : "l"(ctr) : "memory");
+        asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], 1;\n" : "=l"(old) : "l"(ctr) : "memory");
         stamp(dbg, 9);
         if (old + 1 != target) {                            // poll the arrival counter itself: one hop from the last arrival
             const long long t0 = clock64();
@@ -634,8 +637,11 @@ __device__ __forceinline__ void embed_row(const StepCommon& C, int b) {
     }
     const float4* e = reinterpret_cast<const float4*>(C.embed_table + id * C.d_model);
     const float4* pp = reinterpret_cast<const float4*>(C.pos_table + static_cast<long long>(pr) * C.d_model);
+    const float4* p1 = C.text_off >= 0 ? reinterpret_cast<const float4*>(C.pos_table + static_cast<long long>(max(pr - C.text_off, 0)) * C.d_model) : nullptr;
     for (int i = threadIdx.x; i < (C.d_model >> 2); i += CONSUMERS) {
-        const float4 a = __ldg(e + i), c = __ldg(pp + i);
+        float4 a = __ldg(e + i);
+        const float4 c = __ldg(pp + i);
+        if (p1 != nullptr) { const float4 c1 = __ldg(p1 + i); a.x += c1.x; a.y += c1.y; a.z += c1.z; a.w += c1.w; }
         const float4 rr = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
         reinterpret_cast<float4*>(C.x + static_cast<long long>(b) * C.d_model)[i] = rr;
         uint2 pk;
@@ -796,6 +802,7 @@ extern "C" int kx_decode_plan_build(const kx_decode_step_args* g, void* device_p
     StepPlan* plan = reinterpret_cast<StepPlan*>(host.data());
     StepCommon& C = plan->c;
     C.batch = g->batch; C.d_model = D; C.heads = g->heads; C.t_max = g->t_max; C.vocab = g->vocab; C.pos_rows = g->pos_rows;
+    C.text_off = g->text_index_off;
     C.hist_ld = g->history_ld; C.n_phases = n_ph;
     C.eps = g->eps; C.scale_log2 = g->scale * 1.4426950408889634f;
     C.forced = g->forced; C.tokens = g->tokens; C.history = g->history;

@@ -215,7 +215,7 @@ add_positions_kernel(const float* __restrict__ in, float* __restrict__ out, int 
 struct SpliceRows { int count; int start[KX_MAX_IMAGES]; };   // first spliced row of every image, ascending
 __global__ void __launch_bounds__(256)
 embed_splice_pos_kernel(const long long* __restrict__ tokens, int t_text, const float* __restrict__ embed, int vocab,
-                        const float* __restrict__ pos, int dim, const SpliceRows img, int n_img, float* __restrict__ x0,
+                        const float* __restrict__ pos, int dim, const SpliceRows img, int n_img, int alias, float* __restrict__ x0,
                         int* __restrict__ err_flag) {
     const int T = t_text + n_img * img.count;
     const int b = blockIdx.x / T;
@@ -239,6 +239,16 @@ embed_splice_pos_kernel(const long long* __restrict__ tokens, int t_text, const 
         return;
     }
     const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<long long>(t + 2) * dim);
+    if (alias) {
+        // torchscale's `x = embed = scale * tok; x += positions` (in place): the embeddings taken at model.py:238 already
+        // hold pos[ti + 2]; the second forward_embedding adds pos[t + 2].  Same association as the reference: (e + p1) + p2.
+        const float4* p1 = reinterpret_cast<const float4*>(pos + static_cast<long long>(ti + 2) * dim);
+        for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
+            const float4 a = __ldg(e + i), c1 = __ldg(p1 + i), c = __ldg(pp + i);
+            o[i] = make_float4((a.x + c1.x) + c.x, (a.y + c1.y) + c.y, (a.z + c1.z) + c.z, (a.w + c1.w) + c.w);
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
         const float4 a = __ldg(e + i), c = __ldg(pp + i);
         o[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
@@ -445,6 +455,27 @@ cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256)
+cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+    const long long nv = n >> 3;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        float4 a, b;
+        a.x = __uint_as_float(w[0] << 16); a.y = __uint_as_float(w[0] & 0xffff0000u);
+        a.z = __uint_as_float(w[1] << 16); a.w = __uint_as_float(w[1] & 0xffff0000u);
+        b.x = __uint_as_float(w[2] << 16); b.y = __uint_as_float(w[2] & 0xffff0000u);
+        b.z = __uint_as_float(w[3] << 16); b.w = __uint_as_float(w[3] & 0xffff0000u);
+        reinterpret_cast<float4*>(dst)[2 * i] = a;
+        reinterpret_cast<float4*>(dst)[2 * i + 1] = b;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+        const long long i = (nv << 3) + threadIdx.x;
+        dst[i] = __bfloat162float(src[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
 broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long row_elems, int copies) {
     const long long total = row_elems * copies;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -506,7 +537,7 @@ extern "C" int kx_rowstats_cast(const float* x, long long ld_x, void* xb, long l
 
 extern "C" int kx_embed_splice_pos(const long long* tokens, int batch, int t_text, const float* embed_table, int vocab,
                                    const float* pos_table, int pos_rows, int dim, const int* host_img_rows, int img_count,
-                                   int n_img, float* x0, int* err_flag, cudaStream_t stream) {
+                                   int n_img, int alias_positions, float* x0, int* err_flag, cudaStream_t stream) {
     if (!tokens || !embed_table || !x0) { set_error("kx_embed_splice_pos: null pointer"); return KX_ERR_ARG; }
     if (batch <= 0 || t_text <= 0 || n_img < 0 || (dim % 4) || img_count < 0 || img_count > KX_MAX_IMAGES ||
         (img_count > 0 && !host_img_rows)) {
@@ -530,7 +561,8 @@ extern "C" int kx_embed_splice_pos(const long long* tokens, int batch, int t_tex
         return KX_ERR_ARG;
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    embed_splice_pos_kernel<<<batch * T, 256, 0, stream>>>(tokens, t_text, embed_table, vocab, pos_table, dim, img, n_img, x0, err_flag);
+    embed_splice_pos_kernel<<<batch * T, 256, 0, stream>>>(tokens, t_text, embed_table, vocab, pos_table, dim, img, n_img,
+                                                           (alias_positions && pos_table) ? 1 : 0, x0, err_flag);
     return check_launch("kx_embed_splice_pos");
 }
 
@@ -647,6 +679,17 @@ extern "C" int kx_cast_f32_to_bf16(const float* src, void* dst, long long n, cud
     const int blocks = static_cast<int>(std::min<long long>((nv + 255) / 256, static_cast<long long>(sms) * 8));
     cast_f32_bf16_kernel<<<blocks, 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
     return check_launch("kx_cast_f32_to_bf16");
+}
+
+extern "C" int kx_cast_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream) {
+    if (!src || !dst || n <= 0 || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) {
+        set_error("kx_cast_bf16_to_f32: null / unaligned pointer or n <= 0");
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    const long long blocks = std::min<long long>(((n >> 3) + 255) / 256 + 1, 148ll * 16);
+    cast_bf16_f32_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+    return check_launch("kx_cast_bf16_to_f32");
 }
 
 extern "C" int kx_broadcast_rows(const float* src, float* dst, long long row_elems, int copies, cudaStream_t stream) {

@@ -437,40 +437,67 @@ xpos_bwd_kernel(__nv_bfloat16* __restrict__ dqkv, long long ld, int rows, int d_
 // ----------------------------------------------------------------------------- cross-entropy over text rows
 struct SpliceRowsT { int count; int start[KX_MAX_IMAGES]; };
 
-// Row t of the spliced sequence predicts text token ti+1 when it holds text token ti, ti+1 exists and row t+1 is not
-// an image row (the reference's intended loss keeps text positions only and drops the token in front of the image,
-// notes.txt:566-574).  Returns the target id, or -1 for "no loss at this row".
-__device__ __forceinline__ long long ce_target(const long long* __restrict__ tokens, int b, int t, int t_text, int n_img,
-                                               const SpliceRowsT& img) {
-    int ti = t;
-    bool next_is_img = false;
+// Next-token targets (see kx_loss_targets in the header).  One thread per row of the spliced sequence.
+__device__ __forceinline__ bool is_marker(int ti, int n_img, const SpliceRowsT& img) {
     for (int i = 0; i < img.count; ++i) {
-        if (t >= img.start[i]) {
-            if (t < img.start[i] + n_img) return -1;
-            ti -= n_img;
-        }
-        if (t + 1 == img.start[i]) next_is_img = true;
+        const int p = img.start[i] - i * n_img;              // image i sits in front of text token p
+        if (ti == p - 1 || ti == p) return true;             // `<image>`, `</image>` (model.py:70-77)
     }
-    if (next_is_img || ti + 1 >= t_text) return -1;
-    return tokens[static_cast<long long>(b) * t_text + ti + 1];
+    return false;
+}
+
+__global__ void __launch_bounds__(256)
+loss_targets_kernel(const long long* __restrict__ tokens, int batch, int t_text, int n_img, const SpliceRowsT img, int rule,
+                    long long ignore_token, long long* __restrict__ targets, float* __restrict__ count) {
+    const int T = t_text + n_img * img.count;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    int valid = 0;
+    if (row < batch * T) {
+        const int b = row / T, t = row - b * T;
+        int ti = t;
+        bool is_img = false, next_is_img = false;
+        for (int i = 0; i < img.count; ++i) {
+            if (t >= img.start[i]) {
+                if (t < img.start[i] + n_img) is_img = true;
+                ti -= n_img;
+            }
+            if (t + 1 == img.start[i]) next_is_img = true;
+        }
+        long long tgt = -100;
+        if (!is_img) {
+            if (rule == KX_LOSS_NEXT_TOKEN) {
+                if (!next_is_img && ti + 1 < t_text) tgt = tokens[static_cast<long long>(b) * t_text + ti + 1];
+            } else if (!is_marker(ti, n_img, img)) {
+                int nx = ti + 1;
+                while (nx < t_text && is_marker(nx, n_img, img)) ++nx;
+                if (nx < t_text) tgt = tokens[static_cast<long long>(b) * t_text + nx];
+            }
+        }
+        if (tgt >= 0 && tgt == ignore_token) tgt = -100;
+        targets[row] = tgt;
+        valid = tgt >= 0 ? 1 : 0;
+    }
+    if (count != nullptr) {
+        const unsigned mask = __ballot_sync(0xffffffffu, valid);
+        if ((threadIdx.x & 31) == 0 && mask) atomicAdd(count, static_cast<float>(__popc(mask)));
+    }
 }
 
 // One CTA per row.  Pass 1: online (max, sum exp) over the fp32 logits; pass 2 (L2-resident re-read): d(logits) =
-// (softmax - onehot) * inv_count as bf16, zero for rows without a target and for the pad columns [vocab, ld_d).
+// (softmax - onehot) / max(*count, 1) as bf16, zero for rows without a target and for the pad columns [vocab, ld_d).
 // loss_acc[0] += sum of row losses, loss_acc[1] += number of rows with a target.
 __global__ void __launch_bounds__(256)
-ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld_l, const long long* __restrict__ tokens, int t_text,
-                  int n_img, const SpliceRowsT img, int vocab, float inv_count, __nv_bfloat16* __restrict__ dlogits,
+ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld_l, const long long* __restrict__ targets, int vocab,
+                  const float* __restrict__ count, __nv_bfloat16* __restrict__ dlogits,
                   long long ld_d, float* __restrict__ loss_acc, int* __restrict__ err_flag) {
     __shared__ float red[16];
-    const int T = t_text + n_img * img.count;
     const int row = blockIdx.x;
-    const int b = row / T, t = row - b * T;
-    long long tgt = ce_target(tokens, b, t, t_text, n_img, img);
-    if (tgt >= vocab || tgt < -1) {
+    long long tgt = targets[row];
+    if (tgt >= vocab) {
         if (err_flag != nullptr && threadIdx.x == 0) atomicExch(err_flag, 1);
         tgt = -1;
     }
+    const float inv_count = 1.0f / fmaxf(count != nullptr ? __ldg(count) : 1.0f, 1.0f);
     __nv_bfloat16* drow = dlogits != nullptr ? dlogits + static_cast<long long>(row) * ld_d : nullptr;
     if (tgt < 0) {
         if (drow != nullptr)
@@ -523,7 +550,7 @@ ce_fwd_bwd_kernel(const float* __restrict__ logits, long long ld_l, const long l
 // as nn.Embedding(padding_idx=...).  fp32 vector atomics.
 __global__ void __launch_bounds__(256)
 embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ tokens, int t_text, int n_img,
-                 const SpliceRowsT img, int dim, int vocab, int padding_idx, float* __restrict__ d_embed,
+                 const SpliceRowsT img, int dim, int vocab, int padding_idx, int alias, float* __restrict__ d_embed,
                  float* __restrict__ d_pos) {
     const int T = t_text + n_img * img.count;
     const int b = blockIdx.x / T, t = blockIdx.x - b * T;
@@ -537,6 +564,8 @@ embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ to
     }
     const float4* src = reinterpret_cast<const float4*>(dx0 + static_cast<long long>(blockIdx.x) * dim);
     float4* pos = d_pos != nullptr ? reinterpret_cast<float4*>(d_pos + static_cast<long long>(t + 2) * dim) : nullptr;
+    // alias_positions (kx_embed_splice_pos): the row of text token ti also received pos[ti + 2]
+    float4* pos1 = (alias && !is_img && d_pos != nullptr) ? reinterpret_cast<float4*>(d_pos + static_cast<long long>(ti + 2) * dim) : nullptr;
     float4* emb = nullptr;
     if (!is_img && d_embed != nullptr) {
         const long long tok = tokens[static_cast<long long>(b) * t_text + ti];
@@ -545,6 +574,7 @@ embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ to
     for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) {
         const float4 v = src[i];
         if (pos != nullptr) atomicAdd(pos + i, v);
+        if (pos1 != nullptr) atomicAdd(pos1 + i, v);
         if (emb != nullptr) atomicAdd(emb + i, v);
     }
 }
@@ -811,27 +841,37 @@ extern "C" int kx_xpos_bwd(void* dqkv_bf16, long long ld, int rows, int d_model,
     return check_launch("kx_xpos_bwd");
 }
 
-extern "C" int kx_ce_fwd_bwd(const float* logits, long long ld_logits, const long long* tokens, int batch, int t_text,
-                             const int* host_img_rows, int img_count, int n_img, int vocab, float inv_count,
-                             void* dlogits_bf16, long long ld_dlogits, float* loss_acc, int* err_flag, cudaStream_t stream) {
-    if (!logits || !tokens || !loss_acc || batch <= 0 || t_text <= 0 || vocab <= 0 || n_img < 0 || (ld_logits % 2) ||
-        (reinterpret_cast<uintptr_t>(logits) & 7) ||
-        (dlogits_bf16 && ((ld_dlogits % 8) || ld_dlogits < vocab || !KX_ALIGNED16(dlogits_bf16)))) {
-        set_error("kx_ce_fwd_bwd: bad argument (logits rows 8-byte aligned; dlogits rows 16-byte aligned, ld >= vocab)");
+extern "C" int kx_loss_targets(const long long* tokens, int batch, int t_text, const int* host_img_rows, int img_count, int n_img,
+                               int rule, long long ignore_token, long long* targets, float* count, cudaStream_t stream) {
+    if (!tokens || !targets || batch <= 0 || t_text <= 0 || n_img < 0 || (rule != KX_LOSS_REFERENCE && rule != KX_LOSS_NEXT_TOKEN)) {
+        set_error("kx_loss_targets: bad argument (batch=%d t_text=%d n_img=%d rule=%d)", batch, t_text, n_img, rule);
         return KX_ERR_ARG;
     }
     const int T = t_text + n_img * img_count;
     SpliceRowsT img = {};
-    if (!fill_splice(img, host_img_rows, img_count, n_img, T, "kx_ce_fwd_bwd")) return KX_ERR_ARG;
+    if (!fill_splice(img, host_img_rows, img_count, n_img, T, "kx_loss_targets")) return KX_ERR_ARG;
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    ce_fwd_bwd_kernel<<<batch * T, 256, 0, stream>>>(logits, ld_logits, tokens, t_text, n_img, img, vocab, inv_count,
-                                                     reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_dlogits, loss_acc, err_flag);
+    loss_targets_kernel<<<(batch * T + 255) / 256, 256, 0, stream>>>(tokens, batch, t_text, n_img, img, rule, ignore_token, targets, count);
+    return check_launch("kx_loss_targets");
+}
+
+extern "C" int kx_ce_fwd_bwd(const float* logits, long long ld_logits, const long long* targets, int rows, int vocab,
+                             const float* count, void* dlogits_bf16, long long ld_dlogits, float* loss_acc, int* err_flag,
+                             cudaStream_t stream) {
+    if (!logits || !targets || !loss_acc || rows <= 0 || vocab <= 0 || (ld_logits % 2) || (reinterpret_cast<uintptr_t>(logits) & 7) ||
+        (dlogits_bf16 && ((ld_dlogits % 8) || ld_dlogits < vocab || !KX_ALIGNED16(dlogits_bf16)))) {
+        set_error("kx_ce_fwd_bwd: bad argument (logits rows 8-byte aligned; dlogits rows 16-byte aligned, ld >= vocab)");
+        return KX_ERR_ARG;
+    }
+    if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
+    ce_fwd_bwd_kernel<<<rows, 256, 0, stream>>>(logits, ld_logits, targets, vocab, count,
+                                                reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), ld_dlogits, loss_acc, err_flag);
     return check_launch("kx_ce_fwd_bwd");
 }
 
 extern "C" int kx_embed_bwd(const float* dx0, const long long* tokens, int batch, int t_text, const int* host_img_rows,
-                            int img_count, int n_img, int dim, int vocab, int padding_idx, float* d_embed, float* d_pos,
-                            cudaStream_t stream) {
+                            int img_count, int n_img, int dim, int vocab, int padding_idx, int alias_positions, float* d_embed,
+                            float* d_pos, cudaStream_t stream) {
     if (!dx0 || !tokens || batch <= 0 || t_text <= 0 || (dim % 4) || !KX_ALIGNED16(dx0) || (d_embed && !KX_ALIGNED16(d_embed)) ||
         (d_pos && !KX_ALIGNED16(d_pos))) {
         set_error("kx_embed_bwd: bad argument");
@@ -841,7 +881,8 @@ extern "C" int kx_embed_bwd(const float* dx0, const long long* tokens, int batch
     SpliceRowsT img = {};
     if (!fill_splice(img, host_img_rows, img_count, n_img, T, "kx_embed_bwd")) return KX_ERR_ARG;
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
-    embed_bwd_kernel<<<batch * T, 256, 0, stream>>>(dx0, tokens, t_text, n_img, img, dim, vocab, padding_idx, d_embed, d_pos);
+    embed_bwd_kernel<<<batch * T, 256, 0, stream>>>(dx0, tokens, t_text, n_img, img, dim, vocab, padding_idx, alias_positions ? 1 : 0,
+                                                    d_embed, d_pos);
     return check_launch("kx_embed_bwd");
 }
 

@@ -18,6 +18,7 @@ KX_EPI_GENERIC, KX_EPI_QKV_XPOS = 0, 1
 KX_MAX_IMAGES = 16
 KX_DEC_PLAIN, KX_DEC_RESIDUAL, KX_DEC_QKV = 0, 1, 2
 KX_DECODE_MAX_BATCH = 32
+KX_LOSS_REFERENCE, KX_LOSS_NEXT_TOKEN = 0, 1
 
 _f32p = C.c_void_p
 _vp = C.c_void_p
@@ -65,6 +66,7 @@ class DecodeStepArgs(C.Structure):
 
     _fields_ = [
         ("batch", _i), ("layers", _i), ("d_model", _i), ("ffn", _i), ("heads", _i), ("vocab", _i), ("t_max", _i), ("pos_rows", _i),
+        ("text_index_off", _i),
         ("eps", _f), ("scale", _f),
         ("w_qkv", _pp), ("c_qkv", _pp), ("d_qkv", _pp),
         ("w_o", _pp), ("c_o", _pp), ("d_o", _pp),
@@ -95,13 +97,19 @@ SIGNATURES = {
     "kx_perceiver_xattn_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "kx_layernorm_fwd": (_i, [_vp, _i, _ll, _f32p, _i, _i, _f32p, _f32p, _f, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
     "kx_add_positions": (_i, [_f32p, _f32p, _i, _i, _i, _f32p, _i, _vp]),
-    "kx_embed_splice_pos": (_i, [_vp, _i, _i, _f32p, _i, _f32p, _i, _i, C.POINTER(_i), _i, _i, _f32p, _vp, _vp]),
+    "kx_embed_splice_pos": (_i, [_vp, _i, _i, _f32p, _i, _f32p, _i, _i, C.POINTER(_i), _i, _i, _i, _f32p, _vp, _vp]),
     "kx_im2col_patches": (_i, [_f32p, _i, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
     "kx_clip_normalize_u8": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f32p, _vp]),
     "kx_im2col_patches_u8": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
     "kx_xpos_tables": (_i, [_f32p, _f32p, _i, _i, _f, _f32p, _f32p, _f32p, _f32p, _vp]),
     "kx_cast_f32_to_bf16": (_i, [_f32p, _vp, _ll, _vp]),
+    "kx_cast_bf16_to_f32": (_i, [_vp, _f32p, _ll, _vp]),
     "kx_broadcast_rows": (_i, [_f32p, _f32p, _ll, _i, _vp]),
+    # ---- verification precision (bf16x3)
+    "kx_split_bf16x3": (_i, [_f32p, _ll, _i, _i, _i, _vp, _ll, _i, _vp]),
+    "kx_attn_f32": (_i, [_f32p, _ll, _f32p, _f32p, _ll, _f32p, _ll, _i, _i, _i, _i, _i, _f, _vp]),
+    "kx_xpos_apply_f32": (_i, [_f32p, _ll, _i, _i, _i, _f32p, _f32p, _f32p, _f32p, _vp]),
+    "kx_im2col_patches_f32": (_i, [_f32p, _i, _i, _i, _i, _f32p, _i, _f32p, _f32p, _f32p, _i, _vp]),
     # ---- training step
     "kx_attn_fwd_lse": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _f32p, _vp]),
     "kx_attn_bwd": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _f32p, _vp, _vp, _vp, _ll, _f32p, _f32p,
@@ -118,8 +126,9 @@ SIGNATURES = {
     "kx_sum_rows_f32": (_i, [_f32p, _ll, _i, _ll, _f32p, _i, _vp]),
     "kx_colsum_bf16": (_i, [_vp, _ll, _i, _i, _f32p, _vp]),
     "kx_xpos_bwd": (_i, [_vp, _ll, _i, _i, _i, _f32p, _f32p, _f32p, _f32p, _vp]),
-    "kx_ce_fwd_bwd": (_i, [_f32p, _ll, _vp, _i, _i, C.POINTER(_i), _i, _i, _i, _f, _vp, _ll, _f32p, _vp, _vp]),
-    "kx_embed_bwd": (_i, [_f32p, _vp, _i, _i, C.POINTER(_i), _i, _i, _i, _i, _i, _f32p, _f32p, _vp]),
+    "kx_loss_targets": (_i, [_vp, _i, _i, C.POINTER(_i), _i, _i, _i, _ll, _vp, _f32p, _vp]),
+    "kx_ce_fwd_bwd": (_i, [_f32p, _ll, _vp, _i, _i, _f32p, _vp, _ll, _f32p, _vp, _vp]),
+    "kx_embed_bwd": (_i, [_f32p, _vp, _i, _i, C.POINTER(_i), _i, _i, _i, _i, _i, _i, _f32p, _f32p, _vp]),
     "kx_sumsq": (_i, [_f32p, _ll, _f32p, _vp]),
     "kx_clip_scale": (_i, [_f32p, _f, _f, _f32p, _f32p, _vp]),
     "kx_adamw_step": (_i, [_f32p, _f32p, _f32p, _f32p, _vp, _ll, _f, _f, _f, _f, _f, _i, _f32p, _vp]),
@@ -129,7 +138,7 @@ SIGNATURES = {
     "kx_decode_attn_scratch_bytes": (C.c_size_t, [_i, _i, _i]),
     "kx_decode_attn": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _vp, _f, _f32p, _vp, _vp, _ll, _vp]),
     "kx_kv_cache_store": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _vp]),
-    "kx_decode_embed": (_i, [_vp, _i, _f32p, _i, _f32p, _i, _vp, _i, _f32p, _vp, _vp, _vp]),
+    "kx_decode_embed": (_i, [_vp, _i, _f32p, _i, _f32p, _i, _vp, _i, _i, _f32p, _vp, _vp, _vp]),
     "kx_argmax_advance": (_i, [_f32p, _ll, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "kx_decode_plan_bytes": (C.c_size_t, [_i]),
     "kx_decode_step_ctas": (_i, []),

@@ -56,6 +56,11 @@ class KosmosConfig:
     p_latents: int = 64
     p_media_embeds: int = 257
     p_ff_mult: int = 4
+    # torchscale's Decoder.forward_embedding does `x = embed = embed_scale * token_embedding; x += positions` IN PLACE
+    # [recall], so the `[1]` result the reference takes at model.py:238 already carries the text positions and the second
+    # call (model.py:242-244) adds the spliced positions on top: text rows get TWO positional embeddings.  True reproduces
+    # that; False is the out-of-place reading (`x = x + positions`), one positional embedding per row.
+    alias_embed_positions: bool = True
 
     @property
     def vit_tokens(self) -> int:
@@ -285,6 +290,7 @@ class DecodeState:
         self.mid = torch.empty(batch, F, dtype=bf, device=device)
         self.logits = torch.empty(batch, cfg.vocab, dtype=f32, device=device)
         self.scratch, self.counters = ops.decode_attn_scratch(batch, H, t_max, device)
+        self.text_off = -1        # >= 0: new tokens also add pos[row + 2 - text_off] (alias_embed_positions; kx_decode_embed)
         self.tabs = None          # xPos tables [4, t_max, 32], centred like the prompt's (set by the prompt pass)
         self.graph = None         # captured (one step + greedy choice), replayed by Kosmos.generate
         self.plan = None          # flattened arguments of the one-kernel step (kx_decode_plan_build)
@@ -359,7 +365,7 @@ class Decoder(nn.Module):
             half = hd // 2
             # inv_freq exactly as the reference computes it on the host
             inv_freq = (1.0 / (10000 ** (torch.arange(0, half) / half))).to(device=device, dtype=torch.float32)
-            scale = self._pack()["xpos_scale"]
+            scale = _f32(self.layers[0].self_attn.xpos.scale)     # the buffer itself: no weight staging from here
             tabs = ops.xpos_tables(scale, inv_freq, T, (-T) // 2, float(self.cfg.xpos_scale_base), device)
             self._xpos_cache[T] = tabs
         return tabs
@@ -367,7 +373,9 @@ class Decoder(nn.Module):
     # ---- reference API ----------------------------------------------------------------
     def forward_embedding(self, tokens, token_embedding=None, incremental_state=None):
         """(x, embed) as torchscale's Decoder.forward_embedding.  ``tokens`` may be a
-        float (B,T,D) tensor when ``token_embedding`` is given — only its length is used."""
+        float (B,T,D) tensor when ``token_embedding`` is given — only its length is used.  With
+        ``cfg.alias_embed_positions`` (torchscale's in-place ``x += positions`` on ``x = embed = ...``) the second result
+        IS the first: ``embed`` carries the positions too, which is what model.py:238 then splices."""
         p = self._pack()
         T = tokens.size(1)
         if T + 2 > p["pos"].shape[0]:
@@ -383,14 +391,14 @@ class Decoder(nn.Module):
             embed = token_embedding.to(torch.float32).contiguous()
         x = torch.empty_like(embed)
         ops.add_positions(embed, x, p["pos"])
-        return x, embed
+        return (x, x) if self.cfg.alias_embed_positions else (x, embed)
 
     def _check_tokens(self, tokens):
         if tokens.dtype != torch.int64:
             raise TypeError("token ids must be int64")
 
     def run_layers(self, x: torch.Tensor, B: int, T: int, logits: torch.Tensor | None = None, head: bool = True,
-                   state: DecodeState | None = None):
+                   state: DecodeState | None = None, keep: dict | None = None):
         """24 x (sub-LN attention + sub-LN FFN) in place on the fp32 residual stream x [B*T, D], then (``head``)
         final LayerNorm + LM head -> fp32 logits [B*T, vocab].  5 launches per layer: every LayerNorm is folded
         into its consumer GEMM (row statistics travel as partial sums from the producer's epilogue)."""
@@ -429,16 +437,18 @@ class Decoder(nn.Module):
             w, c, d = L["fc2"]                                   # ffn_layernorm -> fc2 (+bias, +residual)
             ops.gemm(mid, w, x, bias=d, res=x, ln=(st_mid, c, F, eps), stats_out=st_b, out2=xb)
             cur = st_b
+            if keep is not None:                                 # per-stage parity tables (tools/stage_errors.py)
+                keep.setdefault("inner_states", []).append(x.view(B, T, D).clone())
         if not head:
             return x
         w, c, d = p["out"]                                       # decoder.layer_norm -> output_projection
         if logits is None:
             logits = torch.empty(M, w.shape[0], dtype=torch.float32, device=dev)
-        ops.gemm(xb, w, logits, bias=d, ln=(cur, c, D, eps))
+        ops.gemm(xb, w, logits[:, :w.shape[0]], bias=d, ln=(cur, c, D, eps))      # bf16 logits: rows padded to 16 bytes
         return logits
 
     # ---- incremental decoding ------------------------------------------
-    def begin_generation(self, x: torch.Tensor, B: int, T: int, t_max: int, head="all") -> tuple[DecodeState, torch.Tensor]:
+    def begin_generation(self, x: torch.Tensor, B: int, T: int, t_max: int, head="all", text_off: int = -1) -> tuple[DecodeState, torch.Tensor]:
         """Prompt pass: the ordinary layers over x [B*T, D] (updated in place) with every layer's rotated k / v stored
         in a fresh cache of t_max rows.  head = "all": logits of every row [B*T, vocab]; "last": only the last row of
         each sequence, in state.logits [B, vocab] (what a generation loop needs)."""
@@ -446,6 +456,7 @@ class Decoder(nn.Module):
             raise ValueError(f"t_max {t_max} is shorter than the prompt ({T})")
         cfg, p = self.cfg, self._pack()
         state = DecodeState(cfg, B, t_max, x.device)
+        state.text_off = text_off
         half = cfg.dim // cfg.heads // 2
         inv_freq = (1.0 / (10000 ** (torch.arange(0, half) / half))).to(device=x.device, dtype=torch.float32)
         state.tabs = ops.xpos_tables(p["xpos_scale"], inv_freq, t_max, (-T) // 2, float(cfg.xpos_scale_base), x.device)
@@ -467,7 +478,7 @@ class Decoder(nn.Module):
         the next-token logits in state.logits.  Does not advance the position (kx_argmax_advance does).  5 launches
         per layer, all reading the position from device memory, so the sequence is CUDA-graph replayable."""
         p = self._pack()
-        ops.decode_embed(state.tok, p["embed"], p["pos"], state.pos, state.x, state.xb, state.err)
+        ops.decode_embed(state.tok, p["embed"], p["pos"], state.pos, state.x, state.xb, state.err, text_index_off=state.text_off)
         self._decode_layers(state)
 
     def _decode_layers(self, state: DecodeState):
@@ -499,7 +510,7 @@ class Decoder(nn.Module):
             k_cache=[state.k[i] for i in range(cfg.layers)], v_cache=[state.v[i] for i in range(cfg.layers)],
             tokens=state.tok, x=state.x, xb=state.xb, q=state.q, att=state.att, mid=state.mid, logits=state.logits,
             keys=state.keys, pos=state.pos, step=state.step, err_flag=state.err, barrier=barrier, heads=cfg.heads, ffn=cfg.ffn, t_max=state.t_max, eps=cfg.eps,
-            scale=(cfg.dim // cfg.heads) ** -0.5, forced=forced, history=history, trace=trace)
+            scale=(cfg.dim // cfg.heads) ** -0.5, forced=forced, history=history, trace=trace, text_index_off=state.text_off)
         return state.plan
 
     def advance(self, state: DecodeState, history=None, forced=None, move=True):
@@ -576,6 +587,17 @@ class _KosmosBase(nn.Module):
         if hasattr(self, "_ws"):
             self._ws.clear()
         self._graphs = {}
+        if getattr(self, "_acc", None) is not None:
+            self._acc.invalidate()
+
+    _PRECISIONS = ("bf16", "bf16x3")
+
+    def _accurate(self):
+        """The verification-precision engine (kosmosx/accurate.py), built on first use."""
+        if getattr(self, "_acc", None) is None:
+            from .accurate import AccurateEngine
+            self._acc = AccurateEngine(self)
+        return self._acc
 
     def load_state_dict(self, *a, **kw):
         r = super().load_state_dict(*a, **kw)
@@ -649,7 +671,7 @@ class _KosmosBase(nn.Module):
         return res
 
     def _generate(self, x0: torch.Tensor, B: int, T: int, max_new_tokens: int, forced=None, return_logits=False,
-                  cuda_graph=True, one_kernel=None):
+                  cuda_graph=True, one_kernel=None, text_off: int = -1):
         """Greedy continuation of the embedded prompt x0 [B*T, D]: prompt pass with cache fill and
         the LM head on the last rows only, then max_new_tokens - 1 one-token steps.  The step + greedy choice is
         captured once as a CUDA graph and replayed (the position is device-resident), so no host value is read until
@@ -659,7 +681,7 @@ class _KosmosBase(nn.Module):
             raise ValueError("max_new_tokens must be >= 1")
         dec = self.decoder
         dev = x0.device
-        state, _ = dec.begin_generation(x0, B, T, T + max_new_tokens, head="last")
+        state, _ = dec.begin_generation(x0, B, T, T + max_new_tokens, head="last", text_off=text_off)
         history = torch.zeros(B, max_new_tokens, dtype=torch.int64, device=dev)
         if forced is not None:
             _require_cuda(forced, "forced tokens")
@@ -730,12 +752,27 @@ class Kosmos(_KosmosBase):
     ``Kosmos()`` takes no positional arguments, like the reference.  Keyword-only extras:
     ``config`` (KosmosConfig), ``device``, ``max_positions`` (the reference's 2048-row table caps the
     spliced length at 2046), ``cuda_graph`` (replay the whole forward as one CUDA
-    graph per input shape).
+    graph per input shape; the logits are copied out of the graph's buffer so the caller owns them, as with the
+    reference — ``graph_alias_output=True`` skips that copy and returns a view of one of two alternating graph
+    buffers, valid until the second-next call with the same shapes), ``logits_dtype`` (torch.float32, or
+    torch.bfloat16 = what the reference returns when the module is cast to bf16: the LM head stores bf16 rows padded
+    to a 16-byte pitch through the TMA-store epilogue and ``forward`` returns the (B, T, vocab) view of them),
+    ``precision``: "bf16" (tensor-core operands rounded to bf16, the speed mode) or "bf16x3" (verification
+    mode: split-operand GEMMs + fp32 everywhere else, logits within 1e-3 of the fp32 reference —
+    kosmosx/accurate.py; may also be switched per call with ``forward(..., precision=...)``).
     """
 
     def __init__(self, *, config: KosmosConfig | None = None, device=None, max_positions: int | None = None,
-                 cuda_graph: bool = False):
+                 cuda_graph: bool = False, precision: str = "bf16", graph_alias_output: bool = False,
+                 logits_dtype: torch.dtype = torch.float32):
         super().__init__()
+        if logits_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("logits_dtype must be torch.float32 or torch.bfloat16")
+        self.logits_dtype = logits_dtype
+        self.graph_alias_output = graph_alias_output
+        if precision not in self._PRECISIONS:
+            raise ValueError(f"precision must be one of {self._PRECISIONS}")
+        self.precision = precision
         cfg = config or KosmosConfig()
         if max_positions is not None:
             cfg.max_positions = max_positions
@@ -890,7 +927,7 @@ class Kosmos(_KosmosBase):
 
     # ---- forward ------------------------------------------------------------------------
     def _forward_impl(self, text_tokens: torch.Tensor, images: torch.Tensor, logits: torch.Tensor | None = None,
-                      img_rows=(2,)):
+                      img_rows=(2,), keep: dict | None = None):
         """images: (B*m, 3, H, W) fp32 (or raw uint8, planar / channels-last) in (sequence, image) order, m = len(img_rows)."""
         cfg = self.cfg
         B, t_text = text_tokens.shape
@@ -900,8 +937,34 @@ class Kosmos(_KosmosBase):
         x0 = self._ws.get("x0", (B * T, cfg.dim), torch.float32, text_tokens.device)
         xv = self._vit(images, media=m)
         self._perceive_project(xv, B, x0, T, img_rows)
-        ops.embed_splice_pos(text_tokens, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=Lq, err_flag=self._err_flag())
-        return self.decoder.run_layers(x0, B, T, logits)
+        ops.embed_splice_pos(text_tokens, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=Lq, err_flag=self._err_flag(),
+                             alias_positions=cfg.alias_embed_positions)
+        if keep is not None:
+            keep["vit"] = xv.view(-1, cfg.vit_tokens, cfg.vit_dim).clone()
+            keep["x0"] = x0.view(B, T, cfg.dim).clone()
+            keep["inner_states"] = [keep["x0"]]
+        if logits is None:
+            logits = self._new_logits(B * T, x0.device)
+        return self.decoder.run_layers(x0, B, T, logits, keep=keep)
+
+    @torch.no_grad()
+    def stages(self, text_tokens, images, image_positions=None, precision: str | None = None) -> dict:
+        """Intermediate tensors of one forward (the oracle's ``stages`` keys: vit, x0, inner_states, logits) for per-stage
+        parity tables; eager, never graphed."""
+        text_tokens, images, img_rows, T = self._prepare_inputs(text_tokens, images, image_positions)
+        keep = {}
+        if (precision or self.precision) == "bf16x3":
+            logits = self._accurate().forward(text_tokens, images, img_rows, keep=keep)
+        else:
+            logits = self._forward_impl(text_tokens, images, img_rows=img_rows, keep=keep)
+        keep["logits"] = logits.view(text_tokens.shape[0], T, -1)[..., :self.cfg.vocab]
+        return keep
+
+    def _new_logits(self, M, device):
+        """fp32 [M, vocab], or bf16 [M, vocab rounded up to 8] (16-byte row pitch: the TMA-store epilogue applies)."""
+        if self.logits_dtype == torch.float32:
+            return torch.empty(M, self.cfg.vocab, dtype=torch.float32, device=device)
+        return torch.empty(M, (self.cfg.vocab + 7) // 8 * 8, dtype=torch.bfloat16, device=device)
 
     def _err_flag(self):
         f = getattr(self, "_errf", None)
@@ -950,7 +1013,7 @@ class Kosmos(_KosmosBase):
         return text_tokens.contiguous(), images, img_rows, T
 
     def forward(self, text_tokens: torch.Tensor, images: torch.Tensor, image_positions=None, normalize_images: bool = False,
-                **kwargs):
+                precision: str | None = None, **kwargs):
         """Reference call (model.py:208-253): images (B,3,H,W), features spliced in front of text token 2.
         Extension (BASELINE.json configs[4]): images (B,m,3,H,W) with ``image_positions`` = m ascending text-token
         indices; image i's 64 feature rows are spliced in front of text token image_positions[i].
@@ -971,11 +1034,20 @@ class Kosmos(_KosmosBase):
             B = text_tokens.shape[0]
             if self.training and torch.is_grad_enabled():
                 return self._forward_train(text_tokens, images, img_rows)
+            precision = precision or self.precision
+            if precision not in self._PRECISIONS:
+                raise ValueError(f"precision must be one of {self._PRECISIONS}")
+            if precision == "bf16x3":
+                if images.dtype == torch.uint8:          # raw pixels: the bit-exact device normalise, then fp32 from there on
+                    images = ops.clip_normalize_u8(images, image=cfg.image)
+                return self._accurate().forward(text_tokens, images, img_rows).view(B, T, cfg.vocab)
             if self.cuda_graph:
                 logits = self._forward_graphed(text_tokens, images, img_rows)
+                if not self.graph_alias_output:
+                    logits = logits.clone()              # the caller owns the result (reference semantics)
             else:
                 logits = self._forward_impl(text_tokens, images, img_rows=img_rows)
-            return logits.view(B, T, cfg.vocab)
+            return logits.view(B, T, -1)[..., :cfg.vocab]
         except Exception as e:
             log.error(f"Failed during model forward pass: {e}")
             raise
@@ -1013,8 +1085,11 @@ class Kosmos(_KosmosBase):
         xv = self._vit(images, media=m)
         self._perceive_project(xv, B, x0, T, img_rows)
         ops.embed_splice_pos(text_tokens, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=cfg.p_latents,
-                             err_flag=self._err_flag())
-        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph, one_kernel)
+                             err_flag=self._err_flag(), alias_positions=cfg.alias_embed_positions)
+        # a generated token continues the TEXT: under alias_embed_positions it takes its text-index position too, so that
+        # a step equals Kosmos.forward over the grown text (what a user of the reference, which has no generate, would run)
+        text_off = cfg.p_latents * m if cfg.alias_embed_positions else -1
+        return self._generate(x0, B, T, int(max_new_tokens), forced_tokens, return_logits, cuda_graph, one_kernel, text_off)
 
     def check_tokens(self):
         """Host-side check (one sync) that no token id of any forward so far was out of range."""
@@ -1033,7 +1108,7 @@ class Kosmos(_KosmosBase):
             st_tok, st_img = text_tokens.clone(), images.clone()
             B, t_text = text_tokens.shape
             M = B * (t_text + self.cfg.p_latents * len(img_rows))
-            outs = [torch.empty(M, self.cfg.vocab, dtype=torch.float32, device=text_tokens.device) for _ in range(2)]
+            outs = [self._new_logits(M, text_tokens.device) for _ in range(2)]
             self._forward_impl(st_tok, st_img, outs[0], img_rows)   # warm-up: stages weights, allocates workspaces
             torch.cuda.synchronize()
             graphs = []
@@ -1063,8 +1138,12 @@ class KosmosLanguage(_KosmosBase):
     def __init__(self, vocab_size: int = 64007, dim: int = 2048, depth: int = 24, ffn_dim: int = 8192,
                  dropout: float = 0.1, multiway: bool = True, decoder_heads: int = 32, activation_fn: str = "gelu",
                  subln: bool = True, alibi_pos_bias: bool = True, alibi_num_heads: int = 16, xpos_rel_pos: bool = True,
-                 max_rel_pos: int = 2048, *args, device=None, max_positions: int | None = None, **kwargs):
+                 max_rel_pos: int = 2048, *args, device=None, max_positions: int | None = None, precision: str = "bf16",
+                 **kwargs):
         super().__init__()
+        if precision not in self._PRECISIONS:
+            raise ValueError(f"precision must be one of {self._PRECISIONS}")
+        self.precision = precision
         if activation_fn != "gelu" or not subln or not xpos_rel_pos:
             raise NotImplementedError("the B200 build implements the reference configuration: gelu, subln, xpos")
         cfg = KosmosConfig(vocab=vocab_size, dim=dim, layers=depth, ffn=ffn_dim, heads=decoder_heads, multiway=multiway,
@@ -1090,6 +1169,8 @@ class KosmosLanguage(_KosmosBase):
         B, T = x.shape
         if T + 2 > self.cfg.max_positions:
             raise ValueError(f"sequence length {T} exceeds the positional table: max is {self.cfg.max_positions - 2}")
+        if (kwargs.get("precision") or self.precision) == "bf16x3":
+            return self._accurate().forward_language(x).view(B, T, self.cfg.vocab)
         dp = self.decoder._pack()
         x0 = self._ws.get("x0", (B * T, self.cfg.dim), torch.float32, x.device)
         ops.embed_splice_pos(x.contiguous(), dp["embed"], dp["pos"], x0)

@@ -275,26 +275,44 @@ def _rows(img_rows):
     return (_abi.C.c_int * max(1, len(img_rows)))(*[int(r) for r in img_rows])
 
 
-def ce_fwd_bwd(logits, tokens, loss_acc, *, img_rows=(), n_img=0, inv_count=1.0, dlogits=None, err_flag=None):
-    """loss_acc fp32 [2] += (sum of row losses, rows counted); dlogits bf16 [B*T, ld >= vocab (multiple of 8)] or None."""
-    _req(logits, torch.float32, "logits"); _req(tokens, torch.int64, "tokens"); _req(loss_acc, torch.float32, "loss_acc")
+_LOSS_RULES = {"reference": _abi.KX_LOSS_REFERENCE, "next_token": _abi.KX_LOSS_NEXT_TOKEN}
+
+
+def loss_targets(tokens, targets, count, *, img_rows=(), n_img=0, rule="reference", ignore_token=None):
+    """targets int64 [B, T] (-100 = no loss) for the spliced sequence; count fp32 [1] += rows with a target."""
+    _req(tokens, torch.int64, "tokens"); _req(targets, torch.int64, "targets")
+    if rule not in _LOSS_RULES:
+        raise ValueError(f"loss rule must be one of {sorted(_LOSS_RULES)}")
     B, t_text = tokens.shape
+    if targets.numel() != B * (t_text + n_img * len(img_rows)) or not targets.is_contiguous():
+        raise ValueError("loss_targets: targets must be contiguous [B, T]")
+    check(lib.kx_loss_targets(tokens.data_ptr(), B, t_text, _rows(img_rows), len(img_rows), n_img, _LOSS_RULES[rule],
+                              -1 if ignore_token is None else int(ignore_token), targets.data_ptr(), _ptr(count), _stream()),
+          "kx_loss_targets")
+    return targets
+
+
+def ce_fwd_bwd(logits, targets, loss_acc, *, count=None, dlogits=None, err_flag=None):
+    """loss_acc fp32 [2] += (sum of row losses, rows counted); dlogits bf16 [rows, ld >= vocab (multiple of 8)] or None;
+    count: device fp32 scalar, the gradient is divided by max(count, 1)."""
+    _req(logits, torch.float32, "logits"); _req(targets, torch.int64, "targets"); _req(loss_acc, torch.float32, "loss_acc")
+    if targets.numel() != logits.shape[0] or not targets.is_contiguous():
+        raise ValueError("ce_fwd_bwd: one target per logits row")
     with _Timed("ce_fwd_bwd", 0.0, 10.0 * logits.shape[0] * logits.shape[1]):
-        check(lib.kx_ce_fwd_bwd(logits.data_ptr(), logits.stride(0), tokens.data_ptr(), B, t_text, _rows(img_rows),
-                                len(img_rows), n_img, logits.shape[1], float(inv_count), _ptr(dlogits),
-                                0 if dlogits is None else dlogits.stride(0), loss_acc.data_ptr(), _ptr(err_flag), _stream()),
-              "kx_ce_fwd_bwd")
+        check(lib.kx_ce_fwd_bwd(logits.data_ptr(), logits.stride(0), targets.data_ptr(), logits.shape[0], logits.shape[1],
+                                _ptr(count), _ptr(dlogits), 0 if dlogits is None else dlogits.stride(0), loss_acc.data_ptr(),
+                                _ptr(err_flag), _stream()), "kx_ce_fwd_bwd")
     return loss_acc
 
 
-def embed_bwd(dx0, tokens, d_embed, d_pos, *, img_rows=(), n_img=0, padding_idx=1):
+def embed_bwd(dx0, tokens, d_embed, d_pos, *, img_rows=(), n_img=0, padding_idx=1, alias_positions=False):
     _req(dx0, torch.float32, "dx0"); _req(tokens, torch.int64, "tokens")
     B, t_text = tokens.shape
     dim = dx0.shape[-1]
     vocab = d_embed.shape[0] if d_embed is not None else 0
     with _Timed("embed_bwd", 0.0, 12.0 * dx0.numel()):
         check(lib.kx_embed_bwd(dx0.data_ptr(), tokens.data_ptr(), B, t_text, _rows(img_rows), len(img_rows), n_img, dim,
-                               vocab, padding_idx, _ptr(d_embed), _ptr(d_pos), _stream()), "kx_embed_bwd")
+                               vocab, padding_idx, 1 if alias_positions else 0, _ptr(d_embed), _ptr(d_pos), _stream()), "kx_embed_bwd")
 
 
 def sumsq(g, out):
@@ -360,9 +378,10 @@ def rowstats_cast(x, xb, stats):
     return xb
 
 
-def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_rows=(), n_img=0, err_flag=None):
+def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_rows=(), n_img=0, err_flag=None, alias_positions=False):
     """Text rows of the spliced sequence: gather + position.  img_rows = first spliced row of every image
-    (ascending; the reference is (2,)); each image takes n_img rows, written by the image_proj GEMM."""
+    (ascending; the reference is (2,)); each image takes n_img rows, written by the image_proj GEMM.
+    alias_positions: text token i at row t gets pos[i+2] + pos[t+2] (torchscale's in-place `x += positions`)."""
     _req(tokens, torch.int64, "tokens")
     B, t_text = tokens.shape
     if not tokens.is_contiguous():
@@ -371,7 +390,7 @@ def embed_splice_pos(tokens, embed_table, pos_table, x0, *, img_rows=(), n_img=0
     with _Timed("embed_splice_pos", 0.0, 12.0 * B * t_text * embed_table.shape[1]):
         check(lib.kx_embed_splice_pos(tokens.data_ptr(), B, t_text, embed_table.data_ptr(), embed_table.shape[0],
                                       _ptr(pos_table), 0 if pos_table is None else pos_table.shape[0],
-                                      embed_table.shape[1], rows, len(img_rows), n_img,
+                                      embed_table.shape[1], rows, len(img_rows), n_img, 1 if alias_positions else 0,
                                       x0.data_ptr(), _ptr(err_flag), _stream()), "kx_embed_splice_pos")
     return x0
 
@@ -464,9 +483,60 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor | None = None) -> torch.Tenso
     return dst
 
 
+def cast_f32(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    _req(src, torch.bfloat16, "src"); _req(dst, torch.float32, "dst")
+    if src.numel() != dst.numel() or not src.is_contiguous() or not dst.is_contiguous():
+        raise ValueError("cast_f32: src and dst must be contiguous and of equal size")
+    check(lib.kx_cast_bf16_to_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "kx_cast_bf16_to_f32")
+    return dst
+
+
 def broadcast_rows(src, dst, copies):
     check(lib.kx_broadcast_rows(src.data_ptr(), dst.data_ptr(), src.numel(), copies, _stream()), "kx_broadcast_rows")
     return dst
+
+
+# ---- verification precision (bf16x3) -------------------------------------------------------------
+def split_bf16x3(src, dst=None, *, weights=False, n_pad=None):
+    """fp32 [rows, n] -> bf16 [rows, 3*n_pad]: (hi | hi | lo) for activations, (hi | lo | hi) for weights, so that ONE
+    kx_gemm_bf16 over K' = 3*n_pad accumulates Ah.Wh + Ah.Wl + Al.Wh in the same TMEM tile."""
+    _req(src, torch.float32, "src")
+    rows, n = src.shape
+    n_pad = (n + 7) // 8 * 8 if n_pad is None else n_pad
+    if dst is None:
+        dst = torch.empty(rows, 3 * n_pad, dtype=torch.bfloat16, device=src.device)
+    _req(dst, torch.bfloat16, "dst")
+    with _Timed("split_bf16x3", 0.0, 10.0 * rows * n):
+        check(lib.kx_split_bf16x3(src.data_ptr(), src.stride(0), rows, n, n_pad, dst.data_ptr(), dst.stride(0),
+                                  1 if weights else 0, _stream()), "kx_split_bf16x3")
+    return dst
+
+
+def attention_f32(q, k, v, out, *, batch, heads, n_q, n_kv, causal, scale):
+    """fp32 softmax(q.k^T*scale).v, head_dim 64; q [batch*n_q, ld], k / v [batch*n_kv, ld_kv] column blocks."""
+    for n, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        _req(t, torch.float32, n)
+    if k.stride(0) != v.stride(0):
+        raise ValueError("attention_f32: k and v must share a row pitch")
+    with _Timed("attn_f32", 4.0 * batch * heads * n_q * n_kv * 64 * (0.5 if causal else 1.0)):
+        check(lib.kx_attn_f32(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(), out.stride(0),
+                              batch, heads, n_q, n_kv, 1 if causal else 0, float(scale), _stream()), "kx_attn_f32")
+    return out
+
+
+def xpos_apply_f32(qkv, d_model, seq_len, tabs):
+    _req(qkv, torch.float32, "qkv")
+    check(lib.kx_xpos_apply_f32(qkv.data_ptr(), qkv.stride(0), qkv.shape[0], d_model, seq_len, *[t.data_ptr() for t in tabs],
+                                _stream()), "kx_xpos_apply_f32")
+    return qkv
+
+
+def im2col_patches_f32(pixels, patches, class_embedding, pos_table, x, *, image, patch, media=1):
+    _req(pixels, torch.float32, "pixels"); _req(patches, torch.float32, "patches")
+    check(lib.kx_im2col_patches_f32(pixels.data_ptr(), pixels.shape[0], media, image, patch, patches.data_ptr(), patches.shape[1],
+                                    class_embedding.data_ptr(), pos_table.data_ptr(), x.data_ptr(), x.shape[-1], _stream()),
+          "kx_im2col_patches_f32")
+    return patches
 
 
 # ---- incremental decoding ----------------------------------------------------------------------
@@ -530,10 +600,10 @@ def kv_cache_store(qkv, k_cache, v_cache, *, batch, seq_len, d_model, t_max):
                                     v_cache.data_ptr(), t_max, _stream()), "kx_kv_cache_store")
 
 
-def decode_embed(tokens, embed_table, pos_table, pos, x, xb, err_flag=None):
+def decode_embed(tokens, embed_table, pos_table, pos, x, xb, err_flag=None, text_index_off=-1):
     _req(tokens, torch.int64, "tokens")
     check(lib.kx_decode_embed(tokens.data_ptr(), tokens.numel(), embed_table.data_ptr(), embed_table.shape[0],
-                              pos_table.data_ptr(), pos_table.shape[0], pos.data_ptr(), embed_table.shape[1], x.data_ptr(),
+                              pos_table.data_ptr(), pos_table.shape[0], pos.data_ptr(), int(text_index_off), embed_table.shape[1], x.data_ptr(),
                               xb.data_ptr(), _ptr(err_flag), _stream()), "kx_decode_embed")
 
 
@@ -558,12 +628,14 @@ def decode_step_buffers(layers, device):
 
 
 def decode_plan_build(plan, *, layers, out, embed_table, pos_table, tabs, k_cache, v_cache, tokens, x, xb, q, att, mid, logits,
-                      keys, pos, step, err_flag, barrier, heads, ffn, t_max, eps, scale, forced=None, history=None, trace=None):
+                      keys, pos, step, err_flag, barrier, heads, ffn, t_max, eps, scale, forced=None, history=None, trace=None,
+                      text_index_off=-1):
     """layers: list of dicts with (w, c, d) triples under "qkv", "o", "fc1", "fc2"; out: the (w, c, d) of the LM head."""
     g = _abi.DecodeStepArgs()
     B, D = x.shape
     g.batch, g.layers, g.d_model, g.ffn, g.heads, g.vocab, g.t_max = B, len(layers), D, ffn, heads, out[0].shape[0], t_max
     g.pos_rows, g.eps, g.scale = pos_table.shape[0], eps, scale
+    g.text_index_off = int(text_index_off)
     keep = []
     for name in ("qkv", "o", "fc1", "fc2"):
         for j, letter in enumerate("wcd"):

@@ -47,12 +47,27 @@ class KosmosTrainer:
 
     def __init__(self, model: Kosmos, *, optimizer: str = "adamw", lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
                  weight_decay: float = 0.1, max_grad_norm: float = 1.0, process_group=None, overlap_all_reduce: bool = True,
-                 train_resampler: bool = True, layout_only: bool = False):
+                 train_resampler: bool = True, layout_only: bool = False, loss_rule: str = "reference",
+                 pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.float32):
+        """loss_rule: "reference" = the rows / targets of the reference's intended loop (notes.txt:566-574: the `<image>`
+        `</image>` markers and the feature rows carry no loss and are never targets; row 0 predicts the first real text
+        token), "next_token" = plain shift by one over the text rows.  pad_token_id: targets equal to it are ignored
+        (None = the reference's loop, which masks nothing).  lr_schedule: callable step -> multiplier of ``lr`` (see
+        ``cosine_with_warmup``), evaluated on the host from the step COUNT — no device value is read.
+        grad_reduce_dtype: torch.float32 all-reduces the flat fp32 gradient buffer; torch.bfloat16 exchanges a bf16
+        copy (half the NVLink bytes, the reference's FSDP ``reduce_dtype`` is 16-bit too, train.py:156-162) and
+        accumulates the received sums back in fp32."""
         if optimizer not in ("adamw", "lion"):
             raise ValueError("optimizer must be 'adamw' or 'lion' (train.py:375-386)")
+        if loss_rule not in ("reference", "next_token"):
+            raise ValueError("loss_rule must be 'reference' or 'next_token'")
+        if grad_reduce_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("grad_reduce_dtype must be torch.float32 or torch.bfloat16")
         self.model = model
         self.cfg = model.cfg
         self.opt, self.lr, self.betas, self.eps, self.wd = optimizer, lr, betas, eps, weight_decay
+        self.loss_rule, self.pad_token_id, self.lr_schedule = loss_rule, pad_token_id, lr_schedule
+        self.grad_reduce_dtype = grad_reduce_dtype
         self.max_grad_norm = max_grad_norm
         self.pg = process_group
         self.overlap = overlap_all_reduce
@@ -193,7 +208,8 @@ class KosmosTrainer:
             vis = self._resampler_forward(xv, B, x, T, img_rows, pos)
         else:
             m._perceive_project(xv, B, x, T, img_rows, pos_table=pos)
-        ops.embed_splice_pos(text_tokens, m.embed.weight, pos, x, img_rows=img_rows, n_img=Lq, err_flag=m._err_flag())
+        ops.embed_splice_pos(text_tokens, m.embed.weight, pos, x, img_rows=img_rows, n_img=Lq, err_flag=m._err_flag(),
+                             alias_positions=cfg.alias_embed_positions)
         tabs = dp._xpos(T, x.device)
         scale = (D // H) ** -0.5
         saved = []
@@ -340,19 +356,6 @@ class KosmosTrainer:
         ops.sum_rows_f32(dlat.view(N, Lq * Dv), self._g(pv.latents).view(-1))
 
     # ------------------------------------------------------------------ loss + backward
-    @staticmethod
-    def n_loss_rows(B, t_text, img_rows, n_lat):
-        """Rows that carry a loss (host arithmetic on shapes only): every text token except the last one and the
-        ones whose next row starts an image block (same rule as kx_ce_fwd_bwd)."""
-        T = t_text + n_lat * len(img_rows)
-        img = [False] * T
-        for r in img_rows:
-            for i in range(r, r + n_lat):
-                img[i] = True
-        text_rows = [t for t in range(T) if not img[t]]
-        dropped = 1 + sum(1 for t in text_rows[:-1] if t + 1 in set(img_rows))
-        return B * (t_text - dropped)
-
     def _backward(self, fw, text_tokens, img_rows, dlogits_in=None, accumulate=False):
         """dlogits_in = None: the fused cross-entropy (loss + its gradient) starts the backward pass; otherwise the
         caller's gradient w.r.t. the logits (B, T, V) does (the autograd bridge of ``Kosmos.forward`` in train mode).
@@ -369,18 +372,24 @@ class KosmosTrainer:
         bf, f32 = torch.bfloat16, torch.float32
         Lq = cfg.p_latents
         dp = m.decoder
-        n_rows = self.n_loss_rows(B, text_tokens.shape[1], img_rows, Lq)
         Vp = _round_up(V)
         dlogits = self._buf("dlogits", (M, Vp), bf)
         self.scalars.zero_()
         self.G.zero_()
         if dlogits_in is None:
-            ops.ce_fwd_bwd(fw["logits"], text_tokens, self.scalars[0:2], img_rows=img_rows, n_img=Lq,
-                           inv_count=1.0 / max(n_rows, 1), dlogits=dlogits, err_flag=m._err_flag())
+            # targets and the number of rows that carry a loss are derived on the device (no host arithmetic on shapes,
+            # pad masking included): scalars[5] = count, read by the cross-entropy kernel for its 1/count
+            targets = self._buf("targets", (B, T), torch.int64)
+            ops.loss_targets(text_tokens, targets, self.scalars[5:6], img_rows=img_rows, n_img=Lq, rule=self.loss_rule,
+                             ignore_token=self.pad_token_id)
+            ops.ce_fwd_bwd(fw["logits"], targets.view(-1), self.scalars[0:2], count=self.scalars[5:6], dlogits=dlogits,
+                           err_flag=m._err_flag())
         else:       # the caller's loss lives in PyTorch: one cast of its gradient into the bf16 GEMM operand (rows padded to Vp)
             if tuple(dlogits_in.shape) != (B, T, V) or not dlogits_in.is_cuda:
                 raise ValueError(f"gradient w.r.t. the logits must be a CUDA tensor of shape {(B, T, V)}")
             dlogits[:, :V].copy_(dlogits_in.reshape(M, V))
+            if Vp > V:
+                dlogits[:, V:].zero_()
         dl = dlogits[:, :V]
         P = ops.ln_bwd_partials(M)
         part_d = self._buf("part_d", (3, P, D), f32)
@@ -435,12 +444,17 @@ class KosmosTrainer:
                               eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(prev["fc2"].bias) if prev else None)
             self._bucket_ready(li, works)                     # (fc2.bias of layer li was written by layer li+1's LayerNorm backward)
         ops.embed_bwd(dx, text_tokens, self._g(m.embed.weight), self._g(m.embed_positions.weight), img_rows=img_rows, n_img=Lq,
-                      padding_idx=m.embed.padding_idx if m.embed.padding_idx is not None else -1)
+                      padding_idx=m.embed.padding_idx if m.embed.padding_idx is not None else -1,
+                      alias_positions=cfg.alias_embed_positions)
         if fw["vis"] is not None:
             self._resampler_backward(fw["vis"], dx, B, T, img_rows)
         self._bucket_ready("tail", works)
-        for w in works:
-            w.wait()
+        self._finish_reduce(works)
+        if dlogits_in is not None and self.world > 1:
+            # autograd bridge: an external optimizer reads param.grad directly, so the all-reduced SUM becomes the MEAN over
+            # ranks here (DistributedDataParallel's convention).  KosmosTrainer.step keeps the sum and folds 1/world into
+            # the clip coefficient instead (one pass less over the buffer).
+            self.G.mul_(1.0 / self.world)
         if g_prev is not None:
             self.G.add_(g_prev)
 
@@ -460,18 +474,35 @@ class KosmosTrainer:
 
     def _bucket_ready(self, which, works):
         """Overlapped all-reduce (sum): as soon as a bucket of bucket_plan() can no longer change, it goes out on
-        NCCL's stream while backward continues on the compute stream.  which = "head" | layer index | "tail"."""
+        NCCL's stream while backward continues on the compute stream.  which = "head" | layer index | "tail".
+        With grad_reduce_dtype = bf16 the bucket is first cast into the bf16 exchange buffer (kx_cast_f32_to_bf16 on the
+        compute stream); ``_finish_reduce`` converts the received sums back."""
         if self.world == 1:
             return
-        dist = torch.distributed
         if not self.overlap:
             if which == "tail":
-                works.append(dist.all_reduce(self.G, group=self.pg, async_op=True))
+                self._reduce_slice(0, self.n_total, works)
             return
         key = f"layer{which}." if isinstance(which, int) else which
         for name, lo, hi in self.bucket_plan():
             if name == key or (isinstance(which, int) and name.startswith(key)):
-                works.append(dist.all_reduce(self.G[lo:hi], group=self.pg, async_op=True))
+                self._reduce_slice(lo, hi, works)
+
+    def _reduce_slice(self, lo, hi, works):
+        dist = torch.distributed
+        if self.grad_reduce_dtype == torch.float32:
+            works.append((dist.all_reduce(self.G[lo:hi], group=self.pg, async_op=True), lo, hi))
+            return
+        g16 = self._buf("g16", (self.n_total,), torch.bfloat16)
+        ops.cast_bf16(self.G[lo:hi], g16[lo:hi])
+        works.append((dist.all_reduce(g16[lo:hi], group=self.pg, async_op=True), lo, hi))
+
+    def _finish_reduce(self, works):
+        for w, lo, hi in works:
+            w.wait()
+        if works and self.grad_reduce_dtype == torch.bfloat16:
+            g16 = self._buf("g16", (self.n_total,), torch.bfloat16)
+            ops.cast_f32(g16, self.G)               # every slice of the plan was exchanged: one pass over the whole buffer
 
     def _layer_span(self, li, decay):
         """[lo, hi) of layer li in the decay / no-decay segment (li == len(layers): the start of what follows them)."""
@@ -491,6 +522,8 @@ class KosmosTrainer:
         """Clip + optimizer over the flat buffers; the gradient is the SUM over ranks and micro-batches: scale by their count."""
         self.t += 1
         sc = self.scalars
+        lr = self.lr * (float(self.lr_schedule(self.t)) if self.lr_schedule is not None else 1.0)
+        self.last_lr = lr
         ops.sumsq(self.G, sc[2:3])
         ops.clip_scale(sc[2:3], self.max_grad_norm, 1.0 / (self.world * max(int(micro_batches), 1)), sc[3:4], sc[4:5])
         nd = self.n_decay
@@ -499,10 +532,10 @@ class KosmosTrainer:
             if hi <= lo:
                 continue
             if self.opt == "adamw":
-                ops.adamw_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], self.M2[lo:hi], wb, lr=self.lr, betas=self.betas,
+                ops.adamw_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], self.M2[lo:hi], wb, lr=lr, betas=self.betas,
                                eps=self.eps, weight_decay=wd, step=self.t, grad_scale=sc[3:4])
             else:
-                ops.lion_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], wb, lr=self.lr, betas=self.betas, weight_decay=wd,
+                ops.lion_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], wb, lr=lr, betas=self.betas, weight_decay=wd,
                               grad_scale=sc[3:4])
         self.model.decoder._packed = None
         if self.train_resampler:
@@ -574,6 +607,32 @@ class KosmosTrainer:
     def grad_norm(self):
         """Global gradient norm of the last step before clipping (device scalar)."""
         return self.scalars[4]
+
+
+def cosine_with_warmup(warmup_steps: int, total_steps: int, num_cycles: float = 0.5):
+    """LR multiplier of the reference's default schedule (train.py:206-251 -> transformers ``get_cosine_schedule_with_warmup``,
+    selected at train.py:560-583 with 1 % warm-up): linear 0 -> 1 over ``warmup_steps``, then half a cosine to 0 at
+    ``total_steps``.  The optimizer step k (1-based) uses the multiplier of scheduler step k - 1, as ``optim.step();
+    scheduler.step()`` does (train.py:655-656).  Pass as ``KosmosTrainer(lr_schedule=...)``."""
+    import math
+
+    def mult(step: int) -> float:
+        cur = step - 1
+        if cur < warmup_steps:
+            return cur / max(1, warmup_steps)
+        progress = (cur - warmup_steps) / max(1, total_steps - warmup_steps)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * num_cycles * 2.0 * progress)))
+    return mult
+
+
+def linear_with_warmup(warmup_steps: int, total_steps: int):
+    """train.py:206-251 with ``scheduler_type="linear"``: transformers ``get_linear_schedule_with_warmup``."""
+    def mult(step: int) -> float:
+        cur = step - 1
+        if cur < warmup_steps:
+            return cur / max(1, warmup_steps)
+        return max(0.0, (total_steps - cur) / max(1, total_steps - warmup_steps))
+    return mult
 
 
 class _KosmosAutograd(torch.autograd.Function):

@@ -31,8 +31,10 @@ in SURVEY.md Appendix A; each class cites the reference call site it serves.
 
 ``emulate_bf16=True`` re-runs the same algorithm with every tensor-core operand
 rounded to bf16 at exactly the points where the CUDA path rounds (fp32
-accumulate, fp32 residual stream, fp32 LayerNorm/softmax/GELU).  It is used by
-the tests to separate "kernel bug" from "bf16 rounding".
+accumulate, fp32 residual stream, fp32 LayerNorm/softmax/GELU), including the
+LayerNorm fold of SURVEY.md A.7 (``_linear`` on an ``_LNOut``: statistics of the
+bf16-rounded rows, gamma rounded into the weight).  It is used by the tests to
+separate "kernel bug" from "bf16 rounding".
 """
 from __future__ import annotations
 
@@ -74,6 +76,10 @@ class OracleConfig:
     p_latents: int = 64
     p_media_embeds: int = 257
     p_ff_mult: int = 4
+    # torchscale decoder.py, Decoder.forward_embedding [recall]: `x = embed = self.embed_scale * token_embedding` followed by
+    # the IN-PLACE `x += positions` — `embed` (the `[1]` result the reference splices at model.py:238) is the same tensor
+    # and carries the positions.  False = the out-of-place reading (`x = x + positions`).
+    alias_embed_positions: bool = True
 
     @property
     def vit_tokens(self) -> int:
@@ -90,16 +96,49 @@ class OracleConfig:
 
 
 class _Emu:
-    """bf16 operand rounding switch shared by every oracle module of one model."""
+    """bf16 operand rounding switch shared by every oracle module of one model.  ``fold`` (with ``on``): LayerNorms that
+    the CUDA path folds into their consumer GEMM (every decoder LayerNorm, the ViT's layer_norm1/2) are
+    evaluated the way the kernels evaluate them, see ``_linear``."""
 
-    def __init__(self, on: bool = False):
+    def __init__(self, on: bool = False, fold: bool = True):
         self.on = on
+        self.fold = fold
 
     def r(self, x: torch.Tensor) -> torch.Tensor:
         return x.to(torch.bfloat16).to(torch.float32) if self.on else x
 
 
+class _LNOut:
+    """A LayerNorm whose evaluation is deferred to the Linear that consumes it (bf16 emulation of the folded path)."""
+
+    def __init__(self, x, ln):
+        self.x, self.ln = x, ln
+
+
+def _ln(emu: _Emu, ln: nn.LayerNorm, x):
+    """ln(x) — or, when emulating the folded kernels, the raw rows + the LayerNorm for ``_linear`` to fold."""
+    if emu.on and emu.fold:
+        return _LNOut(x, ln)
+    return ln(x)
+
+
 def _linear(emu: _Emu, x, lin: nn.Linear):
+    if isinstance(x, _LNOut):
+        # what kx_gemm_bf16 computes with kx_gemm_args.ln_part (gemm.cu: ln_row_stats, epilogue_math; model.py: _fold_ln):
+        #   xb = bf16(x);  mean, E[x^2] - mean^2 of the ROUNDED row;  W' = bf16(W * gamma);  c = W'.1;  d = W.beta + b
+        #   y = rstd * (xb . W'^T - mean * c) + d
+        ln = x.ln
+        xb = emu.r(x.x)
+        n = xb.shape[-1]
+        mean = xb.sum(-1, keepdim=True) / n
+        var = ((xb * xb).sum(-1, keepdim=True) / n - mean * mean).clamp_min(0.0)
+        rstd = torch.rsqrt(var + ln.eps)
+        wp = emu.r(lin.weight * ln.weight[None, :])
+        c = wp.double().sum(1).float()
+        d = lin.weight.double() @ ln.bias.double()
+        if lin.bias is not None:
+            d = d + lin.bias.double()
+        return rstd * (F.linear(xb, wp) - mean * c) + d.float()
     return F.linear(emu.r(x), emu.r(lin.weight), lin.bias)
 
 
@@ -118,7 +157,7 @@ class _ClipAttention(nn.Module):
         self.out_proj = nn.Linear(d, d)
 
     def forward(self, x):
-        B, T, D = x.shape
+        B, T, D = (x.x if isinstance(x, _LNOut) else x).shape
         hd = D // self.h
         e = self.emu
         q = e.r(_linear(e, x, self.q_proj) * hd ** -0.5).view(B, T, self.h, hd).transpose(1, 2)
@@ -159,8 +198,9 @@ class _ClipLayer(nn.Module):
         self.layer_norm2 = nn.LayerNorm(cfg.vit_dim, eps=cfg.eps)
 
     def forward(self, x):
-        x = x + self.self_attn(self.layer_norm1(x))
-        return x + self.mlp(self.layer_norm2(x))
+        e = self.self_attn.emu
+        x = x + self.self_attn(_ln(e, self.layer_norm1, x))
+        return x + self.mlp(_ln(e, self.layer_norm2, x))
 
 
 class _ClipEmbeddings(nn.Module):
@@ -373,7 +413,7 @@ class FeedForwardNetwork(nn.Module):
     def forward(self, x):
         x = _linear(self.emu, x, self.fc1)
         x = F.gelu(x.float()).type_as(x)
-        x = self.ffn_layernorm(self.emu.r(x))
+        x = _ln(self.emu, self.ffn_layernorm, self.emu.r(x))
         return _linear(self.emu, x, self.fc2)
 
 
@@ -398,7 +438,7 @@ class MultiheadAttention(nn.Module):
         keys / values of every step are appended to ``prev_key`` / ``prev_value`` (B, heads, src_len, head_dim) and
         xPos is re-applied to the whole key sequence each step; after the first step the single query is rotated
         with ``offset = src_len - 1``."""
-        B, T, D = x.shape
+        B, T, D = (x.x if isinstance(x, _LNOut) else x).shape
         e = self.emu
         q = _linear(e, x, _inner(self.q_proj))
         k = _linear(e, x, _inner(self.k_proj))
@@ -430,7 +470,7 @@ class MultiheadAttention(nn.Module):
         p = torch.exp(w - m)                                 # == softmax(w, dtype=fp32) numerator
         a = torch.bmm(e.r(p), v) / p.sum(-1, keepdim=True)
         a = e.r(a).view(B, self.h, T, self.hd).transpose(1, 2).reshape(B, T, D)
-        a = _inner(self.inner_attn_ln)(a)
+        a = _ln(e, _inner(self.inner_attn_ln), a)
         return _linear(e, a, _inner(self.out_proj))
 
 
@@ -446,10 +486,11 @@ class DecoderLayer(nn.Module):
 
     def forward(self, x, mask, incremental_state=None, is_first_step=False):
         r = x
-        x = self.self_attn(_inner(self.self_attn_layer_norm)(x), mask, incremental_state, is_first_step)
+        e = self.self_attn.emu
+        x = self.self_attn(_ln(e, _inner(self.self_attn_layer_norm), x), mask, incremental_state, is_first_step)
         x = r + x
         r = x
-        x = _inner(self.ffn)(_inner(self.final_layer_norm)(x))
+        x = _inner(self.ffn)(_ln(e, _inner(self.final_layer_norm), x))
         return r + x
 
 
@@ -500,7 +541,10 @@ class Decoder(nn.Module):
         if token_embedding is None:
             token_embedding = self.embed_tokens(tokens)
         x = embed = self.embed_scale * token_embedding
-        x = x + positions
+        if self.cfg.alias_embed_positions:
+            x += positions                                   # in place: `embed` IS x (torchscale as written)
+        else:
+            x = x + positions
         return x, embed                                      # dropout p=0.1 is identity in eval
 
     def forward(self, prev_output_tokens, incremental_state=None, token_embeddings=None, **kwargs):
@@ -524,8 +568,7 @@ class Decoder(nn.Module):
                 st = incremental_state.setdefault(idx, {})
             x = layer(x, mask, st, first)
             inner_states.append(x)
-        x = self.layer_norm(x)
-        x = F.linear(self.emu.r(x), self.emu.r(self.output_projection.weight))
+        x = _linear(self.emu, _ln(self.emu, self.layer_norm, x), self.output_projection)
         return x, {"inner_states": inner_states, "l_aux": [None] * len(self.layers), "attn": None}
 
 
@@ -556,8 +599,9 @@ class KosmosOracle(nn.Module):
         self.image_proj = nn.Linear(cfg.vit_dim, cfg.dim, bias=False)          # model.py:205-206
         nn.init.normal_(self.image_proj.weight, mean=0, std=cfg.dim ** -0.5)
 
-    def set_emulation(self, on: bool):
+    def set_emulation(self, on: bool, fold: bool = True):
         self.emu.on = on
+        self.emu.fold = fold
 
     def _image_rows(self, images, keep=None):
         """ViT -> perceiver -> image_proj: (B,3,H,W) -> (B,1,64,dim); (B,m,3,H,W) -> (B,m,64,dim)."""
@@ -616,22 +660,36 @@ class KosmosOracle(nn.Module):
         st["is_first_step"] = False
         prefix = torch.zeros(x.size(0), x.size(1), dtype=torch.long)      # only its length and last token are read
         toks, outs = [], []
+        t_text = text_tokens.shape[1]
         for i in range(max_new_tokens):
             nxt = logits.argmax(-1) if forced is None else forced[:, i]
             toks.append(nxt)
             outs.append(logits)
             if i + 1 < max_new_tokens:
                 prefix = torch.cat([prefix, nxt[:, None]], dim=1)
-                logits = self.decoder(prefix, incremental_state=st)[0][:, -1]
+                te = None
+                if self.cfg.alias_embed_positions:
+                    # the reference has no generate: a user would call forward() on the grown text, where text token
+                    # t_text + i gets its text-index position as well (aliased `embed`); forward_embedding adds the other
+                    te = torch.zeros(x.size(0), prefix.size(1), self.cfg.dim)
+                    te[:, -1] = self.embed(nxt) + self.embed_positions.weight[t_text + i + 2]
+                logits = self.decoder(prefix, incremental_state=st, token_embeddings=te)[0][:, -1]
         return torch.stack(toks, 1), torch.stack(outs, 1)
 
     @staticmethod
-    def loss_targets(text_tokens, n_latents, image_positions=None, n_images=1):
-        """Next-token targets per row of the spliced sequence, -100 = no loss.  The row holding text token i
-        predicts text token i+1; image rows, the last text token and the token directly in front of an image are
-        dropped — the intent of the reference's training loop (experimental/model/allModalities/notes.txt:566-574:
-        keep row 0 and the rows after the image block, "tokens < n predict n"), with the class dimension on the
-        vocabulary (the pasted loop feeds CrossEntropyLoss a (B, T, C) tensor, i.e. classes on dim 1 — SURVEY App. C)."""
+    def loss_targets(text_tokens, n_latents, image_positions=None, n_images=1, rule="reference", pad_token_id=None):
+        """Next-token targets per row of the spliced sequence, -100 = no loss.
+
+        rule = "reference": the reference's intended loop, experimental/model/allModalities/notes.txt:566-574 —
+        ``outputs = cat([outputs[:, :1], outputs[:, 67:]])`` then ``loss(outputs[:, :-1], labels[:, 1:])`` with
+        ``labels`` = the text WITHOUT the ``<image>`` ``</image>`` markers (model.py:70-77): rows 0 and 67.. are kept,
+        row 0 predicts the first real text token (text token 3), the marker rows and the 64 feature rows carry no
+        loss.  Generalised to any image position p: text tokens p-1 and p are that image's markers.  The class
+        dimension is the vocabulary (the pasted loop hands CrossEntropyLoss a (B, T, C) tensor, classes on dim 1 — a
+        defect).
+        rule = "next_token": the row of text token i predicts text token i+1; feature rows, the last token and the
+        token directly in front of an image carry no loss.
+        pad_token_id: targets equal to it are ignored (the reference's loop masks nothing: None)."""
         B, t_text = text_tokens.shape
         pos = [2] * n_images if image_positions is None else list(image_positions)
         T = t_text + n_latents * len(pos)
@@ -641,16 +699,26 @@ class KosmosOracle(nn.Module):
             is_img[r:r + n_latents] = True
         text_rows = (~is_img).nonzero().flatten().tolist()
         tgt = torch.full((B, T), -100, dtype=torch.long)
-        for ti, t in enumerate(text_rows):
-            if ti + 1 < t_text and not (t + 1 < T and bool(is_img[t + 1])):
-                tgt[:, t] = text_tokens[:, ti + 1]
+        if rule == "next_token":
+            for ti, t in enumerate(text_rows):
+                if ti + 1 < t_text and not (t + 1 < T and bool(is_img[t + 1])):
+                    tgt[:, t] = text_tokens[:, ti + 1]
+        elif rule == "reference":
+            markers = {q for p in pos for q in (p - 1, p)}
+            real = [ti for ti in range(t_text) if ti not in markers]       # `labels` = only_text_tokens (model.py:77)
+            for a, b in zip(real[:-1], real[1:]):
+                tgt[:, text_rows[a]] = text_tokens[:, b]
+        else:
+            raise ValueError("rule must be 'reference' or 'next_token'")
+        if pad_token_id is not None:
+            tgt[tgt == pad_token_id] = -100
         return tgt
 
-    def loss(self, text_tokens, images, image_positions=None):
+    def loss(self, text_tokens, images, image_positions=None, rule="reference", pad_token_id=None):
         """Mean cross-entropy over the text rows (train.py:647 `loss = model(...)`; see loss_targets)."""
         logits = self.forward(text_tokens, images, image_positions=image_positions)
         m = images.shape[1] if images.ndim == 5 else 1
-        tgt = self.loss_targets(text_tokens, self.cfg.p_latents, image_positions, m)
+        tgt = self.loss_targets(text_tokens, self.cfg.p_latents, image_positions, m, rule, pad_token_id)
         return F.cross_entropy(logits.reshape(-1, logits.shape[-1]), tgt.reshape(-1), ignore_index=-100)
 
     @torch.no_grad()

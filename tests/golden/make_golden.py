@@ -31,7 +31,14 @@ def main():
         cases[name] = dict(B=B, t_text=t_text, col_step=step, vit=st["vit"][:, ::4].half(),
                            perceive=st["perceive"].half(), x0=st["x0"][:, ::2].half(),
                            logits=st["logits"][..., ::step].clone(), logits_emu_bf16=emu[..., ::step].clone())
-    torch.save(dict(cfg=cfg.__dict__, seed_weights=0, seed_inputs=1, cases=cases),
+    # the out-of-place reading of torchscale's forward_embedding (one positional embedding per text row,
+    # OracleConfig.alias_embed_positions = False): same weights, one case
+    model.cfg.alias_embed_positions = False
+    text, images = ko.make_inputs(cfg, 1, 50, seed=1)
+    st = model.stages(text, images)
+    noalias = dict(B=1, t_text=50, col_step=8, x0=st["x0"][:, ::2].half(), logits=st["logits"][..., ::8].clone())
+    model.cfg.alias_embed_positions = True
+    torch.save(dict(cfg=cfg.__dict__, seed_weights=0, seed_inputs=1, cases=cases, noalias_b1_t50=noalias),
                os.path.join(HERE, "tiny_golden.pt"))
     print("wrote", os.path.join(HERE, "tiny_golden.pt"), {k: tuple(v["logits"].shape) for k, v in cases.items()})
 

@@ -118,8 +118,7 @@ def _bucket_worker(rank, world, port, out):
     for li in range(len(tr.layers) - 1, -1, -1):
         tr._bucket_ready(li, works)
     tr._bucket_ready("tail", works)
-    for w in works:
-        w.wait()
+    tr._finish_reduce(works)
     ok_overlap = torch.equal(tr.G, want) and len(works) == len(tr.bucket_plan())
     tr.G = torch.randn(tr.n_total, generator=torch.Generator().manual_seed(100 + rank))
     tr.overlap = False
@@ -127,8 +126,7 @@ def _bucket_worker(rank, world, port, out):
     tr._bucket_ready("head", works)
     tr._bucket_ready(0, works)
     tr._bucket_ready("tail", works)
-    for w in works:
-        w.wait()
+    tr._finish_reduce(works)
     out[rank] = (ok_overlap, torch.equal(tr.G, want), len(works))
     dist.destroy_process_group()
 

@@ -23,6 +23,7 @@ def _pair(max_positions=256, optimizer="adamw", **kw):
     from kosmosx import Kosmos, KosmosConfig, KosmosTrainer
     oc = ko.OracleConfig.tiny(max_positions=max_positions)
     ref = ko.build(oc, seed=0, emulate_bf16=True)
+    ref.emu.fold = False                          # the training forward materialises its LayerNorms (nothing is folded)
     ref.train()                                   # no dropout in the oracle; train() only marks intent
     mine = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
     mine.load_state_dict(ref.state_dict())
@@ -78,13 +79,63 @@ def test_loss_and_gradients_match_oracle_autograd(B, t_text, m, positions):
             assert p.grad is None
 
 
-def test_loss_row_selection_matches_oracle_targets():
+def test_device_loss_targets_match_oracle_rules():
+    """kx_loss_targets against the oracle's restatement of the reference's loop (notes.txt:566-574, rule "reference") and
+    the plain next-token rule, single / multi image, an image at the very start / end, pad masking, and the device count."""
     import kosmos_oracle as ko
-    from kosmosx import KosmosTrainer
-    for t_text, pos in ((20, [2]), (30, [2, 17]), (12, [0, 12]), (9, [3, 3, 8])):
+    from kosmosx import ops
+    g = torch.Generator().manual_seed(0)
+    for t_text, pos in ((20, [2]), (30, [2, 17]), (12, [0, 12]), (9, [3, 3, 8]), (5, [2])):
         rows = tuple(p + 64 * i for i, p in enumerate(pos))
-        tgt = ko.KosmosOracle.loss_targets(torch.zeros(2, t_text, dtype=torch.long), 64, pos, len(pos))
-        assert KosmosTrainer.n_loss_rows(2, t_text, rows, 64) == int((tgt >= 0).sum())
+        text = torch.randint(0, 50, (3, t_text), generator=g)
+        for rule in ("reference", "next_token"):
+            for pad in (None, 7):
+                want = ko.KosmosOracle.loss_targets(text, 64, pos, len(pos), rule=rule, pad_token_id=pad)
+                got = torch.empty(3, t_text + 64 * len(pos), dtype=torch.int64, device="cuda")
+                count = torch.zeros(1, device="cuda")
+                ops.loss_targets(text.cuda(), got, count, img_rows=rows, n_img=64, rule=rule, ignore_token=pad)
+                assert torch.equal(got.cpu(), want), (t_text, pos, rule, pad)
+                assert int(count.item()) == int((want >= 0).sum())
+    # the reference layout literally: rows 0 and 67.. kept, the last one dropped, labels = text without the markers
+    text = torch.arange(100, 112)[None]
+    tgt = ko.KosmosOracle.loss_targets(text, 64)
+    kept = ([0] + list(range(67, 12 + 64)))[:-1]
+    labels = torch.cat([text[:, 0:1], text[:, 3:]], 1)
+    assert tgt[0, kept].tolist() == labels[0, 1:].tolist() and int((tgt >= 0).sum()) == len(kept)
+
+
+@pytest.mark.parametrize("rule,pad", [("next_token", None), ("reference", 3)])
+def test_loss_rules_and_pad_masking_through_the_trainer(rule, pad):
+    import kosmos_oracle as ko
+    ref, mine, trainer, oc = _pair(max_positions=512, loss_rule=rule, pad_token_id=pad)
+    text, images = ko.make_inputs(oc, 2, 26, seed=8)
+    if pad is not None:
+        text[0, 18:] = pad                        # a padded batch (KosmosTokenizer pads with padding=True, model.py:61)
+    loss = trainer.loss_and_grads(text.cuda(), images.cuda())
+    ref.zero_grad()
+    want = ref.loss(text, images, rule=rule, pad_token_id=pad)
+    want.backward()
+    print(f"rule={rule} pad={pad}: loss cuda {loss.item():.5f} oracle {want.item():.5f}")
+    assert abs(loss.item() - want.item()) <= LOSS_TOL
+    _check_grads(ref, mine, trainer)
+
+
+def test_lr_schedule_scales_the_update():
+    """KosmosTrainer(lr_schedule=cosine_with_warmup(...)): step k uses lr * multiplier(k) (train.py:206-251,560-583)."""
+    import kosmos_oracle as ko
+    from kosmosx.train import cosine_with_warmup
+    sched = cosine_with_warmup(warmup_steps=2, total_steps=10)
+    ref, mine, trainer, oc = _pair(optimizer="lion", lr=1e-3, weight_decay=0.0, max_grad_norm=0.0, lr_schedule=sched)
+    text, images = ko.make_inputs(oc, 2, 20, seed=3)
+    tg, ig = text.cuda(), images.cuda()
+    w = mine.decoder.layer_norm.weight
+    for k in range(1, 5):
+        before = w.detach().clone()
+        trainer.step(tg, ig)
+        delta = (w.detach() - before).abs().max().item()          # Lion: every element moves by exactly lr * mult (sign update)
+        assert abs(delta - 1e-3 * sched(k)) <= 1e-7, (k, delta, sched(k))
+        assert abs(trainer.last_lr - 1e-3 * sched(k)) <= 1e-12
+    assert sched(1) == 0.0 and sched(2) == 0.5 and sched(3) == 1.0
 
 
 @pytest.mark.parametrize("optimizer", ["adamw", "lion"])

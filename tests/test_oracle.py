@@ -289,14 +289,20 @@ def test_multi_image_rows_and_media_positions(tiny512):
             want = torch.zeros_like(moved)
             want[rows[i]:rows[i] + 64] = True
             assert torch.equal(moved, want), i
-        # text rows: embedding + position t+2 in spliced coordinates
+        # text rows: embedding + position t+2 in spliced coordinates, and — torchscale's in-place `x += positions` on the
+        # aliased `embed` (alias_embed_positions) — the position i+2 of the un-spliced text on top
         emb = model.embed(text)
         is_img = torch.zeros(st["x0"].shape[1], dtype=torch.bool)
         for r in rows:
             is_img[r:r + 64] = True
         T = is_img.numel()
-        want_text = emb + model.embed_positions.weight[2:T + 2][~is_img]
+        want_text = emb + model.embed_positions.weight[2:text.shape[1] + 2] + model.embed_positions.weight[2:T + 2][~is_img]
         assert torch.allclose(st["x0"][:, ~is_img], want_text, atol=1e-6)
+        model.cfg.alias_embed_positions = False
+        x0_plain = model.stages(text, images, pos)["x0"]
+        model.cfg.alias_embed_positions = True
+        assert torch.allclose(x0_plain[:, ~is_img], emb + model.embed_positions.weight[2:T + 2][~is_img], atol=1e-6)
+        assert torch.equal(x0_plain[:, is_img], st["x0"][:, is_img])          # image rows: one positional embedding either way
         # the same picture at media index 0 and 1 gives different rows (media_pos_emb[0] vs [1]) ...
         same = images[:, :1].expand(-1, 2, -1, -1, -1).contiguous()
         r = model._image_rows(same)
@@ -464,3 +470,95 @@ def test_decoder_stack_matches_hf_kosmos2_text_model(tiny):
     assert got.shape == want.shape == (2, T, cfg.vocab)
     assert (got - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())
     assert len(extra["inner_states"]) == cfg.layers + 1
+
+
+# --------------------------------------------------------------------------- round-2 additions
+def test_forward_embedding_aliases_embed_like_torchscale(tiny):
+    """torchscale: `x = embed = embed_scale * token_embedding; x += positions` — the second result IS the first, so the
+    reference's model.py:238 splices embeddings that already carry positions 2..T_text+1 and text rows end up with two
+    positional embeddings; image rows with one.  alias_embed_positions=False is the out-of-place reading."""
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 2, 12, seed=3)
+    with torch.no_grad():
+        x, embed = model.decoder.forward_embedding(text)
+        assert x.data_ptr() == embed.data_ptr()
+        assert torch.allclose(embed, model.embed(text) + model.embed_positions.weight[2:14], atol=1e-6)
+        x0 = model.embed_inputs(text, images)
+        T = 12 + cfg.p_latents
+        pos = model.embed_positions.weight
+        assert torch.allclose(x0[:, :2], model.embed(text[:, :2]) + pos[2:4] + pos[2:4], atol=1e-6)
+        assert torch.allclose(x0[:, 66:], model.embed(text[:, 2:]) + pos[4:14] + pos[68:T + 2], atol=1e-6)
+        model.cfg.alias_embed_positions = False
+        try:
+            x, embed = model.decoder.forward_embedding(text)
+            assert x.data_ptr() != embed.data_ptr() and torch.equal(embed, model.embed(text))
+            x0p = model.embed_inputs(text, images)
+            assert torch.allclose(x0p[:, 66:], model.embed(text[:, 2:]) + pos[68:T + 2], atol=1e-6)
+            assert torch.equal(x0p[:, 2:66], x0[:, 2:66])
+        finally:
+            model.cfg.alias_embed_positions = True
+
+
+def test_incremental_decoding_equals_full_forward_with_aliased_positions(tiny):
+    """KosmosOracle.generate continues the TEXT: step i equals row T0-1+i of one forward over the grown text, where the
+    new text rows carry both positions (what a user of the reference, which has no generate, would compute)."""
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 2, 9, seed=4)
+    forced = torch.randint(0, cfg.vocab, (2, 5), generator=torch.Generator().manual_seed(1))
+    _, inc = model.generate(text, images, 5, forced=forced)
+    with torch.no_grad():
+        full = model(torch.cat([text, forced[:, :-1]], 1), images)
+    t0 = 9 + cfg.p_latents
+    assert (inc - full[:, t0 - 1:]).abs().max() < 2e-5
+
+
+def test_loss_targets_reference_rule_is_the_pasted_loop():
+    """rule="reference" == experimental/model/allModalities/notes.txt:566-574 applied literally to the reference layout."""
+    t_text = 14
+    text = torch.arange(100, 100 + t_text)[None].repeat(2, 1)
+    tgt = ko.KosmosOracle.loss_targets(text, 64)
+    T = t_text + 64
+    rows = [0] + list(range(67, T))                       # outputs = cat([outputs[:, :1], outputs[:, 67:]])
+    kept = rows[:-1]                                      # outputs[:, :-1]
+    labels = torch.cat([text[:, 0:1], text[:, 3:]], 1)    # only_text_tokens (model.py:77): the text without the two markers
+    assert torch.equal(tgt[:, kept], labels[:, 1:])       # labels[:, 1:]
+    assert int((tgt >= 0).sum()) == 2 * len(kept)
+    nt = ko.KosmosOracle.loss_targets(text, 64, rule="next_token")
+    assert int(nt[0, 0]) == 101 and int(nt[0, 1]) == -100 and int(nt[0, 66]) == 103 and int(tgt[0, 66]) == -100
+    padded = ko.KosmosOracle.loss_targets(text, 64, pad_token_id=105)
+    assert int((padded >= 0).sum()) == int((tgt >= 0).sum()) - 2
+
+
+def test_bf16_emulation_models_the_layernorm_fold(tiny):
+    """emulate_bf16 with fold (what the inference kernels do: statistics of the bf16-rounded rows, gamma rounded into the
+    weight) and without (LayerNorm materialised, what the training forward does) are two roundings of the same function:
+    both within bf16 noise of fp32, and of each other, but not identical."""
+    cfg, model = tiny
+    text, images = ko.make_inputs(cfg, 2, 20, seed=2)
+    with torch.no_grad():
+        want = model(text, images)
+        model.set_emulation(True, fold=True)
+        a = model(text, images)
+        model.set_emulation(True, fold=False)
+        b = model(text, images)
+        model.set_emulation(False)
+    assert (a - want).abs().max() < 8e-2 and (b - want).abs().max() < 8e-2
+    assert 0 < (a - b).abs().max() < 8e-2
+
+
+def test_lr_schedules_equal_transformers():
+    """train.py:206-251 builds transformers' get_cosine_schedule_with_warmup / get_linear_schedule_with_warmup; the
+    multipliers of kosmosx.train must be theirs, step for step (optimizer step k uses the value after k-1 scheduler steps)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kosmos-x_b200"))
+    from transformers import get_cosine_schedule_with_warmup, get_linear_schedule_with_warmup
+    from kosmosx.train import cosine_with_warmup, linear_with_warmup
+    for make_hf, make_mine in ((get_cosine_schedule_with_warmup, cosine_with_warmup), (get_linear_schedule_with_warmup, linear_with_warmup)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([p], lr=1.0)
+        hf = make_hf(opt, num_warmup_steps=7, num_training_steps=60)
+        mine = make_mine(7, 60)
+        for k in range(1, 70):
+            assert abs(opt.param_groups[0]["lr"] - mine(k)) < 1e-12, (k, opt.param_groups[0]["lr"], mine(k))
+            opt.step()
+            hf.step()

@@ -38,7 +38,8 @@ def run(model, batch, prompt, new, layers_note="", one_kernel=True):
     e0.record()
     xv = model._vit(images_p, media=1)
     model._perceive_project(xv, batch, x0, T, img_rows)
-    ops.embed_splice_pos(text_p, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=cfg.p_latents)
+    ops.embed_splice_pos(text_p, dp["embed"], dp["pos"], x0, img_rows=img_rows, n_img=cfg.p_latents,
+                         alias_positions=cfg.alias_embed_positions)
     dec = model.decoder
     state, _ = dec.begin_generation(x0, batch, T, T + new, head="last")
     history = torch.zeros(batch, new, dtype=torch.int64, device=dev)

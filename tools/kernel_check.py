@@ -263,7 +263,11 @@ def case_train_elementwise():
     Vp = (V + 63) // 64 * 64
     dl = torch.full((Bc * Tc, Vp), 7.0, device=dev, dtype=torch.bfloat16)
     acc = torch.zeros(2, device=dev)
-    ops.ce_fwd_bwd(logits, tok, acc, img_rows=rows_img, n_img=n_img, inv_count=1.0 / count, dlogits=dl)
+    tg_dev = torch.empty(Bc, Tc, dtype=torch.long, device=dev)
+    cnt = torch.zeros(1, device=dev)
+    ops.loss_targets(tok, tg_dev, cnt, img_rows=rows_img, n_img=n_img, rule="next_token")
+    ok &= bool(torch.equal(tg_dev, tgt)) and bool(int(cnt.item()) == count)
+    ops.ce_fwd_bwd(logits, tg_dev.view(-1), acc, count=cnt, dlogits=dl)
     ok &= report("ce loss sum", acc[:1], loss.detach().view(1), 2e-3 * count)
     ok &= bool(int(acc[1].item()) == count)
     ok &= report("ce dlogits", dl[:, :V].float() * count, lr_.grad * count, 1e-2)
@@ -281,6 +285,12 @@ def case_train_elementwise():
     want_p = torch.zeros(Tc + 2, D2, device=dev)
     want_p[2:] = dx0.sum(0)
     ok &= report("embed_bwd d_pos", d_pos, want_p, 1e-5)
+    # alias_positions: the row of text token i also feeds pos[i + 2] (torchscale's in-place `x += positions`)
+    d_pos2 = torch.zeros(Tc + 2, D2, device=dev)
+    ops.embed_bwd(dx0.view(-1, D2), tok, None, d_pos2, img_rows=rows_img, n_img=n_img, alias_positions=True)
+    want_p2 = want_p.clone()
+    want_p2[2:2 + t_text] += dx0[:, ~is_img].sum(0)
+    ok &= report("embed_bwd d_pos (aliased positions)", d_pos2, want_p2, 1e-5)
     # ---- gradient norm, clipping scale, AdamW, Lion
     n = 1000003
     pw = torch.randn(n, device=dev); g = torch.randn(n, device=dev) * 3
@@ -621,6 +631,67 @@ def case_ln_fold():
     return ok
 
 
+def case_accurate():
+    """Verification-precision kernels (csrc/accurate.cu): split-operand GEMM vs an fp64 product, fp32 attention, fp32
+    xPos rotation, fp32 patch im2col — each against plain PyTorch in fp64/fp32."""
+    torch.manual_seed(11)
+    ok = True
+    for M, N, K in ((114, 96, 128), (300, 1002, 2048), (257, 256, 588)):
+        a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * K ** -0.5
+        bias = torch.randn(N, device=dev)
+        kp = (K + 63) // 64 * 64
+        a3 = ops.split_bf16x3(a, n_pad=kp); w3 = ops.split_bf16x3(w, weights=True, n_pad=kp)
+        hi = a.bfloat16().float()
+        ok &= bool(torch.equal(a3[:, :K].float(), hi) and torch.equal(a3[:, kp:kp + K], a3[:, :K])
+                   and torch.equal(a3[:, 2 * kp:2 * kp + K].float(), (a - hi).bfloat16().float()))
+        ok &= bool(torch.equal(w3[:, kp:kp + K].float(), (w - w.bfloat16().float()).bfloat16().float()) and (a3[:, K:kp] == 0).all())
+        out = torch.empty(M, N, device=dev)
+        ops.gemm(a3, w3, out, bias=bias)
+        want = (a.double() @ w.double().T + bias.double()).float()
+        ok &= report(f"bf16x3 GEMM {M}x{N}x{K} vs fp64", out, want, 5e-5)
+        plain = torch.empty(M, N, device=dev)
+        ops.gemm(a.bfloat16(), w.bfloat16(), plain, bias=bias)
+        print(f"      (plain bf16 operands: max err {(plain - want).abs().max().item():.2e})")
+    for B, H, nq, nkv, causal in ((2, 3, 114, 114, True), (3, 2, 64, 321, False), (1, 2, 257, 257, False), (2, 2, 33, 33, True)):
+        q = torch.randn(B * nq, H * 64 + 64, device=dev); kv = torch.randn(B * nkv, 2 * H * 64, device=dev)
+        out = torch.zeros(B * nq, H * 64, device=dev)
+        ops.attention_f32(q[:, :H * 64], kv[:, :H * 64], kv[:, H * 64:], out, batch=B, heads=H, n_q=nq, n_kv=nkv, causal=causal, scale=0.125)
+        qh = q[:, :H * 64].view(B, nq, H, 64).transpose(1, 2).double()
+        kh = kv[:, :H * 64].view(B, nkv, H, 64).transpose(1, 2).double()
+        vh = kv[:, H * 64:].view(B, nkv, H, 64).transpose(1, 2).double()
+        sc = qh @ kh.transpose(-1, -2) * 0.125
+        if causal:
+            sc = sc + torch.triu(torch.full((nq, nkv), float("-inf"), device=dev, dtype=torch.float64), 1)
+        want = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B * nq, H * 64).float()
+        ok &= report(f"attn_f32 B={B} H={H} {nq}x{nkv} causal={causal}", out, want, 2e-6)
+    T, D = 50, 128
+    tabs = ops.xpos_tables((torch.arange(0, 64, 2, device=dev) + 25.6) / 89.6, 1.0 / (10000 ** (torch.arange(0, 32, device=dev) / 32)),
+                           T, (-T) // 2, 512.0, dev)
+    qkv = torch.randn(2 * T, 3 * D, device=dev)
+    want = qkv.clone()
+    for blk, (c, s_) in ((0, (tabs[0], tabs[1])), (1, (tabs[2], tabs[3]))):
+        z = qkv[:, blk * D:(blk + 1) * D].view(2, T, D // 64, 32, 2)
+        cc, ss = c.view(1, T, 1, 32), s_.view(1, T, 1, 32)
+        want[:, blk * D:(blk + 1) * D] = torch.stack([z[..., 0] * cc - z[..., 1] * ss, z[..., 1] * cc + z[..., 0] * ss], -1).view(2 * T, D)
+    ops.xpos_apply_f32(qkv, D, T, tabs)
+    ok &= report("xpos_apply_f32", qkv, want, 1e-6)
+    n, media, image, patch, Dv = 4, 2, 56, 14, 128
+    px = torch.randn(n, 3, image, image, device=dev)
+    P = (image // patch) ** 2
+    kp = 640
+    patches = torch.full((n * P, kp), 7.0, device=dev)
+    cls = torch.randn(Dv, device=dev); vpos = torch.randn(P + 1, Dv, device=dev)
+    x = torch.zeros(n, P + 1, Dv, device=dev)
+    ops.im2col_patches_f32(px, patches, cls, vpos, x, image=image, patch=patch, media=media)
+    un = F.unfold(px, patch, stride=patch).transpose(1, 2)                       # (n, P, 588)
+    slot = torch.tensor([(i % media) * (n // media) + i // media for i in range(n)])
+    want = torch.zeros(n, P, kp, device=dev)
+    want[slot, :, :588] = un
+    ok &= bool(torch.equal(patches.view(n, P, kp), want)) and bool(torch.equal(x[:, 0], (cls + vpos[0]).expand(n, -1)))
+    print(f"[{'OK' if ok else 'FAIL'}] im2col_patches_f32 (media-major slots, CLS rows)")
+    return ok
+
+
 def case_embed():
     torch.manual_seed(5)
     ok = True
@@ -634,6 +705,14 @@ def case_embed():
     ref = torch.cat([e[:, :2], torch.zeros(B, n_img, D, device=dev), e[:, 2:]], 1) + pos[2:T + 2]
     ref[:, 2:2 + n_img] = 0
     ok &= report("embed_splice_pos", x0.view(B * T, D), ref.view(B * T, D), 1e-6)
+    # alias_positions: text token i at row t gets (embed + pos[i + 2]) + pos[t + 2]  (torchscale's in-place `x += positions`)
+    xa = torch.zeros(B, T, D, device=dev)
+    ops.embed_splice_pos(tok, emb, pos, xa, img_rows=(2,), n_img=n_img, alias_positions=True)
+    ea = e + pos[2:t_text + 2]
+    refa = torch.cat([ea[:, :2], torch.zeros(B, n_img, D, device=dev), ea[:, 2:]], 1) + pos[2:T + 2]
+    refa[:, 2:2 + n_img] = 0
+    ok &= bool(torch.equal(xa, refa))
+    print(f"[{'OK' if torch.equal(xa, refa) else 'FAIL'}] embed_splice_pos with aliased positions: bit-exact")
     # three images: in front of text tokens 0, 7, 7 (adjacent) -> spliced rows 0, 71, 135
     T3 = t_text + 3 * n_img
     pos3 = torch.randn(T3 + 2, D, device=dev)
@@ -912,6 +991,8 @@ def case_decode():
     err = torch.zeros(1, device=dev, dtype=torch.int32)
     ops.decode_embed(tok, emb, ptab, pos, x, xb, err)
     ok &= bool(torch.equal(x, emb[tok] + ptab[11]) and torch.equal(xb, x.bfloat16()) and int(err.item()) == 0)
+    ops.decode_embed(tok, emb, ptab, pos, x, xb, err, text_index_off=4)       # + the text-index position 11 - 4
+    ok &= bool(torch.equal(x, (emb[tok] + ptab[7]) + ptab[11]) and int(err.item()) == 0)
     ops.decode_embed(torch.tensor([5, 1002, 77], device=dev), emb, ptab, pos, x, xb, err)
     ok &= int(err.item()) == 1
     logits = torch.randn(B, V, device=dev, generator=g)
