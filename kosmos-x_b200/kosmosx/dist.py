@@ -74,3 +74,29 @@ def gather_logits(local_logits: torch.Tensor, global_batch: int):
         dist.broadcast(buf, src=r)
         outs.append(buf)
     return torch.cat(outs, 0)
+
+
+def bind_host_thread_to_gpu(device_index: int) -> str:
+    """Pin the calling thread (and the threads it creates later) to the CPUs NVML reports as closest to the GPU, so that
+    pinned host buffers allocated afterwards — and the copies into / out of them — stay on the GPU's own NUMA node.
+    On an 8-GPU box the ranks otherwise land on arbitrary cores and half of the device<->host traffic crosses the
+    socket interconnect.  Returns a short description; never raises (no NVML = no binding)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            props = torch.cuda.get_device_properties(device_index)
+            bus = "%08X:%02X:%02X.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "NVML reports no CPU affinity for this GPU inside the allowed set; not bound"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to {len(cpus)} CPUs near GPU {device_index} (NVML affinity)"
+    except Exception as e:                                   # noqa: BLE001 — strictly best effort
+        return f"not bound ({type(e).__name__}: {e})"

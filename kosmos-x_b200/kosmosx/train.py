@@ -48,7 +48,8 @@ class KosmosTrainer:
     def __init__(self, model: Kosmos, *, optimizer: str = "adamw", lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
                  weight_decay: float = 0.1, max_grad_norm: float = 1.0, process_group=None, overlap_all_reduce: bool = True,
                  train_resampler: bool = True, layout_only: bool = False, loss_rule: str = "reference",
-                 pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.float32):
+                 pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.float32,
+                 distributed: bool | None = None):
         """loss_rule: "reference" = the rows / targets of the reference's intended loop (notes.txt:566-574: the `<image>`
         `</image>` markers and the feature rows carry no loss and are never targets; row 0 predicts the first real text
         token), "next_token" = plain shift by one over the text rows.  pad_token_id: targets equal to it are ignored
@@ -56,7 +57,8 @@ class KosmosTrainer:
         ``cosine_with_warmup``), evaluated on the host from the step COUNT — no device value is read.
         grad_reduce_dtype: torch.float32 all-reduces the flat fp32 gradient buffer; torch.bfloat16 exchanges a bf16
         copy (half the NVLink bytes, the reference's FSDP ``reduce_dtype`` is 16-bit too, train.py:156-162) and
-        accumulates the received sums back in fp32."""
+        accumulates the received sums back in fp32.  distributed: None = data parallel over ``process_group`` (or the
+        default group) whenever torch.distributed is initialised; False = this process trains alone."""
         if optimizer not in ("adamw", "lion"):
             raise ValueError("optimizer must be 'adamw' or 'lion' (train.py:375-386)")
         if loss_rule not in ("reference", "next_token"):
@@ -73,7 +75,7 @@ class KosmosTrainer:
         self.overlap = overlap_all_reduce
         self.train_resampler = train_resampler
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if distributed is not False and (process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self.t = 0
         self._ws = {}

@@ -310,3 +310,19 @@ def test_gradient_accumulation_over_micro_batches():
     q.grad = 0.5 * g * torch.clamp(1.0 / (mean.norm() + 1e-6), max=1.0)
     torch.optim.AdamW([q], lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0).step()
     assert torch.allclose(w.detach(), q.detach(), atol=2e-6, rtol=0)
+
+
+def test_two_rank_nccl_step_equals_single_process_step():
+    """on >= 2 GPUs, tools/dp_check.py under torchrun (NCCL): 2-rank steps on shards == 1-rank steps on
+    the concatenated batch, replicas bit-identical after 3 steps, overlap on and off, fp32 and bf16 gradient exchange, and
+    the autograd bridge's mean-gradient convention.  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dp_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "DP_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -70,5 +70,78 @@ def main():
             f.write(txt + "\n")
 
 
+def layer_breakdown():
+    """Decoder layer 0 alone, fed the oracle's exact fp32 x0: every intermediate of the 5-launch layer against the
+    bf16-emulating oracle computed from the same input (locates where kernels and emulation part ways)."""
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, KosmosConfig, ops, _abi
+    oc = ko.OracleConfig.tiny()
+    ref = ko.build(oc, seed=0)
+    mine = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda()
+    text, images = ko.make_inputs(oc, 2, 50, seed=1)
+    with torch.no_grad():
+        x0 = ref.embed_inputs(text, images)
+    B, T, D = x0.shape
+    H, Fd, M = oc.heads, oc.ffn, B * T
+    e = ko._Emu(True, True)
+    L = ref.decoder.layers[0]
+    sa = L.self_attn
+    with torch.no_grad():
+        h = ko._ln(e, ko._inner(L.self_attn_layer_norm), x0)
+        q = ko._linear(e, h, ko._inner(sa.q_proj)) * sa.scaling
+        k = ko._linear(e, h, ko._inner(sa.k_proj))
+        v = ko._linear(e, h, ko._inner(sa.v_proj))
+        hd = lambda t: t.view(B, T, H, 64).transpose(1, 2).reshape(B * H, T, 64)
+        qh, kh, vh = hd(q), hd(k), e.r(hd(v))
+        kh = e.r(sa.xpos(kh, offset=0, downscale=True)); qh = e.r(sa.xpos(qh, offset=0, downscale=False))
+        w = torch.bmm(qh, kh.transpose(1, 2)) + torch.triu(torch.full((T, T), float("-inf")), 1)[None]
+        p = torch.exp(w - w.amax(-1, keepdim=True))
+        a = e.r(torch.bmm(e.r(p), vh) / p.sum(-1, keepdim=True))
+        a_exact = torch.bmm(p, vh) / p.sum(-1, keepdim=True)
+        att = a.view(B, H, T, 64).transpose(1, 2).reshape(B, T, D)
+        x_mid = x0 + ko._linear(e, ko._ln(e, ko._inner(sa.inner_attn_ln), att), ko._inner(sa.out_proj))
+        ffn = ko._inner(L.ffn)
+        u = ko._linear(e, ko._ln(e, ko._inner(L.final_layer_norm), x_mid), ffn.fc1)
+        mid = e.r(torch.nn.functional.gelu(u))
+        x_out = x_mid + ko._linear(e, ko._ln(e, ffn.ffn_layernorm, mid), ffn.fc2)
+        unrot = lambda t: t.view(B, H, T, 64).transpose(1, 2).reshape(M, D)
+    dec = mine.decoder
+    pk = dec._pack()["layers"][0]
+    dev = "cuda"
+    bf, f32 = torch.bfloat16, torch.float32
+    x = x0.reshape(M, D).to(dev).clone()
+    xb = torch.empty(M, D, dtype=bf, device=dev); qkv = torch.empty(M, 3 * D, dtype=bf, device=dev)
+    attg = torch.empty(M, D, dtype=bf, device=dev); midg = torch.empty(M, Fd, dtype=bf, device=dev)
+    st_in = torch.empty(1, M, 2, device=dev); st_a = torch.empty((D + 127) // 128, M, 2, device=dev)
+    st_b = torch.empty_like(st_a); st_att = torch.empty(H, M, 2, device=dev); st_mid = torch.empty((Fd + 127) // 128, M, 2, device=dev)
+    tabs = dec._xpos(T, dev)
+    ops.rowstats_cast(x, xb, st_in)
+    wq, c, d = pk["qkv"]
+    ops.gemm(xb, wq, qkv, bias=d, ln=(st_in, c, D, oc.eps), xpos=tuple(tabs), seq_len=T)
+    ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], attg, batch=B, heads=H, seq_len=T, causal=True, scale=0.125, stats_out=st_att)
+    wo, c, d = pk["o"]
+    ops.gemm(attg, wo, x, bias=d, res=x, ln=(st_att, c, D, oc.eps), stats_out=st_a, out2=xb)
+    x_mid_g = x.clone()
+    w1, c, d = pk["fc1"]
+    ops.gemm(xb, w1, midg, bias=d, act=_abi.KX_ACT_GELU, ln=(st_a, c, D, oc.eps), stats_out=st_mid)
+    w2, c, d = pk["fc2"]
+    ops.gemm(midg, w2, x, bias=d, res=x, ln=(st_mid, c, Fd, oc.eps), stats_out=st_b, out2=xb)
+    rows = [("q (rotated, x 1/8)", qkv[:, :D].float() * 0.125, unrot(qh)), ("k (rotated)", qkv[:, D:2 * D], unrot(kh)),
+            ("v", qkv[:, 2 * D:], unrot(vh)), ("attention out", attg, att.reshape(M, D)),
+            ("attention out vs un-rounded-P oracle", attg, unrot(a_exact)),
+            ("x after out_proj", x_mid_g, x_mid.reshape(M, D)), ("gelu(fc1) (bf16)", midg, mid.reshape(M, Fd)),
+            ("x after fc2", x, x_out.reshape(M, D))]
+    print("\n# Decoder layer 0 in isolation (input = the oracle's fp32 x0): kernels vs bf16-emulating oracle\n")
+    print("| tensor | rms(ref) | max-abs / RMS |\n|---|---|---|")
+    for name, g, r in rows:
+        er = err(g, r)
+        print(f"| {name} | {er[2]:.3f} | {er[0]:.2e} / {er[1]:.2e} |")
+
+
 if __name__ == "__main__":
-    main()
+    if "--layer" in sys.argv:
+        layer_breakdown()
+    else:
+        main()
