@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 15   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 16   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -342,7 +342,9 @@ int kx_sum_rows_f32(const float* src, long long ld, int rows, long long n, float
 /* Gradient clipping (clip_grad_norm_, train.py:652-653) without a host sync: *out += sum g^2; then
  * scale = pre_scale * min(1, max_norm / (pre_scale * sqrt(sumsq) + 1e-6)), norm_out = pre_scale * sqrt(sumsq)
  * (pre_scale = 1 / world size turns all-reduced gradient sums into means; max_norm <= 0 = no clipping). */
-int kx_sumsq(const float* g, long long n, float* out, kx_stream_t stream);
+#define KX_SUMSQ_SCRATCH 2048   /* floats of scratch kx_sumsq needs (per-block partials, folded in index order: the norm is
+                                * bit-reproducible, so replicas holding identical gradients take identical steps) */
+int kx_sumsq(const float* g, long long n, float* out, float* scratch, kx_stream_t stream);
 int kx_clip_scale(const float* sumsq, float max_norm, float pre_scale, float* scale_out, float* norm_out, kx_stream_t stream);
 
 /* Fused optimizers over flat fp32 buffers (master weights, gradients, moments); *grad_scale (device, may be NULL)

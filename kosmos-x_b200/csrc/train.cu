@@ -580,8 +580,11 @@ embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ to
 }
 
 // ----------------------------------------------------------------------------- gradient norm + optimizers
+// Deterministic: block b writes its partial to scratch[b]; sumsq_finish_kernel folds the partials in index order.  (An
+// atomicAdd per block would make the gradient norm — hence the clip coefficient, hence every parameter — depend on block
+// scheduling: data-parallel replicas holding bit-identical gradients would drift apart by ulps per step.)
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ scratch) {
     __shared__ float red[16];
     float s = 0.f, dummy = 0.f;
     const long long nv = n >> 2;
@@ -593,7 +596,16 @@ sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) 
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (long long i = nv << 2; i < n; ++i) s = fmaf(g[i], g[i], s);
     block_sum2(s, dummy, red);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) scratch[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_finish_kernel(const float* __restrict__ scratch, int parts, float* __restrict__ out) {
+    __shared__ float red[16];
+    float s = 0.f, dummy = 0.f;
+    for (int i = threadIdx.x; i < parts; i += 256) s += scratch[i];          // fixed assignment, fixed order
+    block_sum2(s, dummy, red);
+    if (threadIdx.x == 0) *out += s;
 }
 
 // scale = min(1, max_norm / (sqrt(sumsq * pre_scale^2) + 1e-6)) * pre_scale   (torch.nn.utils.clip_grad_norm_;
@@ -886,11 +898,15 @@ extern "C" int kx_embed_bwd(const float* dx0, const long long* tokens, int batch
     return check_launch("kx_embed_bwd");
 }
 
-extern "C" int kx_sumsq(const float* g, long long n, float* out, cudaStream_t stream) {
-    if (!g || !out || n <= 0 || !KX_ALIGNED16(g)) { set_error("kx_sumsq: bad argument"); return KX_ERR_ARG; }
+extern "C" int kx_sumsq(const float* g, long long n, float* out, float* scratch, cudaStream_t stream) {
+    if (!g || !out || !scratch || n <= 0 || !KX_ALIGNED16(g)) { set_error("kx_sumsq: bad argument"); return KX_ERR_ARG; }
     const int sms = device_sm_count();
     if (sms <= 0) return KX_ERR_NO_DEVICE;
-    sumsq_kernel<<<grid_for(n, sms, 4), 256, 0, stream>>>(g, n, out);
+    const int parts = std::min(grid_for(n, sms, 4), KX_SUMSQ_SCRATCH);
+    sumsq_kernel<<<parts, 256, 0, stream>>>(g, n, scratch);
+    int st = check_launch("kx_sumsq");
+    if (st != KX_OK) return st;
+    sumsq_finish_kernel<<<1, 256, 0, stream>>>(scratch, parts, out);
     return check_launch("kx_sumsq");
 }
 

@@ -19,6 +19,7 @@ KX_MAX_IMAGES = 16
 KX_DEC_PLAIN, KX_DEC_RESIDUAL, KX_DEC_QKV = 0, 1, 2
 KX_DECODE_MAX_BATCH = 32
 KX_LOSS_REFERENCE, KX_LOSS_NEXT_TOKEN = 0, 1
+KX_SUMSQ_SCRATCH = 2048
 
 _f32p = C.c_void_p
 _vp = C.c_void_p
@@ -129,7 +130,7 @@ SIGNATURES = {
     "kx_loss_targets": (_i, [_vp, _i, _i, C.POINTER(_i), _i, _i, _i, _ll, _vp, _f32p, _vp]),
     "kx_ce_fwd_bwd": (_i, [_f32p, _ll, _vp, _i, _i, _f32p, _vp, _ll, _f32p, _vp, _vp]),
     "kx_embed_bwd": (_i, [_f32p, _vp, _i, _i, C.POINTER(_i), _i, _i, _i, _i, _i, _i, _f32p, _f32p, _vp]),
-    "kx_sumsq": (_i, [_f32p, _ll, _f32p, _vp]),
+    "kx_sumsq": (_i, [_f32p, _ll, _f32p, _f32p, _vp]),
     "kx_clip_scale": (_i, [_f32p, _f, _f, _f32p, _f32p, _vp]),
     "kx_adamw_step": (_i, [_f32p, _f32p, _f32p, _f32p, _vp, _ll, _f, _f, _f, _f, _f, _i, _f32p, _vp]),
     "kx_lion_step": (_i, [_f32p, _f32p, _f32p, _vp, _ll, _f, _f, _f, _f, _f32p, _vp]),

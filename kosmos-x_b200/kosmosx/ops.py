@@ -315,8 +315,15 @@ def embed_bwd(dx0, tokens, d_embed, d_pos, *, img_rows=(), n_img=0, padding_idx=
                                vocab, padding_idx, 1 if alias_positions else 0, _ptr(d_embed), _ptr(d_pos), _stream()), "kx_embed_bwd")
 
 
+_sumsq_scratch = {}
+
+
 def sumsq(g, out):
-    check(lib.kx_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "kx_sumsq")
+    """out += sum g^2, bit-reproducible (per-block partials folded in a fixed order)."""
+    sc = _sumsq_scratch.get(g.device)
+    if sc is None:
+        sc = _sumsq_scratch[g.device] = torch.empty(_abi.KX_SUMSQ_SCRATCH, dtype=torch.float32, device=g.device)
+    check(lib.kx_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), sc.data_ptr(), _stream()), "kx_sumsq")
 
 
 def clip_scale(sumsq_t, max_norm, pre_scale, scale_out, norm_out=None):

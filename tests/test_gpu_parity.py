@@ -16,12 +16,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TOL_EMU_TINY = 4e-2      # tiny config logits (std ~1): max-abs vs bf16-emulating oracle (measured 1.5e-2 .. 2.0e-2)
-RMS_EMU_TINY = 6e-3      # ... and RMS (measured 3.6e-3): flash-style P scaling / summation order are not emulated
-TOL_F32_TINY = 8e-2      # tiny config logits: max-abs vs fp32 oracle
-TOL_EMU_FULL = 6e-2      # full-size (24+24 layers): max-abs vs bf16-emulating oracle
-TOL_F32_FULL = 2.5e-1    # full-size: max-abs vs fp32 oracle (logit std ~1.0)
-RMS_F32_FULL = 2.5e-2    # full-size: RMS error vs fp32 oracle
+# Every bound below is <= 1.5 x the largest value measured on B200 in round 2 (profiles/r2_parity_measured.md); the
+# per-stage growth of the error is tabulated in profiles/r2_stage_errors_*.md.
+TOL_EMU_TINY = 3.0e-2    # tiny config logits (std ~1): max-abs vs bf16-emulating oracle (measured 1.48e-2 .. 2.05e-2)
+RMS_EMU_TINY = 5.0e-3    # ... and RMS (measured 3.0e-3 .. 3.4e-3)
+TOL_F32_TINY = 3.2e-2    # tiny config logits: max-abs vs fp32 oracle (measured 1.73e-2 .. 2.12e-2)
+TOL_EMU_FULL = 5.0e-2    # full-size (24+24 layers): max-abs vs bf16-emulating oracle (measured 3.12e-2 .. 3.40e-2)
+TOL_F32_FULL = 6.0e-2    # full-size: max-abs vs fp32 oracle, logit std 1.0 (measured 3.99e-2)
+RMS_F32_FULL = 1.2e-2    # full-size: RMS error vs fp32 oracle (measured 7.95e-3)
+TOL_DEC_FULL = 4.0e-2    # full-size KV-cache decoding vs own full forward / vs the emulating oracle (measured 2.0e-2 .. 2.6e-2)
 
 
 def _err(got, ref):
@@ -120,7 +123,9 @@ def test_tiny_stages_match_golden(tiny_pair, golden):
     text, images = ko.make_inputs(oc, g["B"], g["t_text"], seed=1)
     B, T = g["B"], g["t_text"] + oc.p_latents
     xv = mine._vit(images.cuda().float()).view(B, oc.vit_tokens, oc.vit_dim)
-    assert _err(xv[:, ::4], g["vit"])[0] <= 5e-2
+    ev = _err(xv[:, ::4], g["vit"])
+    print(f"stages: ViT output vs fp32 golden max={ev[0]:.3e} rms={ev[1]:.3e}")
+    assert ev[0] <= 1.2e-2                                          # measured 5.9e-3 (tools/stage_errors.py)
     with torch.no_grad():
         st = ref.stages(text, images)
     dp = mine.decoder._pack()
@@ -132,8 +137,10 @@ def test_tiny_stages_match_golden(tiny_pair, golden):
     x0 = x0.view(B, T, oc.dim)
     assert _err(x0[:, :2], st["x0"][:, :2])[0] <= 1e-6            # text rows: exact gather + fp32 add
     assert _err(x0[:, 66:], st["x0"][:, 66:])[0] <= 1e-6
-    assert _err(x0[:, 2:66], st["x0"][:, 2:66])[0] <= 5e-2         # image rows through ViT+perceiver (bf16 operands)
-    assert _err(x0[:, ::2], g["x0"])[0] <= 5e-2
+    ex = _err(x0[:, 2:66], st["x0"][:, 2:66])
+    print(f"stages: image rows of x0 vs fp32 oracle max={ex[0]:.3e} rms={ex[1]:.3e}")
+    assert ex[0] <= 1.6e-2                                          # image rows through ViT+perceiver (bf16 operands; measured 1.06e-2)
+    assert _err(x0[:, ::2], g["x0"])[0] <= 1.6e-2
 
 
 @pytest.fixture(scope="module")
@@ -182,8 +189,10 @@ def test_tiny_multi_image_splice(tiny512_pair, name):
     for r in rows:
         is_img[r:r + oc.p_latents] = True
     assert _err(x0[:, ~is_img], st["x0"][:, ~is_img])[0] <= 1e-6
-    assert _err(x0[:, is_img], st["x0"][:, is_img])[0] <= 5e-2
-    assert _err(x0[:, ::2], g["x0"])[0] <= 5e-2
+    ei = _err(x0[:, is_img], st["x0"][:, is_img])
+    print(f"multi-image {name}: image rows of x0 vs fp32 oracle max={ei[0]:.3e}")
+    assert ei[0] <= 2.0e-2
+    assert _err(x0[:, ::2], g["x0"])[0] <= 2.0e-2
     e = _err(got, want)
     eg = _err(got[..., ::g["col_step"]], g["logits_emu_bf16"])
     print(f"multi-image {name} m={m} at {positions}: vs bf16-emulating oracle max={e[0]:.3e} rms={e[1]:.3e}; golden max={eg[0]:.3e}")
@@ -418,7 +427,7 @@ def test_language_model_matches_oracle():
 # --------------------------------------------------------------------------- full size (BASELINE.json configs)
 
 # --------------------------------------------------------------------------- incremental decoding
-TOL_DEC_SELF = 3e-2      # KV-cache path vs the same model's full forward (bf16 operands both ways; measured ~1e-2)
+TOL_DEC_SELF = 1.9e-2    # KV-cache path vs the same model's full forward (bf16 operands both ways; measured 0.84e-2 .. 1.25e-2)
 
 
 def test_tiny_incremental_decoding_vs_oracle(tiny_pair):
@@ -546,7 +555,9 @@ def test_language_model_generate_batches(tiny_cfgs):
         assert e[0] <= TOL_DEC_SELF
         with torch.no_grad():
             want = lm_ref(torch.cat([x, forced[:, :-1]], 1))[:, 8:]
-        assert _err(got, want)[0] <= TOL_F32_TINY
+        ef = _err(got, want)
+        print(f"KosmosLanguage.generate B={B}: vs fp32 oracle max={ef[0]:.3e}")
+        assert ef[0] <= TOL_F32_TINY
     with pytest.raises(ValueError):
         lm.generate(torch.zeros(33, 4, dtype=torch.int64, device="cuda"), 2)
 
@@ -734,7 +745,7 @@ def test_full_size_seq2048_properties(full_pair):
         ref.set_emulation(False)
     e = _err(one, want)
     print(f"C3 sequence 3 (T=2048) vs bf16-emulating oracle: max={e[0]:.3e} rms={e[1]:.3e}")
-    assert e[0] <= 2 * TOL_EMU_FULL
+    assert e[0] <= TOL_EMU_FULL
 
 
 def test_full_size_generate_vs_forward_and_oracle(full_pair):
@@ -750,7 +761,7 @@ def test_full_size_generate_vs_forward_and_oracle(full_pair):
     full = mine(torch.cat([text, forced[:, :-1]], 1).cuda(), images.cuda())
     e = _err(got, full[:, t0 - 1:])
     print(f"full-size incremental decoding vs own full forward: max={e[0]:.3e} rms={e[1]:.3e}")
-    assert e[0] <= TOL_EMU_FULL
+    assert e[0] <= TOL_DEC_FULL
     agree = (got.argmax(-1) == full[:, t0 - 1:].argmax(-1)).float().mean().item()
     assert agree >= 0.9, agree
     with torch.no_grad():
@@ -759,12 +770,12 @@ def test_full_size_generate_vs_forward_and_oracle(full_pair):
         ref.set_emulation(False)
     e16 = _err(got[:1], want)
     print(f"full-size incremental decoding vs bf16-emulating oracle (sequence 0): max={e16[0]:.3e} rms={e16[1]:.3e}")
-    assert e16[0] <= TOL_EMU_FULL
+    assert e16[0] <= TOL_DEC_FULL
     _, got_pk = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True, one_kernel=False)
     _, got_one = mine.generate(text.cuda(), images.cuda(), n, forced_tokens=forced.cuda(), return_logits=True, one_kernel=True)
     ep = _err(got_pk, got_one)
     print(f"full-size per-kernel decoding vs one-kernel step: max={ep[0]:.3e} rms={ep[1]:.3e}")
-    assert ep[0] <= TOL_EMU_FULL and _err(got_one, full[:, t0 - 1:])[0] <= TOL_EMU_FULL
+    assert ep[0] <= TOL_DEC_FULL and _err(got_one, full[:, t0 - 1:])[0] <= TOL_DEC_FULL
     g1 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=False)
     g2 = mine.generate(text.cuda(), images.cuda(), n, one_kernel=False, cuda_graph=False)
     assert torch.equal(g1, g2)
@@ -793,7 +804,7 @@ def test_full_size_training_gradients_vs_oracle(full_pair):
     want.backward()
     ref.set_emulation(False)
     print(f"full-size training: loss cuda {loss.item():.5f} oracle {want.item():.5f}")
-    assert abs(loss.item() - want.item()) <= 1e-2
+    assert abs(loss.item() - want.item()) <= 2.5e-3           # measured 1.5e-3
     ref_named = dict(ref.named_parameters())
     worst = (0.0, "")
     for p in trainer.params:
@@ -801,7 +812,7 @@ def test_full_size_training_gradients_vs_oracle(full_pair):
         g, g_ref = p.grad.detach().float().cpu(), ref_named[n].grad
         rel = ((g - g_ref).norm() / (g_ref.norm() + 1e-12)).item()
         worst = max(worst, (rel, n))
-        assert rel <= 6e-2, f"{n}: relative gradient error {rel:.3e}"
+        assert rel <= 2.9e-2, f"{n}: relative gradient error {rel:.3e}"     # measured worst 1.9e-2
     print(f"full-size training: {len(trainer.params)} gradient tensors, worst relative error {worst[0]:.3e} ({worst[1]})")
     for p in ref.parameters():
         p.grad = None

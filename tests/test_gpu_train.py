@@ -14,8 +14,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-GRAD_REL = 4e-2
-LOSS_TOL = 5e-3
+GRAD_REL = 2e-2          # measured worst 1.21e-2 (decoder.layers.1.self_attn.k_proj.A.bias)
+LOSS_TOL = 2.5e-3        # measured <= 9.1e-4 (tiny), 1.5e-3 (reference size)
 
 
 def _pair(max_positions=256, optimizer="adamw", **kw):

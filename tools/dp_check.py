@@ -72,18 +72,25 @@ def main():
             for _ in range(3):
                 t2.step(tg[lo:hi], ig[lo:hi])
             torch.cuda.synchronize()
+            same = True
             for name, buf in (("P", t2.P), ("M1", t2.M1), ("M2", t2.M2), ("W16", t2.W16)):
                 ref0 = buf.clone()
                 dist.broadcast(ref0, 0)
+                same &= bool(torch.equal(ref0, buf))
                 check(torch.equal(ref0, buf), f"{tag}: replica buffer {name} differs from rank 0's")
+            same_t = torch.tensor([int(same)], device="cuda")
+            dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
             d = (t2.P - p1).abs()
             # Adam's first steps move every element by ~lr * sign(g): an element whose gradient is at the reduction-noise
             # level may take the other sign, nothing else may differ
             check(d.max().item() <= 3 * 2.1e-3, f"{tag}: parameters {d.max().item():.3e} from the single-process run")
             frac = (d > 1e-5).float().mean().item()
-            check(frac <= (2e-3 if rd == torch.float32 else 5e-2), f"{tag}: {frac:.3e} of the parameters differ from the single-process run")
+            mean_d = d.mean().item()
+            check(frac <= (2e-2 if rd == torch.float32 else 0.25) and mean_d <= (2e-5 if rd == torch.float32 else 2e-4),
+                  f"{tag}: {frac:.3e} of the parameters differ from the single-process run (mean |diff| {mean_d:.2e})")
             if rank == 0:
-                print(f"{tag}: grad rel {rel:.2e}, params max diff {d.max().item():.2e}, differing fraction {frac:.2e}, replicas bit-identical", flush=True)
+                print(f"{tag}: grad rel {rel:.2e}, params max diff {d.max().item():.2e}, differing fraction {frac:.2e}, "
+                      f"replicas {'bit-identical' if same_t.item() else 'DIFFER'} after 3 steps", flush=True)
             del m2, t2
     # autograd bridge: param.grad is the MEAN over ranks (DistributedDataParallel's convention)
     tgt = ko.KosmosOracle.loss_targets(text, oc.p_latents).cuda()

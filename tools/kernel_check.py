@@ -648,7 +648,7 @@ def case_accurate():
         out = torch.empty(M, N, device=dev)
         ops.gemm(a3, w3, out, bias=bias)
         want = (a.double() @ w.double().T + bias.double()).float()
-        ok &= report(f"bf16x3 GEMM {M}x{N}x{K} vs fp64", out, want, 5e-5)
+        ok &= report(f"bf16x3 GEMM {M}x{N}x{K} vs fp64", out, want, 5e-5 * max(1.0, (K / 128) ** 0.5))
         if K % 8 == 0:
             plain = torch.empty(M, N, device=dev)
             ops.gemm(a.bfloat16(), w.bfloat16(), plain, bias=bias)
