@@ -451,15 +451,10 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.t_pad = (seq_len + 127) / 128 * 128;
     p.trace = g_attn_trace;
     static bool attr_set = false;
-    static bool poly = true;            // KX_ATTN_POLY=0 keeps every exp2 on the MUFU (A/B measurements)
     if (!attr_set) {
-        const char* e = getenv("KX_ATTN_POLY");
-        poly = !(e && e[0] == '0');
         cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
         cudaError_t e2 = cudaFuncSetAttribute(attn_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        cudaError_t e3 = cudaFuncSetAttribute(attn_pp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        cudaError_t e4 = cudaFuncSetAttribute(attn_pp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
             set_error("kx_attn_fwd: cudaFuncSetAttribute failed");
             return KX_ERR_LAUNCH;
         }
@@ -473,21 +468,14 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     if (p.trace != nullptr && causal) {          // profiling aid (kx_attn_set_trace): same kernel with clock64 stamps
         static bool tattr = false;
         if (!tattr) {
-            cudaFuncSetAttribute(attn_pp_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
             cudaFuncSetAttribute(attn_pp_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
             tattr = true;
         }
-        if (poly) attn_pp_kernel<true, true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
-        else attn_pp_kernel<true, false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        attn_pp_kernel<true, true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
         return check_launch("kx_attn_fwd");
     }
-    if (causal) {
-        if (poly) attn_pp_kernel<true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
-        else attn_pp_kernel<true, false><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
-    } else {
-        if (poly) attn_pp_kernel<false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
-        else attn_pp_kernel<false, false><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
-    }
+    if (causal) attn_pp_kernel<true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+    else attn_pp_kernel<false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
     return check_launch("kx_attn_fwd");
 }
 

@@ -34,32 +34,7 @@ struct DecLin {
     __nv_bfloat16* k_cache; __nv_bfloat16* v_cache; int t_max; int d_model;
     const int* pos;
     const float *xq_cos, *xq_sin, *xk_cos, *xk_sin;
-    int stages;                              // bulk-copy variant: shared-memory stages of one 2048-wide k chunk each
 };
-
-// bulk-copy variant of the weight stream: one stage = 16 weight rows x 2048 k, rows padded by 64 bytes so that the
-// quad-row 16-byte LDS pattern of the MMA fragments touches all 32 banks
-constexpr int TMA_KC = 2048;
-constexpr int TMA_PITCH = TMA_KC * 2 + 64;
-constexpr int TMA_STAGE = 16 * TMA_PITCH;                    // 66560 bytes
-constexpr int TMA_MAX_STAGES = 3;
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void full_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (3ll << 31)) __trap();
-    }
-}
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
@@ -94,38 +69,8 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
-bool pdl_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("KX_DECODE_PDL");
-        return !(e != nullptr && e[0] == '0');
-    }();
-    return on;
-}
-
-template <typename... KArgs, typename... Args>
-cudaError_t launch_chain_smem(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-
-// KX_DECODE_TMA=1 selects the bulk-copy variant.  Measured at B=8: 1.059 ms per step against 1.028 ms for the register
-// variant — with programmatic dependent launch the step is bound by the per-kernel dependency chain (completion signal,
-// activation round trip, reduction, store flush: ~3.5 us x 121 kernels), not by the in-kernel stream rate, so the default
-// stays the simpler register variant.
-bool tma_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("KX_DECODE_TMA");
-        return e != nullptr && e[0] == '1';
-    }();
-    return on;
-}
-
+// A bulk-copy (cp.async.bulk -> smem) variant of decode_linear_kernel was measured in round 1 (1.059 ms per step against
+// 1.028 ms: the step is bound by the per-kernel dependency chain, not by the in-kernel stream rate) and removed in round 2.
 template <typename... KArgs, typename... Args>
 cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -134,7 +79,7 @@ cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStre
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
@@ -154,11 +99,7 @@ int check_chain(cudaError_t e, const char* what) {
 // U = 32-wide k steps (2 x 16-byte weight loads each) a thread keeps in flight; MINB = CTAs per SM the registers allow.
 // Wide N (>= one CTA per SM slot): U = 4, 3 CTAs/SM.  Narrow N (fewer tiles than SMs): one CTA per SM has to keep the
 // whole 45 KB/SM in flight alone, U = 8.
-// TMA = true (opt-in, KX_DECODE_TMA=1): the CTA's whole weight tile is requested with bulk copies (cp.async.bulk ->
-// shared memory, mbarrier complete_tx) by 16 lanes in the kernel's first instructions — BEFORE the dependency wait — so
-// every byte of the matrix is in flight at once (3 CTAs x 65 KB per SM) instead of 8 x 16 bytes per thread per round
-// trip; the fragments are then read from shared memory.
-template <int NB, int U, int MINB, bool TMA>
+template <int NB, int U, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 decode_linear_kernel(const DecLin p) {
     constexpr int NBC = NB * 8;
@@ -217,74 +158,6 @@ decode_linear_kernel(const DecLin p) {
             e_x = p.x[static_cast<long long>(e_b) * p.ld_x + e_n];
         }
     };
-    if constexpr (TMA) {
-        extern __shared__ __align__(128) unsigned char stage_mem[];
-        __shared__ uint64_t full[TMA_MAX_STAGES];
-        const int n_chunks = (p.K + TMA_KC - 1) / TMA_KC;
-        const int stages = min(n_chunks, p.stages);
-        const int rows = min(16, p.N - n0);
-        const uint32_t sbase = smem_u32(stage_mem);
-        if (tid == 0) {
-            for (int i = 0; i < stages; ++i) mbar_init(full + i, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        auto issue = [&](int c) {                           // warp 0, all lanes: lane `row` copies that row's k chunk
-            const int ck = min(TMA_KC, p.K - c * TMA_KC);
-            const int stg = c % stages;
-            if (lane == 0) mbar_arrive_expect_tx(full + stg, static_cast<uint32_t>(rows * ck * 2));
-            __syncwarp();
-            if (lane < rows)
-                bulk_g2s(sbase + stg * TMA_STAGE + lane * TMA_PITCH,
-                         p.w + static_cast<long long>(n0 + lane) * p.ldw + static_cast<long long>(c) * TMA_KC,
-                         static_cast<uint32_t>(ck * 2), full + stg);
-        };
-        if (warp == 0)
-            for (int c = 0; c < stages; ++c) issue(c);      // weights do not depend on the previous kernel
-        pdl_wait();
-        after_wait();
-        for (int c = 0; c < n_chunks; ++c) {
-            const int ck = min(TMA_KC, p.K - c * TMA_KC);
-            const int csteps = ck >> 5;
-            const int cspw = (csteps + 7) >> 3;             // <= 8 steps per warp and chunk
-            const int c_lo = warp * cspw, c_hi = min(csteps, c_lo + cspw);
-            const int stg = c % stages;
-            const uint32_t wrow = sbase + stg * TMA_STAGE + g * TMA_PITCH + t * 16;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint4 av[4][NB];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int sidx = c_lo + half * 4 + u;
-#pragma unroll
-                    for (int nb = 0; nb < NB; ++nb)
-                        av[u][nb] = (sidx < c_hi && aok[nb]) ? ld_act(ap[nb] + (c * (TMA_KC >> 3) + sidx * 4)) : make_uint4(0, 0, 0, 0);
-                }
-                if (half == 0) full_wait(full + stg, (c / stages) & 1);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int sidx = c_lo + half * 4 + u;
-                    if (sidx < c_hi) {
-                        const uint4 wa = lds128(wrow + sidx * 64);
-                        const uint4 wb = lds128(wrow + 8 * TMA_PITCH + sidx * 64);
-#pragma unroll
-                        for (int nb = 0; nb < NB; ++nb) {
-                            mma_bf16_16816(acc[nb], wa.x, wb.x, wa.y, wb.y, av[u][nb].x, av[u][nb].y);
-                            mma_bf16_16816(acc[nb], wa.z, wb.z, wa.w, wb.w, av[u][nb].z, av[u][nb].w);
-                            if (p.ln) {
-                                bf16x2_stats(av[u][nb].x, s1[nb], s2[nb]); bf16x2_stats(av[u][nb].y, s1[nb], s2[nb]);
-                                bf16x2_stats(av[u][nb].z, s1[nb], s2[nb]); bf16x2_stats(av[u][nb].w, s1[nb], s2[nb]);
-                            }
-                        }
-                    }
-                }
-            }
-            if (c + stages < n_chunks) {                    // refill this stage once every warp has consumed it
-                __syncthreads();
-                if (warp == 0) issue(c + stages);
-            }
-        }
-    } else {
     bool waited = false;
     for (int s = s_begin; s < s_end; s += U) {
         uint4 wa[U], wb[U], av[U][NB];
@@ -321,7 +194,6 @@ decode_linear_kernel(const DecLin p) {
     }
 
     if (!waited) { pdl_wait(); after_wait(); }
-    }
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
         red[warp][g][nb * 8 + 2 * t] = acc[nb][0];
@@ -717,31 +589,13 @@ extern "C" int kx_decode_linear(const void* a, long long lda, int batch, const v
     if (sms <= 0) return KX_ERR_NO_DEVICE;
     const int tiles = (N + 15) / 16;
     cudaError_t e;
-    if (tma_enabled()) {
-        const int n_chunks = (K + TMA_KC - 1) / TMA_KC;
-        p.stages = std::min(n_chunks, TMA_MAX_STAGES);
-        const size_t smem = static_cast<size_t>(p.stages) * TMA_STAGE;
-        static bool attr_set = false;
-        if (!attr_set) {
-            const int mx = TMA_MAX_STAGES * TMA_STAGE;
-            cudaError_t a = cudaFuncSetAttribute(decode_linear_kernel<1, 4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            if (a == cudaSuccess) a = cudaFuncSetAttribute(decode_linear_kernel<2, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            if (a == cudaSuccess) a = cudaFuncSetAttribute(decode_linear_kernel<4, 4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-            if (a != cudaSuccess) { (void)cudaGetLastError(); set_error("kx_decode_linear: %s", cudaGetErrorString(a)); return KX_ERR_LAUNCH; }
-            attr_set = true;
-        }
-        if (batch <= 8) e = launch_chain_smem(decode_linear_kernel<1, 4, 3, true>, dim3(tiles), dim3(256), smem, stream, p);
-        else if (batch <= 16) e = launch_chain_smem(decode_linear_kernel<2, 4, 2, true>, dim3(tiles), dim3(256), smem, stream, p);
-        else e = launch_chain_smem(decode_linear_kernel<4, 4, 1, true>, dim3(tiles), dim3(256), smem, stream, p);
-        return check_chain(e, "kx_decode_linear");
-    }
     if (batch <= 8) {
-        if (tiles <= sms + sms / 4) e = launch_chain(decode_linear_kernel<1, 8, 1, false>, dim3(tiles), dim3(256), stream, p);
-        else e = launch_chain(decode_linear_kernel<1, 4, 3, false>, dim3(tiles), dim3(256), stream, p);
+        if (tiles <= sms + sms / 4) e = launch_chain(decode_linear_kernel<1, 8, 1>, dim3(tiles), dim3(256), stream, p);
+        else e = launch_chain(decode_linear_kernel<1, 4, 3>, dim3(tiles), dim3(256), stream, p);
     } else if (batch <= 16) {
-        e = launch_chain(decode_linear_kernel<2, 4, 2, false>, dim3(tiles), dim3(256), stream, p);
+        e = launch_chain(decode_linear_kernel<2, 4, 2>, dim3(tiles), dim3(256), stream, p);
     } else {
-        e = launch_chain(decode_linear_kernel<4, 4, 1, false>, dim3(tiles), dim3(256), stream, p);
+        e = launch_chain(decode_linear_kernel<4, 4, 1>, dim3(tiles), dim3(256), stream, p);
     }
     return check_chain(e, "kx_decode_linear");
 }

@@ -15,6 +15,9 @@
 #include "kx_internal.h"
 #include "ptx.cuh"
 
+#include <mutex>
+#include <unordered_map>
+
 namespace kx {
 
 // Build with -DKX_GEMM_TRACE to record clock64 stamps of epilogue warp 4 of CTA 0 (staged epilogue):
@@ -691,10 +694,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ----------------------------------------------------------------------------- host side
+// cuTensorMapEncodeTiled costs 1-2 us of host time and a GEMM launch needs up to five maps; the un-graphed training step
+// issues ~500 GEMMs over the same few hundred (buffer, shape) pairs every step, so encoded maps are cached per host
+// thread, keyed by everything that goes into the encoding (the cache holds descriptors only — never device data).
+struct TmapKey {
+    const void* ptr; uint64_t inner, outer, stride; uint32_t box_inner, box_outer; int dtype, swizzle;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && stride == o.stride && box_inner == o.box_inner &&
+               box_outer == o.box_outer && dtype == o.dtype && swizzle == o.swizzle;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+        for (uint64_t v : {k.inner, k.outer, k.stride, (uint64_t(k.box_inner) << 32) | k.box_outer, (uint64_t(uint32_t(k.dtype)) << 32) | uint32_t(k.swizzle)})
+            h = (h ^ v) * 0x100000001B3ull + (h >> 29);
+        return static_cast<size_t>(h);
+    }
+};
+
 static bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer,
                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer,
                          CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                          CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+    thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    const TmapKey key{ptr, inner, outer, row_stride_bytes, box_inner, box_outer, static_cast<int>(dtype), static_cast<int>(swizzle)};
+    auto hit = cache.find(key);
+    if (hit != cache.end()) { *tm = hit->second; return true; }
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {row_stride_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
@@ -710,6 +736,8 @@ static bool make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint6
                   box_outer);
         return false;
     }
+    if (cache.size() >= 8192) cache.clear();
+    cache.emplace(key, *tm);
     return true;
 }
 bool make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
@@ -755,12 +783,10 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
         tmOut2 = tmA;
     }
     auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI, ATR, BTR>;
-    static bool attr_set = false;   // per template instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
-        attr_set = true;
-    }
+    static std::once_flag attr_once;   // per template instantiation; safe when several host threads launch GEMMs
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+    if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err)); return KX_ERR_LAUNCH; }
     const int num_m = (ep.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
     const int num_n = (ep.N + BN - 1) / BN;
     int clusters = std::min(num_m * num_n, std::max(1, max_ctas / CG));

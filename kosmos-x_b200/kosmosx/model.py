@@ -692,7 +692,7 @@ class _KosmosBase(nn.Module):
         dec.advance(state, history=history, forced=forced, move=False)       # token 0 comes from the prompt's last row
         steps = max_new_tokens - 1
         if one_kernel is None:
-            one_kernel = B <= 8 and os.environ.get("KX_DECODE_ONE_KERNEL", "1") != "0"
+            one_kernel = B <= 8
             auto = True
         else:
             auto = False

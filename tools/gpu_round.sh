@@ -31,10 +31,5 @@ for w in $what; do
     ncu_attn_bwd) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_bwd_kernel -s 2 -c 1 -o "$out/prof_attn_bwd" -f python tools/kernel_check.py bench_train > "$out/ncu_attn_bwd.log" 2>&1; echo "ncu_attn_bwd exit $?" | tee -a "$out/summary.txt";;
     ncu_wgrad) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 16 -c 1 -o "$out/prof_wgrad" -f python tools/kernel_check.py bench_train > "$out/ncu_wgrad.log" 2>&1; echo "ncu_wgrad exit $?" | tee -a "$out/summary.txt";
                timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 4 -c 1 -o "$out/prof_dgrad" -f python tools/kernel_check.py bench_train > "$out/ncu_dgrad.log" 2>&1; echo "ncu_dgrad exit $?" | tee -a "$out/summary.txt";;
-    attn_dbg) for d in 0 1 2 3; do for poly in 1 0; do echo "dbg=$d poly=$poly"; KX_ATTN_DEBUG=$d KX_ATTN_POLY=$poly timeout 300 python tools/kernel_check.py bench_attn 2>&1 | grep -E "attn causal=True B=8|rror"; done; done | tee "$out/attn_dbg.log";;
-    attn_poly) for poly in 1 0; do KX_ATTN_POLY=$poly timeout 300 python tools/kernel_check.py attn > "$out/attn_poly$poly.log" 2>&1; echo "attn poly=$poly exit $?" | tee -a "$out/summary.txt"; grep -E "FAIL|^==|rror" "$out/attn_poly$poly.log" | tail -5;
-                KX_ATTN_POLY=$poly timeout 300 python tools/kernel_check.py bench_attn > "$out/bench_attn_poly$poly.log" 2>&1; grep -E "attn " "$out/bench_attn_poly$poly.log"; done;;
-    attn_ab)  for impl in 1 0; do KX_ATTN_IMPL=$impl timeout 300 python tools/kernel_check.py attn > "$out/attn_impl$impl.log" 2>&1; echo "attn impl=$impl exit $?" | tee -a "$out/summary.txt"; grep -E "^\[(OK|FAIL)\]|^==|rror|timeout" "$out/attn_impl$impl.log" | tail -12;
-                KX_ATTN_IMPL=$impl timeout 300 python tools/kernel_check.py bench_attn > "$out/bench_attn_impl$impl.log" 2>&1; echo "bench_attn impl=$impl exit $?" | tee -a "$out/summary.txt"; grep -E "attn " "$out/bench_attn_impl$impl.log"; done;;
   esac
 done

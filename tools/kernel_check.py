@@ -831,7 +831,7 @@ def bench_attn(B, H, T, causal):
     ms = e0.elapsed_time(e1) / 10
     fl = 2.0 * B * H * T * T * 64 * 2 / (2 if causal else 1)
     print(f"attn causal={causal} B={B} H={H} T={T}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s "
-          f"({'causal-halved' if causal else 'full'}) impl={os.environ.get('KX_ATTN_IMPL', '1')}")
+          f"({'causal-halved' if causal else 'full'})")
     return True
 
 
