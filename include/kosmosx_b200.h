@@ -197,6 +197,19 @@ int kx_im2col_patches_u8(const unsigned char* pixels, int channels_last, const f
                          int media, int image, int patch, void* patches_bf16, int k_pad, const float* class_embedding,
                          const float* pos_table, float* x, int dim, kx_stream_t stream);
 
+/* CLIPImageProcessor's resize (shortest edge -> model size, PIL bicubic) + centre crop on the device for uint8 images of
+ * any size (kosmosx/model.py:36-38,81-97 -> transformers 4.35 image_transforms.resize = PIL.Image.resize(BICUBIC), then
+ * center_crop).  PIL's 8-bit resampling is fixed-point: horizontal pass, uint8 intermediate, vertical pass, each a 1-D
+ * convolution acc = 2^21 + sum_x px[min + x] * k[x], out = clip8(acc >> 22).  kx / ky: DEVICE int32 coefficient rows
+ * [out_w][ksize_x] / [out_h][ksize_y] (doubles normalised to 1, * 2^22, rounded half away from zero — built on the host,
+ * kosmosx/preprocess.py) and bx / by: DEVICE int32 (first input index, tap count) pairs; only the output columns / rows
+ * INSIDE the crop window are passed, so the crop costs nothing.  The horizontal pass computes input rows [y0, y0+rows)
+ * (what the vertical taps read) into tmp (n * rows * out_w * 3 bytes); out: uint8 (n, out_h, out_w, 3) channels-last,
+ * the layout kx_im2col_patches_u8 / kx_clip_normalize_u8 take with channels_last = 1.  Bit-identical to PIL. */
+int kx_resize_crop_u8(const unsigned char* pixels, int channels_last, int n, int in_h, int in_w, const int* kx, const int* bx,
+                      int ksize_x, const int* ky, const int* by, int ksize_y, int y0, int rows, int out_h, int out_w,
+                      unsigned char* tmp, unsigned char* out, kx_stream_t stream);
+
 /* Row statistics + bf16 copy of an fp32 matrix: xb = bf16(x), stats[m] = (sum, sumsq) of xb's row m
  * ([1][rows][2] fp32).  Seeds the folded-LayerNorm chain (kx_gemm_args.ln_part) for the first decoder layer,
  * whose input comes from kx_embed_splice_pos / the image_proj epilogue rather than from a GEMM with stats_out. */

@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
        --expt-relaxed-constexpr -Wno-deprecated-gpu-targets -Xptxas -v)
 objs=()
 pids=()
-for src in runtime gemm accurate attention attention_pp attention_bwd elementwise train perceiver_attn decode decode_step; do
+for src in runtime gemm accurate preprocess attention attention_pp attention_bwd elementwise train perceiver_attn decode decode_step; do
   obj="$here/build/$src.o"
   objs+=("$obj")
   if [[ ! -f "$obj" || "$here/csrc/$src.cu" -nt "$obj" || "$here/csrc/ptx.cuh" -nt "$obj" || "$here/csrc/kx_internal.h" -nt "$obj" || "$here/../include/kosmosx_b200.h" -nt "$obj" ]]; then

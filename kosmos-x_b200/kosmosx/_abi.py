@@ -102,6 +102,7 @@ SIGNATURES = {
     "kx_im2col_patches": (_i, [_f32p, _i, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
     "kx_clip_normalize_u8": (_i, [_vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _f32p, _vp]),
     "kx_im2col_patches_u8": (_i, [_vp, _i, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i, _vp, _i, _f32p, _f32p, _f32p, _i, _vp]),
+    "kx_resize_crop_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "kx_xpos_tables": (_i, [_f32p, _f32p, _i, _i, _f, _f32p, _f32p, _f32p, _f32p, _vp]),
     "kx_cast_f32_to_bf16": (_i, [_f32p, _vp, _ll, _vp]),
     "kx_cast_bf16_to_f32": (_i, [_vp, _f32p, _ll, _vp]),

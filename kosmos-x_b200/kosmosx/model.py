@@ -986,6 +986,12 @@ class Kosmos(_KosmosBase):
             if images.dtype != torch.uint8:
                 raise TypeError("normalize_images=True takes raw uint8 pixels (CLIP rescale + normalise run on the device)")
             shapes = (planar, (cfg.image, cfg.image, 3))
+            if images.ndim in (4, 5) and tuple(images.shape[-3:]) not in shapes and (images.shape[-1] == 3 or images.shape[-3] == 3):
+                # raw pictures of another size: CLIPImageProcessor's resize + centre crop first (kx_resize_crop_u8)
+                from .preprocess import resize_center_crop_u8
+                lead = images.shape[:-3]
+                images = resize_center_crop_u8(images.reshape(-1, *images.shape[-3:]), cfg.image, cfg.image)
+                images = images.view(*lead, cfg.image, cfg.image, 3)
         else:
             shapes = (planar,)
         if images.ndim not in (4, 5) or tuple(images.shape[-3:]) not in shapes:
@@ -1211,10 +1217,11 @@ class KosmosTokenizer:
     ``tokenizer.convert_tokens_to_ids``, ``tokenizer.pad_token_id``, ``processor(images=..., return_tensors="pt")
     .pixel_values``).  Attributes as in the reference: ``processor``, ``tokenizer``, ``im_idx``, ``im_end_idx``.
 
-    B200 addition: ``tokenize_images`` given a uint8 CUDA tensor of model-sized images ((N,3,H,W) or (N,H,W,3)) runs the
-    processor's rescale + normalise on the device (``kx_clip_normalize_u8``) and returns the same fp32 ``pixel_values``;
-    ``Kosmos.forward(..., normalize_images=True)`` fuses that step into the patch pack instead.  Anything else
-    (PIL images, other sizes: resize / centre crop) goes through the injected processor on the host, as in the reference.
+    B200 addition: ``tokenize_images`` given a uint8 CUDA tensor ((N,3,H,W) or (N,H,W,3), any size) runs the processor's
+    whole pipeline on the device: shortest-edge bicubic resize + centre crop (``kx_resize_crop_u8``, PIL's fixed-point
+    resampling bit for bit) when the size differs from the model's, then rescale + normalise (``kx_clip_normalize_u8``),
+    and returns the same fp32 ``pixel_values``; ``Kosmos.forward(..., normalize_images=True)`` fuses the last step into
+    the patch pack instead.  Anything else (PIL images, lists) goes through the injected processor on the host.
     """
 
     CLIP_REPO = "laion/CLIP-ViT-L-14-laion2B-s32B-b82K"      # model.py:37
@@ -1262,6 +1269,10 @@ class KosmosTokenizer:
         try:
             if isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8:
                 mean, std = self._image_norm()
+                hw = tuple(images.shape[1:3]) if images.shape[-1] == 3 and images.shape[1] != 3 else tuple(images.shape[2:4])
+                if hw != (self.image_size, self.image_size):      # any other size: the processor's resize + centre crop, on the device
+                    from .preprocess import resize_center_crop_u8
+                    images = resize_center_crop_u8(images, self.image_size, self.image_size)
                 return ops.clip_normalize_u8(images.contiguous(), image=self.image_size, mean=mean, std=std)
             return self.processor(images=images, return_tensors="pt").pixel_values
         except Exception as e:

@@ -781,6 +781,65 @@ def clip_preprocess_u8(pixels, channels_last: bool = False, mean=OPENAI_CLIP_MEA
     return torch.from_numpy(np.ascontiguousarray((x - m) / s))
 
 
+def _pil_bicubic_axis(img, out_size: int, axis: int):
+    """One pass of PIL's ImagingResample (8 bits per channel, BICUBIC) along `axis` of a uint8 (H, W, C) array: taps from
+    ``precompute_coeffs`` (support 2 x max(scale, 1), weights normalised to 1 in float64), fixed-point
+    ``normalize_coeffs_8bpc`` (2^22, half away from zero), accumulator seeded with 2^21, ``clip8(acc >> 22)``."""
+    import numpy as np
+    bits = 32 - 8 - 2
+    in_size = img.shape[axis]
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.empty((out_size,) + src.shape[1:], dtype=np.uint8)
+
+    def bicubic(x, a=-0.5):
+        x = abs(x)
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [bicubic((x + xmin - center + 0.5) / filterscale) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        if ww != 0.0:
+            w = [v / ww for v in w]
+        k = np.array([int(-0.5 + v * (1 << bits)) if v < 0 else int(0.5 + v * (1 << bits)) for v in w], dtype=np.int64)
+        acc = np.tensordot(k, src[xmin:xmin + xmax], axes=(0, 0)) + (1 << (bits - 1))
+        out[xx] = np.clip(acc >> bits, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+def clip_resize_center_crop_u8(image, size: int = 224, crop: int | None = None):
+    """``CLIPImageProcessor`` resize + centre crop of transformers 4.35 (the processor the reference builds at
+    model.py:36-38 and calls at model.py:81-97) for ONE uint8 (H, W, 3) image: ``get_resize_output_image_size`` with
+    ``shortest_edge`` (long side = int(size * long / short)), ``PIL.Image.resize(BICUBIC)`` (horizontal pass, uint8,
+    vertical pass), ``center_crop`` (top = (h - crop) // 2).  Returns uint8 (crop, crop, 3).  tests/test_preprocess.py
+    pins it bit for bit against transformers' own ``resize`` / ``center_crop`` (which call PIL)."""
+    import numpy as np
+    crop = size if crop is None else crop
+    a = image.cpu().numpy() if isinstance(image, torch.Tensor) else np.asarray(image)
+    assert a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3
+    h, w = a.shape[:2]
+    short, long = (w, h) if w <= h else (h, w)
+    new_short, new_long = size, int(size * long / short)
+    new_h, new_w = (new_long, new_short) if w <= h else (new_short, new_long)
+    if w != new_w:
+        a = _pil_bicubic_axis(a, new_w, 1)
+    if h != new_h:
+        a = _pil_bicubic_axis(a, new_h, 0)
+    top, left = (new_h - crop) // 2, (new_w - crop) // 2
+    return torch.from_numpy(np.ascontiguousarray(a[top:top + crop, left:left + crop]))
+
+
 def tokenize_texts(input_ids: torch.Tensor, im_idx: int, im_end_idx: int):
     """``KosmosTokenizer.tokenize_texts`` after the HF tokenizer call (reference model.py:68-76):
     ``<s> <image> </image> text </s>`` -> (tokens with the two image tokens after position 0, the text tokens)."""

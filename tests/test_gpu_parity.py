@@ -816,3 +816,83 @@ def test_full_size_training_gradients_vs_oracle(full_pair):
     print(f"full-size training: {len(trainer.params)} gradient tensors, worst relative error {worst[0]:.3e} ({worst[1]})")
     for p in ref.parameters():
         p.grad = None
+
+
+# --------------------------------------------------------------------------- round 2: f4 resize + crop on device, f3 checkpoint on GPU
+@pytest.mark.parametrize("hw,channels_last", [((300, 400), True), ((500, 333), False), ((100, 130), True), ((37, 53), False),
+                                              ((224, 224), True), ((640, 257), True)])
+def test_device_resize_center_crop_is_bit_exact_vs_oracle(hw, channels_last):
+    """kx_resize_crop_u8 (PIL's fixed-point bicubic, crop fused) against the oracle's restatement of CLIPImageProcessor's
+    resize + centre crop, itself pinned bit for bit against transformers / PIL in tests/test_preprocess.py."""
+    import numpy as np
+    import kosmos_oracle as ko
+    from kosmosx.preprocess import resize_center_crop_u8
+    h, w = hw
+    imgs = torch.from_numpy(np.random.default_rng(h + w).integers(0, 256, (3, h, w, 3), dtype=np.uint8))
+    want = torch.stack([ko.clip_resize_center_crop_u8(im, 224, 224) for im in imgs])
+    src = imgs if channels_last else imgs.permute(0, 3, 1, 2).contiguous()
+    got = resize_center_crop_u8(src.cuda(), 224, 224)
+    assert got.shape == (3, 224, 224, 3) and got.dtype == torch.uint8
+    assert torch.equal(got.cpu(), want)
+
+
+def test_forward_on_raw_pictures_of_another_size(tiny512_pair):
+    """Kosmos.forward(normalize_images=True) and KosmosTokenizer.tokenize_images on uint8 pictures that are NOT the model's
+    size: resize (shortest edge) + centre crop + rescale + normalise all on the device == the oracle's host pipeline."""
+    import numpy as np
+    import kosmos_oracle as ko
+    from kosmosx import KosmosTokenizer
+    ref, mine, oc = tiny512_pair
+
+    class _Tok:
+        pad_token_id = 1
+
+        def convert_tokens_to_ids(self, t):
+            return [oc.vocab - 2, oc.vocab - 1]
+
+    tk = KosmosTokenizer(tokenizer=_Tok(), processor=object(), image_size=oc.image)
+    raw = torch.from_numpy(np.random.default_rng(3).integers(0, 256, (2, 90, 141, 3), dtype=np.uint8))
+    cropped = torch.stack([ko.clip_resize_center_crop_u8(im, oc.image, oc.image) for im in raw])
+    pv_want = ko.clip_preprocess_u8(cropped, channels_last=True)
+    pv = tk.tokenize_images(raw.cuda())
+    assert torch.equal(pv.cpu(), pv_want)
+    text, _ = ko.make_inputs(oc, 2, 20, seed=4)
+    a = mine(text.cuda(), raw.cuda(), normalize_images=True).clone()
+    b = mine(text.cuda(), pv).clone()
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        ref.set_emulation(True)
+        want = ref(text, pv_want)
+        ref.set_emulation(False)
+    assert _err(a, want)[0] <= TOL_EMU_TINY
+
+
+def test_load_checkpoint_file_then_forward_matches_oracle(tiny_cfgs, tmp_path):
+    """§8(f)3 on the GPU: a file in the reference's `final_model.pt` layout (train.py:688-695: the unwrapped state_dict,
+    here with the `module.` prefixes a DDP-wrapped save carries and one name of each tied pair dropped) ->
+    load_checkpoint -> forward == the oracle holding those weights; and save_checkpoint round-trips."""
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos
+    oc, kc = tiny_cfgs
+    ref = ko.build(oc, seed=123)
+    sd = {"module." + k: v.clone() for k, v in ref.state_dict().items()
+          if k not in ("decoder.embed_tokens.weight", "embed_positions.weight", "decoder.output_projection.weight")}
+    path = tmp_path / "final_model.pt"
+    torch.save(sd, path)
+    mine = Kosmos(config=kc).cuda()
+    res = mine.load_checkpoint(str(path))
+    assert not res.missing_keys and not res.unexpected_keys
+    text, images = ko.make_inputs(oc, 2, 30, seed=8)
+    with torch.no_grad():
+        want32 = ref(text, images)
+        ref.set_emulation(True)
+        want16 = ref(text, images)
+    got = mine(text.cuda(), images.cuda())
+    assert _err(got, want16)[0] <= TOL_EMU_TINY and _err(got, want32)[0] <= TOL_F32_TINY
+    assert _err(mine(text.cuda(), images.cuda(), precision="bf16x3"), want32)[0] <= TOL_STATED
+    out = tmp_path / "resaved.pt"
+    mine.save_checkpoint(str(out))
+    again = torch.load(out, map_location="cpu", weights_only=True)
+    assert set(again) == set(ref.state_dict())
+    for k, v in ref.state_dict().items():
+        assert torch.equal(again[k].float().cpu(), v.float()), k

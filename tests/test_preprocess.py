@@ -160,3 +160,55 @@ def test_tokenizer_with_a_real_hf_fast_tokenizer_built_offline():
     out = tk.tokenize({"target_text": ["a photo of a cat", "two dogs"], "image": list(imgs.numpy())})
     assert out["attention_mask"].shape == (2, 64 + 9) and out["attention_mask"][1, -3:].tolist() == [0, 0, 0]
     assert out["images"].shape == (2, 3, 224, 224)
+
+
+# --------------------------------------------------------------------------- resize + centre crop (round 2)
+_SIZES = [(300, 400), (224, 224), (500, 333), (100, 130), (640, 480), (37, 53), (224, 300), (1000, 257)]
+
+
+@pytest.mark.parametrize("hw", _SIZES)
+def test_oracle_resize_crop_is_hf_resize_then_center_crop_bit_for_bit(hw):
+    """``clip_resize_center_crop_u8`` against the functions the reference's pinned (4.35, PIL-based) CLIPImageProcessor calls:
+    get_resize_output_image_size(shortest_edge=224), image_transforms.resize(BICUBIC) -> PIL.Image.resize, center_crop.
+    Up- and down-scaling, square, extreme aspect ratios: identical uint8 pixels."""
+    import kosmos_oracle as ko
+    from transformers import image_transforms as it
+    from transformers.image_utils import ChannelDimension, PILImageResampling
+    h, w = hw
+    img = np.random.default_rng(h * 1000 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    size = it.get_resize_output_image_size(img, size=224, default_to_square=False, input_data_format=ChannelDimension.LAST)
+    r = it.resize(img, size=size, resample=PILImageResampling.BICUBIC, input_data_format=ChannelDimension.LAST)
+    want = it.center_crop(r, (224, 224), input_data_format=ChannelDimension.LAST)
+    got = ko.clip_resize_center_crop_u8(img, 224, 224)
+    assert want.dtype == np.uint8 and got.shape == (224, 224, 3)
+    assert np.array_equal(got.numpy(), want)
+
+
+@pytest.mark.parametrize("hw", _SIZES)
+def test_product_resize_tables_reproduce_the_oracle(hw):
+    """kosmosx/preprocess.py builds the fixed-point taps the device kernel consumes; applying them in plain integer numpy
+    (what kx_resize_crop_u8 does on the GPU) must give the oracle's pixels — geometry, taps and crop offsets agree."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kosmos-x_b200"))
+    import kosmos_oracle as ko
+    from kosmosx import preprocess as pp
+    h, w = hw
+    img = np.random.default_rng(7 + h + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    new_h, new_w = pp.resize_output_size(h, w, 224)
+    top, left = (new_h - 224) // 2, (new_w - 224) // 2
+    kx, bx = pp.bicubic_taps(w, new_w)
+    ky, by = pp.bicubic_taps(h, new_h)
+    kx, bx, ky, by = kx[left:left + 224], bx[left:left + 224], ky[top:top + 224], by[top:top + 224]
+    src = img.astype(np.int64)
+    tmp = np.empty((h, 224, 3), dtype=np.uint8)
+    for xx in range(224):
+        lo, n = bx[xx]
+        acc = np.tensordot(src[:, lo:lo + n], kx[xx, :n].astype(np.int64), axes=(1, 0)) + (1 << 21)
+        tmp[:, xx] = np.clip(acc >> 22, 0, 255)
+    out = np.empty((224, 224, 3), dtype=np.uint8)
+    t64 = tmp.astype(np.int64)
+    for yy in range(224):
+        lo, n = by[yy]
+        acc = np.tensordot(ky[yy, :n].astype(np.int64), t64[lo:lo + n], axes=(0, 0)) + (1 << 21)
+        out[yy] = np.clip(acc >> 22, 0, 255)
+    assert np.array_equal(out, ko.clip_resize_center_crop_u8(img, 224, 224).numpy())
