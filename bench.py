@@ -441,7 +441,8 @@ def run_gpu(args):
         model._ws.clear(); model._graphs = {}; model.decoder._ws.clear()
         torch.cuda.empty_cache()
         try:
-            line["train_step"] = train_measure(torch, kdist, dev, model, wl, max(2, min(args.steps, 5)), 3, world, rank, peaks)
+            line["train_step"] = train_measure(torch, kdist, dev, model, wl, max(2, min(args.steps, 5)), 3, world, rank, peaks,
+                                               dropout=args.dropout, reduce_bf16=bool(args.reduce_bf16))
         except Exception as e:                                  # the forward line must still be printed
             line["train_step"] = {"error": f"{type(e).__name__}: {e}"}
         x = None
@@ -490,15 +491,20 @@ def decode_measure(torch, model, batch=8, prompt=512, new=96):
     }
 
 
-def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peaks, optimizer="adamw", detail=True):
+def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peaks, optimizer="adamw", detail=True, dropout=0.1,
+                  reduce_bf16=True):
     """BASELINE.json configs[3]: the data-parallel training step (forward that keeps activations -> CE over text rows ->
     backward -> bucketed NCCL all-reduce overlapped with backward -> clip -> fused AdamW), B sequences per GPU.
     Returns a dict: tokens/s with inputs resident, e2e with H2D of the batch and D2H of the loss every step, and
     (detail) the per-kernel-class breakdown of one instrumented step."""
     from kosmosx import KosmosTrainer, ops
+    from kosmosx.train import cosine_with_warmup
     B, n_img, t_text = wl["batch"], wl["images"], wl["t_text"]
     fkw = dict(image_positions=wl["positions"]) if n_img > 1 else {}
-    trainer = KosmosTrainer(model, optimizer=optimizer, lr=1e-5, weight_decay=0.1, max_grad_norm=1.0)
+    # the reference's training mode: dropout = attention_dropout = 0.1 (model.py:175-177), cosine schedule with warm-up
+    trainer = KosmosTrainer(model, optimizer=optimizer, lr=1e-5, weight_decay=0.1, max_grad_norm=1.0, dropout=dropout,
+                            attention_dropout=dropout, grad_reduce_dtype=torch.bfloat16 if reduce_bf16 else torch.float32,
+                            lr_schedule=cosine_with_warmup(2, 10000))
     g = torch.Generator().manual_seed(11 + rank)
     h_text = torch.randint(0, VOCAB, (B, t_text), dtype=torch.long, generator=g).pin_memory()
     h_img = torch.randn(*((B, 3, 224, 224) if n_img == 1 else (B, n_img, 3, 224, 224)), generator=g).pin_memory()
@@ -536,8 +542,9 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
     step_flops = (3.0 * dec_flops + (162.02e9 + 4.115e9) * n_img) * B           # frozen vision side: forward only
     tfl = step_flops / (ms * 1e-3) / 1e12
     out = {"config": "configs[3]: data-parallel training step, B=%d per GPU, seq=2048, %d image(s)/seq, bf16 operands / fp32 "
-                     "master weights, %s, grad clip 1.0, decoder + LM head + embedding tables + perceiver resampler + image_proj "
-                     "trained (CLIP tower frozen), no dropout, no activation recompute" % (B, n_img, optimizer),
+                     "master weights, %s, grad clip 1.0, cosine LR schedule, decoder + LM head + embedding tables + perceiver resampler + "
+                     "image_proj trained (CLIP tower frozen), dropout = attention_dropout = %.2f, %s gradient all-reduce, no activation "
+                     "recompute" % (B, n_img, optimizer, dropout, "bf16" if reduce_bf16 else "fp32"),
            "value": tokens / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "global_batch": B * world,
            "step_tflops_per_gpu": tfl, "step_frac_of_bf16_peak": {"burst": tfl / peaks["burst"], "sustained": tfl / peaks["sustained"]},
            "flops_per_step_per_gpu": step_flops,
@@ -581,7 +588,8 @@ def run_train(args):
     model = Kosmos(config=KosmosConfig(max_positions=SEQ + 2), device=dev)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.start()
-    r = train_measure(torch, kdist, dev, model, wl, args.steps, args.warmup, world, rank, peaks, optimizer=args.optimizer)
+    r = train_measure(torch, kdist, dev, model, wl, args.steps, args.warmup, world, rank, peaks, optimizer=args.optimizer,
+                      dropout=args.dropout, reduce_bf16=bool(args.reduce_bf16))
     clocks = sampler.stop() if sampler else None
     bd = r.get("breakdown", {})
     top = max(((k, v) for k, v in bd.items() if k.startswith("gemm")), key=lambda kv: kv[1]["ms"], default=(None, None))
@@ -639,6 +647,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["train"], help="c3 = configs[2] (the metric's "
                     "configuration, default); c5 = configs[4], 4 images per sequence; train = configs[3], the training step")
     ap.add_argument("--optimizer", default="adamw", choices=["adamw", "lion"])
+    ap.add_argument("--dropout", type=float, default=0.1, help="dropout = attention_dropout of the training step (reference: 0.1)")
+    ap.add_argument("--reduce-bf16", type=int, default=1, help="exchange gradients in bf16 (default) or fp32 (0)")
     ap.add_argument("--decode-leg", type=int, default=1, help="also time incremental decoding (SURVEY 8(f)2) and report it as "
                     "'decode' inside the forward line (default on, single GPU)")
     ap.add_argument("--train-leg", type=int, default=1, help="also time a few training steps (configs[3]) and report them "

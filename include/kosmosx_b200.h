@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 16   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 17   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -98,6 +98,14 @@ typedef struct kx_gemm_args {
      *   wgrad  dW[N,Kd] = dY[M,N]^T . X[M,Kd]    -> A = dY with a_trans = 1, W = X with b_trans = 1
      * (replaces autograd's mm_backward of every F.linear on the path).  Generic epilogue only. */
     int a_trans, b_trans;
+    /* training only: dropout with probability drop_p on the Linear's output, after bias / activation and BEFORE the residual
+     * add — torchscale's `x = dropout(self_attn(...))` / `x = dropout(fc2(...))` (reference trains with dropout = 0.1,
+     * kosmosx/model.py:175).  The mask is a pure function of (drop_seed, drop_site, row, column): Philox4x32-7, one call
+     * per 8 consecutive columns, keep iff the 16-bit lot < round((1 - p) * 65536), kept values scaled by 65536 / that.
+     * kx_layernorm_bwd regenerates it for the gradient (nothing is stored).  0 = off.  Plain epilogue only. */
+    float drop_p;
+    unsigned int drop_site;
+    unsigned long long drop_seed;
 } kx_gemm_args;
 
 int kx_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, const kx_gemm_args* args,
@@ -275,6 +283,24 @@ int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, c
                 float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin, const float* xk_cos,
                 const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale, kx_stream_t stream);
 
+/* The same pair with attention dropout (torchscale MultiheadAttention: `attn_probs = dropout(attn_weights)`, the reference
+ * trains with attention_dropout = 0.1, kosmosx/model.py:177): the forward keeps probability (q, k) of (batch, head) iff
+ * its 16-bit Philox4x32-7 lot < round((1 - p) * 65536) (one call per 8 consecutive keys of a query row; a pure function
+ * of (drop_seed, drop_site, batch*heads + head, q, k)), sums the row normaliser over ALL probabilities, scales the output
+ * by 1 / (1 - p), and records the keep bits for the backward pass, transposed for its key-major threads:
+ *   drop_mask[((((batch*heads + head) * nb + qb) * nb + kb) * 4 + g) * 128 + r], nb = ceil(seq_len / 128): bit i = query
+ *   128*qb + 32*g + i keeps key 128*kb + r  — kx_attn_dropout_mask_words(batch, heads, seq_len) uint32 words.
+ * The backward reads one word per thread and tile: dV += (M o P / keep)^T dO, dS = P o (M o dP / keep - delta). */
+size_t kx_attn_dropout_mask_words(int batch, int heads, int seq_len);
+int kx_attn_fwd_dropout(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
+                        int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, float drop_p,
+                        unsigned int drop_site, unsigned long long drop_seed, unsigned int* drop_mask, kx_stream_t stream);
+int kx_attn_bwd_dropout(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
+                        const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv, long long ld_dqkv,
+                        float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin, const float* xk_cos,
+                        const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale, float drop_p,
+                        const unsigned int* drop_mask, kx_stream_t stream);
+
 /* Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 int64 installed, CTA 0 of every launch records
  * clock64 stamps [role: compute thread 0, MMA thread][iteration][point]; NULL = off. */
 int kx_attn_bwd_set_trace(long long* device_buffer);
@@ -296,7 +322,17 @@ int kx_ln_bwd_partials(int rows);
 int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, int act, const void* dy_bf16, long long ld_dy,
                      const float* gamma, float eps, const float* dres, long long ld_dres, void* dx, int dx_is_f32,
                      long long ld_dx, void* dxb_bf16, long long ld_dxb, float* partials, int n_partials, float* d_gamma,
-                     float* d_beta, float* d_colsum, int accumulate, int rows, int n, kx_stream_t stream);
+                     float* d_beta, float* d_colsum, int accumulate, int rows, int n, float drop_p, unsigned int drop_site,
+                     unsigned long long drop_seed, kx_stream_t stream);
+/* (drop_p > 0, fp32 residual form only: the Linear output added to the stream at this point went through dropout in the
+ * forward — kx_gemm_args.drop_* with the same (seed, site) — so dxb and d_colsum receive the masked, rescaled gradient while
+ * dx, the residual-stream gradient, stays whole.) */
+
+/* In-place dropout of an fp32 [rows, ld] matrix with the same mask function as kx_gemm_args.drop_*: torchscale's
+ * `x = dropout(x)` closing Decoder.forward_embedding (the call at kosmosx/model.py:242-244), and — applied to the gradient
+ * with the same (seed, site) — its backward.  cols % 8 == 0. */
+int kx_dropout_f32(float* x, long long ld, int rows, int cols, float drop_p, unsigned int drop_site,
+                   unsigned long long drop_seed, kx_stream_t stream);
 
 /* out[n] += column sums of a bf16 matrix (bias gradients: d(bias) = sum over rows of dY). */
 int kx_colsum_bf16(const void* x_bf16, long long ld, int rows, int n, float* out, kx_stream_t stream);

@@ -60,6 +60,8 @@ struct AttnBwdParams {
     int seq_len, heads, batch, t_pad;
     float scale, scale_log2;
     long long* trace;          // TRACE builds only: clock64 stamps of CTA 0, [role: 0 compute thread 0, 1 MMA thread][iteration][16 points]
+    const uint32_t* drop_mask; // DROP builds only: keep bits written by the forward (kx_attn_fwd_dropout), word per (tile, quarter, key)
+    float inv_keep;            // 1 / (1 - p)
 };
 
 static long long* g_attn_bwd_trace = nullptr;         // kx_attn_bwd_set_trace
@@ -78,7 +80,7 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                  : "memory");
 }
 
-template <bool CAUSAL, bool TRACE = false>
+template <bool CAUSAL, bool TRACE = false, bool DROP = false>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -279,6 +281,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int it = 0; it < n_it; ++it) {
             const int i = i0 + it, s = it % BW_SLOTS;
             if (threadIdx.x == 0) KX_BT(0, it, 0);
+            uint32_t mw = 0xffffffffu;                                      // keep bits of queries 32g .. 32g+31 for this key
+            if constexpr (DROP)
+                mw = __ldg(p.drop_mask + ((((static_cast<long long>(bh) * nblk + i) * nblk + j) * 4 + g) << 7) + r);
             mbar_wait_lean(&full[s], (it / BW_SLOTS) & 1);                  // (-lse, -delta) of this query block are in smem
             mbar_wait_lean(bar_s, it & 1);
             tc_fence_after();
@@ -315,10 +320,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             e0 = ex2_approx(x0);
                             e1 = ex2_approx(x1);
                         }
-                        const uint64_t t = fadd2(pack_f32x2(__uint_as_float(dpv[2 * c]), __uint_as_float(dpv[2 * c + 1])), pack_f32x2(l.z, l.w));
+                        float dp0 = __uint_as_float(dpv[2 * c]), dp1 = __uint_as_float(dpv[2 * c + 1]);
+                        uint32_t pmask = 0xffffffffu;
+                        if constexpr (DROP) {              // dS = P o (M o dP / keep - delta); the dV operand is M o P (1/keep on the way out)
+                            const uint32_t b2 = (mw >> (hf * 16 + 2 * c)) & 3u;
+                            dp0 = (b2 & 1u) ? dp0 * p.inv_keep : 0.f;
+                            dp1 = (b2 & 2u) ? dp1 * p.inv_keep : 0.f;
+                            pmask = ((b2 & 1u) ? 0x0000ffffu : 0u) | ((b2 & 2u) ? 0xffff0000u : 0u);
+                        }
+                        const uint64_t t = fadd2(pack_f32x2(dp0, dp1), pack_f32x2(l.z, l.w));
                         float d0, d1;
                         unpack_f32x2(fmul2(pack_f32x2(e0, e1), t), d0, d1);
-                        pp[hf * 8 + c] = pack_bf16(e0, e1);
+                        pp[hf * 8 + c] = pack_bf16(e0, e1) & pmask;
                         dd[hf * 8 + c] = pack_bf16(d0, d1);
                     }
                 } else {
@@ -330,10 +343,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         const bool ok1 = kg < T && q0 + 1 < T && (!CAUSAL || q0 + 1 >= kg);
                         const float p0 = ok0 ? ex2_approx(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, l.x)) : 0.f;
                         const float p1 = ok1 ? ex2_approx(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, l.y)) : 0.f;
+                        float dp0 = __uint_as_float(dpv[2 * c]), dp1 = __uint_as_float(dpv[2 * c + 1]);
+                        uint32_t pmask = 0xffffffffu;
+                        if constexpr (DROP) {
+                            const uint32_t b2 = (mw >> (hf * 16 + 2 * c)) & 3u;
+                            dp0 = (b2 & 1u) ? dp0 * p.inv_keep : 0.f;
+                            dp1 = (b2 & 2u) ? dp1 * p.inv_keep : 0.f;
+                            pmask = ((b2 & 1u) ? 0x0000ffffu : 0u) | ((b2 & 2u) ? 0xffff0000u : 0u);
+                        }
                         // rows beyond T may hold inf / nan in dP or delta: never form 0 * nan
-                        const float d0 = ok0 ? p0 * (__uint_as_float(dpv[2 * c]) + l.z) : 0.f;
-                        const float d1 = ok1 ? p1 * (__uint_as_float(dpv[2 * c + 1]) + l.w) : 0.f;
-                        pp[hf * 8 + c] = pack_bf16(p0, p1);
+                        const float d0 = ok0 ? p0 * (dp0 + l.z) : 0.f;
+                        const float d1 = ok1 ? p1 * (dp1 + l.w) : 0.f;
+                        pp[hf * 8 + c] = pack_bf16(p0, p1) & pmask;
                         dd[hf * 8 + c] = pack_bf16(d0, d1);
                     }
                 }
@@ -363,10 +384,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 uint4 a, c;
-                a.x = pack_bf16(__uint_as_float(vv[8 * u]), __uint_as_float(vv[8 * u + 1]));
-                a.y = pack_bf16(__uint_as_float(vv[8 * u + 2]), __uint_as_float(vv[8 * u + 3]));
-                a.z = pack_bf16(__uint_as_float(vv[8 * u + 4]), __uint_as_float(vv[8 * u + 5]));
-                a.w = pack_bf16(__uint_as_float(vv[8 * u + 6]), __uint_as_float(vv[8 * u + 7]));
+                const float vs = DROP ? p.inv_keep : 1.0f;          // dV accumulated (M o P)^T dO: the 1/keep factor goes on here
+                a.x = pack_bf16(__uint_as_float(vv[8 * u]) * vs, __uint_as_float(vv[8 * u + 1]) * vs);
+                a.y = pack_bf16(__uint_as_float(vv[8 * u + 2]) * vs, __uint_as_float(vv[8 * u + 3]) * vs);
+                a.z = pack_bf16(__uint_as_float(vv[8 * u + 4]) * vs, __uint_as_float(vv[8 * u + 5]) * vs);
+                a.w = pack_bf16(__uint_as_float(vv[8 * u + 6]) * vs, __uint_as_float(vv[8 * u + 7]) * vs);
                 c.x = pack_bf16(__uint_as_float(kk[8 * u]) * p.scale, __uint_as_float(kk[8 * u + 1]) * p.scale);
                 c.y = pack_bf16(__uint_as_float(kk[8 * u + 2]) * p.scale, __uint_as_float(kk[8 * u + 3]) * p.scale);
                 c.z = pack_bf16(__uint_as_float(kk[8 * u + 4]) * p.scale, __uint_as_float(kk[8 * u + 5]) * p.scale);
@@ -476,11 +498,11 @@ extern "C" int kx_attn_bwd_set_trace(long long* device_buffer) {
     return KX_OK;
 }
 
-extern "C" int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
-                           const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv,
-                           long long ld_dqkv, float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin,
-                           const float* xk_cos, const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale,
-                           cudaStream_t stream) {
+static int attn_bwd_impl(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
+                         const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv,
+                         long long ld_dqkv, float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin,
+                         const float* xk_cos, const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale,
+                         float drop_p, const unsigned int* drop_mask, cudaStream_t stream) {
     if (!q || !k || !v || !out || !d_out || !lse || !dq || !dk || !dv || !dq_accum || !delta) { set_error("kx_attn_bwd: null pointer"); return KX_ERR_ARG; }
     if (batch <= 0 || heads <= 0 || seq_len <= 0 || (ld_qkv % 8) || (ld_out % 8) || (ld_dout % 8) || (ld_dqkv % 8)) {
         set_error("kx_attn_bwd: bad shape / pitch (16-byte aligned rows required)");
@@ -526,12 +548,26 @@ extern "C" int kx_attn_bwd(const void* q, const void* k, const void* v, long lon
     p.seq_len = seq_len; p.heads = heads; p.batch = batch; p.t_pad = t_pad;
     p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
     p.trace = g_attn_bwd_trace;
+    p.drop_mask = drop_mask;
+    p.inv_keep = 1.0f;
+    if (drop_mask != nullptr) {
+        if (!causal || !(drop_p > 0.f && drop_p < 1.f) || (reinterpret_cast<uintptr_t>(drop_mask) & 15)) {
+            set_error("kx_attn_bwd_dropout: needs causal attention, 0 < p < 1 and the 16-byte aligned mask of kx_attn_fwd_dropout");
+            return KX_ERR_ARG;
+        }
+        const unsigned thr = static_cast<unsigned>((1.0 - static_cast<double>(drop_p)) * 65536.0 + 0.5);
+        p.inv_keep = 65536.0f / static_cast<float>(thr);
+    }
     const long long ctas = static_cast<long long>(nblk) * heads * batch;
     if (ctas > 0x7fffffffLL) { set_error("kx_attn_bwd: too many tiles"); return KX_ERR_ARG; }
     if (causal && p.trace != nullptr) {           // profiling aid (kx_attn_bwd_set_trace): same kernel with clock64 stamps
         static bool tattr = false;
         if (!tattr) { cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_BYTES); tattr = true; }
         attn_bwd_kernel<true, true><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, p);
+    } else if (causal && drop_mask != nullptr) {
+        static bool dattr = false;
+        if (!dattr) { cudaFuncSetAttribute(attn_bwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_BYTES); dattr = true; }
+        attn_bwd_kernel<true, false, true><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, p);
     } else if (causal) attn_bwd_kernel<true><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, p);
     else attn_bwd_kernel<false><<<static_cast<unsigned>(ctas), BW_THREADS, BW_SMEM_BYTES, stream>>>(tq, tk, tv, tdo, tdq, p);
     int st = check_launch("kx_attn_bwd");
@@ -545,4 +581,23 @@ extern "C" int kx_attn_bwd(const void* q, const void* k, const void* v, long lon
         st = check_launch("kx_attn_bwd (finish)");
     }
     return st;
+}
+
+extern "C" int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
+                           const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv,
+                           long long ld_dqkv, float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin,
+                           const float* xk_cos, const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale,
+                           cudaStream_t stream) {
+    return attn_bwd_impl(q, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq, dk, dv, ld_dqkv, dq_accum, delta, xq_cos, xq_sin,
+                         xk_cos, xk_sin, batch, heads, seq_len, causal, scale, 0.f, nullptr, stream);
+}
+
+extern "C" int kx_attn_bwd_dropout(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
+                                   const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv,
+                                   long long ld_dqkv, float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin,
+                                   const float* xk_cos, const float* xk_sin, int batch, int heads, int seq_len, int causal,
+                                   float scale, float drop_p, const unsigned int* drop_mask, cudaStream_t stream) {
+    if (!drop_mask) { set_error("kx_attn_bwd_dropout: null mask"); return KX_ERR_ARG; }
+    return attn_bwd_impl(q, k, v, ld_qkv, out, ld_out, d_out, ld_dout, lse, dq, dk, dv, ld_dqkv, dq_accum, delta, xq_cos, xq_sin,
+                         xk_cos, xk_sin, batch, heads, seq_len, causal, scale, drop_p, drop_mask, stream);
 }

@@ -20,6 +20,7 @@
 // bf16 and the final O/l is unchanged mathematically.
 #include "kx_internal.h"
 #include "ptx.cuh"
+#include "philox.cuh"
 #include <cstdlib>
 
 namespace kx {
@@ -47,6 +48,8 @@ struct AttnPPParams {
     float* lse_out;                                  // [heads][batch][t_pad] row log-sum-exp in log2 units (training), or null
     int t_pad;
     long long* trace;                                // TRACE builds only: clock64 stamps of CTA (0,0), [4 roles][64 iters][8 points]
+    DropSpec drop;                                   // DROP builds only: attention dropout (training)
+    uint32_t* drop_mask;                             // keep bits, transposed for the backward pass (see kx_attn_fwd_dropout)
 };
 
 static long long* g_attn_trace = nullptr;            // kx_attn_set_trace
@@ -88,7 +91,7 @@ __device__ __forceinline__ PPItem pp_item(const AttnPPParams& p, int item) {
 
 // POLY: 26 of every 64 element pairs take exp2 through exp2_poly_x2 (FMA pipes) instead of MUFU.EX2 —
 // the split that balances the two pipes for this loop (FA4's trick).
-template <bool CAUSAL, bool POLY, bool TRACE = false>
+template <bool CAUSAL, bool POLY, bool TRACE = false, bool DROP = false>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnPPParams p) {
@@ -368,7 +371,36 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             float a0, a1;
             unpack_f32x2(fadd2(acc0, acc1), a0, a1);
-            l_run += a0 + a1;
+            l_run += a0 + a1;                              // the normaliser sums ALL probabilities (dropout acts after softmax)
+            if constexpr (DROP) {
+                // attention dropout: 16 Philox calls give this row's keep bits for the 128 keys of the block; dropped
+                // probabilities become exact zeros in the P operand of P.V (the 1/keep factor is applied once, to O)
+                uint32_t keepw[4] = {0u, 0u, 0u, 0u};
+                const uint32_t bh = static_cast<uint32_t>(it.b * p.heads + head);
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    keepw[c >> 2] |= drop_keep8_attn(p.drop, static_cast<uint32_t>(qrow), static_cast<uint32_t>((kv0 >> 3) + c), bh) << ((c & 3) * 8);
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    const uint32_t b2 = (keepw[i >> 4] >> ((i & 15) * 2)) & 3u;
+                    pv[i] &= ((b2 & 1u) ? 0x0000ffffu : 0u) | ((b2 & 2u) ? 0xffff0000u : 0u);
+                }
+                // the backward pass runs with thread = key: hand it the bits transposed, word (g, key) = this warp's 32
+                // query rows, built with one ballot per key and stored as four coalesced 128-byte rows per block
+                const int nb = (T + 127) >> 7;
+                const int qb = (q0 >> 7) + w, g = warp & 3;
+                uint32_t* dst = p.drop_mask + ((((static_cast<long long>(bh) * nb + qb) * nb + j) * 4 + g) << 7);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t word = 0u;
+#pragma unroll
+                    for (int b = 0; b < 32; ++b) {
+                        const uint32_t bal = __ballot_sync(0xffffffffu, (keepw[c] >> b) & 1u);
+                        if (lane == b) word = bal;
+                    }
+                    dst[c * 32 + lane] = word;
+                }
+            }
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 4);
             // P region: element pair (2c, 2c+1) in column c.  P.V of the previous block must have consumed it
             // (for j == 0 the previous item's epilogue already waited for its last P.V).
@@ -395,7 +427,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(&o_read[w]);                          // the next item's first P.V may overwrite O_w
         if (qrow < T) {
-            const float inv_l = 1.0f / l_run;
+            const float inv_l = DROP ? p.drop.inv_keep / l_run : 1.0f / l_run;
             __nv_bfloat16* o = p.out + static_cast<long long>(row_base + qrow) * p.ld_out + head * 64;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -431,7 +463,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
-                   int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, cudaStream_t stream) {
+                   int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, cudaStream_t stream,
+                   const DropSpec* drop, uint32_t* drop_mask) {
     const unsigned long long rows = (unsigned long long)batch * seq_len;
     CUtensorMap tq, tk, tv;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
@@ -450,10 +483,13 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.lse_out = lse_out;
     p.t_pad = (seq_len + 127) / 128 * 128;
     p.trace = g_attn_trace;
+    p.drop = drop != nullptr ? *drop : DropSpec{};
+    p.drop_mask = drop_mask;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
         cudaError_t e2 = cudaFuncSetAttribute(attn_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_pp_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             set_error("kx_attn_fwd: cudaFuncSetAttribute failed");
             return KX_ERR_LAUNCH;
@@ -473,6 +509,11 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
         }
         attn_pp_kernel<true, true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
         return check_launch("kx_attn_fwd");
+    }
+    if (p.drop.thr != 0u) {
+        if (!causal || drop_mask == nullptr) { set_error("kx_attn_fwd_dropout: causal attention and a mask buffer are required"); return KX_ERR_ARG; }
+        attn_pp_kernel<true, true, false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+        return check_launch("kx_attn_fwd_dropout");
     }
     if (causal) attn_pp_kernel<true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
     else attn_pp_kernel<false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);

@@ -14,6 +14,7 @@
 // The epilogue of tile i overlaps the MMAs of tile i+1 (double-buffered TMEM accumulator).
 #include "kx_internal.h"
 #include "ptx.cuh"
+#include "philox.cuh"
 
 #include <mutex>
 #include <unordered_map>
@@ -92,6 +93,9 @@ struct GemmEpi {
     float2* stats_out;         // [ceil(N/(BN/2))][M] or null
     void* out2;                // bf16 [M, ld_out2] or null
     long long ld_out2;
+    // training: dropout on the Linear's output (after bias / activation, BEFORE the residual add) — torchscale's
+    // `x = dropout(self_attn(...))`, `x = dropout(fc2(...))`; element (m, n) is kept iff drop_keep8(drop, m, n / 8) bit n % 8
+    DropSpec drop;             // thr == 0: off
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -225,6 +229,14 @@ __device__ __forceinline__ void epilogue_math(const GemmEpi& ep, float (&f)[32],
     } else if (ep.act == KX_ACT_QUICK_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = quick_gelu(f[i]);
+    }
+    if (ep.drop.thr != 0u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t keep = drop_keep8(ep.drop, static_cast<uint32_t>(m), static_cast<uint32_t>((n0 >> 3) + i));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[8 * i + u] = ((keep >> u) & 1u) ? f[8 * i + u] * ep.drop.inv_keep : 0.f;
+        }
     }
 }
 
@@ -852,6 +864,13 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
         ep.ln_tiles = g->ln_tiles;
         ep.ln_inv_n = 1.0f / static_cast<float>(g->ln_cols);
         ep.ln_eps = g->ln_eps;
+    }
+    if (g->drop_p > 0.f) {
+        if (!(g->drop_p < 1.f) || g->stats_out || g->ln_part || g->grp_rows) {
+            set_error("kx_gemm_bf16: dropout needs 0 < p < 1 and the plain (unfolded, unscattered) epilogue of the training forward");
+            return KX_ERR_ARG;
+        }
+        ep.drop = make_drop_spec(g->drop_p, g->drop_site, g->drop_seed);
     }
     ep.stats_out = reinterpret_cast<float2*>(g->stats_out);
     ep.out2 = g->out2;

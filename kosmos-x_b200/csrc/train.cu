@@ -11,6 +11,7 @@
 // Everything is fp32 math on 16-byte vector accesses; one pass over each operand.
 #include "kx_internal.h"
 #include "ptx.cuh"
+#include "philox.cuh"
 
 namespace kx {
 
@@ -207,7 +208,7 @@ layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
                      const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ gamma, float eps,
                      const float* dres, long long ld_dres, void* dx_out, long long ld_dx, __nv_bfloat16* __restrict__ dxb,
                      long long ld_dxb, float* __restrict__ part_gamma, float* __restrict__ part_beta,
-                     float* __restrict__ part_col, int rows, int n) {
+                     float* __restrict__ part_col, int rows, int n, const DropSpec drop) {
     extern __shared__ __align__(128) uint8_t lnb_smem[];
     __shared__ float red[4 * (THREADS / 32)];
     __shared__ __align__(8) uint64_t full[LNB_STAGES];
@@ -304,6 +305,14 @@ layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o[u] += r[u];
                 store8(reinterpret_cast<float*>(dx_out) + static_cast<long long>(row) * ld_dx + col, o);
+                if (drop.thr != 0u) {
+                    // the Linear output that was added to the stream here went through dropout in the forward (the GEMM
+                    // epilogue's mask, regenerated): its gradient — the bf16 copy the backward GEMMs read and the bias
+                    // column sums — is masked and rescaled; the stream gradient stored above is not
+                    const uint32_t keep = drop_keep8(drop, static_cast<uint32_t>(row), static_cast<uint32_t>(col >> 3));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) o[u] = ((keep >> u) & 1u) ? o[u] * drop.inv_keep : 0.f;
+                }
                 if (dxb != nullptr) store8(dxb + static_cast<long long>(row) * ld_dxb + col, o);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) acc_c[u] += o[u];
@@ -579,6 +588,25 @@ embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ to
     }
 }
 
+// ----------------------------------------------------------------------------- dropout on an fp32 matrix (decoder input)
+// x[r, c] = keep(r, c) ? x[r, c] / keep_prob : 0, in place: torchscale's `x = dropout(x)` at the end of forward_embedding
+// (the call at model.py:242-244 whose [0] is the decoder input) and, applied to the gradient, its backward.
+__global__ void __launch_bounds__(256)
+dropout_f32_kernel(float* __restrict__ x, long long ld, int rows, int cols, const DropSpec drop) {
+    const int vec = cols >> 3;
+    const long long total = static_cast<long long>(rows) * vec;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int r = static_cast<int>(i / vec), c8 = static_cast<int>(i - static_cast<long long>(r) * vec);
+        float v[8];
+        float* p = x + static_cast<long long>(r) * ld + c8 * 8;
+        load8(p, v);
+        const uint32_t keep = drop_keep8(drop, static_cast<uint32_t>(r), static_cast<uint32_t>(c8));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ((keep >> u) & 1u) ? v[u] * drop.inv_keep : 0.f;
+        store8(p, v);
+    }
+}
+
 // ----------------------------------------------------------------------------- gradient norm + optimizers
 // Deterministic: block b writes its partial to scratch[b]; sumsq_finish_kernel folds the partials in index order.  (An
 // atomicAdd per block would make the gradient norm — hence the clip coefficient, hence every parameter — depend on block
@@ -771,7 +799,12 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, co
                                 const float* gamma, float eps, const float* dres, long long ld_dres, void* dx,
                                 int dx_is_f32, long long ld_dx, void* dxb_bf16, long long ld_dxb, float* partials,
                                 int n_partials, float* d_gamma, float* d_beta, float* d_colsum, int accumulate, int rows,
-                                int n, cudaStream_t stream) {
+                                int n, float drop_p, unsigned int drop_site, unsigned long long drop_seed, cudaStream_t stream) {
+    if (drop_p != 0.f && (!(drop_p > 0.f && drop_p < 1.f) || !dx_is_f32)) {
+        set_error("kx_layernorm_bwd: dropout needs 0 < p < 1 and the fp32 residual form (dx_is_f32)");
+        return KX_ERR_ARG;
+    }
+    const DropSpec drop = make_drop_spec(drop_p, drop_site, drop_seed);
     if (!x || !dy_bf16 || !gamma || !dx || !partials || !d_gamma || !d_beta || rows <= 0 || n <= 0 || (n % 8) || n > 8192 ||
         (ld_x % 8) || (ld_dy % 8) || (ld_dx % 8) || !KX_ALIGNED16(x) || !KX_ALIGNED16(dy_bf16) || !KX_ALIGNED16(dx) ||
         !KX_ALIGNED16(gamma) || !KX_ALIGNED16(partials) || (dres && (!KX_ALIGNED16(dres) || (ld_dres % 4) || !dx_is_f32)) ||
@@ -807,7 +840,7 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, co
             attr = smem;                                                                                                  \
         }                                                                                                                 \
         kern<<<grid, TH, smem, stream>>>(reinterpret_cast<const XT*>(x), ld_x, pre_add, dyp, ld_dy, gamma, eps, dres,     \
-                                         ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n);                          \
+                                         ld_dres, dx, ld_dx, dxbp, ld_dxb, pg, pb, pc, rows, n, drop);                    \
     }
 #define KX_LNB_N(XT, F32, GE)                                                                                             \
     { if (!wide) KX_LNB(XT, F32, 256, GE) else KX_LNB(XT, F32, 1024, GE) }
@@ -896,6 +929,19 @@ extern "C" int kx_embed_bwd(const float* dx0, const long long* tokens, int batch
     embed_bwd_kernel<<<batch * T, 256, 0, stream>>>(dx0, tokens, t_text, n_img, img, dim, vocab, padding_idx, alias_positions ? 1 : 0,
                                                     d_embed, d_pos);
     return check_launch("kx_embed_bwd");
+}
+
+extern "C" int kx_dropout_f32(float* x, long long ld, int rows, int cols, float drop_p, unsigned int drop_site,
+                              unsigned long long drop_seed, cudaStream_t stream) {
+    if (!x || rows <= 0 || cols <= 0 || (cols % 8) || (ld % 4) || !KX_ALIGNED16(x) || !(drop_p > 0.f && drop_p < 1.f)) {
+        set_error("kx_dropout_f32: bad argument (cols %% 8 == 0, 16-byte aligned rows, 0 < p < 1)");
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    dropout_f32_kernel<<<grid_for(static_cast<long long>(rows) * (cols / 8), sms), 256, 0, stream>>>(x, ld, rows, cols,
+                                                                                                   make_drop_spec(drop_p, drop_site, drop_seed));
+    return check_launch("kx_dropout_f32");
 }
 
 extern "C" int kx_sumsq(const float* g, long long n, float* out, float* scratch, cudaStream_t stream) {

@@ -43,6 +43,7 @@ class GemmArgs(C.Structure):
         ("ln_part", _f32p), ("ln_c", _f32p), ("ln_tiles", _i), ("ln_cols", _i), ("ln_eps", _f),
         ("stats_out", _f32p), ("out2", _vp), ("ld_out2", _ll),
         ("a_trans", _i), ("b_trans", _i),
+        ("drop_p", _f), ("drop_site", C.c_uint), ("drop_seed", C.c_ulonglong),
     ]
 
 
@@ -120,7 +121,12 @@ SIGNATURES = {
     "kx_act_layernorm_fwd": (_i, [_vp, _ll, _i, _f32p, _f32p, _f, _vp, _ll, _i, _i, _vp]),
     "kx_ln_bwd_partials": (_i, [_i]),
     "kx_layernorm_bwd": (_i, [_vp, _i, _ll, _f32p, _i, _vp, _ll, _f32p, _f, _f32p, _ll, _vp, _i, _ll, _vp, _ll, _f32p, _i,
-                              _f32p, _f32p, _f32p, _i, _i, _i, _vp]),
+                              _f32p, _f32p, _f32p, _i, _i, _i, _f, C.c_uint, C.c_ulonglong, _vp]),
+    "kx_dropout_f32": (_i, [_f32p, _ll, _i, _i, _f, C.c_uint, C.c_ulonglong, _vp]),
+    "kx_attn_dropout_mask_words": (C.c_size_t, [_i, _i, _i]),
+    "kx_attn_fwd_dropout": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _f32p, _f, C.c_uint, C.c_ulonglong, _vp, _vp]),
+    "kx_attn_bwd_dropout": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _f32p, _vp, _vp, _vp, _ll, _f32p, _f32p,
+                                 _f32p, _f32p, _f32p, _f32p, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "kx_perceiver_xattn_bwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "kx_gelu_fwd": (_i, [_vp, _vp, _ll, _vp]),
     "kx_gelu_bwd": (_i, [_vp, _vp, _vp, _ll, _vp]),

@@ -61,6 +61,10 @@ class KosmosConfig:
     # call (model.py:242-244) adds the spliced positions on top: text rows get TWO positional embeddings.  True reproduces
     # that; False is the out-of-place reading (`x = x + positions`), one positional embedding per row.
     alias_embed_positions: bool = True
+    # torchscale DecoderConfig(dropout=0.1, attention_dropout=0.1), reference model.py:175-177: applied by the training
+    # step (KosmosTrainer / model.train() forward); Kosmos.forward in eval mode is the identity, as nn.Dropout is
+    dropout: float = 0.1
+    attention_dropout: float = 0.1
 
     @property
     def vit_tokens(self) -> int:

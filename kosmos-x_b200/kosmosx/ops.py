@@ -67,14 +67,15 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=None, act=_abi.KX_ACT_NONE,
          grp=None, add_tab=None, add_off=0, xpos=None, seq_len=0, cta_group=0, block_n=0, max_ctas=0, M=None,
-         epi_mode=0, ln=None, stats_out=None, out2=None, a_trans=False, b_trans=False):
+         epi_mode=0, ln=None, stats_out=None, out2=None, a_trans=False, b_trans=False, drop=None):
     """out = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16; out bf16 or fp32 (2-D views, row pitch = stride(0)).
     a_trans / b_trans: the operand is given as [K, M] / [K, N] (backward GEMMs: dgrad = gemm(dY, W, b_trans=True),
     wgrad = gemm(dY, X, a_trans=True, b_trans=True)).
 
     ln = (partials fp32 [tiles, M, 2], c fp32 [N], cols, eps): LayerNorm of the rows of `a` folded into the
     epilogue (w must carry gamma, bias must be W.beta + b).  stats_out fp32 [ceil(N/128), M, 2] and out2
-    (bf16 copy of an fp32 out) make this GEMM the producer of the next fold."""
+    (bf16 copy of an fp32 out) make this GEMM the producer of the next fold.
+    drop = (p, site, seed): training dropout on the Linear's output, before the residual add (kx_gemm_args.drop_*)."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
     g = GemmArgs()
@@ -128,6 +129,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     if out2 is not None:
         _req(out2, torch.bfloat16, "out2")
         g.out2, g.ld_out2 = out2.data_ptr(), out2.stride(0)
+    if drop is not None and drop[0] > 0:
+        g.drop_p, g.drop_site, g.drop_seed = float(drop[0]), int(drop[1]), int(drop[2])
     with _Timed(f"gemm {g.M}x{g.N}x{g.K}" + ("+tn" if a_trans else "+nn" if b_trans else "") + ("+ln" if ln is not None else "") + ("+xpos" if xpos is not None else "")
                 + ("+gelu" if act == _abi.KX_ACT_GELU else "") + ("+res" if res is not None else ""),
                 2.0 * g.M * g.N * g.K,
@@ -136,7 +139,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     return out
 
 
-def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=None, lse_out=None):
+def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=None, lse_out=None, drop=None, drop_mask=None):
     """q, k, v: bf16 2-D views [batch*seq_len, heads*64] sharing one row pitch; out bf16 [batch*seq_len, >=heads*64].
     stats_out fp32 [heads, batch*seq_len, 2]: per-head partial (sum, sumsq) of every output row."""
     if stats_out is not None:
@@ -153,6 +156,14 @@ def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=N
             _req(lse_out, torch.float32, "lse_out")
             if lse_out.numel() != heads * batch * lse_pad(seq_len) or not lse_out.is_contiguous():
                 raise ValueError("attention: lse_out must be contiguous [heads, batch, ceil(seq_len/128)*128]")
+        if drop is not None and drop[0] > 0:          # training: attention dropout, keep bits recorded for the backward pass
+            if lse_out is None or drop_mask is None or drop_mask.dtype != torch.int32 or drop_mask.numel() < attn_dropout_mask_words(batch, heads, seq_len):
+                raise ValueError("attention: dropout needs lse_out and an int32 drop_mask of attn_dropout_mask_words() entries")
+            check(lib.kx_attn_fwd_dropout(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                                          batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out), lse_out.data_ptr(),
+                                          float(drop[0]), int(drop[1]), int(drop[2]), drop_mask.data_ptr(), _stream()),
+                  "kx_attn_fwd_dropout")
+        elif lse_out is not None:
             check(lib.kx_attn_fwd_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
                                       batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out),
                                       lse_out.data_ptr(), _stream()), "kx_attn_fwd_lse")
@@ -167,8 +178,31 @@ def lse_pad(seq_len: int) -> int:
     return (seq_len + 127) // 128 * 128
 
 
+def attn_dropout_mask_words(batch: int, heads: int, seq_len: int) -> int:
+    return int(lib.kx_attn_dropout_mask_words(batch, heads, seq_len))
+
+
+def unpack_attn_dropout_mask(mask: torch.Tensor, batch: int, heads: int, seq_len: int) -> torch.Tensor:
+    """Keep bits recorded by the dropout forward -> bool (batch, heads, seq_len, seq_len) [q, k] (test / inspection helper;
+    the kernels read the packed words).  Entries of tiles the causal forward never visits are undefined."""
+    nb = (seq_len + 127) // 128
+    w = mask[:batch * heads * nb * nb * 512].view(batch, heads, nb, nb, 4, 128).to(torch.int64) & 0xffffffff      # [b,h,qb,kb,g,r]
+    bits = (w.unsqueeze(-1) >> torch.arange(32, device=mask.device)) & 1                                         # [..., g, r, i]
+    keep = bits.permute(0, 1, 2, 4, 6, 3, 5).reshape(batch, heads, nb * 128, nb * 128)                             # q = qb,g,i ; k = kb,r
+    return keep[:, :, :seq_len, :seq_len].bool()
+
+
+def dropout_f32(x, *, p, site, seed):
+    """In-place dropout of an fp32 2-D matrix with the library's mask function (kx_dropout_f32)."""
+    _req(x, torch.float32, "x")
+    check(lib.kx_dropout_f32(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(p), int(site), int(seed), _stream()),
+          "kx_dropout_f32")
+    return x
+
+
 # ---- training step ---------------------------------------------------------------------------
-def attention_bwd(q, k, v, out, d_out, lse, dq, dk, dv, dq_accum, delta, *, batch, heads, seq_len, causal, scale, xpos=None):
+def attention_bwd(q, k, v, out, d_out, lse, dq, dk, dv, dq_accum, delta, *, batch, heads, seq_len, causal, scale, xpos=None,
+                  drop_p=0.0, drop_mask=None):
     """dq, dk, dv (bf16 column blocks sharing one pitch) from d_out; xpos = the four kx_xpos_tables undoes the rotation."""
     for n, t in (("q", q), ("k", k), ("v", v), ("out", out), ("d_out", d_out), ("dq", dq), ("dk", dk), ("dv", dv)):
         _req(t, torch.bfloat16, n)
@@ -180,10 +214,17 @@ def attention_bwd(q, k, v, out, d_out, lse, dq, dk, dv, dq_accum, delta, *, batc
     tabs = [None] * 4 if xpos is None else [t.data_ptr() for t in xpos]
     fl = 10.0 * batch * heads * seq_len * seq_len * 64 * (0.5 if causal else 1.0)
     with _Timed("attn_bwd", fl, 0.0):
-        check(lib.kx_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
-                              d_out.data_ptr(), d_out.stride(0), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
-                              dq.stride(0), dq_accum.data_ptr(), delta.data_ptr(), *tabs, batch, heads, seq_len,
-                              1 if causal else 0, float(scale), _stream()), "kx_attn_bwd")
+        if drop_mask is not None and drop_p > 0:
+            check(lib.kx_attn_bwd_dropout(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                                          d_out.data_ptr(), d_out.stride(0), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                          dv.data_ptr(), dq.stride(0), dq_accum.data_ptr(), delta.data_ptr(), *tabs, batch,
+                                          heads, seq_len, 1 if causal else 0, float(scale), float(drop_p),
+                                          drop_mask.data_ptr(), _stream()), "kx_attn_bwd_dropout")
+        else:
+            check(lib.kx_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                                  d_out.data_ptr(), d_out.stride(0), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                  dq.stride(0), dq_accum.data_ptr(), delta.data_ptr(), *tabs, batch, heads, seq_len,
+                                  1 if causal else 0, float(scale), _stream()), "kx_attn_bwd")
 
 
 def act_layernorm(x, gamma, beta, out, *, act=_abi.KX_ACT_GELU, eps=1e-5):
@@ -202,7 +243,7 @@ def ln_bwd_partials(rows: int) -> int:
 
 
 def layernorm_bwd(x, dy, gamma, dx, d_gamma, d_beta, partials, *, act=_abi.KX_ACT_NONE, eps=1e-5, dres=None, dxb=None,
-                  d_colsum=None, accumulate=False, pre_add=None):
+                  d_colsum=None, accumulate=False, pre_add=None, drop=None):
     """LayerNorm (+GELU) backward; see kx_layernorm_bwd.  partials: fp32 [3, ln_bwd_partials(rows), n]."""
     _req(dy, torch.bfloat16, "dy")
     rows, n = x.shape
@@ -214,6 +255,7 @@ def layernorm_bwd(x, dy, gamma, dx, d_gamma, d_beta, partials, *, act=_abi.KX_AC
                                    dx.data_ptr(), 1 if dx.dtype == torch.float32 else 0, dx.stride(0), _ptr(dxb),
                                    0 if dxb is None else dxb.stride(0), partials.data_ptr(), partials.shape[1],
                                    d_gamma.data_ptr(), d_beta.data_ptr(), _ptr(d_colsum), 1 if accumulate else 0, rows, n,
+                                   *((float(drop[0]), int(drop[1]), int(drop[2])) if drop is not None and drop[0] > 0 else (0.0, 0, 0)),
                                    _stream()), "kx_layernorm_bwd")
     return dx
 

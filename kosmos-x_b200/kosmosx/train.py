@@ -14,7 +14,9 @@ Gradients live in one flat fp32 buffer that is all-reduced in per-layer buckets 
 Trained here (SURVEY.md §8(e) trainable set): the decoder (.A branches), the final LayerNorm, the LM head, the
 token-embedding and position tables, the perceiver resampler and image_proj.  Frozen: the CLIP tower (the reference's
 notes.txt:537 `clip_model.requires_grad_(False)`; its optional last-layer fine-tuning is not built) and the multiway
-.B branches (never executed).  Dropout (p = 0.1 in the reference's train mode) is not applied.
+.B branches (never executed).  Dropout (dropout = attention_dropout = 0.1 in the reference's train mode,
+model.py:175-177) is applied at torchscale's four sites: the decoder input, out_proj's output, fc2's output (Philox masks
+regenerated in backward) and the attention probabilities (keep bits recorded by the forward flash kernel).
 """
 from __future__ import annotations
 
@@ -45,11 +47,14 @@ class KosmosTrainer:
     """One object per process (one process per GPU).  ``step(text_tokens, images)`` runs a whole optimisation step
     and returns the mean loss as a device scalar (no host sync)."""
 
+    SITE_X0 = 0xFFFF0000          # dropout site ids: layer * 4 + {0: out_proj output, 1: fc2 output, 2: attention probabilities}
+
     def __init__(self, model: Kosmos, *, optimizer: str = "adamw", lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
                  weight_decay: float = 0.1, max_grad_norm: float = 1.0, process_group=None, overlap_all_reduce: bool = True,
                  train_resampler: bool = True, layout_only: bool = False, loss_rule: str = "reference",
                  pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.float32,
-                 distributed: bool | None = None):
+                 distributed: bool | None = None, dropout: float | None = None, attention_dropout: float | None = None,
+                 seed: int = 0):
         """loss_rule: "reference" = the rows / targets of the reference's intended loop (notes.txt:566-574: the `<image>`
         `</image>` markers and the feature rows carry no loss and are never targets; row 0 predicts the first real text
         token), "next_token" = plain shift by one over the text rows.  pad_token_id: targets equal to it are ignored
@@ -58,7 +63,12 @@ class KosmosTrainer:
         grad_reduce_dtype: torch.float32 all-reduces the flat fp32 gradient buffer; torch.bfloat16 exchanges a bf16
         copy (half the NVLink bytes, the reference's FSDP ``reduce_dtype`` is 16-bit too, train.py:156-162) and
         accumulates the received sums back in fp32.  distributed: None = data parallel over ``process_group`` (or the
-        default group) whenever torch.distributed is initialised; False = this process trains alone."""
+        default group) whenever torch.distributed is initialised; False = this process trains alone.
+        dropout / attention_dropout: None = the model's config (the reference trains with 0.1 / 0.1, model.py:175-177);
+        0 switches a site off (parity runs).  Masks are Philox4x32-7 functions of (seed, forward count, site, coordinates):
+        the element-wise sites (decoder input, out_proj output, fc2 output) are regenerated in backward, the attention
+        probabilities' keep bits are recorded by the forward kernel (1 bit per score) for the backward kernel.
+        Ranks draw different masks (the seed is offset by the rank)."""
         if optimizer not in ("adamw", "lion"):
             raise ValueError("optimizer must be 'adamw' or 'lion' (train.py:375-386)")
         if loss_rule not in ("reference", "next_token"):
@@ -69,6 +79,12 @@ class KosmosTrainer:
         self.cfg = model.cfg
         self.opt, self.lr, self.betas, self.eps, self.wd = optimizer, lr, betas, eps, weight_decay
         self.loss_rule, self.pad_token_id, self.lr_schedule = loss_rule, pad_token_id, lr_schedule
+        self.p_drop = float(model.cfg.dropout if dropout is None else dropout)
+        self.p_attn = float(model.cfg.attention_dropout if attention_dropout is None else attention_dropout)
+        if not (0.0 <= self.p_drop < 1.0 and 0.0 <= self.p_attn < 1.0):
+            raise ValueError("dropout probabilities must be in [0, 1)")
+        self.seed = int(seed)
+        self._fw_count = 0
         self.grad_reduce_dtype = grad_reduce_dtype
         self.max_grad_norm = max_grad_norm
         self.pg = process_group
@@ -212,6 +228,13 @@ class KosmosTrainer:
             m._perceive_project(xv, B, x, T, img_rows, pos_table=pos)
         ops.embed_splice_pos(text_tokens, m.embed.weight, pos, x, img_rows=img_rows, n_img=Lq, err_flag=m._err_flag(),
                              alias_positions=cfg.alias_embed_positions)
+        # dropout: one 64-bit seed per forward (backward regenerates / re-reads this forward's masks)
+        self._fw_count += 1
+        rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
+        dseed = (self.seed * 0x9E3779B97F4A7C15 + rank * 0xD1B54A32D192ED03 + self._fw_count) & 0xFFFFFFFFFFFFFFFF
+        pd, pa = self.p_drop, self.p_attn
+        if pd > 0:                               # forward_embedding ends with dropout(x) (model.py:242-244 -> torchscale)
+            ops.dropout_f32(x, p=pd, site=self.SITE_X0, seed=dseed)
         tabs = dp._xpos(T, x.device)
         scale = (D // H) ** -0.5
         saved = []
@@ -232,21 +255,23 @@ class KosmosTrainer:
             ops.layernorm(x, L["ln_a"].weight, L["ln_a"].bias, s["h1"], eps=cfg.eps)
             ops.gemm(s["h1"], wqkv, s["qkv"], bias=bqkv, xpos=tuple(tabs), seq_len=T)
             qkv = s["qkv"]
+            if pa > 0:
+                s["dmask"] = self._buf(f"dmask_{li}", (ops.attn_dropout_mask_words(B, H, T),), torch.int32)
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], s["att"], batch=B, heads=H, seq_len=T, causal=True,
-                          scale=scale, lse_out=s["lse"])
+                          scale=scale, lse_out=s["lse"], drop=(pa, li * 4 + 2, dseed), drop_mask=s.get("dmask"))
             ops.layernorm(s["att"], L["ln_i"].weight, L["ln_i"].bias, s["a_ln"], eps=cfg.eps)
-            ops.gemm(s["a_ln"], self._w16(L["o"].weight), s["x_mid"], bias=L["o"].bias, res=x)
+            ops.gemm(s["a_ln"], self._w16(L["o"].weight), s["x_mid"], bias=L["o"].bias, res=x, drop=(pd, li * 4, dseed))
             ops.layernorm(s["x_mid"], L["ln_f"].weight, L["ln_f"].bias, s["h2"], eps=cfg.eps)
             ops.gemm(s["h2"], self._w16(L["fc1"].weight), s["u"], bias=L["fc1"].bias)
             ops.act_layernorm(s["u"], L["ln_ffn"].weight, L["ln_ffn"].bias, s["g_ln"], eps=cfg.eps)
-            ops.gemm(s["g_ln"], self._w16(L["fc2"].weight), x_out, bias=L["fc2"].bias, res=s["x_mid"])
+            ops.gemm(s["g_ln"], self._w16(L["fc2"].weight), x_out, bias=L["fc2"].bias, res=s["x_mid"], drop=(pd, li * 4 + 1, dseed))
             saved.append(s)
             x = x_out
         hF = self._buf("hF", (M, D), bf)
         ops.layernorm(x, dp.layer_norm.weight, dp.layer_norm.bias, hF, eps=cfg.eps)
         logits = self._buf("logits", (M, V), f32)
         ops.gemm(hF, self._w16(m.output_projection.weight), logits, bias=m.output_projection.bias)
-        return dict(saved=saved, x_last=x, hF=hF, logits=logits, B=B, T=T, M=M, tabs=tabs, scale=scale, vis=vis)
+        return dict(saved=saved, x_last=x, hF=hF, logits=logits, B=B, T=T, M=M, tabs=tabs, scale=scale, vis=vis, dseed=dseed)
 
     # ------------------------------------------------------------------ perceiver resampler + image_proj (trainable)
     def _resampler_forward(self, xv, B, x0, T, img_rows, pos):
@@ -412,8 +437,11 @@ class KosmosTrainer:
         if m.output_projection.bias is not None:
             ops.colsum(dl, self._g(m.output_projection.bias))
         last = self.layers[-1] if self.layers else None
+        pd, pa, dseed = self.p_drop, self.p_attn, fw["dseed"]
+        nl = len(self.layers)
         ops.layernorm_bwd(fw["x_last"], dh, dp.layer_norm.weight, dx, self._g(dp.layer_norm.weight), self._g(dp.layer_norm.bias),
-                          part_d, eps=cfg.eps, dxb=dxb, d_colsum=self._g(last["fc2"].bias) if last else None)
+                          part_d, eps=cfg.eps, dxb=dxb, d_colsum=self._g(last["fc2"].bias) if last else None,
+                          drop=(pd, (nl - 1) * 4 + 1, dseed) if last else None)
         works = []
         self._bucket_ready("head", works)                     # the LM head gradient is complete
         for li in range(len(self.layers) - 1, -1, -1):
@@ -426,7 +454,7 @@ class KosmosTrainer:
             ops.gemm(du, self._w16(L["fc1"].weight), dh, b_trans=True)
             ops.gemm(du, s["h2"], self._g(L["fc1"].weight), a_trans=True, b_trans=True)
             ops.layernorm_bwd(s["x_mid"], dh, L["ln_f"].weight, dx, self._g(L["ln_f"].weight), self._g(L["ln_f"].bias), part_d,
-                              eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(L["o"].bias))
+                              eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(L["o"].bias), drop=(pd, li * 4, dseed))
             # ---- attention: x_mid = x_in + out_proj(LN_i(attn(xpos(qkv(LN_a(x_in))))))
             ops.gemm(dxb, self._w16(L["o"].weight), dh, b_trans=True)
             ops.gemm(dxb, s["a_ln"], self._g(L["o"].weight), a_trans=True, b_trans=True)
@@ -435,7 +463,7 @@ class KosmosTrainer:
             qkv = s["qkv"]
             ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], s["att"], datt, s["lse"], dqkv[:, :D], dqkv[:, D:2 * D],
                               dqkv[:, 2 * D:], dq_acc, delta, batch=B, heads=H, seq_len=T, causal=True, scale=fw["scale"],
-                              xpos=tuple(fw["tabs"]))
+                              xpos=tuple(fw["tabs"]), drop_p=pa, drop_mask=s.get("dmask"))
             wqkv, gwqkv = self._qkv(L, "weight")
             _, gbqkv = self._qkv(L, "bias")
             ops.colsum(dqkv, gbqkv)
@@ -443,8 +471,11 @@ class KosmosTrainer:
             ops.gemm(dqkv, s["h1"], gwqkv, a_trans=True, b_trans=True)
             prev = self.layers[li - 1] if li > 0 else None
             ops.layernorm_bwd(s["x_in"], dh, L["ln_a"].weight, dx, self._g(L["ln_a"].weight), self._g(L["ln_a"].bias), part_d,
-                              eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(prev["fc2"].bias) if prev else None)
+                              eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(prev["fc2"].bias) if prev else None,
+                              drop=(pd, (li - 1) * 4 + 1, dseed) if prev else None)
             self._bucket_ready(li, works)                     # (fc2.bias of layer li was written by layer li+1's LayerNorm backward)
+        if pd > 0:                               # backward of the decoder-input dropout: the same mask on the gradient
+            ops.dropout_f32(dx, p=pd, site=self.SITE_X0, seed=dseed)
         ops.embed_bwd(dx, text_tokens, self._g(m.embed.weight), self._g(m.embed_positions.weight), img_rows=img_rows, n_img=Lq,
                       padding_idx=m.embed.padding_idx if m.embed.padding_idx is not None else -1,
                       alias_positions=cfg.alias_embed_positions)
@@ -584,6 +615,7 @@ class KosmosTrainer:
         text_tokens, images, img_rows = self._prepare(text_tokens, images, image_positions)
         fw = self._forward(text_tokens, images, img_rows)
         self._backward(fw, text_tokens, img_rows, accumulate=accumulate)
+        self._last_fw = fw                       # (tests read the dropout seed / recorded attention masks of the step)
         return self.scalars[0] / torch.clamp(self.scalars[1], min=1.0)
 
     def step_accumulated(self, micro_batches):

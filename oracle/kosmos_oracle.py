@@ -80,6 +80,9 @@ class OracleConfig:
     # the IN-PLACE `x += positions` — `embed` (the `[1]` result the reference splices at model.py:238) is the same tensor
     # and carries the positions.  False = the out-of-place reading (`x = x + positions`).
     alias_embed_positions: bool = True
+    # torchscale DecoderConfig(dropout=0.1, attention_dropout=0.1) at model.py:175-177 (training mode only)
+    dropout: float = 0.1
+    attention_dropout: float = 0.1
 
     @property
     def vit_tokens(self) -> int:
@@ -103,6 +106,15 @@ class _Emu:
     def __init__(self, on: bool = False, fold: bool = True):
         self.on = on
         self.fold = fold
+        # training-mode dropout with INJECTED masks (multipliers: 0 or 1 / keep), so that a parity test can hand the
+        # oracle exactly the masks the CUDA path drew: {"x0": (B,T,D), ("attn_out", layer): (B,T,D),
+        # ("ffn_out", layer): (B,T,D), ("attn", layer): (B,H,T,T)}; None = eval mode (identity)
+        self.drop = None
+
+    def d(self, x, key):
+        if self.drop is None or key not in self.drop:
+            return x
+        return x * self.drop[key].to(x.dtype).reshape(x.shape)
 
     def r(self, x: torch.Tensor) -> torch.Tensor:
         return x.to(torch.bfloat16).to(torch.float32) if self.on else x
@@ -432,6 +444,7 @@ class MultiheadAttention(nn.Module):
         self.inner_attn_ln = _wrap(cfg, lambda: nn.LayerNorm(d, eps=cfg.eps))
         self.xpos = XPOS(self.hd, cfg.xpos_scale_base)
         self.use_xpos = True            # tests switch it off to cross-check against HF Kosmos-2's block
+        self.index = 0                  # layer index (set by Decoder): names this layer's dropout masks
 
     def forward(self, x, attn_mask, incremental_state=None, is_first_step=False):
         """``incremental_state`` (a per-layer dict) follows torchscale's MultiheadAttention [recall]: the UN-rotated
@@ -468,7 +481,8 @@ class MultiheadAttention(nn.Module):
             w = w + attn_mask[None]
         m = w.amax(-1, keepdim=True)
         p = torch.exp(w - m)                                 # == softmax(w, dtype=fp32) numerator
-        a = torch.bmm(e.r(p), v) / p.sum(-1, keepdim=True)
+        pd = e.d(p, ("attn", self.index))                    # attention dropout acts on the normalised probabilities
+        a = torch.bmm(e.r(pd), v) / p.sum(-1, keepdim=True)
         a = e.r(a).view(B, self.h, T, self.hd).transpose(1, 2).reshape(B, T, D)
         a = _ln(e, _inner(self.inner_attn_ln), a)
         return _linear(e, a, _inner(self.out_proj))
@@ -488,10 +502,10 @@ class DecoderLayer(nn.Module):
         r = x
         e = self.self_attn.emu
         x = self.self_attn(_ln(e, _inner(self.self_attn_layer_norm), x), mask, incremental_state, is_first_step)
-        x = r + x
+        x = r + e.d(x, ("attn_out", self.self_attn.index))   # x = dropout(self_attn(...)); x = residual + x
         r = x
         x = _inner(self.ffn)(_ln(e, _inner(self.final_layer_norm), x))
-        return r + x
+        return r + e.d(x, ("ffn_out", self.self_attn.index)) # FeedForwardNetwork ends with dropout(fc2(...))
 
 
 class PositionalEmbedding(nn.Embedding):
@@ -516,6 +530,8 @@ class Decoder(nn.Module):
         self.embed_positions = embed_positions
         self.output_projection = output_projection
         self.layers = nn.ModuleList(DecoderLayer(cfg, emu) for _ in range(cfg.layers))
+        for i, layer in enumerate(self.layers):
+            layer.self_attn.index = i
         self.layer_norm = nn.LayerNorm(cfg.dim, eps=cfg.eps)
         # sub-LN init (decoder-only): scale sqrt(log(2*layers)) on fc1/fc2/out_proj/v_proj
         init_scale = math.sqrt(math.log(cfg.layers * 2))
@@ -603,6 +619,10 @@ class KosmosOracle(nn.Module):
         self.emu.on = on
         self.emu.fold = fold
 
+    def set_dropout_masks(self, masks: dict | None):
+        """Training-mode dropout with the given multiplier tensors (see _Emu.drop); None switches it off."""
+        self.emu.drop = masks
+
     def _image_rows(self, images, keep=None):
         """ViT -> perceiver -> image_proj: (B,3,H,W) -> (B,1,64,dim); (B,m,3,H,W) -> (B,m,64,dim)."""
         feats = self._resample(images)
@@ -639,7 +659,8 @@ class KosmosOracle(nn.Module):
         rows = self._image_rows(images)
         model_input = self.decoder.forward_embedding(text_tokens)[1]           # model.py:238
         model_input = self.splice(model_input, rows, image_positions)          # model.py:239-241
-        return self.decoder.forward_embedding(model_input, token_embedding=model_input)[0]   # model.py:242-244
+        x0 = self.decoder.forward_embedding(model_input, token_embedding=model_input)[0]   # model.py:242-244
+        return self.emu.d(x0, "x0")        # forward_embedding ends with dropout(x) (training mode; masks injected, see _Emu)
 
     def forward(self, text_tokens, images, image_positions=None, **kwargs):
         if not isinstance(text_tokens, torch.Tensor) or not isinstance(images, torch.Tensor):

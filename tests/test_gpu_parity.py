@@ -792,7 +792,7 @@ def test_full_size_training_gradients_vs_oracle(full_pair):
     from kosmosx import KosmosTrainer
     ref, mine, oc = full_pair
     text, images = ko.make_inputs(oc, 1, 50, seed=2)
-    trainer = KosmosTrainer(mine)
+    trainer = KosmosTrainer(mine, dropout=0.0, attention_dropout=0.0)
     loss = trainer.loss_and_grads(text.cuda(), images.cuda())
     torch.cuda.synchronize()
     names = {id(p): n for n, p in mine.named_parameters()}

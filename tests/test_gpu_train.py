@@ -28,6 +28,8 @@ def _pair(max_positions=256, optimizer="adamw", **kw):
     mine = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
     mine.load_state_dict(ref.state_dict())
     mine = mine.cuda()
+    kw.setdefault("dropout", 0.0)                 # parity runs: dropout off unless a test asks for it
+    kw.setdefault("attention_dropout", 0.0)
     return ref, mine, KosmosTrainer(mine, optimizer=optimizer, **kw), oc
 
 
@@ -326,3 +328,81 @@ def test_two_rank_nccl_step_equals_single_process_step():
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "DP_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+
+# --------------------------------------------------------------------------- dropout (reference: dropout = attention_dropout = 0.1)
+def test_dropout_mask_function_is_deterministic_and_calibrated():
+    from kosmosx import ops
+    x = torch.ones(512, 1024, device="cuda")
+    a = ops.dropout_f32(x.clone(), p=0.1, site=5, seed=1234)
+    b = ops.dropout_f32(x.clone(), p=0.1, site=5, seed=1234)
+    c = ops.dropout_f32(x.clone(), p=0.1, site=6, seed=1234)
+    d = ops.dropout_f32(x.clone(), p=0.1, site=5, seed=1235)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    keep = 58982 / 65536                                    # round(0.9 * 65536) / 65536
+    vals = torch.unique(a)
+    assert vals.numel() == 2 and vals[0] == 0 and abs(vals[1].item() - 1 / keep) < 1e-6
+    frac = (a != 0).float().mean().item()
+    assert abs(frac - keep) < 4 * (keep * (1 - keep) / a.numel()) ** 0.5 + 1e-4, frac
+    # no structure along rows or columns
+    assert ((a != 0).float().mean(0) - keep).abs().max() < 0.08 and ((a != 0).float().mean(1) - keep).abs().max() < 0.06
+    # the GEMM epilogue draws the same mask, before the residual add
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(512, 256, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(1024, 256, device="cuda", generator=g) * 0.06).bfloat16()
+    bias = torch.randn(1024, device="cuda", generator=g)
+    res = torch.randn(512, 1024, device="cuda", generator=g)
+    plain = torch.empty(512, 1024, device="cuda")
+    ops.gemm(A, W, plain, bias=bias)
+    dropped = torch.empty(512, 1024, device="cuda")
+    ops.gemm(A, W, dropped, bias=bias, res=res, drop=(0.1, 5, 1234))
+    assert torch.allclose(dropped, plain * a + res, atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize("B,t_text,m,positions", [(2, 20, 1, None), (2, 150, 2, [2, 90])])
+def test_training_step_with_dropout_matches_oracle_given_the_same_masks(B, t_text, m, positions):
+    """The whole training step with dropout = attention_dropout = 0.1 (the reference's training mode): the masks the
+    kernels drew are materialised (element-wise sites: the same mask function on a matrix of ones; attention: the keep
+    bits the forward kernel recorded) and injected into the oracle, whose autograd then has to reproduce loss and every
+    gradient — which checks the forward masks, the regenerated backward masks and both flash kernels' dropout paths."""
+    import kosmos_oracle as ko
+    from kosmosx import ops
+    ref, mine, trainer, oc = _pair(max_positions=512, dropout=0.1, attention_dropout=0.1, seed=7)
+    text, images = ko.make_inputs(oc, B, t_text, seed=3, n_images=None if m == 1 else m)
+    loss = trainer.loss_and_grads(text.cuda(), images.cuda(), image_positions=positions)
+    torch.cuda.synchronize()
+    fw = trainer._last_fw
+    T, D, H = fw["T"], oc.dim, oc.heads
+    keep = 58982 / 65536
+
+    def elementwise(site):
+        return ops.dropout_f32(torch.ones(B * T, D, device="cuda"), p=0.1, site=site, seed=fw["dseed"]).view(B, T, D).cpu()
+
+    masks = {"x0": elementwise(trainer.SITE_X0)}
+    for li, s in enumerate(fw["saved"]):
+        masks[("attn_out", li)] = elementwise(li * 4)
+        masks[("ffn_out", li)] = elementwise(li * 4 + 1)
+        kb = ops.unpack_attn_dropout_mask(s["dmask"], B, H, T).cpu()
+        tri = torch.tril(torch.ones(T, T, dtype=torch.bool))
+        frac = kb[:, :, tri].float().mean().item()
+        assert abs(frac - keep) < 0.01, f"attention keep fraction {frac}"
+        masks[("attn", li)] = kb.float() / keep
+    ref.set_dropout_masks(masks)
+    ref.zero_grad()
+    want = ref.loss(text, images, image_positions=positions)
+    want.backward()
+    ref.set_dropout_masks(None)
+    print(f"dropout B={B} T={T} m={m}: loss cuda {loss.item():.5f} oracle {want.item():.5f}")
+    assert abs(loss.item() - want.item()) <= LOSS_TOL
+    n, worst = _check_grads(ref, mine, trainer)
+    print(f"  {n} tensors, worst relative gradient error {worst[0]:.3e} ({worst[1]})")
+    # and dropout actually changed the step: the same input without it gives another loss
+    with torch.no_grad():
+        plain = ref.loss(text, images, image_positions=positions).item()
+    assert abs(plain - want.item()) > 1e-3
+    # a second forward draws new masks; the same trainer seed + forward count reproduces them
+    l2 = trainer.loss_and_grads(text.cuda(), images.cuda(), image_positions=positions).item()
+    assert abs(l2 - loss.item()) > 1e-4
+    _, mine_b, trainer_b, _ = _pair(max_positions=512, dropout=0.1, attention_dropout=0.1, seed=7)
+    assert abs(trainer_b.loss_and_grads(text.cuda(), images.cuda(), image_positions=positions).item() - loss.item()) <= 1e-5

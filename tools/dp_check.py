@@ -48,7 +48,7 @@ def main():
         m = Kosmos(config=kc)
         m.load_state_dict(sd)
         m = m.cuda()
-        return m, KosmosTrainer(m, lr=1e-3, weight_decay=0.1, **kw)
+        return m, KosmosTrainer(m, lr=1e-3, weight_decay=0.1, dropout=0.0, attention_dropout=0.0, **kw)
 
     # the single-process answer on the concatenated batch
     m1, t1 = fresh(distributed=False)

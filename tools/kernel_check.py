@@ -684,7 +684,7 @@ def case_accurate():
     cls = torch.randn(Dv, device=dev); vpos = torch.randn(P + 1, Dv, device=dev)
     x = torch.zeros(n, P + 1, Dv, device=dev)
     ops.im2col_patches_f32(px, patches, cls, vpos, x, image=image, patch=patch, media=media)
-    un = F.unfold(px, patch, stride=patch).transpose(1, 2)                       # (n, P, 588)
+    un = torch.nn.functional.unfold(px, patch, stride=patch).transpose(1, 2)     # (n, P, 588)
     slot = torch.tensor([(i % media) * (n // media) + i // media for i in range(n)])
     want = torch.zeros(n, P, kp, device=dev)
     want[slot, :, :588] = un

@@ -24,7 +24,7 @@ g = torch.Generator().manual_seed(1)
 text = torch.randint(0, 32002, (a.batch, a.t_text), generator=g).cuda()
 img = torch.randn(a.batch, 3, 224, 224, generator=g).cuda()
 if a.train:
-    trainer = KosmosTrainer(model, lr=1e-5)
+    trainer = KosmosTrainer(model, lr=1e-5, dropout=float(os.environ.get("KX_PROFILE_DROPOUT", "0.1")), attention_dropout=float(os.environ.get("KX_PROFILE_DROPOUT", "0.1")))
     model._pack_vision()
     torch.cuda.synchronize()
     print("staging launches:", ops.launch_count(), flush=True)
