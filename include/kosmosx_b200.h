@@ -283,23 +283,27 @@ int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, c
                 float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin, const float* xk_cos,
                 const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale, kx_stream_t stream);
 
-/* The same pair with attention dropout (torchscale MultiheadAttention: `attn_probs = dropout(attn_weights)`, the reference
- * trains with attention_dropout = 0.1, kosmosx/model.py:177): the forward keeps probability (q, k) of (batch, head) iff
- * its 16-bit Philox4x32-7 lot < round((1 - p) * 65536) (one call per 8 consecutive keys of a query row; a pure function
- * of (drop_seed, drop_site, batch*heads + head, q, k)), sums the row normaliser over ALL probabilities, scales the output
- * by 1 / (1 - p), and records the keep bits for the backward pass, transposed for its key-major threads:
- *   drop_mask[((((batch*heads + head) * nb + qb) * nb + kb) * 4 + g) * 128 + r], nb = ceil(seq_len / 128): bit i = query
- *   128*qb + 32*g + i keeps key 128*kb + r  — kx_attn_dropout_mask_words(batch, heads, seq_len) uint32 words.
- * The backward reads one word per thread and tile: dV += (M o P / keep)^T dO, dS = P o (M o dP / keep - delta). */
+/* The same pair with attention dropout (torchscale MultiheadAttention: `attn_probs = dropout(attn_weights)`; the reference
+ * trains with attention_dropout = 0.1, kosmosx/model.py:177).  The keep bits are drawn AHEAD of the flash kernels — whose
+ * softmax warps are their bottleneck — by kx_attn_dropout_masks, a pure function of (drop_seed, drop_site, batch*heads + head,
+ * query, key): Philox4x32-7 words bit-sliced into Bernoulli(keep) bits with keep = round((1 - p) * 4096) / 4096, 1 bit per
+ * score, written in the two layouts the kernels' thread mappings want (nb = ceil(seq_len / 128); causal: only tiles
+ * kb <= qb are written or read; kx_attn_dropout_mask_words() uint32 words each):
+ *   row_mask[(((bh * nb + qb) * nb + kb) * 128 + r) * 4 + c]       bit b: query 128 qb + r keeps key 128 kb + 32 c + b
+ *   key_mask[((((bh * nb + qb) * nb + kb) * 4 + g) * 128 + r]      bit i: query 128 qb + 32 g + i keeps key 128 kb + r
+ * Forward: dropped probabilities are zeroed in the P operand of P.V, the row normaliser sums ALL probabilities, the
+ * output is scaled by 1 / keep.  Backward: dV += (M o P / keep)^T dO, dS = P o (M o dP / keep - delta). */
 size_t kx_attn_dropout_mask_words(int batch, int heads, int seq_len);
+int kx_attn_dropout_masks(float drop_p, unsigned int drop_site, unsigned long long drop_seed, int batch, int heads, int seq_len,
+                          int causal, unsigned int* row_mask, unsigned int* key_mask, kx_stream_t stream);
 int kx_attn_fwd_dropout(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
                         int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, float drop_p,
-                        unsigned int drop_site, unsigned long long drop_seed, unsigned int* drop_mask, kx_stream_t stream);
+                        const unsigned int* row_mask, kx_stream_t stream);
 int kx_attn_bwd_dropout(const void* q, const void* k, const void* v, long long ld_qkv, const void* out, long long ld_out,
                         const void* d_out, long long ld_dout, const float* lse, void* dq, void* dk, void* dv, long long ld_dqkv,
                         float* dq_accum, float* delta, const float* xq_cos, const float* xq_sin, const float* xk_cos,
                         const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale, float drop_p,
-                        const unsigned int* drop_mask, kx_stream_t stream);
+                        const unsigned int* key_mask, kx_stream_t stream);
 
 /* Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 int64 installed, CTA 0 of every launch records
  * clock64 stamps [role: compute thread 0, MMA thread][iteration][point]; NULL = off. */

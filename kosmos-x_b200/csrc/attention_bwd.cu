@@ -60,7 +60,7 @@ struct AttnBwdParams {
     int seq_len, heads, batch, t_pad;
     float scale, scale_log2;
     long long* trace;          // TRACE builds only: clock64 stamps of CTA 0, [role: 0 compute thread 0, 1 MMA thread][iteration][16 points]
-    const uint32_t* drop_mask; // DROP builds only: keep bits written by the forward (kx_attn_fwd_dropout), word per (tile, quarter, key)
+    const uint32_t* drop_mask; // DROP builds only: key-major keep bits of kx_attn_dropout_masks, word per (tile, query quarter, key)
     float inv_keep;            // 1 / (1 - p)
 };
 
@@ -552,11 +552,11 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, long long 
     p.inv_keep = 1.0f;
     if (drop_mask != nullptr) {
         if (!causal || !(drop_p > 0.f && drop_p < 1.f) || (reinterpret_cast<uintptr_t>(drop_mask) & 15)) {
-            set_error("kx_attn_bwd_dropout: needs causal attention, 0 < p < 1 and the 16-byte aligned mask of kx_attn_fwd_dropout");
+            set_error("kx_attn_bwd_dropout: needs causal attention, 0 < p < 1 and the 16-byte aligned key_mask of kx_attn_dropout_masks");
             return KX_ERR_ARG;
         }
-        const unsigned thr = static_cast<unsigned>((1.0 - static_cast<double>(drop_p)) * 65536.0 + 0.5);
-        p.inv_keep = 65536.0f / static_cast<float>(thr);
+        const unsigned thr12 = static_cast<unsigned>((1.0 - static_cast<double>(drop_p)) * 4096.0 + 0.5);   // as kx_attn_dropout_masks
+        p.inv_keep = 4096.0f / static_cast<float>(thr12);
     }
     const long long ctas = static_cast<long long>(nblk) * heads * batch;
     if (ctas > 0x7fffffffLL) { set_error("kx_attn_bwd: too many tiles"); return KX_ERR_ARG; }

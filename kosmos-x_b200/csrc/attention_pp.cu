@@ -48,8 +48,8 @@ struct AttnPPParams {
     float* lse_out;                                  // [heads][batch][t_pad] row log-sum-exp in log2 units (training), or null
     int t_pad;
     long long* trace;                                // TRACE builds only: clock64 stamps of CTA (0,0), [4 roles][64 iters][8 points]
-    DropSpec drop;                                   // DROP builds only: attention dropout (training)
-    uint32_t* drop_mask;                             // keep bits, transposed for the backward pass (see kx_attn_fwd_dropout)
+    const uint4* row_mask;                           // DROP builds only: keep bits of kx_attn_dropout_masks, [tile][query row] x 128 keys
+    float inv_keep;                                  // 1 / keep probability (applied once, to O)
 };
 
 static long long* g_attn_trace = nullptr;            // kx_attn_set_trace
@@ -290,6 +290,12 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int kv0 = j * 128;
             const uint32_t par = (cum + j) & 1;
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 0);
+            uint4 kw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            if constexpr (DROP) {
+                const int nb = (T + 127) >> 7;
+                const long long tile = (static_cast<long long>(it.b * p.heads + head) * nb + ((q0 >> 7) + w)) * nb + j;
+                kw = __ldg(p.row_mask + tile * 128 + r);
+            }
             mbar_wait(&s_full[w], par);
             tc_fence_after();
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 1);
@@ -373,32 +379,13 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             unpack_f32x2(fadd2(acc0, acc1), a0, a1);
             l_run += a0 + a1;                              // the normaliser sums ALL probabilities (dropout acts after softmax)
             if constexpr (DROP) {
-                // attention dropout: 16 Philox calls give this row's keep bits for the 128 keys of the block; dropped
-                // probabilities become exact zeros in the P operand of P.V (the 1/keep factor is applied once, to O)
-                uint32_t keepw[4] = {0u, 0u, 0u, 0u};
-                const uint32_t bh = static_cast<uint32_t>(it.b * p.heads + head);
-#pragma unroll
-                for (int c = 0; c < 16; ++c)
-                    keepw[c >> 2] |= drop_keep8_attn(p.drop, static_cast<uint32_t>(qrow), static_cast<uint32_t>((kv0 >> 3) + c), bh) << ((c & 3) * 8);
+                // attention dropout: this row's keep bits for the block's 128 keys (generated ahead by kx_attn_dropout_masks,
+                // loaded at the top of the iteration); dropped probabilities become exact zeros in the P operand of P.V
+                const uint32_t keepw[4] = {kw.x, kw.y, kw.z, kw.w};
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
                     const uint32_t b2 = (keepw[i >> 4] >> ((i & 15) * 2)) & 3u;
                     pv[i] &= ((b2 & 1u) ? 0x0000ffffu : 0u) | ((b2 & 2u) ? 0xffff0000u : 0u);
-                }
-                // the backward pass runs with thread = key: hand it the bits transposed, word (g, key) = this warp's 32
-                // query rows, built with one ballot per key and stored as four coalesced 128-byte rows per block
-                const int nb = (T + 127) >> 7;
-                const int qb = (q0 >> 7) + w, g = warp & 3;
-                uint32_t* dst = p.drop_mask + ((((static_cast<long long>(bh) * nb + qb) * nb + j) * 4 + g) << 7);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t word = 0u;
-#pragma unroll
-                    for (int b = 0; b < 32; ++b) {
-                        const uint32_t bal = __ballot_sync(0xffffffffu, (keepw[c] >> b) & 1u);
-                        if (lane == b) word = bal;
-                    }
-                    dst[c * 32 + lane] = word;
                 }
             }
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 4);
@@ -427,7 +414,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(&o_read[w]);                          // the next item's first P.V may overwrite O_w
         if (qrow < T) {
-            const float inv_l = DROP ? p.drop.inv_keep / l_run : 1.0f / l_run;
+            const float inv_l = DROP ? p.inv_keep / l_run : 1.0f / l_run;
             __nv_bfloat16* o = p.out + static_cast<long long>(row_base + qrow) * p.ld_out + head * 64;
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -464,7 +451,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
 int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
                    int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, cudaStream_t stream,
-                   const DropSpec* drop, uint32_t* drop_mask) {
+                   float inv_keep, const uint32_t* row_mask) {
     const unsigned long long rows = (unsigned long long)batch * seq_len;
     CUtensorMap tq, tk, tv;
     if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
@@ -483,8 +470,8 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.lse_out = lse_out;
     p.t_pad = (seq_len + 127) / 128 * 128;
     p.trace = g_attn_trace;
-    p.drop = drop != nullptr ? *drop : DropSpec{};
-    p.drop_mask = drop_mask;
+    p.row_mask = reinterpret_cast<const uint4*>(row_mask);
+    p.inv_keep = inv_keep;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
@@ -510,8 +497,8 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
         attn_pp_kernel<true, true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
         return check_launch("kx_attn_fwd");
     }
-    if (p.drop.thr != 0u) {
-        if (!causal || drop_mask == nullptr) { set_error("kx_attn_fwd_dropout: causal attention and a mask buffer are required"); return KX_ERR_ARG; }
+    if (row_mask != nullptr) {
+        if (!causal) { set_error("kx_attn_fwd_dropout: causal attention is required"); return KX_ERR_ARG; }
         attn_pp_kernel<true, true, false, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
         return check_launch("kx_attn_fwd_dropout");
     }

@@ -52,16 +52,22 @@ __device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, uint32_t row, 
     return m;
 }
 
-// attention-probability site: the 8 keys 8*k8 .. 8*k8+7 of query `q` in (batch*heads + head) slice `bh`
-__device__ __forceinline__ uint32_t drop_keep8_attn(const DropSpec& d, uint32_t q, uint32_t k8, uint32_t bh) {
-    const uint4 r = philox4x32_7(q, k8, d.site, 0x61740000u + bh, static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    uint32_t m = 0;
+// Attention-probability site.  The keep bits of 32 consecutive keys of one query row come out of 12 uniform random
+// words by bit-slicing: with thr12 = round(keep * 4096) = sum b_i 2^i, fold m = b_i ? (m | u_i) : (m & u_i) from i = 0 up —
+// every bit of m is then Bernoulli(thr12 / 4096) — three Philox calls and 12 logic ops per 32 elements instead of 32
+// sixteen-bit comparisons.  (q, key group, bh) address the words, so any kernel can regenerate any word.
+__device__ __forceinline__ uint32_t drop_keep32_attn(unsigned long long seed, uint32_t site, uint32_t thr12, uint32_t q, uint32_t kgroup,
+                                                    uint32_t bh) {
+    uint32_t u[12];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        m |= ((w[u] & 0xffffu) < d.thr ? 1u : 0u) << (2 * u);
-        m |= ((w[u] >> 16) < d.thr ? 1u : 0u) << (2 * u + 1);
+    for (int c = 0; c < 3; ++c) {
+        const uint4 r = philox4x32_7(q, (kgroup << 2) | static_cast<uint32_t>(c), site, 0x61740000u + bh, static_cast<uint32_t>(seed),
+                                     static_cast<uint32_t>(seed >> 32));
+        u[4 * c] = r.x; u[4 * c + 1] = r.y; u[4 * c + 2] = r.z; u[4 * c + 3] = r.w;
     }
+    uint32_t m = 0u;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) m = ((thr12 >> i) & 1u) ? (m | u[i]) : (m & u[i]);
     return m;
 }
 

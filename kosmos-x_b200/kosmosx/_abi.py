@@ -124,7 +124,8 @@ SIGNATURES = {
                               _f32p, _f32p, _f32p, _i, _i, _i, _f, C.c_uint, C.c_ulonglong, _vp]),
     "kx_dropout_f32": (_i, [_f32p, _ll, _i, _i, _f, C.c_uint, C.c_ulonglong, _vp]),
     "kx_attn_dropout_mask_words": (C.c_size_t, [_i, _i, _i]),
-    "kx_attn_fwd_dropout": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _f32p, _f, C.c_uint, C.c_ulonglong, _vp, _vp]),
+    "kx_attn_dropout_masks": (_i, [_f, C.c_uint, C.c_ulonglong, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "kx_attn_fwd_dropout": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _f32p, _f32p, _f, _vp, _vp]),
     "kx_attn_bwd_dropout": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _f32p, _vp, _vp, _vp, _ll, _f32p, _f32p,
                                  _f32p, _f32p, _f32p, _f32p, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "kx_perceiver_xattn_bwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),

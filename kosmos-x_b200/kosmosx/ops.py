@@ -139,7 +139,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias=None, res=
     return out
 
 
-def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=None, lse_out=None, drop=None, drop_mask=None):
+def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=None, lse_out=None, drop_p=0.0, row_mask=None):
     """q, k, v: bf16 2-D views [batch*seq_len, heads*64] sharing one row pitch; out bf16 [batch*seq_len, >=heads*64].
     stats_out fp32 [heads, batch*seq_len, 2]: per-head partial (sum, sumsq) of every output row."""
     if stats_out is not None:
@@ -156,13 +156,12 @@ def attention(q, k, v, out, *, batch, heads, seq_len, causal, scale, stats_out=N
             _req(lse_out, torch.float32, "lse_out")
             if lse_out.numel() != heads * batch * lse_pad(seq_len) or not lse_out.is_contiguous():
                 raise ValueError("attention: lse_out must be contiguous [heads, batch, ceil(seq_len/128)*128]")
-        if drop is not None and drop[0] > 0:          # training: attention dropout, keep bits recorded for the backward pass
-            if lse_out is None or drop_mask is None or drop_mask.dtype != torch.int32 or drop_mask.numel() < attn_dropout_mask_words(batch, heads, seq_len):
-                raise ValueError("attention: dropout needs lse_out and an int32 drop_mask of attn_dropout_mask_words() entries")
+        if drop_p > 0:                                # training: attention dropout, keep bits from attn_dropout_masks()
+            if lse_out is None or row_mask is None or row_mask.dtype != torch.int32 or row_mask.numel() < attn_dropout_mask_words(batch, heads, seq_len):
+                raise ValueError("attention: dropout needs lse_out and the int32 row_mask of attn_dropout_masks()")
             check(lib.kx_attn_fwd_dropout(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
                                           batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out), lse_out.data_ptr(),
-                                          float(drop[0]), int(drop[1]), int(drop[2]), drop_mask.data_ptr(), _stream()),
-                  "kx_attn_fwd_dropout")
+                                          float(drop_p), row_mask.data_ptr(), _stream()), "kx_attn_fwd_dropout")
         elif lse_out is not None:
             check(lib.kx_attn_fwd_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
                                       batch, heads, seq_len, 1 if causal else 0, float(scale), _ptr(stats_out),
@@ -182,8 +181,27 @@ def attn_dropout_mask_words(batch: int, heads: int, seq_len: int) -> int:
     return int(lib.kx_attn_dropout_mask_words(batch, heads, seq_len))
 
 
+def attn_dropout_masks(row_mask, key_mask, *, p, site, seed, batch, heads, seq_len, causal=True):
+    """Draw the keep bits of one attention-dropout site into both layouts (kx_attn_dropout_masks)."""
+    for n, t in (("row_mask", row_mask), ("key_mask", key_mask)):
+        if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous() or t.numel() < attn_dropout_mask_words(batch, heads, seq_len):
+            raise ValueError(f"attn_dropout_masks: {n} must be a contiguous int32 CUDA tensor of attn_dropout_mask_words() entries")
+    with _Timed("attn_dropout_masks", 0.0, 8.0 * batch * heads * seq_len * seq_len / 8 / 2):
+        check(lib.kx_attn_dropout_masks(float(p), int(site), int(seed), batch, heads, seq_len, 1 if causal else 0,
+                                        row_mask.data_ptr(), key_mask.data_ptr(), _stream()), "kx_attn_dropout_masks")
+
+
+def unpack_attn_row_mask(mask: torch.Tensor, batch: int, heads: int, seq_len: int) -> torch.Tensor:
+    """row_mask of attn_dropout_masks -> bool (batch, heads, seq_len, seq_len) [q, k] (test helper)."""
+    nb = (seq_len + 127) // 128
+    w = mask[:batch * heads * nb * nb * 512].view(batch, heads, nb, nb, 128, 4).to(torch.int64) & 0xffffffff     # [b,h,qb,kb,r,c]
+    bits = (w.unsqueeze(-1) >> torch.arange(32, device=mask.device)) & 1                                         # [..., r, c, bit]
+    keep = bits.permute(0, 1, 2, 4, 3, 5, 6).reshape(batch, heads, nb * 128, nb * 128)                             # q = qb,r ; k = kb,c,bit
+    return keep[:, :, :seq_len, :seq_len].bool()
+
+
 def unpack_attn_dropout_mask(mask: torch.Tensor, batch: int, heads: int, seq_len: int) -> torch.Tensor:
-    """Keep bits recorded by the dropout forward -> bool (batch, heads, seq_len, seq_len) [q, k] (test / inspection helper;
+    """key_mask of attn_dropout_masks -> bool (batch, heads, seq_len, seq_len) [q, k] (test / inspection helper;
     the kernels read the packed words).  Entries of tiles the causal forward never visits are undefined."""
     nb = (seq_len + 127) // 128
     w = mask[:batch * heads * nb * nb * 512].view(batch, heads, nb, nb, 4, 128).to(torch.int64) & 0xffffffff      # [b,h,qb,kb,g,r]

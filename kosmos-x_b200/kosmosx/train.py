@@ -16,7 +16,7 @@ token-embedding and position tables, the perceiver resampler and image_proj.  Fr
 notes.txt:537 `clip_model.requires_grad_(False)`; its optional last-layer fine-tuning is not built) and the multiway
 .B branches (never executed).  Dropout (dropout = attention_dropout = 0.1 in the reference's train mode,
 model.py:175-177) is applied at torchscale's four sites: the decoder input, out_proj's output, fc2's output (Philox masks
-regenerated in backward) and the attention probabilities (keep bits recorded by the forward flash kernel).
+regenerated in backward) and the attention probabilities (keep bits drawn ahead of the two flash kernels, 1 bit per score).
 """
 from __future__ import annotations
 
@@ -67,7 +67,7 @@ class KosmosTrainer:
         dropout / attention_dropout: None = the model's config (the reference trains with 0.1 / 0.1, model.py:175-177);
         0 switches a site off (parity runs).  Masks are Philox4x32-7 functions of (seed, forward count, site, coordinates):
         the element-wise sites (decoder input, out_proj output, fc2 output) are regenerated in backward, the attention
-        probabilities' keep bits are recorded by the forward kernel (1 bit per score) for the backward kernel.
+        probabilities' keep bits (1 bit per score) are drawn by kx_attn_dropout_masks ahead of the flash kernels.
         Ranks draw different masks (the seed is offset by the rank)."""
         if optimizer not in ("adamw", "lion"):
             raise ValueError("optimizer must be 'adamw' or 'lion' (train.py:375-386)")
@@ -255,10 +255,15 @@ class KosmosTrainer:
             ops.layernorm(x, L["ln_a"].weight, L["ln_a"].bias, s["h1"], eps=cfg.eps)
             ops.gemm(s["h1"], wqkv, s["qkv"], bias=bqkv, xpos=tuple(tabs), seq_len=T)
             qkv = s["qkv"]
-            if pa > 0:
-                s["dmask"] = self._buf(f"dmask_{li}", (ops.attn_dropout_mask_words(B, H, T),), torch.int32)
+            row_mask = None
+            if pa > 0:       # keep bits drawn ahead of the flash kernel: row-major for it (one buffer, reused by every layer),
+                             # key-major for this layer's backward kernel (kept until then: 1 bit per score)
+                words = ops.attn_dropout_mask_words(B, H, T)
+                row_mask = self._buf("dmask_rows", (words,), torch.int32)
+                s["dmask"] = self._buf(f"dmask_{li}", (words,), torch.int32)
+                ops.attn_dropout_masks(row_mask, s["dmask"], p=pa, site=li * 4 + 2, seed=dseed, batch=B, heads=H, seq_len=T)
             ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], s["att"], batch=B, heads=H, seq_len=T, causal=True,
-                          scale=scale, lse_out=s["lse"], drop=(pa, li * 4 + 2, dseed), drop_mask=s.get("dmask"))
+                          scale=scale, lse_out=s["lse"], drop_p=pa, row_mask=row_mask)
             ops.layernorm(s["att"], L["ln_i"].weight, L["ln_i"].bias, s["a_ln"], eps=cfg.eps)
             ops.gemm(s["a_ln"], self._w16(L["o"].weight), s["x_mid"], bias=L["o"].bias, res=x, drop=(pd, li * 4, dseed))
             ops.layernorm(s["x_mid"], L["ln_f"].weight, L["ln_f"].bias, s["h2"], eps=cfg.eps)

@@ -56,7 +56,7 @@ def _kernel_cases():
 
 @pytest.mark.parametrize("case", ["gemm_basic", "gemm_shapes", "gemm_epilogue", "xpos", "gemm_qkv", "attn", "layernorm",
                                   "ln_fold", "embed", "perceiver_attn", "gemm_trans", "train_elementwise", "attn_bwd",
-                                  "perceiver_bwd", "decode", "preprocess", "accurate"])
+                                  "perceiver_bwd", "decode", "preprocess", "accurate", "attn_dropout"])
 def test_kernel_against_torch_fp32(case):
     """Each kernel alone against a plain PyTorch fp32 restatement of the same op (tools/kernel_check.py)."""
     import kernel_check as kc

@@ -446,6 +446,54 @@ def case_attn_bwd():
     return ok
 
 
+def case_attn_dropout():
+    """Attention dropout: the mask generator (both layouts agree, keep fraction, determinism) and both flash kernels against
+    autograd through the eager formula with the SAME mask: out = ((M o P) / keep) V, P = softmax over all scores."""
+    torch.manual_seed(41)
+    ok = True
+    keep = 3686 / 4096
+    for (B, H, T) in ((2, 2, 256), (1, 3, 200), (2, 2, 84), (1, 4, 640)):
+        D, M = H * 64, B * T
+        words = ops.attn_dropout_mask_words(B, H, T)
+        rows = torch.zeros(words, dtype=torch.int32, device=dev); keys = torch.zeros(words, dtype=torch.int32, device=dev)
+        ops.attn_dropout_masks(rows, keys, p=0.1, site=6, seed=99, batch=B, heads=H, seq_len=T)
+        rows2 = torch.zeros_like(rows); keys2 = torch.zeros_like(keys)
+        ops.attn_dropout_masks(rows2, keys2, p=0.1, site=6, seed=99, batch=B, heads=H, seq_len=T)
+        mr, mk = ops.unpack_attn_row_mask(rows, B, H, T), ops.unpack_attn_dropout_mask(keys, B, H, T)
+        tri = torch.tril(torch.ones(T, T, dtype=torch.bool, device=dev))
+        same_layouts = bool(torch.equal(mr[:, :, tri], mk[:, :, tri]))
+        frac = mr[:, :, tri].float().mean().item()
+        ops.attn_dropout_masks(rows2, keys2, p=0.1, site=7, seed=99, batch=B, heads=H, seq_len=T)
+        other = not torch.equal(ops.unpack_attn_row_mask(rows2, B, H, T)[:, :, tri], mr[:, :, tri])
+        good = same_layouts and abs(frac - keep) < 0.01 and other
+        print(f"[{'OK' if good else 'FAIL'}] attn dropout masks B={B} H={H} T={T}: layouts agree={same_layouts} keep fraction={frac:.4f} (want {keep:.4f}) site-dependent={other}")
+        ok &= good
+        qkv = (torch.randn(M, 3 * D, device=dev) * 0.8).bfloat16()
+        d_out = (torch.randn(M, D, device=dev) * 0.5).bfloat16()
+        q0 = qkv[:, :D].float().clone().requires_grad_(True)
+        k0 = qkv[:, D:2 * D].float().clone().requires_grad_(True)
+        v0 = qkv[:, 2 * D:].float().clone().requires_grad_(True)
+        heads = lambda t: t.view(B, T, H, 64).transpose(1, 2)
+        sc = heads(q0) @ heads(k0).transpose(-1, -2) * 0.125 + torch.triu(torch.full((T, T), float("-inf"), device=dev), 1)
+        pm = sc.softmax(-1) * (mr & tri).float() / keep
+        o_ref = (pm @ heads(v0)).transpose(1, 2).reshape(M, D)
+        o_ref.backward(d_out.float())
+        out = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
+        lse = torch.full((H, B, ops.lse_pad(T)), float("nan"), device=dev)
+        ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125,
+                      lse_out=lse, drop_p=0.1, row_mask=rows)
+        ok &= report(f"attn fwd with dropout B={B} H={H} T={T}", out, o_ref.detach(), 2e-2)
+        dqkv = torch.full((M, 3 * D), 9.0, device=dev, dtype=torch.bfloat16)
+        acc = torch.empty(M, D, device=dev); delta = torch.empty(*lse.shape, 2, device=dev)
+        ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, d_out, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                          acc, delta, batch=B, heads=H, seq_len=T, causal=True, scale=0.125, drop_p=0.1, drop_mask=keys)
+        torch.cuda.synchronize()
+        ok &= report(f"attn_bwd with dropout dv B={B} H={H} T={T}", dqkv[:, 2 * D:], v0.grad, 3e-2)
+        ok &= report(f"attn_bwd with dropout dk B={B} H={H} T={T}", dqkv[:, D:2 * D], k0.grad, 3e-2)
+        ok &= report(f"attn_bwd with dropout dq B={B} H={H} T={T}", dqkv[:, :D], q0.grad, 3e-2)
+    return ok
+
+
 def case_xpos():
     ok = True
     for T in (5, 114, 2048):
