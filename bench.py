@@ -55,6 +55,9 @@ WORKLOADS = {
     "c3": dict(batch=8, images=1, positions=None, t_text=SEQ - N_LATENTS,
                name="configs[2]: full Kosmos forward (ViT-L/14 + perceiver + 24-layer decoder + LM head), B=8 per GPU, "
                     "seq=2048 (1984 text + 64 image latents), 1 image 224x224 per sequence"),
+    "strict": dict(batch=8, images=1, positions=None, t_text=2046 - N_LATENTS, seq=2046, max_positions=2048,
+                   name="configs[2] at the reference's own limit: its 2048-row position table (model.py:164) caps the spliced length at "
+                        "T = 2046 (SURVEY.md fact 6): B=8 per GPU, 1982 text + 64 image latents, 1 image 224x224 per sequence"),
     "c5": dict(batch=4, images=4, positions=[2, 450, 898, 1346], t_text=SEQ - 4 * N_LATENTS,
                name="configs[4]: interleaved 4 images/seq (perceiver + image-splice stress), B=4 per GPU, seq=2048 "
                     "(1792 text + 4x64 image latents at spliced rows 2/514/1026/1538)"),
@@ -149,7 +152,8 @@ def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0, wl=None):
     import kosmos_oracle as ko
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = ko.OracleConfig(max_positions=SEQ + 2, multiway=False)    # .B branches never execute
+    SEQ = wl.get("seq", 2048)
+    cfg = ko.OracleConfig(max_positions=wl.get("max_positions", SEQ + 2), multiway=False)    # .B branches never execute
     model = ko.build(cfg, seed=0)
     small = ko.make_inputs(cfg, 1, 50, seed=1)
     multi = wl["images"] > 1
@@ -182,7 +186,8 @@ def gpu_eager_reference(torch, wl, steps=3):
     here only as a baseline."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kosmos_oracle as ko
-    cfg = ko.OracleConfig(max_positions=SEQ + 2, multiway=False)
+    SEQ = wl.get("seq", 2048)
+    cfg = ko.OracleConfig(max_positions=wl.get("max_positions", SEQ + 2), multiway=False)
     with torch.device("cuda"):
         ref = ko.KosmosOracle(cfg)
     ref = ref.to(dtype=torch.bfloat16).eval()
@@ -217,9 +222,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps_done"], "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"].split(":")[0] + " sample: Kosmos.forward on 1 sequence, seq=2048 "
+        "config": {"workload": wl["name"].split(":")[0] + f" sample: Kosmos.forward on 1 sequence, seq={wl.get('seq', 2048)} "
                                f"({wl['t_text']} text + {wl['images']}x64 image latents), {wl['images']} image(s) 224x224, CPU",
-                   "global_batch": 1, "seq_len": SEQ, "parallelism": "cpu"},
+                   "global_batch": 1, "seq_len": wl.get("seq", 2048), "parallelism": "cpu"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -264,13 +269,15 @@ def run_gpu(args):
     peaks = _peaks()
     wl = WORKLOADS[args.workload]
     B, n_img, t_text = wl["batch"], wl["images"], wl["t_text"]
+    SEQ = wl.get("seq", 2048)                              # (shadows the module constant: the strict workload runs T = 2046)
+    max_pos = wl.get("max_positions", SEQ + 2)
     fkw = dict(image_positions=wl["positions"]) if n_img > 1 else {}
 
     numa = kdist.bind_host_thread_to_gpu(local)            # pinned buffers below land on the GPU's own NUMA node
     ldt = torch.bfloat16 if args.logits == "bf16" else torch.float32
     torch.manual_seed(0)                                   # same replicated random-init weights on every rank
     # graph_alias_output: the e2e loop below double-buffers the result itself (the D2H of step i overlaps step i+1)
-    model = Kosmos(config=KosmosConfig(max_positions=SEQ + 2), device=dev, cuda_graph=args.graph, graph_alias_output=True,
+    model = Kosmos(config=KosmosConfig(max_positions=max_pos), device=dev, cuda_graph=args.graph, graph_alias_output=True,
                    logits_dtype=ldt)
     g = torch.Generator().manual_seed(1 + rank)            # each rank owns its shard of the global batch
     h_text = torch.randint(0, VOCAB, (B, t_text), dtype=torch.long, generator=g).pin_memory()
@@ -395,8 +402,8 @@ def run_gpu(args):
     dec = model.decoder
     x = torch.randn(BATCH_PER_GPU * SEQ, 2048, device=dev)
     one = dec._pack()["layers"][:1]
-    dec_block_ms = _time_decoder_block(torch, dec, one, x, BATCH_PER_GPU)
-    flops_seq, dec_layer_flops = forward_flops_per_seq(images=n_img)
+    dec_block_ms = _time_decoder_block(torch, dec, one, x, BATCH_PER_GPU, SEQ)
+    flops_seq, dec_layer_flops = forward_flops_per_seq(T=SEQ, images=n_img)
     blk_tflops = dec_layer_flops * BATCH_PER_GPU / (dec_block_ms * 1e-3) / 1e12
 
     step_tflops = flops_seq * B / (ms_step * 1e-3) / 1e12        # per GPU
@@ -404,7 +411,7 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": wl["name"] + ", random-init weights, max_positions=2050",
+        "config": {"workload": wl["name"] + f", random-init weights, max_positions={max_pos}",
                    "global_batch": B * world, "seq_len": SEQ, "parallelism": f"dp{world}",
                    "l2": "no flush needed: each step streams 3.3 GB of weights and >10 GB of activations (L2 = 126 MB)",
                    "cuda_graph": bool(args.graph), "logits": args.logits},
@@ -421,7 +428,7 @@ def run_gpu(args):
                                            "frac": gemm_tflops / peaks["sustained"],
                                            "frac_of_burst": gemm_tflops / peaks["burst"], "share_of_step": gemm[3] / tot_ms}},
         "gemm_launch_types": gemm_shapes,
-        "decoder_block": {"config": "configs[1]: one decoder layer, B=8, T=2048, d=2048, 32 heads, bf16",
+        "decoder_block": {"config": f"configs[1]: one decoder layer, B=8, T={SEQ}, d=2048, 32 heads, bf16",
                           "ms": dec_block_ms, "tflops": blk_tflops, "frac_of_burst": blk_tflops / peaks["burst"],
                           "frac_of_sustained": blk_tflops / peaks["sustained"]},
         "breakdown": breakdown,
@@ -435,7 +442,7 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if args.train_leg and args.workload == "c3":
+    if args.train_leg and args.workload in ("c3",):
         # configs[3] beside the headline: the data-parallel training step on the same shapes (short run)
         del x, h_out, d_keep
         model._ws.clear(); model._graphs = {}; model.decoder._ws.clear()
@@ -612,7 +619,7 @@ def run_train(args):
     kdist.barrier()
 
 
-def _time_decoder_block(torch, dec, one_layer, x, B, iters=10):
+def _time_decoder_block(torch, dec, one_layer, x, B, SEQ, iters=10):
     """configs[1]: the per-layer launch sequence of Decoder.run_layers on one layer."""
     packed = dec._packed
     saved = packed["layers"]
@@ -645,7 +652,8 @@ def main():
                     "(bf16: the LM head's TMA-store epilogue writes 16-bit rows, as the reference run in 16-bit does; fp32: 2.1 GB per "
                     "GPU per step, the round-1 setting)")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["train"], help="c3 = configs[2] (the metric's "
-                    "configuration, default); c5 = configs[4], 4 images per sequence; train = configs[3], the training step")
+                    "configuration, default); strict = the same at the reference's position-table limit T = 2046; c5 = configs[4], "
+                    "4 images per sequence; train = configs[3], the training step")
     ap.add_argument("--optimizer", default="adamw", choices=["adamw", "lion"])
     ap.add_argument("--dropout", type=float, default=0.1, help="dropout = attention_dropout of the training step (reference: 0.1)")
     ap.add_argument("--reduce-bf16", type=int, default=1, help="exchange gradients in bf16 (default) or fp32 (0)")
