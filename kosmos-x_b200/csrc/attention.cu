@@ -37,16 +37,19 @@ attn_dropout_mask_kernel(unsigned long long seed, uint32_t site, uint32_t thr12,
     for (int c = 0; c < 4; ++c) w[c] = drop_keep32_attn(seed, site, thr12, q, static_cast<uint32_t>(kb * 4 + c), static_cast<uint32_t>(bh));
     const long long tile = (static_cast<long long>(bh) * nb + qb) * nb + kb;
     row_mask[tile * 128 + r] = make_uint4(w[0], w[1], w[2], w[3]);
+    // key-major copy: 32 x 32 bit-matrix transpose inside the warp (5 butterfly steps of one shuffle each) — lane b ends up
+    // with bit i = keep(query 32g + i, key 32c + b)
     uint32_t* dst = key_mask + tile * 512 + g * 128;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        uint32_t word = 0u;
+        uint32_t x = w[c], m = 0x0000ffffu;
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, (w[c] >> b) & 1u);
-            if (lane == b) word = bal;
+        for (int j = 16; j >= 1; j >>= 1) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            x = (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
+            if (j > 1) m ^= m << (j >> 1);
         }
-        dst[c * 32 + lane] = word;
+        dst[c * 32 + lane] = x;
     }
 }
 }  // namespace kx

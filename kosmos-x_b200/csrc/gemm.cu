@@ -520,7 +520,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // previous unit's store has finished reading it; the second warp on the SM sub-partition covers that latency.
             uint8_t* st_main = smem_epi + ew * EPI_WARP_BYTES;
             uint8_t* st_copy = st_main + EPI_STAGE_BYTES;
-            uint64_t* rbar = resbar + ew;
             const bool has_res = (ep.res != nullptr);
             const bool has_copy = OUT_F32 && (ep.out2 != nullptr);
             const bool has_stats = (ep.stats_out != nullptr);
@@ -567,12 +566,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (mr < ep.M && nc < ep.N) tma_prefetch_l2_2d(&tmRes, nc, mr);
                     }
                 }
-                auto issue_res = [&](int c) {               // residual sub-tile of chunk c -> main (freed by wait_main_free)
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(rbar, EPI_STAGE_BYTES);
-                        tma_load_2d(&tmRes, rbar, st_main, nb + c * 32, m_row0);
+                // The residual sub-tile travels global -> REGISTERS (each thread owns one 128-byte row segment per chunk),
+                // requested one chunk ahead, so its latency is covered by the previous chunk's math and store.  (Round 1
+                // brought it in by TMA into the single staging buffer: the load could not be issued before the previous
+                // store had drained that buffer, which left 2.5-4 k idle cycles per chunk in the out_proj epilogue —
+                // profiles/r1_gemm_epilogue_trace_outproj_8warps.txt.)  `res` may alias `out`: plain loads, never .nc.
+                float rn[32];
+                auto load_res = [&](int c) {
+                    const int n0r = nb + c * 32;
+                    if (m < ep.M) {
+                        const float* rp = ep.res + static_cast<long long>(m) * ep.ld_res + n0r;
+                        if (n0r + 32 <= ep.N) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                const float4 x = __ldcg(reinterpret_cast<const float4*>(rp + 4 * g));     // L2 only: streamed once
+                                rn[4 * g] = x.x; rn[4 * g + 1] = x.y; rn[4 * g + 2] = x.z; rn[4 * g + 3] = x.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) rn[i] = (n0r + i < ep.N) ? __ldcg(rp + i) : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) rn[i] = 0.f;
                     }
                 };
+                if (has_res && rows_ok && c_begin < nchunks) load_res(c_begin);
                 KX_GT(it, 0, 1);
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
@@ -585,32 +604,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int n0 = nb + c * 32;
                     KX_GT(it, c, 3);
                     const bool unit_start = OUT_F32 || !(c & 1);
-                    if (rows_ok && has_res) {                // residual: the buffer must be free before the load is issued
-                        wait_main_free();
-                        issue_res(c);
-                    }
                     KX_GT(it, c, 4);
-                    float f[32];
+                    float f[32], rc[32];
                     tmem_ld_wait();
                     KX_GT(it, c, 5);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                     if (c + 1 < nchunks) tmem_ld32(taddr + (c + 1) * 32, v);      // in flight during this chunk's math
                     if (!rows_ok) continue;
+                    if (has_res) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) rc[i] = rn[i];
+                        if (c + 1 < nchunks) load_res(c + 1);                     // next chunk's residual: in flight from here on
+                    }
                     const bool full = n0 + 32 <= ep.N;
                     epilogue_math<EPI>(ep, f, m, n0, full, ln, s_vec + c * 32, s_vec + BN + c * 32);
                     KX_GT(it, c, 6);
                     uint8_t* mb = st_main + lane * 128;
-                    if (unit_start && !has_res) wait_main_free();      // after the math: the previous store has had time to drain
+                    if (unit_start) wait_main_free();                  // after the math: the previous store has had time to drain
                     if constexpr (OUT_F32) {
                         if (has_res) {
-                            mbar_wait(rbar, unit & 1);
                             KX_GT(it, c, 7);
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                const float4 x = *reinterpret_cast<const float4*>(mb + ((g ^ sw) << 4));
-                                f[4 * g] += x.x; f[4 * g + 1] += x.y; f[4 * g + 2] += x.z; f[4 * g + 3] += x.w;
-                            }
+                            for (int i = 0; i < 32; ++i) f[i] += rc[i];
                         }
 #pragma unroll
                         for (int g = 0; g < 8; ++g)
@@ -900,7 +916,7 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     // otherwise (LM head with ld = 32002, image_proj / patch-embed row scatter) direct predicated stores
     bool tma_epi = (g->grp_rows == 0) && (g->add_tab == nullptr) && ((g->ld_out * esz) % 16 == 0) &&
                    ((reinterpret_cast<uintptr_t>(g->out) & 15) == 0);
-    if (g->res) tma_epi = tma_epi && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
+    if (g->res) tma_epi = tma_epi && g->out_f32 && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
     if (g->epi_mode == 1) tma_epi = false;
     ep.tma_store = tma_epi ? 1 : 0;
     // fp32 rows that are only 8-byte aligned (LM head: ld = 32002) still take the staged kernel, which then writes
