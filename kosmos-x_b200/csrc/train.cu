@@ -246,7 +246,7 @@ layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
         for (int u = 0; u < 8; ++u) pa[u] = 0.f;
     }
     if (live) {
-        load8(gamma + col, gm);
+        if constexpr (!GELU) load8(gamma + col, gm);
         if constexpr (PRE_ADD) {
             if (pre_add != nullptr) load8(pre_add + col, pa);
         }
@@ -257,6 +257,98 @@ layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
         const int s = it % LNB_STAGES;
         const uint8_t* st = lnb_smem + static_cast<size_t>(s) * stage_bytes;
         mbar_wait_lean(&full[s], (it / LNB_STAGES) & 1);
+        if constexpr (GELU) {
+            // ---- LN(gelu(u)) backward on packed f32x2 pairs (FFMA2 / FMUL2 / FADD2): the n = 8192 launch was issue-bound at
+            // ~40 scalar instructions per element (ncu: 2.1 TB/s, 33 % of the copy bandwidth); the pair form issues ~half of them.
+            // live across the block reduction: x, dy, Phi(x) (24 registers) — a = x * Phi(x) is recomputed and gamma re-read
+            // from L1 after it, or the 64-register budget of a 1024-thread CTA spills
+            uint64_t x2[4], d2[4], c2[4];
+            {
+                uint4 qx = make_uint4(0u, 0u, 0u, 0u), qd = make_uint4(0u, 0u, 0u, 0u);
+                if (live) {
+                    qx = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(st) + col);
+                    qd = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(st + x_bytes) + col);
+                }
+                const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {       // bf16x2 -> f32x2: the low element is the word shifted up, the high one masked
+                    x2[p] = pack_f32x2(__uint_as_float(wx[p] << 16), __uint_as_float(wx[p] & 0xffff0000u));
+                    d2[p] = pack_f32x2(__uint_as_float(wd[p] << 16), __uint_as_float(wd[p] & 0xffff0000u));
+                }
+            }
+            uint64_t s1p = 0ull, s2p = 0ull, sgp = 0ull, sgap = 0ull;
+            const uint64_t kz = pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float xl, xh_;
+                unpack_f32x2(x2[p], xl, xh_);
+                const uint64_t z = fmul2(pack_f32x2(fabsf(xl), fabsf(xh_)), kz);
+                uint64_t q = ffma2(z, pack_f32x2(-0.003024620935320854f, -0.003024620935320854f),
+                                   pack_f32x2(0.029882797971367836f, 0.029882797971367836f));
+                q = ffma2(q, z, pack_f32x2(-0.14901681244373322f, -0.14901681244373322f));
+                q = ffma2(q, z, pack_f32x2(-0.9183504581451416f, -0.9183504581451416f));
+                q = ffma2(q, z, pack_f32x2(-1.6279104948043823f, -1.6279104948043823f));
+                q = fmul2(q, z);
+                float q0, q1;
+                unpack_f32x2(q, q0, q1);
+                // Phi(x) = 0.5 + copysign(0.5 - 0.5 * erfc(|x| / sqrt2), x)
+                const uint64_t h = ffma2(pack_f32x2(ex2_approx(q0), ex2_approx(q1)), pack_f32x2(-0.5f, -0.5f), pack_f32x2(0.5f, 0.5f));
+                float h0, h1;
+                unpack_f32x2(h, h0, h1);
+                c2[p] = fadd2(pack_f32x2(copysignf(h0, xl), copysignf(h1, xh_)), pack_f32x2(0.5f, 0.5f));
+                const uint64_t av = fmul2(x2[p], c2[p]);
+                const float2 g2 = live ? __ldg(reinterpret_cast<const float2*>(gamma + col) + p) : make_float2(0.f, 0.f);
+                const uint64_t gv = fmul2(d2[p], pack_f32x2(g2.x, g2.y));
+                s1p = fadd2(s1p, av);
+                s2p = ffma2(av, av, s2p);
+                sgp = fadd2(sgp, gv);
+                sgap = ffma2(gv, av, sgap);
+            }
+            float s1, s2, sg, sga, t0, t1;
+            unpack_f32x2(s1p, t0, t1); s1 = t0 + t1;
+            unpack_f32x2(s2p, t0, t1); s2 = t0 + t1;
+            unpack_f32x2(sgp, t0, t1); sg = t0 + t1;
+            unpack_f32x2(sgap, t0, t1); sga = t0 + t1;
+            block_sum4_t<THREADS>(s1, s2, sg, sga, red);     // (its barriers also order this row's smem reads before the refill)
+            if (threadIdx.x == 0) {
+                const int nxt = row + LNB_STAGES * gridDim.x;
+                if (nxt < rows) issue(nxt, s);
+            }
+            const float mean = s1 * inv_n;
+            const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
+            const float mg = sg * inv_n;
+            const float mgx = rstd * (sga - mean * sg) * inv_n;       // mean(g * xhat)
+            if (live) {
+                const uint64_t rs2 = pack_f32x2(rstd, rstd), nmr2 = pack_f32x2(-mean * rstd, -mean * rstd);
+                const uint64_t nmg2 = pack_f32x2(-mg, -mg), nmgx2 = pack_f32x2(-mgx, -mgx);
+                uint32_t ow[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const uint64_t xh = ffma2(fmul2(x2[p], c2[p]), rs2, nmr2);                           // xhat
+                    const float2 g2 = __ldg(reinterpret_cast<const float2*>(gamma + col) + p);
+                    const uint64_t gv = fmul2(d2[p], pack_f32x2(g2.x, g2.y));
+                    uint64_t o = fmul2(ffma2(xh, nmgx2, fadd2(gv, nmg2)), rs2);                          // LayerNorm backward
+                    const uint64_t xx = fmul2(fmul2(x2[p], x2[p]), pack_f32x2(-0.72134752044448170368f, -0.72134752044448170368f));
+                    float e0, e1;
+                    unpack_f32x2(xx, e0, e1);
+                    const uint64_t pdf = fmul2(pack_f32x2(ex2_approx(e0), ex2_approx(e1)), pack_f32x2(0.3989422804014327f, 0.3989422804014327f));
+                    o = fmul2(o, ffma2(x2[p], pdf, c2[p]));                                              // * gelu'(x) = Phi + x phi
+                    float o0, o1, v0, v1;
+                    unpack_f32x2(o, o0, o1);
+                    ow[p] = pack_bf16(o0, o1);
+                    unpack_f32x2(ffma2(d2[p], xh, pack_f32x2(acc_g[2 * p], acc_g[2 * p + 1])), v0, v1);
+                    acc_g[2 * p] = v0; acc_g[2 * p + 1] = v1;
+                    unpack_f32x2(fadd2(d2[p], pack_f32x2(acc_b[2 * p], acc_b[2 * p + 1])), v0, v1);
+                    acc_b[2 * p] = v0; acc_b[2 * p + 1] = v1;
+                    // column sums of what the next GEMM reads: the bf16-rounded values
+                    acc_c[2 * p] += __uint_as_float(ow[p] << 16);
+                    acc_c[2 * p + 1] += __uint_as_float(ow[p] & 0xffff0000u);
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dx_out) + static_cast<long long>(row) * ld_dx + col) =
+                    make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            continue;
+        }
         float xr[8], d[8], r[DX_F32 ? 8 : 1], a[8], cdf[GELU ? 8 : 1];
 #pragma unroll
         for (int u = 0; u < 8; ++u) { xr[u] = 0.f; d[u] = 0.f; }
