@@ -46,15 +46,20 @@ constexpr int EPI_WARPS = 8;       // two per SM sub-partition: warp e handles T
 // prefetched the same way.  Costs 16 KB of staging per epilogue warp, taken from the operand ring.
 constexpr int EPI_STAGE_BYTES = 32 * 128;                    // 32 rows x 128 B
 constexpr int EPI_WARP_BYTES = 2 * EPI_STAGE_BYTES;          // main 4 KB + copy[2] x 2 KB
+// RESBUF: a third 4 KB buffer per epilogue warp receives the fp32 residual sub-tile, so the residual of chunk c+1 is in
+// flight while chunk c is computed and stored (with the shared buffer the load could not be issued before the previous
+// store had drained it: 2.5-4 k idle cycles per chunk in the out_proj epilogue, profiles/r1_gemm_epilogue_trace_outproj_8warps.txt).
+// Paid for with one operand stage (ring 160 -> 128 KB).
 
-template <int CG, int BN, bool TMA_EPI>
+template <int CG, int BN, bool TMA_EPI, bool RESBUF = false>
 struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_ROWS = BN / CG;
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = TMA_EPI ? EPI_WARPS * EPI_WARP_BYTES : 0;
-    static constexpr int RING_BUDGET = TMA_EPI ? (160 * 1024) : (192 * 1024);
+    static constexpr int EPI_PER_WARP = EPI_WARP_BYTES + (RESBUF ? EPI_STAGE_BYTES : 0);
+    static constexpr int EPI_BYTES = TMA_EPI ? EPI_WARPS * EPI_PER_WARP : 0;
+    static constexpr int RING_BUDGET = TMA_EPI ? (RESBUF ? 128 * 1024 : 160 * 1024) : (192 * 1024);
     static constexpr int STAGES = RING_BUDGET / STAGE_BYTES;
     static constexpr int VEC_BYTES = TMA_EPI ? 2 * BN * 4 : 0;   // this tile's bias[] and ln_c[] columns, staged once per tile
     static constexpr int BAR_BYTES = 512;                       // (2*STAGES + 4 + 16) mbarriers + the TMEM slot; STAGES <= 8
@@ -328,12 +333,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t
 // wgrad dW = dY^T . X (both operands [K', *]) need no transposed copies.
 constexpr int MN_ATOM_BYTES = 64 * 128;
 
-template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false>
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false, bool RESBUF = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmOut2, const GemmEpi ep) {
-    using Cfg = GemmCfg<CG, BN, TMA_EPI>;
+    using Cfg = GemmCfg<CG, BN, TMA_EPI, RESBUF>;
     constexpr int STAGES = Cfg::STAGES;
     // SWIZZLE_128B atoms need 1024-byte alignment (identical offset in both CTAs of a pair); the kernel has no
     // static shared memory, so the dynamic window starts at the aligned base of the CTA's allocation.
@@ -518,8 +523,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // One cp.async.bulk group per store.  `main` is single-buffered: before it is overwritten (by the residual
             // load at unit start, or by the first write of the unit, which comes after the math) lane 0 waits until the
             // previous unit's store has finished reading it; the second warp on the SM sub-partition covers that latency.
-            uint8_t* st_main = smem_epi + ew * EPI_WARP_BYTES;
+            uint8_t* st_main = smem_epi + ew * Cfg::EPI_PER_WARP;
             uint8_t* st_copy = st_main + EPI_STAGE_BYTES;
+            uint8_t* st_res = RESBUF ? st_main + EPI_WARP_BYTES : st_main;      // RESBUF: the residual has its own buffer
+            uint64_t* rbar = resbar + ew;
             const bool has_res = (ep.res != nullptr);
             const bool has_copy = OUT_F32 && (ep.out2 != nullptr);
             const bool has_stats = (ep.stats_out != nullptr);
@@ -566,32 +573,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (mr < ep.M && nc < ep.N) tma_prefetch_l2_2d(&tmRes, nc, mr);
                     }
                 }
-                // The residual sub-tile travels global -> REGISTERS (each thread owns one 128-byte row segment per chunk),
-                // requested one chunk ahead, so its latency is covered by the previous chunk's math and store.  (Round 1
-                // brought it in by TMA into the single staging buffer: the load could not be issued before the previous
-                // store had drained that buffer, which left 2.5-4 k idle cycles per chunk in the out_proj epilogue —
-                // profiles/r1_gemm_epilogue_trace_outproj_8warps.txt.)  `res` may alias `out`: plain loads, never .nc.
-                float rn[32];
-                auto load_res = [&](int c) {
-                    const int n0r = nb + c * 32;
-                    if (m < ep.M) {
-                        const float* rp = ep.res + static_cast<long long>(m) * ep.ld_res + n0r;
-                        if (n0r + 32 <= ep.N) {
-#pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                const float4 x = __ldcg(reinterpret_cast<const float4*>(rp + 4 * g));     // L2 only: streamed once
-                                rn[4 * g] = x.x; rn[4 * g + 1] = x.y; rn[4 * g + 2] = x.z; rn[4 * g + 3] = x.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) rn[i] = (n0r + i < ep.N) ? __ldcg(rp + i) : 0.f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) rn[i] = 0.f;
+                auto issue_res = [&](int c) {               // residual sub-tile of chunk c -> st_res (= main unless RESBUF)
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(rbar, EPI_STAGE_BYTES);
+                        tma_load_2d(&tmRes, rbar, st_res, nb + c * 32, m_row0);
                     }
                 };
-                if (has_res && rows_ok && c_begin < nchunks) load_res(c_begin);
+                if constexpr (RESBUF) {                     // first chunk's residual: on its way during the wait for the MMAs
+                    if (rows_ok && has_res && c_begin < nchunks) issue_res(c_begin);
+                }
                 KX_GT(it, 0, 1);
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
@@ -604,29 +594,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int n0 = nb + c * 32;
                     KX_GT(it, c, 3);
                     const bool unit_start = OUT_F32 || !(c & 1);
+                    if constexpr (!RESBUF) {
+                        if (rows_ok && has_res) {            // residual: the buffer must be free before the load is issued
+                            wait_main_free();
+                            issue_res(c);
+                        }
+                    }
                     KX_GT(it, c, 4);
-                    float f[32], rc[32];
+                    float f[32];
                     tmem_ld_wait();
                     KX_GT(it, c, 5);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                     if (c + 1 < nchunks) tmem_ld32(taddr + (c + 1) * 32, v);      // in flight during this chunk's math
                     if (!rows_ok) continue;
-                    if (has_res) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) rc[i] = rn[i];
-                        if (c + 1 < nchunks) load_res(c + 1);                     // next chunk's residual: in flight from here on
-                    }
                     const bool full = n0 + 32 <= ep.N;
                     epilogue_math<EPI>(ep, f, m, n0, full, ln, s_vec + c * 32, s_vec + BN + c * 32);
                     KX_GT(it, c, 6);
                     uint8_t* mb = st_main + lane * 128;
-                    if (unit_start) wait_main_free();                  // after the math: the previous store has had time to drain
+                    if (unit_start && (RESBUF || !has_res)) wait_main_free();      // after the math: the previous store has had time to drain
                     if constexpr (OUT_F32) {
                         if (has_res) {
+                            mbar_wait(rbar, unit & 1);
                             KX_GT(it, c, 7);
+                            const uint8_t* rb = st_res + lane * 128;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) f[i] += rc[i];
+                            for (int g = 0; g < 8; ++g) {
+                                const float4 x = *reinterpret_cast<const float4*>(rb + ((g ^ sw) << 4));
+                                f[4 * g] += x.x; f[4 * g + 1] += x.y; f[4 * g + 2] += x.z; f[4 * g + 3] += x.w;
+                            }
+                            if constexpr (RESBUF) {          // every lane has read the buffer: the next chunk's residual may land in it
+                                __syncwarp();
+                                if (c + 1 < nchunks) issue_res(c + 1);
+                            }
                         }
 #pragma unroll
                         for (int g = 0; g < 8; ++g)
@@ -777,10 +777,10 @@ bool make_tmap_f32_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
     return make_tmap_2d(tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
-template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false>
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false, bool RESBUF = false>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmEpi& ep, int max_ctas,
                        cudaStream_t stream) {
-    using Cfg = GemmCfg<CG, BN, TMA_EPI>;
+    using Cfg = GemmCfg<CG, BN, TMA_EPI, RESBUF>;
     CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
     if constexpr (!ATR) { if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP; }
     else { if (!make_tmap_2d(&tmA, A, ep.M, ep.K, lda * 2, 64, BLOCK_K)) return KX_ERR_TMAP; }       // A given as [K, M]
@@ -810,7 +810,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
         tmRes = tmA;
         tmOut2 = tmA;
     }
-    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI, ATR, BTR>;
+    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI, ATR, BTR, RESBUF>;
     static std::once_flag attr_once;   // per template instantiation; safe when several host threads launch GEMMs
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
@@ -916,7 +916,8 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     // otherwise (LM head with ld = 32002, image_proj / patch-embed row scatter) direct predicated stores
     bool tma_epi = (g->grp_rows == 0) && (g->add_tab == nullptr) && ((g->ld_out * esz) % 16 == 0) &&
                    ((reinterpret_cast<uintptr_t>(g->out) & 15) == 0);
-    if (g->res) tma_epi = tma_epi && g->out_f32 && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
+    if (g->res) tma_epi = tma_epi && ((g->ld_res * 4) % 16 == 0) && ((reinterpret_cast<uintptr_t>(g->res) & 15) == 0);
+    if (g->res && !g->out_f32) tma_epi = false;       // (the staged bf16 store path carries no residual)
     if (g->epi_mode == 1) tma_epi = false;
     ep.tma_store = tma_epi ? 1 : 0;
     // fp32 rows that are only 8-byte aligned (LM head: ld = 32002) still take the staged kernel, which then writes
@@ -945,6 +946,16 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
         if (big) { if (g->a_trans) KX_GEMM_TR(2, 256, true) else KX_GEMM_TR(2, 256, false) }
         else { if (g->a_trans) KX_GEMM_TR(1, 128, true) else KX_GEMM_TR(1, 128, false) }
 #undef KX_GEMM_TR
+    }
+    // residual GEMMs of the forward (out_proj, fc2, ViT / perceiver residual Linears): staged epilogue with the residual's own
+    // buffer; epi_mode 3 keeps the shared-buffer form (A/B measurements, tools/kernel_check.py bench_resbuf)
+    if (tma_epi && ep.tma_store && g->res && g->out_f32 && g->epi == KX_EPI_GENERIC && g->epi_mode != 3 && (cg == 2 || bn == 128)) {
+#define KX_GEMM_RB(CG_, BN_) \
+        if (cg == CG_ && bn == BN_) return launch_gemm<CG_, BN_, true, KX_EPI_GENERIC, true, false, false, true>(A, lda, W, ldw, ep, max_ctas, stream);
+        KX_GEMM_RB(1, 128)
+        KX_GEMM_RB(2, 128)
+        KX_GEMM_RB(2, 256)
+#undef KX_GEMM_RB
     }
 #define KX_GEMM_CASE2(CG_, BN_, T_)                                                                          \
     {                                                                                                        \
