@@ -76,8 +76,7 @@ typedef struct kx_gemm_args {
     int cta_group;                /* 0 = auto, 1 = single CTA tiles, 2 = cta_group::2 pairs */
     int block_n;                  /* 0 = auto, 128 or 256 */
     int max_ctas;                 /* 0 = all SMs */
-    int epi_mode;                 /* 0 = auto (staged TMA-store epilogue when alignment allows), 1 = direct stores,
-                                   * 3 = staged, residual through the shared staging buffer (round-1 form, kept for A/B timing) */
+    int epi_mode;                 /* 0 = auto (staged TMA-store epilogue when alignment allows), 1 = direct stores */
     /* LayerNorm folded into this GEMM (consumer side).  A holds the RAW (un-normalised) rows,
      * W must already be W*diag(gamma), bias must be W.beta + b, and
      *     out = rstd[m] * (A.W^T - mean[m] * ln_c[n]) + bias[n] ...

@@ -46,20 +46,15 @@ constexpr int EPI_WARPS = 8;       // two per SM sub-partition: warp e handles T
 // prefetched the same way.  Costs 16 KB of staging per epilogue warp, taken from the operand ring.
 constexpr int EPI_STAGE_BYTES = 32 * 128;                    // 32 rows x 128 B
 constexpr int EPI_WARP_BYTES = 2 * EPI_STAGE_BYTES;          // main 4 KB + copy[2] x 2 KB
-// RESBUF: a third 4 KB buffer per epilogue warp receives the fp32 residual sub-tile, so the residual of chunk c+1 is in
-// flight while chunk c is computed and stored (with the shared buffer the load could not be issued before the previous
-// store had drained it: 2.5-4 k idle cycles per chunk in the out_proj epilogue, profiles/r1_gemm_epilogue_trace_outproj_8warps.txt).
-// Paid for with one operand stage (ring 160 -> 128 KB).
 
-template <int CG, int BN, bool TMA_EPI, bool RESBUF = false>
+template <int CG, int BN, bool TMA_EPI>
 struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_ROWS = BN / CG;
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_PER_WARP = EPI_WARP_BYTES + (RESBUF ? EPI_STAGE_BYTES : 0);
-    static constexpr int EPI_BYTES = TMA_EPI ? EPI_WARPS * EPI_PER_WARP : 0;
-    static constexpr int RING_BUDGET = TMA_EPI ? (RESBUF ? 128 * 1024 : 160 * 1024) : (192 * 1024);
+    static constexpr int EPI_BYTES = TMA_EPI ? EPI_WARPS * EPI_WARP_BYTES : 0;
+    static constexpr int RING_BUDGET = TMA_EPI ? (160 * 1024) : (192 * 1024);
     static constexpr int STAGES = RING_BUDGET / STAGE_BYTES;
     static constexpr int VEC_BYTES = TMA_EPI ? 2 * BN * 4 : 0;   // this tile's bias[] and ln_c[] columns, staged once per tile
     static constexpr int BAR_BYTES = 512;                       // (2*STAGES + 4 + 16) mbarriers + the TMEM slot; STAGES <= 8
@@ -333,12 +328,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, const uint32_t
 // wgrad dW = dY^T . X (both operands [K', *]) need no transposed copies.
 constexpr int MN_ATOM_BYTES = 64 * 128;
 
-template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false, bool RESBUF = false>
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmOut2, const GemmEpi ep) {
-    using Cfg = GemmCfg<CG, BN, TMA_EPI, RESBUF>;
+    using Cfg = GemmCfg<CG, BN, TMA_EPI>;
     constexpr int STAGES = Cfg::STAGES;
     // SWIZZLE_128B atoms need 1024-byte alignment (identical offset in both CTAs of a pair); the kernel has no
     // static shared memory, so the dynamic window starts at the aligned base of the CTA's allocation.
@@ -520,12 +515,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             //   fp32 out: unit = one 32-column chunk.  With a residual, `main` first receives the residual sub-tile
             //             by TMA (issued at unit start, landing during the TMEM load and the math) and is updated IN PLACE.
             //   bf16 out: unit = two chunks (64 columns = 128-byte rows).
+            // (Round 2 measured two alternatives for the residual and kept this form: a dedicated third buffer per warp so that
+            // the residual of chunk c+1 lands while chunk c is stored, paid for with one operand stage — out_proj 136.7 us against
+            // 127.8 us here; and plain row loads into registers one chunk ahead — 254 us, the per-thread 128-byte row segments
+            // cost 32 L1 wavefronts per load instruction.  profiles/r2_gemm_epilogue_experiments.md.)
             // One cp.async.bulk group per store.  `main` is single-buffered: before it is overwritten (by the residual
             // load at unit start, or by the first write of the unit, which comes after the math) lane 0 waits until the
             // previous unit's store has finished reading it; the second warp on the SM sub-partition covers that latency.
-            uint8_t* st_main = smem_epi + ew * Cfg::EPI_PER_WARP;
+            uint8_t* st_main = smem_epi + ew * EPI_WARP_BYTES;
             uint8_t* st_copy = st_main + EPI_STAGE_BYTES;
-            uint8_t* st_res = RESBUF ? st_main + EPI_WARP_BYTES : st_main;      // RESBUF: the residual has its own buffer
             uint64_t* rbar = resbar + ew;
             const bool has_res = (ep.res != nullptr);
             const bool has_copy = OUT_F32 && (ep.out2 != nullptr);
@@ -573,15 +571,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (mr < ep.M && nc < ep.N) tma_prefetch_l2_2d(&tmRes, nc, mr);
                     }
                 }
-                auto issue_res = [&](int c) {               // residual sub-tile of chunk c -> st_res (= main unless RESBUF)
+                auto issue_res = [&](int c) {               // residual sub-tile of chunk c -> main (freed by wait_main_free)
                     if (lane == 0) {
                         mbar_arrive_expect_tx(rbar, EPI_STAGE_BYTES);
-                        tma_load_2d(&tmRes, rbar, st_res, nb + c * 32, m_row0);
+                        tma_load_2d(&tmRes, rbar, st_main, nb + c * 32, m_row0);
                     }
                 };
-                if constexpr (RESBUF) {                     // first chunk's residual: on its way during the wait for the MMAs
-                    if (rows_ok && has_res && c_begin < nchunks) issue_res(c_begin);
-                }
                 KX_GT(it, 0, 1);
                 mbar_wait(&tfull[a], aph);
                 tc_fence_after();
@@ -594,11 +589,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int n0 = nb + c * 32;
                     KX_GT(it, c, 3);
                     const bool unit_start = OUT_F32 || !(c & 1);
-                    if constexpr (!RESBUF) {
-                        if (rows_ok && has_res) {            // residual: the buffer must be free before the load is issued
-                            wait_main_free();
-                            issue_res(c);
-                        }
+                    if (rows_ok && has_res) {                // residual: the buffer must be free before the load is issued
+                        wait_main_free();
+                        issue_res(c);
                     }
                     KX_GT(it, c, 4);
                     float f[32];
@@ -612,20 +605,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     epilogue_math<EPI>(ep, f, m, n0, full, ln, s_vec + c * 32, s_vec + BN + c * 32);
                     KX_GT(it, c, 6);
                     uint8_t* mb = st_main + lane * 128;
-                    if (unit_start && (RESBUF || !has_res)) wait_main_free();      // after the math: the previous store has had time to drain
+                    if (unit_start && !has_res) wait_main_free();      // after the math: the previous store has had time to drain
                     if constexpr (OUT_F32) {
                         if (has_res) {
                             mbar_wait(rbar, unit & 1);
                             KX_GT(it, c, 7);
-                            const uint8_t* rb = st_res + lane * 128;
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
-                                const float4 x = *reinterpret_cast<const float4*>(rb + ((g ^ sw) << 4));
+                                const float4 x = *reinterpret_cast<const float4*>(mb + ((g ^ sw) << 4));
                                 f[4 * g] += x.x; f[4 * g + 1] += x.y; f[4 * g + 2] += x.z; f[4 * g + 3] += x.w;
-                            }
-                            if constexpr (RESBUF) {          // every lane has read the buffer: the next chunk's residual may land in it
-                                __syncwarp();
-                                if (c + 1 < nchunks) issue_res(c + 1);
                             }
                         }
 #pragma unroll
@@ -777,10 +765,10 @@ bool make_tmap_f32_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
     return make_tmap_2d(tm, ptr, inner, outer, row_stride_bytes, box_inner, box_outer, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
-template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false, bool RESBUF = false>
+template <int CG, int BN, bool OUT_F32, int EPI, bool TMA_EPI, bool ATR = false, bool BTR = false>
 static int launch_gemm(const void* A, long long lda, const void* W, long long ldw, const GemmEpi& ep, int max_ctas,
                        cudaStream_t stream) {
-    using Cfg = GemmCfg<CG, BN, TMA_EPI, RESBUF>;
+    using Cfg = GemmCfg<CG, BN, TMA_EPI>;
     CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
     if constexpr (!ATR) { if (!make_tmap_2d(&tmA, A, ep.K, ep.M, lda * 2, BLOCK_K, BLOCK_M)) return KX_ERR_TMAP; }
     else { if (!make_tmap_2d(&tmA, A, ep.M, ep.K, lda * 2, 64, BLOCK_K)) return KX_ERR_TMAP; }       // A given as [K, M]
@@ -810,7 +798,7 @@ static int launch_gemm(const void* A, long long lda, const void* W, long long ld
         tmRes = tmA;
         tmOut2 = tmA;
     }
-    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI, ATR, BTR, RESBUF>;
+    auto kern = gemm_bf16_kernel<CG, BN, OUT_F32, EPI, TMA_EPI, ATR, BTR>;
     static std::once_flag attr_once;   // per template instantiation; safe when several host threads launch GEMMs
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
@@ -946,16 +934,6 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
         if (big) { if (g->a_trans) KX_GEMM_TR(2, 256, true) else KX_GEMM_TR(2, 256, false) }
         else { if (g->a_trans) KX_GEMM_TR(1, 128, true) else KX_GEMM_TR(1, 128, false) }
 #undef KX_GEMM_TR
-    }
-    // residual GEMMs of the forward (out_proj, fc2, ViT / perceiver residual Linears): staged epilogue with the residual's own
-    // buffer; epi_mode 3 keeps the shared-buffer form (A/B measurements, tools/kernel_check.py bench_resbuf)
-    if (tma_epi && ep.tma_store && g->res && g->out_f32 && g->epi == KX_EPI_GENERIC && g->epi_mode != 3 && (cg == 2 || bn == 128)) {
-#define KX_GEMM_RB(CG_, BN_) \
-        if (cg == CG_ && bn == BN_) return launch_gemm<CG_, BN_, true, KX_EPI_GENERIC, true, false, false, true>(A, lda, W, ldw, ep, max_ctas, stream);
-        KX_GEMM_RB(1, 128)
-        KX_GEMM_RB(2, 128)
-        KX_GEMM_RB(2, 256)
-#undef KX_GEMM_RB
     }
 #define KX_GEMM_CASE2(CG_, BN_, T_)                                                                          \
     {                                                                                                        \

@@ -857,31 +857,6 @@ def case_bench_vit():
     return True
 
 
-def case_bench_resbuf():
-    """A/B of the residual GEMM epilogue: epi_mode 0 (the residual sub-tile has its own staging buffer, 4 operand stages) against
-    epi_mode 3 (round-1 form: shared staging buffer, 5 stages), with the model's full epilogue (LayerNorm fold, +bias, +residual
-    in place, bf16 copy, row statistics) at the decoder and ViT shapes."""
-    torch.manual_seed(0)
-    for M, N, K, fold in ((16384, 2048, 2048, True), (16384, 2048, 8192, True), (2056, 1024, 1024, False), (2056, 1024, 4096, False)):
-        a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
-        bias = torch.randn(N, device=dev); c = w.float().sum(1).contiguous()
-        x = torch.randn(M, N, device=dev); xb = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        part = torch.zeros(1, M, 2, device=dev); part[0, :, 1] = float(K)          # mean 0, var 1
-        bn = 256 if M > 4096 else 128
-        st = torch.empty((N + bn // 2 - 1) // (bn // 2), M, 2, device=dev)
-        outs = {}
-        for mode in (0, 3):
-            xi = x.clone()
-            fn = lambda: ops.gemm(a, w, xi, bias=bias, res=xi, ln=(part, c, K, 1e-5) if fold else None, stats_out=st, out2=xb, epi_mode=mode, block_n=bn)
-            fn(); torch.cuda.synchronize()
-            outs[mode] = (xi.clone(), xb.clone(), st.clone())
-            ms = _time(fn, iters=30)
-            print(f"resbuf A/B {M}x{N}x{K} epi_mode={mode} ({'own residual buffer' if mode == 0 else 'shared buffer (r1)'}): {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.0f} TFLOP/s")
-        same = all(torch.equal(p, q) for p, q in zip(outs[0], outs[3]))
-        print(f"[{'OK' if same else 'FAIL'}] both epilogue forms bit-identical at {M}x{N}x{K}")
-    return True
-
-
 def case_bench_attn():
     for B, H, T, causal in ((8, 32, 2048, True), (8, 32, 1024, True), (8, 32, 4096, True), (8, 32, 256, True),
                             (8, 16, 257, False), (1, 32, 114, True)):
