@@ -511,7 +511,8 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
     # the reference's training mode: dropout = attention_dropout = 0.1 (model.py:175-177), cosine schedule with warm-up
     trainer = KosmosTrainer(model, optimizer=optimizer, lr=1e-5, weight_decay=0.1, max_grad_norm=1.0, dropout=dropout,
                             attention_dropout=dropout, grad_reduce_dtype=torch.bfloat16 if reduce_bf16 else torch.float32,
-                            lr_schedule=cosine_with_warmup(2, 10000))
+                            lr_schedule=cosine_with_warmup(2, 10000), overlap_all_reduce=bool(int(os.environ.get("KX_BENCH_OVERLAP", "0"))),
+                            bwd_max_ctas=int(os.environ.get("KX_BENCH_BWD_CTAS", "0")))
     g = torch.Generator().manual_seed(11 + rank)
     h_text = torch.randint(0, VOCAB, (B, t_text), dtype=torch.long, generator=g).pin_memory()
     h_img = torch.randn(*((B, 3, 224, 224) if n_img == 1 else (B, n_img, 3, 224, 224)), generator=g).pin_memory()
@@ -560,8 +561,9 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
                    "result": "mean loss copied to pinned host memory"},
            "gpu_launches": int(launches), "loss_first": first_loss, "loss_last": float(h_loss[0]),
            "trained_parameters": int(sum(p.numel() for p in trainer.params)),
-           "grad_all_reduce": ("%d buckets (per decoder layer) on NCCL's stream, overlapped with backward" % len(trainer.bucket_plan()))
-                              if world > 1 else "none (1 GPU)"}
+           "grad_all_reduce": (("%d buckets (per decoder layer) on NCCL's stream, overlapped with backward" % len(trainer.bucket_plan()))
+                               if trainer.overlap else "one all-reduce of the flat %s gradient buffer after backward (not overlapped: "
+                               "profiles/r2_nccl_overlap.md)" % ("bf16" if reduce_bf16 else "fp32")) if world > 1 else "none (1 GPU)"}
     if detail:
         ops.profile_begin()
         trainer.step(d_text, d_img, **fkw)

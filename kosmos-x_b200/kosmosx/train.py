@@ -50,25 +50,32 @@ class KosmosTrainer:
     SITE_X0 = 0xFFFF0000          # dropout site ids: layer * 4 + {0: out_proj output, 1: fc2 output, 2: attention probabilities}
 
     def __init__(self, model: Kosmos, *, optimizer: str = "adamw", lr: float = 1e-4, betas=(0.9, 0.95), eps: float = 1e-8,
-                 weight_decay: float = 0.1, max_grad_norm: float = 1.0, process_group=None, overlap_all_reduce: bool = True,
+                 weight_decay: float = 0.1, max_grad_norm: float = 1.0, process_group=None, overlap_all_reduce: bool = False,
                  train_resampler: bool = True, layout_only: bool = False, loss_rule: str = "reference",
-                 pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.float32,
+                 pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.bfloat16,
                  distributed: bool | None = None, dropout: float | None = None, attention_dropout: float | None = None,
-                 seed: int = 0):
-        """loss_rule: "reference" = the rows / targets of the reference's intended loop (notes.txt:566-574: the `<image>`
+                 seed: int = 0, bwd_max_ctas: int = 0):
+        """overlap_all_reduce: False (default) = ONE all-reduce of the whole flat gradient buffer after backward; True = per-layer
+        buckets issued while backward is still running.  Measured on 2 and 8 B200s (profiles/r2_nccl_overlap.md): NCCL's kernels
+        occupy SMs that the persistent, one-CTA-per-SM backward kernels are sized for, so every GEMM / LayerNorm-backward
+        launch that overlaps a bucket runs a partial second wave — the overlapped exchange costs MORE (+8 ms at 2 GPUs, +16 ms
+        at 8) than its exposed time (2.7 GB of bf16 over NVLink: ~6 ms).
+        loss_rule: "reference" = the rows / targets of the reference's intended loop (notes.txt:566-574: the `<image>`
         `</image>` markers and the feature rows carry no loss and are never targets; row 0 predicts the first real text
         token), "next_token" = plain shift by one over the text rows.  pad_token_id: targets equal to it are ignored
         (None = the reference's loop, which masks nothing).  lr_schedule: callable step -> multiplier of ``lr`` (see
         ``cosine_with_warmup``), evaluated on the host from the step COUNT — no device value is read.
-        grad_reduce_dtype: torch.float32 all-reduces the flat fp32 gradient buffer; torch.bfloat16 exchanges a bf16
-        copy (half the NVLink bytes, the reference's FSDP ``reduce_dtype`` is 16-bit too, train.py:156-162) and
-        accumulates the received sums back in fp32.  distributed: None = data parallel over ``process_group`` (or the
+        grad_reduce_dtype: torch.bfloat16 (default) exchanges a bf16 copy of the gradients (2.7 GB instead of 5.4 GB; the
+        reference's FSDP ``reduce_dtype`` is 16-bit too, train.py:156-162) and converts the received sums back to fp32;
+        torch.float32 all-reduces the flat fp32 buffer itself (bit-exact sum of the ranks' fp32 gradients).  distributed: None = data parallel over ``process_group`` (or the
         default group) whenever torch.distributed is initialised; False = this process trains alone.
         dropout / attention_dropout: None = the model's config (the reference trains with 0.1 / 0.1, model.py:175-177);
         0 switches a site off (parity runs).  Masks are Philox4x32-7 functions of (seed, forward count, site, coordinates):
         the element-wise sites (decoder input, out_proj output, fc2 output) are regenerated in backward, the attention
         probabilities' keep bits (1 bit per score) are drawn by kx_attn_dropout_masks ahead of the flash kernels.
-        Ranks draw different masks (the seed is offset by the rank)."""
+        Ranks draw different masks (the seed is offset by the rank).
+        bwd_max_ctas: > 0 caps the grid of the persistent backward GEMMs (they are sized to one CTA per SM; an NCCL kernel
+        resident on a few SMs while they launch would push the CTAs that do not fit into a second wave)."""
         if optimizer not in ("adamw", "lion"):
             raise ValueError("optimizer must be 'adamw' or 'lion' (train.py:375-386)")
         if loss_rule not in ("reference", "next_token"):
@@ -85,6 +92,7 @@ class KosmosTrainer:
             raise ValueError("dropout probabilities must be in [0, 1)")
         self.seed = int(seed)
         self._fw_count = 0
+        self.bwd_max_ctas = int(bwd_max_ctas)
         self.grad_reduce_dtype = grad_reduce_dtype
         self.max_grad_norm = max_grad_norm
         self.pg = process_group
@@ -395,6 +403,10 @@ class KosmosTrainer:
         over micro-batches, the reference's GRADIENT_ACCUMULATE_EVERY, train.py:55,492) instead of replacing it; the kernels
         write rather than accumulate, so the previous sum is parked in a second buffer for the duration of the pass."""
         m, cfg = self.model, self.cfg
+        cap = self.bwd_max_ctas if self.world > 1 else 0
+
+        def gemm(*a_, **k_):
+            return ops.gemm(*a_, max_ctas=cap, **k_)
         g_prev = None
         if accumulate:
             g_prev = self._buf("g_prev", (self.n_total,), torch.float32)
@@ -437,8 +449,8 @@ class KosmosTrainer:
         delta = self._buf("delta", (H, B, ops.lse_pad(T), 2), f32)
         # LM head
         wout = m.output_projection.weight
-        ops.gemm(dl, self._w16(wout), dh, b_trans=True)
-        ops.gemm(dl, fw["hF"], self._g(wout), a_trans=True, b_trans=True)
+        gemm(dl, self._w16(wout), dh, b_trans=True)
+        gemm(dl, fw["hF"], self._g(wout), a_trans=True, b_trans=True)
         if m.output_projection.bias is not None:
             ops.colsum(dl, self._g(m.output_projection.bias))
         last = self.layers[-1] if self.layers else None
@@ -452,17 +464,17 @@ class KosmosTrainer:
         for li in range(len(self.layers) - 1, -1, -1):
             L, s = self.layers[li], fw["saved"][li]
             # ---- FFN: x_out = x_mid + fc2(LN_ffn(gelu(fc1(LN_f(x_mid)))))
-            ops.gemm(dxb, self._w16(L["fc2"].weight), dgl, b_trans=True)
-            ops.gemm(dxb, s["g_ln"], self._g(L["fc2"].weight), a_trans=True, b_trans=True)
+            gemm(dxb, self._w16(L["fc2"].weight), dgl, b_trans=True)
+            gemm(dxb, s["g_ln"], self._g(L["fc2"].weight), a_trans=True, b_trans=True)
             ops.layernorm_bwd(s["u"], dgl, L["ln_ffn"].weight, du, self._g(L["ln_ffn"].weight), self._g(L["ln_ffn"].bias), part_f,
                               act=_abi.KX_ACT_GELU, eps=cfg.eps, d_colsum=self._g(L["fc1"].bias))
-            ops.gemm(du, self._w16(L["fc1"].weight), dh, b_trans=True)
-            ops.gemm(du, s["h2"], self._g(L["fc1"].weight), a_trans=True, b_trans=True)
+            gemm(du, self._w16(L["fc1"].weight), dh, b_trans=True)
+            gemm(du, s["h2"], self._g(L["fc1"].weight), a_trans=True, b_trans=True)
             ops.layernorm_bwd(s["x_mid"], dh, L["ln_f"].weight, dx, self._g(L["ln_f"].weight), self._g(L["ln_f"].bias), part_d,
                               eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(L["o"].bias), drop=(pd, li * 4, dseed))
             # ---- attention: x_mid = x_in + out_proj(LN_i(attn(xpos(qkv(LN_a(x_in))))))
-            ops.gemm(dxb, self._w16(L["o"].weight), dh, b_trans=True)
-            ops.gemm(dxb, s["a_ln"], self._g(L["o"].weight), a_trans=True, b_trans=True)
+            gemm(dxb, self._w16(L["o"].weight), dh, b_trans=True)
+            gemm(dxb, s["a_ln"], self._g(L["o"].weight), a_trans=True, b_trans=True)
             ops.layernorm_bwd(s["att"], dh, L["ln_i"].weight, datt, self._g(L["ln_i"].weight), self._g(L["ln_i"].bias), part_d,
                               eps=cfg.eps)
             qkv = s["qkv"]
@@ -472,8 +484,8 @@ class KosmosTrainer:
             wqkv, gwqkv = self._qkv(L, "weight")
             _, gbqkv = self._qkv(L, "bias")
             ops.colsum(dqkv, gbqkv)
-            ops.gemm(dqkv, wqkv, dh, b_trans=True)
-            ops.gemm(dqkv, s["h1"], gwqkv, a_trans=True, b_trans=True)
+            gemm(dqkv, wqkv, dh, b_trans=True)
+            gemm(dqkv, s["h1"], gwqkv, a_trans=True, b_trans=True)
             prev = self.layers[li - 1] if li > 0 else None
             ops.layernorm_bwd(s["x_in"], dh, L["ln_a"].weight, dx, self._g(L["ln_a"].weight), self._g(L["ln_a"].bias), part_d,
                               eps=cfg.eps, dres=dx, dxb=dxb, d_colsum=self._g(prev["fc2"].bias) if prev else None,

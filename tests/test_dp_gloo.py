@@ -109,6 +109,7 @@ def _bucket_worker(rank, world, port, out):
     kd.init_from_env("gloo")
     _, tr = _tiny_trainer_layout()
     tr.world, tr.overlap = world, True
+    tr.grad_reduce_dtype = torch.float32          # (the bf16 exchange casts with a CUDA kernel; its NCCL test is tools/dp_check.py)
     g = torch.Generator().manual_seed(100 + rank)
     tr.G = torch.randn(tr.n_total, generator=g)
     want = tr.G.clone()
