@@ -54,7 +54,7 @@ class KosmosTrainer:
                  train_resampler: bool = True, layout_only: bool = False, loss_rule: str = "reference",
                  pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.bfloat16,
                  distributed: bool | None = None, dropout: float | None = None, attention_dropout: float | None = None,
-                 seed: int = 0, bwd_max_ctas: int = 0):
+                 seed: int = 0, bwd_max_ctas: int = 0, recompute: bool = False):
         """overlap_all_reduce: False (default) = ONE all-reduce of the whole flat gradient buffer after backward; True = per-layer
         buckets issued while backward is still running.  Measured on 2 and 8 B200s (profiles/r2_nccl_overlap.md): NCCL's kernels
         occupy SMs that the persistent, one-CTA-per-SM backward kernels are sized for, so every GEMM / LayerNorm-backward
@@ -74,6 +74,9 @@ class KosmosTrainer:
         the element-wise sites (decoder input, out_proj output, fc2 output) are regenerated in backward, the attention
         probabilities' keep bits (1 bit per score) are drawn by kx_attn_dropout_masks ahead of the flash kernels.
         Ranks draw different masks (the seed is offset by the rank).
+        recompute: activation checkpointing per decoder layer (the reference wraps the decoder with torch's checkpoint_wrapper,
+        train.py:84-110,528-529): the forward keeps only each layer's fp32 input (134 MB per layer at C3 instead of 1.28 GB) and
+        backward re-runs the layer before differentiating it — bit-identical gradients for one more decoder forward per step.
         bwd_max_ctas: > 0 caps the grid of the persistent backward GEMMs (they are sized to one CTA per SM; an NCCL kernel
         resident on a few SMs while they launch would push the CTAs that do not fit into a second wave)."""
         if optimizer not in ("adamw", "lion"):
@@ -93,6 +96,7 @@ class KosmosTrainer:
         self.seed = int(seed)
         self._fw_count = 0
         self.bwd_max_ctas = int(bwd_max_ctas)
+        self.recompute = bool(recompute)
         self.grad_reduce_dtype = grad_reduce_dtype
         self.max_grad_norm = max_grad_norm
         self.pg = process_group
@@ -245,46 +249,61 @@ class KosmosTrainer:
             ops.dropout_f32(x, p=pd, site=self.SITE_X0, seed=dseed)
         tabs = dp._xpos(T, x.device)
         scale = (D // H) ** -0.5
+        ctx = dict(B=B, T=T, M=M, tabs=tabs, scale=scale, dseed=dseed)
         saved = []
-        for li, L in enumerate(self.layers):
-            s = dict(x_in=x)
-            s["h1"] = self._buf(f"h1_{li}", (M, D), bf)
-            s["qkv"] = self._buf(f"qkv_{li}", (M, 3 * D), bf)
-            s["att"] = self._buf(f"att_{li}", (M, D), bf)
-            s["lse"] = self._buf(f"lse_{li}", (H, B, ops.lse_pad(T)), f32)
-            s["a_ln"] = self._buf(f"aln_{li}", (M, D), bf)
-            s["x_mid"] = self._buf(f"xmid_{li}", (M, D), f32)
-            s["h2"] = self._buf(f"h2_{li}", (M, D), bf)
-            s["u"] = self._buf(f"u_{li}", (M, F), bf)
-            s["g_ln"] = self._buf(f"gln_{li}", (M, F), bf)
-            x_out = self._buf(f"xout_{li}", (M, D), f32)
-            wqkv, _ = self._qkv(L, "weight")
-            bqkv, _ = self._qkv(L, "bias")
-            ops.layernorm(x, L["ln_a"].weight, L["ln_a"].bias, s["h1"], eps=cfg.eps)
-            ops.gemm(s["h1"], wqkv, s["qkv"], bias=bqkv, xpos=tuple(tabs), seq_len=T)
-            qkv = s["qkv"]
-            row_mask = None
-            if pa > 0:       # keep bits drawn ahead of the flash kernel: row-major for it (one buffer, reused by every layer),
-                             # key-major for this layer's backward kernel (kept until then: 1 bit per score)
-                words = ops.attn_dropout_mask_words(B, H, T)
-                row_mask = self._buf("dmask_rows", (words,), torch.int32)
-                s["dmask"] = self._buf(f"dmask_{li}", (words,), torch.int32)
-                ops.attn_dropout_masks(row_mask, s["dmask"], p=pa, site=li * 4 + 2, seed=dseed, batch=B, heads=H, seq_len=T)
-            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], s["att"], batch=B, heads=H, seq_len=T, causal=True,
-                          scale=scale, lse_out=s["lse"], drop_p=pa, row_mask=row_mask)
-            ops.layernorm(s["att"], L["ln_i"].weight, L["ln_i"].bias, s["a_ln"], eps=cfg.eps)
-            ops.gemm(s["a_ln"], self._w16(L["o"].weight), s["x_mid"], bias=L["o"].bias, res=x, drop=(pd, li * 4, dseed))
-            ops.layernorm(s["x_mid"], L["ln_f"].weight, L["ln_f"].bias, s["h2"], eps=cfg.eps)
-            ops.gemm(s["h2"], self._w16(L["fc1"].weight), s["u"], bias=L["fc1"].bias)
-            ops.act_layernorm(s["u"], L["ln_ffn"].weight, L["ln_ffn"].bias, s["g_ln"], eps=cfg.eps)
-            ops.gemm(s["g_ln"], self._w16(L["fc2"].weight), x_out, bias=L["fc2"].bias, res=s["x_mid"], drop=(pd, li * 4 + 1, dseed))
-            saved.append(s)
-            x = x_out
+        for li in range(len(self.layers)):
+            # recompute: every layer writes into ONE shared set of activation buffers and only its input survives; backward
+            # re-runs the layer first (the dropout masks are functions of (seed, site), so the second pass draws the same ones)
+            s = self._layer_forward(li, x, ctx, tag="rc" if self.recompute else str(li))
+            saved.append(dict(x_in=x) if self.recompute else s)
+            x = s["x_out"]
         hF = self._buf("hF", (M, D), bf)
         ops.layernorm(x, dp.layer_norm.weight, dp.layer_norm.bias, hF, eps=cfg.eps)
         logits = self._buf("logits", (M, V), f32)
         ops.gemm(hF, self._w16(m.output_projection.weight), logits, bias=m.output_projection.bias)
         return dict(saved=saved, x_last=x, hF=hF, logits=logits, B=B, T=T, M=M, tabs=tabs, scale=scale, vis=vis, dseed=dseed)
+
+    def _layer_forward(self, li, x, ctx, tag):
+        """Training forward of decoder layer li from its fp32 input x; returns the activations backward needs (+ x_out).
+        `tag` names the buffer set: one per layer normally, one shared set under activation recompute."""
+        cfg, L = self.cfg, self.layers[li]
+        B, T, M, tabs, scale, dseed = ctx["B"], ctx["T"], ctx["M"], ctx["tabs"], ctx["scale"], ctx["dseed"]
+        D, F, H = cfg.dim, cfg.ffn, cfg.heads
+        bf, f32 = torch.bfloat16, torch.float32
+        pd, pa = self.p_drop, self.p_attn
+        s = dict(x_in=x)
+        s["h1"] = self._buf(f"h1_{tag}", (M, D), bf)
+        s["qkv"] = self._buf(f"qkv_{tag}", (M, 3 * D), bf)
+        s["att"] = self._buf(f"att_{tag}", (M, D), bf)
+        s["lse"] = self._buf(f"lse_{tag}", (H, B, ops.lse_pad(T)), f32)
+        s["a_ln"] = self._buf(f"aln_{tag}", (M, D), bf)
+        s["x_mid"] = self._buf(f"xmid_{tag}", (M, D), f32)
+        s["h2"] = self._buf(f"h2_{tag}", (M, D), bf)
+        s["u"] = self._buf(f"u_{tag}", (M, F), bf)
+        s["g_ln"] = self._buf(f"gln_{tag}", (M, F), bf)
+        x_out = self._buf(f"xout_{li}", (M, D), f32)          # always per layer: it IS the next layer's saved input
+        wqkv, _ = self._qkv(L, "weight")
+        bqkv, _ = self._qkv(L, "bias")
+        ops.layernorm(x, L["ln_a"].weight, L["ln_a"].bias, s["h1"], eps=cfg.eps)
+        ops.gemm(s["h1"], wqkv, s["qkv"], bias=bqkv, xpos=tuple(tabs), seq_len=T)
+        qkv = s["qkv"]
+        row_mask = None
+        if pa > 0:       # keep bits drawn ahead of the flash kernel: row-major for it (one buffer, reused by every layer),
+                         # key-major for this layer's backward kernel (kept until then: 1 bit per score)
+            words = ops.attn_dropout_mask_words(B, H, T)
+            row_mask = self._buf("dmask_rows", (words,), torch.int32)
+            s["dmask"] = self._buf(f"dmask_{tag}", (words,), torch.int32)
+            ops.attn_dropout_masks(row_mask, s["dmask"], p=pa, site=li * 4 + 2, seed=dseed, batch=B, heads=H, seq_len=T)
+        ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], s["att"], batch=B, heads=H, seq_len=T, causal=True,
+                      scale=scale, lse_out=s["lse"], drop_p=pa, row_mask=row_mask)
+        ops.layernorm(s["att"], L["ln_i"].weight, L["ln_i"].bias, s["a_ln"], eps=cfg.eps)
+        ops.gemm(s["a_ln"], self._w16(L["o"].weight), s["x_mid"], bias=L["o"].bias, res=x, drop=(pd, li * 4, dseed))
+        ops.layernorm(s["x_mid"], L["ln_f"].weight, L["ln_f"].bias, s["h2"], eps=cfg.eps)
+        ops.gemm(s["h2"], self._w16(L["fc1"].weight), s["u"], bias=L["fc1"].bias)
+        ops.act_layernorm(s["u"], L["ln_ffn"].weight, L["ln_ffn"].bias, s["g_ln"], eps=cfg.eps)
+        ops.gemm(s["g_ln"], self._w16(L["fc2"].weight), x_out, bias=L["fc2"].bias, res=s["x_mid"], drop=(pd, li * 4 + 1, dseed))
+        s["x_out"] = x_out
+        return s
 
     # ------------------------------------------------------------------ perceiver resampler + image_proj (trainable)
     def _resampler_forward(self, xv, B, x0, T, img_rows, pos):
@@ -463,6 +482,8 @@ class KosmosTrainer:
         self._bucket_ready("head", works)                     # the LM head gradient is complete
         for li in range(len(self.layers) - 1, -1, -1):
             L, s = self.layers[li], fw["saved"][li]
+            if self.recompute:               # activation checkpointing (train.py:84-110): rebuild the layer's activations from its input
+                s = self._layer_forward(li, s["x_in"], fw, tag="rc")
             # ---- FFN: x_out = x_mid + fc2(LN_ffn(gelu(fc1(LN_f(x_mid)))))
             gemm(dxb, self._w16(L["fc2"].weight), dgl, b_trans=True)
             gemm(dxb, s["g_ln"], self._g(L["fc2"].weight), a_trans=True, b_trans=True)

@@ -412,3 +412,22 @@ def test_training_step_with_dropout_matches_oracle_given_the_same_masks(B, t_tex
     assert abs(l2 - loss.item()) > 1e-4
     _, mine_b, trainer_b, _ = _pair(max_positions=512, dropout=pd, attention_dropout=pa, seed=7)
     assert abs(trainer_b.loss_and_grads(text.cuda(), images.cuda(), image_positions=positions).item() - loss.item()) <= 1e-5
+
+
+def test_activation_recompute_gives_the_same_gradients():
+    """KosmosTrainer(recompute=True) (activation checkpointing, train.py:84-110): only each layer's input is kept, backward
+    re-runs the layer — same loss and gradients as the run that keeps everything, with dropout on (the masks are functions of
+    (seed, site), so the second pass draws the same ones), and far fewer bytes held."""
+    import kosmos_oracle as ko
+    _, mine_a, tr_a, oc = _pair(max_positions=512, dropout=0.1, attention_dropout=0.1, seed=11)
+    _, mine_b, tr_b, _ = _pair(max_positions=512, dropout=0.1, attention_dropout=0.1, seed=11, recompute=True)
+    text, images = ko.make_inputs(oc, 2, 150, seed=3)
+    la = tr_a.loss_and_grads(text.cuda(), images.cuda()).item()
+    lb = tr_b.loss_and_grads(text.cuda(), images.cuda()).item()
+    assert abs(la - lb) <= 1e-5
+    rel = ((tr_a.G - tr_b.G).norm() / tr_a.G.norm()).item()
+    print(f"recompute vs stored activations: loss {la:.5f} / {lb:.5f}, gradient rel diff {rel:.2e}")
+    assert rel <= 1e-5                       # (not bitwise: dQ is reduced across CTAs by TMA reduce-add, order not fixed)
+    held = lambda tr: sum(b.numel() * b.element_size() for k, b in tr._ws.items() if any(k[0].startswith(p) for p in
+                                                                                         ("h1_", "qkv_", "att_", "aln_", "xmid_", "h2_", "u_", "gln_")))
+    assert held(tr_b) * oc.layers == held(tr_a)
