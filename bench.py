@@ -499,7 +499,7 @@ def decode_measure(torch, model, batch=8, prompt=512, new=96):
 
 
 def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peaks, optimizer="adamw", detail=True, dropout=0.1,
-                  reduce_bf16=True):
+                  reduce_bf16=True, clip_last=False, recompute=False):
     """BASELINE.json configs[3]: the data-parallel training step (forward that keeps activations -> CE over text rows ->
     backward -> bucketed NCCL all-reduce overlapped with backward -> clip -> fused AdamW), B sequences per GPU.
     Returns a dict: tokens/s with inputs resident, e2e with H2D of the batch and D2H of the loss every step, and
@@ -512,7 +512,8 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
     trainer = KosmosTrainer(model, optimizer=optimizer, lr=1e-5, weight_decay=0.1, max_grad_norm=1.0, dropout=dropout,
                             attention_dropout=dropout, grad_reduce_dtype=torch.bfloat16 if reduce_bf16 else torch.float32,
                             lr_schedule=cosine_with_warmup(2, 10000), overlap_all_reduce=bool(int(os.environ.get("KX_BENCH_OVERLAP", "0"))),
-                            bwd_max_ctas=int(os.environ.get("KX_BENCH_BWD_CTAS", "0")))
+                            bwd_max_ctas=int(os.environ.get("KX_BENCH_BWD_CTAS", "0")), train_clip_last_layer=clip_last,
+                            recompute=recompute)
     g = torch.Generator().manual_seed(11 + rank)
     h_text = torch.randint(0, VOCAB, (B, t_text), dtype=torch.long, generator=g).pin_memory()
     h_img = torch.randn(*((B, 3, 224, 224) if n_img == 1 else (B, n_img, 3, 224, 224)), generator=g).pin_memory()
@@ -551,8 +552,9 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
     tfl = step_flops / (ms * 1e-3) / 1e12
     out = {"config": "configs[3]: data-parallel training step, B=%d per GPU, seq=2048, %d image(s)/seq, bf16 operands / fp32 "
                      "master weights, %s, grad clip 1.0, cosine LR schedule, decoder + LM head + embedding tables + perceiver resampler + "
-                     "image_proj trained (CLIP tower frozen), dropout = attention_dropout = %.2f, %s gradient all-reduce, no activation "
-                     "recompute" % (B, n_img, optimizer, dropout, "bf16" if reduce_bf16 else "fp32"),
+                     "image_proj trained (%s), dropout = attention_dropout = %.2f, %s gradient all-reduce, %s"
+                     % (B, n_img, optimizer, "CLIP frozen except its last encoder layer" if clip_last else "CLIP tower frozen", dropout,
+                        "bf16" if reduce_bf16 else "fp32", "activation recompute per decoder layer" if recompute else "no activation recompute"),
            "value": tokens / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "global_batch": B * world,
            "step_tflops_per_gpu": tfl, "step_frac_of_bf16_peak": {"burst": tfl / peaks["burst"], "sustained": tfl / peaks["sustained"]},
            "flops_per_step_per_gpu": step_flops,
@@ -598,7 +600,8 @@ def run_train(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler: sampler.start()
     r = train_measure(torch, kdist, dev, model, wl, args.steps, args.warmup, world, rank, peaks, optimizer=args.optimizer,
-                      dropout=args.dropout, reduce_bf16=bool(args.reduce_bf16))
+                      dropout=args.dropout, reduce_bf16=bool(args.reduce_bf16), clip_last=bool(args.clip_last),
+                      recompute=bool(args.recompute))
     clocks = sampler.stop() if sampler else None
     bd = r.get("breakdown", {})
     top = max(((k, v) for k, v in bd.items() if k.startswith("gemm")), key=lambda kv: kv[1]["ms"], default=(None, None))
@@ -658,6 +661,8 @@ def main():
                     "4 images per sequence; train = configs[3], the training step")
     ap.add_argument("--optimizer", default="adamw", choices=["adamw", "lion"])
     ap.add_argument("--dropout", type=float, default=0.1, help="dropout = attention_dropout of the training step (reference: 0.1)")
+    ap.add_argument("--clip-last", type=int, default=0, help="--workload train: also train CLIP's last encoder layer (notes.txt:537-538)")
+    ap.add_argument("--recompute", type=int, default=0, help="--workload train: activation recompute per decoder layer (train.py:84-110)")
     ap.add_argument("--reduce-bf16", type=int, default=1, help="exchange gradients in bf16 (default) or fp32 (0)")
     ap.add_argument("--decode-leg", type=int, default=1, help="also time incremental decoding (SURVEY 8(f)2) and report it as "
                     "'decode' inside the forward line (default on, single GPU)")

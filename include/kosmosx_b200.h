@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 17   /* returned by kx_abi_version(); bumped on any signature change */
+#define KX_ABI_VERSION 18   /* returned by kx_abi_version(); bumped on any signature change */
 
 typedef struct CUstream_st* kx_stream_t; /* == cudaStream_t */
 
@@ -388,6 +388,10 @@ int kx_perceiver_xattn_bwd(const void* q, long long ld_q, const void* kv, long l
                            long long ld_dkv, int batch, int heads, int n_q, int n_kv, float scale, kx_stream_t stream);
 int kx_gelu_fwd(const void* u_bf16, void* out_bf16, long long n, kx_stream_t stream);
 int kx_gelu_bwd(const void* u_bf16, const void* dmid_bf16, void* du_bf16, long long n, kx_stream_t stream);
+/* The same pair with the activation named (KX_ACT_GELU = the two above; KX_ACT_QUICK_GELU = CLIP's x*sigmoid(1.702x),
+ * [HF] activations.py QuickGELUActivation): the MLP of the last ViT layer when it is fine-tuned (notes.txt:537-538). */
+int kx_act_fwd(const void* u_bf16, void* out_bf16, long long n, int act, kx_stream_t stream);
+int kx_act_bwd(const void* u_bf16, const void* dmid_bf16, void* du_bf16, long long n, int act, kx_stream_t stream);
 int kx_gather_rows(const void* src, int src_is_f32, long long ld_src, void* dst_bf16, long long ld_dst, int rows, int n,
                    int grp_rows, int grp_stride, int grp_off, int accumulate, kx_stream_t stream);
 int kx_sum_rows_f32(const float* src, long long ld, int rows, long long n, float* out, int accumulate, kx_stream_t stream);

@@ -778,17 +778,24 @@ lion_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 // ----------------------------------------------------------------------------- perceiver feed-forward GELU (no LayerNorm behind it)
-// mid = gelu(u);  du = dmid * gelu'(u)   (bf16, 8 elements per thread)
+// mid = gelu(u);  du = dmid * gelu'(u)   (bf16, 8 elements per thread).  QUICK: CLIP's x * sigmoid(1.702 x) (the last ViT
+// layer when it is fine-tuned) instead of the erf form.
+__device__ __forceinline__ float quick_gelu_grad(float x) {       // s + 1.702 x s (1 - s),  s = sigmoid(1.702 x)
+    const float s = 1.0f / (1.0f + __expf(-1.702f * x));
+    return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
+}
+template <bool QUICK>
 __global__ void __launch_bounds__(256)
 gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ out, long long nvec) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float v[8];
         load8(u + i * 8, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = gelu_exact(v[k]);
+        for (int k = 0; k < 8; ++k) v[k] = QUICK ? quick_gelu(v[k]) : gelu_exact(v[k]);
         store8(out + i * 8, v);
     }
 }
+template <bool QUICK>
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ dmid, __nv_bfloat16* __restrict__ du, long long nvec) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -796,7 +803,7 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __rest
         load8(u + i * 8, v);
         load8(dmid + i * 8, d);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] *= gelu_grad(v[k]);
+        for (int k = 0; k < 8; ++k) d[k] *= QUICK ? quick_gelu_grad(v[k]) : gelu_grad(v[k]);
         store8(du + i * 8, d);
     }
 }
@@ -1078,24 +1085,43 @@ extern "C" int kx_lion_step(float* p, const float* g, float* m, void* w_bf16, lo
     return check_launch("kx_lion_step");
 }
 
-extern "C" int kx_gelu_fwd(const void* u_bf16, void* out_bf16, long long n, cudaStream_t stream) {
-    if (!u_bf16 || !out_bf16 || n <= 0 || (n % 8) || !KX_ALIGNED16(u_bf16) || !KX_ALIGNED16(out_bf16)) { set_error("kx_gelu_fwd: bad argument"); return KX_ERR_ARG; }
-    const int sms = device_sm_count();
-    if (sms <= 0) return KX_ERR_NO_DEVICE;
-    gelu_fwd_kernel<<<grid_for(n / 8, sms), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u_bf16), reinterpret_cast<__nv_bfloat16*>(out_bf16), n / 8);
-    return check_launch("kx_gelu_fwd");
-}
-
-extern "C" int kx_gelu_bwd(const void* u_bf16, const void* dmid_bf16, void* du_bf16, long long n, cudaStream_t stream) {
-    if (!u_bf16 || !dmid_bf16 || !du_bf16 || n <= 0 || (n % 8) || !KX_ALIGNED16(u_bf16) || !KX_ALIGNED16(dmid_bf16) || !KX_ALIGNED16(du_bf16)) {
-        set_error("kx_gelu_bwd: bad argument");
+extern "C" int kx_act_fwd(const void* u_bf16, void* out_bf16, long long n, int act, cudaStream_t stream) {
+    if (!u_bf16 || !out_bf16 || n <= 0 || (n % 8) || !KX_ALIGNED16(u_bf16) || !KX_ALIGNED16(out_bf16) ||
+        (act != KX_ACT_GELU && act != KX_ACT_QUICK_GELU)) {
+        set_error("kx_act_fwd: bad argument");
         return KX_ERR_ARG;
     }
     const int sms = device_sm_count();
     if (sms <= 0) return KX_ERR_NO_DEVICE;
-    gelu_bwd_kernel<<<grid_for(n / 8, sms), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(u_bf16), reinterpret_cast<const __nv_bfloat16*>(dmid_bf16),
-                                                              reinterpret_cast<__nv_bfloat16*>(du_bf16), n / 8);
-    return check_launch("kx_gelu_bwd");
+    const auto* u = reinterpret_cast<const __nv_bfloat16*>(u_bf16);
+    auto* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+    if (act == KX_ACT_QUICK_GELU) gelu_fwd_kernel<true><<<grid_for(n / 8, sms), 256, 0, stream>>>(u, out, n / 8);
+    else gelu_fwd_kernel<false><<<grid_for(n / 8, sms), 256, 0, stream>>>(u, out, n / 8);
+    return check_launch("kx_act_fwd");
+}
+
+extern "C" int kx_act_bwd(const void* u_bf16, const void* dmid_bf16, void* du_bf16, long long n, int act, cudaStream_t stream) {
+    if (!u_bf16 || !dmid_bf16 || !du_bf16 || n <= 0 || (n % 8) || !KX_ALIGNED16(u_bf16) || !KX_ALIGNED16(dmid_bf16) || !KX_ALIGNED16(du_bf16) ||
+        (act != KX_ACT_GELU && act != KX_ACT_QUICK_GELU)) {
+        set_error("kx_act_bwd: bad argument");
+        return KX_ERR_ARG;
+    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return KX_ERR_NO_DEVICE;
+    const auto* u = reinterpret_cast<const __nv_bfloat16*>(u_bf16);
+    const auto* dm = reinterpret_cast<const __nv_bfloat16*>(dmid_bf16);
+    auto* du = reinterpret_cast<__nv_bfloat16*>(du_bf16);
+    if (act == KX_ACT_QUICK_GELU) gelu_bwd_kernel<true><<<grid_for(n / 8, sms), 256, 0, stream>>>(u, dm, du, n / 8);
+    else gelu_bwd_kernel<false><<<grid_for(n / 8, sms), 256, 0, stream>>>(u, dm, du, n / 8);
+    return check_launch("kx_act_bwd");
+}
+
+extern "C" int kx_gelu_fwd(const void* u_bf16, void* out_bf16, long long n, cudaStream_t stream) {
+    return kx_act_fwd(u_bf16, out_bf16, n, KX_ACT_GELU, stream);
+}
+
+extern "C" int kx_gelu_bwd(const void* u_bf16, const void* dmid_bf16, void* du_bf16, long long n, cudaStream_t stream) {
+    return kx_act_bwd(u_bf16, dmid_bf16, du_bf16, n, KX_ACT_GELU, stream);
 }
 
 extern "C" int kx_gather_rows(const void* src, int src_is_f32, long long ld_src, void* dst_bf16, long long ld_dst, int rows, int n,

@@ -131,6 +131,8 @@ SIGNATURES = {
     "kx_perceiver_xattn_bwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "kx_gelu_fwd": (_i, [_vp, _vp, _ll, _vp]),
     "kx_gelu_bwd": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "kx_act_fwd": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "kx_act_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "kx_gather_rows": (_i, [_vp, _i, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "kx_sum_rows_f32": (_i, [_f32p, _ll, _i, _ll, _f32p, _i, _vp]),
     "kx_colsum_bf16": (_i, [_vp, _ll, _i, _i, _f32p, _vp]),

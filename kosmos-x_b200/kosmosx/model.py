@@ -816,11 +816,27 @@ class Kosmos(_KosmosBase):
                     media_pos=_f32(self.perceive.media_pos_emb).view(-1, cfg.vit_dim),
                     p_norm=(_f32(self.perceive.norm.weight), _f32(self.perceive.norm.bias)), w_ip=_bf16(self.image_proj.weight))
 
+    @staticmethod
+    def _pack_clip_layer(L):
+        """One CLIP encoder layer staged for the 5-launch inference layer: layer_norm1 / layer_norm2 are folded into q|k|v and
+        fc1 (same scheme as the decoder)."""
+        a = L.self_attn
+        return dict(
+            qkv=_fold_ln(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0),
+                         torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0), L.layer_norm1),
+            w_o=_bf16(a.out_proj.weight), b_o=_f32(a.out_proj.bias),
+            fc1=_fold_ln(L.mlp.fc1.weight, L.mlp.fc1.bias, L.layer_norm2),
+            w_fc2=_bf16(L.mlp.fc2.weight), b_fc2=_f32(L.mlp.fc2.bias),
+        )
+
     def _pack_vision(self):
         if self._vis_packed is not None:
             if getattr(self, "_resampler_dirty", False):
                 self._vis_packed.update(self._pack_resampler())
                 self._resampler_dirty = False
+            if getattr(self, "_clip_last_dirty", False):          # KosmosTrainer(train_clip_last_layer=True) stepped it
+                self._vis_packed["layers"][-1] = self._pack_clip_layer(self.clip_model.encoder.layers[-1])
+                self._clip_last_dirty = False
             return self._vis_packed
         cfg, cm = self.cfg, self.clip_model
         _require_cuda(cm.pre_layrnorm.weight, "Kosmos parameters")
@@ -828,17 +844,8 @@ class Kosmos(_KosmosBase):
         k_pad = (k + 63) // 64 * 64
         wp = torch.zeros(cfg.vit_dim, k_pad, dtype=torch.float32, device=cm.pre_layrnorm.weight.device)
         wp[:, :k] = cm.embeddings.patch_embedding.weight.detach().reshape(cfg.vit_dim, k)
-        layers = []
-        for L in cm.encoder.layers:
-            a = L.self_attn
-            # layer_norm1 / layer_norm2 are folded into q|k|v and fc1 (same scheme as the decoder)
-            layers.append(dict(
-                qkv=_fold_ln(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0),
-                             torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0), L.layer_norm1),
-                w_o=_bf16(a.out_proj.weight), b_o=_f32(a.out_proj.bias),
-                fc1=_fold_ln(L.mlp.fc1.weight, L.mlp.fc1.bias, L.layer_norm2),
-                w_fc2=_bf16(L.mlp.fc2.weight), b_fc2=_f32(L.mlp.fc2.bias),
-            ))
+        layers = [self._pack_clip_layer(L) for L in cm.encoder.layers]
+        self._clip_last_dirty = False
         self._vis_packed = dict(
             k_pad=k_pad, w_patch=_bf16(wp), cls=_f32(cm.embeddings.class_embedding),
             vpos=_f32(cm.embeddings.position_embedding.weight),
@@ -850,11 +857,12 @@ class Kosmos(_KosmosBase):
         return self._vis_packed
 
     # ---- stages -------------------------------------------------------------------------
-    def _vit(self, images: torch.Tensor, media: int = 1) -> torch.Tensor:
+    def _vit(self, images: torch.Tensor, media: int = 1, upto: int | None = None) -> torch.Tensor:
         """CLIPVisionTransformer.forward ([HF] modeling_clip.py:667-697) -> fp32 [N*Tv, Dv] (un-normalised) for the
         N = images.shape[0] images.  media > 1: `images` is (sequences*media, 3, H, W) in (sequence, media) order and
         the output rows are media-major (image i of every sequence is one contiguous block).  uint8 `images`
-        ((N,3,H,W) or (N,H,W,3)) are raw pixels: CLIP's rescale + normalise is fused into the patch pack."""
+        ((N,3,H,W) or (N,H,W,3)) are raw pixels: CLIP's rescale + normalise is fused into the patch pack.
+        upto: run only encoder layers [0, upto) (KosmosTrainer fine-tuning the last layer runs that one itself)."""
         cfg, vp, ws = self.cfg, self._pack_vision(), self._ws
         B = images.shape[0]
         Tv, Dv, P = cfg.vit_tokens, cfg.vit_dim, cfg.vit_tokens - 1
@@ -879,7 +887,7 @@ class Kosmos(_KosmosBase):
         st_b = ws.get("vst_b", ((Dv + 63) // 64, M, 2), torch.float32, dev)
         ops.rowstats_cast(x, xb, st0)
         cur = st0
-        for L in vp["layers"]:                                               # 5 launches per layer, no stand-alone LayerNorm
+        for L in vp["layers"][:upto]:                                        # 5 launches per layer, no stand-alone LayerNorm
             w, c, d = L["qkv"]
             ops.gemm(xb, w, qkv, bias=d, ln=(cur, c, Dv, cfg.eps))
             ops.attention(qkv[:, :Dv], qkv[:, Dv:2 * Dv], qkv[:, 2 * Dv:], att, batch=B, heads=cfg.vit_heads,

@@ -288,16 +288,17 @@ def perceiver_attention_bwd(q, kv, out, d_out, dq, dkv, *, batch, heads, n_q, n_
               "kx_perceiver_xattn_bwd")
 
 
-def gelu_fwd(u, out):
+def gelu_fwd(u, out, act=_abi.KX_ACT_GELU):
+    """out = act(u), bf16 (act: KX_ACT_GELU or KX_ACT_QUICK_GELU)."""
     _req(u, torch.bfloat16, "u"); _req(out, torch.bfloat16, "out")
-    check(lib.kx_gelu_fwd(u.data_ptr(), out.data_ptr(), u.numel(), _stream()), "kx_gelu_fwd")
+    check(lib.kx_act_fwd(u.data_ptr(), out.data_ptr(), u.numel(), int(act), _stream()), "kx_act_fwd")
     return out
 
 
-def gelu_bwd(u, dmid, du):
+def gelu_bwd(u, dmid, du, act=_abi.KX_ACT_GELU):
     for n, t in (("u", u), ("dmid", dmid), ("du", du)):
         _req(t, torch.bfloat16, n)
-    check(lib.kx_gelu_bwd(u.data_ptr(), dmid.data_ptr(), du.data_ptr(), u.numel(), _stream()), "kx_gelu_bwd")
+    check(lib.kx_act_bwd(u.data_ptr(), dmid.data_ptr(), du.data_ptr(), u.numel(), int(act), _stream()), "kx_act_bwd")
     return du
 
 

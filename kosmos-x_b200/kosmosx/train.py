@@ -54,7 +54,7 @@ class KosmosTrainer:
                  train_resampler: bool = True, layout_only: bool = False, loss_rule: str = "reference",
                  pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.bfloat16,
                  distributed: bool | None = None, dropout: float | None = None, attention_dropout: float | None = None,
-                 seed: int = 0, bwd_max_ctas: int = 0, recompute: bool = False):
+                 seed: int = 0, bwd_max_ctas: int = 0, recompute: bool = False, train_clip_last_layer: bool = False):
         """overlap_all_reduce: False (default) = ONE all-reduce of the whole flat gradient buffer after backward; True = per-layer
         buckets issued while backward is still running.  Measured on 2 and 8 B200s (profiles/r2_nccl_overlap.md): NCCL's kernels
         occupy SMs that the persistent, one-CTA-per-SM backward kernels are sized for, so every GEMM / LayerNorm-backward
@@ -77,6 +77,9 @@ class KosmosTrainer:
         recompute: activation checkpointing per decoder layer (the reference wraps the decoder with torch's checkpoint_wrapper,
         train.py:84-110,528-529): the forward keeps only each layer's fp32 input (134 MB per layer at C3 instead of 1.28 GB) and
         backward re-runs the layer before differentiating it — bit-identical gradients for one more decoder forward per step.
+        train_clip_last_layer: also train the last encoder layer of the CLIP ViT (the reference freezes CLIP except its last
+        layer, notes.txt:537-538 / model.py:184-190); the other 23 stay frozen on the inference kernels.  Needs train_resampler
+        (the gradient reaches the ViT through the resampler's norm_media).
         bwd_max_ctas: > 0 caps the grid of the persistent backward GEMMs (they are sized to one CTA per SM; an NCCL kernel
         resident on a few SMs while they launch would push the CTAs that do not fit into a second wave)."""
         if optimizer not in ("adamw", "lion"):
@@ -102,6 +105,9 @@ class KosmosTrainer:
         self.pg = process_group
         self.overlap = overlap_all_reduce
         self.train_resampler = train_resampler
+        self.train_clip_last = bool(train_clip_last_layer)
+        if self.train_clip_last and not train_resampler:
+            raise ValueError("train_clip_last_layer needs train_resampler=True (the gradient reaches the ViT through the resampler)")
         self.world = 1
         if distributed is not False and (process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
@@ -146,9 +152,20 @@ class KosmosTrainer:
                 nodecay += [attn.norm_media.weight, attn.norm_media.bias, attn.norm_latents.weight, attn.norm_latents.bias,
                             ff[0].weight, ff[0].bias]
             vd.append(m.image_proj.weight)
+            nodecay += [pv.norm.weight, pv.norm.bias, pv.latents, pv.media_pos_emb]
+            self.clip_last = None
+            if self.train_clip_last:             # last CLIP encoder layer: q|k|v adjacent like a decoder layer's
+                Lc = m.clip_model.encoder.layers[-1]
+                a = Lc.self_attn
+                self.clip_last = dict(q=a.q_proj, k=a.k_proj, v=a.v_proj, o=a.out_proj, fc1=Lc.mlp.fc1, fc2=Lc.mlp.fc2,
+                                      ln1=Lc.layer_norm1, ln2=Lc.layer_norm2)
+                vd += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.out_proj.weight, Lc.mlp.fc1.weight, Lc.mlp.fc2.weight]
+                nodecay += [a.q_proj.bias, a.k_proj.bias, a.v_proj.bias, a.out_proj.bias, Lc.mlp.fc1.bias, Lc.mlp.fc2.bias,
+                            Lc.layer_norm1.weight, Lc.layer_norm1.bias, Lc.layer_norm2.weight, Lc.layer_norm2.bias]
+                if cfg.vit_dim % _ALIGN:
+                    raise ValueError("train_clip_last_layer: vit_dim must be a multiple of 64")
             decay += vd
             self.n_vision_decay_params = len(vd)
-            nodecay += [pv.norm.weight, pv.norm.bias, pv.latents, pv.media_pos_emb]
         d = cfg.dim
         for q, k, v in ((L["q"], L["k"], L["v"]) for L in self.layers):
             if q.weight.numel() % _ALIGN or q.bias.numel() % _ALIGN:
@@ -193,8 +210,18 @@ class KosmosTrainer:
         """Re-derive the bf16 tensor-core copies from the fp32 master weights (after load_state_dict or any
         in-place edit of the parameters).  The optimizer kernels keep them in sync afterwards."""
         ops.cast_bf16(self.P[:self.n_decay], self.W16)
-        self.model.decoder._packed = None            # the inference path re-stages its folded weights lazily
-        self.model._resampler_dirty = True
+        self._inference_copies_stale()
+
+    def _inference_copies_stale(self):
+        """The inference path re-stages its folded / split weights lazily from the fp32 masters."""
+        m = self.model
+        m.decoder._packed = None
+        if self.train_resampler:
+            m._resampler_dirty = True
+        if self.train_clip_last:
+            m._clip_last_dirty = True
+        if getattr(m, "_acc", None) is not None:
+            m._acc.invalidate()
 
     def _w16(self, p):
         s = self.seg[id(p)]
@@ -231,11 +258,17 @@ class KosmosTrainer:
         dp = m.decoder
         # frozen vision side on the inference kernels: image rows of x0 (+ their positions)
         x = self._buf("x0", (M, D), f32)
-        xv = m._vit(images, media=len(img_rows))
+        clip = None
+        if self.train_clip_last:                 # 23 frozen layers on the inference kernels, the last one kept for backward
+            clip = self._clip_last_forward(m._vit(images, media=len(img_rows), upto=-1), B * len(img_rows))
+            xv = clip["xv"]
+        else:
+            xv = m._vit(images, media=len(img_rows))
         pos = m.embed_positions.weight
         vis = None
         if self.train_resampler:
             vis = self._resampler_forward(xv, B, x, T, img_rows, pos)
+            vis["clip"] = clip
         else:
             m._perceive_project(xv, B, x, T, img_rows, pos_table=pos)
         ops.embed_splice_pos(text_tokens, m.embed.weight, pos, x, img_rows=img_rows, n_img=Lq, err_flag=m._err_flag(),
@@ -304,6 +337,78 @@ class KosmosTrainer:
         ops.gemm(s["g_ln"], self._w16(L["fc2"].weight), x_out, bias=L["fc2"].bias, res=s["x_mid"], drop=(pd, li * 4 + 1, dseed))
         s["x_out"] = x_out
         return s
+
+    # ------------------------------------------------------------------ last CLIP encoder layer (optional fine-tuning)
+    def _clip_last_forward(self, x_in, N):
+        """CLIPEncoderLayer.forward ([HF] modeling_clip.py:380-410) of the LAST ViT layer on the trainer's bf16 weight copies,
+        keeping what backward needs: x_mid = x + out_proj(attn(qkv(LN1 x))), xv = x_mid + fc2(act(fc1(LN2 x_mid))).
+        x_in: the stream after the frozen layers, fp32 [N*Tv, Dv] (a workspace of the model: copied)."""
+        cfg, L = self.cfg, self.clip_last
+        Tv, Dv, Hv, Fm = cfg.vit_tokens, cfg.vit_dim, cfg.vit_heads, cfg.vit_mlp
+        M = N * Tv
+        bf, f32 = torch.bfloat16, torch.float32
+        s = dict(N=N)
+        s["x_in"] = self._buf("c_xin", (M, Dv), f32)
+        s["x_in"].copy_(x_in)
+        for name, shape, dt in (("h1", (M, Dv), bf), ("qkv", (M, 3 * Dv), bf), ("att", (M, Dv), bf), ("x_mid", (M, Dv), f32),
+                                ("h2", (M, Dv), bf), ("u", (M, Fm), bf), ("mid", (M, Fm), bf), ("xv", (M, Dv), f32),
+                                ("lse", (Hv, N, ops.lse_pad(Tv)), f32)):
+            s[name] = self._buf("c_" + name, shape, dt)
+        act = _abi.KX_ACT_GELU if cfg.vit_act == "gelu" else _abi.KX_ACT_QUICK_GELU
+        wqkv, _ = self._qkv(L, "weight")
+        bqkv, _ = self._qkv(L, "bias")
+        ops.layernorm(s["x_in"], L["ln1"].weight, L["ln1"].bias, s["h1"], eps=cfg.eps)
+        ops.gemm(s["h1"], wqkv, s["qkv"], bias=bqkv)
+        qkv = s["qkv"]
+        ops.attention(qkv[:, :Dv], qkv[:, Dv:2 * Dv], qkv[:, 2 * Dv:], s["att"], batch=N, heads=Hv, seq_len=Tv, causal=False,
+                      scale=(Dv // Hv) ** -0.5, lse_out=s["lse"])
+        ops.gemm(s["att"], self._w16(L["o"].weight), s["x_mid"], bias=L["o"].bias, res=s["x_in"])
+        ops.layernorm(s["x_mid"], L["ln2"].weight, L["ln2"].bias, s["h2"], eps=cfg.eps)
+        ops.gemm(s["h2"], self._w16(L["fc1"].weight), s["u"], bias=L["fc1"].bias)
+        ops.gelu_fwd(s["u"], s["mid"], act)
+        ops.gemm(s["mid"], self._w16(L["fc2"].weight), s["xv"], bias=L["fc2"].bias, res=s["x_mid"])
+        return s
+
+    def _clip_last_backward(self, s, dxv, dxvb):
+        """Parameter gradients of the last ViT layer from dxv = d(loss)/d(ViT output) (fp32) and its bf16 copy dxvb; nothing
+        flows further (the layers below are frozen)."""
+        cfg, L = self.cfg, self.clip_last
+        Tv, Dv, Hv, Fm = cfg.vit_tokens, cfg.vit_dim, cfg.vit_heads, cfg.vit_mlp
+        N = s["N"]
+        M = N * Tv
+        bf, f32 = torch.bfloat16, torch.float32
+        act = _abi.KX_ACT_GELU if cfg.vit_act == "gelu" else _abi.KX_ACT_QUICK_GELU
+        dmid = self._buf("c_dmid", (M, Fm), bf)
+        du = self._buf("c_du", (M, Fm), bf)
+        dh = self._buf("c_dh", (M, Dv), bf)
+        datt = self._buf("c_datt", (M, Dv), bf)
+        dqkv = self._buf("c_dqkv", (M, 3 * Dv), bf)
+        dq_acc = self._buf("c_dqacc", (M, Dv), f32)
+        delta = self._buf("c_delta", (Hv, N, ops.lse_pad(Tv), 2), f32)
+        part = self._buf("c_part", (3, ops.ln_bwd_partials(M), Dv), f32)
+        # MLP: xv = x_mid + fc2(act(fc1(LN2(x_mid))))
+        ops.colsum(dxvb, self._g(L["fc2"].bias))
+        ops.gemm(dxvb, self._w16(L["fc2"].weight), dmid, b_trans=True)
+        ops.gemm(dxvb, s["mid"], self._g(L["fc2"].weight), a_trans=True, b_trans=True)
+        ops.gelu_bwd(s["u"], dmid, du, act)
+        ops.colsum(du, self._g(L["fc1"].bias))
+        ops.gemm(du, self._w16(L["fc1"].weight), dh, b_trans=True)
+        ops.gemm(du, s["h2"], self._g(L["fc1"].weight), a_trans=True, b_trans=True)
+        ops.layernorm_bwd(s["x_mid"], dh, L["ln2"].weight, dxv, self._g(L["ln2"].weight), self._g(L["ln2"].bias), part,
+                          eps=cfg.eps, dres=dxv, dxb=dxvb, d_colsum=self._g(L["o"].bias))
+        # attention: x_mid = x_in + out_proj(attn(qkv(LN1(x_in))))
+        ops.gemm(dxvb, self._w16(L["o"].weight), datt, b_trans=True)
+        ops.gemm(dxvb, s["att"], self._g(L["o"].weight), a_trans=True, b_trans=True)
+        qkv = s["qkv"]
+        ops.attention_bwd(qkv[:, :Dv], qkv[:, Dv:2 * Dv], qkv[:, 2 * Dv:], s["att"], datt, s["lse"], dqkv[:, :Dv],
+                          dqkv[:, Dv:2 * Dv], dqkv[:, 2 * Dv:], dq_acc, delta, batch=N, heads=Hv, seq_len=Tv, causal=False,
+                          scale=(Dv // Hv) ** -0.5)
+        wqkv, gwqkv = self._qkv(L, "weight")
+        _, gbqkv = self._qkv(L, "bias")
+        ops.colsum(dqkv, gbqkv)
+        ops.gemm(dqkv, wqkv, dh, b_trans=True)
+        ops.gemm(dqkv, s["h1"], gwqkv, a_trans=True, b_trans=True)
+        ops.layernorm_bwd(s["x_in"], dh, L["ln1"].weight, dxv, self._g(L["ln1"].weight), self._g(L["ln1"].bias), part, eps=cfg.eps)
 
     # ------------------------------------------------------------------ perceiver resampler + image_proj (trainable)
     def _resampler_forward(self, xv, B, x0, T, img_rows, pos):
@@ -380,7 +485,12 @@ class KosmosTrainer:
         dkv = self._buf("v_dkv", (N * (Tv + Lq), 2 * inner), bf)
         dcat = self._buf("v_dcat", (N * (Tv + Lq), Dv), bf)
         dxn = self._buf("v_dxn", (N * Tv, Dv), bf)
-        dxm = self._buf("v_dxm", (B * Tv, Dv), f32)
+        clip = vs.get("clip")
+        # d(loss)/d(ViT output): thrown away while CLIP is frozen (one block of scratch), summed over the resampler's layers
+        # when its last layer trains
+        dxm = self._buf("v_dxm", (N * Tv if clip else B * Tv, Dv), f32)
+        dxmb = self._buf("v_dxmb", (N * Tv, Dv), bf) if clip else None
+        n_pl = len(pv.layers)
         part_m = self._buf("v_partm", (3, ops.ln_bwd_partials(B * Tv), Dv), f32)
         g_mp = self._g(pv.media_pos_emb).view(-1, Dv)
         mp = pv.media_pos_emb.view(-1, Dv)
@@ -410,9 +520,16 @@ class KosmosTrainer:
             ops.gather_rows(dcat, dxn, grp=(Tv, Tv + Lq, 0))
             for i in range(nm):
                 blk = slice(i * B * Tv, (i + 1) * B * Tv)
-                ops.layernorm_bwd(vs["xv"][blk], dxn[blk], attn.norm_media.weight, dxm, self._g(attn.norm_media.weight),
-                                  self._g(attn.norm_media.bias), part_m, pre_add=mp[i], d_colsum=g_mp[i], accumulate=True)
+                dst = dxm[blk] if clip else dxm
+                # d_colsum sums dx INCLUDING dres: with the running sum in dst, media_pos_emb[i]'s gradient (the sum over the
+                # layers of each one's column sums) is the column sum of the last call's total
+                ops.layernorm_bwd(vs["xv"][blk], dxn[blk], attn.norm_media.weight, dst, self._g(attn.norm_media.weight),
+                                  self._g(attn.norm_media.bias), part_m, pre_add=mp[i], accumulate=True,
+                                  d_colsum=g_mp[i] if not clip or li == 0 else None,
+                                  dres=dst if clip and li < n_pl - 1 else None, dxb=dxmb[blk] if clip and li == 0 else None)
         ops.sum_rows_f32(dlat.view(N, Lq * Dv), self._g(pv.latents).view(-1))
+        if clip:
+            self._clip_last_backward(clip, dxm, dxmb)
 
     # ------------------------------------------------------------------ loss + backward
     def _backward(self, fw, text_tokens, img_rows, dlogits_in=None, accumulate=False):
@@ -608,9 +725,7 @@ class KosmosTrainer:
             else:
                 ops.lion_step(self.P[lo:hi], self.G[lo:hi], self.M1[lo:hi], wb, lr=lr, betas=self.betas, weight_decay=wd,
                               grad_scale=sc[3:4])
-        self.model.decoder._packed = None
-        if self.train_resampler:
-            self.model._resampler_dirty = True
+        self._inference_copies_stale()
 
     # ------------------------------------------------------------------ public API
     def _prepare(self, text_tokens, images, image_positions):

@@ -103,6 +103,35 @@ def test_gradient_bucket_plan_tiles_the_flat_buffer():
                                                     and "embed" not in by_id[id(p)])
 
 
+def test_bucket_plan_with_the_last_clip_layer_unfrozen():
+    """train_clip_last_layer=True (notes.txt:537-538): the last ViT layer's 16 tensors join the tail buckets (its gradient is
+    the last one backward produces), q|k|v adjacent, Linear weights in the decay segment; the plan still tiles the buffer."""
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, KosmosConfig, KosmosTrainer
+    oc = ko.OracleConfig.tiny(layers=3)
+    model = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
+    base = KosmosTrainer(model, layout_only=True)
+    tr = KosmosTrainer(model, layout_only=True, train_clip_last_layer=True)
+    assert len(tr.params) == len(base.params) + 16
+    plan = tr.bucket_plan()
+    spans = sorted((lo, hi) for _, lo, hi in plan)
+    assert spans[0][0] == 0 and spans[-1][1] == tr.n_total
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+    by_id = {id(p): n for n, p in model.named_parameters()}
+    last = f"clip_model.encoder.layers.{oc.vit_layers - 1}."
+    clip = [p for p in tr.params if by_id[id(p)].startswith("clip_model")]
+    assert len(clip) == 16 and all(by_id[id(p)].startswith(last) for p in clip)
+    for p in clip:
+        s = tr.seg[id(p)]
+        assert [n for n, lo, hi in plan if lo <= s.off and s.off + s.numel <= hi] == ["tail"]
+        assert (s.off < tr.n_decay) == (p.ndim == 2)
+    a = model.clip_model.encoder.layers[-1].self_attn
+    sq, sk, sv = (tr.seg[id(x.weight)] for x in (a.q_proj, a.k_proj, a.v_proj))
+    assert sk.off == sq.off + sq.numel and sv.off == sk.off + sk.numel
+    with pytest.raises(ValueError):
+        KosmosTrainer(model, layout_only=True, train_clip_last_layer=True, train_resampler=False)
+
+
 def _bucket_worker(rank, world, port, out):
     os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
