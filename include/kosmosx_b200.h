@@ -132,7 +132,7 @@ int kx_attn_set_trace(long long* device_buffer);
  * model.py:231): per (batch, head) softmax(q.k^T * scale - rowmax) . v with n_q latent queries and
  * n_kv = media + latent keys, head_dim 64.  q: [batch*n_q, ld_q], kv: [batch*n_kv, ld_kv] with
  * k at column head*64 and v at column v_col_off + head*64.  out: bf16 [batch*n_q, ld_out].
- */
+ * Runs on the tensor-core flash kernel of kx_attn_fwd (its keys-per-sequence != queries-per-sequence form). */
 int kx_perceiver_xattn_fwd(const void* q, long long ld_q, const void* kv, long long ld_kv, int v_col_off, void* out,
                            long long ld_out, int batch, int heads, int n_q, int n_kv, float scale,
                            kx_stream_t stream);

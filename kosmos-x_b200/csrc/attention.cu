@@ -5,9 +5,9 @@
 #include "philox.cuh"
 
 namespace kx {
-int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
-                   int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, cudaStream_t stream,
-                   float inv_keep, const uint32_t* row_mask);   // attention_pp.cu
+int launch_attn_pp(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv, void* out, long long ld_out,
+                   int batch, int heads, int seq_len, int kv_len, int causal, float scale, float* stats_out, float* lse_out,
+                   cudaStream_t stream, float inv_keep, const uint32_t* row_mask);   // attention_pp.cu
 
 // keep probability as the 12-bit fixed-point fraction the bit-sliced mask generator realises exactly
 inline unsigned attn_keep_thr12(float drop_p) { return static_cast<unsigned>((1.0 - static_cast<double>(drop_p)) * 4096.0 + 0.5); }
@@ -67,7 +67,8 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, long long 
     }
     if (device_sm_count() <= 0) return KX_ERR_NO_DEVICE;
     if (stats_out && (reinterpret_cast<uintptr_t>(stats_out) & 7)) { set_error("kx_attn_fwd: stats_out must be 8-byte aligned"); return KX_ERR_ARG; }
-    return launch_attn_pp(q, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, causal, scale, stats_out, lse_out, stream, inv_keep, row_mask);
+    return launch_attn_pp(q, ld_qkv, k, v, ld_qkv, out, ld_out, batch, heads, seq_len, seq_len, causal, scale, stats_out, lse_out, stream,
+                          inv_keep, row_mask);
 }
 
 extern "C" int kx_attn_fwd(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out,

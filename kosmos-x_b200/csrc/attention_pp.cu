@@ -1,9 +1,8 @@
-// attn_pp_kernel: flash-attention forward, head_dim 64, "ping-pong" variant (the default path of
-// kx_attn_fwd; attention.cu keeps the first-generation kernel, selectable with KX_ATTN_IMPL=0).
-//
-// Same contract as attention.cu (torchscale MultiheadAttention core, SURVEY.md A.4 / HF CLIPAttention
-// [HF] modeling_clip.py:318-331), reorganised around what limited the first kernel (ncu, profiles/):
-// issue slots and TMEM re-reads in the softmax, not the tensor pipe.
+// attn_pp_kernel: flash-attention forward, head_dim 64, "ping-pong" kernel behind kx_attn_fwd* (torchscale
+// MultiheadAttention core, SURVEY.md A.4 / HF CLIPAttention [HF] modeling_clip.py:318-331) and, with kv_len != seq_len,
+// behind kx_perceiver_xattn_fwd (flamingo_pytorch PerceiverAttention, SURVEY.md A.2: 64 latent queries over
+// 257 media tokens + 64 latents).  Organised around what limits attention at head_dim 64 (ncu, profiles/): issue slots
+// and TMEM re-reads in the softmax, not the tensor pipe.
 //
 // One CTA = TWO 128-row query tiles (A, B) of one (batch, head) sharing every K/V block; 1 CTA/SM.
 //   warps 0-3  softmax of tile A   } thread == query row.  S row read ONCE from TMEM into registers
@@ -21,7 +20,7 @@
 #include "kx_internal.h"
 #include "ptx.cuh"
 #include "philox.cuh"
-#include <cstdlib>
+#include <mutex>
 
 namespace kx {
 
@@ -41,7 +40,7 @@ constexpr float PP_RESCALE_THRESHOLD = 8.0f;         // log2 units
 struct AttnPPParams {
     __nv_bfloat16* out;
     long long ld_out;
-    int seq_len, heads, batch, num_pairs;
+    int seq_len, kv_len, heads, batch, num_pairs;    // queries / keys per (batch, head); kv_len == seq_len unless cross-attention
     float scale_log2;                                // scale * log2(e)
     float2* stats_out;                               // [heads][batch*seq_len] partial (sum, sumsq) of the stored row, or null
     long long total_rows;
@@ -71,7 +70,7 @@ __device__ __forceinline__ int pp_sched(int n, int cta, int grid) {
     return n * grid + ((n & 1) ? grid - 1 - cta : cta);
 }
 struct PPItem {
-    int pair, head, b, nblk0, nblk1, q0, row_base;
+    int pair, head, b, nblk0, nblk1, q0, row_base, kv_base;
 };
 template <bool CAUSAL>
 __device__ __forceinline__ PPItem pp_item(const AttnPPParams& p, int item) {
@@ -81,11 +80,12 @@ __device__ __forceinline__ PPItem pp_item(const AttnPPParams& p, int item) {
     const int r = item % bh;
     it.head = r % p.heads;
     it.b = r / p.heads;
-    const int nkv = (p.seq_len + 127) >> 7;
+    const int nkv = (p.kv_len + 127) >> 7;
     it.nblk0 = CAUSAL ? min(2 * it.pair + 1, nkv) : nkv;
     it.nblk1 = CAUSAL ? min(2 * it.pair + 2, nkv) : nkv;
     it.q0 = it.pair * 256;
     it.row_base = it.b * p.seq_len;
+    it.kv_base = it.b * p.kv_len;
     return it;
 }
 
@@ -112,7 +112,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int T = p.seq_len;
+    const int T = p.seq_len, Tk = p.kv_len;
     const int num_items = p.num_pairs * p.heads * p.batch;
     const int grid = gridDim.x;
 
@@ -159,10 +159,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         const uint32_t s = kv % PP_KV_STAGES, ph = (kv / PP_KV_STAGES) & 1;
                         mbar_wait(&k_empty[s], ph ^ 1);
                         mbar_arrive_expect_tx(&k_full[s], PP_TILE_BYTES);
-                        tma_load_2d(&tmK, &k_full[s], smem + PP_SMEM_K + s * PP_TILE_BYTES, it.head * 64, it.row_base + j * 128, kEvictLast);
+                        tma_load_2d(&tmK, &k_full[s], smem + PP_SMEM_K + s * PP_TILE_BYTES, it.head * 64, it.kv_base + j * 128, kEvictLast);
                         mbar_wait(&v_empty[s], ph ^ 1);
                         mbar_arrive_expect_tx(&v_full[s], PP_TILE_BYTES);
-                        tma_load_2d(&tmV, &v_full[s], smem + PP_SMEM_V + s * PP_TILE_BYTES, it.head * 64, it.row_base + j * 128, kEvictLast);
+                        tma_load_2d(&tmV, &v_full[s], smem + PP_SMEM_V + s * PP_TILE_BYTES, it.head * 64, it.kv_base + j * 128, kEvictLast);
                     }
                 }
             }
@@ -308,9 +308,9 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 2);
 
             // ---- mask: only the diagonal block (causal) and the ragged tail block
-            const bool need_mask = (kv0 + 128 > T) || (CAUSAL && (kv0 + 127 > q0 + w * 128));
+            const bool need_mask = (kv0 + 128 > Tk) || (CAUSAL && (kv0 + 127 > q0 + w * 128));
             if (need_mask) {
-                int limit = T - kv0;
+                int limit = Tk - kv0;
                 if (CAUSAL) limit = min(limit, qrow - kv0 + 1);
 #pragma unroll
                 for (int i = 0; i < 128; ++i)
@@ -449,18 +449,20 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 8) tmem_dealloc<1>(tmem_base, PP_TMEM_COLS);
 }
 
-int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
-                   int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, cudaStream_t stream,
-                   float inv_keep, const uint32_t* row_mask) {
-    const unsigned long long rows = (unsigned long long)batch * seq_len;
+int launch_attn_pp(const void* q, long long ld_q, const void* k, const void* v, long long ld_kv, void* out, long long ld_out,
+                   int batch, int heads, int seq_len, int kv_len, int causal, float scale, float* stats_out, float* lse_out,
+                   cudaStream_t stream, float inv_keep, const uint32_t* row_mask) {
+    const unsigned long long rows = (unsigned long long)batch * seq_len, kv_rows = (unsigned long long)batch * kv_len;
+    if (causal && kv_len != seq_len) { set_error("kx_attn_fwd: causal attention needs as many keys as queries"); return KX_ERR_ARG; }
     CUtensorMap tq, tk, tv;
-    if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
-    if (!make_tmap_bf16_2d(&tk, k, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
-    if (!make_tmap_bf16_2d(&tv, v, (uint64_t)heads * 64, rows, ld_qkv * 2, 64, 128)) return KX_ERR_TMAP;
+    if (!make_tmap_bf16_2d(&tq, q, (uint64_t)heads * 64, rows, ld_q * 2, 64, 128)) return KX_ERR_TMAP;
+    if (!make_tmap_bf16_2d(&tk, k, (uint64_t)heads * 64, kv_rows, ld_kv * 2, 64, 128)) return KX_ERR_TMAP;
+    if (!make_tmap_bf16_2d(&tv, v, (uint64_t)heads * 64, kv_rows, ld_kv * 2, 64, 128)) return KX_ERR_TMAP;
     AttnPPParams p;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ld_out = ld_out;
     p.seq_len = seq_len;
+    p.kv_len = kv_len;
     p.heads = heads;
     p.batch = batch;
     p.num_pairs = (seq_len + 255) / 256;
@@ -472,16 +474,18 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     p.trace = g_attn_trace;
     p.row_mask = reinterpret_cast<const uint4*>(row_mask);
     p.inv_keep = inv_keep;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::once_flag attr_once;
+    static bool attr_ok = false;
+    std::call_once(attr_once, [] {
         cudaError_t e1 = cudaFuncSetAttribute(attn_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
         cudaError_t e2 = cudaFuncSetAttribute(attn_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attn_pp_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            set_error("kx_attn_fwd: cudaFuncSetAttribute failed");
-            return KX_ERR_LAUNCH;
-        }
-        attr_set = true;
+        cudaError_t e3 = cudaFuncSetAttribute(attn_pp_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        cudaError_t e4 = cudaFuncSetAttribute(attn_pp_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
+        attr_ok = e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess;
+    });
+    if (!attr_ok) {
+        set_error("kx_attn_fwd: cudaFuncSetAttribute failed");
+        return KX_ERR_LAUNCH;
     }
     const long long items = static_cast<long long>(p.num_pairs) * heads * batch;
     const int sms = device_sm_count();
@@ -489,11 +493,6 @@ int launch_attn_pp(const void* q, const void* k, const void* v, long long ld_qkv
     if (items > 0x7fffffffLL) { set_error("kx_attn_fwd: too many tiles"); return KX_ERR_ARG; }
     dim3 grid(static_cast<unsigned>(items < sms ? items : sms));    // persistent: one CTA per SM, static item schedule
     if (p.trace != nullptr && causal) {          // profiling aid (kx_attn_set_trace): same kernel with clock64 stamps
-        static bool tattr = false;
-        if (!tattr) {
-            cudaFuncSetAttribute(attn_pp_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM_BYTES);
-            tattr = true;
-        }
         attn_pp_kernel<true, true, true><<<grid, PP_THREADS, PP_SMEM_BYTES, stream>>>(tq, tk, tv, p);
         return check_launch("kx_attn_fwd");
     }

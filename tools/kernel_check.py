@@ -803,17 +803,30 @@ def case_embed():
 
 
 def case_perceiver_attn():
+    """Cross-attention through the tensor-core flash kernel (kv_len != seq_len): the model's shape, ragged query / key counts,
+    a query count above one 128-row tile and above one tile pair; then the time of the model's launch (B = 8)."""
     torch.manual_seed(6)
-    B, H, nq, nkv = 2, 8, 64, 321
-    q = torch.randn(B * nq, H * 64, device=dev).bfloat16()
-    kv = torch.randn(B * nkv, 2 * H * 64, device=dev).bfloat16()
-    out = torch.zeros(B * nq, H * 64, device=dev, dtype=torch.bfloat16)
-    ops.perceiver_attention(q, kv, out, batch=B, heads=H, n_q=nq, n_kv=nkv, v_col_off=H * 64, scale=0.125)
-    qh = q.float().view(B, nq, H, 64).transpose(1, 2)
-    kh = kv[:, :H * 64].float().view(B, nkv, H, 64).transpose(1, 2)
-    vh = kv[:, H * 64:].float().view(B, nkv, H, 64).transpose(1, 2)
-    ref = ((qh @ kh.transpose(-1, -2)) * 0.125).softmax(-1) @ vh
-    return report("perceiver xattn", out, ref.transpose(1, 2).reshape(B * nq, H * 64), 2e-2)
+    ok = True
+    for B, H, nq, nkv in ((2, 8, 64, 321), (3, 2, 33, 130), (1, 4, 200, 77), (2, 3, 300, 321), (8, 8, 64, 321)):
+        q = torch.randn(B * nq, H * 64, device=dev).bfloat16()
+        kv = torch.randn(B * nkv, 2 * H * 64, device=dev).bfloat16()
+        out = torch.zeros(B * nq, H * 64, device=dev, dtype=torch.bfloat16)
+        ops.perceiver_attention(q, kv, out, batch=B, heads=H, n_q=nq, n_kv=nkv, v_col_off=H * 64, scale=0.125)
+        qh = q.float().view(B, nq, H, 64).transpose(1, 2)
+        kh = kv[:, :H * 64].float().view(B, nkv, H, 64).transpose(1, 2)
+        vh = kv[:, H * 64:].float().view(B, nkv, H, 64).transpose(1, 2)
+        ref = ((qh @ kh.transpose(-1, -2)) * 0.125).softmax(-1) @ vh
+        ok &= report(f"perceiver xattn B={B} H={H} {nq}x{nkv}", out, ref.transpose(1, 2).reshape(B * nq, H * 64), 2e-2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        ops.perceiver_attention(q, kv, out, batch=B, heads=H, n_q=nq, n_kv=nkv, v_col_off=H * 64, scale=0.125)
+    e0.record()
+    for _ in range(50):
+        ops.perceiver_attention(q, kv, out, batch=B, heads=H, n_q=nq, n_kv=nkv, v_col_off=H * 64, scale=0.125)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"  perceiver xattn B=8 H=8 64x321: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per launch (back to back)")
+    return ok
 
 
 def bench_gemm(M, N, K, cg, bn, iters=20):
