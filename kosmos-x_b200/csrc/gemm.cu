@@ -67,6 +67,7 @@ struct GemmCfg {
 
 struct GemmEpi {
     int M, N, K;
+    int raster_g, raster_nc, raster_nfast;   // tile order (tile_coords): m-blocks per group, n-blocks per chunk, which index runs fastest
     const float* bias;         // [N] fp32 or null
     const float* res;          // fp32 residual, indexed like out (row remap applied), or null
     long long ld_res;
@@ -98,15 +99,23 @@ struct GemmEpi {
     DropSpec drop;             // thr == 0: off
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
-    constexpr int G = 8;       // m-blocks per raster group: neighbours in time share B tiles in L2
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int G, int NC, bool n_fast, int& m_blk, int& n_blk) {
+    // Raster: groups of G m-blocks; inside a group, chunks of up to NC n-blocks; the tiles in flight at one time (one per
+    // cluster) then cover ~G x NC blocks, A and B footprints balanced.  Inside a chunk the index that runs fastest decides
+    // which operand's sharers get ADJACENT cluster ids (cluster launches map block ids to SM ids contiguously): n_fast puts
+    // the clusters sharing an A row-block next to each other.  Measured (profiles/r2_gemm_raster.md): n fastest in 8 x 8
+    // chunks cuts fc2's DRAM reads 915 -> 750 MB per launch; G = 16 when the weights are the larger operand (LM head) halves
+    // the passes over W, 1.19 -> 0.93 GB; step time equal within noise (the step is power-bound).  kx_gemm_bf16 picks them.
     const int per_group = G * num_n;
     const int g = t / per_group;
     const int first_m = g * G;
     const int gsz = min(G, num_m - first_m);
     const int r = t - g * per_group;
-    m_blk = first_m + r % gsz;
-    n_blk = r / gsz;
+    const int chunk = r / (gsz * NC);
+    const int w = min(NC, num_n - chunk * NC);
+    const int rr = r - chunk * gsz * NC;
+    m_blk = first_m + (n_fast ? rr / w : rr % gsz);
+    n_blk = chunk * NC + (n_fast ? rr % w : rr / gsz);
 }
 
 // bias -> [xPos rotation] -> activation on one 32-column chunk of row m (shared by both store paths)
@@ -403,9 +412,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================= TMA producer =================
         int s = 0;
         uint32_t ph = 0;
+        // W (K-major B) is re-read by every m-block group; the activations stream through once per group: keep W in L2
+        const uint64_t b_hint = (!ATR && !BTR) ? kEvictLast : kEvictNormal;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             int m_blk, n_blk;
-            tile_coords(t, num_m, num_n, m_blk, n_blk);
+            tile_coords(t, num_m, num_n, ep.raster_g, ep.raster_nc, ep.raster_nfast != 0, m_blk, n_blk);
             const int m0 = m_blk * (BLOCK_M * CG) + rank * BLOCK_M;
             const int n0 = n_blk * BN + rank * Cfg::B_ROWS;
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -418,7 +429,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     else
 #pragma unroll
                         for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(&tmA, &full[s], sa + c * MN_ATOM_BYTES, m0 + c * 64, kb * BLOCK_K);
-                    if constexpr (!BTR) tma_load_2d(&tmB, &full[s], sb, kb * BLOCK_K, n0);
+                    if constexpr (!BTR) tma_load_2d(&tmB, &full[s], sb, kb * BLOCK_K, n0, b_hint);
                     else
 #pragma unroll
                         for (int c = 0; c < Cfg::B_ROWS / 64; ++c) tma_load_2d(&tmB, &full[s], sb + c * MN_ATOM_BYTES, n0 + c * 64, kb * BLOCK_K);
@@ -429,7 +440,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     else
 #pragma unroll
                         for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d_cg2(&tmA, &full[s], sa + c * MN_ATOM_BYTES, m0 + c * 64, kb * BLOCK_K);
-                    if constexpr (!BTR) tma_load_2d_cg2(&tmB, &full[s], sb, kb * BLOCK_K, n0);
+                    if constexpr (!BTR) tma_load_2d_cg2(&tmB, &full[s], sb, kb * BLOCK_K, n0, b_hint);
                     else
 #pragma unroll
                         for (int c = 0; c < Cfg::B_ROWS / 64; ++c) tma_load_2d_cg2(&tmB, &full[s], sb + c * MN_ATOM_BYTES, n0 + c * 64, kb * BLOCK_K);
@@ -488,7 +499,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (!TMA_EPI) {
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 int m_blk, n_blk;
-                tile_coords(t, num_m, num_n, m_blk, n_blk);
+                tile_coords(t, num_m, num_n, ep.raster_g, ep.raster_nc, ep.raster_nfast != 0, m_blk, n_blk);
                 const int a = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 const int m = m_blk * (BLOCK_M * CG) + rank * BLOCK_M + q * 32 + lane;
@@ -538,7 +549,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             };
             for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
                 int m_blk, n_blk;
-                tile_coords(t, num_m, num_n, m_blk, n_blk);
+                tile_coords(t, num_m, num_n, ep.raster_g, ep.raster_nc, ep.raster_nfast != 0, m_blk, n_blk);
                 const int a = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 const int m_row0 = m_blk * (BLOCK_M * CG) + rank * BLOCK_M + q * 32;
@@ -565,7 +576,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int tn = t + num_clusters;
                     if (tn < num_tiles) {
                         int mb2, nb2;
-                        tile_coords(tn, num_m, num_n, mb2, nb2);
+                        tile_coords(tn, num_m, num_n, ep.raster_g, ep.raster_nc, ep.raster_nfast != 0, mb2, nb2);
                         const int mr = mb2 * (BLOCK_M * CG) + rank * BLOCK_M + q * 32;
                         const int nc = nb2 * BN + (c_begin + lane) * 32;
                         if (mr < ep.M && nc < ep.N) tma_prefetch_l2_2d(&tmRes, nc, mr);
@@ -845,6 +856,9 @@ extern "C" int kx_gemm_bf16(const void* A, long long lda, const void* W, long lo
     }
     GemmEpi ep = {};
     ep.M = g->M; ep.N = g->N; ep.K = g->K;
+    ep.raster_g = g->M >= g->N ? 8 : 16;      // tile order: see tile_coords
+    ep.raster_nc = 8;
+    ep.raster_nfast = 1;
     ep.bias = g->bias; ep.res = g->res; ep.ld_res = g->ld_res;
     ep.out = g->out; ep.ld_out = g->ld_out; ep.act = g->act;
     ep.grp_rows = g->grp_rows; ep.grp_stride = g->grp_stride; ep.grp_off = g->grp_off;
