@@ -165,34 +165,38 @@ act_layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, in
 // third partial (the bias gradient of the Linear whose output was added to the stream at this point).
 constexpr int LNB_STAGES = 3;
 
+// Four sums over the warp in 6 shuffles instead of 20: the first two butterfly steps halve the number of values a lane
+// carries (a lane keeps the pair / the value its own half will own and sends the other), the last three reduce the one that
+// is left.  On return lanes [8v, 8v + 8) hold the warp total of value v (a, b, c, d = 0..3) in `a`.  Fixed order: bit-reproducible.
+__device__ __forceinline__ void warp_sum4_owner(float& a, float b, float c, float d) {
+    const int lane = threadIdx.x & 31;
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    float k0 = hi16 ? c : a, k1 = hi16 ? d : b;
+    k0 += __shfl_xor_sync(0xffffffffu, hi16 ? a : c, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, hi16 ? b : d, 16);
+    float k = hi8 ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    a = k;
+}
+
 template <int THREADS>
 __device__ __forceinline__ void block_sum4_t(float& a, float& b, float& c, float& d, float* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-        d += __shfl_xor_sync(0xffffffffu, d, o);
-    }
     constexpr int W = THREADS / 32;
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { red[w] = a; red[W + w] = b; red[2 * W + w] = c; red[3 * W + w] = d; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    warp_sum4_owner(a, b, c, d);
+    if ((lane & 7) == 0) red[(lane >> 3) * W + w] = a;          // lanes 0 / 8 / 16 / 24 own value 0 / 1 / 2 / 3
     __syncthreads();
-    if constexpr (W <= 8) {
-        a = 0.f; b = 0.f; c = 0.f; d = 0.f;
-#pragma unroll
-        for (int i = 0; i < W; ++i) { a += red[i]; b += red[W + i]; c += red[2 * W + i]; d += red[3 * W + i]; }
-    } else {                                             // 32 warps: every warp folds the 4 x 32 partials with shuffles
-        const int l = threadIdx.x & 31;
-        a = red[l]; b = red[W + l]; c = red[2 * W + l]; d = red[3 * W + l];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-            c += __shfl_xor_sync(0xffffffffu, c, o);
-            d += __shfl_xor_sync(0xffffffffu, d, o);
-        }
-    }
+    // every warp folds the 4 x W partials the same way (W <= 32: one partial per lane and value) and broadcasts the totals
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    if (lane < W) { p0 = red[lane]; p1 = red[W + lane]; p2 = red[2 * W + lane]; p3 = red[3 * W + lane]; }
+    warp_sum4_owner(p0, p1, p2, p3);
+    a = __shfl_sync(0xffffffffu, p0, 0);
+    b = __shfl_sync(0xffffffffu, p0, 8);
+    c = __shfl_sync(0xffffffffu, p0, 16);
+    d = __shfl_sync(0xffffffffu, p0, 24);
     __syncthreads();
 }
 
