@@ -289,7 +289,10 @@ int kx_attn_bwd(const void* q, const void* k, const void* v, long long ld_qkv, c
  * query, key): Philox4x32-7 words bit-sliced into Bernoulli(keep) bits with keep = round((1 - p) * 4096) / 4096, 1 bit per
  * score, written in the two layouts the kernels' thread mappings want (nb = ceil(seq_len / 128); causal: only tiles
  * kb <= qb are written or read; kx_attn_dropout_mask_words() uint32 words each):
- *   row_mask[(((bh * nb + qb) * nb + kb) * 128 + r) * 4 + c]       bit b: query 128 qb + r keeps key 128 kb + 32 c + b
+ *   row_mask[(((bh * nb + qb) * nb + kb) * 128 + r) * 4 + c]       query 128 qb + r keeps key 128 kb + 32 c + k at bit
+ *                                                                  (k/2)%8 + 8 (k%2) + 16 (k/16)  (even / odd keys of each
+ *                                                                  16-key half in separate bytes: the forward kernel masks
+ *                                                                  bf16 pairs with one shift + one byte-permute per pair)
  *   key_mask[((((bh * nb + qb) * nb + kb) * 4 + g) * 128 + r]      bit i: query 128 qb + 32 g + i keeps key 128 kb + r
  * Forward: dropped probabilities are zeroed in the P operand of P.V, the row normaliser sums ALL probabilities, the
  * output is scaled by 1 / keep.  Backward: dV += (M o P / keep)^T dO, dS = P o (M o dP / keep - delta). */

@@ -13,8 +13,13 @@ int launch_attn_pp(const void* q, long long ld_q, const void* k, const void* v, 
 inline unsigned attn_keep_thr12(float drop_p) { return static_cast<unsigned>((1.0 - static_cast<double>(drop_p)) * 4096.0 + 0.5); }
 
 // One CTA per 128 x 128 tile of one (batch, head): thread = query row.  Four 32-key words per row go out row-major (the
-// forward kernel's thread = query row reads its uint4) and, transposed with one ballot per key, key-major (the backward
-// kernel's thread = key reads one word per query quarter).
+// forward kernel's thread = query row reads its uint4) and, transposed inside the warp, key-major (the backward kernel's
+// thread = key reads one word per query quarter).
+// The forward kernel masks P as bf16 PAIRS (keys 2j, 2j+1 share a register), so the keep bit of key k = 2j + e of a word is
+// DEFINED to be bit (j % 8) + 8 e + 16 (j / 8) of the Philox word: inside each 16-key half the even keys' bits sit in the
+// low byte and the odd keys' in the high byte, one shift puts both bits of a pair on the sign positions of two bytes and
+// one PRMT (sign-replicate mode) expands them to the pair mask.  The bits are i.i.d., so naming them this way costs nothing:
+// the row-major word is the raw word, and the transposed copy only stores its columns at the permuted key index.
 __global__ void __launch_bounds__(128)
 attn_dropout_mask_kernel(unsigned long long seed, uint32_t site, uint32_t thr12, int nb, int causal, uint4* __restrict__ row_mask,
                          uint32_t* __restrict__ key_mask) {
@@ -38,8 +43,9 @@ attn_dropout_mask_kernel(unsigned long long seed, uint32_t site, uint32_t thr12,
     const long long tile = (static_cast<long long>(bh) * nb + qb) * nb + kb;
     row_mask[tile * 128 + r] = make_uint4(w[0], w[1], w[2], w[3]);
     // key-major copy: 32 x 32 bit-matrix transpose inside the warp (5 butterfly steps of one shuffle each) — lane b ends up
-    // with bit i = keep(query 32g + i, key 32c + b)
+    // with bit i = (bit b of query 32g + i's word c) = keep(query 32g + i, key 32c + key_of_bit(b))
     uint32_t* dst = key_mask + tile * 512 + g * 128;
+    const int key_of_bit = 2 * ((lane >> 4) * 8 + (lane & 7)) + ((lane >> 3) & 1);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t x = w[c], m = 0x0000ffffu;
@@ -49,7 +55,7 @@ attn_dropout_mask_kernel(unsigned long long seed, uint32_t site, uint32_t thr12,
             x = (lane & j) ? ((x & ~m) | ((y & ~m) >> j)) : ((x & m) | ((y & m) << j));
             if (j > 1) m ^= m << (j >> 1);
         }
-        dst[c * 32 + lane] = x;
+        dst[c * 32 + key_of_bit] = x;
     }
 }
 }  // namespace kx

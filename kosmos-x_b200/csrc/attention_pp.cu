@@ -384,8 +384,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint32_t keepw[4] = {kw.x, kw.y, kw.z, kw.w};
 #pragma unroll
                 for (int i = 0; i < 64; ++i) {
-                    const uint32_t b2 = (keepw[i >> 4] >> ((i & 15) * 2)) & 3u;
-                    pv[i] &= ((b2 & 1u) ? 0x0000ffffu : 0u) | ((b2 & 2u) ? 0xffff0000u : 0u);
+                    // pair i = keys (2i, 2i + 1): their keep bits are 8 apart in the word (attention.cu: the definition of the keep bits); shift
+                    // them onto the sign bits of two bytes, PRMT replicates each sign over a 16-bit half -> the pair mask
+                    const int jj = i & 15;
+                    const uint32_t x = keepw[i >> 4] << (7 - (jj & 7));
+                    uint32_t m;
+                    if (jj < 8) asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(m) : "r"(x));
+                    else asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(m) : "r"(x));
+                    pv[i] &= m;
                 }
             }
             if (threadIdx.x == w * 128) KX_TRACE(w, j, 4);

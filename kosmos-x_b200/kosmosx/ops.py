@@ -195,8 +195,11 @@ def unpack_attn_row_mask(mask: torch.Tensor, batch: int, heads: int, seq_len: in
     """row_mask of attn_dropout_masks -> bool (batch, heads, seq_len, seq_len) [q, k] (test helper)."""
     nb = (seq_len + 127) // 128
     w = mask[:batch * heads * nb * nb * 512].view(batch, heads, nb, nb, 128, 4).to(torch.int64) & 0xffffffff     # [b,h,qb,kb,r,c]
-    bits = (w.unsqueeze(-1) >> torch.arange(32, device=mask.device)) & 1                                         # [..., r, c, bit]
-    keep = bits.permute(0, 1, 2, 4, 3, 5, 6).reshape(batch, heads, nb * 128, nb * 128)                             # q = qb,r ; k = kb,c,bit
+    # key k = 2j + e of a word sits at bit (j % 8) + 8 e + 16 (j / 8): the pair layout of attention.cu
+    k = torch.arange(32, device=mask.device)
+    pos = (k // 2) % 8 + 8 * (k % 2) + 16 * (k // 16)
+    bits = (w.unsqueeze(-1) >> pos) & 1                                                                          # [..., r, c, key]
+    keep = bits.permute(0, 1, 2, 4, 3, 5, 6).reshape(batch, heads, nb * 128, nb * 128)                             # q = qb,r ; k = kb,c,key
     return keep[:, :, :seq_len, :seq_len].bool()
 
 

@@ -923,6 +923,21 @@ def case_bench_train():
                                          dqkv[:, 2 * D:], acc, delta, batch=B, heads=H, seq_len=T, causal=True, scale=0.125))
     fl = 10.0 * B * H * T * T * 64 / 2
     print(f"attn_bwd B={B} H={H} T={T}: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s (causal-halved, 5 MMAs)")
+    # the same pair with attention dropout (keep bits drawn ahead by the mask kernel)
+    words = ops.attn_dropout_mask_words(B, H, T)
+    rows = torch.zeros(words, dtype=torch.int32, device=dev); keys = torch.zeros(words, dtype=torch.int32, device=dev)
+    ms = _time(lambda: ops.attn_dropout_masks(rows, keys, p=0.1, site=6, seed=99, batch=B, heads=H, seq_len=T))
+    print(f"attn_dropout_masks B={B} H={H} T={T}: {ms*1e3:.1f} us")
+    ms = _time(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125,
+                                     lse_out=lse, drop_p=0.1, row_mask=rows))
+    print(f"attn fwd + lse + dropout: {ms*1e3:.1f} us  {4.0 * B * H * T * T * 64 / 2 / ms / 1e9:.0f} TFLOP/s (causal-halved)")
+    ms = _time(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, batch=B, heads=H, seq_len=T, causal=True, scale=0.125,
+                                     lse_out=lse))
+    print(f"attn fwd + lse (no dropout): {ms*1e3:.1f} us")
+    ms = _time(lambda: ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, d_out, lse, dqkv[:, :D], dqkv[:, D:2 * D],
+                                         dqkv[:, 2 * D:], acc, delta, batch=B, heads=H, seq_len=T, causal=True, scale=0.125,
+                                         drop_p=0.1, drop_mask=keys))
+    print(f"attn_bwd + dropout: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s")
     # LayerNorm backward, residual form (n = 2048) and FFN form (n = 8192, GELU)
     x = torch.randn(M, D, device=dev); dy = torch.randn(M, D, device=dev).bfloat16()
     gamma = torch.ones(D, device=dev); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev); dc = torch.zeros(D, device=dev)
