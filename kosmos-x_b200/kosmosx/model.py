@@ -991,6 +991,9 @@ class Kosmos(_KosmosBase):
         cfg = self.cfg
         _require_cuda(text_tokens, "text_tokens")
         _require_cuda(images, "images")
+        tr = getattr(self, "_trainer", None)
+        if tr is not None:                # an external torch.optim stepped the fp32 masters since the copies were staged?
+            tr.refresh_if_stepped_externally()
         if text_tokens.dtype != torch.int64 or text_tokens.ndim != 2:
             raise TypeError("text_tokens must be an int64 tensor of shape (B, T_text)")
         planar = (3, cfg.image, cfg.image)
@@ -1076,7 +1079,7 @@ class Kosmos(_KosmosBase):
         the activations backward needs), returned as ONE autograd node whose backward is the hand-scheduled sm_100a
         backward pass.  Gradients land in ``param.grad`` (views of the trainer's flat buffer) and accumulate across
         backward calls like autograd's do until ``zero_grad()``; call backward once per forward; the CLIP tower and the multiway ``.B`` branches are
-        frozen; dropout is not applied.  A ``KosmosTrainer`` built on this model beforehand is used, else one is made
+        frozen; dropout follows the trainer's settings (the config's 0.1 / 0.1 unless overridden).  A ``KosmosTrainer`` built on this model beforehand is used, else one is made
         (``KosmosTrainer(model)``: flat fp32 master / gradient buffers)."""
         tr = getattr(self, "_trainer", None)
         if tr is None:

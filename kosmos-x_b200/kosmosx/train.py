@@ -210,12 +210,26 @@ class KosmosTrainer:
         """Re-derive the bf16 tensor-core copies from the fp32 master weights (after load_state_dict or any
         in-place edit of the parameters).  The optimizer kernels keep them in sync afterwards."""
         ops.cast_bf16(self.P[:self.n_decay], self.W16)
+        self._p_version = self._params_version()
         self._inference_copies_stale()
+
+    def _params_version(self):
+        """Sum of PyTorch's in-place version counters of the trained parameters (each ``Parameter`` keeps its own, even
+        though its storage is a slice of the flat buffer): changes whenever anything edits a parameter through PyTorch."""
+        return sum(p._version for p in self.params)
+
+    def refresh_if_stepped_externally(self):
+        """An external optimizer (the autograd-bridge loop) or ``load_state_dict`` edits the fp32 masters in place, which no
+        kernel of this library sees happen: PyTorch's version counters of the parameters tell.  Called by the inference entry
+        points of the model, so an eval forward / generate right after ``optimizer.step()`` runs on the stepped weights."""
+        if self._params_version() != self._p_version:
+            self.sync_weights()
 
     def _inference_copies_stale(self):
         """The inference path re-stages its folded / split weights lazily from the fp32 masters."""
         m = self.model
         m.decoder._packed = None
+        m._graphs = {}                           # captured forwards read the staged buffers that are about to be replaced
         if self.train_resampler:
             m._resampler_dirty = True
         if self.train_clip_last:

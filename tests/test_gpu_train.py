@@ -499,3 +499,44 @@ def test_activation_forward_backward_kernels(act):
     y.backward(d.float())
     assert (out.float() - y.detach()).abs().max().item() <= 2 ** -8 * y.detach().abs().max().item() + 1e-6
     assert ((du.float() - x.grad).abs() <= 2 ** -8 * x.grad.abs() + 2e-3).all()
+
+
+def test_inference_after_a_step_sees_the_new_weights_graphed_and_through_an_external_optimizer():
+    """ The inference path stages folded copies of the weights and, with cuda_graph=True, replays captured
+    forwards that read those copies.  After KosmosTrainer.step, and after an EXTERNAL torch.optim step through the autograd
+    bridge (which edits the fp32 masters in place, unseen by the library), the next eval forward must run on the new weights:
+    same logits as a fresh model loaded from the state_dict."""
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, KosmosConfig, KosmosTrainer
+    oc = ko.OracleConfig.tiny(max_positions=256)
+    ref = ko.build(oc, seed=0)
+    cfg = KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__})
+    text, images = ko.make_inputs(oc, 2, 30, seed=4)
+    tg, ig = text.cuda(), images.cuda()
+
+    def fresh_logits(model):
+        f = Kosmos(config=cfg)
+        f.load_state_dict(model.state_dict())
+        return f.cuda().eval()(tg, ig)
+
+    # 1. the fused step, forward replayed as a CUDA graph
+    mine = Kosmos(config=cfg, cuda_graph=True)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda().eval()
+    trainer = KosmosTrainer(mine, lr=3e-3, weight_decay=0.0, dropout=0.0, attention_dropout=0.0)
+    before = mine(tg, ig).clone()                    # captures the graph on the initial weights
+    for _ in range(2):
+        trainer.step(tg, ig)
+    after = mine(tg, ig)
+    assert not torch.equal(before, after)
+    assert torch.equal(after, fresh_logits(mine))
+    # 2. the autograd bridge with torch.optim.SGD
+    mine.train()
+    opt = torch.optim.SGD([p for p in mine.parameters() if p.requires_grad], lr=0.05)
+    logits = mine(tg, ig)
+    logits.float().square().mean().backward()
+    opt.step()
+    mine.eval()
+    stepped = mine(tg, ig)                           # no training forward in between: the version counter has to notice
+    assert not torch.equal(stepped, after)
+    assert torch.equal(stepped, fresh_logits(mine))
