@@ -25,7 +25,7 @@ for w in $what; do
       full gemm_lm_head gemm_bf16 24 1 python tools/profile_step.py --steps 1 --layers 2 --vit-layers 1;;
     full_train)
       full attn_bwd attn_bwd_kernel 1 1 python tools/profile_step.py --train --steps 1 --layers 2 --vit-layers 1
-      full attn_fwd_dropout "attn_pp_kernel" 2 1 python tools/profile_step.py --train --steps 1 --layers 2 --vit-layers 1
+      full attn_fwd_dropout "attn_pp_kernel<\(bool\)1, \(bool\)1, \(bool\)0, \(bool\)1" 0 1 python tools/profile_step.py --train --steps 1 --layers 2 --vit-layers 1
       full ln_bwd_gelu "layernorm_bwd_kernel<__nv_bfloat16, \(bool\)0, \(int\)1024" 0 1 python tools/profile_step.py --train --steps 1 --layers 2 --vit-layers 1
       full gemm_dgrad_wgrad gemm_bf16 34 4 python tools/profile_step.py --train --steps 1 --layers 2 --vit-layers 1
       full attn_dropout_masks attn_dropout_mask_kernel 0 1 python tools/profile_step.py --train --steps 1 --layers 2 --vit-layers 1;;
