@@ -12,6 +12,7 @@
 #include "kx_internal.h"
 #include "ptx.cuh"
 #include "philox.cuh"
+#include <mutex>
 
 namespace kx {
 
@@ -425,6 +426,217 @@ layernorm_bwd_kernel(const XT* __restrict__ x, long long ld_x, const float* __re
         store8(part_gamma + o, acc_g);
         store8(part_beta + o, acc_b);
         if (part_col != nullptr) store8(part_col + o, acc_c);
+    }
+}
+
+// ----------------------------------------------------------------------------- LN(gelu(u)) backward, wide rows (2048 < n <= 8192)
+// The ffn_layernorm backward of the decoder (n = 8192, 24 launches per step).  Same math as the GELU branch above, organised around
+// what ncu showed of it (1024 threads x 8 columns: 44 instructions per element, 46 % issue-active, 92 bytes of spills at the
+// 64-register budget, two block barriers per row with every warp in the same phase):
+//   * 512 threads x 16 columns (two 16-byte chunks per thread): the block reduction costs half as much per element and the
+//     128-register budget holds the three column accumulators AND gamma (no L1 re-reads);
+//   * two rows in flight per CTA, software-pipelined: an iteration runs phase A of row k+1 (Phi, a = u Phi, the four sums ->
+//     per-warp partials in smem) and phase B of row k (totals -> dx, column accumulators), ONE __syncthreads per row, and the
+//     fold of row k's partials (LDS + 10 shuffles) is independent of phase A, so ptxas interleaves the two;
+//   * nothing of a row is live in registers across the barrier: phase B re-reads u / dy from the ring slot and Phi from a
+//     thread-private fp32 stash in shared memory (written by phase A; same thread, same addresses: no hazard).
+// Ring: LNW_STAGES slots of (u, dy) filled by bulk copies two to three rows ahead; a slot is refilled after the barrier that
+// ends the iteration of its phase B.
+constexpr int LNW_THREADS = 512;
+constexpr int LNW_STAGES = 5;
+constexpr int LNW_STASH_BYTES = 4 * LNW_THREADS * 16;         // per buffer: [chunk][half][thread] float4
+
+template <bool FULL>                                          // FULL: n == 16 * LNW_THREADS, every thread owns two live chunks
+__global__ void __launch_bounds__(LNW_THREADS, 1)
+ln_gelu_bwd_wide_kernel(const __nv_bfloat16* __restrict__ x, long long ld_x, const __nv_bfloat16* __restrict__ dy, long long ld_dy,
+                        const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx, long long ld_dx,
+                        float* __restrict__ part_gamma, float* __restrict__ part_beta, float* __restrict__ part_col, int rows, int n) {
+    extern __shared__ __align__(128) uint8_t lnw_smem[];
+    __shared__ float red[2][4 * (LNW_THREADS / 32)];
+    __shared__ __align__(8) uint64_t full[LNW_STAGES];
+    constexpr int W = LNW_THREADS / 32;
+    const uint32_t row_bytes = static_cast<uint32_t>(n) * 2;  // one operand row (bf16); a slot holds u then dy
+    const uint32_t stage_bytes = 2 * row_bytes;
+    uint8_t* stash = lnw_smem + static_cast<size_t>(LNW_STAGES) * stage_bytes;
+    const float inv_n = 1.0f / static_cast<float>(n);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col[2] = {tid * 8, (LNW_THREADS + tid) * 8};
+    const bool live[2] = {FULL || col[0] < n, FULL || col[1] < n};
+    const int grid = gridDim.x;
+    const int n_rows = (rows - static_cast<int>(blockIdx.x) + grid - 1) / grid;      // rows blockIdx.x + k * grid, k < n_rows
+
+    auto issue = [&](int k) {                           // thread 0 only
+        const int s = k % LNW_STAGES;                   // (== the slot phase B of row k - LNW_STAGES just released)
+        const long long row = blockIdx.x + static_cast<long long>(k) * grid;
+        uint8_t* st = lnw_smem + static_cast<size_t>(s) * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        lnb_bulk_load(st, x + row * ld_x, row_bytes, &full[s]);
+        lnb_bulk_load(st + row_bytes, dy + row * ld_dy, row_bytes, &full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < LNW_STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        for (int k = 0; k < LNW_STAGES && k < n_rows; ++k) issue(k);
+    }
+
+    uint64_t gm2[2][4], acc_g[2][4], acc_b[2][4], acc_c[2][4];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        float g[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g[u] = 0.f;
+        if (live[c]) load8(gamma + col[c], g);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            gm2[c][p] = pack_f32x2(g[2 * p], g[2 * p + 1]);
+            acc_g[c][p] = 0ull; acc_b[c][p] = 0ull; acc_c[c][p] = 0ull;
+        }
+    }
+    __syncthreads();
+
+    // bf16x2 word -> f32x2: the low element is the word shifted up, the high one masked
+    auto widen = [](uint32_t w) { return pack_f32x2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
+
+    // ---- phase A of row k: Phi(u) -> stash[k & 1], per-warp partial sums of (a, a^2, g, g a) -> red[k & 1]
+    auto phase_a = [&](int k, int slot) {
+        const uint8_t* st = lnw_smem + static_cast<size_t>(slot) * stage_bytes;
+        uint8_t* sb = stash + (k & 1) * LNW_STASH_BYTES;
+        uint64_t s1p = 0ull, s2p = 0ull, sgp = 0ull, sgap = 0ull;
+        const uint64_t kz = pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint4 qx = make_uint4(0u, 0u, 0u, 0u), qd = make_uint4(0u, 0u, 0u, 0u);
+            if (live[c]) {
+                qx = *reinterpret_cast<const uint4*>(st + col[c] * 2);
+                qd = *reinterpret_cast<const uint4*>(st + row_bytes + col[c] * 2);
+            }
+            const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
+            uint64_t phi[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const uint64_t x2 = widen(wx[p]), d2 = widen(wd[p]);
+                float xl, xh_;
+                unpack_f32x2(x2, xl, xh_);
+                const uint64_t z = fmul2(pack_f32x2(fabsf(xl), fabsf(xh_)), kz);
+                uint64_t q = ffma2(z, pack_f32x2(-0.003024620935320854f, -0.003024620935320854f),
+                                   pack_f32x2(0.029882797971367836f, 0.029882797971367836f));
+                q = ffma2(q, z, pack_f32x2(-0.14901681244373322f, -0.14901681244373322f));
+                q = ffma2(q, z, pack_f32x2(-0.9183504581451416f, -0.9183504581451416f));
+                q = ffma2(q, z, pack_f32x2(-1.6279104948043823f, -1.6279104948043823f));
+                q = fmul2(q, z);
+                float q0, q1;
+                unpack_f32x2(q, q0, q1);
+                // Phi(x) = 0.5 + copysign(0.5 - 0.5 * erfc(|x| / sqrt2), x)
+                const uint64_t h = ffma2(pack_f32x2(ex2_approx(q0), ex2_approx(q1)), pack_f32x2(-0.5f, -0.5f), pack_f32x2(0.5f, 0.5f));
+                float h0, h1;
+                unpack_f32x2(h, h0, h1);
+                phi[p] = fadd2(pack_f32x2(copysignf(h0, xl), copysignf(h1, xh_)), pack_f32x2(0.5f, 0.5f));
+                const uint64_t av = fmul2(x2, phi[p]);
+                const uint64_t gv = fmul2(d2, gm2[c][p]);
+                s1p = fadd2(s1p, av);
+                s2p = ffma2(av, av, s2p);
+                sgp = fadd2(sgp, gv);
+                sgap = ffma2(gv, av, sgap);
+            }
+            *reinterpret_cast<ulonglong2*>(sb + ((c * 2 + 0) * LNW_THREADS + tid) * 16) = make_ulonglong2(phi[0], phi[1]);
+            *reinterpret_cast<ulonglong2*>(sb + ((c * 2 + 1) * LNW_THREADS + tid) * 16) = make_ulonglong2(phi[2], phi[3]);
+        }
+        float s1, s2, sg, sga, t0, t1;
+        unpack_f32x2(s1p, t0, t1); s1 = t0 + t1;
+        unpack_f32x2(s2p, t0, t1); s2 = t0 + t1;
+        unpack_f32x2(sgp, t0, t1); sg = t0 + t1;
+        unpack_f32x2(sgap, t0, t1); sga = t0 + t1;
+        warp_sum4_owner(s1, s2, sg, sga);
+        if ((lane & 7) == 0) red[k & 1][(lane >> 3) * W + warp] = s1;      // lanes 0 / 8 / 16 / 24 own value 0 / 1 / 2 / 3
+    };
+
+    // ---- row totals from the per-warp partials (every warp folds them the same way: bit-identical in all threads)
+    struct Totals { float mean, rstd, mg, mgx; };
+    auto fold = [&](int k) {
+        const float* r = red[k & 1];
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        if (lane < W) { p0 = r[lane]; p1 = r[W + lane]; p2 = r[2 * W + lane]; p3 = r[3 * W + lane]; }
+        warp_sum4_owner(p0, p1, p2, p3);
+        const float s1 = __shfl_sync(0xffffffffu, p0, 0), s2 = __shfl_sync(0xffffffffu, p0, 8);
+        const float sg = __shfl_sync(0xffffffffu, p0, 16), sga = __shfl_sync(0xffffffffu, p0, 24);
+        Totals t;
+        t.mean = s1 * inv_n;
+        t.rstd = rsqrtf(fmaxf(s2 * inv_n - t.mean * t.mean, 0.f) + eps);
+        t.mg = sg * inv_n;
+        t.mgx = t.rstd * (sga - t.mean * sg) * inv_n;              // mean(g * xhat)
+        return t;
+    };
+
+    // ---- phase B of row k: dx = LN backward * gelu'(u), column accumulators
+    auto phase_b = [&](int k, int slot, const Totals& t) {
+        const uint8_t* st = lnw_smem + static_cast<size_t>(slot) * stage_bytes;
+        const uint8_t* sb = stash + (k & 1) * LNW_STASH_BYTES;
+        const long long row = blockIdx.x + static_cast<long long>(k) * grid;
+        const uint64_t rs2 = pack_f32x2(t.rstd, t.rstd), nmr2 = pack_f32x2(-t.mean * t.rstd, -t.mean * t.rstd);
+        const uint64_t nmg2 = pack_f32x2(-t.mg, -t.mg), nmgx2 = pack_f32x2(-t.mgx, -t.mgx);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (!live[c]) continue;
+            const uint4 qx = *reinterpret_cast<const uint4*>(st + col[c] * 2);
+            const uint4 qd = *reinterpret_cast<const uint4*>(st + row_bytes + col[c] * 2);
+            const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(sb + ((c * 2 + 0) * LNW_THREADS + tid) * 16);
+            const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(sb + ((c * 2 + 1) * LNW_THREADS + tid) * 16);
+            const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w};
+            const uint64_t phi[4] = {f0.x, f0.y, f1.x, f1.y};
+            uint32_t ow[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const uint64_t x2 = widen(wx[p]), d2 = widen(wd[p]);
+                const uint64_t xh = ffma2(fmul2(x2, phi[p]), rs2, nmr2);                             // xhat
+                const uint64_t gv = fmul2(d2, gm2[c][p]);
+                uint64_t o = fmul2(ffma2(xh, nmgx2, fadd2(gv, nmg2)), rs2);                          // LayerNorm backward
+                const uint64_t xx = fmul2(fmul2(x2, x2), pack_f32x2(-0.72134752044448170368f, -0.72134752044448170368f));
+                float e0, e1;
+                unpack_f32x2(xx, e0, e1);
+                const uint64_t pdf = fmul2(pack_f32x2(ex2_approx(e0), ex2_approx(e1)), pack_f32x2(0.3989422804014327f, 0.3989422804014327f));
+                o = fmul2(o, ffma2(x2, pdf, phi[p]));                                                // * gelu'(x) = Phi + x phi
+                float o0, o1;
+                unpack_f32x2(o, o0, o1);
+                ow[p] = pack_bf16(o0, o1);
+                acc_g[c][p] = ffma2(d2, xh, acc_g[c][p]);
+                acc_b[c][p] = fadd2(d2, acc_b[c][p]);
+                acc_c[c][p] = fadd2(widen(ow[p]), acc_c[c][p]);   // column sums of what the next GEMM reads: the bf16-rounded values
+            }
+            *reinterpret_cast<uint4*>(dx + row * ld_dx + col[c]) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+    };
+
+    mbar_wait_lean(&full[0], 0);
+    phase_a(0, 0);
+    __syncthreads();
+    int sb_slot = 0, sa_slot = 1 % LNW_STAGES;          // ring slots of row k (phase B) and row k + 1 (phase A)
+    uint32_t sa_par = (1 / LNW_STAGES) & 1;
+    for (int k = 0; k + 1 < n_rows; ++k) {
+        mbar_wait_lean(&full[sa_slot], sa_par);
+        const Totals t = fold(k);
+        phase_a(k + 1, sa_slot);
+        phase_b(k, sb_slot, t);
+        __syncthreads();      // row k+1's partials complete; every read of row k's slot is done
+        if (tid == 0 && k + LNW_STAGES < n_rows) issue(k + LNW_STAGES);
+        sb_slot = sa_slot;
+        if (++sa_slot == LNW_STAGES) { sa_slot = 0; sa_par ^= 1u; }
+    }
+    {
+        const Totals t = fold(n_rows - 1);
+        phase_b(n_rows - 1, sb_slot, t);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (!live[c]) continue;
+        const long long o = static_cast<long long>(blockIdx.x) * n + col[c];
+        *reinterpret_cast<ulonglong2*>(part_gamma + o) = make_ulonglong2(acc_g[c][0], acc_g[c][1]);
+        *reinterpret_cast<ulonglong2*>(part_gamma + o + 4) = make_ulonglong2(acc_g[c][2], acc_g[c][3]);
+        *reinterpret_cast<ulonglong2*>(part_beta + o) = make_ulonglong2(acc_b[c][0], acc_b[c][1]);
+        *reinterpret_cast<ulonglong2*>(part_beta + o + 4) = make_ulonglong2(acc_b[c][2], acc_b[c][3]);
+        if (part_col != nullptr) {
+            *reinterpret_cast<ulonglong2*>(part_col + o) = make_ulonglong2(acc_c[c][0], acc_c[c][1]);
+            *reinterpret_cast<ulonglong2*>(part_col + o + 4) = make_ulonglong2(acc_c[c][2], acc_c[c][3]);
+        }
     }
 }
 
@@ -949,7 +1161,24 @@ extern "C" int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, co
     { if (!wide) KX_LNB(XT, F32, 256, GE) else KX_LNB(XT, F32, 1024, GE) }
     if (act == KX_ACT_GELU) {
         if (!x_is_bf16 || dx_is_f32) { set_error("kx_layernorm_bwd: the GELU form takes a bf16 pre-activation and writes a bf16 gradient"); return KX_ERR_ARG; }
-        KX_LNB_N(__nv_bfloat16, false, true)
+        if (wide) {
+            // ffn_layernorm of the decoder: the two-rows-in-flight kernel (512 threads x 16 columns)
+            const int wsmem = LNW_STAGES * n * 4 + 2 * LNW_STASH_BYTES;
+            static std::once_flag once;
+            static bool ok = false;
+            std::call_once(once, [] {
+                constexpr int most = LNW_STAGES * 8192 * 4 + 2 * LNW_STASH_BYTES;
+                ok = cudaFuncSetAttribute(ln_gelu_bwd_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most) == cudaSuccess &&
+                     cudaFuncSetAttribute(ln_gelu_bwd_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most) == cudaSuccess;
+            });
+            if (!ok) { set_error("kx_layernorm_bwd: cudaFuncSetAttribute failed (wide GELU form)"); return KX_ERR_LAUNCH; }
+            auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+            auto dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+            if (n == 16 * LNW_THREADS)
+                ln_gelu_bwd_wide_kernel<true><<<grid, LNW_THREADS, wsmem, stream>>>(xb, ld_x, dyp, ld_dy, gamma, eps, dxp, ld_dx, pg, pb, pc, rows, n);
+            else
+                ln_gelu_bwd_wide_kernel<false><<<grid, LNW_THREADS, wsmem, stream>>>(xb, ld_x, dyp, ld_dy, gamma, eps, dxp, ld_dx, pg, pb, pc, rows, n);
+        } else KX_LNB(__nv_bfloat16, false, 256, true)
     } else if (x_is_bf16) { if (dx_is_f32) KX_LNB_N(__nv_bfloat16, true, false) else KX_LNB_N(__nv_bfloat16, false, false) }
     else { if (dx_is_f32) KX_LNB_N(float, true, false) else KX_LNB_N(float, false, false) }
 #undef KX_LNB_N

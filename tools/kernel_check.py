@@ -178,8 +178,12 @@ def case_train_elementwise():
     ok = True
     F = torch.nn.functional
     # ---- LayerNorm backward: fp32 residual form (dres add, bf16 copy, column sums) and bf16 forms, n = 2048 / 8192 / ragged 200
+    # (the wide GELU form is its own kernel, two rows in flight per CTA: more rows than SMs, fewer, one, and rows narrower than 8192
+    # whose second column chunk is partly / entirely dead)
     for (rows, n, xdt, act) in ((1000, 2048, torch.float32, 0), (515, 8192, torch.bfloat16, 1), (300, 200, torch.bfloat16, 0),
-                                (64, 4096, torch.float32, 0)):
+                                (64, 4096, torch.float32, 0), (100, 8192, torch.bfloat16, 1), (1, 8192, torch.bfloat16, 1),
+                                (1200, 8192, torch.bfloat16, 1), (450, 6144, torch.bfloat16, 1), (333, 4096, torch.bfloat16, 1),
+                                (200, 2056, torch.bfloat16, 1), (150, 1024, torch.bfloat16, 1)):
         x = torch.randn(rows, n, device=dev) * 1.5 + 0.3
         x = x.to(xdt)
         gamma = torch.rand(n, device=dev) + 0.5
