@@ -308,8 +308,10 @@ int kx_attn_bwd_dropout(const void* q, const void* k, const void* v, long long l
                         const float* xk_sin, int batch, int heads, int seq_len, int causal, float scale, float drop_p,
                         const unsigned int* key_mask, kx_stream_t stream);
 
-/* Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 int64 installed, CTA 0 of every launch records
- * clock64 stamps [role: compute thread 0, MMA thread][iteration][point]; NULL = off. */
+/* Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 + 4 * (number of CTAs) int64 installed, one CTA of
+ * every launch (named by word 1023 of the buffer; negative = CTA 0) records clock64 stamps [role: compute thread 0, MMA thread]
+ * [iteration][point] and every CTA b leaves {SM id, globaltimer ns at entry, at its first ready score tile, at exit} at word
+ * 1024 + 4 b; NULL = off. */
 int kx_attn_bwd_set_trace(long long* device_buffer);
 
 /* out = LayerNorm(act(x)) * gamma + beta in one pass, bf16 in / bf16 out (ffn_layernorm(gelu(fc1 x)), SURVEY A.4:

@@ -59,7 +59,7 @@ struct AttnBwdParams {
     long long ld_dkv;
     int seq_len, heads, batch, t_pad;
     float scale, scale_log2;
-    long long* trace;          // TRACE builds only: clock64 stamps of CTA 0, [role: 0 compute thread 0, 1 MMA thread][iteration][16 points]
+    long long* trace;          // TRACE builds only: clock64 stamps of one CTA, [role: 0 compute thread 0, 1 MMA thread][iteration][16 points], then per-CTA records
     const uint32_t* drop_mask; // DROP builds only: key-major keep bits of kx_attn_dropout_masks, word per (tile, query quarter, key)
     float inv_keep;            // 1 / (1 - p)
 };
@@ -69,7 +69,7 @@ static long long* g_attn_bwd_trace = nullptr;         // kx_attn_bwd_set_trace
 #define KX_BT(role, iter, point)                                                                      \
     do {                                                                                              \
         if constexpr (TRACE) {                                                                        \
-            if (p.trace != nullptr && blockIdx.x == 0 && (iter) < 32)                                 \
+            if (p.trace != nullptr && blockIdx.x == trace_cta && (iter) < 32)                         \
                 p.trace[((role) * 32 + (iter)) * 16 + (point)] = clock64();                           \
         }                                                                                             \
     } while (0)
@@ -104,6 +104,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int T = p.seq_len;
     const int nblk = (T + 127) >> 7;
+    // TRACE builds: the CTA whose timeline is recorded is named by the buffer's last timeline word (a negative value means
+    // CTA 0); every CTA also leaves {SM id, globaltimer at entry, at its first ready score tile, at exit} behind the timelines.
+    [[maybe_unused]] unsigned trace_cta = 0;
+    if constexpr (TRACE) {
+        if (p.trace != nullptr) {
+            const long long want = p.trace[1023];
+            trace_cta = want > 0 ? static_cast<unsigned>(want) : 0u;
+            if (threadIdx.x == 0) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                p.trace[1024 + 4 * static_cast<long long>(blockIdx.x)] = smid;
+                p.trace[1024 + 4 * static_cast<long long>(blockIdx.x) + 1] = static_cast<long long>(globaltimer_ns());
+            }
+        }
+    }
     // (batch, head) major, key block minor: the 16 CTAs that share one (batch, head) run close together in time, so its
     // Q / dO blocks and its dQ accumulator tiles stay in L2.  (Key-block-major order made the kernel DRAM-bound: ncu
     // measured 3.2 GB of traffic per launch — every Q / dO re-read and every dQ reduce-add went to HBM.)
@@ -278,16 +293,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint8_t* ds_row = smem + BW_SMEM_DS + (g >> 1) * BW_TILE + r * 128;
         const int ch0 = (g & 1) * 4;
 
+        // DROP: keep bits of queries 32g .. 32g+31 for this key, loaded one query block ahead (the round trip to L2 / DRAM at
+        // the top of every iteration sat on the critical path of the compute warps)
+        auto mask_word = [&](int i) {
+            return __ldg(p.drop_mask + ((((static_cast<long long>(bh) * nblk + i) * nblk + j) * 4 + g) << 7) + r);
+        };
+        uint32_t mw_next = 0xffffffffu;
+        if constexpr (DROP) mw_next = mask_word(i0);
         for (int it = 0; it < n_it; ++it) {
             const int i = i0 + it, s = it % BW_SLOTS;
             if (threadIdx.x == 0) KX_BT(0, it, 0);
-            uint32_t mw = 0xffffffffu;                                      // keep bits of queries 32g .. 32g+31 for this key
-            if constexpr (DROP)
-                mw = __ldg(p.drop_mask + ((((static_cast<long long>(bh) * nblk + i) * nblk + j) * 4 + g) << 7) + r);
+            const uint32_t mw = mw_next;
+            if constexpr (DROP) {
+                if (it + 1 < n_it) mw_next = mask_word(i + 1);
+            }
             mbar_wait_lean(&full[s], (it / BW_SLOTS) & 1);                  // (-lse, -delta) of this query block are in smem
             mbar_wait_lean(bar_s, it & 1);
             tc_fence_after();
             if (threadIdx.x == 0) KX_BT(0, it, 1);
+            if constexpr (TRACE) {
+                if (p.trace != nullptr && threadIdx.x == 0 && it == 0)
+                    p.trace[1024 + 4 * static_cast<long long>(blockIdx.x) + 2] = static_cast<long long>(globaltimer_ns());
+            }
             const float4* ld = s_ld + s * 64 + g * 16;          // {-lse(q0), -lse(q1), -delta(q0), -delta(q1)} per query pair
             const bool edge = (CAUSAL && i == j) || (i * 128 + 128 > T) || (j * 128 + 128 > T);
             mbar_wait_lean(bar_dp, it & 1);
@@ -403,6 +430,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (warp == BW_W_TMA) tmem_dealloc<1>(tmem_base, BW_TMEM_COLS);
+    if constexpr (TRACE) {
+        if (p.trace != nullptr && threadIdx.x == 0)
+            p.trace[1024 + 4 * static_cast<long long>(blockIdx.x) + 3] = static_cast<long long>(globaltimer_ns());
+    }
 }
 
 // nld[h][b][t/2] = {-lse(t0), -lse(t1), -delta(t0), -delta(t1)}, delta = sum_d dO[b,t,h,d] * O[b,t,h,d]  (8 lanes per (row, head)).
@@ -491,8 +522,10 @@ attn_bwd_finish_kernel(const float* __restrict__ dq_accum, __nv_bfloat16* __rest
 
 using namespace kx;
 
-// Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 int64 installed, CTA 0 of every launch records
-// clock64 stamps [role: compute thread 0, MMA thread][iteration][point]; NULL = off.
+// Profiling aid for kx_attn_bwd (causal): with a device buffer of 2*32*16 + 4 * (number of CTAs) int64 installed, one CTA of every
+// launch (the one named by word 1023 of the buffer; negative = CTA 0) records clock64 stamps [role: compute thread 0, MMA thread]
+// [iteration][point], and every CTA b leaves {SM id, globaltimer ns at entry, at its first ready score tile, at exit} at
+// word 1024 + 4 b; NULL = off.
 extern "C" int kx_attn_bwd_set_trace(long long* device_buffer) {
     g_attn_bwd_trace = device_buffer;
     return KX_OK;
