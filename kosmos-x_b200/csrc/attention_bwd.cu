@@ -62,6 +62,8 @@ struct AttnBwdParams {
     long long* trace;          // TRACE builds only: clock64 stamps of one CTA, [role: 0 compute thread 0, 1 MMA thread][iteration][16 points], then per-CTA records
     const uint32_t* drop_mask; // DROP builds only: key-major keep bits of kx_attn_dropout_masks, word per (tile, query quarter, key)
     float inv_keep;            // 1 / (1 - p)
+    const float* k_cos;        // [seq_len][32] xPos tables of the keys (transpose of the QKV epilogue's rotation, applied to dK on
+    const float* k_sin;        // the way out), or null
 };
 
 static long long* g_attn_bwd_trace = nullptr;         // kx_attn_bwd_set_trace
@@ -409,6 +411,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (kg < T) {
             const long long off = static_cast<long long>(row_base + kg) * p.ld_dkv + head * 64 + g * 16;
 #pragma unroll
+            for (int u = 0; u < 16; ++u) kk[u] = __float_as_uint(__uint_as_float(kk[u]) * p.scale);
+            if (p.k_cos != nullptr) {
+                // dK = R^T(dK): the transpose of the xPos rotation the QKV epilogue applied to k (pairs (2u, 2u + 1) of this
+                // thread's 16 columns; previously a second pass over the stored bf16 dK in attn_bwd_finish_kernel)
+                const float4* cp = reinterpret_cast<const float4*>(p.k_cos + static_cast<long long>(kg) * 32 + g * 8);
+                const float4* sp = reinterpret_cast<const float4*>(p.k_sin + static_cast<long long>(kg) * 32 + g * 8);
+                const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float a = __uint_as_float(kk[2 * u]), b = __uint_as_float(kk[2 * u + 1]);
+                    kk[2 * u] = __float_as_uint(a * cc[u] + b * ss[u]);
+                    kk[2 * u + 1] = __float_as_uint(b * cc[u] - a * ss[u]);
+                }
+            }
+#pragma unroll
             for (int u = 0; u < 2; ++u) {
                 uint4 a, c;
                 const float vs = DROP ? p.inv_keep : 1.0f;          // dV accumulated (M o P)^T dO: the 1/keep factor goes on here
@@ -416,10 +435,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 a.y = pack_bf16(__uint_as_float(vv[8 * u + 2]) * vs, __uint_as_float(vv[8 * u + 3]) * vs);
                 a.z = pack_bf16(__uint_as_float(vv[8 * u + 4]) * vs, __uint_as_float(vv[8 * u + 5]) * vs);
                 a.w = pack_bf16(__uint_as_float(vv[8 * u + 6]) * vs, __uint_as_float(vv[8 * u + 7]) * vs);
-                c.x = pack_bf16(__uint_as_float(kk[8 * u]) * p.scale, __uint_as_float(kk[8 * u + 1]) * p.scale);
-                c.y = pack_bf16(__uint_as_float(kk[8 * u + 2]) * p.scale, __uint_as_float(kk[8 * u + 3]) * p.scale);
-                c.z = pack_bf16(__uint_as_float(kk[8 * u + 4]) * p.scale, __uint_as_float(kk[8 * u + 5]) * p.scale);
-                c.w = pack_bf16(__uint_as_float(kk[8 * u + 6]) * p.scale, __uint_as_float(kk[8 * u + 7]) * p.scale);
+                c.x = pack_bf16(__uint_as_float(kk[8 * u]), __uint_as_float(kk[8 * u + 1]));
+                c.y = pack_bf16(__uint_as_float(kk[8 * u + 2]), __uint_as_float(kk[8 * u + 3]));
+                c.z = pack_bf16(__uint_as_float(kk[8 * u + 4]), __uint_as_float(kk[8 * u + 5]));
+                c.w = pack_bf16(__uint_as_float(kk[8 * u + 6]), __uint_as_float(kk[8 * u + 7]));
                 *reinterpret_cast<uint4*>(p.dv + off + 8 * u) = a;
                 *reinterpret_cast<uint4*>(p.dk + off + 8 * u) = c;
             }
@@ -438,9 +457,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 // nld[h][b][t/2] = {-lse(t0), -lse(t1), -delta(t0), -delta(t1)}, delta = sum_d dO[b,t,h,d] * O[b,t,h,d]  (8 lanes per (row, head)).
 // Both come out negated so that the main kernel's packed FFMA2 / FADD2 take them as plain addends.
+// The same pass zeroes the fp32 dQ accumulator (the lane that reads 16 bytes of (row, head) clears the matching 32 bytes): it
+// replaces a separate 268 MB memset at the C3 shape.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ld_o, const __nv_bfloat16* __restrict__ d_o, long long ld_do,
-                  const float* __restrict__ lse, float2* __restrict__ nld, int batch, int heads, int seq_len, int t_pad) {
+                  const float* __restrict__ lse, float2* __restrict__ nld, float* __restrict__ dq_zero, int batch, int heads,
+                  int seq_len, int t_pad) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long total = static_cast<long long>(batch) * seq_len * heads * 8;
     const bool active = idx < total;
@@ -451,6 +473,11 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ld_o, const __n
     const long long row = rh / heads;
     const uint4 a = *reinterpret_cast<const uint4*>(o + row * ld_o + head * 64 + sub * 8);
     const uint4 c = *reinterpret_cast<const uint4*>(d_o + row * ld_do + head * 64 + sub * 8);
+    if (active) {
+        float4* z = reinterpret_cast<float4*>(dq_zero + (row * heads + head) * 64 + sub * 8);
+        z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
     const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
     float s = 0.f;
@@ -471,38 +498,27 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ld_o, const __n
     }
 }
 
-// dq (bf16) = R^T(dq_accum) and dk = R^T(dk) in place, R = the xPos rotation of the QKV epilogue (kx_xpos_bwd does the
-// same on bf16 inputs; this variant reads the fp32 dQ accumulator).  ld in elements of the bf16 matrix.
+// dq (bf16) = R^T(dq_accum), R = the xPos rotation of the QKV epilogue on q (dK gets its rotation in the main kernel's
+// epilogue).  ld in elements of the bf16 matrix.
 __global__ void __launch_bounds__(256)
-attn_bwd_finish_kernel(const float* __restrict__ dq_accum, __nv_bfloat16* __restrict__ dq, __nv_bfloat16* __restrict__ dk,
-                       long long ld, int rows, int d_model, int seq_len, const float* __restrict__ q_cos,
-                       const float* __restrict__ q_sin, const float* __restrict__ k_cos, const float* __restrict__ k_sin) {
-    const int vec_per_row = (2 * d_model) >> 3;
+attn_bwd_finish_kernel(const float* __restrict__ dq_accum, __nv_bfloat16* __restrict__ dq, long long ld, int rows, int d_model,
+                       int seq_len, const float* __restrict__ q_cos, const float* __restrict__ q_sin) {
+    const int vec_per_row = d_model >> 3;
     const long long total = static_cast<long long>(rows) * vec_per_row;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int row = static_cast<int>(i / vec_per_row);
-        int col = static_cast<int>(i - static_cast<long long>(row) * vec_per_row) * 8;
-        const bool is_k = col >= d_model;
-        if (is_k) col -= d_model;
-        float v[8];
-        if (!is_k) {
-            const float4 a = *reinterpret_cast<const float4*>(dq_accum + static_cast<long long>(row) * d_model + col);
-            const float4 c = *reinterpret_cast<const float4*>(dq_accum + static_cast<long long>(row) * d_model + col + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-        } else {
-            const uint4 q = *reinterpret_cast<const uint4*>(dk + static_cast<long long>(row) * ld + col);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const float2 f = __bfloat1622float2(h[u]); v[2 * u] = f.x; v[2 * u + 1] = f.y; }
-        }
+        const int col = static_cast<int>(i - static_cast<long long>(row) * vec_per_row) * 8;
+        const float4 a = *reinterpret_cast<const float4*>(dq_accum + static_cast<long long>(row) * d_model + col);
+        const float4 c = *reinterpret_cast<const float4*>(dq_accum + static_cast<long long>(row) * d_model + col + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
         float o[8];
         if (q_cos != nullptr) {
             const int t = row % seq_len;
             const int j0 = (col & 63) >> 1;
-            const float4 c = __ldg(reinterpret_cast<const float4*>((is_k ? k_cos : q_cos) + t * 32 + j0));
-            const float4 s = __ldg(reinterpret_cast<const float4*>((is_k ? k_sin : q_sin) + t * 32 + j0));
-            const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(q_cos + t * 32 + j0));
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(q_sin + t * 32 + j0));
+            const float cc[4] = {cv.x, cv.y, cv.z, cv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 o[2 * u] = v[2 * u] * cc[u] + v[2 * u + 1] * ss[u];
@@ -514,7 +530,7 @@ attn_bwd_finish_kernel(const float* __restrict__ dq_accum, __nv_bfloat16* __rest
         }
         uint4 q;
         q.x = pack_bf16(o[0], o[1]); q.y = pack_bf16(o[2], o[3]); q.z = pack_bf16(o[4], o[5]); q.w = pack_bf16(o[6], o[7]);
-        *reinterpret_cast<uint4*>((is_k ? dk : dq) + static_cast<long long>(row) * ld + col) = q;
+        *reinterpret_cast<uint4*>(dq + static_cast<long long>(row) * ld + col) = q;
     }
 }
 
@@ -565,13 +581,11 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, long long 
         attr_set = true;
     }
     const long long d_model = static_cast<long long>(heads) * 64;
-    cudaError_t e = cudaMemsetAsync(dq_accum, 0, rows * d_model * sizeof(float), stream);
-    if (e != cudaSuccess) { set_error("kx_attn_bwd: memset failed: %s", cudaGetErrorString(e)); return KX_ERR_LAUNCH; }
     {
         const long long total = static_cast<long long>(rows) * heads * 8;
         attn_delta_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<const __nv_bfloat16*>(out), ld_out, reinterpret_cast<const __nv_bfloat16*>(d_out), ld_dout, lse,
-            reinterpret_cast<float2*>(delta), batch, heads, seq_len, t_pad);
+            reinterpret_cast<float2*>(delta), dq_accum, batch, heads, seq_len, t_pad);
         int st = check_launch("kx_attn_bwd (delta)");
         if (st != KX_OK) return st;
     }
@@ -583,6 +597,7 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, long long 
     p.trace = g_attn_bwd_trace;
     p.drop_mask = drop_mask;
     p.inv_keep = 1.0f;
+    p.k_cos = xk_cos; p.k_sin = xk_sin;
     if (drop_mask != nullptr) {
         if (!causal || !(drop_p > 0.f && drop_p < 1.f) || (reinterpret_cast<uintptr_t>(drop_mask) & 15)) {
             set_error("kx_attn_bwd_dropout: needs causal attention, 0 < p < 1 and the 16-byte aligned key_mask of kx_attn_dropout_masks");
@@ -606,11 +621,10 @@ static int attn_bwd_impl(const void* q, const void* k, const void* v, long long 
     int st = check_launch("kx_attn_bwd");
     if (st != KX_OK) return st;
     {
-        const long long total = static_cast<long long>(rows) * (2 * d_model / 8);
+        const long long total = static_cast<long long>(rows) * (d_model / 8);
         const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sms) * 8));
-        attn_bwd_finish_kernel<<<blocks, 256, 0, stream>>>(dq_accum, reinterpret_cast<__nv_bfloat16*>(dq),
-                                                          reinterpret_cast<__nv_bfloat16*>(dk), ld_dqkv, static_cast<int>(rows),
-                                                          static_cast<int>(d_model), seq_len, xq_cos, xq_sin, xk_cos, xk_sin);
+        attn_bwd_finish_kernel<<<blocks, 256, 0, stream>>>(dq_accum, reinterpret_cast<__nv_bfloat16*>(dq), ld_dqkv, static_cast<int>(rows),
+                                                          static_cast<int>(d_model), seq_len, xq_cos, xq_sin);
         st = check_launch("kx_attn_bwd (finish)");
     }
     return st;
