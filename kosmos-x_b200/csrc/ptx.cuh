@@ -375,8 +375,15 @@ __device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& e0, floa
     float p0, p1, t0, t1;
     unpack_f32x2(p, p0, p1);
     unpack_f32x2(t, t0, t1);
-    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
-    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+    // exponent patch on the ALU pipe (SHF + IADD3): ptxas turns `p + (t << 23)` into one IMAD, and the FMA pipe is the one
+    // that bounds the softmax loops (one warp instruction per 2 cycles and scheduler; profiles/r2_attn_softmax_scheduling_experiments.md)
+    uint32_t s0, s1, r0, r1;
+    asm("shf.l.clamp.b32 %0, 0, %1, 23;" : "=r"(s0) : "r"(__float_as_uint(t0)));       // (t << 23): funnel shift of {t, 0}
+    asm("shf.l.clamp.b32 %0, 0, %1, 23;" : "=r"(s1) : "r"(__float_as_uint(t1)));
+    asm("add.u32 %0, %1, %2;" : "=r"(r0) : "r"(__float_as_uint(p0)), "r"(s0));
+    asm("add.u32 %0, %1, %2;" : "=r"(r1) : "r"(__float_as_uint(p1)), "r"(s1));
+    e0 = __uint_as_float(r0);
+    e1 = __uint_as_float(r1);
 }
 
 // ----------------------------------------------------------------------------- descriptors
