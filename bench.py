@@ -513,7 +513,11 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
                             attention_dropout=dropout, grad_reduce_dtype=torch.bfloat16 if reduce_bf16 else torch.float32,
                             lr_schedule=cosine_with_warmup(2, 10000), overlap_all_reduce=bool(int(os.environ.get("KX_BENCH_OVERLAP", "0"))),
                             bwd_max_ctas=int(os.environ.get("KX_BENCH_BWD_CTAS", "0")), train_clip_last_layer=clip_last,
-                            recompute=recompute)
+                            recompute=recompute,
+                            # N > 1: ZeRO-1 style optimizer (reduce-scatter / each rank's slice of AdamW / all-gather of the bf16
+                            # copies) unless KX_BENCH_SHARD=0 asks for the all-reduce + replicated optimizer
+                            shard_optimizer=(world > 1 and reduce_bf16 and not int(os.environ.get("KX_BENCH_OVERLAP", "0"))
+                                             and bool(int(os.environ.get("KX_BENCH_SHARD", "1")))))
     g = torch.Generator().manual_seed(11 + rank)
     h_text = torch.randint(0, VOCAB, (B, t_text), dtype=torch.long, generator=g).pin_memory()
     h_img = torch.randn(*((B, 3, 224, 224) if n_img == 1 else (B, n_img, 3, 224, 224)), generator=g).pin_memory()
@@ -564,7 +568,11 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
            "gpu_launches": int(launches), "loss_first": first_loss, "loss_last": float(h_loss[0]),
            "trained_parameters": int(sum(p.numel() for p in trainer.params)),
            "grad_all_reduce": (("%d buckets (per decoder layer) on NCCL's stream, overlapped with backward" % len(trainer.bucket_plan()))
-                               if trainer.overlap else "one all-reduce of the flat %s gradient buffer after backward (not overlapped: "
+                               if trainer.overlap else
+                               "sharded optimizer: reduce-scatter of the bf16 Linear-weight gradients after backward, each rank updates 1/%d "
+                               "of the fp32 masters, all-gather of the bf16 copies (small replicated tail: one bf16 all-reduce)" % world
+                               if trainer.shard_optimizer else
+                               "one all-reduce of the flat %s gradient buffer after backward (not overlapped: "
                                "profiles/r2_nccl_overlap.md)" % ("bf16" if reduce_bf16 else "fp32")) if world > 1 else "none (1 GPU)"}
     if detail:
         ops.profile_begin()
@@ -580,6 +588,7 @@ def train_measure(torch, kdist, dev, model, wl, steps, warmup, world, rank, peak
         out["breakdown"] = {k: {"launches": a[0], "ms": a[2], "share": a[2] / tot,
                                 **({"tflops": a[1] / (a[2] * 1e-3) / 1e12} if a[1] else {})}
                             for k, a in sorted(agg.items(), key=lambda kv: -kv[1][2])}
+    trainer.gather_masters()                 # (collective; every rank is here) the model is used again after this leg
     del trainer
     return out
 

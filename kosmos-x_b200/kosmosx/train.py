@@ -54,7 +54,8 @@ class KosmosTrainer:
                  train_resampler: bool = True, layout_only: bool = False, loss_rule: str = "reference",
                  pad_token_id: int | None = None, lr_schedule=None, grad_reduce_dtype: torch.dtype = torch.bfloat16,
                  distributed: bool | None = None, dropout: float | None = None, attention_dropout: float | None = None,
-                 seed: int = 0, bwd_max_ctas: int = 0, recompute: bool = False, train_clip_last_layer: bool = False):
+                 seed: int = 0, bwd_max_ctas: int = 0, recompute: bool = False, train_clip_last_layer: bool = False,
+                 shard_optimizer: bool = False):
         """overlap_all_reduce: False (default) = ONE all-reduce of the whole flat gradient buffer after backward; True = per-layer
         buckets issued while backward is still running.  Measured on 2 and 8 B200s (profiles/r2_nccl_overlap.md): NCCL's kernels
         occupy SMs that the persistent, one-CTA-per-SM backward kernels are sized for, so every GEMM / LayerNorm-backward
@@ -80,6 +81,16 @@ class KosmosTrainer:
         train_clip_last_layer: also train the last encoder layer of the CLIP ViT (the reference freezes CLIP except its last
         layer, notes.txt:537-538 / model.py:184-190); the other 23 stay frozen on the inference kernels.  Needs train_resampler
         (the gradient reaches the ViT through the resampler's norm_media).
+        shard_optimizer: with more than one rank, ``step`` / ``step_accumulated`` run the optimizer ZeRO-1 style: the bf16 gradients
+        of the weight-decay segment (every Linear weight, 1.3 G of the 1.37 G trained parameters) are REDUCE-SCATTERED instead of
+        all-reduced, each rank clips (its shard's sum of squares + one scalar all-reduce) and updates only its 1/world slice of the
+        fp32 masters / moments, and the updated bf16 tensor-core copies are ALL-GATHERED — the same bytes on NVLink as the one
+        all-reduce (which is a reduce-scatter + all-gather inside NCCL), the 8 ms optimizer pass divided by the world size, no
+        cast of the whole buffer back to fp32.  The small no-decay segment (biases, LayerNorms, the embedding tables) stays
+        replicated.  The fp32 masters and the moments outside a rank's slice go stale: ``gather_masters()`` (a collective, call it
+        on EVERY rank) brings the masters up to date before ``state_dict()`` / ``save_checkpoint`` / an inference forward, which
+        raise until then.  ``loss_and_grads`` and the autograd bridge keep the all-reduce (their contract is the summed gradient in
+        ``param.grad``).  Needs the bf16 exchange and ``overlap_all_reduce=False``.
         bwd_max_ctas: > 0 caps the grid of the persistent backward GEMMs (they are sized to one CTA per SM; an NCCL kernel
         resident on a few SMs while they launch would push the CTAs that do not fit into a second wave)."""
         if optimizer not in ("adamw", "lion"):
@@ -111,6 +122,11 @@ class KosmosTrainer:
         self.world = 1
         if distributed is not False and (process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
+        self.shard_optimizer = bool(shard_optimizer) and self.world > 1
+        if self.shard_optimizer and (overlap_all_reduce or grad_reduce_dtype != torch.bfloat16):
+            raise ValueError("shard_optimizer needs grad_reduce_dtype=torch.bfloat16 and overlap_all_reduce=False")
+        self._defer_reduce = False               # step() of the sharded optimizer: backward leaves the exchange to _optimize_sharded
+        self._masters_sharded = False            # the fp32 masters outside this rank's slice are stale (see gather_masters)
         self.t = 0
         self._ws = {}
         self._fw_serial = 0                      # autograd bridge: which forward the saved activations belong to
@@ -183,6 +199,9 @@ class KosmosTrainer:
             off += _round_up(p.numel())
         self.n_total = off
         self.params = decay + nodecay
+        # sharded optimizer: the decay segment is cut into `world` equal chunks (padded; the in-place all-gather of the bf16 copies
+        # and the reduce-scatter of the bf16 gradients need equal counts per rank)
+        self._nd_pad = _round_up(self.n_decay, self.world * 1024) if self.shard_optimizer else self.n_decay
         if layout_only:
             return
         f32 = dict(dtype=torch.float32, device=dev)
@@ -190,7 +209,8 @@ class KosmosTrainer:
         self.G = torch.zeros(off, **f32)
         self.M1 = torch.zeros(off, **f32)
         self.M2 = torch.zeros(off, **f32) if self.opt == "adamw" else None
-        self.W16 = torch.zeros(self.n_decay, dtype=torch.bfloat16, device=dev)
+        self._W16p = torch.zeros(self._nd_pad, dtype=torch.bfloat16, device=dev)
+        self.W16 = self._W16p[:self.n_decay]
         with torch.no_grad():
             for p in self.params:
                 s = self.seg[id(p)]
@@ -203,12 +223,15 @@ class KosmosTrainer:
         for p in m.parameters():
             if id(p) not in trained:
                 p.requires_grad_(False)
-        self.scalars = torch.zeros(8, **f32)       # [0:2] loss sum / rows, [2] sum g^2, [3] clip scale, [4] grad norm
+        self.scalars = torch.zeros(8, **f32)       # [0:2] loss sum / rows, [2] sum g^2, [3] clip scale, [4] grad norm, [5] loss rows, [6:8] partial sums g^2 (sharded optimizer)
+        if self.shard_optimizer:
+            m.register_state_dict_pre_hook(lambda module, prefix, keep_vars: self._require_whole_masters("state_dict()"))
         self.sync_weights()
 
     def sync_weights(self):
         """Re-derive the bf16 tensor-core copies from the fp32 master weights (after load_state_dict or any
         in-place edit of the parameters).  The optimizer kernels keep them in sync afterwards."""
+        self._require_whole_masters("sync_weights()")
         ops.cast_bf16(self.P[:self.n_decay], self.W16)
         self._p_version = self._params_version()
         self._inference_copies_stale()
@@ -222,8 +245,34 @@ class KosmosTrainer:
         """An external optimizer (the autograd-bridge loop) or ``load_state_dict`` edits the fp32 masters in place, which no
         kernel of this library sees happen: PyTorch's version counters of the parameters tell.  Called by the inference entry
         points of the model, so an eval forward / generate right after ``optimizer.step()`` runs on the stepped weights."""
+        self._require_whole_masters("an inference forward")
         if self._params_version() != self._p_version:
             self.sync_weights()
+
+    # ------------------------------------------------------------------ sharded optimizer (ZeRO-1)
+    def shard_range(self, rank=None):
+        """[lo, hi) of the decay segment whose masters / moments ``rank`` (default: this one) owns under shard_optimizer."""
+        if rank is None:
+            rank = torch.distributed.get_rank(self.pg)
+        chunk = self._nd_pad // self.world
+        return min(rank * chunk, self.n_decay), min((rank + 1) * chunk, self.n_decay)
+
+    def _require_whole_masters(self, what):
+        if self._masters_sharded:
+            raise RuntimeError(f"KosmosTrainer(shard_optimizer=True): {what} needs the whole fp32 master weights, but every rank has only "
+                               "updated its own slice since the last gather — call trainer.gather_masters() on EVERY rank first")
+
+    def gather_masters(self):
+        """Collective (every rank of the group must call it): each rank broadcasts the slice of the fp32 masters it owns, so
+        ``state_dict()``, ``save_checkpoint`` and the inference path see the stepped weights everywhere.  The moments stay sharded."""
+        if not self._masters_sharded:
+            return
+        dist = torch.distributed
+        for r in range(self.world):
+            lo, hi = self.shard_range(r)
+            if hi > lo:
+                dist.broadcast(self.P[lo:hi], src=dist.get_global_rank(self.pg, r) if self.pg is not None else r, group=self.pg)
+        self._masters_sharded = False
 
     def _inference_copies_stale(self):
         """The inference path re-stages its folded / split weights lazily from the fp32 masters."""
@@ -679,7 +728,7 @@ class KosmosTrainer:
         NCCL's stream while backward continues on the compute stream.  which = "head" | layer index | "tail".
         With grad_reduce_dtype = bf16 the bucket is first cast into the bf16 exchange buffer (kx_cast_f32_to_bf16 on the
         compute stream); ``_finish_reduce`` converts the received sums back."""
-        if self.world == 1:
+        if self.world == 1 or self._defer_reduce:
             return
         if not self.overlap:
             if which == "tail":
@@ -741,6 +790,49 @@ class KosmosTrainer:
                               grad_scale=sc[3:4])
         self._inference_copies_stale()
 
+    def _optimize_sharded(self, micro_batches: int = 1):
+        """shard_optimizer: exchange + clip + optimizer (see the constructor).  self.G holds this rank's LOCAL gradient sum."""
+        dist = torch.distributed
+        self.t += 1
+        sc = self.scalars
+        lr = self.lr * (float(self.lr_schedule(self.t)) if self.lr_schedule is not None else 1.0)
+        self.last_lr = lr
+        nd, nt, bf16 = self.n_decay, self.n_total, torch.bfloat16
+        rank = dist.get_rank(self.pg)
+        chunk = self._nd_pad // self.world
+        lo, hi = self.shard_range(rank)
+        g16d = self._ws.get("g16d")
+        if g16d is None:                         # (zeros: the padding behind the decay segment is exchanged too)
+            g16d = self._ws["g16d"] = torch.zeros(self._nd_pad, dtype=bf16, device=self.P.device)
+        g16s = self._buf("g16s", (chunk,), bf16)
+        g16n = self._buf("g16n", (nt - nd,), bf16)
+        ops.cast_bf16(self.G[:nd], g16d[:nd])
+        ops.cast_bf16(self.G[nd:], g16n)
+        dist.reduce_scatter_tensor(g16s, g16d, group=self.pg)
+        dist.all_reduce(g16n, group=self.pg)
+        ops.cast_f32(g16n, self.G[nd:])
+        sc[6:8].zero_()                          # (kx_sumsq accumulates; [5] is the cross-entropy's row count)
+        if hi > lo:
+            ops.cast_f32(g16s[:hi - lo], self.G[lo:hi])
+            ops.sumsq(self.G[lo:hi], sc[6:7])
+        dist.all_reduce(sc[6:7], group=self.pg)                  # every rank receives the same bits: replicas stay identical
+        ops.sumsq(self.G[nd:], sc[7:8])
+        torch.add(sc[6:7], sc[7:8], out=sc[2:3])
+        ops.clip_scale(sc[2:3], self.max_grad_norm, 1.0 / (self.world * max(int(micro_batches), 1)), sc[3:4], sc[4:5])
+        for a, b, wd, wb in ((lo, hi, self.wd, self.W16), (nd, nt, 0.0, None)):
+            if b <= a:
+                continue
+            w16 = wb[a:b] if wb is not None else None
+            if self.opt == "adamw":
+                ops.adamw_step(self.P[a:b], self.G[a:b], self.M1[a:b], self.M2[a:b], w16, lr=lr, betas=self.betas,
+                               eps=self.eps, weight_decay=wd, step=self.t, grad_scale=sc[3:4])
+            else:
+                ops.lion_step(self.P[a:b], self.G[a:b], self.M1[a:b], w16, lr=lr, betas=self.betas, weight_decay=wd,
+                              grad_scale=sc[3:4])
+        dist.all_gather_into_tensor(self._W16p, self._W16p[rank * chunk:(rank + 1) * chunk], group=self.pg)
+        self._masters_sharded = True
+        self._inference_copies_stale()
+
     # ------------------------------------------------------------------ public API
     def _prepare(self, text_tokens, images, image_positions):
         cfg = self.cfg
@@ -793,15 +885,29 @@ class KosmosTrainer:
         if not micro_batches:
             raise ValueError("step_accumulated needs at least one micro-batch")
         total = None
-        for i, mb in enumerate(micro_batches):
-            loss = self.loss_and_grads(*mb, accumulate=i > 0).clone()
-            total = loss if total is None else total + loss
-        self._optimize(len(micro_batches))
+        self._defer_reduce = self.shard_optimizer        # sharded optimizer: ONE exchange, of the accumulated local sums
+        try:
+            for i, mb in enumerate(micro_batches):
+                loss = self.loss_and_grads(*mb, accumulate=i > 0).clone()
+                total = loss if total is None else total + loss
+        finally:
+            self._defer_reduce = False
+        if self.shard_optimizer:
+            self._optimize_sharded(len(micro_batches))
+        else:
+            self._optimize(len(micro_batches))
         return total / len(micro_batches)
 
     def step(self, text_tokens, images, image_positions=None):
-        loss = self.loss_and_grads(text_tokens, images, image_positions)
-        self._optimize()
+        self._defer_reduce = self.shard_optimizer
+        try:
+            loss = self.loss_and_grads(text_tokens, images, image_positions)
+        finally:
+            self._defer_reduce = False
+        if self.shard_optimizer:
+            self._optimize_sharded()
+        else:
+            self._optimize()
         return loss
 
     @property

@@ -168,3 +168,114 @@ def test_two_rank_gloo_bucketed_gradient_all_reduce():
     out = mgr.dict()
     mp.spawn(_bucket_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: (True, True, 1), 1: (True, True, 1)}
+
+
+# --------------------------------------------------------------------------- sharded optimizer (ZeRO-1): host logic
+class _TorchOps:
+    """torch stand-ins for the CUDA kernels the optimizer path calls — this test is about the exchange / slicing logic of
+    KosmosTrainer._optimize_sharded (which collective moves which slice), not about the kernels (tools/dp_check.py runs the
+    real thing on NCCL)."""
+
+    @staticmethod
+    def cast_bf16(src, dst=None):
+        if dst is None:
+            return src.to(torch.bfloat16)
+        dst.copy_(src)
+        return dst
+
+    @staticmethod
+    def cast_f32(src, dst):
+        dst.copy_(src)
+        return dst
+
+    @staticmethod
+    def sumsq(g, out):
+        out += (g.double() ** 2).sum().float()
+
+    @staticmethod
+    def clip_scale(sumsq_t, max_norm, pre_scale, scale_out, norm_out=None):
+        norm = sumsq_t.sqrt() * pre_scale
+        if norm_out is not None:
+            norm_out.copy_(norm)
+        c = torch.clamp(max_norm / (norm + 1e-6), max=1.0) if max_norm > 0 else torch.ones(1)
+        scale_out.copy_(c * pre_scale)
+
+    @staticmethod
+    def adamw_step(p, g, m, v, wb, *, lr, betas, eps, weight_decay, step, grad_scale=None):
+        gi = g * (grad_scale if grad_scale is not None else 1.0)
+        p.mul_(1.0 - lr * weight_decay)
+        m.mul_(betas[0]).add_(gi, alpha=1 - betas[0])
+        v.mul_(betas[1]).addcmul_(gi, gi, value=1 - betas[1])
+        bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+        p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+        if wb is not None:
+            wb.copy_(p)
+
+
+def _sharded_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    kd.init_from_env("gloo")
+    import kosmos_oracle as ko
+    import kosmosx.train as ktrain
+    from kosmosx import Kosmos, KosmosConfig, KosmosTrainer
+    ktrain.ops = _TorchOps
+    oc = ko.OracleConfig.tiny(layers=3)
+
+    def make(shard):
+        torch.manual_seed(0)
+        model = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
+        tr = KosmosTrainer(model, layout_only=True, shard_optimizer=shard, lr=1e-2, weight_decay=0.1)
+        n = tr.n_total
+        g = torch.Generator().manual_seed(7)
+        tr.P = torch.randn(n, generator=g)
+        tr.M1, tr.M2 = torch.zeros(n), torch.zeros(n)
+        tr._W16p = torch.zeros(tr._nd_pad, dtype=torch.bfloat16)
+        tr.W16 = tr._W16p[:tr.n_decay]
+        tr.W16.copy_(tr.P[:tr.n_decay])
+        tr.scalars = torch.zeros(8)
+        return tr
+
+    a, b = make(True), make(False)
+    ok = a.shard_optimizer and a.world == world and not b.shard_optimizer
+    spans = [a.shard_range(r) for r in range(world)]
+    ok &= spans[0][0] == 0 and spans[-1][1] == a.n_decay and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    ok &= a._nd_pad % (world * 1024) == 0 and a._nd_pad >= a.n_decay
+    for step in range(3):
+        g_local = torch.randn(a.n_total, generator=torch.Generator().manual_seed(100 * step + rank)) * 0.1
+        a.G, b.G = g_local.clone(), g_local.clone()
+        a.scalars.zero_(); b.scalars.zero_()
+        a._optimize_sharded()
+        works = []
+        b._bucket_ready("tail", works)           # one bf16 all-reduce of the whole buffer, converted back to fp32
+        b._finish_reduce(works)
+        b._optimize()
+    lo, hi = a.shard_range()
+    nd = a.n_decay
+    own = all(torch.equal(getattr(a, k)[lo:hi], getattr(b, k)[lo:hi]) and torch.equal(getattr(a, k)[nd:], getattr(b, k)[nd:])
+              for k in ("P", "M1", "M2"))
+    stale = not torch.equal(a.P[:nd], b.P[:nd])                  # the other rank's slice has not been updated here
+    raised = False
+    try:
+        a.model.state_dict()                                     # (layout_only trainers register no hook: ask the guard directly)
+        a._require_whole_masters("state_dict()")
+    except RuntimeError:
+        raised = True
+    a.gather_masters()
+    whole = torch.equal(a.P, b.P) and torch.equal(a.W16, b.W16) and not a._masters_sharded
+    norm_same = torch.equal(a.scalars[4], b.scalars[4])
+    out[rank] = (bool(ok), bool(own), bool(stale), raised, bool(whole), bool(norm_same))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_optimizer_equals_the_all_reduce_step():
+    """KosmosTrainer(shard_optimizer=True): reduce-scatter of the bf16 decay-segment gradients + each rank's slice of the update +
+    all-gather of the bf16 copies gives, after gather_masters(), exactly the masters / copies of the all-reduce + replicated
+    optimizer (a sum of two values has one order), the replicated tail is updated everywhere, and state_dict() is refused
+    while the masters are sharded."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: (True,) * 6, 1: (True,) * 6}

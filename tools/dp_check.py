@@ -9,7 +9,9 @@ all-reduce overlapped with backward AND the single all-reduce after it, in fp32 
      tolerance), and the mean of the rank losses == its loss;
   2. after 3 optimizer steps the replicas are BIT-IDENTICAL (every rank compares its flat master / moment buffers with
      rank 0's) and within Adam's sign-flip bound of the single-process run;
-  3. the autograd bridge (model.train(); loss.backward(); torch.optim) leaves the MEAN gradient in param.grad.
+  3. the autograd bridge (model.train(); loss.backward(); torch.optim) leaves the MEAN gradient in param.grad;
+  4. KosmosTrainer(shard_optimizer=True) (reduce-scatter, each rank updates its slice, all-gather of the bf16 copies) reproduces
+     the all-reduce run after 3 steps — bit for bit at 2 ranks — and state_dict() refuses to run until gather_masters().
 Exit code 0 = all checks passed on every rank.
 """
 import os
@@ -94,7 +96,46 @@ def main():
             if rank == 0:
                 print(f"{tag}: grad rel {rel:.2e}, params max diff {d.max().item():.2e}, differing fraction {frac:.2e}, "
                       f"replicas {'bit-identical' if same_t.item() else 'DIFFER'} after 3 steps", flush=True)
+            if not overlap and rd == torch.bfloat16:
+                ar = {k: getattr(t2, k).clone() for k in ("P", "M1", "M2", "W16")}      # what the sharded optimizer must reproduce
             del m2, t2
+    # sharded optimizer (ZeRO-1): reduce-scatter + each rank's slice of the update + all-gather of the bf16 copies
+    m3, t3 = fresh(shard_optimizer=True)
+    for _ in range(3):
+        t3.step(tg[lo:hi], ig[lo:hi])
+    try:
+        m3.state_dict()
+        check(False, "sharded: state_dict() before gather_masters() did not raise")
+    except RuntimeError:
+        pass
+    slo, shi = t3.shard_range()
+    own = all(torch.equal(getattr(t3, k)[slo:shi], ar[k][slo:shi]) for k in ("P", "M1", "M2"))
+    nd = t3.n_decay
+    tail = all(torch.equal(getattr(t3, k)[nd:], ar[k][nd:]) for k in ("P", "M1", "M2"))
+    t3.gather_masters()
+    m3.state_dict()
+    torch.cuda.synchronize()
+    dP, dW = (t3.P - ar["P"]).abs(), (t3.W16.float() - ar["W16"].float()).abs()
+    if world == 2:          # a sum of two bf16 values has one order: the sharded step must reproduce the all-reduce step bit for bit
+        check(own and tail, "sharded: this rank's slice of P / M1 / M2 (or the replicated tail) differs from the all-reduce run")
+        check(torch.equal(t3.P, ar["P"]) and torch.equal(t3.W16, ar["W16"]), "sharded: gathered masters / bf16 copies differ from the all-reduce run")
+    else:                   # (ring order of the reduce-scatter differs from the all-reduce's)
+        check(dP.max().item() <= 3 * 2.1e-3 and dP.mean().item() <= 2e-4, f"sharded: masters {dP.max().item():.3e} / mean {dP.mean().item():.2e} from the all-reduce run")
+    same = True
+    for name, buf in (("P", t3.P), ("W16", t3.W16)):
+        ref0 = buf.clone()
+        dist.broadcast(ref0, 0)
+        same &= bool(torch.equal(ref0, buf))
+        check(torch.equal(ref0, buf), f"sharded: replica buffer {name} differs from rank 0's after gather_masters()")
+    m3.eval()
+    with torch.no_grad():
+        lg = m3(tg[lo:hi], ig[lo:hi])          # inference after training on the gathered weights
+    check(bool(torch.isfinite(lg).all()), "sharded: inference after gather_masters() is not finite")
+    if rank == 0:
+        print(f"shard_optimizer: slice {slo}..{shi} of {nd}; vs the all-reduce run: masters max diff {dP.max().item():.2e}, bf16 copies max diff "
+              f"{dW.max().item():.2e}, own slice + tail {'bit-identical' if own and tail else 'differ'}, replicas "
+              f"{'bit-identical' if same else 'DIFFER'} after gather", flush=True)
+    del m3, t3
     # autograd bridge: param.grad is the MEAN over ranks (DistributedDataParallel's convention)
     tgt = ko.KosmosOracle.loss_targets(text, oc.p_latents).cuda()
     def bridge(model, tok, img, tg_):
