@@ -134,13 +134,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023) { printf("kx attn_bwd: dynamic smem base not 1024-aligned\n"); __trap(); }
-        mbar_init(kv_full, 1);
-        for (int s = 0; s < BW_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(bar_s, 1); mbar_init(bar_dp, 1); mbar_init(bar_pds, BW_COMPUTE); mbar_init(bar_dq, 1); mbar_init(bar_dqr, 128); mbar_init(bar_fin, 1); mbar_init(bar_sfree, BW_COMPUTE);
         fence_mbar_init();
     }
     if (warp == BW_W_TMA) {
-        if (lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO); prefetch_tmap(&tmDQ); }
+        // The producer's own barriers are initialised by the producer warp, and K_j, V_j and the first query blocks are requested
+        // BEFORE the TMEM allocation and the CTA-wide barrier: a CTA lives ~20 us and every CTA pays this prologue (the per-CTA
+        // records of the trace build: 2.3 us from entry to the first ready score tile, 11 % of the kernel).
+        if (lane == 0) {
+            mbar_init(kv_full, 1);
+            for (int s = 0; s < BW_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            fence_mbar_init();
+            mbar_arrive_expect_tx(kv_full, 2 * BW_TILE);
+            tma_load_2d(&tmK, kv_full, smem + BW_SMEM_K, head * 64, row_base + j * 128, kEvictFirst);
+            tma_load_2d(&tmV, kv_full, smem + BW_SMEM_V, head * 64, row_base + j * 128, kEvictFirst);
+            for (int it = 0; it < BW_SLOTS && it < n_it; ++it) {
+                const int i = i0 + it;
+                mbar_arrive_expect_tx(&full[it], 2 * BW_TILE + 1024);
+                tma_load_2d(&tmQ, &full[it], smem + BW_SMEM_Q + it * BW_TILE, head * 64, row_base + i * 128, kEvictLast);
+                tma_load_2d(&tmDO, &full[it], smem + BW_SMEM_DO + it * BW_TILE, head * 64, row_base + i * 128, kEvictLast);
+                bulk_load_1d(s_ld + it * 64, p.nld + vec_base + i * 128, 1024, &full[it]);
+            }
+            prefetch_tmap(&tmDQ);
+        }
+        __syncwarp();
         tmem_alloc<1>(tmem_slot, BW_TMEM_COLS);
         tmem_relinquish<1>();
     }
@@ -188,11 +205,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     } else if (warp >= BW_W_TMA) {
         if (warp == BW_W_TMA) {
             if (elect_one()) {
-                // ================= TMA producer =================
-                mbar_arrive_expect_tx(kv_full, 2 * BW_TILE);
-                tma_load_2d(&tmK, kv_full, smem + BW_SMEM_K, head * 64, row_base + j * 128, kEvictFirst);
-                tma_load_2d(&tmV, kv_full, smem + BW_SMEM_V, head * 64, row_base + j * 128, kEvictFirst);
-                for (int it = 0; it < n_it; ++it) {
+                // ================= TMA producer (K_j, V_j and the first BW_SLOTS query blocks were requested in the prologue) =================
+                for (int it = BW_SLOTS; it < n_it; ++it) {
                     const int i = i0 + it, s = it % BW_SLOTS;
                     mbar_wait_lean(&empty[s], ((it / BW_SLOTS) & 1) ^ 1);
                     mbar_arrive_expect_tx(&full[s], 2 * BW_TILE + 1024);
