@@ -217,7 +217,8 @@ def case_train_elementwise():
         ops.layernorm_bwd(x, dy, gamma, dx if xdt != torch.float32 else dx.clone(), dg, db, part, act=act, accumulate=True)
         ok &= report(f"ln_bwd dgamma accumulate {rows}x{n}", dg, 2 * gr.grad, 6e-3)
     # ---- LN(gelu(u)) forward
-    for (rows, n) in ((700, 8192), (333, 256)):
+    # (wide rows run the two-rows-in-flight kernel: more rows than SMs, fewer, one, a partly / entirely dead second column chunk)
+    for (rows, n) in ((700, 8192), (333, 256), (100, 8192), (1, 8192), (1500, 8192), (450, 6144), (333, 4096), (200, 2056), (150, 2048)):
         u = torch.randn(rows, n, device=dev).bfloat16()
         gamma, beta = torch.rand(n, device=dev) + 0.5, torch.randn(n, device=dev)
         out = torch.zeros(rows, n, device=dev, dtype=torch.bfloat16)
