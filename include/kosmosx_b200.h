@@ -273,8 +273,8 @@ int kx_im2col_patches_f32(const float* pixels, int batch, int media, int image, 
  * kx_attn_fwd; dq/dk/dv are column blocks sharing ld_dqkv.  When the four xPos tables (kx_xpos_tables) are given,
  * dq and dk are returned as gradients of the UN-rotated projections (the transpose of the KX_EPI_QKV_XPOS rotation is
  * applied on the way out); NULL tables = plain attention.  Scratch: dq_accum fp32 [batch*seq_len, heads*64] (zeroed
- * by the call) and delta fp32 (TWICE the size of lse: (-lse, -rowsum(dO*O)) pairs).  Three kernels: delta = rowsum(dO*O), the main kernel (one CTA
- * per (batch, head, 128-key block)), and the dq/dk finish.  Replaces autograd through bmm / softmax / bmm and
+ * by the call) and delta fp32 (TWICE the size of lse: (-lse, -rowsum(dO*O)) pairs).  Three kernels: delta = rowsum(dO*O) (which also
+ * zeroes dq_accum), the main kernel (one CTA per (batch, head, 128-key block); dk leaves it rotated), and the dq finish.  Replaces autograd through bmm / softmax / bmm and
  * XPOS.forward of torchscale MultiheadAttention. */
 int kx_attn_fwd_lse(const void* q, const void* k, const void* v, long long ld_qkv, void* out, long long ld_out, int batch,
                     int heads, int seq_len, int causal, float scale, float* stats_out, float* lse_out, kx_stream_t stream);
@@ -326,7 +326,8 @@ int kx_act_layernorm_fwd(const void* x_bf16, long long ld_x, int act, const floa
  * Linear whose output was added to the stream there.  dx_is_f32 = 0: dx is bf16 (dres/dxb must be NULL), d_colsum sums
  * the stored bf16 values.  partials: fp32 scratch [3][kx_ln_bwd_partials(rows)][n].  accumulate = 1 adds into d_*.
  * pre_add (NULL or fp32 [n], n <= 2048, act none): the LayerNorm input is x + pre_add (the perceiver's
- * `x + media_pos_emb[i]`; d_colsum is then the gradient of that table row when dres is NULL). */
+ * `x + media_pos_emb[i]`; d_colsum is then the gradient of that table row when dres is NULL).
+ * The GELU form on wide rows (2048 < n <= 8192: the decoder's ffn_layernorm) runs its own kernel, two rows in flight per CTA. */
 int kx_ln_bwd_partials(int rows);
 int kx_layernorm_bwd(const void* x, int x_is_bf16, long long ld_x, const float* pre_add, int act, const void* dy_bf16, long long ld_dy,
                      const float* gamma, float eps, const float* dres, long long ld_dres, void* dx, int dx_is_f32,
