@@ -279,3 +279,28 @@ def test_two_rank_gloo_sharded_optimizer_equals_the_all_reduce_step():
     out = mgr.dict()
     mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: (True,) * 6, 1: (True,) * 6}
+
+
+def test_sharded_optimizer_plan_and_argument_checks():
+    """shard_range() cuts the padded decay segment into `world` equal, 1024-aligned chunks that tile it; a single rank or
+    layout without torch.distributed keeps the replicated optimizer; the options that cannot be combined are refused."""
+    _, tr = _tiny_trainer_layout()
+    assert not tr.shard_optimizer and tr._nd_pad == tr.n_decay            # world == 1: nothing to shard
+    import kosmos_oracle as ko
+    from kosmosx import Kosmos, KosmosConfig, KosmosTrainer
+    oc = ko.OracleConfig.tiny(layers=3)
+    model = Kosmos(config=KosmosConfig(**{k: getattr(oc, k) for k in KosmosConfig.__dataclass_fields__}))
+    one = KosmosTrainer(model, layout_only=True, shard_optimizer=True)
+    assert not one.shard_optimizer                                        # asked for, but this process trains alone
+    for world in (2, 3, 8, 64):
+        tr.world, tr.shard_optimizer = world, True
+        tr._nd_pad = (tr.n_decay + world * 1024 - 1) // (world * 1024) * (world * 1024)
+        spans = [tr.shard_range(r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == tr.n_decay
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        chunk = tr._nd_pad // world
+        assert chunk % 1024 == 0 and all(lo % 1024 == 0 or lo == tr.n_decay for lo, _ in spans)
+        assert all(hi - lo == chunk for lo, hi in spans if hi < tr.n_decay)   # only the last non-empty slice may be short
+    tr._masters_sharded = True
+    with pytest.raises(RuntimeError, match="gather_masters"):
+        tr._require_whole_masters("state_dict()")
