@@ -357,7 +357,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         float x0, x1;
                         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), sl2x2, pack_f32x2(l.x, l.y)), x0, x1);
                         float e0, e1;
-                        if (c == 1 || c == 4 || c == 6) {             // 3 of 8 pairs on the FMA pipes: the loop is MUFU-bound otherwise
+                        // 3 of 8 pairs on the FMA pipes (the loop is MUFU-bound otherwise); none with dropout, whose mask logic already
+                        // loads the FMA / ALU pipes (A/B on one box: 721 us with {1, 4, 6}, 703 us with two pairs, 683 us with none;
+                        // without dropout 614 us either way)
+                        if (!DROP && (c == 1 || c == 4 || c == 6)) {
                             exp2_poly_x2(x0, x1, e0, e1);
                         } else {
                             e0 = ex2_approx(x0);

@@ -89,7 +89,7 @@ __device__ __forceinline__ PPItem pp_item(const AttnPPParams& p, int item) {
     return it;
 }
 
-// POLY: 26 of every 64 element pairs take exp2 through exp2_poly_x2 (FMA pipes) instead of MUFU.EX2 —
+// POLY: 26 of every 64 element pairs (13 in the dropout build) take exp2 through exp2_poly_x2 (FMA pipes) instead of MUFU.EX2 —
 // the split that balances the two pipes for this loop (FA4's trick).
 template <bool CAUSAL, bool POLY, bool TRACE = false, bool DROP = false>
 __global__ void __launch_bounds__(PP_THREADS, 1)
@@ -365,7 +365,9 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint64_t x = ffma2(pack_f32x2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sl2x2, nm2);
                 float x0, x1, e0, e1;
                 unpack_f32x2(x, x0, x1);
-                if (POLY && ((i % 5) == 1 || (i % 5) == 3)) {
+                // 26 of 64 pairs through the polynomial; 13 with dropout, whose masking adds ALU / FMA-pipe work of its own (A/B on
+                // one box, forward + lse + dropout at C3: 278 us with 26, 261 us with 13, 275 us with none)
+                if (POLY && ((i % 5) == 1 || (!DROP && (i % 5) == 3))) {
                     exp2_poly_x2(x0, x1, e0, e1);
                 } else {
                     e0 = ex2_approx(x0);
